@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""Benchmark of the voxelised multi-view pose path (BASELINE.json metric: frames/s).
+
+  python bench.py --gpus N --steps K --warmup W            # this backend (one JSON line on rank 0)
+  python bench.py --impl reference --gpus N --steps K ...  # the CPU oracle port of the reference path
+
+Workload (BASELINE.json configs[2], the largest single-GPU configuration): per GPU a batch of
+B = 8 synthetic frames, each 5 views of 3x384x288, PoseResNet-50 -> 80x80x20 root grid ->
+10 proposals per frame (all forced valid) -> 64^3 person cubes -> V2VNet -> soft-argmax.
+A "step" is one forward of that batch; `value` = frames/s with the images already resident in
+HBM; `e2e` = the same through the public module call with the images in pinned host memory
+(H2D inside the timed region) and the predictions read back (D2H).  With N > 1 each rank runs
+its own batch (frames are independent units: weak scaling, no data-path collective).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BATCH = 8
+VIEWS = 5
+PROPOSALS = 10
+IMAGE_SIZE = [288, 384]      # [w, h]
+HEATMAP_SIZE = [72, 96]
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def make_cfg(batch):
+    from selfpose3d_b200.config import default_config
+    cfg = default_config()
+    cfg.NETWORK.IMAGE_SIZE, cfg.NETWORK.HEATMAP_SIZE = list(IMAGE_SIZE), list(HEATMAP_SIZE)
+    cfg.MULTI_PERSON.MAX_PEOPLE_NUM = PROPOSALS
+    cfg.MULTI_PERSON.THRESHOLD = -1e9       # untrained-like nets score low: force every proposal slot valid
+    cfg.TEST.BATCH_SIZE = batch
+    return cfg
+
+
+def oracle_cfg(cfg):
+    return dict(image_size=cfg.NETWORK.IMAGE_SIZE, heatmap_size=cfg.NETWORK.HEATMAP_SIZE,
+                space_size=cfg.MULTI_PERSON.SPACE_SIZE, space_center=cfg.MULTI_PERSON.SPACE_CENTER,
+                initial_cube_size=cfg.MULTI_PERSON.INITIAL_CUBE_SIZE, grid_size=cfg.PICT_STRUCT.GRID_SIZE,
+                cube_size=cfg.PICT_STRUCT.CUBE_SIZE, max_people=cfg.MULTI_PERSON.MAX_PEOPLE_NUM,
+                threshold=cfg.MULTI_PERSON.THRESHOLD, beta=cfg.NETWORK.BETA, root_idx=cfg.DATASET.ROOTIDX)
+
+
+def cpu_reference_frames_per_s(steps, warmup, frames_per_step=1):
+    """Times the CPU oracle port of the reference path (oracle/pipeline.py: torch CPU convs,
+    grid_sample, ... exactly the calls the reference makes) on `frames_per_step` frames per step."""
+    from selfpose3d_b200 import synthetic
+    from selfpose3d_b200.models import multi_person_posenet_ssv
+    from oracle import pipeline
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = make_cfg(frames_per_step)
+    model = multi_person_posenet_ssv.get_multi_person_pose_net(cfg, is_train=False)
+    sd = synthetic.trained_like_state_dict(model, seed=0)
+    cams = synthetic.ring_cameras(VIEWS, seed=0)
+    meta = synthetic.make_meta(cams, frames_per_step, IMAGE_SIZE)
+    images = synthetic.random_images(frames_per_step, VIEWS, IMAGE_SIZE, seed=0)
+    cam_arrays = {k: np.stack([m["camera"][k].numpy() for m in meta]) for k in meta[0]["camera"]}
+    args = (sd, oracle_cfg(cfg), cam_arrays, [m["center"].numpy() for m in meta],
+            [m["scale"].numpy() for m in meta], [m["rotation"].numpy() for m in meta])
+    with torch.no_grad():
+        for _ in range(warmup):
+            pipeline.inference(*args, images=images)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pipeline.inference(*args, images=images)
+        dt = time.perf_counter() - t0
+    return frames_per_step * steps / dt, dt / steps
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1] or [r for (_, r) in self.rows]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    fps, spf = cpu_reference_frames_per_s(args.steps, args.warmup, 1)
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": spf * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(1),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": "1 frame per step (5 views 3x384x288, 10 proposals), oracle/pipeline.py on torch CPU "
+                                   "with %d threads" % torch.get_num_threads()},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(batch):
+    return {"workload": "BASELINE configs[2]: 5-view 3x384x288 synthetic frames, batch=%d per GPU, PoseResNet-50 + "
+                        "RootNet (80x80x20) + PoseNet (10 proposals x 64^3), all proposals valid" % batch,
+            "batch_per_gpu": batch, "views": VIEWS, "proposals": PROPOSALS, "image": "3x384x288",
+            "root_grid": "80x80x20", "person_cube": "64x64x64",
+            "cache": "per-step working set (several GB of activations) exceeds the 126 MB L2; no explicit flush",
+            "parallelism": "independent frames per rank, no data-path collective"}
+
+
+def run_ours(args, rank, world, local_rank):
+    from selfpose3d_b200 import synthetic, _lib, ops
+    from selfpose3d_b200.models import multi_person_posenet_ssv
+    import selfpose3d_b200.profiler as prof
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.load()
+    cfg = make_cfg(BATCH)
+    model = multi_person_posenet_ssv.get_multi_person_pose_net(cfg, is_train=False)
+    model.load_state_dict(synthetic.trained_like_state_dict(model, seed=0), strict=True)
+    model = model.to(dev).eval()
+    cams = synthetic.ring_cameras(VIEWS, seed=0)
+    meta = synthetic.make_meta(cams, BATCH, IMAGE_SIZE)
+    host_images = [im.pin_memory() for im in synthetic.random_images(BATCH, VIEWS, IMAGE_SIZE, seed=rank)]
+    dev_images = [im.to(dev) for im in host_images]
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return model(views1=dev_images, meta1=meta, inference=True)[0]
+
+    def step_e2e():
+        views = [im.to(dev, non_blocking=True) for im in host_images]
+        pred = model(views1=views, meta1=meta, inference=True)[0]
+        return pred.cpu()
+
+    def timed(fn, steps, profile=False):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count
+        t0 = time.perf_counter()
+        e0.record()
+        if profile:
+            prof.enable()
+        for _ in range(steps):
+            fn()
+        if profile:
+            prof.disable()
+        e1.record()
+        barrier()
+        t1 = time.perf_counter()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, _lib.launch_count - l0, t0, t1
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms, launches, t0, t1 = timed(step_resident, args.steps, profile=True)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    kernels = prof.summary()
+    step_e2e()
+    ms_e2e, _, _, _ = timed(step_e2e, args.steps)
+
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    frames = BATCH * world * args.steps
+    value = frames / (ms * 1e-3)
+    e2e_value = frames / (ms_e2e * 1e-3)
+    h2d = sum(int(im.numel()) * 4 for im in host_images)
+    d2h = BATCH * PROPOSALS * cfg.NETWORK.NUM_JOINTS * 5 * 4
+
+    # dominant kernel family: the convolutions (tensor roofline); the un-projection is reported beside it (HBM)
+    conv = kernels.get("conv", {"ms": 0.0, "work": 0.0, "launches": 0})
+    unp = kernels.get("unproject", {"ms": 0.0, "work": 0.0, "launches": 0})
+    conv_tflops = conv["work"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
+    unp_gbs = unp["work"] / (unp["ms"] * 1e-3) / 1e9 if unp["ms"] > 0 else 0.0
+    roofline = {"kernel": "sp3d_conv_fwd (implicit-GEMM convolution family, all launches of the step)",
+                "bound": "tensor", "achieved": conv_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": conv_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
+                "peak_source": peaks["source"] + " (sustained bf16: kernels timed inside a long step)",
+                "launches_per_step": conv["launches"] / max(args.steps, 1),
+                "share_of_step": conv["ms"] / ms if ms > 0 else None}
+    roofline_unproject = {"kernel": "sp3d_unproject_fwd (person cubes + root grid)", "bound": "hbm",
+                          "achieved": unp_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                          "frac": unp_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                          "launches_per_step": unp["launches"] / max(args.steps, 1),
+                          "share_of_step": unp["ms"] / ms if ms > 0 else None}
+
+    cpu_fps, cpu_spf = cpu_reference_frames_per_s(1, 0, 1) if not args.no_cpu_baseline else (None, None)
+    line = {
+        "metric": "frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(BATCH),
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "roofline_unproject": roofline_unproject,
+        "kernel_ms_per_step": {k: v["ms"] / max(args.steps, 1) for k, v in kernels.items()},
+        "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": "1 frame (5 views 3x384x288, 10 proposals) through oracle/pipeline.py on torch CPU, "
+                                   "no warm-up, %s s" % (None if cpu_spf is None else round(cpu_spf, 2))},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

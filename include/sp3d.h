@@ -1,0 +1,192 @@
+/*
+ * libsp3d -- C ABI of the B200 (sm_100a) kernels behind the SelfPose3d / VoxelPose
+ * voxelised multi-view pose path.
+ *
+ * The reference (CAMMA-public/SelfPose3d) has no FFI layer: its replaceable seam is the
+ * Python nn.Module API.  Each entry point below replaces the ATen /
+ * cuDNN call sequence of one reference function; the citation says which.
+ *
+ * Conventions (all entry points):
+ *   - plain C, POD argument structs, raw DEVICE pointers, explicit sizes and strides;
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it, performs no
+ *     host synchronisation, allocates and frees nothing (scratch comes from the caller);
+ *   - returns 0 (SP3D_OK) or a negative sp3d_status; never throws; re-entrant (no global state);
+ *   - float tensors are IEEE fp32 unless a dtype field says otherwise;
+ *   - "channel-last" means [.., spatial.., C_pitch] with the channel index fastest.
+ */
+#ifndef SP3D_H
+#define SP3D_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SP3D_ABI_VERSION 1
+#define SP3D_MAX_VIEWS 8
+#define SP3D_CAM_FLOATS 32
+
+typedef enum {
+  SP3D_OK = 0,
+  SP3D_ERR_INVALID_ARG = -1,
+  SP3D_ERR_UNSUPPORTED = -2,
+  SP3D_ERR_LAUNCH = -3,
+  SP3D_ERR_WORKSPACE = -4
+} sp3d_status;
+
+typedef enum { SP3D_F32 = 0, SP3D_BF16 = 1 } sp3d_dtype;
+
+/* ABI version of the loaded library and a static description of an error code. */
+int sp3d_abi_version(void);
+const char* sp3d_strerror(int status);
+/* Last CUDA error string recorded by a failed launch on the calling thread ("" if none). */
+const char* sp3d_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Packed camera record, one per (sample, view): SP3D_CAM_FLOATS fp32 values
+ *   [0..8] R row-major   [9..11] T (camera centre, world mm)   [12,13] fx fy   [14,15] cx cy
+ *   [16..18] k1 k2 k3    [19,20] p1 p2    [21..26] 2x3 affine original-image -> network input
+ *   [27] width = 2*center_x   [28] height = 2*center_y   [29] flip (0/1)   [30,31] reserved
+ * Replaces the per-(sample, view) host work of lib/models/project_layer.py:64-75 and
+ * lib/utils/cameras.py:13-24 (unfold_camera_param).
+ * ------------------------------------------------------------------------------------------ */
+
+/* Fused multi-view un-projection: per voxel back-projection into every view, bilinear sample
+ * of all channels, masked mean over views, clamp to [0,1].
+ * Replaces ProjectLayer.get_voxel / forward, lib/models/project_layer.py:42-106, together with
+ * compute_grid (:22-40), cameras.project_pose (lib/utils/cameras.py:27-55,111-113) and
+ * affine_transform_pts_cuda (lib/utils/transforms.py:119-123). */
+typedef struct {
+  const float* heatmaps[SP3D_MAX_VIEWS]; /* per view: [B, C, h, w] addressed through the strides below */
+  int64_t hm_stride_b, hm_stride_c, hm_stride_h, hm_stride_w; /* in elements */
+  const float* cams;        /* [B, V, SP3D_CAM_FLOATS] */
+  const float* centers;     /* [n_cubes, center_stride]: x, y, z, flag(, score) */
+  int center_stride;        /* floats between consecutive cube centres (>= 3) */
+  int check_flag;           /* 1: cubes with centers[.][3] < 0 are skipped and written as zeros */
+  int cubes_per_sample;     /* sample of cube q is q / cubes_per_sample ... */
+  const int32_t* cube_sample; /* ... unless this optional [n_cubes] table gives it (compacted proposals) */
+  const float* lin_x;       /* [X] torch.linspace(-size/2, size/2, X) values (no centre) */
+  const float* lin_y;       /* [Y] */
+  const float* lin_z;       /* [Z] */
+  int B, V, C, h, w;
+  int n_cubes, X, Y, Z;
+  float img_w, img_h;       /* cfg.NETWORK.IMAGE_SIZE */
+  int view_begin, view_end; /* views summed by this call (multi-GPU view sharding); 0, V for all */
+  int partial;              /* 0: write clamp(num/(den+1e-6),0,1); 1: write raw numerators and the
+                               view count as channel C (all-reduce, then sp3d_unproject_finalize) */
+  void* cubes;              /* output, dtype out_dtype */
+  int out_dtype;            /* sp3d_dtype */
+  int64_t out_stride_cube, out_stride_c, out_stride_vox; /* in elements; voxel = (ix*Y+iy)*Z+iz */
+  int out_c_pad;            /* channels [C, out_c_pad) are written as zeros (channel-last padding); 0 = none */
+  float* grids;             /* optional [n_cubes, X*Y*Z, 3] voxel-centre coordinates, or NULL */
+} sp3d_unproject_args;
+int sp3d_unproject_fwd(const sp3d_unproject_args* a, void* stream);
+
+/* Divide / NaN / clamp step of the un-projection after partial sums were all-reduced:
+ * buf is [n, (C+1), N] channel-first or [n, N, pitch] channel-last partial output. */
+typedef struct {
+  float* buf;
+  int64_t n_cubes, C, N;
+  int64_t stride_cube, stride_c, stride_vox;
+} sp3d_unproject_finalize_args;
+int sp3d_unproject_finalize(const sp3d_unproject_finalize_args* a, void* stream);
+
+/* 3-D NMS (3x3x3 local maxima, non-maxima zeroed) + top-K + index -> world location + flag.
+ * Replaces core.proposal.nms/max_pool/get_index (lib/core/proposal.py:18-48) and
+ * ProposalLayer[Soft].forward/get_real_loc (lib/models/cuboid_proposal_net_soft.py:46-68,
+ * lib/models/cuboid_proposal_net.py:42-83, no-GT branch).
+ * Tie policy: highest value, then lowest flat index. */
+typedef struct {
+  const float* root_cubes;  /* [B, X, Y, Z] contiguous */
+  int B, X, Y, Z, K;        /* K <= 32 */
+  float threshold;
+  double space_size[3], space_center[3];
+  int loc_f64;              /* 1: evaluate get_real_loc in float64 after the float32 idx/(n-1)
+                               (config values were float64 numpy arrays), 0: all float32 (YAML lists) */
+  float* grid_centers;      /* [B, K, 5]: x, y, z, flag = (score > threshold) - 1, score */
+  int32_t* topk_index;      /* optional [B, K] flat voxel index, or NULL */
+} sp3d_nms_topk_args;
+int sp3d_nms_topk3d(const sp3d_nms_topk_args* a, void* stream);
+
+/* Soft-argmax over a voxel cube: sum_v softmax(beta * x)_v * grid_v, one (x,y,z) per channel.
+ * Replaces SoftArgmaxLayer.forward, lib/models/pose_regression_net.py:19-28.  The voxel
+ * coordinates are rebuilt from lin_* + centre (bit-identical to ProjectLayer's `grids`). */
+typedef struct {
+  const void* x;            /* [n_cubes, C, N] through strides, dtype x_dtype */
+  int x_dtype;
+  int64_t stride_cube, stride_c, stride_vox;
+  int n_cubes, C, X, Y, Z;
+  const float* centers;     /* [n_cubes, center_stride] */
+  int center_stride;
+  int check_flag;           /* 1: cubes with centers[.][3] < 0 produce zeros */
+  const float* lin_x; const float* lin_y; const float* lin_z;
+  float beta;
+  float* out;               /* [n_cubes, C, 3] */
+  float* workspace;         /* sp3d_softargmax3d_workspace() bytes */
+  int64_t workspace_bytes;
+} sp3d_softargmax_args;
+int64_t sp3d_softargmax3d_workspace(const sp3d_softargmax_args* a);
+int sp3d_softargmax3d_fwd(const sp3d_softargmax_args* a, void* stream);
+
+/* Convolution family on channel-last activations, evaluated as an implicit GEMM
+ *   out[n, o*ostride+ooffset, co] = act( scale[co] * sum_{t,ci} in[n, o*stride + tap_off0 + t*tap_step, ci]
+ *                                        * weight[t, ci, co] + shift[co] (+ residual) )
+ * with zero padding outside the input.  2-D tensors use D = 1.  One call covers a regular
+ * convolution; a transposed convolution with kernel = m*stride is stride^d calls (one per output
+ * phase) with ostride = stride, ooffset = phase.
+ * Replaces cudnn conv3d/conv_transpose3d + batch_norm + relu (+ residual add) of
+ * lib/models/v2v_net.py:10-69,124 and conv2d/conv_transpose2d + batch_norm + relu of
+ * lib/models/pose_resnet.py:58-93,102-124,161-207 (evaluation-mode BatchNorm folded into
+ * scale/shift by the caller). */
+typedef enum { SP3D_CONV_SIMT_F32 = 0, SP3D_CONV_TC_BF16 = 1, SP3D_CONV_TC_TF32X3 = 2 } sp3d_conv_algo;
+typedef struct {
+  const void* in;           /* [N, D, H, W, cin_pitch] */
+  const void* weight;       /* [ntaps, cin, cout_pitch_w] packed, taps ordered (kd, kh, kw) */
+  const float* scale;       /* [cout] or NULL (=1) */
+  const float* shift;       /* [cout] or NULL (=0) */
+  const void* residual;     /* same addressing as out, or NULL */
+  void* out;                /* [N, TD, TH, TW, cout_pitch] */
+  int N, D, H, W, cin, cin_pitch;
+  int OD, OH, OW;           /* virtual output grid of this call */
+  int TD, TH, TW;           /* full output tensor extent */
+  int cout, cout_pitch;     /* channels computed per position, and the distance between positions;
+                               padding channels [cout, cout_pitch) are written as zeros */
+  int cout_pitch_w;         /* row length of the packed weight (>= cout, multiple of 4) */
+  int ksize[3];             /* taps per axis */
+  int stride[3];
+  int tap_off0[3], tap_step[3];
+  int ostride[3], ooffset[3];
+  int relu;                 /* 0: none; 1: ReLU after the residual add; 2: ReLU before the residual add */
+  int algo;                 /* sp3d_conv_algo */
+  int in_dtype, out_dtype;  /* sp3d_dtype (SIMT path: F32 only) */
+} sp3d_conv_args;
+int sp3d_conv_fwd(const sp3d_conv_args* a, void* stream);
+
+/* Max pooling on channel-last activations (window k, stride s, padding p per axis; -inf padding).
+ * Replaces F.max_pool3d(k2,s2) (lib/models/v2v_net.py:54) and nn.MaxPool2d(3,2,1)
+ * (lib/models/pose_resnet.py:105). */
+typedef struct {
+  const void* in; void* out;
+  int N, D, H, W, C, c_pitch;
+  int OD, OH, OW;
+  int k[3], s[3], p[3];
+  int dtype;
+} sp3d_maxpool_args;
+int sp3d_maxpool_fwd(const sp3d_maxpool_args* a, void* stream);
+
+/* Layout change between the reference's channel-first tensors [N, C, S] and channel-last
+ * [N, S, c_pitch] (S = product of spatial extents); padding channels are written as zeros. */
+typedef struct {
+  const void* src; void* dst;
+  int64_t N, C, S;
+  int64_t c_pitch;
+  int to_channel_last;      /* 1: [N,C,S] -> [N,S,c_pitch]; 0: reverse */
+  int src_dtype, dst_dtype;
+} sp3d_layout_args;
+int sp3d_layout_convert(const sp3d_layout_args* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SP3D_H */

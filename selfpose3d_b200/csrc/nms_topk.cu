@@ -1,0 +1,134 @@
+// K3 -- 3-D non-maximum suppression + top-K proposals + index -> world location.
+//
+// One CTA per sample.  Pass 1: every thread walks its voxels in ascending flat index, evaluates
+// v' = (x == max over the 3x3x3 neighbourhood) ? x : 0 (the reference zeroes non-maxima rather
+// than removing them) and keeps its K best (value desc, index asc) in shared memory.  Pass 2: K
+// rounds of a block-wide arg-max over the list heads.  Tie policy: highest value, lowest index.
+//
+// Reference semantics: lib/core/proposal.py:18-48, lib/models/cuboid_proposal_net_soft.py:46-68.
+#include "sp3d_common.cuh"
+#include <math.h>
+
+namespace sp3d {
+
+constexpr int kNmsThreads = 256;
+constexpr int kNmsMaxK = 32;
+
+__device__ __forceinline__ bool better(float va, int ia, float vb, int ib) {
+  return va > vb || (va == vb && ia < ib);
+}
+
+__global__ void __launch_bounds__(kNmsThreads) nms_topk_kernel(const sp3d_nms_topk_args a) {
+  extern __shared__ unsigned char smem_raw[];
+  // per-thread candidate lists, interleaved so that slot s of thread t is at [s * kNmsThreads + t]
+  float* cand_v = reinterpret_cast<float*>(smem_raw);
+  int* cand_i = reinterpret_cast<int*>(cand_v + a.K * kNmsThreads);
+  __shared__ float red_v[kNmsThreads / 32];
+  __shared__ int red_i[kNmsThreads / 32];
+  __shared__ int red_t[kNmsThreads / 32];
+  __shared__ int win_t;
+
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int K = a.K;
+  const int X = a.X, Y = a.Y, Z = a.Z;
+  const int N = X * Y * Z;
+  const float* x = a.root_cubes + (int64_t)b * N;
+  const float ninf = -INFINITY;
+
+  for (int s = 0; s < K; ++s) {
+    cand_v[s * kNmsThreads + tid] = ninf;
+    cand_i[s * kNmsThreads + tid] = 0x7fffffff;
+  }
+  for (int n = tid; n < N; n += kNmsThreads) {
+    const int iz = n % Z, iy = (n / Z) % Y, ix = n / (Z * Y);
+    const float c = x[n];
+    float mx = ninf;
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int xx = ix + dx;
+      if (xx < 0 || xx >= X) continue;
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int yy = iy + dy;
+        if (yy < 0 || yy >= Y) continue;
+        for (int dz = -1; dz <= 1; ++dz) {
+          const int zz = iz + dz;
+          if (zz < 0 || zz >= Z) continue;
+          mx = fmaxf(mx, x[(xx * Y + yy) * Z + zz]);
+        }
+      }
+    }
+    const float v = (c == mx) ? c : 0.0f;
+    // insertion into this thread's sorted list; indices arrive ascending, so strict '>' keeps ties ordered
+    if (v > cand_v[(K - 1) * kNmsThreads + tid]) {
+      int s = K - 1;
+      while (s > 0 && v > cand_v[(s - 1) * kNmsThreads + tid]) {
+        cand_v[s * kNmsThreads + tid] = cand_v[(s - 1) * kNmsThreads + tid];
+        cand_i[s * kNmsThreads + tid] = cand_i[(s - 1) * kNmsThreads + tid];
+        --s;
+      }
+      cand_v[s * kNmsThreads + tid] = v;
+      cand_i[s * kNmsThreads + tid] = n;
+    }
+  }
+  __syncthreads();
+
+  int head = 0;  // this thread's next unconsumed candidate
+  for (int k = 0; k < K; ++k) {
+    float v = head < K ? cand_v[head * kNmsThreads + tid] : ninf;
+    int i = head < K ? cand_i[head * kNmsThreads + tid] : 0x7fffffff;
+    int t = tid;
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ov = __shfl_down_sync(0xffffffffu, v, off);
+      const int oi = __shfl_down_sync(0xffffffffu, i, off);
+      const int ot = __shfl_down_sync(0xffffffffu, t, off);
+      if (better(ov, oi, v, i)) { v = ov; i = oi; t = ot; }
+    }
+    if ((tid & 31) == 0) { red_v[tid >> 5] = v; red_i[tid >> 5] = i; red_t[tid >> 5] = t; }
+    __syncthreads();
+    if (tid == 0) {
+      float bv = red_v[0]; int bi = red_i[0]; int bt = red_t[0];
+      for (int w = 1; w < kNmsThreads / 32; ++w)
+        if (better(red_v[w], red_i[w], bv, bi)) { bv = red_v[w]; bi = red_i[w]; bt = red_t[w]; }
+      win_t = bt;
+      const int iz = bi % Z, iy = (bi / Z) % Y, ix = bi / (Z * Y);
+      const int idx[3] = {ix, iy, iz};
+      const int dims[3] = {X, Y, Z};
+      float* gc = a.grid_centers + ((int64_t)b * K + k) * 5;
+      for (int d = 0; d < 3; ++d) {
+        const float q = __fdiv_rn((float)idx[d], __fsub_rn((float)dims[d], 1.0f));
+        float loc;
+        if (a.loc_f64) {
+          const double s = a.space_size[d];
+          loc = (float)(__dsub_rn(__dadd_rn(__dmul_rn((double)q, s), a.space_center[d]), s / 2.0));
+        } else {
+          const float s = (float)a.space_size[d];
+          loc = __fsub_rn(__fadd_rn(__fmul_rn(q, s), (float)a.space_center[d]), __fdiv_rn(s, 2.0f));
+        }
+        gc[d] = loc;
+      }
+      gc[3] = (bv > a.threshold) ? 0.0f : -1.0f;
+      gc[4] = bv;
+      if (a.topk_index != nullptr) a.topk_index[(int64_t)b * K + k] = bi;
+    }
+    __syncthreads();
+    if (tid == win_t) ++head;
+  }
+}
+
+}  // namespace sp3d
+
+extern "C" int sp3d_nms_topk3d(const sp3d_nms_topk_args* a, void* stream) {
+  using namespace sp3d;
+  if (a == nullptr || a->root_cubes == nullptr || a->grid_centers == nullptr || a->K < 1 || a->K > kNmsMaxK ||
+      a->B < 0 || a->X < 1 || a->Y < 1 || a->Z < 1)
+    return SP3D_ERR_INVALID_ARG;
+  if ((int64_t)a->X * a->Y * a->Z < a->K) return SP3D_ERR_INVALID_ARG;  // torch.topk would raise
+  if (a->B == 0) return SP3D_OK;
+  const size_t smem = (size_t)a->K * kNmsThreads * (sizeof(float) + sizeof(int));
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(nms_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_last_error(e); return SP3D_ERR_LAUNCH; }
+  }
+  nms_topk_kernel<<<a->B, kNmsThreads, smem, static_cast<cudaStream_t>(stream)>>>(*a);
+  return check_launch();
+}

@@ -1,0 +1,204 @@
+// K4 -- soft-argmax over a voxel cube (online softmax, single pass over the cube).
+//
+// grid = (splits, n_cubes).  Each CTA streams a contiguous voxel range of one cube; a thread owns
+// one voxel per step and keeps, per channel, the running (max, sum e, sum e*(g - centre)) of the
+// online softmax in registers; warps and CTAs merge those states in float64; a second tiny kernel
+// merges the splits and adds the centre back.  Voxel coordinates g are rebuilt as
+// fl(lin + centre), i.e. exactly the `grids` tensor of ProjectLayer, and accumulated relative to
+// the cube centre to keep magnitudes (and float32 rounding) small.
+//
+// Reference semantics: SoftArgmaxLayer.forward, lib/models/pose_regression_net.py:19-28.
+#include "sp3d_common.cuh"
+#include <math.h>
+
+namespace sp3d {
+
+constexpr int kSaThreads = 256;
+constexpr int kSaGroup = 16;
+constexpr int kSaState = 5;  // m, s, wx, wy, wz (float64 in the workspace)
+
+struct SaState {
+  double m, s, wx, wy, wz;
+};
+
+__device__ __forceinline__ SaState sa_merge(const SaState& a, const SaState& b) {
+  if (b.s == 0.0) return a;
+  if (a.s == 0.0) return b;
+  const double M = a.m > b.m ? a.m : b.m;
+  const double fa = exp(a.m - M), fb = exp(b.m - M);
+  SaState r;
+  r.m = M;
+  r.s = a.s * fa + b.s * fb;
+  r.wx = a.wx * fa + b.wx * fb;
+  r.wy = a.wy * fa + b.wy * fb;
+  r.wz = a.wz * fa + b.wz * fb;
+  return r;
+}
+
+__device__ __forceinline__ SaState sa_shfl_down(const SaState& a, int off) {
+  SaState r;
+  r.m = __shfl_down_sync(0xffffffffu, a.m, off);
+  r.s = __shfl_down_sync(0xffffffffu, a.s, off);
+  r.wx = __shfl_down_sync(0xffffffffu, a.wx, off);
+  r.wy = __shfl_down_sync(0xffffffffu, a.wy, off);
+  r.wz = __shfl_down_sync(0xffffffffu, a.wz, off);
+  return r;
+}
+
+template <typename T>
+__device__ __forceinline__ float load_as_float(const T* p);
+template <>
+__device__ __forceinline__ float load_as_float<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// VEC: channel-last float32 input with 16-byte aligned voxels -> float4 loads of 4 channels.
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(const sp3d_softargmax_args a, int splits,
+                                                                         int vox_per_split) {
+  __shared__ SaState s_red[kSaThreads / 32];
+  const int cube = blockIdx.y;
+  const int split = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int N = a.X * a.Y * a.Z;
+  const float* cen = a.centers + (int64_t)cube * a.center_stride;
+  double* ws = reinterpret_cast<double*>(a.workspace) + ((int64_t)cube * splits + split) * a.C * kSaState;
+  if (a.check_flag && !(cen[3] >= 0.0f)) {
+    for (int i = tid; i < a.C * kSaState; i += kSaThreads) ws[i] = 0.0;
+    return;
+  }
+  const float cx = cen[0], cy = cen[1], cz = cen[2];
+  const int v_begin = split * vox_per_split;
+  const int v_end = min(N, v_begin + vox_per_split);
+  const T* xb = reinterpret_cast<const T*>(a.x) + (int64_t)cube * a.stride_cube;
+
+  for (int c0 = 0; c0 < a.C; c0 += kSaGroup) {
+    const int cn = min(kSaGroup, a.C - c0);
+    float m[kSaGroup], s[kSaGroup], wx[kSaGroup], wy[kSaGroup], wz[kSaGroup];
+#pragma unroll
+    for (int j = 0; j < kSaGroup; ++j) { m[j] = -INFINITY; s[j] = 0.f; wx[j] = 0.f; wy[j] = 0.f; wz[j] = 0.f; }
+    for (int vox = v_begin + tid; vox < v_end; vox += kSaThreads) {
+      const int iz = vox % a.Z, iy = (vox / a.Z) % a.Y, ix = vox / (a.Z * a.Y);
+      // g = fl(lin + centre) as in ProjectLayer.compute_grid; accumulate g - centre
+      const float gx = __fsub_rn(__fadd_rn(a.lin_x[ix], cx), cx);
+      const float gy = __fsub_rn(__fadd_rn(a.lin_y[iy], cy), cy);
+      const float gz = __fsub_rn(__fadd_rn(a.lin_z[iz], cz), cz);
+      const T* p = xb + (int64_t)vox * a.stride_vox + (int64_t)c0 * a.stride_c;
+      float xv[kSaGroup];
+      if (VEC) {
+#pragma unroll
+        for (int j = 0; j < kSaGroup; j += 4) {
+          if (j < cn) {
+            const float4 q = ldg4(reinterpret_cast<const float*>(p) + j);
+            xv[j] = q.x; xv[j + 1] = q.y; xv[j + 2] = q.z; xv[j + 3] = q.w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kSaGroup; ++j)
+          if (j < cn) xv[j] = load_as_float<T>(p + (int64_t)j * a.stride_c);
+      }
+#pragma unroll
+      for (int j = 0; j < kSaGroup; ++j) {
+        if (j < cn) {
+          const float z = __fmul_rn(a.beta, xv[j]);
+          if (z > m[j]) {
+            const float sc = expf(m[j] - z);  // exp(-inf) = 0 on the first element
+            s[j] = fmaf(s[j], sc, 1.0f);
+            wx[j] = fmaf(wx[j], sc, gx);
+            wy[j] = fmaf(wy[j], sc, gy);
+            wz[j] = fmaf(wz[j], sc, gz);
+            m[j] = z;
+          } else {
+            const float e = expf(z - m[j]);
+            s[j] += e;
+            wx[j] = fmaf(e, gx, wx[j]);
+            wy[j] = fmaf(e, gy, wy[j]);
+            wz[j] = fmaf(e, gz, wz[j]);
+          }
+        }
+      }
+    }
+    // merge threads -> CTA, one channel at a time, in float64
+    for (int j = 0; j < cn; ++j) {
+      SaState st{(double)m[j], (double)s[j], (double)wx[j], (double)wy[j], (double)wz[j]};
+      for (int off = 16; off > 0; off >>= 1) st = sa_merge(st, sa_shfl_down(st, off));
+      if ((tid & 31) == 0) s_red[tid >> 5] = st;
+      __syncthreads();
+      if (tid == 0) {
+        SaState r = s_red[0];
+        for (int w = 1; w < kSaThreads / 32; ++w) r = sa_merge(r, s_red[w]);
+        double* o = ws + (int64_t)(c0 + j) * kSaState;
+        o[0] = r.m; o[1] = r.s; o[2] = r.wx; o[3] = r.wy; o[4] = r.wz;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void softargmax_merge_kernel(const sp3d_softargmax_args a, int splits) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (cube, channel)
+  if (i >= a.n_cubes * a.C) return;
+  const int cube = i / a.C, c = i % a.C;
+  const float* cen = a.centers + (int64_t)cube * a.center_stride;
+  float* o = a.out + (int64_t)i * 3;
+  if (a.check_flag && !(cen[3] >= 0.0f)) { o[0] = o[1] = o[2] = 0.0f; return; }
+  const double* ws = reinterpret_cast<const double*>(a.workspace);
+  SaState r{0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int sp = 0; sp < splits; ++sp) {
+    const double* p = ws + (((int64_t)cube * splits + sp) * a.C + c) * kSaState;
+    SaState t{p[0], p[1], p[2], p[3], p[4]};
+    r = sa_merge(r, t);
+  }
+  o[0] = (float)((double)cen[0] + r.wx / r.s);
+  o[1] = (float)((double)cen[1] + r.wy / r.s);
+  o[2] = (float)((double)cen[2] + r.wz / r.s);
+}
+
+static int sa_splits(const sp3d_softargmax_args* a) {
+  const int64_t N = (int64_t)a->X * a->Y * a->Z;
+  int splits = (int)((148 * 4 + a->n_cubes - 1) / (a->n_cubes > 0 ? a->n_cubes : 1));
+  const int max_splits = (int)((N + 1023) / 1024);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  return splits;
+}
+
+}  // namespace sp3d
+
+extern "C" int64_t sp3d_softargmax3d_workspace(const sp3d_softargmax_args* a) {
+  if (a == nullptr || a->n_cubes < 0 || a->C < 1) return 0;
+  return (int64_t)a->n_cubes * sp3d::sa_splits(a) * a->C * sp3d::kSaState * (int64_t)sizeof(double);
+}
+
+extern "C" int sp3d_softargmax3d_fwd(const sp3d_softargmax_args* a, void* stream) {
+  using namespace sp3d;
+  if (a == nullptr || a->x == nullptr || a->out == nullptr || a->centers == nullptr || a->lin_x == nullptr ||
+      a->lin_y == nullptr || a->lin_z == nullptr || a->C < 1 || a->n_cubes < 0 || a->X < 1 || a->Y < 1 || a->Z < 1 ||
+      a->center_stride < 3 || (a->check_flag && a->center_stride < 4))
+    return SP3D_ERR_INVALID_ARG;
+  if (a->x_dtype != SP3D_F32 && a->x_dtype != SP3D_BF16) return SP3D_ERR_UNSUPPORTED;
+  if (a->n_cubes == 0) return SP3D_OK;
+  if (a->n_cubes > 65535) return SP3D_ERR_INVALID_ARG;
+  if (a->workspace == nullptr || a->workspace_bytes < sp3d_softargmax3d_workspace(a) ||
+      (reinterpret_cast<uintptr_t>(a->workspace) % 8) != 0)
+    return SP3D_ERR_WORKSPACE;
+  const int splits = sa_splits(a);
+  const int N = a->X * a->Y * a->Z;
+  const int vps = (N + splits - 1) / splits;
+  dim3 grid(splits, a->n_cubes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a->x_dtype == SP3D_F32) {
+    const bool vec = a->stride_c == 1 && (a->stride_vox % 4) == 0 && (a->stride_cube % 4) == 0 &&
+                     (reinterpret_cast<uintptr_t>(a->x) % 16) == 0 && a->stride_vox >= ((a->C + 3) / 4) * 4;
+    if (vec) softargmax_partial_kernel<float, true><<<grid, kSaThreads, 0, st>>>(*a, splits, vps);
+    else softargmax_partial_kernel<float, false><<<grid, kSaThreads, 0, st>>>(*a, splits, vps);
+  } else {
+    softargmax_partial_kernel<__nv_bfloat16, false><<<grid, kSaThreads, 0, st>>>(*a, splits, vps);
+  }
+  int rc = check_launch();
+  if (rc != SP3D_OK) return rc;
+  const int total = a->n_cubes * a->C;
+  softargmax_merge_kernel<<<(total + 127) / 128, 128, 0, st>>>(*a, splits);
+  return check_launch();
+}

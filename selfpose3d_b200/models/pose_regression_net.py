@@ -1,0 +1,85 @@
+"""PoseRegressionNet -- per-person cube: un-project -> V2VNet -> soft-argmax joints.
+
+Interface mirror of the reference's ``lib/models/pose_regression_net.py:13-53``
+(``SoftArgmaxLayer``, ``PoseRegressionNet``); state-dict keys ``v2v_net.*`` identical.
+``forward`` keeps the reference contract (one proposal slot across the batch, rows with
+``flag < 0`` skipped and left zero); ``regress`` is the batched entry that takes any number of
+cube centres at once (all proposal slots of all samples), which is how the top-level model
+calls it.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .project_layer import ProjectLayer
+from .v2v_net import V2VNet
+
+
+class SoftArgmaxLayer(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.beta = cfg.NETWORK.BETA
+
+    def forward(self, x, grids):
+        """``x [B,C,X,Y,Z]`` (or ``[B,C,N]``), ``grids [B,N,3]`` -> ``[B,C,3]`` (reference :19-28).
+
+        The kernel rebuilds voxel coordinates from per-axis vectors, so the explicit ``grids``
+        tensor is decomposed back into (axis values, zero centre); it must be the separable
+        x-major / z-fastest grid ``ProjectLayer`` produces."""
+        B, C = int(x.shape[0]), int(x.shape[1])
+        if x.dim() != 5:
+            raise ValueError("SoftArgmaxLayer expects [B,C,X,Y,Z] cubes")
+        X, Y, Z = [int(s) for s in x.shape[2:]]
+        x = x.float().contiguous()
+        out = torch.empty(B, C, 3, device=x.device, dtype=torch.float32)
+        zero = torch.zeros(1, 3, device=x.device, dtype=torch.float32)
+        g = grids.float().reshape(B, X, Y, Z, 3)
+        for i in range(B):   # per-sample axes (API path only; the batched path never builds `grids`)
+            lin = (g[i, :, 0, 0, 0].contiguous(), g[i, 0, :, 0, 1].contiguous(), g[i, 0, 0, :, 2].contiguous())
+            out[i] = ops.softargmax_axes(x[i:i + 1], (C * X * Y * Z, X * Y * Z, 1), 1, C, (X, Y, Z), zero, lin,
+                                         self.beta)[0]
+        return out
+
+
+class PoseRegressionNet(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.grid_size = cfg.PICT_STRUCT.GRID_SIZE
+        self.cube_size = cfg.PICT_STRUCT.CUBE_SIZE
+        self.num_joints = cfg.NETWORK.NUM_JOINTS
+
+        self.project_layer = ProjectLayer(cfg)
+        self.v2v_net = V2VNet(cfg.NETWORK.NUM_JOINTS, cfg.NETWORK.NUM_JOINTS)
+        self.soft_argmax_layer = SoftArgmaxLayer(cfg)
+
+    def regress(self, all_heatmaps, cams, centers, cube_sample, chunk=16):
+        """Joints of ``n`` person cubes: ``centers [n,>=3]`` (all valid), ``cube_sample [n]`` int32
+        sample index of each cube -> ``[n, J, 3]`` world mm.  Cubes are processed ``chunk`` at a
+        time to bound activation memory (a 64^3 cube needs ~0.4 GB of float32 activations)."""
+        n = int(centers.shape[0])
+        J = self.num_joints
+        out = torch.empty(n, J, 3, device=centers.device, dtype=torch.float32)
+        X, Y, Z = [int(s) for s in self.cube_size]
+        for s in range(0, n, chunk):
+            e = min(n, s + chunk)
+            cubes, _ = self.project_layer.project_cl(all_heatmaps, cams, centers[s:e], False, self.grid_size,
+                                                     self.cube_size, cube_sample=cube_sample[s:e])
+            y = self.v2v_net.forward_cl(cubes)
+            pitch = int(y.shape[-1])
+            out[s:e] = ops.softargmax(y, (X * Y * Z * pitch, 1, pitch), e - s, J, (X, Y, Z), centers[s:e],
+                                      self.grid_size, self.soft_argmax_layer.beta)
+        return out
+
+    def forward(self, all_heatmaps, meta, grid_centers, flip_xcoords=None):
+        device = all_heatmaps[0].device
+        B = int(all_heatmaps[0].shape[0])
+        pred = torch.zeros(B, self.num_joints, 3, device=device)
+        index = torch.nonzero(grid_centers[:, 3] >= 0).flatten()      # host sync, as the reference's boolean mask
+        if index.numel() == 0:
+            return pred
+        cams = ops.pack_cameras(meta, self.project_layer.img_size, flip_xcoords).to(device, non_blocking=True)
+        centers = grid_centers.to(device=device, dtype=torch.float32)[index].contiguous()
+        pred[index] = self.regress(all_heatmaps, cams, centers, index.to(torch.int32))
+        return pred

@@ -1,0 +1,376 @@
+"""Thin torch-tensor front end of the C ABI (``include/sp3d.h``).
+
+PyTorch is used here for device memory, streams and nothing else: every
+function takes CUDA tensors, fills the POD argument struct and launches the
+hand-written kernel on torch's current stream.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .utils.transforms import get_affine_transform
+
+_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.Sp3dError(
+                "selfpose3d_b200 kernels need CUDA tensors (got a %s tensor); this backend has no CPU path"
+                % t.device.type)
+
+
+def round_up(v, m):
+    return (int(v) + m - 1) // m * m
+
+
+# --------------------------------------------------------------------------------------------- cameras
+def pack_cameras(meta, image_size, flip_xcoords=None):
+    """``meta`` (list over views of collated dicts) -> ``[B, V, 32]`` float32 CPU tensor.
+
+    One host pass replaces the per-(sample, view) ``get_affine_transform`` /
+    ``unfold_camera_param`` calls of ``lib/models/project_layer.py:64-75``.  Camera
+    parameters are cast to float32 exactly where the reference casts them
+    (``lib/utils/cameras.py:14-23``, ``project_layer.py:69-72``).  If ``meta`` lives
+    on a GPU (DataParallel scatter) this costs one device->host copy per tensor.
+    """
+    V = len(meta)
+    B = int(meta[0]["center"].shape[0])
+    table = np.zeros((B, V, _lib.CAM_FLOATS), dtype=np.float32)
+    flips = None
+    if flip_xcoords is not None:
+        flips = np.asarray(torch.as_tensor(flip_xcoords).detach().cpu()).astype(bool)
+    for c, m in enumerate(meta):
+        center = np.asarray(m["center"].detach().cpu())
+        scale = np.asarray(m["scale"].detach().cpu())
+        rot = np.asarray(m["rotation"].detach().cpu())
+        cam = {k: np.asarray(v.detach().cpu()) for k, v in m["camera"].items()
+               if k in ("R", "T", "fx", "fy", "cx", "cy", "k", "p")}
+        table[:, c, 0:9] = cam["R"].reshape(B, 9)
+        table[:, c, 9:12] = cam["T"].reshape(B, 3)
+        table[:, c, 12] = cam["fx"].reshape(B)
+        table[:, c, 13] = cam["fy"].reshape(B)
+        table[:, c, 14] = cam["cx"].reshape(B)
+        table[:, c, 15] = cam["cy"].reshape(B)
+        table[:, c, 16:19] = cam["k"].reshape(B, 3)
+        table[:, c, 19:21] = cam["p"].reshape(B, 2)
+        for i in range(B):
+            trans = get_affine_transform(center[i], scale[i], rot[i], image_size)
+            table[i, c, 21:27] = trans.reshape(6)
+            # width, height = center * 2, compared against float32 pixels (project_layer.py:68,78-80)
+            table[i, c, 27] = center[i][0] * 2
+            table[i, c, 28] = center[i][1] * 2
+            table[i, c, 29] = 1.0 if (flips is not None and flips[i]) else 0.0
+    return torch.from_numpy(table)
+
+
+_LIN_CACHE = {}
+
+
+def linspace_axes(grid_size, cube_size, device):
+    """The three ``torch.linspace(-s/2, s/2, n)`` vectors of ``compute_grid``
+    (``lib/models/project_layer.py:28-30``), evaluated once on the host and cached on ``device``."""
+    key = (tuple(float(s) for s in grid_size), tuple(int(n) for n in cube_size), str(device))
+    if key not in _LIN_CACHE:
+        _LIN_CACHE[key] = tuple(
+            torch.linspace(-key[0][a] / 2, key[0][a] / 2, key[1][a]).to(device) for a in range(3))
+    return _LIN_CACHE[key]
+
+
+# --------------------------------------------------------------------------------------------- K1
+def unproject(heatmaps, hm_strides, cams, centers, grid_size, cube_size, image_size, heatmap_hw, channels,
+              out, out_strides, out_c_pad=0, check_flag=False, cubes_per_sample=1, cube_sample=None,
+              grids=None, view_range=None, partial=False):
+    """Launch the fused un-projection.
+
+    heatmaps: list[V] of CUDA float32 tensors sharing ``hm_strides = (b, c, h, w)`` element strides.
+    cams ``[B,V,32]``, centers ``[n_cubes, >=3]`` float32 CUDA.  ``out`` receives the cubes through
+    ``out_strides = (cube, channel, voxel)``.
+    """
+    _require_cuda(cams, centers, out, *heatmaps)
+    a = _lib.UnprojectArgs()
+    V = len(heatmaps)
+    for v in range(V):
+        a.heatmaps[v] = heatmaps[v].data_ptr()
+    a.hm_stride_b, a.hm_stride_c, a.hm_stride_h, a.hm_stride_w = [int(s) for s in hm_strides]
+    a.cams = cams.data_ptr()
+    a.centers = centers.data_ptr()
+    a.center_stride = int(centers.stride(0))
+    a.check_flag = int(bool(check_flag))
+    a.cubes_per_sample = int(cubes_per_sample)
+    a.cube_sample = cube_sample.data_ptr() if cube_sample is not None else None
+    lin = linspace_axes(grid_size, cube_size, out.device)
+    a.lin_x, a.lin_y, a.lin_z = lin[0].data_ptr(), lin[1].data_ptr(), lin[2].data_ptr()
+    a.B = int(cams.shape[0])
+    a.V = V
+    a.C = int(channels)
+    a.h, a.w = int(heatmap_hw[0]), int(heatmap_hw[1])
+    a.n_cubes = int(centers.shape[0])
+    a.X, a.Y, a.Z = [int(s) for s in cube_size]
+    a.img_w, a.img_h = float(image_size[0]), float(image_size[1])
+    a.view_begin, a.view_end = (0, V) if view_range is None else (int(view_range[0]), int(view_range[1]))
+    a.partial = int(bool(partial))
+    a.cubes = out.data_ptr()
+    a.out_dtype = _DT[out.dtype]
+    a.out_stride_cube, a.out_stride_c, a.out_stride_vox = [int(s) for s in out_strides]
+    a.out_c_pad = int(out_c_pad)
+    a.grids = grids.data_ptr() if grids is not None else None
+    n_vox = a.X * a.Y * a.Z
+    work = (a.view_end - a.view_begin) * a.B * a.C * a.h * a.w * 4 + a.n_cubes * a.C * n_vox * out.element_size()
+    _lib.call("sp3d_unproject_fwd", a, _stream(), kind="unproject", work=work)
+
+
+def unproject_finalize(buf, n_cubes, channels, n_vox, strides):
+    a = _lib.UnprojectFinalizeArgs()
+    a.buf = buf.data_ptr()
+    a.n_cubes, a.C, a.N = int(n_cubes), int(channels), int(n_vox)
+    a.stride_cube, a.stride_c, a.stride_vox = [int(s) for s in strides]
+    _lib.call("sp3d_unproject_finalize", a, _stream(), kind="unproject_finalize",
+              work=2 * 4 * int(n_cubes) * (int(channels) + 1) * int(n_vox))
+
+
+# --------------------------------------------------------------------------------------------- K3
+def nms_topk(root_cubes, max_people, threshold, space_size, space_center, loc_f64=False, return_index=False):
+    """``root_cubes [B,X,Y,Z]`` float32 contiguous -> ``grid_centers [B,K,5]``."""
+    _require_cuda(root_cubes)
+    if not root_cubes.is_contiguous() or root_cubes.dtype != torch.float32:
+        raise _lib.Sp3dError("nms_topk expects a contiguous float32 [B,X,Y,Z] tensor")
+    B, X, Y, Z = root_cubes.shape
+    K = int(max_people)
+    gc = torch.empty(B, K, 5, device=root_cubes.device, dtype=torch.float32)
+    idx = torch.empty(B, K, device=root_cubes.device, dtype=torch.int32) if return_index else None
+    a = _lib.NmsTopkArgs()
+    a.root_cubes = root_cubes.data_ptr()
+    a.B, a.X, a.Y, a.Z, a.K = B, X, Y, Z, K
+    a.threshold = float(threshold)
+    for d in range(3):
+        a.space_size[d] = float(space_size[d])
+        a.space_center[d] = float(space_center[d])
+    a.loc_f64 = int(bool(loc_f64))
+    a.grid_centers = gc.data_ptr()
+    a.topk_index = idx.data_ptr() if idx is not None else None
+    _lib.call("sp3d_nms_topk3d", a, _stream(), kind="nms_topk", work=4 * B * X * Y * Z)
+    return (gc, idx) if return_index else gc
+
+
+# --------------------------------------------------------------------------------------------- K4
+def softargmax_axes(x, strides, n_cubes, channels, cube_size, centers, lin, beta, check_flag=False):
+    """Soft-argmax with explicit per-axis coordinate vectors ``lin = (x[X], y[Y], z[Z])`` (centre-free)."""
+    return softargmax(x, strides, n_cubes, channels, cube_size, centers, None, beta, check_flag, lin=lin)
+
+
+def softargmax(x, strides, n_cubes, channels, cube_size, centers, grid_size, beta, check_flag=False, lin=None):
+    """``x`` addressed as ``[n_cubes, C, N]`` through ``strides = (cube, channel, voxel)`` -> ``[n_cubes, C, 3]``."""
+    _require_cuda(x, centers)
+    out = torch.empty(n_cubes, channels, 3, device=x.device, dtype=torch.float32)
+    a = _lib.SoftargmaxArgs()
+    a.x = x.data_ptr()
+    a.x_dtype = _DT[x.dtype]
+    a.stride_cube, a.stride_c, a.stride_vox = [int(s) for s in strides]
+    a.n_cubes, a.C = int(n_cubes), int(channels)
+    a.X, a.Y, a.Z = [int(s) for s in cube_size]
+    a.centers = centers.data_ptr()
+    a.center_stride = int(centers.stride(0))
+    a.check_flag = int(bool(check_flag))
+    if lin is None:
+        lin = linspace_axes(grid_size, cube_size, x.device)
+    a.lin_x, a.lin_y, a.lin_z = lin[0].data_ptr(), lin[1].data_ptr(), lin[2].data_ptr()
+    a.beta = float(beta)
+    a.out = out.data_ptr()
+    nbytes = int(_lib.load().sp3d_softargmax3d_workspace(a))
+    ws = torch.empty(max(nbytes // 8, 1), device=x.device, dtype=torch.float64)
+    a.workspace = ws.data_ptr()
+    a.workspace_bytes = nbytes
+    _lib.call("sp3d_softargmax3d_fwd", a, _stream(), launches=2, kind="softargmax",
+              work=a.n_cubes * a.C * a.X * a.Y * a.Z * x.element_size())
+    return out
+
+
+# --------------------------------------------------------------------------------------------- layout
+def to_channel_last(x, c_pitch=None, dtype=None):
+    """Channel-first ``[N, C, *spatial]`` (contiguous) -> channel-last ``[N, *spatial, c_pitch]``."""
+    _require_cuda(x)
+    x = x.contiguous()
+    N, Cc = int(x.shape[0]), int(x.shape[1])
+    spatial = tuple(int(s) for s in x.shape[2:])
+    S = int(np.prod(spatial))
+    c_pitch = round_up(Cc, 4) if c_pitch is None else int(c_pitch)
+    dst = torch.empty((N,) + spatial + (c_pitch,), device=x.device, dtype=dtype or x.dtype)
+    a = _lib.LayoutArgs()
+    a.src, a.dst = x.data_ptr(), dst.data_ptr()
+    a.N, a.C, a.S, a.c_pitch = N, Cc, S, c_pitch
+    a.to_channel_last = 1
+    a.src_dtype, a.dst_dtype = _DT[x.dtype], _DT[dst.dtype]
+    _lib.call("sp3d_layout_convert", a, _stream(), kind="layout", work=N * Cc * S * (x.element_size() + dst.element_size()))
+    return dst
+
+
+def to_channel_first(x, channels, dtype=None):
+    """Channel-last ``[N, *spatial, c_pitch]`` -> contiguous channel-first ``[N, channels, *spatial]``."""
+    _require_cuda(x)
+    if not x.is_contiguous():
+        raise _lib.Sp3dError("to_channel_first expects a contiguous channel-last tensor")
+    N = int(x.shape[0])
+    spatial = tuple(int(s) for s in x.shape[1:-1])
+    S = int(np.prod(spatial))
+    dst = torch.empty((N, int(channels)) + spatial, device=x.device, dtype=dtype or x.dtype)
+    a = _lib.LayoutArgs()
+    a.src, a.dst = x.data_ptr(), dst.data_ptr()
+    a.N, a.C, a.S, a.c_pitch = N, int(channels), S, int(x.shape[-1])
+    a.to_channel_last = 0
+    a.src_dtype, a.dst_dtype = _DT[x.dtype], _DT[dst.dtype]
+    _lib.call("sp3d_layout_convert", a, _stream(), kind="layout",
+              work=N * int(channels) * S * (x.element_size() + dst.element_size()))
+    return dst
+
+
+# --------------------------------------------------------------------------------------------- conv family
+def _set3(field, vals):
+    for i in range(3):
+        field[i] = int(vals[i])
+
+
+def conv_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksize, stride, tap_off0, tap_step,
+                ostride, ooffset, relu, algo=_lib.CONV_SIMT_F32, cin_real=None):
+    """One implicit-GEMM convolution launch.  ``x`` / ``out`` are channel-last 5-D ``[N,D,H,W,pitch]``."""
+    a = _lib.ConvArgs()
+    a.in_ = x.data_ptr()
+    a.weight = weight.data_ptr()
+    a.scale = scale.data_ptr() if scale is not None else None
+    a.shift = shift.data_ptr() if shift is not None else None
+    a.residual = residual.data_ptr() if residual is not None else None
+    a.out = out.data_ptr()
+    a.N, a.D, a.H, a.W = [int(s) for s in x.shape[:4]]
+    a.cin = int(cin)
+    a.cin_pitch = int(x.shape[4])
+    a.OD, a.OH, a.OW = [int(s) for s in out_grid]
+    a.TD, a.TH, a.TW = [int(s) for s in out.shape[1:4]]
+    a.cout = int(cout)
+    a.cout_pitch = int(out.shape[4])
+    a.cout_pitch_w = int(weight.shape[-1])
+    _set3(a.ksize, ksize)
+    _set3(a.stride, stride)
+    _set3(a.tap_off0, tap_off0)
+    _set3(a.tap_step, tap_step)
+    _set3(a.ostride, ostride)
+    _set3(a.ooffset, ooffset)
+    a.relu = int(relu)
+    a.algo = int(algo)
+    a.in_dtype, a.out_dtype = _DT[x.dtype], _DT[out.dtype]
+    flops = 2.0 * a.N * a.OD * a.OH * a.OW * a.cout * (cin_real or a.cin) * (a.ksize[0] * a.ksize[1] * a.ksize[2])
+    _lib.call("sp3d_conv_fwd", a, _stream(), kind="conv", work=flops)
+
+
+def maxpool(x, channels, k, s, p):
+    """Channel-last ``[N,D,H,W,pitch]`` max pooling; returns the pooled channel-last tensor."""
+    _require_cuda(x)
+    N, D, H, W, pitch = [int(v) for v in x.shape]
+    dims = (D, H, W)
+    o = [(dims[i] + 2 * p[i] - k[i]) // s[i] + 1 for i in range(3)]
+    out = torch.empty((N, o[0], o[1], o[2], pitch), device=x.device, dtype=x.dtype)
+    a = _lib.MaxpoolArgs()
+    a.in_, a.out = x.data_ptr(), out.data_ptr()
+    a.N, a.D, a.H, a.W, a.C, a.c_pitch = N, D, H, W, int(channels), pitch
+    a.OD, a.OH, a.OW = o
+    _set3(a.k, k)
+    _set3(a.s, s)
+    _set3(a.p, p)
+    a.dtype = _DT[x.dtype]
+    _lib.call("sp3d_maxpool_fwd", a, _stream(), kind="maxpool",
+              work=(N * D * H * W + N * o[0] * o[1] * o[2]) * int(channels) * x.element_size())
+    return out
+
+
+class PackedConv:
+    """A convolution (regular or transposed) with evaluation-mode BatchNorm folded in, packed for
+    ``sp3d_conv_fwd``: weights ``[taps, cin_p, cout_p]``, per-channel ``scale`` / ``shift``.
+
+    Built from the reference-shaped parameters (``nn.Conv{2,3}d`` ``[Cout,Cin,k..]`` or
+    ``nn.ConvTranspose{2,3}d`` ``[Cin,Cout,k..]``, optional ``nn.BatchNorm``), so the module tree
+    and its state dict stay exactly the reference's.
+    """
+
+    def __init__(self, weight, bias=None, bn=None, stride=1, padding=0, transposed=False, relu=0):
+        w = weight.detach()
+        self.nd = w.dim() - 2
+        self.transposed = bool(transposed)
+        self.relu = int(relu)
+        k = [1] * (3 - self.nd) + [int(s) for s in w.shape[2:]]
+        self.k = k
+        self.stride = [1] * (3 - self.nd) + [int(stride)] * self.nd
+        self.padding = [0] * (3 - self.nd) + [int(padding)] * self.nd
+        w5 = w.reshape(w.shape[0], w.shape[1], *k).float()
+        if transposed:
+            self.cin, self.cout = int(w.shape[0]), int(w.shape[1])
+            w5 = w5.permute(1, 0, 2, 3, 4)  # -> [Cout, Cin, kd, kh, kw]
+        else:
+            self.cout, self.cin = int(w.shape[0]), int(w.shape[1])
+        self.cin_p = round_up(self.cin, 4)
+        self.cout_pw = round_up(self.cout, 4)
+        dev = w.device
+
+        scale = None
+        shift = bias.detach().float().clone() if bias is not None else None
+        if bn is not None:
+            inv = torch.rsqrt(bn.running_var.detach().float() + bn.eps)
+            scale = bn.weight.detach().float() * inv
+            base = shift if shift is not None else torch.zeros(self.cout, device=dev)
+            shift = (base - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
+        self.scale = scale.contiguous() if scale is not None else None
+        self.shift = shift.contiguous() if shift is not None else None
+
+        def pack(sub):  # sub: [Cout, Cin, a, b, c] -> [a*b*c, cin_p, cout_pw]
+            t = sub.permute(2, 3, 4, 1, 0).reshape(-1, self.cin, self.cout)
+            out = torch.zeros(t.shape[0], self.cin_p, self.cout_pw, device=dev, dtype=torch.float32)
+            out[:, :self.cin, :self.cout] = t
+            return out.contiguous()
+
+        if not transposed:
+            self.weights = [pack(w5)]
+            self.phases = [None]
+        else:
+            # one stride-1 sub-convolution per output phase (see include/sp3d.h, sp3d_conv_args)
+            self.weights, self.phases = [], []
+            s, p = self.stride, self.padding
+            for pd in range(s[0]):
+                for ph in range(s[1]):
+                    for pw in range(s[2]):
+                        phase = (pd, ph, pw)
+                        t0 = [(phase[i] + p[i]) % s[i] for i in range(3)]
+                        sub = w5[:, :, t0[0]::s[0], t0[1]::s[1], t0[2]::s[2]]
+                        off0 = [(phase[i] + p[i] - t0[i]) // s[i] for i in range(3)]
+                        self.weights.append(pack(sub))
+                        self.phases.append((phase, off0, [int(v) for v in sub.shape[2:]]))
+
+    def out_shape(self, dims):
+        if not self.transposed:
+            return [(dims[i] + 2 * self.padding[i] - self.k[i]) // self.stride[i] + 1 for i in range(3)]
+        return [(dims[i] - 1) * self.stride[i] - 2 * self.padding[i] + self.k[i] for i in range(3)]
+
+    def __call__(self, x, residual=None, out_pitch=None, algo=_lib.CONV_SIMT_F32):
+        """``x``: channel-last ``[N,D,H,W,pitch>=cin_p]`` float32.  Returns channel-last output."""
+        N, D, H, W, pitch = [int(v) for v in x.shape]
+        if pitch < self.cin_p:
+            raise _lib.Sp3dError("activation pitch %d smaller than packed cin %d" % (pitch, self.cin_p))
+        o = self.out_shape((D, H, W))
+        out_pitch = round_up(self.cout, 4) if out_pitch is None else int(out_pitch)
+        out = torch.empty((N, o[0], o[1], o[2], out_pitch), device=x.device, dtype=torch.float32)
+        if not self.transposed:
+            conv_launch(x, self.weights[0], self.scale, self.shift, residual, out, self.cin_p, self.cout, o, self.k,
+                        self.stride, [-p for p in self.padding], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu, algo,
+                        cin_real=self.cin)
+        else:
+            for wgt, (phase, off0, ks) in zip(self.weights, self.phases):
+                grid = [(o[i] - phase[i] + self.stride[i] - 1) // self.stride[i] for i in range(3)]
+                conv_launch(x, wgt, self.scale, self.shift, residual, out, self.cin_p, self.cout, grid, ks,
+                            [1, 1, 1], off0, [-1, -1, -1], self.stride, phase, self.relu, algo, cin_real=self.cin)
+        return out

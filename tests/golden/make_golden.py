@@ -278,7 +278,30 @@ def gold_inference():
     save("cuboid_proposal_allj", root_cubes=rc, grid_centers=gcs, seed=31)
 
 
+def gold_state_dict_keys():
+    import json
+    from easydict import EasyDict
+    out = {}
+    ref_cfg.NETWORK.NUM_JOINTS = 15
+    ref_cfg.NETWORK.ROOTNET_ROOTHM = True
+    ref_cfg.NETWORK.ROOTNET_TRAIN_SYNTH = False
+    ref_cfg.WITH_ATTN = True
+    ref_cfg.ATTN_NUM_LAYERS = 18
+    ref_cfg.MULTI_PERSON.INITIAL_CUBE_SIZE = [80, 80, 20]
+    ref_cfg.PICT_STRUCT.CUBE_SIZE = [64, 64, 64]
+    m = multi_person_posenet_ssv.get_multi_person_pose_net(ref_cfg, is_train=False)
+    out["multi_person_posenet_ssv_attn"] = {k: list(v.shape) for k, v in m.state_dict().items()}
+    ref_cfg.WITH_ATTN = False
+    ref_cfg.NETWORK.ROOTNET_ROOTHM = False
+    m = multi_person_posenet.get_multi_person_pose_net(ref_cfg, is_train=False)
+    out["multi_person_posenet"] = {k: list(v.shape) for k, v in m.state_dict().items()}
+    with open(os.path.join(HERE, "state_dict_keys.json"), "w") as f:
+        json.dump(out, f)
+    print("state_dict_keys.json", {k: len(v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
+    gold_state_dict_keys()
     gold_affine()
     gold_project_pose()
     gold_project_layer()

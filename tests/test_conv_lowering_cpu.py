@@ -1,0 +1,127 @@
+"""CPU check of the host-side convolution lowering (``ops.PackedConv``): BatchNorm folding, weight
+packing, tap offsets and the per-phase decomposition of transposed convolutions are validated by
+executing the exact ``sp3d_conv_fwd`` argument semantics (include/sp3d.h) with a small torch
+emulator and comparing with ``torch.nn.functional`` on the reference-shaped parameters."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from selfpose3d_b200 import ops
+
+
+def emulate_conv_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksize, stride, tap_off0,
+                        tap_step, ostride, ooffset, relu, algo=0, cin_real=None):
+    N, D, H, W, _ = x.shape
+    dims = (D, H, W)
+    acc = torch.zeros((N,) + tuple(out_grid) + (cout,), dtype=torch.float64)
+    t = 0
+    for td in range(ksize[0]):
+        for th in range(ksize[1]):
+            for tw in range(ksize[2]):
+                tt = (td, th, tw)
+                idx, ok = [], []
+                for a in range(3):
+                    i = torch.arange(out_grid[a]) * stride[a] + tap_off0[a] + tt[a] * tap_step[a]
+                    ok.append((i >= 0) & (i < dims[a]))
+                    idx.append(i.clamp(0, dims[a] - 1))
+                xs = x[:, idx[0]][:, :, idx[1]][:, :, :, idx[2]][..., :cin].double()
+                m = (ok[0][:, None, None] & ok[1][None, :, None] & ok[2][None, None, :]).double()
+                acc += torch.einsum("ndhwc,co->ndhwo", xs * m[None, ..., None], weight[t, :cin, :cout].double())
+                t += 1
+    v = acc
+    if scale is not None:
+        v = v * scale.double()
+    if shift is not None:
+        v = v + shift.double()
+    sl = tuple(slice(ooffset[a], ooffset[a] + ostride[a] * out_grid[a], ostride[a]) for a in range(3))
+    if relu == 2:
+        v = v.clamp_min(0)
+    if residual is not None:
+        v = v + residual[(slice(None),) + sl][..., :cout].double()
+    if relu == 1:
+        v = v.clamp_min(0)
+    out[(slice(None),) + sl + (slice(0, cout),)] = v.float()
+    out[(slice(None),) + sl + (slice(cout, None),)] = 0
+
+
+@pytest.fixture(autouse=True)
+def _patch(monkeypatch):
+    monkeypatch.setattr(ops, "conv_launch", emulate_conv_launch)
+
+
+def cl(x):   # [N,C,*sp] -> channel-last 5-D with pitch rounded to 4
+    if x.dim() == 4:
+        x = x.unsqueeze(2)
+    N, C = x.shape[:2]
+    out = torch.zeros((N,) + tuple(x.shape[2:]) + (ops.round_up(C, 4),))
+    out[..., :C] = x.permute(0, 2, 3, 4, 1)
+    return out
+
+
+def cf(y, C, nd):
+    y = y[..., :C].permute(0, 4, 1, 2, 3)
+    return y[:, :, 0] if nd == 2 else y
+
+
+def rand_bn(bn):
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_(0, 0.2)
+        bn.running_mean.normal_(0, 0.2)
+        bn.running_var.uniform_(0.5, 1.5)
+    return bn.eval()
+
+
+@pytest.mark.parametrize("k,s,p,cin,cout", [(7, 1, 3, 3, 16), (3, 1, 1, 5, 6), (1, 1, 0, 6, 15), (3, 2, 1, 4, 8)])
+def test_conv3d_lowering(k, s, p, cin, cout):
+    torch.manual_seed(0)
+    conv, bn = nn.Conv3d(cin, cout, k, s, p), rand_bn(nn.BatchNorm3d(cout))
+    x = torch.randn(2, cin, 6, 5, 7)
+    want = F.relu(bn(conv(x)))
+    got = cf(ops.PackedConv(conv.weight, conv.bias, bn, s, p, relu=1)(cl(x)), cout, 3)
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("k,s,p,cin,cout,hw", [(7, 2, 3, 3, 8, (13, 10)), (3, 2, 1, 8, 8, (9, 12)), (1, 2, 0, 8, 12, (9, 7))])
+def test_conv2d_lowering_with_residual(k, s, p, cin, cout, hw):
+    torch.manual_seed(1)
+    conv, bn = nn.Conv2d(cin, cout, k, s, p, bias=False), rand_bn(nn.BatchNorm2d(cout))
+    x = torch.randn(2, cin, *hw)
+    y0 = bn(conv(x))
+    res = torch.randn_like(y0)
+    want = F.relu(y0 + res)
+    got = cf(ops.PackedConv(conv.weight, None, bn, s, p, relu=1)(cl(x), residual=cl(res)), cout, 2)
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
+
+
+def test_conv_transpose3d_k2s2_lowering_relu_before_skip():
+    torch.manual_seed(2)
+    ct, bn = nn.ConvTranspose3d(6, 4, 2, 2), rand_bn(nn.BatchNorm3d(4))
+    x = torch.randn(2, 6, 3, 4, 2)
+    skip = torch.randn(2, 4, 6, 8, 4)
+    want = F.relu(bn(ct(x))) + skip
+    got = cf(ops.PackedConv(ct.weight, ct.bias, bn, 2, 0, transposed=True, relu=2)(cl(x), residual=cl(skip)), 4, 3)
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("hw", [(3, 4), (5, 2)])
+def test_conv_transpose2d_k4s2p1_lowering(hw):
+    torch.manual_seed(3)
+    ct, bn = nn.ConvTranspose2d(8, 6, 4, 2, 1, bias=False), rand_bn(nn.BatchNorm2d(6))
+    x = torch.randn(2, 8, *hw)
+    want = F.relu(bn(ct(x)))
+    got = cf(ops.PackedConv(ct.weight, None, bn, 2, 1, transposed=True, relu=1)(cl(x)), 6, 2)
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
+
+
+def test_output_pitch_one_and_padding_lanes_zero():
+    torch.manual_seed(4)
+    conv = nn.Conv3d(8, 1, 1)
+    x = torch.randn(1, 8, 4, 4, 4)
+    y = ops.PackedConv(conv.weight, conv.bias, None, 1, 0)(cl(x), out_pitch=1)
+    torch.testing.assert_close(y[..., 0], conv(x)[:, 0], rtol=1e-5, atol=1e-6)
+    conv = nn.Conv3d(8, 15, 1)
+    y = ops.PackedConv(conv.weight, conv.bias, None, 1, 0)(cl(x))
+    assert y.shape[-1] == 16 and not y[..., 15].any()
