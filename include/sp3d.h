@@ -72,6 +72,9 @@ typedef struct {
   int B, V, C, h, w;
   int n_cubes, X, Y, Z;
   float img_w, img_h;       /* cfg.NETWORK.IMAGE_SIZE */
+  float hm_cfg_w, hm_cfg_h; /* cfg.NETWORK.HEATMAP_SIZE: scales network-input pixels to heat-map coordinates
+                               (project_layer.py:84-90); normally == (w, h).  The tensor extents (w, h) are what
+                               grid_sample un-normalises and bounds-checks against (:93). */
   int view_begin, view_end; /* views summed by this call (multi-GPU view sharding); 0, V for all */
   int partial;              /* 0: write clamp(num/(den+1e-6),0,1); 1: write raw numerators and the
                                view count as channel C (all-reduce, then sp3d_unproject_finalize) */

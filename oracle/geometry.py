@@ -175,7 +175,8 @@ def bilinear_sample_zeros(img, fx, fy, dtype=np.float32):
     return out
 
 
-def view_sample_coords(grid, cam, center, trans, image_size, heatmap_size, flip, dtype=np.float32):
+def view_sample_coords(grid, cam, center, trans, image_size, heatmap_size, flip, dtype=np.float32,
+                       tensor_wh=None):
     """Per-voxel heat-map coordinates of one view (project_layer.py:76-90).
 
     Returns ``(fx, fy, mask, px, py)``: un-normalised sampling coordinates, the
@@ -203,8 +204,11 @@ def view_sample_coords(grid, cam, center, trans, image_size, heatmap_size, flip,
     v = ((qy * h).astype(t) / H).astype(t)
     sx = np.clip((((u / (w - t(1))).astype(t) * t(2)).astype(t) - t(1)).astype(t), t(-1.1), t(1.1))   # :87-90
     sy = np.clip((((v / (h - t(1))).astype(t) * t(2)).astype(t) - t(1)).astype(t), t(-1.1), t(1.1))
-    fx = (((sx + t(1)) / t(2)).astype(t) * (w - t(1))).astype(t)          # align_corners=True un-normalise
-    fy = (((sy + t(1)) / t(2)).astype(t) * (h - t(1))).astype(t)
+    # align_corners=True un-normalise: grid_sample uses the TENSOR extent (== heatmap_size unless the
+    # network input is not a multiple of 32, see tests/golden "inference_images")
+    tw, th = (w, h) if tensor_wh is None else (t(tensor_wh[0]), t(tensor_wh[1]))
+    fx = (((sx + t(1)) / t(2)).astype(t) * (tw - t(1))).astype(t)
+    fy = (((sy + t(1)) / t(2)).astype(t) * (th - t(1))).astype(t)
     return fx, fy, mask, px, py
 
 
@@ -241,7 +245,7 @@ def unproject(heatmaps, cams, centers, scales, rotations, image_size, heatmap_si
             fl = bool(flip[i]) if flip is not None else False
             fx, fy, mask, px, py = view_sample_coords(
                 grid.astype(t), cams[c][i], centers[c][i], trans.astype(np.float32), image_size,
-                heatmap_size, fl, dtype=t)
+                heatmap_size, fl, dtype=t, tensor_wh=(w, h))
             s = bilinear_sample_zeros(heatmaps[c, i], fx, fy, dtype=t)
             m = mask.astype(t)
             num = (num + s * m[None]).astype(t)                            # :93,96

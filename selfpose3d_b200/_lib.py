@@ -29,7 +29,7 @@ class UnprojectArgs(C.Structure):
         ("lin_x", C.c_void_p), ("lin_y", C.c_void_p), ("lin_z", C.c_void_p),
         ("B", C.c_int), ("V", C.c_int), ("C", C.c_int), ("h", C.c_int), ("w", C.c_int),
         ("n_cubes", C.c_int), ("X", C.c_int), ("Y", C.c_int), ("Z", C.c_int),
-        ("img_w", C.c_float), ("img_h", C.c_float),
+        ("img_w", C.c_float), ("img_h", C.c_float), ("hm_cfg_w", C.c_float), ("hm_cfg_h", C.c_float),
         ("view_begin", C.c_int), ("view_end", C.c_int), ("partial", C.c_int),
         ("cubes", C.c_void_p), ("out_dtype", C.c_int),
         ("out_stride_cube", C.c_int64), ("out_stride_c", C.c_int64), ("out_stride_vox", C.c_int64),

@@ -25,7 +25,8 @@ struct ViewSample {
 
 // World point -> heat-map sampling position of one view.  `cam` points at SP3D_CAM_FLOATS floats.
 __device__ __forceinline__ ViewSample project_view(const float* __restrict__ cam, float gx, float gy, float gz,
-                                                   float img_w, float img_h, float hm_w, float hm_h) {
+                                                   float img_w, float img_h, float cfg_w, float cfg_h,
+                                                   float hm_w, float hm_h) {
   const float dx = __fsub_rn(gx, cam[9]);
   const float dy = __fsub_rn(gy, cam[10]);
   const float dz = __fsub_rn(gz, cam[11]);
@@ -57,10 +58,10 @@ __device__ __forceinline__ ViewSample project_view(const float* __restrict__ cam
   float qx = __fadd_rn(__fadd_rn(__fmul_rn(cam[21], px), __fmul_rn(cam[22], py)), cam[23]);
   const float qy = __fadd_rn(__fadd_rn(__fmul_rn(cam[24], px), __fmul_rn(cam[25], py)), cam[26]);
   if (cam[29] != 0.0f) qx = __fsub_rn(img_w, qx);
-  const float uu = __fdiv_rn(__fmul_rn(qx, hm_w), img_w);
-  const float vv = __fdiv_rn(__fmul_rn(qy, hm_h), img_h);
-  float sx = __fsub_rn(__fmul_rn(__fdiv_rn(uu, __fsub_rn(hm_w, 1.0f)), 2.0f), 1.0f);
-  float sy = __fsub_rn(__fmul_rn(__fdiv_rn(vv, __fsub_rn(hm_h, 1.0f)), 2.0f), 1.0f);
+  const float uu = __fdiv_rn(__fmul_rn(qx, cfg_w), img_w);
+  const float vv = __fdiv_rn(__fmul_rn(qy, cfg_h), img_h);
+  float sx = __fsub_rn(__fmul_rn(__fdiv_rn(uu, __fsub_rn(cfg_w, 1.0f)), 2.0f), 1.0f);
+  float sy = __fsub_rn(__fmul_rn(__fdiv_rn(vv, __fsub_rn(cfg_h, 1.0f)), 2.0f), 1.0f);
   sx = (sx != sx) ? sx : fminf(fmaxf(sx, -1.1f), 1.1f);
   sy = (sy != sy) ? sy : fminf(fmaxf(sy, -1.1f), 1.1f);
   // grid_sample(align_corners=True) un-normalisation
@@ -129,7 +130,8 @@ __global__ void __launch_bounds__(kUnprojThreads) unproject_kernel(const sp3d_un
     for (int j = 0; j < kChanGroup; ++j) num[j] = 0.0f;
     float den = 0.0f;
     for (int v = a.view_begin; v < a.view_end; ++v) {
-      const ViewSample s = project_view(s_cam + v * SP3D_CAM_FLOATS, gx, gy, gz, a.img_w, a.img_h, hm_w, hm_h);
+      const ViewSample s = project_view(s_cam + v * SP3D_CAM_FLOATS, gx, gy, gz, a.img_w, a.img_h, a.hm_cfg_w,
+                                          a.hm_cfg_h, hm_w, hm_h);
       den = __fadd_rn(den, s.m);
       if (s.m == 0.0f) continue;  // masked views contribute exact zeros
       const float* hm = a.heatmaps[v] + (int64_t)sample * a.hm_stride_b + (int64_t)c0 * a.hm_stride_c;
@@ -200,7 +202,9 @@ __global__ void unproject_finalize_kernel(const sp3d_unproject_finalize_args a) 
 
 extern "C" int sp3d_unproject_fwd(const sp3d_unproject_args* a, void* stream) {
   using namespace sp3d;
-  if (a == nullptr || a->V < 1 || a->V > SP3D_MAX_VIEWS || a->C < 1 || a->n_cubes < 0 || a->cubes == nullptr ||
+  if (a == nullptr || a->n_cubes < 0) return SP3D_ERR_INVALID_ARG;
+  if (a->n_cubes == 0) return SP3D_OK;  // nothing to fill (no valid proposal): pointers may be null
+  if (a->V < 1 || a->V > SP3D_MAX_VIEWS || a->C < 1 || a->cubes == nullptr ||
       a->cams == nullptr || a->centers == nullptr || a->lin_x == nullptr || a->lin_y == nullptr ||
       a->lin_z == nullptr || a->center_stride < 3 || a->cubes_per_sample < 1 || a->view_begin < 0 ||
       a->view_end > a->V || a->view_begin > a->view_end || (a->check_flag && a->center_stride < 4))
@@ -208,7 +212,6 @@ extern "C" int sp3d_unproject_fwd(const sp3d_unproject_args* a, void* stream) {
   for (int v = a->view_begin; v < a->view_end; ++v)
     if (a->heatmaps[v] == nullptr) return SP3D_ERR_INVALID_ARG;
   if (a->out_dtype != SP3D_F32 && a->out_dtype != SP3D_BF16) return SP3D_ERR_UNSUPPORTED;
-  if (a->n_cubes == 0) return SP3D_OK;
   const int N = a->X * a->Y * a->Z;
   if (N <= 0 || a->n_cubes > 65535) return SP3D_ERR_INVALID_ARG;
   bool cl = a->hm_stride_c == 1 && (a->hm_stride_w % 4) == 0 && (a->hm_stride_h % 4) == 0 && (a->hm_stride_b % 4) == 0;

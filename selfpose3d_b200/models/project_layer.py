@@ -71,13 +71,11 @@ class ProjectLayer(nn.Module):
         dev = hms[0].device
         cubes = torch.empty(n_cubes, X, Y, Z, pitch, device=dev, dtype=dtype)
         grids = torch.empty(n_cubes, X * Y * Z, 3, device=dev, dtype=torch.float32) if want_grids else None
-        w, h = int(self.heatmap_size[0]), int(self.heatmap_size[1])
-        if tuple(hms[0].shape[2:]) != (h, w):
-            raise ValueError("heat-maps are %s but cfg.NETWORK.HEATMAP_SIZE says [w,h]=%s"
-                             % (tuple(hms[0].shape[2:]), (w, h)))
-        ops.unproject(hms, st, cams, centers, grid_size, (X, Y, Z), self.img_size, (h, w), C,
+        # scaling uses cfg.NETWORK.HEATMAP_SIZE, sampling the tensor's own extent -- as the reference (:50,84-93)
+        ops.unproject(hms, st, cams, centers, grid_size, (X, Y, Z), self.img_size, tuple(hms[0].shape[2:]), C,
                       cubes, (X * Y * Z * pitch, 1, pitch), out_c_pad=pitch, check_flag=check_flag,
-                      cubes_per_sample=cubes_per_sample, cube_sample=cube_sample, grids=grids)
+                      cubes_per_sample=cubes_per_sample, cube_sample=cube_sample, grids=grids,
+                      heatmap_cfg_wh=self.heatmap_size)
         return cubes, grids
 
     def get_voxel(self, heatmaps, meta, grid_size, grid_center, cube_size, flip_xcoords=None):
@@ -89,9 +87,9 @@ class ProjectLayer(nn.Module):
         hms, st = _common_strides(heatmaps)
         cubes = torch.empty(B, C, X, Y, Z, device=device, dtype=torch.float32)   # the reference's NCDHW layout
         grids = torch.empty(B, X * Y * Z, 3, device=device, dtype=torch.float32)
-        w, h = int(self.heatmap_size[0]), int(self.heatmap_size[1])
-        ops.unproject(hms, st, cams, centers, grid_size, (X, Y, Z), self.img_size, (h, w), C,
-                      cubes, (C * X * Y * Z, X * Y * Z, 1), check_flag=check, grids=grids)
+        ops.unproject(hms, st, cams, centers, grid_size, (X, Y, Z), self.img_size, tuple(hms[0].shape[2:]), C,
+                      cubes, (C * X * Y * Z, X * Y * Z, 1), check_flag=check, grids=grids,
+                      heatmap_cfg_wh=self.heatmap_size)
         return cubes, grids
 
     def forward(self, heatmaps, meta, grid_size, grid_center, cube_size, flip_xcoords=None):

@@ -89,7 +89,7 @@ def linspace_axes(grid_size, cube_size, device):
 # --------------------------------------------------------------------------------------------- K1
 def unproject(heatmaps, hm_strides, cams, centers, grid_size, cube_size, image_size, heatmap_hw, channels,
               out, out_strides, out_c_pad=0, check_flag=False, cubes_per_sample=1, cube_sample=None,
-              grids=None, view_range=None, partial=False):
+              grids=None, view_range=None, partial=False, heatmap_cfg_wh=None):
     """Launch the fused un-projection.
 
     heatmaps: list[V] of CUDA float32 tensors sharing ``hm_strides = (b, c, h, w)`` element strides.
@@ -117,6 +117,9 @@ def unproject(heatmaps, hm_strides, cams, centers, grid_size, cube_size, image_s
     a.n_cubes = int(centers.shape[0])
     a.X, a.Y, a.Z = [int(s) for s in cube_size]
     a.img_w, a.img_h = float(image_size[0]), float(image_size[1])
+    if heatmap_cfg_wh is None:
+        heatmap_cfg_wh = (a.w, a.h)
+    a.hm_cfg_w, a.hm_cfg_h = float(heatmap_cfg_wh[0]), float(heatmap_cfg_wh[1])
     a.view_begin, a.view_end = (0, V) if view_range is None else (int(view_range[0]), int(view_range[1]))
     a.partial = int(bool(partial))
     a.cubes = out.data_ptr()

@@ -39,6 +39,8 @@ def test_struct_sizes_match_header_layout():
 def test_invalid_arguments_are_rejected_without_a_gpu():
     lib = _lib.load()
     a = _lib.UnprojectArgs()
+    assert lib.sp3d_unproject_fwd(ctypes.byref(a), None) == 0      # n_cubes == 0: nothing to do
+    a.n_cubes = 1
     assert lib.sp3d_unproject_fwd(ctypes.byref(a), None) == -1
     n = _lib.NmsTopkArgs()
     assert lib.sp3d_nms_topk3d(ctypes.byref(n), None) == -1
