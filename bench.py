@@ -167,6 +167,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     _lib.load()
+    ops.set_volume_dtype(torch.bfloat16 if args.volume_dtype == "bf16" else torch.float32)
     cfg = make_cfg(BATCH)
     model = multi_person_posenet_ssv.get_multi_person_pose_net(cfg, is_train=False)
     model.load_state_dict(synthetic.trained_like_state_dict(model, seed=0), strict=True)
@@ -250,7 +251,10 @@ def run_ours(args, rank, world, local_rank):
     line = {
         "metric": "frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(BATCH),
+        "vs_baseline": None, "dtype": "bf16" if args.volume_dtype == "bf16" else "f32",
+        "dtype_detail": ("V2V 3-D convolutions: bf16 operands, float32 accumulation (tcgen05); backbone, un-projection "
+                         "geometry, NMS, soft-argmax: float32") if args.volume_dtype == "bf16" else "float32 everywhere",
+        "data": "synthetic", "config": workload_config(BATCH),
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
@@ -272,6 +276,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--volume-dtype", default="bf16", choices=["f32", "bf16"],
+                    help="voxel-cube / V2V activation dtype: bf16 = tcgen05 tensor-core convolutions with float32 "
+                         "accumulation, f32 = float32 SIMT convolutions (bit-faithful parity path)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -150,7 +150,7 @@ def check(status, what):
         raise Sp3dError("%s failed: %s%s" % (what, msg, (" [" + cuda + "]") if cuda else ""))
 
 
-def call(name, args, stream, launches=1, kind=None, work=0.0):
+def call(name, args, stream, launches=1, kind=None, work=0.0, detail=None):
     """Invoke ``sp3d_<name>(&args, stream)`` and raise on a non-zero status.
 
     ``kind`` / ``work`` tag the launch (kernel family, algorithmic FLOPs or bytes) for
@@ -163,4 +163,4 @@ def call(name, args, stream, launches=1, kind=None, work=0.0):
     check(status, name)
     launch_count += launches
     if start is not None:
-        profiler.end(kind or name, start, work)
+        profiler.end(kind or name, start, work, detail)

@@ -261,6 +261,47 @@ __global__ void maxpool_f32_kernel(const sp3d_maxpool_args a) {
   }
 }
 
+// bf16 variant: 8 channels per 16-byte vector
+__global__ void maxpool_bf16_kernel(const sp3d_maxpool_args a) {
+  const int cvec = a.c_pitch / 8;
+  const int64_t total = (int64_t)a.N * a.OD * a.OH * a.OW * cvec;
+  const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(a.in);
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    int64_t pos = i / cvec;
+    const int ow = (int)(pos % a.OW); pos /= a.OW;
+    const int oh = (int)(pos % a.OH); pos /= a.OH;
+    const int od = (int)(pos % a.OD);
+    const int n = (int)(pos / a.OD);
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    for (int kd = 0; kd < a.k[0]; ++kd) {
+      const int id = od * a.s[0] - a.p[0] + kd;
+      if (id < 0 || id >= a.D) continue;
+      for (int kh = 0; kh < a.k[1]; ++kh) {
+        const int ih = oh * a.s[1] - a.p[1] + kh;
+        if (ih < 0 || ih >= a.H) continue;
+        for (int kw = 0; kw < a.k[2]; ++kw) {
+          const int iw = ow * a.s[2] - a.p[2] + kw;
+          if (iw < 0 || iw >= a.W) continue;
+          const uint4 q = __ldg(reinterpret_cast<const uint4*>(
+              in + ((((int64_t)n * a.D + id) * a.H + ih) * a.W + iw) * a.c_pitch + cv * 8));
+          const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&q);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], __bfloat162float(h[j]));
+        }
+      }
+    }
+    __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(m[j]);
+    *reinterpret_cast<uint4*>(out + ((((int64_t)n * a.OD + od) * a.OH + oh) * a.OW + ow) * a.c_pitch + cv * 8) =
+        *reinterpret_cast<const uint4*>(o);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ layout
 // [N, C, S] <-> [N, S, c_pitch] through a 32x32 shared-memory transpose tile.
 template <typename SrcT, typename DstT>
@@ -315,15 +356,17 @@ static int launch_layout(const sp3d_layout_args* a, cudaStream_t st) {
 
 extern "C" int sp3d_maxpool_fwd(const sp3d_maxpool_args* a, void* stream) {
   using namespace sp3d;
-  if (a == nullptr || a->in == nullptr || a->out == nullptr || a->N < 0 || a->C < 1 || (a->c_pitch % 4) != 0 ||
-      a->c_pitch < a->C)
+  if (a == nullptr || a->in == nullptr || a->out == nullptr || a->N < 0 || a->C < 1 || a->c_pitch < a->C)
     return SP3D_ERR_INVALID_ARG;
-  if (a->dtype != SP3D_F32) return SP3D_ERR_UNSUPPORTED;
-  const int64_t total = (int64_t)a->N * a->OD * a->OH * a->OW * (a->c_pitch / 4);
+  if (a->dtype != SP3D_F32 && a->dtype != SP3D_BF16) return SP3D_ERR_UNSUPPORTED;
+  const int vec = a->dtype == SP3D_F32 ? 4 : 8;
+  if ((a->c_pitch % vec) != 0) return SP3D_ERR_INVALID_ARG;
+  const int64_t total = (int64_t)a->N * a->OD * a->OH * a->OW * (a->c_pitch / vec);
   if (total == 0) return SP3D_OK;
   const int64_t want = (total + 255) / 256;
   const int blocks = (int)(want < 148 * 32 ? want : 148 * 32);
-  maxpool_f32_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
+  if (a->dtype == SP3D_F32) maxpool_f32_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
+  else maxpool_bf16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
   return check_launch();
 }
 

@@ -1,6 +1,389 @@
-// K2/K5 (tensor-core form) -- placeholder dispatcher until the tcgen05 kernels land.
+// K2 (tensor-core form) -- stride-1 3-D convolution as an im2col-free implicit GEMM on tcgen05.
+//
+// One persistent CTA per SM walks output bricks of TX x 16 x 8 voxels (x, y, z; z fastest).
+//   * warp 0 (1 thread)  : TMA-loads the brick's input HALO ((TX+k-1) x (16+k-1) x (8+k-1) voxels x <=64
+//                          channels, bf16, channel-last) as ONE 5-D tiled box with hardware swizzle and
+//                          out-of-bounds zero fill (= the convolution's zero padding), double buffered;
+//   * warp 1 (1 thread)  : streams the packed weights of one tap per stage through a small TMA ring;
+//   * warps 2,3 (1 thread each): issue tcgen05.mma.  A tap (dx,dy,dz) is NOT a new load: it is the same
+//                          shared-memory halo with the A-descriptor start address moved by
+//                          ((dx*HY + dy)*HZ + dz) rows and SBO = HZ rows (8 consecutive z voxels form a
+//                          core-matrix group, 16 y values form the 128 rows of M).  Verified on B200 by
+//                          csrc/probe/tc_probe.cu: the swizzle is a function of the absolute smem address,
+//                          so row-shifted starts with base_offset = 0 address the right data.
+//                          Accumulators (TX tiles x N fp32 columns, double buffered) live in TMEM;
+//   * warps 4..7         : epilogue.  tcgen05.ld the accumulator row of "their" voxel, apply folded
+//                          BatchNorm scale/shift, optional residual and ReLU, convert, store channel-last.
+//
+// Reference semantics: cudnn conv3d / conv_transpose3d(k2,s2) + batch_norm(eval) + relu (+ add) as wired in
+// lib/models/v2v_net.py:10-69,124.
 #include "sp3d_common.cuh"
+#include "tc_common.cuh"
+#include <cuda.h>
 
 namespace sp3d {
-int conv_tc(const sp3d_conv_args*, cudaStream_t) { return SP3D_ERR_UNSUPPORTED; }
+
+using namespace tc;
+
+constexpr int kTcThreads = 256;
+constexpr int kWStages = 4;
+constexpr int kBY = 16, kBZ = 8;   // brick extent in y and z: 128 rows of M = 16 groups of 8 z-voxels
+
+struct TcConvParams {
+  int n_cubes, X, Y, Z;          // input spatial extent (= virtual output grid; stride 1)
+  int bricks_x, bricks_y, bricks_z, n_bricks;
+  int n_chunks;                  // K chunks of (RB / 2) channels
+  int cout, cout_pitch;          // channels stored / distance between output positions (elements)
+  int TD, TH, TW;                // full output tensor extent
+  int ostride, ooff[3];          // output position = o * ostride + ooff (transposed-conv phases)
+  int relu;
+  int out_f32;                   // 1: store float32, 0: bf16
+  const float* scale;
+  const float* shift;
+  const void* residual;          // same dtype / addressing as out
+  void* out;
+};
+
+template <int KS, int RB, int N, int TX>
+struct TcCfg {
+  static constexpr int P = KS / 2;
+  static constexpr int HX = TX + KS - 1, HY = kBY + KS - 1, HZ = kBZ + KS - 1;
+  static constexpr int kHaloRows = HX * HY * HZ;
+  static constexpr int kHaloBytes = kHaloRows * RB;
+  static constexpr int kHaloStride = (kHaloBytes + 1023) / 1024 * 1024;
+  static constexpr int kWBytes = N * RB;
+  static constexpr int kWStride = (kWBytes + 1023) / 1024 * 1024;
+  static constexpr int kSmemBytes = 2 * kHaloStride + kWStages * kWStride + 1024;   // + alignment slack
+  static constexpr int kTaps = KS * KS * KS;
+  static constexpr int kKSteps = RB / 32;       // tcgen05.mma K = 16 bf16 = 32 bytes
+  static constexpr int kIssuers = TX >= 2 ? 2 : 1;
+  static constexpr uint32_t kLayout = RB == 128 ? kSwizzle128 : (RB == 64 ? kSwizzle64 : kSwizzle32);
+  static_assert(2 * TX * N <= 512, "accumulators exceed TMEM");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+};
+
+template <int KS, int RB, int N, int TX>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
+                 const TcConvParams p) {
+  using C = TcCfg<KS, RB, N, TX>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t halo_full[2], halo_empty[2], w_full[kWStages], w_empty[kWStages], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_scale[N], s_shift[N];
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* halo = smem;                               // [2][kHaloStride]
+  uint8_t* wbuf = smem + 2 * C::kHaloStride;          // [kWStages][kWStride]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&halo_full[i], 1);
+      mbar_init(&halo_empty[i], C::kIssuers);
+      mbar_init(&acc_full[i], C::kIssuers);
+      mbar_init(&acc_empty[i], 128);
+    }
+    for (int i = 0; i < kWStages; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], C::kIssuers);
+    }
+    fence_barrier_init();
+  }
+  for (int i = tid; i < N; i += kTcThreads) {
+    s_scale[i] = (p.scale != nullptr && i < p.cout) ? p.scale[i] : 1.0f;
+    s_shift[i] = (p.shift != nullptr && i < p.cout) ? p.shift[i] : 0.0f;
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  if (warp == 1 && lane == 0) {
+    tma_prefetch_desc(&map_in);
+    tma_prefetch_desc(&map_w);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  auto brick_coords = [&](int b, int& n, int& x0, int& y0, int& z0) {
+    const int bz = b % p.bricks_z;
+    const int by = (b / p.bricks_z) % p.bricks_y;
+    const int bx = (b / (p.bricks_z * p.bricks_y)) % p.bricks_x;
+    n = b / (p.bricks_z * p.bricks_y * p.bricks_x);
+    x0 = bx * TX; y0 = by * kBY; z0 = bz * kBZ;
+  };
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ halo producer
+    uint32_t u = 0;
+    for (int b = blockIdx.x; b < p.n_bricks; b += gridDim.x) {
+      int n, x0, y0, z0;
+      brick_coords(b, n, x0, y0, z0);
+      for (int c = 0; c < p.n_chunks; ++c, ++u) {
+        const uint32_t buf = u & 1;
+        mbar_wait(&halo_empty[buf], ((u >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&halo_full[buf], C::kHaloBytes);
+        tma_load_5d(halo + buf * C::kHaloStride, &map_in, &halo_full[buf], c * (RB / 2), z0 - C::P, y0 - C::P,
+                    x0 - C::P, n);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ weight producer (one tap per stage)
+    uint32_t w = 0;
+    for (int b = blockIdx.x; b < p.n_bricks; b += gridDim.x) {
+      for (int c = 0; c < p.n_chunks; ++c) {
+        for (int tap = 0; tap < C::kTaps; ++tap, ++w) {
+          const uint32_t st = w % kWStages;
+          mbar_wait(&w_empty[st], ((w / kWStages) & 1) ^ 1);
+          mbar_arrive_expect_tx(&w_full[st], C::kWBytes);
+          tma_load_2d(wbuf + st * C::kWStride, &map_w, &w_full[st], 0, (tap * p.n_chunks + c) * N);
+        }
+      }
+    }
+  } else if ((warp == 2 || warp == 3) && lane == 0 && (warp - 2) < C::kIssuers) {
+    // ------------------------------------------------------------------ MMA issuers
+    const int q = warp - 2;
+    const uint32_t idesc = make_idesc(kFmtBF16, 128, N);
+    const uint64_t a_desc0 = make_smem_desc(smem_u32(halo), 0, C::HZ * RB, C::kLayout);
+    const uint64_t b_desc0 = make_smem_desc(smem_u32(wbuf), 0, 8 * RB, C::kLayout);
+    uint32_t u = 0, w = 0, it = 0;
+    for (int b = blockIdx.x; b < p.n_bricks; b += gridDim.x, ++it) {
+      const uint32_t accbuf = it & 1;
+      mbar_wait(&acc_empty[accbuf], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int c = 0; c < p.n_chunks; ++c, ++u) {
+        const uint32_t buf = u & 1;
+        mbar_wait(&halo_full[buf], (u >> 1) & 1);
+        const uint64_t a_desc = a_desc0 + (uint64_t)((buf * C::kHaloStride) >> 4);
+        for (int tap = 0; tap < C::kTaps; ++tap, ++w) {
+          const uint32_t st = w % kWStages;
+          mbar_wait(&w_full[st], (w / kWStages) & 1);
+          tc_fence_after();
+          const int dz = tap % KS, dy = (tap / KS) % KS, dx = tap / (KS * KS);
+          const uint64_t b_desc = b_desc0 + (uint64_t)((st * C::kWStride) >> 4);
+          const uint32_t tap_rows = (uint32_t)((dx * C::HY + dy) * C::HZ + dz);
+#pragma unroll
+          for (int t = q; t < TX; t += C::kIssuers) {
+            const uint64_t a_tile = a_desc + (uint64_t)(((tap_rows + (uint32_t)(t * C::HY * C::HZ)) * RB) >> 4);
+            const uint32_t d_tmem = tmem_base + (accbuf * TX + t) * N;
+#pragma unroll
+            for (int k = 0; k < C::kKSteps; ++k)
+              mma_f16_ss(d_tmem, a_tile + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                         (c | tap | k) ? 1u : 0u);
+          }
+          mma_commit(&w_empty[st]);
+        }
+        mma_commit(&halo_empty[buf]);
+      }
+      mma_commit(&acc_full[accbuf]);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (thread <-> accumulator row)
+    const int row = tid - 128;                 // 0..127 = TMEM lane
+    const int ly = row >> 3, lz = row & 7;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t it = 0;
+    for (int b = blockIdx.x; b < p.n_bricks; b += gridDim.x, ++it) {
+      int n, x0, y0, z0;
+      brick_coords(b, n, x0, y0, z0);
+      const uint32_t accbuf = it & 1;
+      mbar_wait(&acc_full[accbuf], (it >> 1) & 1);
+      tc_fence_after();
+      const int y = y0 + ly, z = z0 + lz;
+#pragma unroll
+      for (int t = 0; t < TX; ++t) {
+        const int x = x0 + t;
+        const bool in_range = (x < p.X) && (y < p.Y) && (z < p.Z);
+        const int64_t pos = (((int64_t)n * p.TD + (x * p.ostride + p.ooff[0])) * p.TH + (y * p.ostride + p.ooff[1])) * p.TW +
+                            (z * p.ostride + p.ooff[2]);
+        const uint32_t taddr = tmem_base + lane_base + (accbuf * TX + t) * N;
+#pragma unroll
+        for (int n0 = 0; n0 < N; n0 += 16) {
+          uint32_t v[16];
+          tmem_ld_x16(taddr + n0, v);      // warp-collective: every lane takes part, stores are predicated
+          tmem_ld_wait();
+          if (!in_range) continue;
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float r = __uint_as_float(v[j]) * s_scale[n0 + j] + s_shift[n0 + j];
+            if (p.relu == 2) r = fmaxf(r, 0.0f);
+            f[j] = r;
+          }
+          if (p.out_f32) {
+            float* o = reinterpret_cast<float*>(p.out) + pos * p.cout_pitch + n0;
+            const float* rs = p.residual ? reinterpret_cast<const float*>(p.residual) + pos * p.cout_pitch + n0 : nullptr;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (n0 + j < p.cout_pitch) {
+                float r = f[j];
+                if (rs) r += rs[j];
+                if (p.relu == 1) r = fmaxf(r, 0.0f);
+                o[j] = (n0 + j < p.cout) ? r : 0.0f;
+              }
+            }
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pos * p.cout_pitch + n0;
+            const __nv_bfloat16* rs =
+                p.residual ? reinterpret_cast<const __nv_bfloat16*>(p.residual) + pos * p.cout_pitch + n0 : nullptr;
+            if (n0 + 16 <= p.cout_pitch && (p.cout_pitch & 7) == 0) {   // full group of 16 channels: two 16-byte stores
+              uint4 rv[2];
+              if (rs) {
+                rv[0] = *reinterpret_cast<const uint4*>(rs);
+                rv[1] = *reinterpret_cast<const uint4*>(rs + 8);
+              }
+              const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(rv);
+              __align__(16) __nv_bfloat16 ob[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float r = f[j];
+                if (rs) r += __bfloat162float(rb[j]);
+                if (p.relu == 1) r = fmaxf(r, 0.0f);
+                ob[j] = __float2bfloat16_rn((n0 + j < p.cout) ? r : 0.0f);
+              }
+              *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(ob);
+              *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<const uint4*>(ob + 8);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (n0 + j < p.cout_pitch) {
+                  float r = f[j];
+                  if (rs) r += __bfloat162float(rs[j]);
+                  if (p.relu == 1) r = fmaxf(r, 0.0f);
+                  o[j] = __float2bfloat16_rn((n0 + j < p.cout) ? r : 0.0f);
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[accbuf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    cudaDriverEntryPointQueryResult q;
+    void* ptr = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for(int rb) {
+  return rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+template <int KS, int RB, int N, int TX>
+static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
+  using C = TcCfg<KS, RB, N, TX>;
+  EncodeTiledFn encode = get_encode();
+  if (encode == nullptr) return SP3D_ERR_UNSUPPORTED;
+  const int chunk_ch = RB / 2;
+  const int n_chunks = (a->cin + chunk_ch - 1) / chunk_ch;
+
+  CUtensorMap map_in, map_w;
+  {  // activations: [N][X][Y][Z][cin_pitch] bf16, box = {chunk, HZ, HY, HX, 1}
+    cuuint64_t gdim[5] = {(cuuint64_t)a->cin_pitch, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->D, (cuuint64_t)a->N};
+    cuuint64_t gstr[4] = {(cuuint64_t)a->cin_pitch * 2, (cuuint64_t)a->cin_pitch * 2 * a->W,
+                          (cuuint64_t)a->cin_pitch * 2 * a->W * a->H, (cuuint64_t)a->cin_pitch * 2 * a->W * a->H * a->D};
+    cuuint32_t box[5] = {(cuuint32_t)chunk_ch, (cuuint32_t)C::HZ, (cuuint32_t)C::HY, (cuuint32_t)C::HX, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    if (encode(&map_in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(a->in), gdim, gstr, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(RB), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return SP3D_ERR_INVALID_ARG;
+  }
+  {  // weights: [taps * n_chunks * N rows][chunk channels] bf16 (K-major rows), box = {chunk, N}
+    cuuint64_t gdim[2] = {(cuuint64_t)chunk_ch, (cuuint64_t)C::kTaps * n_chunks * N};
+    cuuint64_t gstr[1] = {(cuuint64_t)RB};
+    cuuint32_t box[2] = {(cuuint32_t)chunk_ch, (cuuint32_t)N};
+    cuuint32_t es[2] = {1, 1};
+    if (encode(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a->weight), gdim, gstr, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(RB), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return SP3D_ERR_INVALID_ARG;
+  }
+  TcConvParams p{};
+  p.n_cubes = a->N; p.X = a->D; p.Y = a->H; p.Z = a->W;
+  p.bricks_x = (a->D + TX - 1) / TX;
+  p.bricks_y = (a->H + kBY - 1) / kBY;
+  p.bricks_z = (a->W + kBZ - 1) / kBZ;
+  p.n_bricks = a->N * p.bricks_x * p.bricks_y * p.bricks_z;
+  p.n_chunks = n_chunks;
+  p.cout = a->cout; p.cout_pitch = a->cout_pitch;
+  p.TD = a->TD; p.TH = a->TH; p.TW = a->TW;
+  p.ostride = a->ostride[0];
+  p.ooff[0] = a->ooffset[0]; p.ooff[1] = a->ooffset[1]; p.ooff[2] = a->ooffset[2];
+  p.relu = a->relu;
+  p.out_f32 = a->out_dtype == SP3D_F32;
+  p.scale = a->scale; p.shift = a->shift; p.residual = a->residual; p.out = a->out;
+
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  auto kern = conv3d_tc_kernel<KS, RB, N, TX>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+  if (e != cudaSuccess) { set_last_error(e); return SP3D_ERR_LAUNCH; }
+  const int grid = p.n_bricks < n_sm ? p.n_bricks : n_sm;
+  kern<<<grid, kTcThreads, C::kSmemBytes, st>>>(map_in, map_w, p);
+  return check_launch();
+}
+
+// Shapes taken by the tensor-core path (everything V2VNet needs).  cin here is the padded channel count.
+int conv_tc(const sp3d_conv_args* a, cudaStream_t st) {
+  if (a->algo != SP3D_CONV_TC_BF16) return SP3D_ERR_UNSUPPORTED;   // TF32x3 variant: not built yet
+  if (a->in_dtype != SP3D_BF16) return SP3D_ERR_UNSUPPORTED;
+  if (a->out_dtype != SP3D_BF16 && a->out_dtype != SP3D_F32) return SP3D_ERR_UNSUPPORTED;
+  const int ks = a->ksize[0];
+  if (a->ksize[1] != ks || a->ksize[2] != ks) return SP3D_ERR_UNSUPPORTED;
+  for (int d = 0; d < 3; ++d) {
+    if (a->stride[d] != 1 || a->tap_step[d] != 1 || a->tap_off0[d] != -(ks / 2)) return SP3D_ERR_UNSUPPORTED;
+    if (a->ostride[d] != a->ostride[0]) return SP3D_ERR_UNSUPPORTED;
+  }
+  if (a->OD != a->D || a->OH != a->H || a->OW != a->W) return SP3D_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(a->in) % 16) || (reinterpret_cast<uintptr_t>(a->weight) % 16) ||
+      (reinterpret_cast<uintptr_t>(a->out) % 16) || (a->cin_pitch % 8))
+    return SP3D_ERR_INVALID_ARG;
+  const int cin = a->cin, n = a->cout_pitch_w;   // packed weight rows per tap = N of the MMA
+  if (a->cout > n) return SP3D_ERR_INVALID_ARG;
+#define SP3D_TC_CASE(KS_, CIN_, RB_, N_, TX_) \
+  if (ks == KS_ && cin == CIN_ && n == N_) return launch_tc<KS_, RB_, N_, TX_>(a, st);
+  SP3D_TC_CASE(7, 16, 32, 16, 2)
+  SP3D_TC_CASE(3, 16, 32, 32, 4)
+  SP3D_TC_CASE(3, 32, 64, 32, 4)
+  SP3D_TC_CASE(3, 32, 64, 64, 4)
+  SP3D_TC_CASE(3, 64, 128, 64, 2)
+  SP3D_TC_CASE(3, 64, 128, 128, 1)
+  SP3D_TC_CASE(3, 128, 128, 128, 1)
+  SP3D_TC_CASE(1, 16, 32, 32, 4)
+  SP3D_TC_CASE(1, 32, 64, 64, 4)
+  SP3D_TC_CASE(1, 64, 128, 128, 2)
+  SP3D_TC_CASE(1, 32, 64, 16, 4)
+  SP3D_TC_CASE(1, 128, 128, 64, 4)
+  SP3D_TC_CASE(1, 64, 128, 32, 4)
+#undef SP3D_TC_CASE
+  return SP3D_ERR_UNSUPPORTED;
+}
+
 }  // namespace sp3d

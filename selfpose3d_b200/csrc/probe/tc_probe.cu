@@ -231,6 +231,80 @@ static int run_case(const Case& c, bool verbose) {
   return bad == 0 ? 0 : 1;
 }
 
+
+// ---------------------------------------------------------------------------------------------- issue-rate probe
+// `issuers` warps each issue repeat*8 MMAs (compile-time unrolled descriptor offsets) into their own accumulator.
+template <int N, bool TF32>
+__global__ void __launch_bounds__(128) rate_kernel(uint32_t layout_type, uint32_t row_bytes, int issuers, int repeat,
+                                                   long long* __restrict__ cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar[4];
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t a_bytes = 128 * row_bytes, b_bytes = N * row_bytes;
+  for (uint32_t i = tid * 16; i < a_bytes + b_bytes + 1024; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = tmem_base + (uint32_t)warp * (N >= 128 ? 128 : N);
+  const uint32_t base = smem_u32(smem);
+  const uint32_t b_base = base + ((a_bytes + 1023) & ~1023u);
+  const uint32_t idesc = make_idesc(TF32 ? kFmtTF32 : kFmtBF16, 128, N);
+  const uint64_t da = make_smem_desc(base, 0, 8 * row_bytes, layout_type);
+  const uint64_t db = make_smem_desc(b_base, 0, 8 * row_bytes, layout_type);
+  const int ksteps = row_bytes / 32;   // MMAs per swizzled row
+  long long t0 = clock64();
+  if (warp < issuers && lane == 0) {
+    for (int r = 0; r < repeat; ++r) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint64_t off = (uint64_t)((j % ksteps) * 2);
+        if (TF32) mma_tf32_ss(tm, da + off, db + off, idesc, 1u);
+        else mma_f16_ss(tm, da + off, db + off, idesc, 1u);
+      }
+    }
+    mma_commit(&bar[warp]);
+    mbar_wait(&bar[warp], 0);
+    cycles[warp] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+template <int N, bool TF32>
+static void run_rate(const char* name, uint32_t layout_type, uint32_t row_bytes) {
+  long long* d_cyc;
+  CK(cudaMalloc(&d_cyc, 32));
+  CK(cudaFuncSetAttribute(rate_kernel<N, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  for (int issuers : {1, 2, 4}) {
+    if (issuers * (N >= 128 ? 128 : N) > 512) continue;
+    const int repeat = 256;
+    CK(cudaMemset(d_cyc, 0, 32));
+    rate_kernel<N, TF32><<<1, 128, 128 * row_bytes + N * row_bytes + 4096, 0>>>(layout_type, row_bytes, issuers, repeat, d_cyc);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("rate kernel failed: %s\n", cudaGetErrorString(e)); exit(3); }
+    long long cyc[4];
+    CK(cudaMemcpy(cyc, d_cyc, 32, cudaMemcpyDeviceToHost));
+    long long mx = 0;
+    for (int i = 0; i < issuers; ++i) mx = cyc[i] > mx ? cyc[i] : mx;
+    const double per = (double)mx / (repeat * 8);
+    const int kk = TF32 ? 8 : 16;
+    printf("rate2 %-18s N=%3d issuers=%d : %7.1f cycles per MMA per issuer, %6.1f MACs/cycle/SM (floor %d cyc)\n", name, N,
+           issuers, per, issuers * 128.0 * N * kk / per, 128 * N / 256 * (TF32 ? 1 : 1));
+  }
+  cudaFree(d_cyc);
+}
+
 // ---------------------------------------------------------------------------------------------- TMA probe
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -327,6 +401,20 @@ static int run_tma(uint32_t layout_type, int C, bool overlap_probe) {
 int main(int argc, char** argv) {
   int fails = 0;
   const bool timing = argc > 1 && !strcmp(argv[1], "timing");
+  if (argc > 1 && !strcmp(argv[1], "rate2")) {
+    run_rate<16, false>("bf16 SW128", kSwizzle128, 128);
+    run_rate<32, false>("bf16 SW128", kSwizzle128, 128);
+    run_rate<64, false>("bf16 SW128", kSwizzle128, 128);
+    run_rate<128, false>("bf16 SW128", kSwizzle128, 128);
+    run_rate<256, false>("bf16 SW128", kSwizzle128, 128);
+    run_rate<16, false>("bf16 SW32", kSwizzle32, 32);
+    run_rate<32, false>("bf16 SW64", kSwizzle64, 64);
+    run_rate<16, true>("tf32 SW128", kSwizzle128, 128);
+    run_rate<32, true>("tf32 SW128", kSwizzle128, 128);
+    run_rate<64, true>("tf32 SW128", kSwizzle128, 128);
+    run_rate<128, true>("tf32 SW128", kSwizzle128, 128);
+    return 0;
+  }
   if (!timing) {
     // 1. plain tiles
     Case basic[] = {

@@ -64,8 +64,10 @@ class PoseRegressionNet(nn.Module):
         X, Y, Z = [int(s) for s in self.cube_size]
         for s in range(0, n, chunk):
             e = min(n, s + chunk)
+            bf16 = ops.volume_dtype() == torch.bfloat16
             cubes, _ = self.project_layer.project_cl(all_heatmaps, cams, centers[s:e], False, self.grid_size,
-                                                     self.cube_size, cube_sample=cube_sample[s:e])
+                                                     self.cube_size, cube_sample=cube_sample[s:e],
+                                                     dtype=ops.volume_dtype(), c_pitch=ops.round_up(J, 16) if bf16 else None)
             y = self.v2v_net.forward_cl(cubes)
             pitch = int(y.shape[-1])
             out[s:e] = ops.softargmax(y, (X * Y * Z * pitch, 1, pitch), e - s, J, (X, Y, Z), centers[s:e],

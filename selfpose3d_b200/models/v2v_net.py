@@ -19,6 +19,13 @@ import torch.nn as nn
 from .. import ops
 
 
+def _to_volume_cl(x):
+    """Channel-first float tensor -> channel-last activations in the configured volume dtype."""
+    if ops.volume_dtype() == torch.bfloat16:
+        return ops.to_channel_last(x.float(), c_pitch=ops.round_up(x.shape[1], 16), dtype=torch.bfloat16)
+    return ops.to_channel_last(x.float())
+
+
 def _no_train(module):
     if module.training:
         raise NotImplementedError(
@@ -62,7 +69,7 @@ class Basic3DBlock(nn.Module):
 
     def forward(self, x):
         _no_train(self)
-        return ops.to_channel_first(self.forward_cl(ops.to_channel_last(x.float())), self.block[0].out_channels)
+        return ops.to_channel_first(self.forward_cl(_to_volume_cl(x)), self.block[0].out_channels)
 
 
 class Res3DBlock(nn.Module):
@@ -103,7 +110,7 @@ class Res3DBlock(nn.Module):
 
     def forward(self, x):
         _no_train(self)
-        return ops.to_channel_first(self.forward_cl(ops.to_channel_last(x.float())), self.out_planes)
+        return ops.to_channel_first(self.forward_cl(_to_volume_cl(x)), self.out_planes)
 
 
 class Pool3DBlock(nn.Module):
@@ -119,7 +126,7 @@ class Pool3DBlock(nn.Module):
 
     def forward(self, x):
         c = x.shape[1]
-        return ops.to_channel_first(self.forward_cl(ops.to_channel_last(x.float()), c), c)
+        return ops.to_channel_first(self.forward_cl(_to_volume_cl(x), c), c)
 
 
 class Upsample3DBlock(nn.Module):
@@ -147,7 +154,7 @@ class Upsample3DBlock(nn.Module):
 
     def forward(self, x):
         _no_train(self)
-        return ops.to_channel_first(self.forward_cl(ops.to_channel_last(x.float())), self.out_planes)
+        return ops.to_channel_first(self.forward_cl(_to_volume_cl(x)), self.out_planes)
 
 
 class EncoderDecorder(nn.Module):
@@ -179,7 +186,7 @@ class EncoderDecorder(nn.Module):
 
     def forward(self, x):
         _no_train(self)
-        return ops.to_channel_first(self.forward_cl(ops.to_channel_last(x.float())), 32)
+        return ops.to_channel_first(self.forward_cl(_to_volume_cl(x)), 32)
 
 
 class V2VNet(nn.Module):
@@ -210,10 +217,11 @@ class V2VNet(nn.Module):
         x = self.front_layers[0].forward_cl(x)
         x = self.front_layers[1].forward_cl(x)
         x = self.encoder_decoder.forward_cl(x)
-        return self._out_packed()(x, out_pitch=out_pitch)
+        # the score / heat-map volume leaves the net in float32 in either mode (NMS and soft-argmax read it)
+        return self._out_packed()(x, out_pitch=out_pitch, out_dtype=torch.float32)
 
     def forward(self, x):
-        y = self.forward_cl(ops.to_channel_last(x.float()))
+        y = self.forward_cl(_to_volume_cl(x))
         return ops.to_channel_first(y, self.output_channels)
 
     def _initialize_weights(self):

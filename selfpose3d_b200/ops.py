@@ -75,6 +75,21 @@ def pack_cameras(meta, image_size, flip_xcoords=None):
 
 _LIN_CACHE = {}
 
+# dtype of the voxel cubes and V2V activations: float32 -> float32 SIMT convolutions (bit-faithful parity
+# path), bfloat16 -> tcgen05 tensor-core convolutions with float32 accumulation.
+_VOLUME_DTYPE = torch.float32
+
+
+def set_volume_dtype(dtype):
+    global _VOLUME_DTYPE
+    if dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("volume dtype must be torch.float32 or torch.bfloat16")
+    _VOLUME_DTYPE = dtype
+
+
+def volume_dtype():
+    return _VOLUME_DTYPE
+
 
 def linspace_axes(grid_size, cube_size, device):
     """The three ``torch.linspace(-s/2, s/2, n)`` vectors of ``compute_grid``
@@ -243,7 +258,7 @@ def _set3(field, vals):
 
 
 def conv_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksize, stride, tap_off0, tap_step,
-                ostride, ooffset, relu, algo=_lib.CONV_SIMT_F32, cin_real=None):
+                ostride, ooffset, relu, algo=_lib.CONV_SIMT_F32, cin_real=None, cout_pitch_w=None):
     """One implicit-GEMM convolution launch.  ``x`` / ``out`` are channel-last 5-D ``[N,D,H,W,pitch]``."""
     a = _lib.ConvArgs()
     a.in_ = x.data_ptr()
@@ -259,7 +274,7 @@ def conv_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksi
     a.TD, a.TH, a.TW = [int(s) for s in out.shape[1:4]]
     a.cout = int(cout)
     a.cout_pitch = int(out.shape[4])
-    a.cout_pitch_w = int(weight.shape[-1])
+    a.cout_pitch_w = int(weight.shape[-1]) if cout_pitch_w is None else int(cout_pitch_w)
     _set3(a.ksize, ksize)
     _set3(a.stride, stride)
     _set3(a.tap_off0, tap_off0)
@@ -270,7 +285,8 @@ def conv_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksi
     a.algo = int(algo)
     a.in_dtype, a.out_dtype = _DT[x.dtype], _DT[out.dtype]
     flops = 2.0 * a.N * a.OD * a.OH * a.OW * a.cout * (cin_real or a.cin) * (a.ksize[0] * a.ksize[1] * a.ksize[2])
-    _lib.call("sp3d_conv_fwd", a, _stream(), kind="conv", work=flops)
+    detail = "conv algo%d k%d %d->%d @%dx%dx%dx%d" % (a.algo, a.ksize[2], cin_real or a.cin, a.cout, a.N, a.OD, a.OH, a.OW)
+    _lib.call("sp3d_conv_fwd", a, _stream(), kind="conv", work=flops, detail=detail)
 
 
 def maxpool(x, channels, k, s, p):
@@ -337,9 +353,12 @@ class PackedConv:
             out[:, :self.cin, :self.cout] = t
             return out.contiguous()
 
+        self._subs = []      # float32 [Cout, Cin, a, b, c] sub-kernels (one, or one per transposed-conv phase)
+        self._tc = None      # lazily built bf16 packing for the tcgen05 path
         if not transposed:
             self.weights = [pack(w5)]
             self.phases = [None]
+            self._subs = [w5]
         else:
             # one stride-1 sub-convolution per output phase (see include/sp3d.h, sp3d_conv_args)
             self.weights, self.phases = [], []
@@ -353,14 +372,74 @@ class PackedConv:
                         off0 = [(phase[i] + p[i] - t0[i]) // s[i] for i in range(3)]
                         self.weights.append(pack(sub))
                         self.phases.append((phase, off0, [int(v) for v in sub.shape[2:]]))
+                        self._subs.append(sub)
 
     def out_shape(self, dims):
         if not self.transposed:
             return [(dims[i] + 2 * self.padding[i] - self.k[i]) // self.stride[i] + 1 for i in range(3)]
         return [(dims[i] - 1) * self.stride[i] - 2 * self.padding[i] + self.k[i] for i in range(3)]
 
-    def __call__(self, x, residual=None, out_pitch=None, algo=_lib.CONV_SIMT_F32):
-        """``x``: channel-last ``[N,D,H,W,pitch>=cin_p]`` float32.  Returns channel-last output."""
+    # ------------------------------------------------------------------ tcgen05 (bf16) path
+    def tc_supported(self):
+        """Stride-1 "same" 3-D convolutions with k in {1,3,7} and k2/s2 transposed convolutions."""
+        if self.nd != 3:
+            return False
+        if self.transposed:
+            return self.k == [2, 2, 2] and self.stride == [2, 2, 2] and self.padding == [0, 0, 0]
+        return (self.k[0] in (1, 3, 7) and self.k == [self.k[0]] * 3 and self.stride == [1, 1, 1]
+                and self.padding == [self.k[0] // 2] * 3)
+
+    def _tc_pack(self):
+        """bf16 weights ``[taps, n_chunks, N, chunk]`` (rows = output channel, K-major), N = cout padded to a
+        tcgen05 N in {16,32,64,128}, chunk = min(cin padded to 16, 64) channels (= one swizzled smem row)."""
+        if self._tc is None:
+            n = next(v for v in (16, 32, 64, 128) if v >= self.cout)
+            cin_tc = round_up(self.cin, 16)
+            chunk = min(cin_tc, 64)
+            if cin_tc % chunk:
+                raise _lib.Sp3dError("unsupported channel count %d for the tensor-core path" % self.cin)
+            packs = []
+            for sub in self._subs:
+                taps = int(sub.shape[2] * sub.shape[3] * sub.shape[4])
+                t = sub.permute(2, 3, 4, 0, 1).reshape(taps, self.cout, self.cin)
+                full = torch.zeros(taps, n, cin_tc, device=sub.device, dtype=torch.float32)
+                full[:, :self.cout, :self.cin] = t
+                full = full.reshape(taps, n, cin_tc // chunk, chunk).permute(0, 2, 1, 3)
+                packs.append(full.to(torch.bfloat16).contiguous())
+            self._tc = (packs, n, cin_tc)
+        return self._tc
+
+    def _call_tc(self, x, residual, out_pitch, out_dtype):
+        if not self.tc_supported():
+            raise _lib.Sp3dError("convolution shape not covered by the tensor-core path")
+        packs, n, cin_tc = self._tc_pack()
+        N, D, H, W, pitch = [int(v) for v in x.shape]
+        if pitch < cin_tc or pitch % 8:
+            raise _lib.Sp3dError("bf16 activation pitch %d incompatible with packed cin %d" % (pitch, cin_tc))
+        o = self.out_shape((D, H, W))
+        out_dtype = torch.bfloat16 if out_dtype is None else out_dtype
+        out_pitch = round_up(self.cout, 16) if out_pitch is None else int(out_pitch)
+        out = torch.empty((N, o[0], o[1], o[2], out_pitch), device=x.device, dtype=out_dtype)
+        if residual is not None and (residual.dtype != out_dtype or residual.shape != out.shape):
+            raise _lib.Sp3dError("residual must match the output dtype and shape")
+        if not self.transposed:
+            conv_launch(x, packs[0], self.scale, self.shift, residual, out, cin_tc, self.cout, o, self.k, [1, 1, 1],
+                        [-p for p in self.padding], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu, _lib.CONV_TC_BF16,
+                        cin_real=self.cin, cout_pitch_w=n)
+        else:
+            for wgt, (phase, off0, ks) in zip(packs, self.phases):
+                conv_launch(x, wgt, self.scale, self.shift, residual, out, cin_tc, self.cout, (D, H, W), ks, [1, 1, 1],
+                            off0, [1, 1, 1], self.stride, phase, self.relu, _lib.CONV_TC_BF16, cin_real=self.cin,
+                            cout_pitch_w=n)
+        return out
+
+    def __call__(self, x, residual=None, out_pitch=None, algo=None, out_dtype=None):
+        """``x``: channel-last ``[N,D,H,W,pitch]``.  float32 activations take the float32 SIMT kernel,
+        bf16 activations the tcgen05 kernel (``out_dtype`` float32 there gives a float32 result)."""
+        if algo is None:
+            algo = _lib.CONV_TC_BF16 if x.dtype == torch.bfloat16 else _lib.CONV_SIMT_F32
+        if algo == _lib.CONV_TC_BF16:
+            return self._call_tc(x, residual, out_pitch, out_dtype)
         N, D, H, W, pitch = [int(v) for v in x.shape]
         if pitch < self.cin_p:
             raise _lib.Sp3dError("activation pitch %d smaller than packed cin %d" % (pitch, self.cin_p))

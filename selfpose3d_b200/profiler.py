@@ -33,17 +33,30 @@ def begin():
     return ev
 
 
-def end(kind, start, work):
+def end(kind, start, work, detail=None):
     ev = torch.cuda.Event(enable_timing=True)
     ev.record()
-    _records.append((kind, start, ev, float(work)))
+    _records.append((kind, start, ev, float(work), detail))
 
 
 def summary():
     """{kind: {"ms": total device ms, "work": total algorithmic work, "launches": n}} (call after a sync)."""
     out = {}
-    for kind, e0, e1, work in _records:
+    for kind, e0, e1, work, _ in _records:
         d = out.setdefault(kind, {"ms": 0.0, "work": 0.0, "launches": 0})
+        d["ms"] += e0.elapsed_time(e1)
+        d["work"] += work
+        d["launches"] += 1
+    return out
+
+
+def detail_summary():
+    """Like ``summary`` but keyed by the per-launch detail string (layer shape); launches without one are skipped."""
+    out = {}
+    for _, e0, e1, work, detail in _records:
+        if detail is None:
+            continue
+        d = out.setdefault(detail, {"ms": 0.0, "work": 0.0, "launches": 0})
         d["ms"] += e0.elapsed_time(e1)
         d["work"] += work
         d["launches"] += 1

@@ -1,0 +1,110 @@
+"""GPU tests of the tcgen05 (bf16 operands, float32 accumulation) convolution path against the
+float64 CPU reference evaluated on the same bf16-rounded operands."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+from oracle import nets  # noqa: E402
+from selfpose3d_b200 import ops, synthetic  # noqa: E402
+from selfpose3d_b200.models import v2v_net  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def rand_bn(bn, seed):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(bn.weight.shape, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(bn.bias.shape, generator=g) * 0.2)
+        bn.running_mean.copy_(torch.randn(bn.running_mean.shape, generator=g) * 0.2)
+        bn.running_var.copy_(torch.rand(bn.running_var.shape, generator=g) + 0.5)
+    return bn.eval()
+
+
+def to_cl_bf16(x):   # [N,C,X,Y,Z] float (bf16-representable) -> channel-last bf16, pitch = C rounded up to 16
+    return ops.to_channel_last(x.to(DEV), c_pitch=ops.round_up(x.shape[1], 16), dtype=torch.bfloat16)
+
+
+# every (kernel, cin, cout) the V2V nets use; spatial extent with partial bricks in x, y and z
+CONV_CASES = [(7, 15, 16), (7, 1, 16), (3, 16, 32), (3, 32, 32), (3, 32, 64), (3, 64, 64), (3, 64, 128),
+              (3, 128, 128), (1, 16, 32), (1, 32, 64), (1, 64, 128), (1, 32, 15), (1, 32, 1)]
+
+
+@pytest.mark.parametrize("k,cin,cout", CONV_CASES)
+def test_tc_conv_matches_float64_reference(k, cin, cout):
+    torch.manual_seed(k * 1000 + cin * 10 + cout)
+    conv = nn.Conv3d(cin, cout, k, 1, k // 2)
+    bn = rand_bn(nn.BatchNorm3d(cout), cin + cout)
+    with torch.no_grad():
+        conv.weight.copy_(bf16_round(conv.weight))
+    x = bf16_round(torch.randn(2, cin, 6, 20, 12))
+    res = bf16_round(torch.randn(2, cout, 6, 20, 12))
+    with torch.no_grad():
+        want = F.relu(bn.double()(conv.double()(x.double())) + res.double())
+    conv, bn = conv.float().to(DEV), bn.float().to(DEV)
+    pc = ops.PackedConv(conv.weight, conv.bias, bn, 1, k // 2, relu=1)
+    pitch = ops.round_up(cout, 16)
+    res_cl = ops.to_channel_last(res.to(DEV), c_pitch=pitch, dtype=torch.float32)
+    y = pc(to_cl_bf16(x), residual=res_cl, out_pitch=pitch, out_dtype=torch.float32)
+    got = ops.to_channel_first(y, cout).cpu().double()
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) <= 2e-5 * scale, float((got - want).abs().max()) / scale
+    if pitch > cout:
+        assert not y[..., cout:].any()
+    # bf16 output + bf16 residual: one bf16 rounding of the result on top
+    yb = pc(to_cl_bf16(x), residual=res_cl.to(torch.bfloat16), out_pitch=pitch)
+    gotb = ops.to_channel_first(yb, cout, dtype=torch.float32).cpu().double()
+    assert float((gotb - want).abs().max()) <= 6e-3 * scale
+
+
+@pytest.mark.parametrize("cin,cout", [(128, 64), (64, 32)])
+def test_tc_transposed_conv_matches_float64_reference(cin, cout):
+    torch.manual_seed(cin)
+    ct = nn.ConvTranspose3d(cin, cout, 2, 2)
+    bn = rand_bn(nn.BatchNorm3d(cout), cin)
+    with torch.no_grad():
+        ct.weight.copy_(bf16_round(ct.weight))
+    x = bf16_round(torch.randn(2, cin, 4, 16, 8))
+    skip = bf16_round(torch.randn(2, cout, 8, 32, 16))
+    with torch.no_grad():
+        want = F.relu(bn.double()(ct.double()(x.double()))) + skip.double()
+    ct, bn = ct.float().to(DEV), bn.float().to(DEV)
+    pc = ops.PackedConv(ct.weight, ct.bias, bn, 2, 0, transposed=True, relu=2)
+    skip_cl = ops.to_channel_last(skip.to(DEV), c_pitch=cout, dtype=torch.float32)
+    y = pc(to_cl_bf16(x), residual=skip_cl, out_pitch=cout, out_dtype=torch.float32)
+    got = ops.to_channel_first(y, cout).cpu().double()
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) <= 2e-5 * scale
+
+
+def test_v2v_net_bf16_mode_vs_float64_oracle():
+    """Whole V2VNet(15,15) on a 32^3 cube and V2VNet(1,1) on a 40x40x12 grid in bf16 tensor-core mode.
+    bf16 activations carry ~3 significant digits; the result is compared with the float64 oracle relative
+    to the output range (this is the throughput mode, not the parity mode)."""
+    for cin, shape, seed in ((15, (1, 15, 32, 32, 32), 41), (1, (2, 1, 40, 40, 12), 42)):
+        net = v2v_net.V2VNet(cin, cin)
+        sd = synthetic.trained_like_state_dict(net, seed=seed)
+        net.load_state_dict(sd, strict=True)
+        x = torch.from_numpy(np.random.RandomState(seed).rand(*shape).astype(np.float32))
+        y64 = nets.v2v_forward(x, sd, dtype=torch.float64)
+        ops.set_volume_dtype(torch.bfloat16)
+        try:
+            y = net.to(DEV).eval()(x.to(DEV)).cpu().double()
+            if cin == 1:   # the root net's pitch-1 float32 score volume (what sp3d_nms_topk3d reads)
+                xcl = ops.to_channel_last(x.to(DEV), c_pitch=16, dtype=torch.bfloat16)
+                y1 = net.forward_cl(xcl, out_pitch=1)
+                assert y1.shape == (2, 40, 40, 12, 1) and y1.dtype == torch.float32
+                assert torch.equal(y1[..., 0].cpu().double(), y[:, 0])
+        finally:
+            ops.set_volume_dtype(torch.float32)
+        err = float((y - y64).abs().max()) / float(y64.abs().max())
+        print("V2VNet(%d) bf16 mode: max error / output range = %.3g" % (cin, err))
+        assert err < 5e-2, err
