@@ -26,8 +26,14 @@ namespace sp3d {
 using namespace tc;
 
 constexpr int kTcThreads = 256;
-constexpr int kWStages = 4;
 constexpr int kBY = 16, kBZ = 8;   // brick extent in y and z: 128 rows of M = 16 groups of 8 z-voxels
+
+constexpr int largest_divisor_le(int n, int cap) {
+  int best = 1;
+  for (int d = 1; d <= n && d <= cap; ++d)
+    if (n % d == 0) best = d;
+  return best;
+}
 
 struct TcConvParams {
   int n_cubes, X, Y, Z;          // input spatial extent (= virtual output grid; stride 1)
@@ -44,17 +50,24 @@ struct TcConvParams {
   void* out;
 };
 
-template <int KS, int RB, int N, int TX>
+// KS kernel extent, RB bytes per smem row (= channels per K chunk * 2), N = MMA N (padded cout),
+// TX = x-slices (M tiles) per brick, G = taps per weight stage, S = weight stages.
+template <int KS, int RB, int N, int TX, int G, int S>
 struct TcCfg {
   static constexpr int P = KS / 2;
   static constexpr int HX = TX + KS - 1, HY = kBY + KS - 1, HZ = kBZ + KS - 1;
   static constexpr int kHaloRows = HX * HY * HZ;
   static constexpr int kHaloBytes = kHaloRows * RB;
   static constexpr int kHaloStride = (kHaloBytes + 1023) / 1024 * 1024;
-  static constexpr int kWBytes = N * RB;
-  static constexpr int kWStride = (kWBytes + 1023) / 1024 * 1024;
-  static constexpr int kSmemBytes = 2 * kHaloStride + kWStages * kWStride + 1024;   // + alignment slack
   static constexpr int kTaps = KS * KS * KS;
+  static constexpr int kGroups = kTaps / G;             // weight stages consumed per (brick, chunk)
+  static constexpr int kTapBytes = N * RB;
+  static constexpr int kWBytes = G * kTapBytes;         // one stage = G consecutive taps
+  static constexpr int kWStride = (kWBytes + 1023) / 1024 * 1024;
+  static constexpr int kTapsPerLoad = largest_divisor_le(G, 256 / N);   // TMA box rows <= 256
+  static constexpr int kLoads = G / kTapsPerLoad;
+  static constexpr int kSmemBytes = 2 * kHaloStride + S * kWStride + 1024;   // + alignment slack
+  static_assert(kTaps % G == 0, "taps per stage must divide the tap count");
   static constexpr int kKSteps = RB / 32;       // tcgen05.mma K = 16 bf16 = 32 bytes
   static constexpr int kIssuers = TX >= 2 ? 2 : 1;
   static constexpr uint32_t kLayout = RB == 128 ? kSwizzle128 : (RB == 64 ? kSwizzle64 : kSwizzle32);
@@ -62,11 +75,12 @@ struct TcCfg {
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
-template <int KS, int RB, int N, int TX>
+template <int KS, int RB, int N, int TX, int G, int S>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
                  const TcConvParams p) {
-  using C = TcCfg<KS, RB, N, TX>;
+  using C = TcCfg<KS, RB, N, TX, G, S>;
+  constexpr int kWStages = S;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t halo_full[2], halo_empty[2], w_full[kWStages], w_empty[kWStages], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
@@ -76,7 +90,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_consta
   uint8_t* halo = smem;                               // [2][kHaloStride]
   uint8_t* wbuf = smem + 2 * C::kHaloStride;          // [kWStages][kWStride]
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&halo_full[i], 1);
@@ -105,7 +120,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);   // warp-uniform for the compiler
 
   auto brick_coords = [&](int b, int& n, int& x0, int& y0, int& z0) {
     const int bz = b % p.bricks_z;
@@ -130,20 +145,26 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_consta
       }
     }
   } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------------ weight producer (one tap per stage)
+    // ------------------------------------------------------------------ weight producer (G taps per stage)
+    // packed weights: rows ordered [chunk][tap][N]; a stage holds taps g*G .. g*G+G-1 of one chunk
     uint32_t w = 0;
     for (int b = blockIdx.x; b < p.n_bricks; b += gridDim.x) {
       for (int c = 0; c < p.n_chunks; ++c) {
-        for (int tap = 0; tap < C::kTaps; ++tap, ++w) {
+        for (int g = 0; g < C::kGroups; ++g, ++w) {
           const uint32_t st = w % kWStages;
           mbar_wait(&w_empty[st], ((w / kWStages) & 1) ^ 1);
           mbar_arrive_expect_tx(&w_full[st], C::kWBytes);
-          tma_load_2d(wbuf + st * C::kWStride, &map_w, &w_full[st], 0, (tap * p.n_chunks + c) * N);
+#pragma unroll 1
+          for (int l = 0; l < C::kLoads; ++l)
+            tma_load_2d(wbuf + st * C::kWStride + l * (C::kTapsPerLoad * C::kTapBytes), &map_w, &w_full[st], 0,
+                        ((c * C::kTaps + g * G) + l * C::kTapsPerLoad) * N);
         }
       }
     }
-  } else if ((warp == 2 || warp == 3) && lane == 0 && (warp - 2) < C::kIssuers) {
+  } else if ((warp == 2 || warp == 3) && (warp - 2) < C::kIssuers) {
     // ------------------------------------------------------------------ MMA issuers
+    // The whole warp runs this loop (warp-uniform control flow and values, so the descriptor arithmetic
+    // stays in uniform registers); only the tcgen05.mma / commit instructions are predicated on lane 0.
     const int q = warp - 2;
     const uint32_t idesc = make_idesc(kFmtBF16, 128, N);
     const uint64_t a_desc0 = make_smem_desc(smem_u32(halo), 0, C::HZ * RB, C::kLayout);
@@ -156,28 +177,46 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_consta
       for (int c = 0; c < p.n_chunks; ++c, ++u) {
         const uint32_t buf = u & 1;
         mbar_wait(&halo_full[buf], (u >> 1) & 1);
-        const uint64_t a_desc = a_desc0 + (uint64_t)((buf * C::kHaloStride) >> 4);
-        for (int tap = 0; tap < C::kTaps; ++tap, ++w) {
+        // descriptor low words advance in 16-byte units; the high words (SBO, version, layout) never change
+        const uint32_t a_lo0 = (uint32_t)a_desc0 + (uint32_t)((buf * C::kHaloStride) >> 4);
+        const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
+        constexpr uint32_t kRow16 = RB / 16;                       // one halo row in 16-byte units
+        uint32_t accum = c ? 1u : 0u;                              // first tap of the first chunk overwrites
+        int dz = 0, dy = 0;
+        uint32_t a_tap = a_lo0;                                    // start of the current tap's shifted window
+        for (int g = 0; g < C::kGroups; ++g, ++w) {
           const uint32_t st = w % kWStages;
           mbar_wait(&w_full[st], (w / kWStages) & 1);
           tc_fence_after();
-          const int dz = tap % KS, dy = (tap / KS) % KS, dx = tap / (KS * KS);
-          const uint64_t b_desc = b_desc0 + (uint64_t)((st * C::kWStride) >> 4);
-          const uint32_t tap_rows = (uint32_t)((dx * C::HY + dy) * C::HZ + dz);
+          uint32_t b_lo = (uint32_t)b_desc0 + (uint32_t)((st * C::kWStride) >> 4);
+#pragma unroll(G % KS == 0 ? KS : 1)
+          for (int j = 0; j < G; ++j) {
 #pragma unroll
-          for (int t = q; t < TX; t += C::kIssuers) {
-            const uint64_t a_tile = a_desc + (uint64_t)(((tap_rows + (uint32_t)(t * C::HY * C::HZ)) * RB) >> 4);
-            const uint32_t d_tmem = tmem_base + (accbuf * TX + t) * N;
+            for (int t = q; t < TX; t += C::kIssuers) {
+              const uint32_t a_lo = a_tap + (uint32_t)(t * C::HY * C::HZ) * kRow16;
+              const uint32_t d_tmem = tmem_base + (accbuf * TX + t) * N;
 #pragma unroll
-            for (int k = 0; k < C::kKSteps; ++k)
-              mma_f16_ss(d_tmem, a_tile + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                         (c | tap | k) ? 1u : 0u);
+              for (int k = 0; k < C::kKSteps; ++k)
+                if (elect_one_sync()) mma_f16_ss_lohi(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k ? 1u : accum);
+            }
+            accum = 1u;
+            b_lo += (uint32_t)(C::kTapBytes >> 4);
+            // next tap: z fastest, then y, then x
+            a_tap += kRow16;
+            if (++dz == KS) {
+              dz = 0;
+              a_tap += (uint32_t)(C::HZ - KS) * kRow16;
+              if (++dy == KS) {
+                dy = 0;
+                a_tap += (uint32_t)((C::HY - KS) * C::HZ) * kRow16;
+              }
+            }
           }
-          mma_commit(&w_empty[st]);
+          if (elect_one_sync()) mma_commit(&w_empty[st]);
         }
-        mma_commit(&halo_empty[buf]);
+        if (elect_one_sync()) mma_commit(&halo_empty[buf]);
       }
-      mma_commit(&acc_full[accbuf]);
+      if (elect_one_sync()) mma_commit(&acc_full[accbuf]);
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (thread <-> accumulator row)
@@ -291,9 +330,9 @@ static CUtensorMapSwizzle swizzle_for(int rb) {
   return rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
-template <int KS, int RB, int N, int TX>
+template <int KS, int RB, int N, int TX, int G, int S>
 static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
-  using C = TcCfg<KS, RB, N, TX>;
+  using C = TcCfg<KS, RB, N, TX, G, S>;
   EncodeTiledFn encode = get_encode();
   if (encode == nullptr) return SP3D_ERR_UNSUPPORTED;
   const int chunk_ch = RB / 2;
@@ -311,10 +350,10 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return SP3D_ERR_INVALID_ARG;
   }
-  {  // weights: [taps * n_chunks * N rows][chunk channels] bf16 (K-major rows), box = {chunk, N}
+  {  // weights: [n_chunks * taps * N rows][chunk channels] bf16 (K-major rows), box = {chunk, taps_per_load * N}
     cuuint64_t gdim[2] = {(cuuint64_t)chunk_ch, (cuuint64_t)C::kTaps * n_chunks * N};
     cuuint64_t gstr[1] = {(cuuint64_t)RB};
-    cuuint32_t box[2] = {(cuuint32_t)chunk_ch, (cuuint32_t)N};
+    cuuint32_t box[2] = {(cuuint32_t)chunk_ch, (cuuint32_t)(C::kTapsPerLoad * N)};
     cuuint32_t es[2] = {1, 1};
     if (encode(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a->weight), gdim, gstr, box, es,
                CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(RB), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -342,7 +381,7 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   }
-  auto kern = conv3d_tc_kernel<KS, RB, N, TX>;
+  auto kern = conv3d_tc_kernel<KS, RB, N, TX, G, S>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
   if (e != cudaSuccess) { set_last_error(e); return SP3D_ERR_LAUNCH; }
   const int grid = p.n_bricks < n_sm ? p.n_bricks : n_sm;
@@ -367,21 +406,22 @@ int conv_tc(const sp3d_conv_args* a, cudaStream_t st) {
     return SP3D_ERR_INVALID_ARG;
   const int cin = a->cin, n = a->cout_pitch_w;   // packed weight rows per tap = N of the MMA
   if (a->cout > n) return SP3D_ERR_INVALID_ARG;
-#define SP3D_TC_CASE(KS_, CIN_, RB_, N_, TX_) \
-  if (ks == KS_ && cin == CIN_ && n == N_) return launch_tc<KS_, RB_, N_, TX_>(a, st);
-  SP3D_TC_CASE(7, 16, 32, 16, 2)
-  SP3D_TC_CASE(3, 16, 32, 32, 4)
-  SP3D_TC_CASE(3, 32, 64, 32, 4)
-  SP3D_TC_CASE(3, 32, 64, 64, 4)
-  SP3D_TC_CASE(3, 64, 128, 64, 2)
-  SP3D_TC_CASE(3, 64, 128, 128, 1)
-  SP3D_TC_CASE(3, 128, 128, 128, 1)
-  SP3D_TC_CASE(1, 16, 32, 32, 4)
-  SP3D_TC_CASE(1, 32, 64, 64, 4)
-  SP3D_TC_CASE(1, 64, 128, 128, 2)
-  SP3D_TC_CASE(1, 32, 64, 16, 4)
-  SP3D_TC_CASE(1, 128, 128, 64, 4)
-  SP3D_TC_CASE(1, 64, 128, 32, 4)
+  // (kernel, padded cin, row bytes, N, x-slices per brick, taps per weight stage, weight stages)
+#define SP3D_TC_CASE(KS_, CIN_, RB_, N_, TX_, G_, S_) \
+  if (ks == KS_ && cin == CIN_ && n == N_) return launch_tc<KS_, RB_, N_, TX_, G_, S_>(a, st);
+  SP3D_TC_CASE(7, 16, 32, 16, 2, 49, 2)
+  SP3D_TC_CASE(3, 16, 32, 32, 4, 27, 2)
+  SP3D_TC_CASE(3, 32, 64, 32, 4, 9, 3)
+  SP3D_TC_CASE(3, 32, 64, 64, 4, 9, 2)
+  SP3D_TC_CASE(3, 64, 128, 64, 2, 1, 4)
+  SP3D_TC_CASE(3, 64, 128, 128, 2, 1, 2)
+  SP3D_TC_CASE(3, 128, 128, 128, 2, 1, 2)
+  SP3D_TC_CASE(1, 16, 32, 32, 4, 1, 2)
+  SP3D_TC_CASE(1, 32, 64, 64, 4, 1, 2)
+  SP3D_TC_CASE(1, 64, 128, 128, 2, 1, 2)
+  SP3D_TC_CASE(1, 32, 64, 16, 4, 1, 2)
+  SP3D_TC_CASE(1, 128, 128, 64, 4, 1, 2)
+  SP3D_TC_CASE(1, 64, 128, 32, 4, 1, 2)
 #undef SP3D_TC_CASE
   return SP3D_ERR_UNSUPPORTED;
 }

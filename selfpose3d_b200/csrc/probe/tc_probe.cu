@@ -236,12 +236,12 @@ static int run_case(const Case& c, bool verbose) {
 // `issuers` warps each issue repeat*8 MMAs (compile-time unrolled descriptor offsets) into their own accumulator.
 template <int N, bool TF32>
 __global__ void __launch_bounds__(128) rate_kernel(uint32_t layout_type, uint32_t row_bytes, int issuers, int repeat,
-                                                   long long* __restrict__ cycles) {
+                                                   int pitch_rows, long long* __restrict__ cycles) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar[4];
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t a_bytes = 128 * row_bytes, b_bytes = N * row_bytes;
+  const uint32_t a_bytes = (16 * pitch_rows + 16) * row_bytes, b_bytes = N * row_bytes;
   for (uint32_t i = tid * 16; i < a_bytes + b_bytes + 1024; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
   if (tid == 0) {
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(128) rate_kernel(uint32_t layout_type, uint32_
   const uint32_t base = smem_u32(smem);
   const uint32_t b_base = base + ((a_bytes + 1023) & ~1023u);
   const uint32_t idesc = make_idesc(TF32 ? kFmtTF32 : kFmtBF16, 128, N);
-  const uint64_t da = make_smem_desc(base, 0, 8 * row_bytes, layout_type);
+  const uint64_t da = make_smem_desc(base, 0, pitch_rows * row_bytes, layout_type);
   const uint64_t db = make_smem_desc(b_base, 0, 8 * row_bytes, layout_type);
   const int ksteps = row_bytes / 32;   // MMAs per swizzled row
   long long t0 = clock64();
@@ -268,8 +268,10 @@ __global__ void __launch_bounds__(128) rate_kernel(uint32_t layout_type, uint32_
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const uint64_t off = (uint64_t)((j % ksteps) * 2);
-        if (TF32) mma_tf32_ss(tm, da + off, db + off, idesc, 1u);
-        else mma_f16_ss(tm, da + off, db + off, idesc, 1u);
+        // pitch_rows != 8 mimics the conv kernel: every MMA starts at a different (unaligned) halo row
+        const uint64_t shift = pitch_rows == 8 ? 0 : (uint64_t)((j + 1) * (row_bytes >> 4));
+        if (TF32) mma_tf32_ss(tm, da + off + shift, db + off, idesc, 1u);
+        else mma_f16_ss(tm, da + off + shift, db + off, idesc, 1u);
       }
     }
     mma_commit(&bar[warp]);
@@ -282,7 +284,7 @@ __global__ void __launch_bounds__(128) rate_kernel(uint32_t layout_type, uint32_
 }
 
 template <int N, bool TF32>
-static void run_rate(const char* name, uint32_t layout_type, uint32_t row_bytes) {
+static void run_rate(const char* name, uint32_t layout_type, uint32_t row_bytes, int pitch_rows = 8) {
   long long* d_cyc;
   CK(cudaMalloc(&d_cyc, 32));
   CK(cudaFuncSetAttribute(rate_kernel<N, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -290,7 +292,8 @@ static void run_rate(const char* name, uint32_t layout_type, uint32_t row_bytes)
     if (issuers * (N >= 128 ? 128 : N) > 512) continue;
     const int repeat = 256;
     CK(cudaMemset(d_cyc, 0, 32));
-    rate_kernel<N, TF32><<<1, 128, 128 * row_bytes + N * row_bytes + 4096, 0>>>(layout_type, row_bytes, issuers, repeat, d_cyc);
+    rate_kernel<N, TF32><<<1, 128, (16 * pitch_rows + 16) * row_bytes + N * row_bytes + 4096, 0>>>(layout_type, row_bytes, issuers, repeat,
+                                                                                                   pitch_rows, d_cyc);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("rate kernel failed: %s\n", cudaGetErrorString(e)); exit(3); }
     long long cyc[4];
@@ -299,7 +302,7 @@ static void run_rate(const char* name, uint32_t layout_type, uint32_t row_bytes)
     for (int i = 0; i < issuers; ++i) mx = cyc[i] > mx ? cyc[i] : mx;
     const double per = (double)mx / (repeat * 8);
     const int kk = TF32 ? 8 : 16;
-    printf("rate2 %-18s N=%3d issuers=%d : %7.1f cycles per MMA per issuer, %6.1f MACs/cycle/SM (floor %d cyc)\n", name, N,
+    printf("rate2 %-18s pitch=%2d N=%3d issuers=%d : %7.1f cycles per MMA per issuer, %6.1f MACs/cycle/SM (floor %d cyc)\n", name, pitch_rows, N,
            issuers, per, issuers * 128.0 * N * kk / per, 128 * N / 256 * (TF32 ? 1 : 1));
   }
   cudaFree(d_cyc);
@@ -406,7 +409,12 @@ int main(int argc, char** argv) {
     run_rate<32, false>("bf16 SW128", kSwizzle128, 128);
     run_rate<64, false>("bf16 SW128", kSwizzle128, 128);
     run_rate<128, false>("bf16 SW128", kSwizzle128, 128);
-    run_rate<256, false>("bf16 SW128", kSwizzle128, 128);
+    run_rate<16, false>("bf16 SW32", kSwizzle32, 32, 14);
+    run_rate<32, false>("bf16 SW32", kSwizzle32, 32, 10);
+    run_rate<32, false>("bf16 SW64", kSwizzle64, 64, 10);
+    run_rate<64, false>("bf16 SW64", kSwizzle64, 64, 10);
+    run_rate<64, false>("bf16 SW128", kSwizzle128, 128, 10);
+    run_rate<128, false>("bf16 SW128", kSwizzle128, 128, 10);
     run_rate<16, false>("bf16 SW32", kSwizzle32, 32);
     run_rate<32, false>("bf16 SW64", kSwizzle64, 64);
     run_rate<16, true>("tf32 SW128", kSwizzle128, 128);

@@ -390,7 +390,7 @@ class PackedConv:
                 and self.padding == [self.k[0] // 2] * 3)
 
     def _tc_pack(self):
-        """bf16 weights ``[taps, n_chunks, N, chunk]`` (rows = output channel, K-major), N = cout padded to a
+        """bf16 weights ``[n_chunks, taps, N, chunk]`` (rows = output channel, K-major), N = cout padded to a
         tcgen05 N in {16,32,64,128}, chunk = min(cin padded to 16, 64) channels (= one swizzled smem row)."""
         if self._tc is None:
             n = next(v for v in (16, 32, 64, 128) if v >= self.cout)
@@ -404,7 +404,7 @@ class PackedConv:
                 t = sub.permute(2, 3, 4, 0, 1).reshape(taps, self.cout, self.cin)
                 full = torch.zeros(taps, n, cin_tc, device=sub.device, dtype=torch.float32)
                 full[:, :self.cout, :self.cin] = t
-                full = full.reshape(taps, n, cin_tc // chunk, chunk).permute(0, 2, 1, 3)
+                full = full.reshape(taps, n, cin_tc // chunk, chunk).permute(2, 0, 1, 3)
                 packs.append(full.to(torch.bfloat16).contiguous())
             self._tc = (packs, n, cin_tc)
         return self._tc
