@@ -19,8 +19,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=bench.BATCH)
 ap.add_argument("--proposals", type=int, default=bench.PROPOSALS)
 ap.add_argument("--warmup", type=int, default=1)
+ap.add_argument("--volume-dtype", default="bf16", choices=["bf16", "f32"])
 a = ap.parse_args()
 
+from selfpose3d_b200 import ops  # noqa: E402
+ops.set_volume_dtype(torch.bfloat16 if a.volume_dtype == "bf16" else torch.float32)
 bench.PROPOSALS = a.proposals
 cfg = bench.make_cfg(a.batch)
 model = multi_person_posenet_ssv.get_multi_person_pose_net(cfg, is_train=False)
