@@ -26,7 +26,20 @@ struct ConvTile {
   static constexpr int TM = kBM / TY;                                 // rows per thread
 };
 
-template <int BN>
+// 4 consecutive channels of an activation tensor as float4 (float32 or bf16 storage)
+__device__ __forceinline__ float4 load4(const float* p) { return ldg4(p); }
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
+  const uint2 q = __ldg(reinterpret_cast<const uint2*>(p));
+  const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&q.x);
+  const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&q.y);
+  return make_float4(__bfloat162float(lo.x), __bfloat162float(lo.y), __bfloat162float(hi.x), __bfloat162float(hi.y));
+}
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ void store1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <int BN, typename InT, typename OutT>
 __global__ void __launch_bounds__(kConvThreads) conv_igemm_f32_kernel(const sp3d_conv_args a) {
   using T = ConvTile<BN>;
   constexpr int TM = T::TM, TN = T::TN, TX = T::TX;
@@ -71,7 +84,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_f32_kernel(const sp3d
   constexpr int kBVec = kBK * kBVecPerRow;
   constexpr int kBIter = (kBVec + kConvThreads - 1) / kConvThreads;
 
-  const float* in = reinterpret_cast<const float*>(a.in);
+  const InT* in = reinterpret_cast<const InT*>(a.in);
   const float* wgt = reinterpret_cast<const float*>(a.weight);
 
   float4 a_reg[2];
@@ -92,7 +105,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_f32_kernel(const sp3d
         const int ih = info.z + ((pk >> 10) & 1023) - 512;
         const int iw = info.w + (pk & 1023) - 512;
         if (id >= 0 && id < a.D && ih >= 0 && ih < a.H && iw >= 0 && iw < a.W)
-          v = ldg4(in + ((((int64_t)info.x * a.D + id) * a.H + ih) * a.W + iw) * a.cin_pitch + c);
+          v = load4(in + ((((int64_t)info.x * a.D + id) * a.H + ih) * a.W + iw) * a.cin_pitch + c);
       }
       a_reg[i] = v;
     }
@@ -169,8 +182,8 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_f32_kernel(const sp3d
   }
 
   // epilogue: scale/shift (+ residual) (+ ReLU), channel-last store
-  float* out = reinterpret_cast<float*>(a.out);
-  const float* res = reinterpret_cast<const float*>(a.residual);
+  OutT* out = reinterpret_cast<OutT*>(a.out);
+  const OutT* res = reinterpret_cast<const OutT*>(a.residual);
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int r = ty * TM + i;
@@ -182,8 +195,8 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_f32_kernel(const sp3d
     const int n = (int)(m / ((int64_t)a.OW * a.OH * a.OD));
     const int64_t pos = (((int64_t)n * a.TD + od * a.ostride[0] + a.ooffset[0]) * a.TH + oh * a.ostride[1] + a.ooffset[1]) *
                             a.TW + ow * a.ostride[2] + a.ooffset[2];
-    float* o = out + pos * a.cout_pitch;
-    const float* rp = res ? res + pos * a.cout_pitch : nullptr;
+    OutT* o = out + pos * a.cout_pitch;
+    const OutT* rp = res ? res + pos * a.cout_pitch : nullptr;
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       const int co = n0 + tx * TN + j;
@@ -192,11 +205,11 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_f32_kernel(const sp3d
         if (a.scale) v *= a.scale[co];
         if (a.shift) v += a.shift[co];
         if (a.relu == 2) v = fmaxf(v, 0.f);
-        if (rp) v += rp[co];
+        if (rp) v += to_f32(rp[co]);
         if (a.relu == 1) v = fmaxf(v, 0.f);
-        o[co] = v;
+        store1(o + co, v);
       } else if (co < a.cout_pitch) {
-        o[co] = 0.f;
+        store1(o + co, 0.f);
       }
     }
   }
@@ -206,7 +219,14 @@ template <int BN>
 static int launch_conv(const sp3d_conv_args* a, cudaStream_t st) {
   const int64_t M_total = (int64_t)a->N * a->OD * a->OH * a->OW;
   dim3 grid(ceil_div(M_total, kBM), ceil_div(a->cout, BN));
-  conv_igemm_f32_kernel<BN><<<grid, kConvThreads, 0, st>>>(*a);
+  if (a->in_dtype == SP3D_F32 && a->out_dtype == SP3D_F32)
+    conv_igemm_f32_kernel<BN, float, float><<<grid, kConvThreads, 0, st>>>(*a);
+  else if (a->in_dtype == SP3D_F32 && a->out_dtype == SP3D_BF16)
+    conv_igemm_f32_kernel<BN, float, __nv_bfloat16><<<grid, kConvThreads, 0, st>>>(*a);
+  else if (a->in_dtype == SP3D_BF16 && a->out_dtype == SP3D_BF16)
+    conv_igemm_f32_kernel<BN, __nv_bfloat16, __nv_bfloat16><<<grid, kConvThreads, 0, st>>>(*a);
+  else
+    return SP3D_ERR_UNSUPPORTED;
   return check_launch();
 }
 
@@ -217,12 +237,12 @@ int conv_simt_f32(const sp3d_conv_args* a, cudaStream_t st) {
     return SP3D_ERR_INVALID_ARG;
   if ((reinterpret_cast<uintptr_t>(a->in) % 16) != 0 || (reinterpret_cast<uintptr_t>(a->weight) % 16) != 0)
     return SP3D_ERR_INVALID_ARG;
+  // float32 math on float32 or bf16 storage (the bf16 forms serve the strided 2-D convolutions of the bf16 backbone)
   for (int d = 0; d < 3; ++d) {
     const int lo = a->tap_off0[d] + (a->tap_step[d] < 0 ? (a->ksize[d] - 1) * a->tap_step[d] : 0);
     const int hi = a->tap_off0[d] + (a->tap_step[d] > 0 ? (a->ksize[d] - 1) * a->tap_step[d] : 0);
     if (lo < -500 || hi > 500) return SP3D_ERR_UNSUPPORTED;
   }
-  if (a->in_dtype != SP3D_F32 || a->out_dtype != SP3D_F32) return SP3D_ERR_UNSUPPORTED;
   if (a->cout > 64) return launch_conv<128>(a, st);
   if (a->cout > 32) return launch_conv<64>(a, st);
   if (a->cout > 16) return launch_conv<32>(a, st);

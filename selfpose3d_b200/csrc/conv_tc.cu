@@ -1,22 +1,27 @@
-// K2 (tensor-core form) -- stride-1 3-D convolution as an im2col-free implicit GEMM on tcgen05.
+// K2 / K5 (tensor-core form) -- convolutions as an im2col-free implicit GEMM on tcgen05.
 //
-// One persistent CTA per SM walks output bricks of TX x 16 x 8 voxels (x, y, z; z fastest).
-//   * warp 0 (1 thread)  : TMA-loads the brick's input HALO ((TX+k-1) x (16+k-1) x (8+k-1) voxels x <=64
+// One persistent CTA per SM walks work items = (output brick of TX x 16 x 8 positions (x, y, z; z fastest),
+// tile of N output channels).  3-D tensors map (X, Y, Z) to (x, y, z); 2-D image batches map
+// (image, row, column) to (x, y, z) with a kernel extent of 1 along x.
+//   * warp 0 (1 thread)  : TMA-loads the brick's input HALO ((TX+kx-1) x (16+k-1) x (8+k-1) positions x <=64
 //                          channels, bf16, channel-last) as ONE 5-D tiled box with hardware swizzle and
-//                          out-of-bounds zero fill (= the convolution's zero padding), double buffered;
-//   * warp 1 (1 thread)  : streams the packed weights of one tap per stage through a small TMA ring;
-//   * warps 2,3 (1 thread each): issue tcgen05.mma.  A tap (dx,dy,dz) is NOT a new load: it is the same
-//                          shared-memory halo with the A-descriptor start address moved by
-//                          ((dx*HY + dy)*HZ + dz) rows and SBO = HZ rows (8 consecutive z voxels form a
-//                          core-matrix group, 16 y values form the 128 rows of M).  Verified on B200 by
-//                          csrc/probe/tc_probe.cu: the swizzle is a function of the absolute smem address,
-//                          so row-shifted starts with base_offset = 0 address the right data.
+//                          out-of-bounds zero fill (= the convolution's zero padding), double buffered.
+//                          Stride-2 convolutions use the tensor map's element strides;
+//   * warp 1 (1 thread)  : streams the packed weights, G taps per stage, through a small TMA ring;
+//   * warps 2,3          : issue tcgen05.mma (warp-uniform loop, elect.sync-predicated).  A tap (dx,dy,dz) is
+//                          NOT a new load: it is the same shared-memory halo with the A-descriptor start
+//                          address moved by ((dx*HY + dy)*HZ + dz) rows and SBO = HZ rows (8 consecutive z
+//                          positions form a core-matrix group, 16 y values form the 128 rows of M).  Verified on
+//                          B200 by csrc/probe/tc_probe.cu: the swizzle is a function of the absolute smem
+//                          address, so row-shifted starts with base_offset = 0 address the right data.
 //                          Accumulators (TX tiles x N fp32 columns, double buffered) live in TMEM;
-//   * warps 4..7         : epilogue.  tcgen05.ld the accumulator row of "their" voxel, apply folded
-//                          BatchNorm scale/shift, optional residual and ReLU, convert, store channel-last.
+//   * warps 4..7         : epilogue.  tcgen05.ld the accumulator row of "their" position, apply folded
+//                          BatchNorm scale/shift, optional residual and ReLU, convert, store channel-last
+//                          (strided positions for the phases of a transposed convolution).
 //
 // Reference semantics: cudnn conv3d / conv_transpose3d(k2,s2) + batch_norm(eval) + relu (+ add) as wired in
-// lib/models/v2v_net.py:10-69,124.
+// lib/models/v2v_net.py:10-69,124, and conv2d / conv_transpose2d(k4,s2,p1) + batch_norm + relu (+ add) of
+// lib/models/pose_resnet.py:58-93,118-124,161-207.
 #include "sp3d_common.cuh"
 #include "tc_common.cuh"
 #include <cuda.h>
@@ -26,7 +31,7 @@ namespace sp3d {
 using namespace tc;
 
 constexpr int kTcThreads = 256;
-constexpr int kBY = 16, kBZ = 8;   // brick extent in y and z: 128 rows of M = 16 groups of 8 z-voxels
+constexpr int kBY = 16, kBZ = 8;   // brick extent in y and z: 128 rows of M = 16 groups of 8 z-positions
 
 constexpr int largest_divisor_le(int n, int cap) {
   int best = 1;
@@ -36,12 +41,16 @@ constexpr int largest_divisor_le(int n, int cap) {
 }
 
 struct TcConvParams {
-  int n_cubes, X, Y, Z;          // input spatial extent (= virtual output grid; stride 1)
+  int X, Y, Z;                   // output grid of this launch (bricks enumerate it)
+  int n_outer;                   // leading (cube) dimension
   int bricks_x, bricks_y, bricks_z, n_bricks;
-  int n_chunks;                  // K chunks of (RB / 2) channels
-  int cout, cout_pitch;          // channels stored / distance between output positions (elements)
+  int n_tiles;                   // tiles of N output channels
+  int n_chunks;                  // K chunks of (RB / 2) input channels
+  int istride[3];                // input step per output step (x, y, z)
+  int origin[3];                 // input offset of tap 0 (x, y, z)
+  int cout, cout_pitch;          // channels computed / distance between output positions (elements)
   int TD, TH, TW;                // full output tensor extent
-  int ostride, ooff[3];          // output position = o * ostride + ooff (transposed-conv phases)
+  int ostride[3], ooff[3];       // output position = o * ostride + ooff (transposed-conv phases)
   int relu;
   int out_f32;                   // 1: store float32, 0: bf16
   const float* scale;
@@ -50,23 +59,23 @@ struct TcConvParams {
   void* out;
 };
 
-// KS kernel extent, RB bytes per smem row (= channels per K chunk * 2), N = MMA N (padded cout),
-// TX = x-slices (M tiles) per brick, G = taps per weight stage, S = weight stages.
-template <int KS, int RB, int N, int TX, int G, int S>
+// KSX / KS kernel extent along x / along y and z, RB bytes per smem row (= channels per K chunk * 2),
+// N = MMA N (output-channel tile), TX = x-slices (M tiles) per brick, G = taps per weight stage, S = weight stages.
+// HB = halo buffers (2 for the compute-heavy kernels, deeper for 1x1 where a work item is a few MMAs).
+template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB = 2>
 struct TcCfg {
-  static constexpr int P = KS / 2;
-  static constexpr int HX = TX + KS - 1, HY = kBY + KS - 1, HZ = kBZ + KS - 1;
+  static constexpr int HX = TX + KSX - 1, HY = kBY + KS - 1, HZ = kBZ + KS - 1;
   static constexpr int kHaloRows = HX * HY * HZ;
   static constexpr int kHaloBytes = kHaloRows * RB;
   static constexpr int kHaloStride = (kHaloBytes + 1023) / 1024 * 1024;
-  static constexpr int kTaps = KS * KS * KS;
+  static constexpr int kTaps = KSX * KS * KS;
   static constexpr int kGroups = kTaps / G;             // weight stages consumed per (brick, chunk)
   static constexpr int kTapBytes = N * RB;
   static constexpr int kWBytes = G * kTapBytes;         // one stage = G consecutive taps
   static constexpr int kWStride = (kWBytes + 1023) / 1024 * 1024;
   static constexpr int kTapsPerLoad = largest_divisor_le(G, 256 / N);   // TMA box rows <= 256
   static constexpr int kLoads = G / kTapsPerLoad;
-  static constexpr int kSmemBytes = 2 * kHaloStride + S * kWStride + 1024;   // + alignment slack
+  static constexpr int kSmemBytes = HB * kHaloStride + S * kWStride + 1024;   // + alignment slack
   static_assert(kTaps % G == 0, "taps per stage must divide the tap count");
   static constexpr int kKSteps = RB / 32;       // tcgen05.mma K = 16 bf16 = 32 bytes
   static constexpr int kIssuers = TX >= 2 ? 2 : 1;
@@ -75,27 +84,29 @@ struct TcCfg {
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
-template <int KS, int RB, int N, int TX, int G, int S>
+template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB>
 __global__ void __launch_bounds__(kTcThreads, 1)
-conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
-                 const TcConvParams p) {
-  using C = TcCfg<KS, RB, N, TX, G, S>;
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
+               const TcConvParams p) {
+  using C = TcCfg<KSX, KS, RB, N, TX, G, S, HB>;
   constexpr int kWStages = S;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t halo_full[2], halo_empty[2], w_full[kWStages], w_empty[kWStages], acc_full[2], acc_empty[2];
+  __shared__ uint64_t halo_full[HB], halo_empty[HB], w_full[kWStages], w_empty[kWStages], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_scale[N], s_shift[N];
+  __shared__ float s_scale[2][N], s_shift[2][N];      // per accumulator buffer (the channel tile may change per item)
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* halo = smem;                               // [2][kHaloStride]
-  uint8_t* wbuf = smem + 2 * C::kHaloStride;          // [kWStages][kWStride]
+  uint8_t* halo = smem;                               // [HB][kHaloStride]
+  uint8_t* wbuf = smem + HB * C::kHaloStride;         // [kWStages][kWStride]
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < HB; ++i) {
       mbar_init(&halo_full[i], 1);
       mbar_init(&halo_empty[i], C::kIssuers);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], C::kIssuers);
       mbar_init(&acc_empty[i], 128);
     }
@@ -105,9 +116,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_consta
     }
     fence_barrier_init();
   }
-  for (int i = tid; i < N; i += kTcThreads) {
-    s_scale[i] = (p.scale != nullptr && i < p.cout) ? p.scale[i] : 1.0f;
-    s_shift[i] = (p.shift != nullptr && i < p.cout) ? p.shift[i] : 0.0f;
+  for (int i = tid; i < 2 * N; i += kTcThreads) {     // channel tile 0 (the only one unless n_tiles > 1)
+    const int co = i % N;
+    s_scale[i / N][co] = (p.scale != nullptr && co < p.cout) ? p.scale[co] : 1.0f;
+    s_shift[i / N][co] = (p.shift != nullptr && co < p.cout) ? p.shift[co] : 0.0f;
   }
   if (warp == 0) {
     tmem_alloc(&tmem_base_s, 512);
@@ -122,7 +134,12 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);   // warp-uniform for the compiler
 
-  auto brick_coords = [&](int b, int& n, int& x0, int& y0, int& z0) {
+  // work item -> (outer index, brick origin in output coordinates, channel tile); the channel tile is the fastest
+  // index so that concurrently running CTAs share one input halo through L2
+  const int n_items = p.n_bricks * p.n_tiles;
+  auto item_coords = [&](int wi, int& n, int& x0, int& y0, int& z0, int& nt) {
+    nt = wi % p.n_tiles;
+    const int b = wi / p.n_tiles;
     const int bz = b % p.bricks_z;
     const int by = (b / p.bricks_z) % p.bricks_y;
     const int bx = (b / (p.bricks_z * p.bricks_y)) % p.bricks_x;
@@ -133,22 +150,24 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_consta
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ halo producer
     uint32_t u = 0;
-    for (int b = blockIdx.x; b < p.n_bricks; b += gridDim.x) {
-      int n, x0, y0, z0;
-      brick_coords(b, n, x0, y0, z0);
+    for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x) {
+      int n, x0, y0, z0, nt;
+      item_coords(wi, n, x0, y0, z0, nt);
       for (int c = 0; c < p.n_chunks; ++c, ++u) {
-        const uint32_t buf = u & 1;
-        mbar_wait(&halo_empty[buf], ((u >> 1) & 1) ^ 1);
+        const uint32_t buf = u % HB;
+        mbar_wait(&halo_empty[buf], ((u / HB) & 1) ^ 1);
         mbar_arrive_expect_tx(&halo_full[buf], C::kHaloBytes);
-        tma_load_5d(halo + buf * C::kHaloStride, &map_in, &halo_full[buf], c * (RB / 2), z0 - C::P, y0 - C::P,
-                    x0 - C::P, n);
+        tma_load_5d(halo + buf * C::kHaloStride, &map_in, &halo_full[buf], c * (RB / 2),
+                    z0 * p.istride[2] + p.origin[2], y0 * p.istride[1] + p.origin[1],
+                    x0 * p.istride[0] + p.origin[0], n);
       }
     }
   } else if (warp == 1 && lane == 0) {
     // ------------------------------------------------------------------ weight producer (G taps per stage)
-    // packed weights: rows ordered [chunk][tap][N]; a stage holds taps g*G .. g*G+G-1 of one chunk
+    // packed weights: rows ordered [n_tile][chunk][tap][N]; a stage holds taps g*G .. g*G+G-1 of one chunk
     uint32_t w = 0;
-    for (int b = blockIdx.x; b < p.n_bricks; b += gridDim.x) {
+    for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x) {
+      const int nt = wi % p.n_tiles;
       for (int c = 0; c < p.n_chunks; ++c) {
         for (int g = 0; g < C::kGroups; ++g, ++w) {
           const uint32_t st = w % kWStages;
@@ -157,26 +176,26 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_consta
 #pragma unroll 1
           for (int l = 0; l < C::kLoads; ++l)
             tma_load_2d(wbuf + st * C::kWStride + l * (C::kTapsPerLoad * C::kTapBytes), &map_w, &w_full[st], 0,
-                        ((c * C::kTaps + g * G) + l * C::kTapsPerLoad) * N);
+                        (((nt * p.n_chunks + c) * C::kTaps + g * G) + l * C::kTapsPerLoad) * N);
         }
       }
     }
   } else if ((warp == 2 || warp == 3) && (warp - 2) < C::kIssuers) {
     // ------------------------------------------------------------------ MMA issuers
-    // The whole warp runs this loop (warp-uniform control flow and values, so the descriptor arithmetic
-    // stays in uniform registers); only the tcgen05.mma / commit instructions are predicated on lane 0.
+    // The whole warp runs this loop (warp-uniform control flow and values); only the tcgen05.mma / commit
+    // instructions are predicated on the elected lane.
     const int q = warp - 2;
     const uint32_t idesc = make_idesc(kFmtBF16, 128, N);
     const uint64_t a_desc0 = make_smem_desc(smem_u32(halo), 0, C::HZ * RB, C::kLayout);
     const uint64_t b_desc0 = make_smem_desc(smem_u32(wbuf), 0, 8 * RB, C::kLayout);
     uint32_t u = 0, w = 0, it = 0;
-    for (int b = blockIdx.x; b < p.n_bricks; b += gridDim.x, ++it) {
+    for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x, ++it) {
       const uint32_t accbuf = it & 1;
       mbar_wait(&acc_empty[accbuf], ((it >> 1) & 1) ^ 1);
       tc_fence_after();
       for (int c = 0; c < p.n_chunks; ++c, ++u) {
-        const uint32_t buf = u & 1;
-        mbar_wait(&halo_full[buf], (u >> 1) & 1);
+        const uint32_t buf = u % HB;
+        mbar_wait(&halo_full[buf], (u / HB) & 1);
         // descriptor low words advance in 16-byte units; the high words (SBO, version, layout) never change
         const uint32_t a_lo0 = (uint32_t)a_desc0 + (uint32_t)((buf * C::kHaloStride) >> 4);
         const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
@@ -224,19 +243,32 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_consta
     const int ly = row >> 3, lz = row & 7;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t it = 0;
-    for (int b = blockIdx.x; b < p.n_bricks; b += gridDim.x, ++it) {
-      int n, x0, y0, z0;
-      brick_coords(b, n, x0, y0, z0);
+    for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x, ++it) {
+      int n, x0, y0, z0, nt;
+      item_coords(wi, n, x0, y0, z0, nt);
       const uint32_t accbuf = it & 1;
       mbar_wait(&acc_full[accbuf], (it >> 1) & 1);
       tc_fence_after();
       const int y = y0 + ly, z = z0 + lz;
+      const int ch0 = nt * N;                  // first output channel of this tile
+      if (p.n_tiles > 1) {
+        // this item's scale/shift into the accumulator buffer's slot: every reader of the slot's previous
+        // contents (two items ago) has arrived on acc_empty before this item's acc_full could complete
+        if (row < N) {
+          const int co = ch0 + row;
+          s_scale[accbuf][row] = (p.scale != nullptr && co < p.cout) ? __ldg(p.scale + co) : 1.0f;
+          s_shift[accbuf][row] = (p.shift != nullptr && co < p.cout) ? __ldg(p.shift + co) : 0.0f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      const float* sc_s = s_scale[p.n_tiles > 1 ? accbuf : 0];
+      const float* sh_s = s_shift[p.n_tiles > 1 ? accbuf : 0];
 #pragma unroll
       for (int t = 0; t < TX; ++t) {
         const int x = x0 + t;
         const bool in_range = (x < p.X) && (y < p.Y) && (z < p.Z);
-        const int64_t pos = (((int64_t)n * p.TD + (x * p.ostride + p.ooff[0])) * p.TH + (y * p.ostride + p.ooff[1])) * p.TW +
-                            (z * p.ostride + p.ooff[2]);
+        const int64_t pos = (((int64_t)n * p.TD + (x * p.ostride[0] + p.ooff[0])) * p.TH + (y * p.ostride[1] + p.ooff[1])) *
+                                p.TW + (z * p.ostride[2] + p.ooff[2]);
         const uint32_t taddr = tmem_base + lane_base + (accbuf * TX + t) * N;
 #pragma unroll
         for (int n0 = 0; n0 < N; n0 += 16) {
@@ -244,30 +276,31 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_consta
           tmem_ld_x16(taddr + n0, v);      // warp-collective: every lane takes part, stores are predicated
           tmem_ld_wait();
           if (!in_range) continue;
+          const int cbase = ch0 + n0;
           float f[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float r = __uint_as_float(v[j]) * s_scale[n0 + j] + s_shift[n0 + j];
+            float r = __uint_as_float(v[j]) * sc_s[n0 + j] + sh_s[n0 + j];
             if (p.relu == 2) r = fmaxf(r, 0.0f);
             f[j] = r;
           }
           if (p.out_f32) {
-            float* o = reinterpret_cast<float*>(p.out) + pos * p.cout_pitch + n0;
-            const float* rs = p.residual ? reinterpret_cast<const float*>(p.residual) + pos * p.cout_pitch + n0 : nullptr;
+            float* o = reinterpret_cast<float*>(p.out) + pos * p.cout_pitch + cbase;
+            const float* rs = p.residual ? reinterpret_cast<const float*>(p.residual) + pos * p.cout_pitch + cbase : nullptr;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              if (n0 + j < p.cout_pitch) {
+              if (cbase + j < p.cout_pitch) {
                 float r = f[j];
                 if (rs) r += rs[j];
                 if (p.relu == 1) r = fmaxf(r, 0.0f);
-                o[j] = (n0 + j < p.cout) ? r : 0.0f;
+                o[j] = (cbase + j < p.cout) ? r : 0.0f;
               }
             }
           } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pos * p.cout_pitch + n0;
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pos * p.cout_pitch + cbase;
             const __nv_bfloat16* rs =
-                p.residual ? reinterpret_cast<const __nv_bfloat16*>(p.residual) + pos * p.cout_pitch + n0 : nullptr;
-            if (n0 + 16 <= p.cout_pitch && (p.cout_pitch & 7) == 0) {   // full group of 16 channels: two 16-byte stores
+                p.residual ? reinterpret_cast<const __nv_bfloat16*>(p.residual) + pos * p.cout_pitch + cbase : nullptr;
+            if (cbase + 16 <= p.cout_pitch && (p.cout_pitch & 7) == 0) {   // full group of 16 channels: two 16-byte stores
               uint4 rv[2];
               if (rs) {
                 rv[0] = *reinterpret_cast<const uint4*>(rs);
@@ -280,18 +313,18 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_consta
                 float r = f[j];
                 if (rs) r += __bfloat162float(rb[j]);
                 if (p.relu == 1) r = fmaxf(r, 0.0f);
-                ob[j] = __float2bfloat16_rn((n0 + j < p.cout) ? r : 0.0f);
+                ob[j] = __float2bfloat16_rn((cbase + j < p.cout) ? r : 0.0f);
               }
               *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(ob);
               *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<const uint4*>(ob + 8);
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                if (n0 + j < p.cout_pitch) {
+                if (cbase + j < p.cout_pitch) {
                   float r = f[j];
                   if (rs) r += __bfloat162float(rs[j]);
                   if (p.relu == 1) r = fmaxf(r, 0.0f);
-                  o[j] = __float2bfloat16_rn((n0 + j < p.cout) ? r : 0.0f);
+                  o[j] = __float2bfloat16_rn((cbase + j < p.cout) ? r : 0.0f);
                 }
               }
             }
@@ -330,28 +363,31 @@ static CUtensorMapSwizzle swizzle_for(int rb) {
   return rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
-template <int KS, int RB, int N, int TX, int G, int S>
+template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB>
 static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
-  using C = TcCfg<KS, RB, N, TX, G, S>;
+  using C = TcCfg<KSX, KS, RB, N, TX, G, S, HB>;
   EncodeTiledFn encode = get_encode();
   if (encode == nullptr) return SP3D_ERR_UNSUPPORTED;
   const int chunk_ch = RB / 2;
   const int n_chunks = (a->cin + chunk_ch - 1) / chunk_ch;
+  const int n_tiles = (a->cout + N - 1) / N;
 
   CUtensorMap map_in, map_w;
-  {  // activations: [N][X][Y][Z][cin_pitch] bf16, box = {chunk, HZ, HY, HX, 1}
+  {  // activations: [N][D][H][W][cin_pitch] bf16; box = {chunk, HZ, HY, HX, 1} positions, stepped by the conv stride
     cuuint64_t gdim[5] = {(cuuint64_t)a->cin_pitch, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->D, (cuuint64_t)a->N};
     cuuint64_t gstr[4] = {(cuuint64_t)a->cin_pitch * 2, (cuuint64_t)a->cin_pitch * 2 * a->W,
                           (cuuint64_t)a->cin_pitch * 2 * a->W * a->H, (cuuint64_t)a->cin_pitch * 2 * a->W * a->H * a->D};
-    cuuint32_t box[5] = {(cuuint32_t)chunk_ch, (cuuint32_t)C::HZ, (cuuint32_t)C::HY, (cuuint32_t)C::HX, 1};
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    cuuint32_t es[5] = {1, (cuuint32_t)a->stride[2], (cuuint32_t)a->stride[1], (cuuint32_t)a->stride[0], 1};
+    // with an element stride s the box extent is given in traversed elements: ceil(box / s) elements are loaded
+    cuuint32_t box[5] = {(cuuint32_t)chunk_ch, (cuuint32_t)(C::HZ * a->stride[2]), (cuuint32_t)(C::HY * a->stride[1]),
+                         (cuuint32_t)(C::HX * a->stride[0]), 1};
     if (encode(&map_in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(a->in), gdim, gstr, box, es,
                CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(RB), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return SP3D_ERR_INVALID_ARG;
   }
-  {  // weights: [n_chunks * taps * N rows][chunk channels] bf16 (K-major rows), box = {chunk, taps_per_load * N}
-    cuuint64_t gdim[2] = {(cuuint64_t)chunk_ch, (cuuint64_t)C::kTaps * n_chunks * N};
+  {  // weights: [n_tiles * n_chunks * taps * N rows][chunk channels] bf16 (K-major rows), box = {chunk, taps_per_load * N}
+    cuuint64_t gdim[2] = {(cuuint64_t)chunk_ch, (cuuint64_t)C::kTaps * n_chunks * n_tiles * N};
     cuuint64_t gstr[1] = {(cuuint64_t)RB};
     cuuint32_t box[2] = {(cuuint32_t)chunk_ch, (cuuint32_t)(C::kTapsPerLoad * N)};
     cuuint32_t es[2] = {1, 1};
@@ -361,16 +397,21 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
       return SP3D_ERR_INVALID_ARG;
   }
   TcConvParams p{};
-  p.n_cubes = a->N; p.X = a->D; p.Y = a->H; p.Z = a->W;
-  p.bricks_x = (a->D + TX - 1) / TX;
-  p.bricks_y = (a->H + kBY - 1) / kBY;
-  p.bricks_z = (a->W + kBZ - 1) / kBZ;
+  p.n_outer = a->N; p.X = a->OD; p.Y = a->OH; p.Z = a->OW;
+  p.bricks_x = (a->OD + TX - 1) / TX;
+  p.bricks_y = (a->OH + kBY - 1) / kBY;
+  p.bricks_z = (a->OW + kBZ - 1) / kBZ;
   p.n_bricks = a->N * p.bricks_x * p.bricks_y * p.bricks_z;
+  p.n_tiles = n_tiles;
   p.n_chunks = n_chunks;
+  for (int d = 0; d < 3; ++d) {
+    p.istride[d] = a->stride[d];
+    p.origin[d] = a->tap_off0[d];
+    p.ostride[d] = a->ostride[d];
+    p.ooff[d] = a->ooffset[d];
+  }
   p.cout = a->cout; p.cout_pitch = a->cout_pitch;
   p.TD = a->TD; p.TH = a->TH; p.TW = a->TW;
-  p.ostride = a->ostride[0];
-  p.ooff[0] = a->ooffset[0]; p.ooff[1] = a->ooffset[1]; p.ooff[2] = a->ooffset[2];
   p.relu = a->relu;
   p.out_f32 = a->out_dtype == SP3D_F32;
   p.scale = a->scale; p.shift = a->shift; p.residual = a->residual; p.out = a->out;
@@ -381,47 +422,55 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   }
-  auto kern = conv3d_tc_kernel<KS, RB, N, TX, G, S>;
+  auto kern = conv_tc_kernel<KSX, KS, RB, N, TX, G, S, HB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
   if (e != cudaSuccess) { set_last_error(e); return SP3D_ERR_LAUNCH; }
-  const int grid = p.n_bricks < n_sm ? p.n_bricks : n_sm;
+  const int items = p.n_bricks * p.n_tiles;
+  const int grid = items < n_sm ? items : n_sm;
   kern<<<grid, kTcThreads, C::kSmemBytes, st>>>(map_in, map_w, p);
   return check_launch();
 }
 
-// Shapes taken by the tensor-core path (everything V2VNet needs).  cin here is the padded channel count.
+// Shapes taken by the tensor-core path.  `cin` is the padded channel count (a multiple of 16, or of 64 above 64),
+// `cout_pitch_w` the output-channel tile N the weights were packed for.
 int conv_tc(const sp3d_conv_args* a, cudaStream_t st) {
   if (a->algo != SP3D_CONV_TC_BF16) return SP3D_ERR_UNSUPPORTED;   // TF32x3 variant: not built yet
   if (a->in_dtype != SP3D_BF16) return SP3D_ERR_UNSUPPORTED;
   if (a->out_dtype != SP3D_BF16 && a->out_dtype != SP3D_F32) return SP3D_ERR_UNSUPPORTED;
-  const int ks = a->ksize[0];
-  if (a->ksize[1] != ks || a->ksize[2] != ks) return SP3D_ERR_UNSUPPORTED;
-  for (int d = 0; d < 3; ++d) {
-    if (a->stride[d] != 1 || a->tap_step[d] != 1 || a->tap_off0[d] != -(ks / 2)) return SP3D_ERR_UNSUPPORTED;
-    if (a->ostride[d] != a->ostride[0]) return SP3D_ERR_UNSUPPORTED;
-  }
-  if (a->OD != a->D || a->OH != a->H || a->OW != a->W) return SP3D_ERR_UNSUPPORTED;
+  const int ks = a->ksize[1], ksx = a->ksize[0];
+  if (a->ksize[2] != ks || (ksx != ks && ksx != 1)) return SP3D_ERR_UNSUPPORTED;
+  for (int d = 0; d < 3; ++d)
+    if (a->tap_step[d] != 1 || a->stride[d] < 1 || a->stride[d] > 2) return SP3D_ERR_UNSUPPORTED;
+  if (a->stride[0] != 1 || a->stride[1] != a->stride[2]) return SP3D_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(a->in) % 16) || (reinterpret_cast<uintptr_t>(a->weight) % 16) ||
       (reinterpret_cast<uintptr_t>(a->out) % 16) || (a->cin_pitch % 8))
     return SP3D_ERR_INVALID_ARG;
-  const int cin = a->cin, n = a->cout_pitch_w;   // packed weight rows per tap = N of the MMA
-  if (a->cout > n) return SP3D_ERR_INVALID_ARG;
-  // (kernel, padded cin, row bytes, N, x-slices per brick, taps per weight stage, weight stages)
-#define SP3D_TC_CASE(KS_, CIN_, RB_, N_, TX_, G_, S_) \
-  if (ks == KS_ && cin == CIN_ && n == N_) return launch_tc<KS_, RB_, N_, TX_, G_, S_>(a, st);
-  SP3D_TC_CASE(7, 16, 32, 16, 2, 49, 2)
-  SP3D_TC_CASE(3, 16, 32, 32, 4, 27, 2)
-  SP3D_TC_CASE(3, 32, 64, 32, 4, 9, 3)
-  SP3D_TC_CASE(3, 32, 64, 64, 4, 9, 2)
-  SP3D_TC_CASE(3, 64, 128, 64, 2, 1, 4)
-  SP3D_TC_CASE(3, 64, 128, 128, 2, 1, 2)
-  SP3D_TC_CASE(3, 128, 128, 128, 2, 1, 2)
-  SP3D_TC_CASE(1, 16, 32, 32, 4, 1, 2)
-  SP3D_TC_CASE(1, 32, 64, 64, 4, 1, 2)
-  SP3D_TC_CASE(1, 64, 128, 128, 2, 1, 2)
-  SP3D_TC_CASE(1, 32, 64, 16, 4, 1, 2)
-  SP3D_TC_CASE(1, 128, 128, 64, 4, 1, 2)
-  SP3D_TC_CASE(1, 64, 128, 32, 4, 1, 2)
+  const int cin = a->cin, n = a->cout_pitch_w;
+  const int rb = cin >= 64 ? 128 : cin * 2;
+  if (cin >= 64 && (cin % 64)) return SP3D_ERR_UNSUPPORTED;
+  if (a->cin_pitch < cin) return SP3D_ERR_INVALID_ARG;
+  // (kernel x, kernel yz, row bytes, N, x-slices per brick, taps per weight stage, weight stages)
+#define SP3D_TC_CASE(KSX_, KS_, RB_, N_, TX_, G_, S_, HB_) \
+  if (ksx == KSX_ && ks == KS_ && rb == RB_ && n == N_) return launch_tc<KSX_, KS_, RB_, N_, TX_, G_, S_, HB_>(a, st);
+  // 3-D (V2VNet)
+  SP3D_TC_CASE(7, 7, 32, 16, 2, 49, 2, 2)
+  SP3D_TC_CASE(3, 3, 32, 32, 4, 27, 2, 2)
+  SP3D_TC_CASE(3, 3, 64, 32, 4, 9, 3, 2)
+  SP3D_TC_CASE(3, 3, 64, 64, 4, 9, 2, 2)
+  SP3D_TC_CASE(3, 3, 128, 64, 2, 1, 4, 2)
+  SP3D_TC_CASE(3, 3, 128, 128, 2, 1, 2, 2)
+  // 1x1(x1) on any rank: a work item is a handful of MMAs, so the halo ring is deeper
+  SP3D_TC_CASE(1, 1, 32, 32, 4, 1, 2, 6)
+  SP3D_TC_CASE(1, 1, 64, 64, 4, 1, 2, 4)
+  SP3D_TC_CASE(1, 1, 64, 16, 4, 1, 2, 4)
+  SP3D_TC_CASE(1, 1, 128, 16, 4, 1, 2, 3)
+  SP3D_TC_CASE(1, 1, 128, 32, 4, 1, 2, 3)
+  SP3D_TC_CASE(1, 1, 128, 64, 4, 1, 4, 3)
+  SP3D_TC_CASE(1, 1, 128, 128, 2, 1, 4, 4)
+  // 2-D (PoseResNet): 3x3, and the 2x2 sub-kernels of the 4x4 stride-2 transposed convolutions
+  SP3D_TC_CASE(1, 3, 128, 64, 4, 1, 4, 2)
+  SP3D_TC_CASE(1, 3, 128, 128, 2, 3, 2, 2)
+  SP3D_TC_CASE(1, 2, 128, 128, 2, 2, 3, 2)
 #undef SP3D_TC_CASE
   return SP3D_ERR_UNSUPPORTED;
 }

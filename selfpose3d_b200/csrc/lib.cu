@@ -35,14 +35,16 @@ extern "C" const char* sp3d_last_cuda_error(void) { return sp3d::g_last_error; }
 extern "C" int sp3d_conv_fwd(const sp3d_conv_args* a, void* stream) {
   using namespace sp3d;
   if (a == nullptr || a->in == nullptr || a->weight == nullptr || a->out == nullptr || a->N < 0 || a->cin < 1 ||
-      a->cout < 1 || a->cout_pitch < a->cout || a->cout_pitch_w < a->cout || a->OD < 0 || a->OH < 0 || a->OW < 0)
+      a->cout < 1 || a->cout_pitch < a->cout || a->cout_pitch_w < 1 || a->OD < 0 || a->OH < 0 || a->OW < 0)
     return SP3D_ERR_INVALID_ARG;
   for (int d = 0; d < 3; ++d)
     if (a->ksize[d] < 1 || a->stride[d] < 1 || a->ostride[d] < 1 || a->ooffset[d] < 0) return SP3D_ERR_INVALID_ARG;
   if ((int64_t)a->N * a->OD * a->OH * a->OW == 0) return SP3D_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (a->algo) {
-    case SP3D_CONV_SIMT_F32: return conv_simt_f32(a, st);
+    case SP3D_CONV_SIMT_F32:
+      if (a->cout_pitch_w < a->cout) return SP3D_ERR_INVALID_ARG;
+      return conv_simt_f32(a, st);
     case SP3D_CONV_TC_BF16:
     case SP3D_CONV_TC_TF32X3: return conv_tc(a, st);
     default: return SP3D_ERR_UNSUPPORTED;

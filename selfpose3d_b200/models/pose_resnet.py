@@ -153,14 +153,16 @@ class PoseResNet(nn.Module):
         """``x``: channel-last ``[N,1,H,W,4]`` float32 image batch -> ``(heat-maps [N,1,h,w,pitch], features)``."""
         _no_train(self)
         stem, deconvs, head = self._packed()
-        x = stem(x)
+        # bf16 mode: the 7x7 stem reads the float32 image and writes bf16; from there on activations are bf16
+        # (tcgen05 convolutions where the shape is covered) and the heat-maps leave the net in float32
+        x = stem(x, out_dtype=torch.bfloat16 if ops.volume_dtype() == torch.bfloat16 else None)
         x = ops.maxpool(x, 64, [1, 3, 3], [1, 2, 2], [0, 1, 1])
         for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
             for blk in layer:
                 x = blk.forward_cl(x)
         for d in deconvs:
             x = d(x)
-        return head(x, out_pitch=out_pitch), x
+        return head(x, out_pitch=out_pitch, out_dtype=torch.float32), x
 
     def forward(self, x, attn=False):
         """``[N,3,H,W]`` -> ``[N,J,H/4,W/4]`` (reference :191-207).  The result is a zero-copy

@@ -381,30 +381,40 @@ class PackedConv:
 
     # ------------------------------------------------------------------ tcgen05 (bf16) path
     def tc_supported(self):
-        """Stride-1 "same" 3-D convolutions with k in {1,3,7} and k2/s2 transposed convolutions."""
-        if self.nd != 3:
-            return False
-        if self.transposed:
-            return self.k == [2, 2, 2] and self.stride == [2, 2, 2] and self.padding == [0, 0, 0]
-        return (self.k[0] in (1, 3, 7) and self.k == [self.k[0]] * 3 and self.stride == [1, 1, 1]
-                and self.padding == [self.k[0] // 2] * 3)
+        """What ``csrc/conv_tc.cu`` takes: 3-D "same" convolutions with k in {1,3,7} and k2/s2 transposed
+        convolutions (V2VNet); 2-D 1x1 (stride 1 or 2), 3x3 stride-1 "same" convolutions and k4/s2/p1
+        transposed convolutions on >= 64 input channels (PoseResNet)."""
+        k, s, p = self.k, self.stride, self.padding
+        if self.nd == 3:
+            if self.transposed:
+                return k == [2, 2, 2] and s == [2, 2, 2] and p == [0, 0, 0]
+            return k[0] in (1, 3, 7) and k == [k[0]] * 3 and s == [1, 1, 1] and p == [k[0] // 2] * 3
+        if self.nd == 2 and self.cin % 64 == 0:
+            if self.transposed:
+                return k == [1, 4, 4] and s == [1, 2, 2] and p == [0, 1, 1]
+            if k == [1, 1, 1]:
+                return s in ([1, 1, 1], [1, 2, 2]) and p == [0, 0, 0]
+            return k == [1, 3, 3] and s == [1, 1, 1] and p == [0, 1, 1]
+        return False
 
     def _tc_pack(self):
-        """bf16 weights ``[n_chunks, taps, N, chunk]`` (rows = output channel, K-major), N = cout padded to a
-        tcgen05 N in {16,32,64,128}, chunk = min(cin padded to 16, 64) channels (= one swizzled smem row)."""
+        """bf16 weights ``[n_tiles, n_chunks, taps, N, chunk]`` (rows = output channel, K-major): N = output-channel
+        tile (cout padded to 16/32/64/128, or tiles of 128), chunk = min(cin padded to 16, 64) channels (= one
+        swizzled smem row).  Taps are ordered by ascending input offset (transposed sub-kernels are flipped)."""
         if self._tc is None:
-            n = next(v for v in (16, 32, 64, 128) if v >= self.cout)
-            cin_tc = round_up(self.cin, 16)
+            n = next((v for v in (16, 32, 64, 128) if v >= self.cout), 128)
+            n_tiles = -(-self.cout // n)
+            cin_tc = round_up(self.cin, 16) if self.cin < 64 else round_up(self.cin, 64)
             chunk = min(cin_tc, 64)
-            if cin_tc % chunk:
-                raise _lib.Sp3dError("unsupported channel count %d for the tensor-core path" % self.cin)
             packs = []
             for sub in self._subs:
+                if self.transposed:
+                    sub = sub.flip(2, 3, 4)
                 taps = int(sub.shape[2] * sub.shape[3] * sub.shape[4])
                 t = sub.permute(2, 3, 4, 0, 1).reshape(taps, self.cout, self.cin)
-                full = torch.zeros(taps, n, cin_tc, device=sub.device, dtype=torch.float32)
+                full = torch.zeros(taps, n_tiles * n, cin_tc, device=sub.device, dtype=torch.float32)
                 full[:, :self.cout, :self.cin] = t
-                full = full.reshape(taps, n, cin_tc // chunk, chunk).permute(2, 0, 1, 3)
+                full = full.reshape(taps, n_tiles, n, cin_tc // chunk, chunk).permute(1, 3, 0, 2, 4)
                 packs.append(full.to(torch.bfloat16).contiguous())
             self._tc = (packs, n, cin_tc)
         return self._tc
@@ -422,30 +432,41 @@ class PackedConv:
         out = torch.empty((N, o[0], o[1], o[2], out_pitch), device=x.device, dtype=out_dtype)
         if residual is not None and (residual.dtype != out_dtype or residual.shape != out.shape):
             raise _lib.Sp3dError("residual must match the output dtype and shape")
+        xk, outk, resk = x, out, residual
+        if self.nd == 2:   # image batch -> the brick's x axis: [N,1,H,W,C] viewed as [1,N,H,W,C]
+            xk = x.view(1, N, H, W, pitch)
+            outk = out.view(1, N, o[1], o[2], out_pitch)
+            resk = residual.view(1, N, o[1], o[2], out_pitch) if residual is not None else None
+            D, o = N, [N, o[1], o[2]]
         if not self.transposed:
-            conv_launch(x, packs[0], self.scale, self.shift, residual, out, cin_tc, self.cout, o, self.k, [1, 1, 1],
+            conv_launch(xk, packs[0], self.scale, self.shift, resk, outk, cin_tc, self.cout, o, self.k, self.stride,
                         [-p for p in self.padding], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu, _lib.CONV_TC_BF16,
                         cin_real=self.cin, cout_pitch_w=n)
         else:
             for wgt, (phase, off0, ks) in zip(packs, self.phases):
-                conv_launch(x, wgt, self.scale, self.shift, residual, out, cin_tc, self.cout, (D, H, W), ks, [1, 1, 1],
-                            off0, [1, 1, 1], self.stride, phase, self.relu, _lib.CONV_TC_BF16, cin_real=self.cin,
+                origin = [off0[i] - (ks[i] - 1) for i in range(3)]     # taps ascend from the lowest input offset
+                conv_launch(xk, wgt, self.scale, self.shift, resk, outk, cin_tc, self.cout, (D, H, W), ks, [1, 1, 1],
+                            origin, [1, 1, 1], self.stride, phase, self.relu, _lib.CONV_TC_BF16, cin_real=self.cin,
                             cout_pitch_w=n)
         return out
 
     def __call__(self, x, residual=None, out_pitch=None, algo=None, out_dtype=None):
-        """``x``: channel-last ``[N,D,H,W,pitch]``.  float32 activations take the float32 SIMT kernel,
-        bf16 activations the tcgen05 kernel (``out_dtype`` float32 there gives a float32 result)."""
+        """``x``: channel-last ``[N,D,H,W,pitch]``.  float32 activations take the float32 SIMT kernel; bf16
+        activations the tcgen05 kernel where the shape is covered (``out_dtype`` float32 there gives a float32
+        result), else the SIMT kernel with bf16 storage and float32 math."""
         if algo is None:
-            algo = _lib.CONV_TC_BF16 if x.dtype == torch.bfloat16 else _lib.CONV_SIMT_F32
+            algo = _lib.CONV_TC_BF16 if (x.dtype == torch.bfloat16 and self.tc_supported()) else _lib.CONV_SIMT_F32
         if algo == _lib.CONV_TC_BF16:
             return self._call_tc(x, residual, out_pitch, out_dtype)
         N, D, H, W, pitch = [int(v) for v in x.shape]
         if pitch < self.cin_p:
             raise _lib.Sp3dError("activation pitch %d smaller than packed cin %d" % (pitch, self.cin_p))
         o = self.out_shape((D, H, W))
-        out_pitch = round_up(self.cout, 4) if out_pitch is None else int(out_pitch)
-        out = torch.empty((N, o[0], o[1], o[2], out_pitch), device=x.device, dtype=torch.float32)
+        if out_dtype is None:
+            out_dtype = x.dtype
+        if out_pitch is None:
+            out_pitch = round_up(self.cout, 4 if out_dtype == torch.float32 else 16)
+        out = torch.empty((N, o[0], o[1], o[2], int(out_pitch)), device=x.device, dtype=out_dtype)
         if not self.transposed:
             conv_launch(x, self.weights[0], self.scale, self.shift, residual, out, self.cin_p, self.cout, o, self.k,
                         self.stride, [-p for p in self.padding], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu, algo,

@@ -125,3 +125,66 @@ def test_output_pitch_one_and_padding_lanes_zero():
     conv = nn.Conv3d(8, 15, 1)
     y = ops.PackedConv(conv.weight, conv.bias, None, 1, 0)(cl(x))
     assert y.shape[-1] == 16 and not y[..., 15].any()
+
+
+# ---------------------------------------------------------------------------------------------- tcgen05 packing
+def emulate_any_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksize, stride, tap_off0,
+                       tap_step, ostride, ooffset, relu, algo=0, cin_real=None, cout_pitch_w=None):
+    """Dispatch on the packing: the tensor-core launch carries [n_tiles, n_chunks, taps, N, chunk] bf16 weights."""
+    if algo == 1:
+        nt, nc, taps, n, chunk = weight.shape
+        weight = weight.float().permute(2, 1, 4, 0, 3).reshape(taps, nc * chunk, nt * n)
+        assert cout_pitch_w == n and cin == nc * chunk
+    emulate_conv_launch(x.float(), weight, scale, shift, None if residual is None else residual.float(), out, cin, cout,
+                        out_grid, ksize, stride, tap_off0, tap_step, ostride, ooffset, relu)
+
+
+def cl16(x):   # bf16 channel-last, pitch rounded to 16
+    if x.dim() == 4:
+        x = x.unsqueeze(2)
+    N, C = x.shape[:2]
+    out = torch.zeros((N,) + tuple(x.shape[2:]) + (ops.round_up(C, 16),))
+    out[..., :C] = x.permute(0, 2, 3, 4, 1)
+    return out.to(torch.bfloat16)
+
+
+def bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("case", ["1x1", "1x1s2", "3x3", "deconv", "3d_k3", "3d_convT"])
+def test_tensorcore_lowering(monkeypatch, case):
+    monkeypatch.setattr(ops, "conv_launch", emulate_any_launch)
+    torch.manual_seed(7)
+    if case in ("1x1", "1x1s2", "3x3"):
+        k, s, p = {"1x1": (1, 1, 0), "1x1s2": (1, 2, 0), "3x3": (3, 1, 1)}[case]
+        conv, bn = nn.Conv2d(64, 256, k, s, p, bias=False), rand_bn(nn.BatchNorm2d(256))
+        conv.weight.data = bf(conv.weight.data)
+        x = bf(torch.randn(3, 64, 9, 7))
+        want = F.relu(bn(conv(x)))
+        pc = ops.PackedConv(conv.weight, None, bn, s, p, relu=1)
+        assert pc.tc_supported()
+        got = cf(pc(cl16(x), out_dtype=torch.float32), 256, 2)
+    elif case == "deconv":
+        ct, bn = nn.ConvTranspose2d(64, 256, 4, 2, 1, bias=False), rand_bn(nn.BatchNorm2d(256))
+        ct.weight.data = bf(ct.weight.data)
+        x = bf(torch.randn(2, 64, 5, 3))
+        want = F.relu(bn(ct(x)))
+        pc = ops.PackedConv(ct.weight, None, bn, 2, 1, transposed=True, relu=1)
+        assert pc.tc_supported()
+        got = cf(pc(cl16(x), out_dtype=torch.float32), 256, 2)
+    elif case == "3d_k3":
+        conv, bn = nn.Conv3d(128, 128, 3, 1, 1), rand_bn(nn.BatchNorm3d(128))
+        conv.weight.data = bf(conv.weight.data)
+        x = bf(torch.randn(1, 128, 4, 5, 3))
+        want = F.relu(bn(conv(x)))
+        pc = ops.PackedConv(conv.weight, conv.bias, bn, 1, 1, relu=1)
+        got = cf(pc(cl16(x), out_dtype=torch.float32), 128, 3)
+    else:
+        ct, bn = nn.ConvTranspose3d(128, 64, 2, 2), rand_bn(nn.BatchNorm3d(64))
+        ct.weight.data = bf(ct.weight.data)
+        x = bf(torch.randn(1, 128, 3, 2, 4))
+        want = F.relu(bn(ct(x)))
+        pc = ops.PackedConv(ct.weight, ct.bias, bn, 2, 0, transposed=True, relu=2)
+        got = cf(pc(cl16(x), out_dtype=torch.float32), 64, 3)
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)

@@ -108,3 +108,88 @@ def test_v2v_net_bf16_mode_vs_float64_oracle():
         err = float((y - y64).abs().max()) / float(y64.abs().max())
         print("V2VNet(%d) bf16 mode: max error / output range = %.3g" % (cin, err))
         assert err < 5e-2, err
+
+
+# ------------------------------------------------------------------------------------------ 2-D (PoseResNet) shapes
+CONV2D_CASES = [(1, 1, 0, 64, 64), (1, 1, 0, 64, 256), (1, 1, 0, 256, 64), (1, 1, 0, 1024, 512), (1, 2, 0, 256, 512),
+                (3, 1, 1, 64, 64), (3, 1, 1, 128, 128), (3, 1, 1, 256, 256), (1, 1, 0, 256, 15)]
+
+
+@pytest.mark.parametrize("k,s,p,cin,cout", CONV2D_CASES)
+def test_tc_conv2d_matches_float64_reference(k, s, p, cin, cout):
+    torch.manual_seed(k * 100 + s * 10 + cin + cout)
+    conv = nn.Conv2d(cin, cout, k, s, p, bias=(cout == 15))
+    bn = rand_bn(nn.BatchNorm2d(cout), cin + cout)
+    with torch.no_grad():
+        conv.weight.copy_(bf16_round(conv.weight * (1.0 / (cin ** 0.5))))
+    x = bf16_round(torch.randn(5, cin, 21, 13))
+    with torch.no_grad():
+        y0 = bn.double()(conv.double()(x.double()))
+    res = bf16_round(torch.randn(*y0.shape))
+    want = F.relu(y0 + res.double())
+    conv, bn = conv.float().to(DEV), bn.float().to(DEV)
+    pc = ops.PackedConv(conv.weight, conv.bias, bn, s, p, relu=1)
+    assert pc.tc_supported()
+    pitch = ops.round_up(cout, 16)
+    xcl = ops.to_channel_last(x.unsqueeze(2).to(DEV), c_pitch=cin, dtype=torch.bfloat16)
+    res_cl = ops.to_channel_last(res.unsqueeze(2).to(DEV), c_pitch=pitch, dtype=torch.float32)
+    y = pc(xcl, residual=res_cl, out_pitch=pitch, out_dtype=torch.float32)
+    got = ops.to_channel_first(y, cout)[:, :, 0].cpu().double()
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) <= 2e-5 * scale, float((got - want).abs().max()) / scale
+
+
+@pytest.mark.parametrize("cin", [256, 2048])
+def test_tc_deconv2d_k4s2_matches_float64_reference(cin):
+    torch.manual_seed(cin)
+    ct = nn.ConvTranspose2d(cin, 256, 4, 2, 1, bias=False)
+    bn = rand_bn(nn.BatchNorm2d(256), cin)
+    with torch.no_grad():
+        ct.weight.copy_(bf16_round(ct.weight))
+    x = bf16_round(torch.randn(3, cin, 12, 9))
+    with torch.no_grad():
+        want = F.relu(bn.double()(ct.double()(x.double())))
+    ct, bn = ct.float().to(DEV), bn.float().to(DEV)
+    pc = ops.PackedConv(ct.weight, None, bn, 2, 1, transposed=True, relu=1)
+    assert pc.tc_supported()
+    xcl = ops.to_channel_last(x.unsqueeze(2).to(DEV), c_pitch=cin, dtype=torch.bfloat16)
+    y = pc(xcl, out_pitch=256, out_dtype=torch.float32)
+    got = ops.to_channel_first(y, 256)[:, :, 0].cpu().double()
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) <= 2e-5 * scale, float((got - want).abs().max()) / scale
+
+
+def test_simt_conv_bf16_storage_strided():
+    """3x3 stride-2 and the 7x7 stride-2 stem stay on the float32-math SIMT kernel with bf16 storage."""
+    torch.manual_seed(3)
+    conv = nn.Conv2d(64, 64, 3, 2, 1, bias=False)
+    bn = rand_bn(nn.BatchNorm2d(64), 9)
+    with torch.no_grad():
+        conv.weight.copy_(bf16_round(conv.weight))
+    x = bf16_round(torch.randn(2, 64, 17, 11))
+    with torch.no_grad():
+        want = F.relu(bn.double()(conv.double()(x.double())))
+    conv, bn = conv.float().to(DEV), bn.float().to(DEV)
+    pc = ops.PackedConv(conv.weight, None, bn, 2, 1, relu=1)
+    assert not pc.tc_supported()
+    xcl = ops.to_channel_last(x.unsqueeze(2).to(DEV), c_pitch=64, dtype=torch.bfloat16)
+    y = pc(xcl)
+    assert y.dtype == torch.bfloat16
+    got = ops.to_channel_first(y, 64, dtype=torch.float32)[:, :, 0].cpu().double()
+    assert float((got - want).abs().max()) <= 6e-3 * float(want.abs().max())
+
+
+def test_pose_resnet_bf16_mode_vs_reference_golden(golden):
+    from selfpose3d_b200.config import default_config
+    from selfpose3d_b200.models import pose_resnet
+    g = golden("pose_resnet50")
+    net = pose_resnet.get_pose_net(default_config(), is_train=False)
+    net.load_state_dict(synthetic.trained_like_state_dict(net, seed=int(g["seed"])), strict=True)
+    ops.set_volume_dtype(torch.bfloat16)
+    try:
+        y = net.to(DEV).eval()(torch.from_numpy(g["x"]).to(DEV)).cpu().numpy()
+    finally:
+        ops.set_volume_dtype(torch.float32)
+    err = float(np.abs(y - g["y"]).max()) / float(np.abs(g["y"]).max())
+    print("PoseResNet-50 bf16 mode: max error / output range = %.3g" % err)
+    assert err < 5e-2, err
