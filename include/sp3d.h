@@ -163,8 +163,15 @@ typedef struct {
   int relu;                 /* 0: none; 1: ReLU after the residual add; 2: ReLU before the residual add */
   int algo;                 /* sp3d_conv_algo */
   int in_dtype, out_dtype;  /* sp3d_dtype (SIMT path: F32 only) */
+  int fused_phases;         /* tensor-core path only.  1: kernel-2 stride-2 transposed 3-D convolution in ONE launch:
+                               ksize = (1,1,1), ostride = (2,2,2), the packed weight has 8 * cout rows ordered
+                               (px, py, pz, co), and out[2x+px, 2y+py, 2z+pz, co] is written for all 8 phases
+                               (cout_pitch == cout).  0: one launch per phase through ostride / ooffset. */
 } sp3d_conv_args;
 int sp3d_conv_fwd(const sp3d_conv_args* a, void* stream);
+/* Debug aid (profiles/conv_stalls.py): when given a device buffer of 148 * 16 uint64, every tensor-core
+ * convolution launch writes per-CTA pipeline wait cycles into it (process-global; NULL switches it off). */
+void sp3d_debug_conv_profile(void* dev_u64_buffer);
 
 /* Max pooling on channel-last activations (window k, stride s, padding p per axis; -inf padding).
  * Replaces F.max_pool3d(k2,s2) (lib/models/v2v_net.py:54) and nn.MaxPool2d(3,2,1)

@@ -78,6 +78,7 @@ class ConvArgs(C.Structure):
         ("cout", C.c_int), ("cout_pitch", C.c_int), ("cout_pitch_w", C.c_int),
         ("ksize", _i3), ("stride", _i3), ("tap_off0", _i3), ("tap_step", _i3), ("ostride", _i3), ("ooffset", _i3),
         ("relu", C.c_int), ("algo", C.c_int), ("in_dtype", C.c_int), ("out_dtype", C.c_int),
+        ("fused_phases", C.c_int),
     ]
 
 
@@ -110,6 +111,7 @@ SYMBOLS = {
     "sp3d_softargmax3d_workspace": (C.c_int64, [C.POINTER(SoftargmaxArgs)]),
     "sp3d_softargmax3d_fwd": (C.c_int, [C.POINTER(SoftargmaxArgs), C.c_void_p]),
     "sp3d_conv_fwd": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
+    "sp3d_debug_conv_profile": (None, [C.c_void_p]),
     "sp3d_maxpool_fwd": (C.c_int, [C.POINTER(MaxpoolArgs), C.c_void_p]),
     "sp3d_layout_convert": (C.c_int, [C.POINTER(LayoutArgs), C.c_void_p]),
 }

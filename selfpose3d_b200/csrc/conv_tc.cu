@@ -25,12 +25,13 @@
 #include "sp3d_common.cuh"
 #include "tc_common.cuh"
 #include <cuda.h>
+#include <string.h>
 
 namespace sp3d {
 
 using namespace tc;
 
-constexpr int kTcThreads = 256;
+constexpr int kTcBaseThreads = 128;   // warps 0-3: halo producer, weight producer, MMA issuers; then EG x 4 epilogue warps
 constexpr int kBY = 16, kBZ = 8;   // brick extent in y and z: 128 rows of M = 16 groups of 8 z-positions
 
 constexpr int largest_divisor_le(int n, int cap) {
@@ -39,6 +40,10 @@ constexpr int largest_divisor_le(int n, int cap) {
     if (n % d == 0) best = d;
   return best;
 }
+
+struct alignas(64) TcStoreMaps {
+  CUtensorMap m[4];              // [0] for a regular launch; one per (px, py) phase pair for the fused transposed form
+};
 
 struct TcConvParams {
   int X, Y, Z;                   // output grid of this launch (bricks enumerate it)
@@ -57,13 +62,25 @@ struct TcConvParams {
   const float* shift;
   const void* residual;          // same dtype / addressing as out
   void* out;
+  int fused_cols;                // fused k2/s2 transposed convolution: columns per (px, py) output phase pair
+                                 // (= 2 * cout: (pz, co) is contiguous in the output), else 0
+  int tma_store;                 // 1: epilogue stages rows in smem and stores (and pre-loads the residual) by TMA
+  int has_res;
+  unsigned long long* prof;      // optional per-CTA wait-cycle counters (sp3d_debug_conv_profile), else NULL
 };
+constexpr int kProfSlots = 16;    // per CTA: mma total, wait halo, wait weights, wait acc_empty, epi total, epi wait, items, -
 
 // KSX / KS kernel extent along x / along y and z, RB bytes per smem row (= channels per K chunk * 2),
 // N = MMA N (output-channel tile), TX = x-slices (M tiles) per brick, G = taps per weight stage, S = weight stages.
 // HB = halo buffers (2 for the compute-heavy kernels, deeper for 1x1 where a work item is a few MMAs).
-template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB = 2>
+template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB = 2, int SB = 2, int SR = 128, int EG = 2>
 struct TcCfg {
+  static constexpr int kThreads = kTcBaseThreads + 128 * EG;
+  // epilogue staging ring: SB slots of one x-slice (128 positions) x kStageRow bytes (one swizzled TMA-store box)
+  static constexpr int kStageRow = N * 2 < SR ? N * 2 : SR;   // SR caps the chunk where smem is short
+  static constexpr int kStageBytes = 128 * kStageRow;
+  static_assert(SB >= 2, "the staging ring needs two slots");
+  static_assert(EG == 1 || (EG == 2 && TX % 2 == 0), "x-slices must split evenly over the epilogue groups");
   static constexpr int HX = TX + KSX - 1, HY = kBY + KS - 1, HZ = kBZ + KS - 1;
   static constexpr int kHaloRows = HX * HY * HZ;
   static constexpr int kHaloBytes = kHaloRows * RB;
@@ -75,29 +92,32 @@ struct TcCfg {
   static constexpr int kWStride = (kWBytes + 1023) / 1024 * 1024;
   static constexpr int kTapsPerLoad = largest_divisor_le(G, 256 / N);   // TMA box rows <= 256
   static constexpr int kLoads = G / kTapsPerLoad;
-  static constexpr int kSmemBytes = HB * kHaloStride + S * kWStride + 1024;   // + alignment slack
+  static constexpr int kSmemBytes = HB * kHaloStride + S * kWStride + EG * SB * kStageBytes + 1024;   // + alignment slack
   static_assert(kTaps % G == 0, "taps per stage must divide the tap count");
   static constexpr int kKSteps = RB / 32;       // tcgen05.mma K = 16 bf16 = 32 bytes
   static constexpr int kIssuers = TX >= 2 ? 2 : 1;
   static constexpr uint32_t kLayout = RB == 128 ? kSwizzle128 : (RB == 64 ? kSwizzle64 : kSwizzle32);
   static_assert(2 * TX * N <= 512, "accumulators exceed TMEM");
-  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+  static_assert(kSmemBytes + 3072 <= 227 * 1024, "shared memory budget (dynamic + ~3 KB static)");
 };
 
-template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB, int SB, int SR, int EG>
+__global__ void __launch_bounds__(kTcBaseThreads + 128 * EG, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
+               const __grid_constant__ TcStoreMaps maps_out, const __grid_constant__ TcStoreMaps maps_res,
                const TcConvParams p) {
-  using C = TcCfg<KSX, KS, RB, N, TX, G, S, HB>;
+  using C = TcCfg<KSX, KS, RB, N, TX, G, S, HB, SB, SR, EG>;
   constexpr int kWStages = S;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t halo_full[HB], halo_empty[HB], w_full[kWStages], w_empty[kWStages], acc_full[2], acc_empty[2];
+  __shared__ uint64_t res_full[EG][SB];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_scale[2][N], s_shift[2][N];      // per accumulator buffer (the channel tile may change per item)
+  __shared__ __align__(16) float s_scale[2][N], s_shift[2][N];      // per accumulator buffer (the channel tile may change per item)
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* halo = smem;                               // [HB][kHaloStride]
   uint8_t* wbuf = smem + HB * C::kHaloStride;         // [kWStages][kWStride]
+  uint8_t* stage = wbuf + kWStages * C::kWStride;     // [SB][kStageBytes]
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
@@ -108,18 +128,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], C::kIssuers);
-      mbar_init(&acc_empty[i], 128);
+      mbar_init(&acc_empty[i], 128 * EG);
     }
     for (int i = 0; i < kWStages; ++i) {
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], C::kIssuers);
     }
+    for (int i = 0; i < EG * SB; ++i) mbar_init(&res_full[0][0] + i, 1);
     fence_barrier_init();
   }
-  for (int i = tid; i < 2 * N; i += kTcThreads) {     // channel tile 0 (the only one unless n_tiles > 1)
+  for (int i = tid; i < 2 * N; i += C::kThreads) {     // channel tile 0 (the only one unless n_tiles > 1)
     const int co = i % N;
-    s_scale[i / N][co] = (p.scale != nullptr && co < p.cout) ? p.scale[co] : 1.0f;
-    s_shift[i / N][co] = (p.shift != nullptr && co < p.cout) ? p.shift[co] : 0.0f;
+    const int cs = p.fused_cols ? co % p.cout : co;
+    s_scale[i / N][co] = (p.scale != nullptr && cs < p.cout) ? p.scale[cs] : 1.0f;
+    s_shift[i / N][co] = (p.shift != nullptr && cs < p.cout) ? p.shift[cs] : 0.0f;
   }
   if (warp == 0) {
     tmem_alloc(&tmem_base_s, 512);
@@ -128,6 +150,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
   if (warp == 1 && lane == 0) {
     tma_prefetch_desc(&map_in);
     tma_prefetch_desc(&map_w);
+    if (p.tma_store) tma_prefetch_desc(&maps_out.m[0]);
+    if (p.has_res) tma_prefetch_desc(&maps_res.m[0]);
   }
   tc_fence_before();
   __syncthreads();
@@ -189,13 +213,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
     const uint64_t a_desc0 = make_smem_desc(smem_u32(halo), 0, C::HZ * RB, C::kLayout);
     const uint64_t b_desc0 = make_smem_desc(smem_u32(wbuf), 0, 8 * RB, C::kLayout);
     uint32_t u = 0, w = 0, it = 0;
+    long long t_begin = 0, t_halo = 0, t_w = 0, t_acc = 0, t0 = 0;
+    const bool prof = p.prof != nullptr;
+    if (prof) t_begin = clock64();
     for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x, ++it) {
       const uint32_t accbuf = it & 1;
+      if (prof) t0 = clock64();
       mbar_wait(&acc_empty[accbuf], ((it >> 1) & 1) ^ 1);
+      if (prof) t_acc += clock64() - t0;
       tc_fence_after();
       for (int c = 0; c < p.n_chunks; ++c, ++u) {
         const uint32_t buf = u % HB;
+        if (prof) t0 = clock64();
         mbar_wait(&halo_full[buf], (u / HB) & 1);
+        if (prof) t_halo += clock64() - t0;
         // descriptor low words advance in 16-byte units; the high words (SBO, version, layout) never change
         const uint32_t a_lo0 = (uint32_t)a_desc0 + (uint32_t)((buf * C::kHaloStride) >> 4);
         const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
@@ -205,7 +236,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
         uint32_t a_tap = a_lo0;                                    // start of the current tap's shifted window
         for (int g = 0; g < C::kGroups; ++g, ++w) {
           const uint32_t st = w % kWStages;
+          if (prof) t0 = clock64();
           mbar_wait(&w_full[st], (w / kWStages) & 1);
+          if (prof) t_w += clock64() - t0;
           tc_fence_after();
           uint32_t b_lo = (uint32_t)b_desc0 + (uint32_t)((st * C::kWStride) >> 4);
 #pragma unroll(G % KS == 0 ? KS : 1)
@@ -237,17 +270,228 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
       }
       if (elect_one_sync()) mma_commit(&acc_full[accbuf]);
     }
+    if (prof && q == 0 && lane == 0) {
+      unsigned long long* o = p.prof + (size_t)blockIdx.x * kProfSlots;
+      o[0] = clock64() - t_begin; o[1] = t_halo; o[2] = t_w; o[3] = t_acc; o[6] = it;
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (thread <-> accumulator row)
-    const int row = tid - 128;                 // 0..127 = TMEM lane
+    const int row = (tid - 128) & 127;         // 0..127 = TMEM lane
+    const int grp = (tid - 128) >> 7;          // epilogue group: x-slices grp, grp + EG, ... of every brick
+    uint8_t* gstage = stage + grp * SB * C::kStageBytes;
+    uint64_t* gres_full = res_full[grp];
+    const int bar_id = 1 + grp;
     const int ly = row >> 3, lz = row & 7;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t it = 0;
-    for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x, ++it) {
+    long long e_begin = 0, e_wait = 0, e0 = 0;
+    const bool prof = p.prof != nullptr;
+    if (prof) e_begin = clock64();
+    // ---- staged form: TMEM -> registers -> swizzled smem rows (residual pre-loaded there by TMA) -> TMA store.
+    // A unit = one x-slice (128 positions) x one chunk of kStageRow bytes of channels; units walk a ring of SB slots.
+    auto staged = [&](auto tag) {
+      using T = decltype(tag);
+      constexpr int COLS = C::kStageRow / (int)sizeof(T);   // accumulator columns per unit
+      constexpr int CPU = 16 / (int)sizeof(T);              // columns per 16-byte smem unit
+      constexpr int UNITS = C::kStageRow / 16;
+      constexpr int NSC = N / COLS;                         // units per x-slice
+      constexpr uint32_t SWZ = C::kStageRow == 128 ? 7u : (C::kStageRow == 64 ? 3u : 1u);
+      const bool has_res = p.has_res != 0;
+      const bool leader = row == 0;
+      int pf_wi = blockIdx.x, pf_t = grp, pf_sc = 0;          // residual prefetch cursor (leader)
+      uint32_t pf_u = 0;
+      auto issue_res = [&]() {
+        int n, x0, y0, z0, nt;
+        item_coords(pf_wi, n, x0, y0, z0, nt);
+        const uint32_t b = pf_u % SB;
+        mbar_arrive_expect_tx(&gres_full[b], C::kStageBytes);
+        int gc = nt * N + pf_sc * COLS, mi = 0;
+        if (p.fused_cols) {
+          mi = gc / p.fused_cols;
+          gc -= mi * p.fused_cols;
+        }
+        tma_load_5d(gstage + b * C::kStageBytes, &maps_res.m[mi], &gres_full[b], gc, z0, y0, x0 + pf_t, n);
+        ++pf_u;
+        if (++pf_sc == NSC) {
+          pf_sc = 0;
+          if ((pf_t += EG) >= TX) {
+            pf_t = grp;
+            pf_wi += gridDim.x;
+          }
+        }
+      };
+      if (has_res && leader)
+        for (int i = 0; i < SB - 1 && pf_wi < n_items; ++i) issue_res();
+      // N <= 32: the folded-BatchNorm scale / shift stay in registers (shared-memory loads queue behind the tensor
+      // core's operand reads while MMAs run); wider tiles read them as float4 from shared memory
+      constexpr bool kRegSS = N <= 32;
+      float reg_sc[kRegSS ? N : 1], reg_sh[kRegSS ? N : 1];
+      if constexpr (kRegSS) {
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+          reg_sc[c] = s_scale[0][c];
+          reg_sh[c] = s_shift[0][c];
+        }
+      }
+      uint32_t u = 0;
+      long long pe[5] = {0, 0, 0, 0, 0};   // tmem load, residual wait, math + smem, fence + barrier, store + ring wait
+      for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x, ++it) {
+        int n, x0, y0, z0, nt;
+        item_coords(wi, n, x0, y0, z0, nt);
+        const uint32_t accbuf = it & 1;
+        if (prof) e0 = clock64();
+        mbar_wait(&acc_full[accbuf], (it >> 1) & 1);
+        if (prof) e_wait += clock64() - e0;
+        tc_fence_after();
+        const int ch0 = nt * N;
+        if (p.n_tiles > 1) {
+          if (row < N) {
+            const int co = p.fused_cols ? (ch0 + row) % p.cout : ch0 + row;
+            s_scale[accbuf][row] = (p.scale != nullptr && co < p.cout) ? __ldg(p.scale + co) : 1.0f;
+            s_shift[accbuf][row] = (p.shift != nullptr && co < p.cout) ? __ldg(p.shift + co) : 0.0f;
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          if constexpr (kRegSS) {
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+              reg_sc[c] = s_scale[accbuf][c];
+              reg_sh[c] = s_shift[accbuf][c];
+            }
+          }
+        }
+        const float* sc_s = s_scale[p.n_tiles > 1 ? accbuf : 0];
+        const float* sh_s = s_shift[p.n_tiles > 1 ? accbuf : 0];
+#pragma unroll 1
+        for (int t = grp; t < TX; t += EG) {
+#pragma unroll(NSC <= 2 ? NSC : 1)
+          for (int sc = 0; sc < NSC; ++sc, ++u) {
+            const uint32_t b = u % SB;
+            uint8_t* sbuf = gstage + b * C::kStageBytes;
+            const uint32_t taddr = tmem_base + lane_base + (accbuf * TX + t) * N + sc * COLS;
+            uint32_t v[COLS];
+            if constexpr (COLS >= 16) {
+#pragma unroll
+              for (int c = 0; c < COLS; c += 16) tmem_ld_x16(taddr + c, v + c);
+            } else {
+              tmem_ld_x8(taddr, v);
+            }
+            long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+            if (prof) c0 = clock64();
+            tmem_ld_wait();
+            if (prof) c1 = clock64();
+            if (has_res) mbar_wait(&gres_full[b], (u / SB) & 1);
+            if (prof) c2 = clock64();
+            const uint32_t sbuf_s = smem_u32(sbuf);
+#pragma unroll
+            for (int j = 0; j < UNITS; ++j) {
+              const uint32_t off = (uint32_t)row * C::kStageRow + j * 16;
+              const uint32_t q = sbuf_s + (off ^ (((off >> 7) & SWZ) << 4));
+              const int col0 = sc * COLS + j * CPU;
+              float r[CPU];
+#pragma unroll
+              for (int i = 0; i < CPU; i += 4) {
+                float4 s4, h4;
+                if constexpr (kRegSS) {
+                  s4 = make_float4(reg_sc[col0 + i], reg_sc[col0 + i + 1], reg_sc[col0 + i + 2], reg_sc[col0 + i + 3]);
+                  h4 = make_float4(reg_sh[col0 + i], reg_sh[col0 + i + 1], reg_sh[col0 + i + 2], reg_sh[col0 + i + 3]);
+                } else {
+                  s4 = *reinterpret_cast<const float4*>(sc_s + col0 + i);
+                  h4 = *reinterpret_cast<const float4*>(sh_s + col0 + i);
+                }
+                r[i + 0] = __uint_as_float(v[j * CPU + i + 0]) * s4.x + h4.x;
+                r[i + 1] = __uint_as_float(v[j * CPU + i + 1]) * s4.y + h4.y;
+                r[i + 2] = __uint_as_float(v[j * CPU + i + 2]) * s4.z + h4.z;
+                r[i + 3] = __uint_as_float(v[j * CPU + i + 3]) * s4.w + h4.w;
+              }
+              if (p.relu == 2) {
+#pragma unroll
+                for (int i = 0; i < CPU; ++i) r[i] = fmaxf(r[i], 0.0f);
+              }
+              uint4 o;
+              if constexpr (sizeof(T) == 4) {
+                if (has_res) {
+                  const uint4 rv = lds128(q);
+                  r[0] += __uint_as_float(rv.x); r[1] += __uint_as_float(rv.y);
+                  r[2] += __uint_as_float(rv.z); r[3] += __uint_as_float(rv.w);
+                }
+                if (p.relu == 1) {
+#pragma unroll
+                  for (int i = 0; i < CPU; ++i) r[i] = fmaxf(r[i], 0.0f);
+                }
+                o = make_uint4(__float_as_uint(r[0]), __float_as_uint(r[1]), __float_as_uint(r[2]), __float_as_uint(r[3]));
+              } else {
+                if (has_res) {
+                  const uint4 rv = lds128(q);
+                  const uint32_t w4[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    r[2 * i] += __uint_as_float(w4[i] << 16);
+                    r[2 * i + 1] += __uint_as_float(w4[i] & 0xffff0000u);
+                  }
+                }
+                if (p.relu == 1) {
+#pragma unroll
+                  for (int i = 0; i < CPU; ++i) r[i] = fmaxf(r[i], 0.0f);
+                }
+                uint32_t w4[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const __nv_bfloat162 h = __floats2bfloat162_rn(r[2 * i], r[2 * i + 1]);
+                  w4[i] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                o = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+              }
+              sts128(q, o);
+            }
+            if (prof) c3 = clock64();
+            fence_proxy_async_smem();
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            if (prof) c4 = clock64();
+            if (prof) { pe[0] += c1 - c0; pe[1] += c2 - c1; pe[2] += c3 - c2; pe[3] += c4 - c3; }
+            if (leader) {
+              int gc = ch0 + sc * COLS, mi = 0;
+              if (p.fused_cols) {
+                mi = gc / p.fused_cols;
+                gc -= mi * p.fused_cols;
+              }
+              tma_store_5d(&maps_out.m[mi], sbuf, gc, z0, y0, x0 + t, n);
+              bulk_commit();
+              if (has_res) {
+                if (pf_wi < n_items) {         // slot (u - 1) % SB: its store (unit u - 1) must have left smem
+                  bulk_wait_read<1>();
+                  issue_res();
+                }
+              } else {
+                bulk_wait_read<SB - 1>();      // slot (u + 1) % SB: the store of unit u + 1 - SB has left smem
+              }
+            }
+            if (!has_res) asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            if (prof) pe[4] += clock64() - c4;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&acc_empty[accbuf]);
+      }
+      if (leader) bulk_wait<0>();
+      if (prof && leader && grp == 0) {
+        unsigned long long* o = p.prof + (size_t)blockIdx.x * kProfSlots;
+        for (int i = 0; i < 5; ++i) o[8 + i] = pe[i];
+      }
+    };
+    if (p.tma_store) {
+      if (p.out_f32) staged(float{});
+      else staged(__nv_bfloat16{});
+    }
+    // ---- direct form (rows whose byte pitch is not a multiple of 16, e.g. the 1-channel float32 score volume)
+    // (compiled for the N = 16 kernels only: that is where a 1- or 15-channel float32 head lands)
+    if constexpr (N == 16)
+    for (int wi = blockIdx.x; !p.tma_store && wi < n_items; wi += gridDim.x, ++it) {
       int n, x0, y0, z0, nt;
       item_coords(wi, n, x0, y0, z0, nt);
       const uint32_t accbuf = it & 1;
+      if (prof) e0 = clock64();
       mbar_wait(&acc_full[accbuf], (it >> 1) & 1);
+      if (prof) e_wait += clock64() - e0;
       tc_fence_after();
       const int y = y0 + ly, z = z0 + lz;
       const int ch0 = nt * N;                  // first output channel of this tile
@@ -259,12 +503,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
           s_scale[accbuf][row] = (p.scale != nullptr && co < p.cout) ? __ldg(p.scale + co) : 1.0f;
           s_shift[accbuf][row] = (p.shift != nullptr && co < p.cout) ? __ldg(p.shift + co) : 0.0f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
       }
       const float* sc_s = s_scale[p.n_tiles > 1 ? accbuf : 0];
       const float* sh_s = s_shift[p.n_tiles > 1 ? accbuf : 0];
 #pragma unroll
-      for (int t = 0; t < TX; ++t) {
+      for (int t = grp; t < TX; t += EG) {
         const int x = x0 + t;
         const bool in_range = (x < p.X) && (y < p.Y) && (z < p.Z);
         const int64_t pos = (((int64_t)n * p.TD + (x * p.ostride[0] + p.ooff[0])) * p.TH + (y * p.ostride[1] + p.ooff[1])) *
@@ -334,6 +578,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
       tc_fence_before();
       mbar_arrive(&acc_empty[accbuf]);
     }
+    if (prof && row == 0 && grp == 0) {
+      unsigned long long* o = p.prof + (size_t)blockIdx.x * kProfSlots;
+      o[4] = clock64() - e_begin; o[5] = e_wait;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -341,6 +589,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+// Debug only (profiles/conv_stalls.py): a device buffer of 148 * kProfSlots u64 receiving per-CTA wait cycles.
+static unsigned long long* g_conv_prof = nullptr;
+void set_conv_profile(void* dev) { g_conv_prof = static_cast<unsigned long long*>(dev); }
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -363,16 +615,57 @@ static CUtensorMapSwizzle swizzle_for(int rb) {
   return rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
-template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB>
+template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB, int SB, int SR, int EG>
 static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
-  using C = TcCfg<KSX, KS, RB, N, TX, G, S, HB>;
+  using C = TcCfg<KSX, KS, RB, N, TX, G, S, HB, SB, SR, EG>;
   EncodeTiledFn encode = get_encode();
   if (encode == nullptr) return SP3D_ERR_UNSUPPORTED;
   const int chunk_ch = RB / 2;
   const int n_chunks = (a->cin + chunk_ch - 1) / chunk_ch;
-  const int n_tiles = (a->cout + N - 1) / N;
+  const int n_tiles = a->fused_phases ? (8 * a->cout) / N : (a->cout + N - 1) / N;
 
   CUtensorMap map_in, map_w;
+  TcStoreMaps maps_out, maps_res;
+  memset(&maps_out, 0, sizeof(maps_out));
+  memset(&maps_res, 0, sizeof(maps_res));
+  const int esz = a->out_dtype == SP3D_F32 ? 4 : 2;
+  const bool fused = a->fused_phases != 0;
+  const bool tma_store = ((int64_t)a->cout_pitch * esz) % 16 == 0 &&
+                         (a->residual == nullptr || reinterpret_cast<uintptr_t>(a->residual) % 16 == 0);
+  if (!tma_store && N != 16) return SP3D_ERR_UNSUPPORTED;   // the direct-store epilogue exists in the N = 16 kernels only
+  if (fused && (!tma_store || a->cout_pitch != a->cout || (2 * a->cout * esz) % 128 || (8 * a->cout) % N)) return SP3D_ERR_UNSUPPORTED;
+  if (tma_store) {
+    // output / residual viewed through the launch's output stride and offset (transposed-convolution phases):
+    // [N][OD][OH][OW][cout_pitch] with scaled strides; box = one x-slice of the brick x one staged channel chunk.
+    // Fused k2/s2 transposed form: one view per (px, py); (pz, co) is contiguous, so dim 0 spans 2 * cout elements.
+    const int64_t pe = (int64_t)a->cout_pitch * esz;
+    for (int d = 0; d < 3; ++d) {
+      const int full = d == 0 ? a->TD : (d == 1 ? a->TH : a->TW);
+      const int og = d == 0 ? a->OD : (d == 1 ? a->OH : a->OW);
+      const int off = fused ? a->ostride[d] - 1 : a->ooffset[d];
+      if ((int64_t)(og - 1) * a->ostride[d] + off >= full) return SP3D_ERR_INVALID_ARG;
+    }
+    cuuint64_t gdim[5] = {(cuuint64_t)(fused ? 2 * a->cout : a->cout_pitch), (cuuint64_t)a->OW, (cuuint64_t)a->OH,
+                          (cuuint64_t)a->OD, (cuuint64_t)a->N};
+    cuuint64_t gstr[4] = {(cuuint64_t)(pe * a->ostride[2]), (cuuint64_t)(pe * a->TW * a->ostride[1]),
+                          (cuuint64_t)(pe * a->TW * a->TH * a->ostride[0]), (cuuint64_t)(pe * a->TW * a->TH * a->TD)};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)(C::kStageRow / esz), (cuuint32_t)kBZ, (cuuint32_t)kBY, 1, 1};
+    const CUtensorMapDataType dt = esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    for (int mi = 0; mi < (fused ? 4 : 1); ++mi) {
+      const int ox = fused ? (mi >> 1) : a->ooffset[0], oy = fused ? (mi & 1) : a->ooffset[1], oz = fused ? 0 : a->ooffset[2];
+      const int64_t base_off = (((int64_t)ox * a->TH + oy) * a->TW + oz) * pe;
+      if (encode(&maps_out.m[mi], dt, 5, static_cast<uint8_t*>(a->out) + base_off, gdim, gstr, box, es,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(C::kStageRow), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return SP3D_ERR_INVALID_ARG;
+      if (a->residual != nullptr &&
+          encode(&maps_res.m[mi], dt, 5, const_cast<uint8_t*>(static_cast<const uint8_t*>(a->residual)) + base_off, gdim,
+                 gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(C::kStageRow),
+                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return SP3D_ERR_INVALID_ARG;
+    }
+  }
   {  // activations: [N][D][H][W][cin_pitch] bf16; box = {chunk, HZ, HY, HX, 1} positions, stepped by the conv stride
     cuuint64_t gdim[5] = {(cuuint64_t)a->cin_pitch, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->D, (cuuint64_t)a->N};
     cuuint64_t gstr[4] = {(cuuint64_t)a->cin_pitch * 2, (cuuint64_t)a->cin_pitch * 2 * a->W,
@@ -415,6 +708,10 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
   p.relu = a->relu;
   p.out_f32 = a->out_dtype == SP3D_F32;
   p.scale = a->scale; p.shift = a->shift; p.residual = a->residual; p.out = a->out;
+  p.prof = g_conv_prof;
+  p.tma_store = tma_store ? 1 : 0;
+  p.fused_cols = fused ? 2 * a->cout : 0;
+  p.has_res = a->residual != nullptr ? 1 : 0;
 
   static int n_sm = 0;
   if (n_sm == 0) {
@@ -422,12 +719,12 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   }
-  auto kern = conv_tc_kernel<KSX, KS, RB, N, TX, G, S, HB>;
+  auto kern = conv_tc_kernel<KSX, KS, RB, N, TX, G, S, HB, SB, SR, EG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
   if (e != cudaSuccess) { set_last_error(e); return SP3D_ERR_LAUNCH; }
   const int items = p.n_bricks * p.n_tiles;
   const int grid = items < n_sm ? items : n_sm;
-  kern<<<grid, kTcThreads, C::kSmemBytes, st>>>(map_in, map_w, p);
+  kern<<<grid, C::kThreads, C::kSmemBytes, st>>>(map_in, map_w, maps_out, maps_res, p);
   return check_launch();
 }
 
@@ -437,6 +734,9 @@ int conv_tc(const sp3d_conv_args* a, cudaStream_t st) {
   if (a->algo != SP3D_CONV_TC_BF16) return SP3D_ERR_UNSUPPORTED;   // TF32x3 variant: not built yet
   if (a->in_dtype != SP3D_BF16) return SP3D_ERR_UNSUPPORTED;
   if (a->out_dtype != SP3D_BF16 && a->out_dtype != SP3D_F32) return SP3D_ERR_UNSUPPORTED;
+  if (a->fused_phases && (a->ksize[0] != 1 || a->ksize[1] != 1 || a->ksize[2] != 1 || a->ostride[0] != 2 ||
+                          a->ostride[1] != 2 || a->ostride[2] != 2 || a->cout_pitch_w != 128))
+    return SP3D_ERR_UNSUPPORTED;
   const int ks = a->ksize[1], ksx = a->ksize[0];
   if (a->ksize[2] != ks || (ksx != ks && ksx != 1)) return SP3D_ERR_UNSUPPORTED;
   for (int d = 0; d < 3; ++d)
@@ -450,27 +750,30 @@ int conv_tc(const sp3d_conv_args* a, cudaStream_t st) {
   if (cin >= 64 && (cin % 64)) return SP3D_ERR_UNSUPPORTED;
   if (a->cin_pitch < cin) return SP3D_ERR_INVALID_ARG;
   // (kernel x, kernel yz, row bytes, N, x-slices per brick, taps per weight stage, weight stages)
-#define SP3D_TC_CASE(KSX_, KS_, RB_, N_, TX_, G_, S_, HB_) \
-  if (ksx == KSX_ && ks == KS_ && rb == RB_ && n == N_) return launch_tc<KSX_, KS_, RB_, N_, TX_, G_, S_, HB_>(a, st);
+#define SP3D_TC_CASE(KSX_, KS_, RB_, N_, TX_, G_, S_, HB_, SB_, SR_, EG_) \
+  if (ksx == KSX_ && ks == KS_ && rb == RB_ && n == N_) \
+    return launch_tc<KSX_, KS_, RB_, N_, TX_, G_, S_, HB_, SB_, SR_, EG_>(a, st);
+  // (kernel x, kernel yz, row bytes, N, x-slices per brick, taps per weight stage, weight stages, halo buffers,
+  //  epilogue staging slots per group, staged row bytes cap, epilogue groups)
   // 3-D (V2VNet)
-  SP3D_TC_CASE(7, 7, 32, 16, 2, 49, 2, 2)
-  SP3D_TC_CASE(3, 3, 32, 32, 4, 27, 2, 2)
-  SP3D_TC_CASE(3, 3, 64, 32, 4, 9, 3, 2)
-  SP3D_TC_CASE(3, 3, 64, 64, 4, 9, 2, 2)
-  SP3D_TC_CASE(3, 3, 128, 64, 2, 1, 4, 2)
-  SP3D_TC_CASE(3, 3, 128, 128, 2, 1, 2, 2)
+  SP3D_TC_CASE(7, 7, 32, 16, 2, 49, 2, 2, 2, 128, 2)
+  SP3D_TC_CASE(3, 3, 32, 32, 4, 27, 2, 2, 3, 128, 2)
+  SP3D_TC_CASE(3, 3, 64, 32, 4, 9, 2, 2, 2, 128, 2)
+  SP3D_TC_CASE(3, 3, 64, 64, 4, 3, 3, 2, 2, 64, 2)
+  SP3D_TC_CASE(3, 3, 128, 64, 2, 1, 3, 2, 2, 64, 1)
+  SP3D_TC_CASE(3, 3, 128, 128, 2, 1, 2, 2, 2, 32, 1)
   // 1x1(x1) on any rank: a work item is a handful of MMAs, so the halo ring is deeper
-  SP3D_TC_CASE(1, 1, 32, 32, 4, 1, 2, 6)
-  SP3D_TC_CASE(1, 1, 64, 64, 4, 1, 2, 4)
-  SP3D_TC_CASE(1, 1, 64, 16, 4, 1, 2, 4)
-  SP3D_TC_CASE(1, 1, 128, 16, 4, 1, 2, 3)
-  SP3D_TC_CASE(1, 1, 128, 32, 4, 1, 2, 3)
-  SP3D_TC_CASE(1, 1, 128, 64, 4, 1, 4, 3)
-  SP3D_TC_CASE(1, 1, 128, 128, 2, 1, 4, 4)
+  SP3D_TC_CASE(1, 1, 32, 32, 4, 1, 2, 6, 3, 128, 2)
+  SP3D_TC_CASE(1, 1, 64, 64, 4, 1, 2, 4, 2, 128, 2)
+  SP3D_TC_CASE(1, 1, 64, 16, 4, 1, 2, 4, 3, 128, 2)
+  SP3D_TC_CASE(1, 1, 128, 16, 4, 1, 2, 3, 3, 128, 2)
+  SP3D_TC_CASE(1, 1, 128, 32, 4, 1, 2, 2, 3, 128, 2)
+  SP3D_TC_CASE(1, 1, 128, 64, 4, 1, 2, 2, 2, 128, 2)
+  SP3D_TC_CASE(1, 1, 128, 128, 2, 1, 3, 3, 2, 128, 2)
   // 2-D (PoseResNet): 3x3, and the 2x2 sub-kernels of the 4x4 stride-2 transposed convolutions
-  SP3D_TC_CASE(1, 3, 128, 64, 4, 1, 4, 2)
-  SP3D_TC_CASE(1, 3, 128, 128, 2, 3, 2, 2)
-  SP3D_TC_CASE(1, 2, 128, 128, 2, 2, 3, 2)
+  SP3D_TC_CASE(1, 3, 128, 64, 4, 1, 3, 2, 2, 64, 1)
+  SP3D_TC_CASE(1, 3, 128, 128, 2, 3, 2, 2, 2, 128, 1)
+  SP3D_TC_CASE(1, 2, 128, 128, 2, 2, 3, 2, 2, 128, 1)
 #undef SP3D_TC_CASE
   return SP3D_ERR_UNSUPPORTED;
 }

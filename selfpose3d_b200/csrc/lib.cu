@@ -14,6 +14,7 @@ void set_last_error(cudaError_t e) {
 
 int conv_simt_f32(const sp3d_conv_args* a, cudaStream_t st);
 int conv_tc(const sp3d_conv_args* a, cudaStream_t st);
+void set_conv_profile(void* dev);
 
 }  // namespace sp3d
 
@@ -31,6 +32,8 @@ extern "C" const char* sp3d_strerror(int status) {
 }
 
 extern "C" const char* sp3d_last_cuda_error(void) { return sp3d::g_last_error; }
+
+extern "C" void sp3d_debug_conv_profile(void* dev_u64_buffer) { sp3d::set_conv_profile(dev_u64_buffer); }
 
 extern "C" int sp3d_conv_fwd(const sp3d_conv_args* a, void* stream) {
   using namespace sp3d;

@@ -258,7 +258,7 @@ def _set3(field, vals):
 
 
 def conv_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksize, stride, tap_off0, tap_step,
-                ostride, ooffset, relu, algo=_lib.CONV_SIMT_F32, cin_real=None, cout_pitch_w=None):
+                ostride, ooffset, relu, algo=_lib.CONV_SIMT_F32, cin_real=None, cout_pitch_w=None, fused_phases=False):
     """One implicit-GEMM convolution launch.  ``x`` / ``out`` are channel-last 5-D ``[N,D,H,W,pitch]``."""
     a = _lib.ConvArgs()
     a.in_ = x.data_ptr()
@@ -284,8 +284,12 @@ def conv_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksi
     a.relu = int(relu)
     a.algo = int(algo)
     a.in_dtype, a.out_dtype = _DT[x.dtype], _DT[out.dtype]
+    a.fused_phases = int(bool(fused_phases))
     flops = 2.0 * a.N * a.OD * a.OH * a.OW * a.cout * (cin_real or a.cin) * (a.ksize[0] * a.ksize[1] * a.ksize[2])
-    detail = "conv algo%d k%d %d->%d @%dx%dx%dx%d" % (a.algo, a.ksize[2], cin_real or a.cin, a.cout, a.N, a.OD, a.OH, a.OW)
+    if fused_phases:
+        flops *= 8
+    detail = "conv%s algo%d k%d %d->%d @%dx%dx%dx%d" % ("T8" if fused_phases else "", a.algo, a.ksize[2], cin_real or a.cin,
+                                                       a.cout, a.N, a.OD, a.OH, a.OW)
     _lib.call("sp3d_conv_fwd", a, _stream(), kind="conv", work=flops, detail=detail)
 
 
@@ -419,6 +423,25 @@ class PackedConv:
             self._tc = (packs, n, cin_tc)
         return self._tc
 
+    def _tc_fused_ok(self, out_pitch, out_dtype):
+        """k2/s2 transposed 3-D convolution as ONE launch (all 8 output phases are extra GEMM columns)."""
+        esz = 4 if out_dtype == torch.float32 else 2
+        return (self.transposed and self.nd == 3 and self.k == [2, 2, 2] and (8 * self.cout) % 128 == 0
+                and out_pitch == self.cout and (2 * self.cout * esz) % 128 == 0)
+
+    def _tc_pack_fused(self):
+        """bf16 ``[n_tiles, n_chunks, 1, 128, chunk]``: GEMM rows ordered (px, py, pz, co)."""
+        if getattr(self, "_tc_fused", None) is None:
+            w = torch.stack([sub.reshape(self.cout, self.cin) for sub in self._subs], 0)   # [8 phases (pd,ph,pw), Cout, Cin]
+            cin_tc = round_up(self.cin, 16) if self.cin < 64 else round_up(self.cin, 64)
+            chunk = min(cin_tc, 64)
+            full = torch.zeros(8 * self.cout, cin_tc, device=w.device, dtype=torch.float32)
+            full[:, :self.cin] = w.reshape(8 * self.cout, self.cin)
+            n_tiles = 8 * self.cout // 128
+            full = full.reshape(n_tiles, 128, cin_tc // chunk, chunk).permute(0, 2, 1, 3).unsqueeze(2)
+            self._tc_fused = (full.to(torch.bfloat16).contiguous(), cin_tc)
+        return self._tc_fused
+
     def _call_tc(self, x, residual, out_pitch, out_dtype):
         if not self.tc_supported():
             raise _lib.Sp3dError("convolution shape not covered by the tensor-core path")
@@ -442,6 +465,11 @@ class PackedConv:
             conv_launch(xk, packs[0], self.scale, self.shift, resk, outk, cin_tc, self.cout, o, self.k, self.stride,
                         [-p for p in self.padding], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu, _lib.CONV_TC_BF16,
                         cin_real=self.cin, cout_pitch_w=n)
+        elif self._tc_fused_ok(out_pitch, out_dtype):
+            wgt, _ = self._tc_pack_fused()
+            conv_launch(xk, wgt, self.scale, self.shift, resk, outk, cin_tc, self.cout, (D, H, W), [1, 1, 1], [1, 1, 1],
+                        [0, 0, 0], [1, 1, 1], self.stride, [0, 0, 0], self.relu, _lib.CONV_TC_BF16, cin_real=self.cin,
+                        cout_pitch_w=128, fused_phases=True)
         else:
             for wgt, (phase, off0, ks) in zip(packs, self.phases):
                 origin = [off0[i] - (ks[i] - 1) for i in range(3)]     # taps ascend from the lowest input offset

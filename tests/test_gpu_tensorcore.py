@@ -65,24 +65,33 @@ def test_tc_conv_matches_float64_reference(k, cin, cout):
     assert float((gotb - want).abs().max()) <= 6e-3 * scale
 
 
+@pytest.mark.parametrize("shape", [(4, 16, 8), (3, 20, 12)])     # whole bricks / ragged in x, y and z
+@pytest.mark.parametrize("with_skip", [True, False])
 @pytest.mark.parametrize("cin,cout", [(128, 64), (64, 32)])
-def test_tc_transposed_conv_matches_float64_reference(cin, cout):
+def test_tc_transposed_conv_matches_float64_reference(cin, cout, with_skip, shape):
+    """k2/s2 transposed convolution (one fused launch: the 8 output phases are GEMM columns) + BN + ReLU (+ skip)."""
     torch.manual_seed(cin)
     ct = nn.ConvTranspose3d(cin, cout, 2, 2)
     bn = rand_bn(nn.BatchNorm3d(cout), cin)
     with torch.no_grad():
         ct.weight.copy_(bf16_round(ct.weight))
-    x = bf16_round(torch.randn(2, cin, 4, 16, 8))
-    skip = bf16_round(torch.randn(2, cout, 8, 32, 16))
+    x = bf16_round(torch.randn(2, cin, *shape))
+    skip = bf16_round(torch.randn(2, cout, *[2 * v for v in shape]))
     with torch.no_grad():
-        want = F.relu(bn.double()(ct.double()(x.double()))) + skip.double()
+        want = F.relu(bn.double()(ct.double()(x.double())))
+        if with_skip:
+            want = want + skip.double()
     ct, bn = ct.float().to(DEV), bn.float().to(DEV)
     pc = ops.PackedConv(ct.weight, ct.bias, bn, 2, 0, transposed=True, relu=2)
+    assert pc._tc_fused_ok(cout, torch.float32) and pc._tc_fused_ok(cout, torch.bfloat16)
     skip_cl = ops.to_channel_last(skip.to(DEV), c_pitch=cout, dtype=torch.float32)
-    y = pc(to_cl_bf16(x), residual=skip_cl, out_pitch=cout, out_dtype=torch.float32)
+    y = pc(to_cl_bf16(x), residual=skip_cl if with_skip else None, out_pitch=cout, out_dtype=torch.float32)
     got = ops.to_channel_first(y, cout).cpu().double()
     scale = float(want.abs().max())
     assert float((got - want).abs().max()) <= 2e-5 * scale
+    yb = pc(to_cl_bf16(x), residual=skip_cl.to(torch.bfloat16) if with_skip else None, out_pitch=cout)
+    gotb = ops.to_channel_first(yb, cout, dtype=torch.float32).cpu().double()
+    assert float((gotb - want).abs().max()) <= 6e-3 * scale
 
 
 def test_v2v_net_bf16_mode_vs_float64_oracle():
