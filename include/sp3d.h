@@ -35,7 +35,7 @@ typedef enum {
   SP3D_ERR_WORKSPACE = -4
 } sp3d_status;
 
-typedef enum { SP3D_F32 = 0, SP3D_BF16 = 1 } sp3d_dtype;
+typedef enum { SP3D_F32 = 0, SP3D_BF16 = 1, SP3D_F16 = 2 } sp3d_dtype;
 
 /* ABI version of the loaded library and a static description of an error code. */
 int sp3d_abi_version(void);
@@ -83,8 +83,23 @@ typedef struct {
   int64_t out_stride_cube, out_stride_c, out_stride_vox; /* in elements; voxel = (ix*Y+iy)*Z+iz */
   int out_c_pad;            /* channels [C, out_c_pad) are written as zeros (channel-last padding); 0 = none */
   float* grids;             /* optional [n_cubes, X*Y*Z, 3] voxel-centre coordinates, or NULL */
+  int hm_dtype;             /* sp3d_dtype of the heat-maps: SP3D_F32, or SP3D_F16 (math_mode 1 only) */
+  int math_mode;            /* 0: float32 arithmetic in the reference's operation order (bit-faithful mask, parity
+                               form).  1: throughput form for the bf16 volume mode -- FMA-contracted projection,
+                               half2 tap blending; needs SP3D_F16 channel-last heat-maps with 16 channels per pixel
+                               (sp3d_heatmaps_to_f16), bf16 channel-last cubes with pitch 16, all views, no grids */
 } sp3d_unproject_args;
 int sp3d_unproject_fwd(const sp3d_unproject_args* a, void* stream);
+
+/* float32 heat-maps of V views ([B, C, h, w] through the strides, C <= 16) -> fp16 channel-last
+ * [V][B][h][w][16] (channels >= C zero): the input layout of sp3d_unproject_fwd's math_mode 1. */
+typedef struct {
+  const float* heatmaps[SP3D_MAX_VIEWS];
+  int64_t stride_b, stride_c, stride_h, stride_w; /* in elements */
+  int V, B, C, h, w;
+  void* out;
+} sp3d_heatmaps_f16_args;
+int sp3d_heatmaps_to_f16(const sp3d_heatmaps_f16_args* a, void* stream);
 
 /* Divide / NaN / clamp step of the un-projection after partial sums were all-reduced:
  * buf is [n, (C+1), N] channel-first or [n, N, pitch] channel-last partial output. */

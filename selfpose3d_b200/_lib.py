@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libsp3d.so")
 
 MAX_VIEWS = 8
 CAM_FLOATS = 32
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 CONV_SIMT_F32, CONV_TC_BF16, CONV_TC_TF32X3 = 0, 1, 2
 
 _i3 = C.c_int * 3
@@ -35,6 +35,16 @@ class UnprojectArgs(C.Structure):
         ("out_stride_cube", C.c_int64), ("out_stride_c", C.c_int64), ("out_stride_vox", C.c_int64),
         ("out_c_pad", C.c_int),
         ("grids", C.c_void_p),
+        ("hm_dtype", C.c_int), ("math_mode", C.c_int),
+    ]
+
+
+class HeatmapsF16Args(C.Structure):
+    _fields_ = [
+        ("heatmaps", C.c_void_p * MAX_VIEWS),
+        ("stride_b", C.c_int64), ("stride_c", C.c_int64), ("stride_h", C.c_int64), ("stride_w", C.c_int64),
+        ("V", C.c_int), ("B", C.c_int), ("C", C.c_int), ("h", C.c_int), ("w", C.c_int),
+        ("out", C.c_void_p),
     ]
 
 
@@ -106,6 +116,7 @@ SYMBOLS = {
     "sp3d_strerror": (C.c_char_p, [C.c_int]),
     "sp3d_last_cuda_error": (C.c_char_p, []),
     "sp3d_unproject_fwd": (C.c_int, [C.POINTER(UnprojectArgs), C.c_void_p]),
+    "sp3d_heatmaps_to_f16": (C.c_int, [C.POINTER(HeatmapsF16Args), C.c_void_p]),
     "sp3d_unproject_finalize": (C.c_int, [C.POINTER(UnprojectFinalizeArgs), C.c_void_p]),
     "sp3d_nms_topk3d": (C.c_int, [C.POINTER(NmsTopkArgs), C.c_void_p]),
     "sp3d_softargmax3d_workspace": (C.c_int64, [C.POINTER(SoftargmaxArgs)]),

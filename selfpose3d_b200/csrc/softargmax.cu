@@ -136,6 +136,110 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(const sp
   }
 }
 
+
+// Streaming form for channel-last float32 volumes (the layout V2VNet's head writes): `LPV` lanes share a voxel,
+// each owning 4 consecutive channels, so one 16-byte load per lane is a fully coalesced 512-byte warp request
+// and the online-softmax state is 20 registers per lane.  The CTA merge is parallel: shared per-channel maximum
+// first, then every lane rescales its state once and plain sums are reduced (float64 from here on).
+template <int LPV>
+__global__ void __launch_bounds__(kSaThreads) softargmax_stream_kernel(const sp3d_softargmax_args a, int splits,
+                                                                        int vox_per_split) {
+  constexpr int kWarps = kSaThreads / 32;
+  __shared__ float s_g[3][256];
+  __shared__ float s_max[kWarps][4 * LPV];
+  __shared__ double s_sum[kWarps][4 * LPV][4];
+  const int cube = blockIdx.y, split = blockIdx.x, tid = threadIdx.x;
+  const int N = a.X * a.Y * a.Z;
+  const float* cen = a.centers + (int64_t)cube * a.center_stride;
+  double* ws = reinterpret_cast<double*>(a.workspace) + ((int64_t)cube * splits + split) * a.C * kSaState;
+  if (a.check_flag && !(cen[3] >= 0.0f)) {
+    for (int i = tid; i < a.C * kSaState; i += kSaThreads) ws[i] = 0.0;
+    return;
+  }
+  const float cx = cen[0], cy = cen[1], cz = cen[2];
+  // g - centre with g = fl(lin + centre), the `grids` values of ProjectLayer.compute_grid
+  for (int i = tid; i < a.X; i += kSaThreads) s_g[0][i] = __fsub_rn(__fadd_rn(a.lin_x[i], cx), cx);
+  for (int i = tid; i < a.Y; i += kSaThreads) s_g[1][i] = __fsub_rn(__fadd_rn(a.lin_y[i], cy), cy);
+  for (int i = tid; i < a.Z; i += kSaThreads) s_g[2][i] = __fsub_rn(__fadd_rn(a.lin_z[i], cz), cz);
+  __syncthreads();
+  const int v_begin = split * vox_per_split;
+  const int v_end = min(N, v_begin + vox_per_split);
+  const float* xb = reinterpret_cast<const float*>(a.x) + (int64_t)cube * a.stride_cube;
+  const int cq = tid % LPV;                      // channel quad of this lane
+  const int nch = min(4, a.C - 4 * cq);          // live channels in the quad (<= 0: none)
+  float m[4], s[4], wx[4], wy[4], wz[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { m[k] = -INFINITY; s[k] = 0.f; wx[k] = 0.f; wy[k] = 0.f; wz[k] = 0.f; }
+  for (int vox = v_begin + tid / LPV; vox < v_end; vox += kSaThreads / LPV) {
+    const int iz = vox % a.Z, t = vox / a.Z;
+    const int iy = t % a.Y, ix = t / a.Y;
+    const float gx = s_g[0][ix], gy = s_g[1][iy], gz = s_g[2][iz];
+    const float4 q = ldg4(xb + (int64_t)vox * a.stride_vox + 4 * cq);
+    const float xv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < nch) {
+        const float z = __fmul_rn(a.beta, xv[k]);
+        if (z > m[k]) {
+          const float sc = expf(m[k] - z);  // exp(-inf) = 0 on the first element
+          s[k] = fmaf(s[k], sc, 1.0f);
+          wx[k] = fmaf(wx[k], sc, gx);
+          wy[k] = fmaf(wy[k], sc, gy);
+          wz[k] = fmaf(wz[k], sc, gz);
+          m[k] = z;
+        } else {
+          const float e = expf(z - m[k]);
+          s[k] += e;
+          wx[k] = fmaf(e, gx, wx[k]);
+          wy[k] = fmaf(e, gy, wy[k]);
+          wz[k] = fmaf(e, gz, wz[k]);
+        }
+      }
+    }
+  }
+  // CTA-wide maximum per channel
+  const int lane = tid & 31, warp = tid >> 5;
+  float mm[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    mm[k] = m[k];
+    for (int off = LPV; off < 32; off <<= 1) mm[k] = fmaxf(mm[k], __shfl_xor_sync(0xffffffffu, mm[k], off));
+  }
+  if (lane < LPV) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s_max[warp][4 * lane + k] = mm[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float M = s_max[0][4 * cq + k];
+    for (int w = 1; w < kWarps; ++w) M = fmaxf(M, s_max[w][4 * cq + k]);
+    mm[k] = M;
+    // this lane's state on the common maximum (an empty state has s = 0 and m = -inf: factor forced to 0)
+    const double f = (s[k] > 0.0f) ? exp((double)m[k] - (double)M) : 0.0;
+    double v4[4] = {(double)s[k] * f, (double)wx[k] * f, (double)wy[k] * f, (double)wz[k] * f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      for (int off = LPV; off < 32; off <<= 1) v4[i] += __shfl_xor_sync(0xffffffffu, v4[i], off);
+    if (lane < LPV) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s_sum[warp][4 * lane + k][i] = v4[i];
+    }
+  }
+  __syncthreads();
+  if (tid < 4 * LPV && tid < a.C) {
+    double r[4] = {0.0, 0.0, 0.0, 0.0};
+    float M = s_max[0][tid];
+    for (int w = 0; w < kWarps; ++w) {
+      M = fmaxf(M, s_max[w][tid]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[i] += s_sum[w][tid][i];
+    }
+    double* o = ws + (int64_t)tid * kSaState;
+    o[0] = (double)M; o[1] = r[0]; o[2] = r[1]; o[3] = r[2]; o[4] = r[3];
+  }
+}
+
 __global__ void softargmax_merge_kernel(const sp3d_softargmax_args a, int splits) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (cube, channel)
   if (i >= a.n_cubes * a.C) return;
@@ -157,7 +261,7 @@ __global__ void softargmax_merge_kernel(const sp3d_softargmax_args a, int splits
 
 static int sa_splits(const sp3d_softargmax_args* a) {
   const int64_t N = (int64_t)a->X * a->Y * a->Z;
-  int splits = (int)((148 * 4 + a->n_cubes - 1) / (a->n_cubes > 0 ? a->n_cubes : 1));
+  int splits = (int)((148 * 8 + a->n_cubes - 1) / (a->n_cubes > 0 ? a->n_cubes : 1));
   const int max_splits = (int)((N + 1023) / 1024);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -191,7 +295,11 @@ extern "C" int sp3d_softargmax3d_fwd(const sp3d_softargmax_args* a, void* stream
   if (a->x_dtype == SP3D_F32) {
     const bool vec = a->stride_c == 1 && (a->stride_vox % 4) == 0 && (a->stride_cube % 4) == 0 &&
                      (reinterpret_cast<uintptr_t>(a->x) % 16) == 0 && a->stride_vox >= ((a->C + 3) / 4) * 4;
-    if (vec) softargmax_partial_kernel<float, true><<<grid, kSaThreads, 0, st>>>(*a, splits, vps);
+    const bool stream = vec && a->C <= 16 && a->X <= 256 && a->Y <= 256 && a->Z <= 256;
+    if (stream && a->C > 8) softargmax_stream_kernel<4><<<grid, kSaThreads, 0, st>>>(*a, splits, vps);
+    else if (stream && a->C > 4) softargmax_stream_kernel<2><<<grid, kSaThreads, 0, st>>>(*a, splits, vps);
+    else if (stream) softargmax_stream_kernel<1><<<grid, kSaThreads, 0, st>>>(*a, splits, vps);
+    else if (vec) softargmax_partial_kernel<float, true><<<grid, kSaThreads, 0, st>>>(*a, splits, vps);
     else softargmax_partial_kernel<float, false><<<grid, kSaThreads, 0, st>>>(*a, splits, vps);
   } else {
     softargmax_partial_kernel<__nv_bfloat16, false><<<grid, kSaThreads, 0, st>>>(*a, splits, vps);

@@ -200,6 +200,10 @@ __global__ void unproject_finalize_kernel(const sp3d_unproject_finalize_args a) 
 
 }  // namespace sp3d
 
+namespace sp3d {
+int unproject_fast(const sp3d_unproject_args* a, cudaStream_t st);
+}
+
 extern "C" int sp3d_unproject_fwd(const sp3d_unproject_args* a, void* stream) {
   using namespace sp3d;
   if (a == nullptr || a->n_cubes < 0) return SP3D_ERR_INVALID_ARG;
@@ -214,6 +218,8 @@ extern "C" int sp3d_unproject_fwd(const sp3d_unproject_args* a, void* stream) {
   if (a->out_dtype != SP3D_F32 && a->out_dtype != SP3D_BF16) return SP3D_ERR_UNSUPPORTED;
   const int N = a->X * a->Y * a->Z;
   if (N <= 0 || a->n_cubes > 65535) return SP3D_ERR_INVALID_ARG;
+  if (a->math_mode == 1) return unproject_fast(a, static_cast<cudaStream_t>(stream));
+  if (a->math_mode != 0 || a->hm_dtype != SP3D_F32) return SP3D_ERR_UNSUPPORTED;
   bool cl = a->hm_stride_c == 1 && (a->hm_stride_w % 4) == 0 && (a->hm_stride_h % 4) == 0 && (a->hm_stride_b % 4) == 0;
   for (int v = a->view_begin; v < a->view_end && cl; ++v) cl = (reinterpret_cast<uintptr_t>(a->heatmaps[v]) % 16) == 0;
   // float4 taps read whole groups of 4 channels: the pitch must cover them

@@ -62,12 +62,18 @@ class PoseRegressionNet(nn.Module):
         J = self.num_joints
         out = torch.empty(n, J, 3, device=centers.device, dtype=torch.float32)
         X, Y, Z = [int(s) for s in self.cube_size]
+        bf16 = ops.volume_dtype() == torch.bfloat16
+        hms_f16 = None
+        if bf16 and 1 < J <= 16:   # throughput un-projection reads fp16 channel-last maps: convert once per forward
+            from .project_layer import _common_strides
+            hms, st = _common_strides(all_heatmaps)
+            hms_f16 = ops.heatmaps_to_f16(hms, st, J)
         for s in range(0, n, chunk):
             e = min(n, s + chunk)
-            bf16 = ops.volume_dtype() == torch.bfloat16
             cubes, _ = self.project_layer.project_cl(all_heatmaps, cams, centers[s:e], False, self.grid_size,
                                                      self.cube_size, cube_sample=cube_sample[s:e],
-                                                     dtype=ops.volume_dtype(), c_pitch=ops.round_up(J, 16) if bf16 else None)
+                                                     dtype=ops.volume_dtype(), c_pitch=ops.round_up(J, 16) if bf16 else None,
+                                                     hms_f16=hms_f16)
             y = self.v2v_net.forward_cl(cubes)
             pitch = int(y.shape[-1])
             out[s:e] = ops.softargmax(y, (X * Y * Z * pitch, 1, pitch), e - s, J, (X, Y, Z), centers[s:e],

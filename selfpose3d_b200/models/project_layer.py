@@ -56,7 +56,8 @@ class ProjectLayer(nn.Module):
         return gc.contiguous(), check
 
     def project_cl(self, heatmaps, cams, centers, check_flag, grid_size, cube_size, channels=None,
-                   cubes_per_sample=1, cube_sample=None, want_grids=False, dtype=torch.float32, c_pitch=None):
+                   cubes_per_sample=1, cube_sample=None, want_grids=False, dtype=torch.float32, c_pitch=None,
+                   hms_f16=None):
         """Layout-native un-projection: returns channel-last cubes ``[n_cubes,X,Y,Z,pitch]``
         (padding channels zero) and optionally ``grids [n_cubes,N,3]``.
 
@@ -70,6 +71,16 @@ class ProjectLayer(nn.Module):
         pitch = ops.round_up(C, 4) if c_pitch is None else int(c_pitch)
         dev = hms[0].device
         cubes = torch.empty(n_cubes, X, Y, Z, pitch, device=dev, dtype=dtype)
+        if dtype == torch.bfloat16 and pitch == 16 and 1 < C <= 16 and not want_grids and Z <= 256:
+            # throughput form (bf16 volume mode): fp16 channel-last maps, half2 tap blending
+            h, w = int(hms[0].shape[2]), int(hms[0].shape[3])
+            if hms_f16 is None:
+                hms_f16 = ops.heatmaps_to_f16(hms, st, C)
+            ops.unproject([hms_f16[v] for v in range(len(hms))], (h * w * 16, 1, w * 16, 16), cams, centers, grid_size,
+                          (X, Y, Z), self.img_size, (h, w), C, cubes, (X * Y * Z * 16, 1, 16), out_c_pad=16,
+                          check_flag=check_flag, cubes_per_sample=cubes_per_sample, cube_sample=cube_sample,
+                          heatmap_cfg_wh=self.heatmap_size, fast=True)
+            return cubes, None
         grids = torch.empty(n_cubes, X * Y * Z, 3, device=dev, dtype=torch.float32) if want_grids else None
         # scaling uses cfg.NETWORK.HEATMAP_SIZE, sampling the tensor's own extent -- as the reference (:50,84-93)
         ops.unproject(hms, st, cams, centers, grid_size, (X, Y, Z), self.img_size, tuple(hms[0].shape[2:]), C,

@@ -14,7 +14,7 @@ import torch
 from . import _lib
 from .utils.transforms import get_affine_transform
 
-_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}
 
 
 def _stream():
@@ -104,8 +104,9 @@ def linspace_axes(grid_size, cube_size, device):
 # --------------------------------------------------------------------------------------------- K1
 def unproject(heatmaps, hm_strides, cams, centers, grid_size, cube_size, image_size, heatmap_hw, channels,
               out, out_strides, out_c_pad=0, check_flag=False, cubes_per_sample=1, cube_sample=None,
-              grids=None, view_range=None, partial=False, heatmap_cfg_wh=None):
-    """Launch the fused un-projection.
+              grids=None, view_range=None, partial=False, heatmap_cfg_wh=None, fast=False):
+    """Launch the fused un-projection.  ``fast``: the throughput form (fp16 channel-last maps from
+    ``heatmaps_to_f16``, bf16 channel-last cubes with pitch 16; see ``csrc/unproject_fast.cu``).
 
     heatmaps: list[V] of CUDA float32 tensors sharing ``hm_strides = (b, c, h, w)`` element strides.
     cams ``[B,V,32]``, centers ``[n_cubes, >=3]`` float32 CUDA.  ``out`` receives the cubes through
@@ -142,9 +143,28 @@ def unproject(heatmaps, hm_strides, cams, centers, grid_size, cube_size, image_s
     a.out_stride_cube, a.out_stride_c, a.out_stride_vox = [int(s) for s in out_strides]
     a.out_c_pad = int(out_c_pad)
     a.grids = grids.data_ptr() if grids is not None else None
+    a.hm_dtype = _DT[heatmaps[0].dtype]
+    a.math_mode = int(bool(fast))
     n_vox = a.X * a.Y * a.Z
     work = (a.view_end - a.view_begin) * a.B * a.C * a.h * a.w * 4 + a.n_cubes * a.C * n_vox * out.element_size()
     _lib.call("sp3d_unproject_fwd", a, _stream(), kind="unproject", work=work)
+
+
+def heatmaps_to_f16(heatmaps, hm_strides, channels):
+    """list[V] of float32 ``[B,C,h,w]`` CUDA maps (common strides) -> one fp16 tensor ``[V,B,h,w,16]``
+    (channels >= C zero): the heat-map layout of the throughput un-projection."""
+    _require_cuda(*heatmaps)
+    V = len(heatmaps)
+    B, _, h, w = [int(s) for s in heatmaps[0].shape]
+    out = torch.empty(V, B, h, w, 16, device=heatmaps[0].device, dtype=torch.float16)
+    a = _lib.HeatmapsF16Args()
+    for v in range(V):
+        a.heatmaps[v] = heatmaps[v].data_ptr()
+    a.stride_b, a.stride_c, a.stride_h, a.stride_w = [int(s) for s in hm_strides]
+    a.V, a.B, a.C, a.h, a.w = V, B, int(channels), h, w
+    a.out = out.data_ptr()
+    _lib.call("sp3d_heatmaps_to_f16", a, _stream(), kind="layout", work=V * B * h * w * (int(channels) * 4 + 32))
+    return out
 
 
 def unproject_finalize(buf, n_cubes, channels, n_vox, strides):

@@ -104,6 +104,45 @@ def test_unproject_seeded_vs_oracle_many_channels():
     assert np.abs(clb[..., :17].permute(0, 4, 1, 2, 3).float().cpu().numpy() - o_cubes).max() <= 4e-3  # bf16 rounding
 
 
+@pytest.mark.parametrize("cube", [[12, 8, 16], [10, 13, 21]])    # whole tiles / ragged in x, y and z
+def test_unproject_throughput_form_vs_oracle(cube):
+    """math_mode 1 (fp16 channel-last maps, half2 tap blending, bf16 cubes) against the float32 numpy oracle:
+    15 channels, 5 views, rotation + scale + flip, one invalid cube.  Tolerance = bf16 output step (3.9e-3) plus the
+    half-precision blend (~1e-3); voxels within 1e-2 px of an image border may take the other in-image decision
+    and are counted, not compared."""
+    cfg = default_config()
+    cfg.NETWORK.IMAGE_SIZE, cfg.NETWORK.HEATMAP_SIZE = [96, 128], [24, 32]
+    cams = synthetic.ring_cameras(5, seed=7)
+    B, C = 2, 15
+    meta = synthetic.make_meta(cams, B, (96, 128), rotation=[[5.0, -12.0]] * 5, scale_mul=[[1.1, 0.9]] * 5)
+    rs = np.random.RandomState(3)
+    hm_np = rs.rand(5, B, C, 32, 24).astype(np.float32)
+    centers = np.array([[200.0, -700.0, 900.0, 0.0, 1.0], [-900.0, 300.0, 1000.0, 2.0, 1.0],
+                        [100.0, 100.0, 700.0, -1.0, 0.0]], dtype=np.float32)
+    flip = np.array([True, False])
+    layer = project_layer.ProjectLayer(cfg)
+    hms = [torch.from_numpy(h).to(DEV) for h in hm_np]
+    camt = ops.pack_cameras(meta, cfg.NETWORK.IMAGE_SIZE, flip).to(DEV)
+    cen = torch.from_numpy(centers).to(DEV)
+    sample = torch.tensor([0, 1, 1], dtype=torch.int32, device=DEV)
+    before = _lib.launch_count
+    got, _ = layer.project_cl(hms, camt, cen, True, [2000.0] * 3, cube, cube_sample=sample, dtype=torch.bfloat16,
+                              c_pitch=16)
+    assert _lib.launch_count - before == 2          # fp16 conversion + the fused kernel
+    assert got.shape == (3, cube[0], cube[1], cube[2], 16) and got.dtype == torch.bfloat16
+    assert not got[..., 15:].any() and not got[2].any()      # padding channel and the invalid cube are zeros
+    cams_nested = [[{k: np.asarray(v[i]) for k, v in m["camera"].items()} for i in range(B)] for m in meta]
+    for q, b in ((0, 0), (1, 1)):
+        want, _ = geometry.unproject(
+            hm_np[:, b:b + 1], [[c[b]] for c in cams_nested], [m["center"].numpy()[b:b + 1] for m in meta],
+            [m["scale"].numpy()[b:b + 1] for m in meta], [m["rotation"].numpy()[b:b + 1] for m in meta], (96, 128),
+            (24, 32), [2000.0] * 3, centers[q:q + 1], cube, flip=flip[b:b + 1])
+        diff = np.abs(got[q, ..., :15].permute(3, 0, 1, 2).float().cpu().numpy() - want[0])
+        bad = diff > 6e-3
+        assert bad.mean() < 2e-3, (bad.mean(), diff.max())     # border-decision voxels only
+        assert np.median(diff) < 1.5e-3
+
+
 def test_unproject_view_sharded_partial_sums_equal_full():
     """Multi-GPU exchange: sum of per-view-shard partial numerators/counts + finalize == full."""
     g_cfg = default_config()
