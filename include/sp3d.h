@@ -182,6 +182,11 @@ typedef struct {
                                ksize = (1,1,1), ostride = (2,2,2), the packed weight has 8 * cout rows ordered
                                (px, py, pz, co), and out[2x+px, 2y+py, 2z+pz, co] is written for all 8 phases
                                (cout_pitch == cout).  0: one launch per phase through ostride / ooffset. */
+  int zfold;                /* tensor-core path only.  F > 1: F consecutive output positions along W share one GEMM row
+                               (3-D "same" convolutions with cin_pitch == cin, cout_pitch == channel tile, W % F == 0):
+                               the packed weight holds, per (kd, kh), k + F - 1 windows e of [F * cout_pitch][cin] rows
+                               ordered (ro, co) with tap kw = e - ro (zero rows where that is outside the kernel);
+                               cout_pitch_w = F * cout_pitch.  0 / 1: off */
 } sp3d_conv_args;
 int sp3d_conv_fwd(const sp3d_conv_args* a, void* stream);
 /* Debug aid (profiles/conv_stalls.py): when given a device buffer of 148 * 16 uint64, every tensor-core
@@ -210,6 +215,18 @@ typedef struct {
   int src_dtype, dst_dtype;
 } sp3d_layout_args;
 int sp3d_layout_convert(const sp3d_layout_args* a, void* stream);
+
+/* 2 x 2 space-to-depth of an image batch ([N, C, H, W] through the strides, float32 or bf16, H and W even) into
+ * channel-last bf16 [N, H/2, W/2, dst_pitch] with channel (py * 2 + px) * C + c; channels >= 4 C are zeros.
+ * Turns the stride-2 convolutions of PoseResNet (lib/models/pose_resnet.py:58-93,102-105) into stride-1 ones. */
+typedef struct {
+  const void* src; void* dst;
+  int src_dtype;            /* SP3D_F32 or SP3D_BF16 */
+  int64_t stride_n, stride_c, stride_y, stride_x; /* source strides in elements */
+  int N, C, H, W;
+  int dst_pitch;            /* >= 4 C, multiple of 8 */
+} sp3d_s2d_args;
+int sp3d_space_to_depth(const sp3d_s2d_args* a, void* stream);
 
 #ifdef __cplusplus
 }

@@ -88,7 +88,7 @@ class ConvArgs(C.Structure):
         ("cout", C.c_int), ("cout_pitch", C.c_int), ("cout_pitch_w", C.c_int),
         ("ksize", _i3), ("stride", _i3), ("tap_off0", _i3), ("tap_step", _i3), ("ostride", _i3), ("ooffset", _i3),
         ("relu", C.c_int), ("algo", C.c_int), ("in_dtype", C.c_int), ("out_dtype", C.c_int),
-        ("fused_phases", C.c_int),
+        ("fused_phases", C.c_int), ("zfold", C.c_int),
     ]
 
 
@@ -99,6 +99,14 @@ class MaxpoolArgs(C.Structure):
         ("OD", C.c_int), ("OH", C.c_int), ("OW", C.c_int),
         ("k", _i3), ("s", _i3), ("p", _i3),
         ("dtype", C.c_int),
+    ]
+
+
+class S2DArgs(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("dst", C.c_void_p), ("src_dtype", C.c_int),
+        ("stride_n", C.c_int64), ("stride_c", C.c_int64), ("stride_y", C.c_int64), ("stride_x", C.c_int64),
+        ("N", C.c_int), ("C", C.c_int), ("H", C.c_int), ("W", C.c_int), ("dst_pitch", C.c_int),
     ]
 
 
@@ -125,6 +133,7 @@ SYMBOLS = {
     "sp3d_debug_conv_profile": (None, [C.c_void_p]),
     "sp3d_maxpool_fwd": (C.c_int, [C.POINTER(MaxpoolArgs), C.c_void_p]),
     "sp3d_layout_convert": (C.c_int, [C.POINTER(LayoutArgs), C.c_void_p]),
+    "sp3d_space_to_depth": (C.c_int, [C.POINTER(S2DArgs), C.c_void_p]),
 }
 
 _lib = None

@@ -64,6 +64,7 @@ struct TcConvParams {
   void* out;
   int fused_cols;                // fused k2/s2 transposed convolution: columns per (px, py) output phase pair
                                  // (= 2 * cout: (pz, co) is contiguous in the output), else 0
+  int col_mod;                   // > 0: GEMM column -> channel is col % col_mod (fused phases, z-fold)
   int tma_store;                 // 1: epilogue stages rows in smem and stores (and pre-loads the residual) by TMA
   int has_res;
   unsigned long long* prof;      // optional per-CTA wait-cycle counters (sp3d_debug_conv_profile), else NULL
@@ -73,7 +74,7 @@ constexpr int kProfSlots = 16;    // per CTA: mma total, wait halo, wait weights
 // KSX / KS kernel extent along x / along y and z, RB bytes per smem row (= channels per K chunk * 2),
 // N = MMA N (output-channel tile), TX = x-slices (M tiles) per brick, G = taps per weight stage, S = weight stages.
 // HB = halo buffers (2 for the compute-heavy kernels, deeper for 1x1 where a work item is a few MMAs).
-template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB = 2, int SB = 2, int SR = 128, int EG = 2>
+template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB = 2, int SB = 2, int SR = 128, int EG = 2, int F = 1>
 struct TcCfg {
   static constexpr int kThreads = kTcBaseThreads + 128 * EG;
   // epilogue staging ring: SB slots of one x-slice (128 positions) x kStageRow bytes (one swizzled TMA-store box)
@@ -81,32 +82,41 @@ struct TcCfg {
   static constexpr int kStageBytes = 128 * kStageRow;
   static_assert(SB >= 2, "the staging ring needs two slots");
   static_assert(EG == 1 || (EG == 2 && TX % 2 == 0), "x-slices must split evenly over the epilogue groups");
-  static constexpr int HX = TX + KSX - 1, HY = kBY + KS - 1, HZ = kBZ + KS - 1;
+  // z-fold F: F consecutive z positions form ONE smem row (RB = F * bytes per position) and F outputs share one GEMM
+  // row (N = F * channel tile); a z "tap" becomes a window starting at any position inside the row sequence, so
+  // KS + F - 1 windows (with zero weight blocks where window and output do not meet) replace F * KS narrow MMAs.
+  static constexpr int kPad = (KS - 1) / 2;
+  static constexpr int kPosBytes = RB / F;                          // bytes of one position (K of one window)
+  static constexpr int kE0 = F * ((kPad + F - 1) / F) - kPad;       // first window, in positions from the aligned row start
+  static constexpr int KZ = KS + F - 1;                             // windows along z
+  static constexpr int HX = TX + KSX - 1, HY = kBY + KS - 1, HZ = kBZ + (kE0 + KZ - 1) / F;
   static constexpr int kHaloRows = HX * HY * HZ;
   static constexpr int kHaloBytes = kHaloRows * RB;
   static constexpr int kHaloStride = (kHaloBytes + 1023) / 1024 * 1024;
-  static constexpr int kTaps = KSX * KS * KS;
+  static constexpr int kTaps = KSX * KS * KZ;
   static constexpr int kGroups = kTaps / G;             // weight stages consumed per (brick, chunk)
-  static constexpr int kTapBytes = N * RB;
+  static constexpr int kTapBytes = N * kPosBytes;
   static constexpr int kWBytes = G * kTapBytes;         // one stage = G consecutive taps
   static constexpr int kWStride = (kWBytes + 1023) / 1024 * 1024;
   static constexpr int kTapsPerLoad = largest_divisor_le(G, 256 / N);   // TMA box rows <= 256
   static constexpr int kLoads = G / kTapsPerLoad;
   static constexpr int kSmemBytes = HB * kHaloStride + S * kWStride + EG * SB * kStageBytes + 1024;   // + alignment slack
   static_assert(kTaps % G == 0, "taps per stage must divide the tap count");
-  static constexpr int kKSteps = RB / 32;       // tcgen05.mma K = 16 bf16 = 32 bytes
+  static constexpr int kKSteps = kPosBytes / 32;   // tcgen05.mma K = 16 bf16 = 32 bytes
   static constexpr int kIssuers = TX >= 2 ? 2 : 1;
   static constexpr uint32_t kLayout = RB == 128 ? kSwizzle128 : (RB == 64 ? kSwizzle64 : kSwizzle32);
+  static constexpr uint32_t kLayoutW = kPosBytes == 128 ? kSwizzle128 : (kPosBytes == 64 ? kSwizzle64 : kSwizzle32);
+  static_assert(F == 1 || (KSX == KS && kPosBytes >= 32), "z-fold: 3-D same convolutions, one K chunk");
   static_assert(2 * TX * N <= 512, "accumulators exceed TMEM");
   static_assert(kSmemBytes + 3072 <= 227 * 1024, "shared memory budget (dynamic + ~3 KB static)");
 };
 
-template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB, int SB, int SR, int EG>
+template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB, int SB, int SR, int EG, int F>
 __global__ void __launch_bounds__(kTcBaseThreads + 128 * EG, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ TcStoreMaps maps_out, const __grid_constant__ TcStoreMaps maps_res,
                const TcConvParams p) {
-  using C = TcCfg<KSX, KS, RB, N, TX, G, S, HB, SB, SR, EG>;
+  using C = TcCfg<KSX, KS, RB, N, TX, G, S, HB, SB, SR, EG, F>;
   constexpr int kWStages = S;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t halo_full[HB], halo_empty[HB], w_full[kWStages], w_empty[kWStages], acc_full[2], acc_empty[2];
@@ -139,7 +149,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
   }
   for (int i = tid; i < 2 * N; i += C::kThreads) {     // channel tile 0 (the only one unless n_tiles > 1)
     const int co = i % N;
-    const int cs = p.fused_cols ? co % p.cout : co;
+    const int cs = p.col_mod ? co % p.col_mod : co;
     s_scale[i / N][co] = (p.scale != nullptr && cs < p.cout) ? p.scale[cs] : 1.0f;
     s_shift[i / N][co] = (p.shift != nullptr && cs < p.cout) ? p.shift[cs] : 0.0f;
   }
@@ -211,7 +221,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
     const int q = warp - 2;
     const uint32_t idesc = make_idesc(kFmtBF16, 128, N);
     const uint64_t a_desc0 = make_smem_desc(smem_u32(halo), 0, C::HZ * RB, C::kLayout);
-    const uint64_t b_desc0 = make_smem_desc(smem_u32(wbuf), 0, 8 * RB, C::kLayout);
+    const uint64_t b_desc0 = make_smem_desc(smem_u32(wbuf), 0, 8 * C::kPosBytes, C::kLayoutW);
     uint32_t u = 0, w = 0, it = 0;
     long long t_begin = 0, t_halo = 0, t_w = 0, t_acc = 0, t0 = 0;
     const bool prof = p.prof != nullptr;
@@ -231,9 +241,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
         const uint32_t a_lo0 = (uint32_t)a_desc0 + (uint32_t)((buf * C::kHaloStride) >> 4);
         const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
         constexpr uint32_t kRow16 = RB / 16;                       // one halo row in 16-byte units
+        constexpr uint32_t kPos16 = C::kPosBytes / 16;             // one position (= row unless z-folded)
         uint32_t accum = c ? 1u : 0u;                              // first tap of the first chunk overwrites
         int dz = 0, dy = 0;
-        uint32_t a_tap = a_lo0;                                    // start of the current tap's shifted window
+        uint32_t a_tap = a_lo0 + C::kE0 * kPos16;                  // start of the current tap's shifted window
         for (int g = 0; g < C::kGroups; ++g, ++w) {
           const uint32_t st = w % kWStages;
           if (prof) t0 = clock64();
@@ -241,7 +252,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
           if (prof) t_w += clock64() - t0;
           tc_fence_after();
           uint32_t b_lo = (uint32_t)b_desc0 + (uint32_t)((st * C::kWStride) >> 4);
-#pragma unroll(G % KS == 0 ? KS : 1)
+#pragma unroll(G % C::KZ == 0 ? C::KZ : 1)
           for (int j = 0; j < G; ++j) {
 #pragma unroll
             for (int t = q; t < TX; t += C::kIssuers) {
@@ -254,10 +265,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
             accum = 1u;
             b_lo += (uint32_t)(C::kTapBytes >> 4);
             // next tap: z fastest, then y, then x
-            a_tap += kRow16;
-            if (++dz == KS) {
+            a_tap += kPos16;
+            if (++dz == C::KZ) {
               dz = 0;
-              a_tap += (uint32_t)(C::HZ - KS) * kRow16;
+              a_tap += (uint32_t)C::HZ * kRow16 - (uint32_t)C::KZ * kPos16;
               if (++dy == KS) {
                 dy = 0;
                 a_tap += (uint32_t)((C::HY - KS) * C::HZ) * kRow16;
@@ -346,7 +357,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
         const int ch0 = nt * N;
         if (p.n_tiles > 1) {
           if (row < N) {
-            const int co = p.fused_cols ? (ch0 + row) % p.cout : ch0 + row;
+            const int co = p.col_mod ? (ch0 + row) % p.col_mod : ch0 + row;
             s_scale[accbuf][row] = (p.scale != nullptr && co < p.cout) ? __ldg(p.scale + co) : 1.0f;
             s_shift[accbuf][row] = (p.shift != nullptr && co < p.cout) ? __ldg(p.shift + co) : 0.0f;
           }
@@ -615,14 +626,17 @@ static CUtensorMapSwizzle swizzle_for(int rb) {
   return rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
-template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB, int SB, int SR, int EG>
+template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB, int SB, int SR, int EG, int F>
 static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
-  using C = TcCfg<KSX, KS, RB, N, TX, G, S, HB, SB, SR, EG>;
+  using C = TcCfg<KSX, KS, RB, N, TX, G, S, HB, SB, SR, EG, F>;
   EncodeTiledFn encode = get_encode();
   if (encode == nullptr) return SP3D_ERR_UNSUPPORTED;
-  const int chunk_ch = RB / 2;
+  const int chunk_ch = C::kPosBytes / 2;
+  if (F > 1 && (a->zfold != F || a->W % F || a->OW % F || a->cin_pitch != chunk_ch || a->cout_pitch * F != N ||
+                a->fused_phases || a->stride[2] != 1 || a->ostride[2] != 1 || a->tap_off0[2] != -C::kPad))
+    return SP3D_ERR_UNSUPPORTED;
   const int n_chunks = (a->cin + chunk_ch - 1) / chunk_ch;
-  const int n_tiles = a->fused_phases ? (8 * a->cout) / N : (a->cout + N - 1) / N;
+  const int n_tiles = a->fused_phases ? (8 * a->cout) / N : (F > 1 ? 1 : (a->cout + N - 1) / N);
 
   CUtensorMap map_in, map_w;
   TcStoreMaps maps_out, maps_res;
@@ -645,9 +659,9 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
       const int off = fused ? a->ostride[d] - 1 : a->ooffset[d];
       if ((int64_t)(og - 1) * a->ostride[d] + off >= full) return SP3D_ERR_INVALID_ARG;
     }
-    cuuint64_t gdim[5] = {(cuuint64_t)(fused ? 2 * a->cout : a->cout_pitch), (cuuint64_t)a->OW, (cuuint64_t)a->OH,
+    cuuint64_t gdim[5] = {(cuuint64_t)(fused ? 2 * a->cout : a->cout_pitch * F), (cuuint64_t)a->OW / F, (cuuint64_t)a->OH,
                           (cuuint64_t)a->OD, (cuuint64_t)a->N};
-    cuuint64_t gstr[4] = {(cuuint64_t)(pe * a->ostride[2]), (cuuint64_t)(pe * a->TW * a->ostride[1]),
+    cuuint64_t gstr[4] = {(cuuint64_t)(pe * a->ostride[2] * F), (cuuint64_t)(pe * a->TW * a->ostride[1]),
                           (cuuint64_t)(pe * a->TW * a->TH * a->ostride[0]), (cuuint64_t)(pe * a->TW * a->TH * a->TD)};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     cuuint32_t box[5] = {(cuuint32_t)(C::kStageRow / esz), (cuuint32_t)kBZ, (cuuint32_t)kBY, 1, 1};
@@ -667,12 +681,12 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
     }
   }
   {  // activations: [N][D][H][W][cin_pitch] bf16; box = {chunk, HZ, HY, HX, 1} positions, stepped by the conv stride
-    cuuint64_t gdim[5] = {(cuuint64_t)a->cin_pitch, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->D, (cuuint64_t)a->N};
-    cuuint64_t gstr[4] = {(cuuint64_t)a->cin_pitch * 2, (cuuint64_t)a->cin_pitch * 2 * a->W,
+    cuuint64_t gdim[5] = {(cuuint64_t)a->cin_pitch * F, (cuuint64_t)a->W / F, (cuuint64_t)a->H, (cuuint64_t)a->D, (cuuint64_t)a->N};
+    cuuint64_t gstr[4] = {(cuuint64_t)a->cin_pitch * 2 * F, (cuuint64_t)a->cin_pitch * 2 * a->W,
                           (cuuint64_t)a->cin_pitch * 2 * a->W * a->H, (cuuint64_t)a->cin_pitch * 2 * a->W * a->H * a->D};
     cuuint32_t es[5] = {1, (cuuint32_t)a->stride[2], (cuuint32_t)a->stride[1], (cuuint32_t)a->stride[0], 1};
     // with an element stride s the box extent is given in traversed elements: ceil(box / s) elements are loaded
-    cuuint32_t box[5] = {(cuuint32_t)chunk_ch, (cuuint32_t)(C::HZ * a->stride[2]), (cuuint32_t)(C::HY * a->stride[1]),
+    cuuint32_t box[5] = {(cuuint32_t)(chunk_ch * F), (cuuint32_t)(C::HZ * a->stride[2]), (cuuint32_t)(C::HY * a->stride[1]),
                          (cuuint32_t)(C::HX * a->stride[0]), 1};
     if (encode(&map_in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(a->in), gdim, gstr, box, es,
                CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(RB), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -681,25 +695,26 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
   }
   {  // weights: [n_tiles * n_chunks * taps * N rows][chunk channels] bf16 (K-major rows), box = {chunk, taps_per_load * N}
     cuuint64_t gdim[2] = {(cuuint64_t)chunk_ch, (cuuint64_t)C::kTaps * n_chunks * n_tiles * N};
-    cuuint64_t gstr[1] = {(cuuint64_t)RB};
+    cuuint64_t gstr[1] = {(cuuint64_t)C::kPosBytes};
     cuuint32_t box[2] = {(cuuint32_t)chunk_ch, (cuuint32_t)(C::kTapsPerLoad * N)};
     cuuint32_t es[2] = {1, 1};
     if (encode(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a->weight), gdim, gstr, box, es,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(RB), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(C::kPosBytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return SP3D_ERR_INVALID_ARG;
   }
   TcConvParams p{};
-  p.n_outer = a->N; p.X = a->OD; p.Y = a->OH; p.Z = a->OW;
+  p.n_outer = a->N; p.X = a->OD; p.Y = a->OH; p.Z = a->OW / F;
   p.bricks_x = (a->OD + TX - 1) / TX;
   p.bricks_y = (a->OH + kBY - 1) / kBY;
-  p.bricks_z = (a->OW + kBZ - 1) / kBZ;
+  p.bricks_z = (a->OW / F + kBZ - 1) / kBZ;
   p.n_bricks = a->N * p.bricks_x * p.bricks_y * p.bricks_z;
   p.n_tiles = n_tiles;
   p.n_chunks = n_chunks;
   for (int d = 0; d < 3; ++d) {
     p.istride[d] = a->stride[d];
     p.origin[d] = a->tap_off0[d];
+    if (F > 1 && d == 2) p.origin[d] = -((C::kPad + F - 1) / F);   // in rows of F positions
     p.ostride[d] = a->ostride[d];
     p.ooff[d] = a->ooffset[d];
   }
@@ -711,6 +726,7 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
   p.prof = g_conv_prof;
   p.tma_store = tma_store ? 1 : 0;
   p.fused_cols = fused ? 2 * a->cout : 0;
+  p.col_mod = fused ? a->cout : (F > 1 ? a->cout_pitch : 0);
   p.has_res = a->residual != nullptr ? 1 : 0;
 
   static int n_sm = 0;
@@ -719,7 +735,7 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   }
-  auto kern = conv_tc_kernel<KSX, KS, RB, N, TX, G, S, HB, SB, SR, EG>;
+  auto kern = conv_tc_kernel<KSX, KS, RB, N, TX, G, S, HB, SB, SR, EG, F>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
   if (e != cudaSuccess) { set_last_error(e); return SP3D_ERR_LAUNCH; }
   const int items = p.n_bricks * p.n_tiles;
@@ -746,17 +762,22 @@ int conv_tc(const sp3d_conv_args* a, cudaStream_t st) {
       (reinterpret_cast<uintptr_t>(a->out) % 16) || (a->cin_pitch % 8))
     return SP3D_ERR_INVALID_ARG;
   const int cin = a->cin, n = a->cout_pitch_w;
-  const int rb = cin >= 64 ? 128 : cin * 2;
+  const int zf = a->zfold > 1 ? a->zfold : 1;
+  const int rb = cin >= 64 ? 128 : cin * 2 * zf;
   if (cin >= 64 && (cin % 64)) return SP3D_ERR_UNSUPPORTED;
   if (a->cin_pitch < cin) return SP3D_ERR_INVALID_ARG;
   // (kernel x, kernel yz, row bytes, N, x-slices per brick, taps per weight stage, weight stages)
+#define SP3D_TC_CASE_F(KSX_, KS_, RB_, N_, TX_, G_, S_, HB_, SB_, SR_, EG_, F_) \
+  if (ksx == KSX_ && ks == KS_ && rb == RB_ && n == N_ && zf == F_) \
+    return launch_tc<KSX_, KS_, RB_, N_, TX_, G_, S_, HB_, SB_, SR_, EG_, F_>(a, st);
 #define SP3D_TC_CASE(KSX_, KS_, RB_, N_, TX_, G_, S_, HB_, SB_, SR_, EG_) \
-  if (ksx == KSX_ && ks == KS_ && rb == RB_ && n == N_) \
-    return launch_tc<KSX_, KS_, RB_, N_, TX_, G_, S_, HB_, SB_, SR_, EG_>(a, st);
+  SP3D_TC_CASE_F(KSX_, KS_, RB_, N_, TX_, G_, S_, HB_, SB_, SR_, EG_, 1)
   // (kernel x, kernel yz, row bytes, N, x-slices per brick, taps per weight stage, weight stages, halo buffers,
   //  epilogue staging slots per group, staged row bytes cap, epilogue groups)
   // 3-D (V2VNet)
   SP3D_TC_CASE(7, 7, 32, 16, 2, 49, 2, 2, 2, 128, 2)
+  // 7^3 stem, z-folded by 2: rows of 2 positions x 16 channels, N = 2 x 16, 8 windows per (dx, dy); one halo buffer
+  SP3D_TC_CASE_F(7, 7, 64, 32, 4, 8, 3, 1, 2, 128, 1, 2)
   SP3D_TC_CASE(3, 3, 32, 32, 4, 27, 2, 2, 3, 128, 2)
   SP3D_TC_CASE(3, 3, 64, 32, 4, 9, 2, 2, 2, 128, 2)
   SP3D_TC_CASE(3, 3, 64, 64, 4, 3, 3, 2, 2, 64, 2)
@@ -774,7 +795,10 @@ int conv_tc(const sp3d_conv_args* a, cudaStream_t st) {
   SP3D_TC_CASE(1, 3, 128, 64, 4, 1, 3, 2, 2, 64, 1)
   SP3D_TC_CASE(1, 3, 128, 128, 2, 3, 2, 2, 2, 128, 1)
   SP3D_TC_CASE(1, 2, 128, 128, 2, 2, 3, 2, 2, 128, 1)
+  // 7x7/s2 stem on the 2x2 space-to-depth image (4x4 taps over 16 channels)
+  SP3D_TC_CASE(1, 4, 32, 64, 4, 4, 3, 2, 2, 128, 2)
 #undef SP3D_TC_CASE
+#undef SP3D_TC_CASE_F
   return SP3D_ERR_UNSUPPORTED;
 }
 

@@ -1,0 +1,75 @@
+// 2 x 2 space-to-depth of an image batch into the channel-last bf16 layout the tensor-core convolution reads:
+//   dst[n, y', x', (py * 2 + px) * C + c] = src[n, c, 2 y' + py, 2 x' + px]          (channels >= 4 C are zero)
+// A stride-2 convolution on src becomes a stride-1 convolution (kernel ceil-halved) on dst, which is how the 7x7/s2
+// stem and the 3x3/s2 convolutions of PoseResNet (lib/models/pose_resnet.py:102-105, 58-93) reach the tcgen05 path.
+#include "sp3d_common.cuh"
+
+namespace sp3d {
+
+template <typename T>
+__device__ __forceinline__ float s2d_load(const T* p);
+template <>
+__device__ __forceinline__ float s2d_load<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float s2d_load<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// one thread per (output position, group of 8 output channels) -> one 16-byte store
+template <typename T>
+__global__ void space_to_depth_kernel(const sp3d_s2d_args a) {
+  const int groups = a.dst_pitch / 8;
+  const int OH = a.H / 2, OW = a.W / 2;
+  const int64_t total = (int64_t)a.N * OH * OW * groups;
+  const T* src = reinterpret_cast<const T*>(a.src);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const int64_t pos = i / groups;
+    const int x = (int)(pos % OW), y = (int)((pos / OW) % OH);
+    const int64_t n = pos / ((int64_t)OW * OH);
+    __align__(16) __nv_bfloat16 o[8];
+    if (sizeof(T) == 2 && a.stride_c == 1 && (a.C % 8) == 0 && 8 * g < 4 * a.C) {
+      // channel-last bf16 source: 8 consecutive channels of one source pixel = one 16-byte copy
+      const int q = (8 * g) / a.C, c0 = (8 * g) % a.C;
+      const T* p = src + n * a.stride_n + (int64_t)(2 * y + (q >> 1)) * a.stride_y + (int64_t)(2 * x + (q & 1)) * a.stride_x + c0;
+      *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(p);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int ch = 8 * g + j;
+        float v = 0.0f;
+        if (ch < 4 * a.C) {
+          const int q = ch / a.C, c = ch % a.C;
+          v = s2d_load<T>(src + n * a.stride_n + (int64_t)c * a.stride_c + (int64_t)(2 * y + (q >> 1)) * a.stride_y +
+                          (int64_t)(2 * x + (q & 1)) * a.stride_x);
+        }
+        o[j] = __float2bfloat16_rn(v);
+      }
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.dst) + pos * a.dst_pitch + 8 * g) =
+        *reinterpret_cast<const uint4*>(o);
+  }
+}
+
+}  // namespace sp3d
+
+extern "C" int sp3d_space_to_depth(const sp3d_s2d_args* a, void* stream) {
+  using namespace sp3d;
+  if (a == nullptr || a->src == nullptr || a->dst == nullptr || a->N < 0 || a->C < 1 || a->H < 2 || a->W < 2 ||
+      (a->H & 1) || (a->W & 1) || a->dst_pitch < 4 * a->C || (a->dst_pitch % 8) ||
+      (reinterpret_cast<uintptr_t>(a->dst) % 16))
+    return SP3D_ERR_INVALID_ARG;
+  if (a->src_dtype != SP3D_F32 && a->src_dtype != SP3D_BF16) return SP3D_ERR_UNSUPPORTED;
+  const int64_t total = (int64_t)a->N * (a->H / 2) * (a->W / 2) * (a->dst_pitch / 8);
+  if (total == 0) return SP3D_OK;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a->src_dtype == SP3D_F32) {
+    space_to_depth_kernel<float><<<blocks, 256, 0, st>>>(*a);
+  } else {
+    // the 16-byte copy path needs aligned source pixels
+    if (a->stride_c == 1 && (a->C % 8) == 0 &&
+        ((reinterpret_cast<uintptr_t>(a->src) % 16) || (a->stride_x % 8) || (a->stride_y % 8) || (a->stride_n % 8)))
+      return SP3D_ERR_INVALID_ARG;
+    space_to_depth_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(*a);
+  }
+  return check_launch();
+}

@@ -31,6 +31,24 @@ def _pc(conv, bn, relu):
     return ops.PackedConv(conv.weight, conv.bias, bn, conv.stride[0], conv.padding[0], relu=relu)
 
 
+def _s2d(conv, bn, relu):
+    """Space-to-depth form of a stride-2 3x3 / 7x7 convolution for the tcgen05 path (None if not applicable)."""
+    if conv.stride[0] != 2 or conv.bias is not None or (conv.kernel_size[0], conv.padding[0]) not in ((3, 1), (7, 3)):
+        return None
+    if not (conv.in_channels * 4 < 64 or conv.in_channels % 16 == 0) or conv.out_channels % 64:
+        return None
+    return ops.S2DConv(conv.weight, bn, conv.padding[0], relu)
+
+
+def _strided_conv_cl(pc, s2d, x):
+    """``x``: channel-last ``[N,1,H,W,C]``.  bf16 activations with even extents take the space-to-depth tensor-core
+    form of a stride-2 convolution; everything else the generic kernel."""
+    N, _, H, W, C = [int(v) for v in x.shape]
+    if s2d is not None and x.dtype == torch.bfloat16 and H % 2 == 0 and W % 2 == 0 and C == s2d.cin:
+        return s2d(x, (H * W * C, 1, W * C, C), N, H, W)
+    return pc(x)
+
+
 class BasicBlock(nn.Module):
     expansion = 1
 
@@ -75,12 +93,13 @@ class Bottleneck(nn.Module):
     def _packed(self):
         def build():
             d = _pc(self.downsample[0], self.downsample[1], 0) if self.downsample is not None else None
-            return _pc(self.conv1, self.bn1, 1), _pc(self.conv2, self.bn2, 1), _pc(self.conv3, self.bn3, 1), d
+            return (_pc(self.conv1, self.bn1, 1), _pc(self.conv2, self.bn2, 1), _pc(self.conv3, self.bn3, 1), d,
+                    _s2d(self.conv2, self.bn2, 1))
         return self._cache.get(self, build)
 
     def forward_cl(self, x):
-        a, b, c, d = self._packed()
-        return c(b(a(x)), residual=x if d is None else d(x))
+        a, b, c, d, b2 = self._packed()
+        return c(_strided_conv_cl(b, b2, a(x)), residual=x if d is None else d(x))
 
 
 class PoseResNet(nn.Module):
@@ -145,17 +164,26 @@ class PoseResNet(nn.Module):
                 deconvs.append(ops.PackedConv(ct.weight, ct.bias, bn, ct.stride[0], ct.padding[0], transposed=True,
                                               relu=1))
             head = _pc(self.final_layer, None, 0)
-            return stem, deconvs, head
+            return stem, deconvs, head, _s2d(self.conv1, self.bn1, 1)
         mods = nn.ModuleList([self.conv1, self.bn1, self.deconv_layers, self.final_layer])
         return self._cache.get(mods, build)
 
-    def forward_cl(self, x, out_pitch=None):
-        """``x``: channel-last ``[N,1,H,W,4]`` float32 image batch -> ``(heat-maps [N,1,h,w,pitch], features)``."""
+    def forward_cl(self, x, out_pitch=None, image=None):
+        """``x``: channel-last ``[N,1,H,W,4]`` float32 image batch, or ``image``: the ``[N,3,H,W]`` float32 tensor
+        itself -> ``(heat-maps [N,1,h,w,pitch], features)``."""
         _no_train(self)
-        stem, deconvs, head = self._packed()
+        stem, deconvs, head, stem_s2d = self._packed()
         # bf16 mode: the 7x7 stem reads the float32 image and writes bf16; from there on activations are bf16
         # (tcgen05 convolutions where the shape is covered) and the heat-maps leave the net in float32
-        x = stem(x, out_dtype=torch.bfloat16 if ops.volume_dtype() == torch.bfloat16 else None)
+        bf16 = ops.volume_dtype() == torch.bfloat16
+        if image is not None and bf16 and stem_s2d is not None and image.shape[2] % 2 == 0 and image.shape[3] % 2 == 0:
+            # straight from the NCHW float32 image: 2x2 space-to-depth (bf16) + 4x4 tensor-core convolution
+            n, _, h, w = [int(v) for v in image.shape]
+            x = stem_s2d(image, image.stride(), n, h, w)
+        else:
+            if x is None:
+                x = ops.to_channel_last(image.unsqueeze(2), c_pitch=4)
+            x = stem(x, out_dtype=torch.bfloat16 if bf16 else None)
         x = ops.maxpool(x, 64, [1, 3, 3], [1, 2, 2], [0, 1, 1])
         for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
             for blk in layer:
@@ -167,8 +195,7 @@ class PoseResNet(nn.Module):
     def forward(self, x, attn=False):
         """``[N,3,H,W]`` -> ``[N,J,H/4,W/4]`` (reference :191-207).  The result is a zero-copy
         channel-last view (``stride(1) == 1``), which the un-projection kernel reads directly."""
-        xin = ops.to_channel_last(x.float().unsqueeze(2), c_pitch=4)
-        y, feat = self.forward_cl(xin, out_pitch=ops.round_up(self.num_joints, 4))
+        y, feat = self.forward_cl(None, out_pitch=ops.round_up(self.num_joints, 4), image=x.float().contiguous())
         out = y[:, 0].permute(0, 3, 1, 2)[:, :self.num_joints]
         if attn:
             return out, feat[:, 0].permute(0, 3, 1, 2)[:, :feat.shape[-1]]

@@ -271,6 +271,71 @@ def to_channel_first(x, channels, dtype=None):
     return dst
 
 
+def space_to_depth(x, channels, strides, n, h, w, dst_pitch):
+    """``x`` addressed as ``[n, channels, h, w]`` through element ``strides = (n, c, y, x)`` (float32 or bf16) ->
+    channel-last bf16 ``[n, 1, h/2, w/2, dst_pitch]`` with channel ``(py*2+px)*channels + c``."""
+    _require_cuda(x)
+    out = torch.empty(n, 1, h // 2, w // 2, dst_pitch, device=x.device, dtype=torch.bfloat16)
+    a = _lib.S2DArgs()
+    a.src, a.dst = x.data_ptr(), out.data_ptr()
+    a.src_dtype = _DT[x.dtype]
+    a.stride_n, a.stride_c, a.stride_y, a.stride_x = [int(s) for s in strides]
+    a.N, a.C, a.H, a.W, a.dst_pitch = int(n), int(channels), int(h), int(w), int(dst_pitch)
+    _lib.call("sp3d_space_to_depth", a, _stream(), kind="layout",
+              work=n * h * w * channels * x.element_size() + out.numel() * 2)
+    return out
+
+
+class S2DConv:
+    """A stride-2 2-D convolution (3x3/p1 or 7x7/p3, + folded BatchNorm + ReLU) evaluated on the tcgen05 path as a
+    stride-1 convolution over the 2x2 space-to-depth tensor: tap ``d`` with offset ``t = d - pad`` lands on
+    sub-pixel ``t mod 2`` of tap ``floor(t / 2)``, so the kernel shrinks to 2x2 / 4x4 over ``4 * cin`` channels."""
+
+    def __init__(self, weight, bn, padding, relu):
+        w = weight.detach().float()
+        self.cout, self.cin, k = int(w.shape[0]), int(w.shape[1]), int(w.shape[2])
+        pad = int(padding)
+        self.dmin = (0 - pad) // 2
+        self.kp = (k - 1 - pad) // 2 - self.dmin + 1
+        c4 = 4 * self.cin
+        self.cin_tc = round_up(c4, 16) if c4 < 64 else round_up(c4, 64)
+        chunk = min(self.cin_tc, 64)
+        self.n = next((v for v in (64, 128) if v >= self.cout), 128)
+        n_tiles = -(-self.cout // self.n)
+        w2 = torch.zeros(self.kp, self.kp, n_tiles * self.n, self.cin_tc, device=w.device, dtype=torch.float32)
+        for dy in range(k):
+            ty = dy - pad
+            for dx in range(k):
+                tx = dx - pad
+                q = (ty - 2 * (ty // 2)) * 2 + (tx - 2 * (tx // 2))
+                w2[ty // 2 - self.dmin, tx // 2 - self.dmin, :self.cout, q * self.cin:(q + 1) * self.cin] = w[:, :, dy, dx]
+        taps = self.kp * self.kp
+        full = w2.reshape(taps, n_tiles, self.n, self.cin_tc // chunk, chunk).permute(1, 3, 0, 2, 4)
+        self.weight = full.to(torch.bfloat16).contiguous()
+        inv = torch.rsqrt(bn.running_var.detach().float() + bn.eps)
+        self.scale = (bn.weight.detach().float() * inv).contiguous()
+        self.shift = (bn.bias.detach().float() - bn.running_mean.detach().float() * self.scale).contiguous()
+        self.relu = int(relu)
+
+    @staticmethod
+    def supported(conv, h, w):
+        k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+        return (s == 2 and (k, p) in ((3, 1), (7, 3)) and h % 2 == 0 and w % 2 == 0 and conv.bias is None
+                and (conv.in_channels * 4 < 64 or conv.in_channels % 16 == 0) and conv.out_channels % 64 == 0)
+
+    def __call__(self, x, strides, n, h, w):
+        """``x``: source addressed as ``[n, cin, h, w]`` through ``strides``; returns channel-last bf16
+        ``[n, 1, h/2, w/2, cout]``."""
+        xs = space_to_depth(x, self.cin, strides, n, h, w, self.cin_tc)
+        oh, ow = h // 2, w // 2
+        out = torch.empty(n, 1, oh, ow, round_up(self.cout, 16), device=x.device, dtype=torch.bfloat16)
+        conv_launch(xs.view(1, n, oh, ow, self.cin_tc), self.weight, self.scale, self.shift, None,
+                    out.view(1, n, oh, ow, out.shape[-1]), self.cin_tc, self.cout, (n, oh, ow), [1, self.kp, self.kp],
+                    [1, 1, 1], [0, self.dmin, self.dmin], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu, _lib.CONV_TC_BF16,
+                    cin_real=self.cin * 4, cout_pitch_w=self.n)
+        return out
+
+
 # --------------------------------------------------------------------------------------------- conv family
 def _set3(field, vals):
     for i in range(3):
@@ -278,7 +343,8 @@ def _set3(field, vals):
 
 
 def conv_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksize, stride, tap_off0, tap_step,
-                ostride, ooffset, relu, algo=_lib.CONV_SIMT_F32, cin_real=None, cout_pitch_w=None, fused_phases=False):
+                ostride, ooffset, relu, algo=_lib.CONV_SIMT_F32, cin_real=None, cout_pitch_w=None, fused_phases=False,
+                zfold=0):
     """One implicit-GEMM convolution launch.  ``x`` / ``out`` are channel-last 5-D ``[N,D,H,W,pitch]``."""
     a = _lib.ConvArgs()
     a.in_ = x.data_ptr()
@@ -305,6 +371,7 @@ def conv_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksi
     a.algo = int(algo)
     a.in_dtype, a.out_dtype = _DT[x.dtype], _DT[out.dtype]
     a.fused_phases = int(bool(fused_phases))
+    a.zfold = int(zfold)
     flops = 2.0 * a.N * a.OD * a.OH * a.OW * a.cout * (cin_real or a.cin) * (a.ksize[0] * a.ksize[1] * a.ksize[2])
     if fused_phases:
         flops *= 8
@@ -443,6 +510,28 @@ class PackedConv:
             self._tc = (packs, n, cin_tc)
         return self._tc
 
+    ZFOLD = 2
+
+    def _tc_zfold_ok(self, w_extent, out_pitch):
+        """The 7^3 stem (cin <= 16 -> 16 channels) runs z-folded: 2 output positions per GEMM row (N = 32)."""
+        return (self.nd == 3 and not self.transposed and self.k == [7, 7, 7] and self.stride == [1, 1, 1]
+                and self.padding == [3, 3, 3] and self.cin <= 16 and self.cout == 16 and out_pitch == 16
+                and w_extent % self.ZFOLD == 0)
+
+    def _tc_pack_zfold(self):
+        """bf16 ``[1, 1, kd*kh*(k+F-1), F*16, 16]``: per (kd, kh) the k+F-1 windows e, rows (ro, co), tap kw = e - ro."""
+        if getattr(self, "_tc_zf", None) is None:
+            F, k = self.ZFOLD, self.k[2]
+            w5 = self._subs[0]                                     # [Cout, Cin, kd, kh, kw]
+            full = torch.zeros(self.k[0], self.k[1], k + F - 1, F, 16, 16, device=w5.device, dtype=torch.float32)
+            for e in range(k + F - 1):
+                for ro in range(F):
+                    kw = e - ro
+                    if 0 <= kw < k:
+                        full[:, :, e, ro, :self.cout, :self.cin] = w5[:, :, :, :, kw].permute(2, 3, 0, 1)
+            self._tc_zf = full.reshape(1, 1, -1, F * 16, 16).to(torch.bfloat16).contiguous()
+        return self._tc_zf
+
     def _tc_fused_ok(self, out_pitch, out_dtype):
         """k2/s2 transposed 3-D convolution as ONE launch (all 8 output phases are extra GEMM columns)."""
         esz = 4 if out_dtype == torch.float32 else 2
@@ -481,7 +570,11 @@ class PackedConv:
             outk = out.view(1, N, o[1], o[2], out_pitch)
             resk = residual.view(1, N, o[1], o[2], out_pitch) if residual is not None else None
             D, o = N, [N, o[1], o[2]]
-        if not self.transposed:
+        if not self.transposed and pitch == 16 and self._tc_zfold_ok(W, out_pitch):
+            conv_launch(xk, self._tc_pack_zfold(), self.scale, self.shift, resk, outk, 16, self.cout, o, self.k,
+                        self.stride, [-p for p in self.padding], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu,
+                        _lib.CONV_TC_BF16, cin_real=self.cin, cout_pitch_w=16 * self.ZFOLD, zfold=self.ZFOLD)
+        elif not self.transposed:
             conv_launch(xk, packs[0], self.scale, self.shift, resk, outk, cin_tc, self.cout, o, self.k, self.stride,
                         [-p for p in self.padding], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu, _lib.CONV_TC_BF16,
                         cin_real=self.cin, cout_pitch_w=n)

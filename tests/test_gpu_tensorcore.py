@@ -94,6 +94,55 @@ def test_tc_transposed_conv_matches_float64_reference(cin, cout, with_skip, shap
     assert float((gotb - want).abs().max()) <= 6e-3 * scale
 
 
+@pytest.mark.parametrize("cin", [15, 1])
+@pytest.mark.parametrize("shape", [(6, 20, 12), (5, 17, 34), (3, 9, 7)])    # even W: z-folded kernel; odd W: plain kernel
+def test_tc_stem_conv7_zfold_matches_float64_reference(cin, shape):
+    """The 7^3 stem: two output positions along W share one GEMM row (N = 2 x 16) when W is even."""
+    torch.manual_seed(cin)
+    conv = nn.Conv3d(cin, 16, 7, 1, 3)
+    bn = rand_bn(nn.BatchNorm3d(16), cin)
+    with torch.no_grad():
+        conv.weight.copy_(bf16_round(conv.weight))
+    x = bf16_round(torch.randn(2, cin, *shape))
+    with torch.no_grad():
+        want = F.relu(bn.double()(conv.double()(x.double())))
+    conv, bn = conv.float().to(DEV), bn.float().to(DEV)
+    pc = ops.PackedConv(conv.weight, conv.bias, bn, 1, 3, relu=1)
+    assert pc._tc_zfold_ok(shape[2], 16) == (shape[2] % 2 == 0)
+    y = pc(to_cl_bf16(x), out_pitch=16, out_dtype=torch.float32)
+    got = ops.to_channel_first(y, 16).cpu().double()
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) <= 2e-5 * scale, float((got - want).abs().max()) / scale
+    yb = pc(to_cl_bf16(x), out_pitch=16)
+    gotb = ops.to_channel_first(yb, 16, dtype=torch.float32).cpu().double()
+    assert float((gotb - want).abs().max()) <= 6e-3 * scale
+
+
+@pytest.mark.parametrize("k,p,cin,cout,hw", [(3, 1, 128, 128, (24, 18)), (3, 1, 256, 256, (12, 34)), (7, 3, 3, 64, (40, 36))])
+def test_tc_stride2_conv_space_to_depth_matches_float64_reference(k, p, cin, cout, hw):
+    """Stride-2 3x3 / 7x7 convolutions as stride-1 tensor-core convolutions over the 2x2 space-to-depth tensor."""
+    torch.manual_seed(k * 100 + cin)
+    conv = nn.Conv2d(cin, cout, k, 2, p, bias=False)
+    bn = rand_bn(nn.BatchNorm2d(cout), cin)
+    with torch.no_grad():
+        conv.weight.copy_(bf16_round(conv.weight))
+    x = bf16_round(torch.randn(3, cin, *hw))
+    with torch.no_grad():
+        want = F.relu(bn.double()(conv.double()(x.double())))
+    conv, bn = conv.float().to(DEV), bn.float().to(DEV)
+    sc = ops.S2DConv(conv.weight, bn, p, relu=1)
+    xd = x.to(DEV)
+    if cin == 3:      # the stem reads the channel-first float32 image directly
+        y = sc(xd, xd.stride(), 3, hw[0], hw[1])
+    else:             # trunk convolutions read channel-last bf16 activations
+        xcl = ops.to_channel_last(xd.unsqueeze(2), c_pitch=cin, dtype=torch.bfloat16)
+        y = sc(xcl, (hw[0] * hw[1] * cin, 1, hw[1] * cin, cin), 3, hw[0], hw[1])
+    got = ops.to_channel_first(y, cout, dtype=torch.float32)[:, :, 0].cpu().double()
+    scale = float(want.abs().max())
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= 6e-3 * scale, float((got - want).abs().max()) / scale
+
+
 def test_v2v_net_bf16_mode_vs_float64_oracle():
     """Whole V2VNet(15,15) on a 32^3 cube and V2VNet(1,1) on a 40x40x12 grid in bf16 tensor-core mode.
     bf16 activations carry ~3 significant digits; the result is compared with the float64 oracle relative
