@@ -11,21 +11,22 @@
 
 namespace sp3d {
 
-constexpr int kNmsThreads = 256;
+constexpr int kNmsMaxThreads = 1024;   // one CTA per sample: as many threads as the candidate lists leave room for
 constexpr int kNmsMaxK = 32;
 
 __device__ __forceinline__ bool better(float va, int ia, float vb, int ib) {
   return va > vb || (va == vb && ia < ib);
 }
 
-__global__ void __launch_bounds__(kNmsThreads) nms_topk_kernel(const sp3d_nms_topk_args a) {
+__global__ void __launch_bounds__(kNmsMaxThreads) nms_topk_kernel(const sp3d_nms_topk_args a) {
+  const int kNmsThreads = blockDim.x;
   extern __shared__ unsigned char smem_raw[];
   // per-thread candidate lists, interleaved so that slot s of thread t is at [s * kNmsThreads + t]
   float* cand_v = reinterpret_cast<float*>(smem_raw);
   int* cand_i = reinterpret_cast<int*>(cand_v + a.K * kNmsThreads);
-  __shared__ float red_v[kNmsThreads / 32];
-  __shared__ int red_i[kNmsThreads / 32];
-  __shared__ int red_t[kNmsThreads / 32];
+  __shared__ float red_v[kNmsMaxThreads / 32];
+  __shared__ int red_i[kNmsMaxThreads / 32];
+  __shared__ int red_t[kNmsMaxThreads / 32];
   __shared__ int win_t;
 
   const int b = blockIdx.x;
@@ -124,11 +125,14 @@ extern "C" int sp3d_nms_topk3d(const sp3d_nms_topk_args* a, void* stream) {
     return SP3D_ERR_INVALID_ARG;
   if ((int64_t)a->X * a->Y * a->Z < a->K) return SP3D_ERR_INVALID_ARG;  // torch.topk would raise
   if (a->B == 0) return SP3D_OK;
-  const size_t smem = (size_t)a->K * kNmsThreads * (sizeof(float) + sizeof(int));
+  // per-thread candidate lists of K (value, index) pairs live in shared memory: 1024 threads up to K = 25
+  int threads = kNmsMaxThreads;
+  while ((size_t)a->K * threads * 8 > 200 * 1024) threads /= 2;
+  const size_t smem = (size_t)a->K * threads * (sizeof(float) + sizeof(int));
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(nms_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_last_error(e); return SP3D_ERR_LAUNCH; }
   }
-  nms_topk_kernel<<<a->B, kNmsThreads, smem, static_cast<cudaStream_t>(stream)>>>(*a);
+  nms_topk_kernel<<<a->B, threads, smem, static_cast<cudaStream_t>(stream)>>>(*a);
   return check_launch();
 }

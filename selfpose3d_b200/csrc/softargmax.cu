@@ -141,6 +141,14 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_partial_kernel(const sp
 // each owning 4 consecutive channels, so one 16-byte load per lane is a fully coalesced 512-byte warp request
 // and the online-softmax state is 20 registers per lane.  The CTA merge is parallel: shared per-channel maximum
 // first, then every lane rescales its state once and plain sums are reduced (float64 from here on).
+// 2^x on the special-function unit (2 ulp); the argument is a small non-positive difference wherever the
+// weight matters, so the result is as accurate as expf for this use
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int LPV>
 __global__ void __launch_bounds__(kSaThreads) softargmax_stream_kernel(const sp3d_softargmax_args a, int splits,
                                                                         int vox_per_split) {
@@ -170,29 +178,55 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_stream_kernel(const sp3
   float m[4], s[4], wx[4], wy[4], wz[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) { m[k] = -INFINITY; s[k] = 0.f; wx[k] = 0.f; wy[k] = 0.f; wz[k] = 0.f; }
-  for (int vox = v_begin + tid / LPV; vox < v_end; vox += kSaThreads / LPV) {
-    const int iz = vox % a.Z, t = vox / a.Z;
-    const int iy = t % a.Y, ix = t / a.Y;
-    const float gx = s_g[0][ix], gy = s_g[1][iy], gz = s_g[2][iz];
-    const float4 q = ldg4(xb + (int64_t)vox * a.stride_vox + 4 * cq);
-    const float xv[4] = {q.x, q.y, q.z, q.w};
+  // voxel (ix, iy, iz) advances by a constant step: carried incrementally instead of two integer divisions per voxel
+  constexpr int kStep = kSaThreads / LPV;
+  const int step_z = kStep % a.Z, step_yq = kStep / a.Z;
+  const int step_y = step_yq % a.Y, step_x = step_yq / a.Y;
+  int vox = v_begin + tid / LPV;
+  int iz = vox % a.Z, iy = (vox / a.Z) % a.Y, ix = vox / (a.Z * a.Y);
+  const float kLog2e = 1.4426950408889634f;
+  constexpr int kUnroll = 4;   // loads of 4 voxels in flight per lane before the (serially dependent) updates
+  while (vox < v_end) {
+    float4 q[kUnroll];
+    float g[kUnroll][3];
+    bool live[kUnroll];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (k < nch) {
-        const float z = __fmul_rn(a.beta, xv[k]);
-        if (z > m[k]) {
-          const float sc = expf(m[k] - z);  // exp(-inf) = 0 on the first element
-          s[k] = fmaf(s[k], sc, 1.0f);
-          wx[k] = fmaf(wx[k], sc, gx);
-          wy[k] = fmaf(wy[k], sc, gy);
-          wz[k] = fmaf(wz[k], sc, gz);
-          m[k] = z;
-        } else {
-          const float e = expf(z - m[k]);
-          s[k] += e;
-          wx[k] = fmaf(e, gx, wx[k]);
-          wy[k] = fmaf(e, gy, wy[k]);
-          wz[k] = fmaf(e, gz, wz[k]);
+    for (int j = 0; j < kUnroll; ++j) {
+      live[j] = vox < v_end;
+      if (live[j]) {
+        q[j] = ldg4(xb + (int64_t)vox * a.stride_vox + 4 * cq);
+        g[j][0] = s_g[0][ix]; g[j][1] = s_g[1][iy]; g[j][2] = s_g[2][iz];
+      }
+      vox += kStep;
+      iz += step_z;
+      if (iz >= a.Z) { iz -= a.Z; ++iy; }
+      iy += step_y;
+      if (iy >= a.Y) { iy -= a.Y; ++ix; }
+      ix += step_x;
+    }
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+      if (!live[j]) continue;
+      const float gx = g[j][0], gy = g[j][1], gz = g[j][2];
+      const float xv[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < nch) {
+          const float z = __fmul_rn(a.beta, xv[k]);        // the reference's float32 beta * x
+          if (z > m[k]) {
+            const float sc = ex2_approx((m[k] - z) * kLog2e);  // 2^-inf = 0 on the first element
+            s[k] = fmaf(s[k], sc, 1.0f);
+            wx[k] = fmaf(wx[k], sc, gx);
+            wy[k] = fmaf(wy[k], sc, gy);
+            wz[k] = fmaf(wz[k], sc, gz);
+            m[k] = z;
+          } else {
+            const float e = ex2_approx((z - m[k]) * kLog2e);
+            s[k] += e;
+            wx[k] = fmaf(e, gx, wx[k]);
+            wy[k] = fmaf(e, gy, wy[k]);
+            wz[k] = fmaf(e, gz, wz[k]);
+          }
         }
       }
     }
@@ -240,23 +274,42 @@ __global__ void __launch_bounds__(kSaThreads) softargmax_stream_kernel(const sp3
   }
 }
 
+// one warp per (cube, channel): lanes take the splits, shared maximum first, then plain float64 sums
 __global__ void softargmax_merge_kernel(const sp3d_softargmax_args a, int splits) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (cube, channel)
+  const int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);  // (cube, channel)
+  const int lane = threadIdx.x & 31;
   if (i >= a.n_cubes * a.C) return;
   const int cube = i / a.C, c = i % a.C;
   const float* cen = a.centers + (int64_t)cube * a.center_stride;
   float* o = a.out + (int64_t)i * 3;
-  if (a.check_flag && !(cen[3] >= 0.0f)) { o[0] = o[1] = o[2] = 0.0f; return; }
-  const double* ws = reinterpret_cast<const double*>(a.workspace);
-  SaState r{0.0, 0.0, 0.0, 0.0, 0.0};
-  for (int sp = 0; sp < splits; ++sp) {
-    const double* p = ws + (((int64_t)cube * splits + sp) * a.C + c) * kSaState;
-    SaState t{p[0], p[1], p[2], p[3], p[4]};
-    r = sa_merge(r, t);
+  if (a.check_flag && !(cen[3] >= 0.0f)) {
+    if (lane < 3) o[lane] = 0.0f;
+    return;
   }
-  o[0] = (float)((double)cen[0] + r.wx / r.s);
-  o[1] = (float)((double)cen[1] + r.wy / r.s);
-  o[2] = (float)((double)cen[2] + r.wz / r.s);
+  const double* ws = reinterpret_cast<const double*>(a.workspace);
+  double M = -INFINITY;
+  for (int sp = lane; sp < splits; sp += 32) {
+    const double* p = ws + (((int64_t)cube * splits + sp) * a.C + c) * kSaState;
+    if (p[1] > 0.0) M = fmax(M, p[0]);
+  }
+  for (int off = 16; off > 0; off >>= 1) M = fmax(M, __shfl_xor_sync(0xffffffffu, M, off));
+  double r[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int sp = lane; sp < splits; sp += 32) {
+    const double* p = ws + (((int64_t)cube * splits + sp) * a.C + c) * kSaState;
+    if (p[1] > 0.0) {
+      const double f = exp(p[0] - M);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) r[k] += p[1 + k] * f;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    for (int off = 16; off > 0; off >>= 1) r[k] += __shfl_xor_sync(0xffffffffu, r[k], off);
+  if (lane == 0) {
+    o[0] = (float)((double)cen[0] + r[1] / r[0]);
+    o[1] = (float)((double)cen[1] + r[2] / r[0]);
+    o[2] = (float)((double)cen[2] + r[3] / r[0]);
+  }
 }
 
 static int sa_splits(const sp3d_softargmax_args* a) {
@@ -307,6 +360,6 @@ extern "C" int sp3d_softargmax3d_fwd(const sp3d_softargmax_args* a, void* stream
   int rc = check_launch();
   if (rc != SP3D_OK) return rc;
   const int total = a->n_cubes * a->C;
-  softargmax_merge_kernel<<<(total + 127) / 128, 128, 0, st>>>(*a, splits);
+  softargmax_merge_kernel<<<(total + 3) / 4, 128, 0, st>>>(*a, splits);
   return check_launch();
 }
