@@ -190,9 +190,34 @@ def run_ours(args, rank, world, local_rank):
     def step_resident():
         return model(views1=dev_images, meta1=meta, inference=True)[0]
 
+    # end-to-end step through the public module call: every step's images come from pinned host memory and the
+    # predictions go back to the host.  The copy of step i+1's images runs on a side stream while step i computes
+    # (two device buffers); it is still one full H2D per step inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [[torch.empty_like(im, device=dev) for im in host_images] for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    state = {"i": 0, "primed": False}
+
+    def upload(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])          # the step that read this slot has finished
+            for d, h in zip(slots[slot], host_images):
+                d.copy_(h, non_blocking=True)
+            ready[slot].record(copy_stream)
+
     def step_e2e():
-        views = [im.to(dev, non_blocking=True) for im in host_images]
-        pred = model(views1=views, meta1=meta, inference=True)[0]
+        cur = state["i"] & 1
+        if not state["primed"]:
+            consumed[0].record()
+            consumed[1].record()
+            upload(cur)
+            state["primed"] = True
+        upload(cur ^ 1)                                     # next step's images, overlapping this step's kernels
+        torch.cuda.current_stream().wait_event(ready[cur])
+        pred = model(views1=slots[cur], meta1=meta, inference=True)[0]
+        consumed[cur].record()
+        state["i"] += 1
         return pred.cpu()
 
     def timed(fn, steps, profile=False):

@@ -129,14 +129,54 @@ def test_output_pitch_one_and_padding_lanes_zero():
 
 # ---------------------------------------------------------------------------------------------- tcgen05 packing
 def emulate_any_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksize, stride, tap_off0,
-                       tap_step, ostride, ooffset, relu, algo=0, cin_real=None, cout_pitch_w=None):
-    """Dispatch on the packing: the tensor-core launch carries [n_tiles, n_chunks, taps, N, chunk] bf16 weights."""
+                       tap_step, ostride, ooffset, relu, algo=0, cin_real=None, cout_pitch_w=None, fused_phases=False,
+                       zfold=0):
+    """Dispatch on the packing: the tensor-core launch carries [n_tiles, n_chunks, taps, N, chunk] bf16 weights;
+    `fused_phases` and `zfold` follow the sp3d_conv_args field descriptions in include/sp3d.h."""
+    res = None if residual is None else residual.float()
     if algo == 1:
         nt, nc, taps, n, chunk = weight.shape
         weight = weight.float().permute(2, 1, 4, 0, 3).reshape(taps, nc * chunk, nt * n)
         assert cout_pitch_w == n and cin == nc * chunk
-    emulate_conv_launch(x.float(), weight, scale, shift, None if residual is None else residual.float(), out, cin, cout,
-                        out_grid, ksize, stride, tap_off0, tap_step, ostride, ooffset, relu)
+    if fused_phases:
+        # ksize (1,1,1), ostride (2,2,2): GEMM rows (px, py, pz, co); one 1x1 launch per phase is the same thing
+        assert list(ksize) == [1, 1, 1] and list(ostride) == [2, 2, 2] and weight.shape[2] == 8 * cout
+        for ph in range(8):
+            off = [(ph >> 2) & 1, (ph >> 1) & 1, ph & 1]
+            emulate_conv_launch(x.float(), weight[:, :, ph * cout:(ph + 1) * cout], scale, shift, res, out, cin, cout,
+                                out_grid, ksize, stride, tap_off0, tap_step, ostride, off, relu)
+        return
+    if zfold and zfold > 1:
+        # per (kd, kh): k + F - 1 windows e of rows (ro, co) holding tap kw = e - ro, zero rows elsewhere
+        F_, k = zfold, ksize[2]
+        pitch = out.shape[-1]
+        assert cout_pitch_w == F_ * pitch and weight.shape[2] == F_ * pitch
+        w = weight.reshape(ksize[0], ksize[1], k + F_ - 1, cin, F_, pitch)
+        std = torch.zeros(ksize[0], ksize[1], k, cin, pitch)
+        for e in range(k + F_ - 1):
+            for ro in range(F_):
+                kw = e - ro
+                if 0 <= kw < k:
+                    if ro == 0 or e - ro + 0 == kw:
+                        if ro > 0:
+                            assert torch.equal(std[:, :, kw], w[:, :, e, :, ro])    # every output position sees the same tap
+                        std[:, :, kw] = w[:, :, e, :, ro]
+                else:
+                    assert not w[:, :, e, :, ro].any()
+        weight = std.reshape(-1, cin, pitch)
+    emulate_conv_launch(x.float(), weight, scale, shift, res, out, cin, cout, out_grid, ksize, stride, tap_off0,
+                        tap_step, ostride, ooffset, relu)
+
+
+def emulate_space_to_depth(x, channels, strides, n, h, w, dst_pitch):
+    """include/sp3d.h, sp3d_s2d_args: dst[n, y', x', (py*2+px)*C + c] = src[n, c, 2y'+py, 2x'+px]."""
+    src = torch.as_strided(x, (n, channels, h, w), strides).float()
+    out = torch.zeros(n, 1, h // 2, w // 2, dst_pitch)
+    for py in range(2):
+        for px in range(2):
+            q = py * 2 + px
+            out[:, 0, :, :, q * channels:(q + 1) * channels] = src[:, :, py::2, px::2].permute(0, 2, 3, 1)
+    return out.to(torch.bfloat16)
 
 
 def cl16(x):   # bf16 channel-last, pitch rounded to 16
@@ -152,7 +192,25 @@ def bf(t):
     return t.to(torch.bfloat16).float()
 
 
-@pytest.mark.parametrize("case", ["1x1", "1x1s2", "3x3", "deconv", "3d_k3", "3d_convT"])
+@pytest.mark.parametrize("k,p,cin,cout,hw", [(3, 1, 64, 64, (8, 6)), (7, 3, 3, 64, (12, 10))])
+def test_space_to_depth_stride2_lowering(monkeypatch, k, p, cin, cout, hw):
+    """ops.S2DConv: a stride-2 convolution as a stride-1 one over the 2x2 space-to-depth tensor (weight re-indexing,
+    asymmetric tap origin, channel order)."""
+    monkeypatch.setattr(ops, "conv_launch", emulate_any_launch)
+    monkeypatch.setattr(ops, "space_to_depth", emulate_space_to_depth)
+    torch.manual_seed(11)
+    conv, bn = nn.Conv2d(cin, cout, k, 2, p, bias=False), rand_bn(nn.BatchNorm2d(cout))
+    conv.weight.data = bf(conv.weight.data)
+    x = bf(torch.randn(2, cin, *hw))
+    want = F.relu(bn(conv(x)))
+    sc = ops.S2DConv(conv.weight, bn, p, relu=1)
+    y = sc(x, x.stride(), 2, hw[0], hw[1])
+    got = y[:, 0, :, :, :cout].permute(0, 3, 1, 2).float()
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= 1e-2 * float(want.abs().max())    # bf16 output
+
+
+@pytest.mark.parametrize("case", ["1x1", "1x1s2", "3x3", "deconv", "3d_k3", "3d_convT", "3d_stem_zfold"])
 def test_tensorcore_lowering(monkeypatch, case):
     monkeypatch.setattr(ops, "conv_launch", emulate_any_launch)
     torch.manual_seed(7)

@@ -19,7 +19,7 @@ from selfpose3d_b200.utils import cameras, transforms
 
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "sp3d.h")).read()
-    declared = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(sp3d_[a-z0-9_]+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^(?:int|int64_t|void|const char\*)\s+(sp3d_[a-z0-9_]+)\s*\(", header, flags=re.M))
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     lib = _lib.load()
     for name in declared:
