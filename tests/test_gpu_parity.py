@@ -143,6 +143,34 @@ def test_unproject_throughput_form_vs_oracle(cube):
         assert np.median(diff) < 1.5e-3
 
 
+def test_unproject_full_size_throughput_vs_float32_form():
+    """BASELINE size (64^3 x 15 channels, 96x72 maps, 5 views): the throughput form against the oracle-validated
+    float32 form on the same inputs, plus size-independent properties -- linearity in the heat-maps (no clamp active
+    for maps in [0, 0.5]) and values inside [0, 1]."""
+    cfg = default_config()
+    cfg.NETWORK.IMAGE_SIZE, cfg.NETWORK.HEATMAP_SIZE = [288, 384], [72, 96]
+    B, C = 2, 15
+    meta = synthetic.make_meta(synthetic.ring_cameras(5, seed=0), B, (288, 384))
+    g = torch.Generator().manual_seed(5)
+    h1 = [torch.rand(B, C, 96, 72, generator=g).mul_(0.5).to(DEV) for _ in range(5)]
+    h2 = [torch.rand(B, C, 96, 72, generator=g).mul_(0.5).to(DEV) for _ in range(5)]
+    cams = ops.pack_cameras(meta, cfg.NETWORK.IMAGE_SIZE).to(DEV)
+    cen = torch.tensor([[300.0, -900.0, 900.0, 0.0, 1.0], [-1500.0, 400.0, 1000.0, 1.0, 1.0]], device=DEV)
+    layer = project_layer.ProjectLayer(cfg)
+
+    def run(hms, dtype, pitch):
+        return layer.project_cl(hms, cams, cen, True, [2000.0] * 3, [64] * 3, dtype=dtype, c_pitch=pitch)[0][..., :C].float()
+
+    exact = run(h1, torch.float32, 16)
+    fast = run(h1, torch.bfloat16, 16)
+    diff = (fast - exact).abs()
+    assert float((diff > 6e-3).float().mean()) < 2e-3 and float(diff.median()) < 1.5e-3
+    assert float(fast.min()) >= 0.0 and float(fast.max()) <= 1.0
+    both = run([a + b for a, b in zip(h1, h2)], torch.bfloat16, 16)
+    lin = (both - (fast + run(h2, torch.bfloat16, 16))).abs()
+    assert float((lin > 1.2e-2).float().mean()) < 2e-3       # three bf16 roundings + border-decision voxels
+
+
 def test_unproject_view_sharded_partial_sums_equal_full():
     """Multi-GPU exchange: sum of per-view-shard partial numerators/counts + finalize == full."""
     g_cfg = default_config()
