@@ -5,8 +5,11 @@
 // instead of bit-faithful float32 operation order:
 //   * heat-maps are read as fp16, channel-last, 16 channels per pixel (32 bytes = one sector, two 16-byte loads
 //     per tap); sp3d_heatmaps_to_f16 produces that layout from the float32 maps in one pass;
-//   * a warp covers a compact 2 x 4 x 4 block of voxels, so the four taps of its 32 lanes fall into a handful of
-//     heat-map pixels: a tap load is 1-3 L1 wavefronts instead of the ~12 of a 32-long z run;
+//   * a lane owns a run of 4 consecutive z voxels of one (x, y) column and keeps the 2 x 2 x 16-channel tap cell of
+//     the current view in registers: consecutive voxels are ~0.4 heat-map pixels apart, so the cell is re-loaded
+//     about 1.8 times per run instead of 4; the 32 lanes of a warp are a compact 4 x 8 block of columns, so a tap
+//     load touches a handful of 128-byte lines; finished runs are transposed through shared memory so that global
+//     stores are full lines;
 //   * per (cube, view) the camera is pre-composed once per CTA in shared memory: o = R (centre - T), and the
 //     pixel -> heat-map-coordinate chain (input affine, flip, heat-map scaling, grid_sample un-normalisation)
 //     collapses into one 2 x 3 affine; the projection is FMA-contracted and divides by multiplying with
@@ -18,6 +21,7 @@
 // than the float32 form (tests count them; they are < 1e-4 of the voxels).
 #include "sp3d_common.cuh"
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace sp3d {
 
@@ -43,8 +47,46 @@ struct FastParams {
   int64_t out_stride_cube;
 };
 
+// 1/x on the special-function unit (1 ulp): one MUFU instead of the IEEE reciprocal's call + slow path
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint4 ldg_u4(const unsigned char* base, uint32_t byte_off) {
+  return __ldg(reinterpret_cast<const uint4*>(base + byte_off));
+}
 __device__ __forceinline__ uint32_t h2_as_u32(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
 __device__ __forceinline__ __half2 u32_as_h2(uint32_t v) { return *reinterpret_cast<__half2*>(&v); }
+
+// per-(cube, view) record: R, o = R (centre - T) (+1e-5 on z), f, c, k, p, and the 2 x 3 affine from clamped pixels
+// of the original image to heat-map coordinates (input affine, flip, heat-map scaling, grid_sample un-normalisation)
+__device__ __forceinline__ void compose_view(const FastParams& a, int sample, int v, const float* s_center, float* s) {
+  const float* cam = a.cams + ((int64_t)sample * a.V + v) * SP3D_CAM_FLOATS;
+  const float dx = s_center[0] - cam[9], dy = s_center[1] - cam[10], dz = s_center[2] - cam[11];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    s[3 * r] = cam[3 * r];
+    s[3 * r + 1] = cam[3 * r + 1];
+    s[3 * r + 2] = cam[3 * r + 2];
+    s[9 + r] = cam[3 * r] * dx + cam[3 * r + 1] * dy + cam[3 * r + 2] * dz + (r == 2 ? 1e-5f : 0.0f);
+  }
+#pragma unroll
+  for (int i = 12; i < 21; ++i) s[i] = cam[i];
+  // network-input pixel q -> heat-map coordinate: ((q * cfg / img) / (cfg - 1)) * (extent - 1), x flipped first
+  const float kx = a.hm_cfg_w / a.img_w / (a.hm_cfg_w - 1.0f) * (float)(a.w - 1);
+  const float ky = a.hm_cfg_h / a.img_h / (a.hm_cfg_h - 1.0f) * (float)(a.h - 1);
+  const bool flip = cam[29] != 0.0f;
+  const float sx = flip ? -kx : kx;
+  s[21] = sx * cam[21];
+  s[22] = sx * cam[22];
+  s[23] = sx * cam[23] + (flip ? a.img_w * kx : 0.0f);
+  s[24] = ky * cam[24];
+  s[25] = ky * cam[25];
+  s[26] = ky * cam[26];
+  s[27] = cam[27];
+  s[28] = cam[28];
+}
 
 __global__ void __launch_bounds__(kFastThreads) unproject_fast_kernel(const FastParams a) {
   __shared__ __align__(16) float s_view[SP3D_MAX_VIEWS][kViewFloats];
@@ -56,33 +98,7 @@ __global__ void __launch_bounds__(kFastThreads) unproject_fast_kernel(const Fast
   if (tid < 4) s_center[tid] = (tid < 3 || a.center_stride > 3) ? a.centers[(int64_t)cube * a.center_stride + tid] : 0.0f;
   for (int i = tid; i < a.Z; i += kFastThreads) s_linz[i] = a.lin_z[i];
   __syncthreads();
-  if (tid < a.V) {
-    const float* cam = a.cams + ((int64_t)sample * a.V + tid) * SP3D_CAM_FLOATS;
-    float* s = s_view[tid];
-    const float dx = s_center[0] - cam[9], dy = s_center[1] - cam[10], dz = s_center[2] - cam[11];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      s[3 * r] = cam[3 * r];
-      s[3 * r + 1] = cam[3 * r + 1];
-      s[3 * r + 2] = cam[3 * r + 2];
-      s[9 + r] = cam[3 * r] * dx + cam[3 * r + 1] * dy + cam[3 * r + 2] * dz + (r == 2 ? 1e-5f : 0.0f);
-    }
-#pragma unroll
-    for (int i = 12; i < 21; ++i) s[i] = cam[i];
-    // network-input pixel q -> heat-map coordinate: ((q * cfg / img) / (cfg - 1)) * (extent - 1), x flipped first
-    const float kx = a.hm_cfg_w / a.img_w / (a.hm_cfg_w - 1.0f) * (float)(a.w - 1);
-    const float ky = a.hm_cfg_h / a.img_h / (a.hm_cfg_h - 1.0f) * (float)(a.h - 1);
-    const bool flip = cam[29] != 0.0f;
-    const float sx = flip ? -kx : kx;
-    s[21] = sx * cam[21];
-    s[22] = sx * cam[22];
-    s[23] = sx * cam[23] + (flip ? a.img_w * kx : 0.0f);
-    s[24] = ky * cam[24];
-    s[25] = ky * cam[25];
-    s[26] = ky * cam[26];
-    s[27] = cam[27];
-    s[28] = cam[28];
-  }
+  if (tid < a.V) compose_view(a, sample, tid, s_center, s_view[tid]);
   __syncthreads();
 
   // thread -> voxel inside the CTA tile: warp = 2 x 4 x 4 block, 8 warps = 2 (x) x 2 (y) x 2 (z)
@@ -125,7 +141,7 @@ __global__ void __launch_bounds__(kFastThreads) unproject_fast_kernel(const Fast
       const float xc = fmaf(s[0], gx, fmaf(s[1], gy, fmaf(s[2], gz, s[9])));
       const float yc = fmaf(s[3], gx, fmaf(s[4], gy, fmaf(s[5], gz, s[10])));
       const float zc = fmaf(s[6], gx, fmaf(s[7], gy, fmaf(s[8], gz, s[11])));
-      const float inv = __frcp_rn(zc);
+      const float inv = rcp_approx(zc);
       const float y0 = xc * inv, y1 = yc * inv;
       const float r2 = fminf(fmaf(y0, y0, y1 * y1), 1e10f);
       const float radial = fmaf(r2, fmaf(r2, fmaf(r2, s[18], s[17]), s[16]), 1.0f);
@@ -188,6 +204,152 @@ __global__ void __launch_bounds__(kFastThreads) unproject_fast_kernel(const Fast
   }
 }
 
+
+// z-run form: CTA = 4 x 8 columns x the whole z extent; warp w takes z in [w * RZ, (w + 1) * RZ) in runs of 4
+constexpr int kRun = 4;
+constexpr int kColsX = 4, kColsY = 8;
+constexpr int kRowBytes = kRun * 32 + 16;      // one lane's finished run (4 voxels x 32 B) + padding against bank conflicts
+
+__global__ void __launch_bounds__(kFastThreads, 2) unproject_zrun_kernel(const FastParams a) {
+  __shared__ __align__(16) float s_view[SP3D_MAX_VIEWS][kViewFloats];
+  __shared__ float s_linz[256];
+  __shared__ float s_center[4];
+  __shared__ __align__(16) unsigned char s_out[kFastThreads / 32][32 * kRowBytes];
+  const int cube = blockIdx.y;
+  const int sample = a.cube_sample ? a.cube_sample[cube] : cube / a.cubes_per_sample;
+  const int tid = threadIdx.x;
+  if (tid < 4) s_center[tid] = (tid < 3 || a.center_stride > 3) ? a.centers[(int64_t)cube * a.center_stride + tid] : 0.0f;
+  for (int i = tid; i < a.Z; i += kFastThreads) s_linz[i] = a.lin_z[i];
+  __syncthreads();
+  if (tid < a.V) compose_view(a, sample, tid, s_center, s_view[tid]);
+  __syncthreads();
+
+  const int lane = tid & 31, warp = tid >> 5;
+  const int tiles_y = (a.Y + kColsY - 1) / kColsY;
+  const int tx0 = (blockIdx.x / tiles_y) * kColsX, ty0 = (blockIdx.x % tiles_y) * kColsY;
+  const int ix = tx0 + (lane >> 3), iy = ty0 + (lane & 7);
+  const bool col_ok = ix < a.X && iy < a.Y;
+  const bool skip = a.check_flag && !(s_center[3] >= 0.0f);
+  const float gx = col_ok ? a.lin_x[ix] : 0.0f, gy = col_ok ? a.lin_y[iy] : 0.0f;
+  const float wmax = (float)(a.w + 1), hmax = (float)(a.h + 1);
+  const int64_t hm_sample = (int64_t)sample * a.h * a.w * 16;
+  const int RZ = (a.Z + 7) / 8;
+  unsigned char* my_out = s_out[warp];
+  __nv_bfloat16* cube_out = a.cubes + (int64_t)cube * a.out_stride_cube;
+
+  for (int z0 = warp * RZ; z0 < min(a.Z, (warp + 1) * RZ); z0 += kRun) {
+    __half2 acc[kRun][8];
+    float den[kRun];
+#pragma unroll
+    for (int j = 0; j < kRun; ++j) {
+      den[j] = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[j][c] = __float2half2_rn(0.0f);
+    }
+    if (col_ok && !skip) {
+      for (int v = 0; v < a.V; ++v) {
+        float s[kViewFloats];
+#pragma unroll
+        for (int i = 0; i < kViewFloats / 4; ++i) {
+          const float4 t = reinterpret_cast<const float4*>(s_view[v])[i];
+          s[4 * i] = t.x; s[4 * i + 1] = t.y; s[4 * i + 2] = t.z; s[4 * i + 3] = t.w;
+        }
+        // camera-frame coordinates are affine in z along the run
+        const float bx = fmaf(s[0], gx, fmaf(s[1], gy, s[9]));
+        const float by = fmaf(s[3], gx, fmaf(s[4], gy, s[10]));
+        const float bz = fmaf(s[6], gx, fmaf(s[7], gy, s[11]));
+        const unsigned char* hm = reinterpret_cast<const unsigned char*>(a.heatmaps[v] + hm_sample);
+        int key = 0x7fffffff;                    // (y0, x0) of the cell held in t00..t11
+        uint4 c00a, c00b, c01a, c01b, c10a, c10b, c11a, c11b;
+        c00a = c00b = c01a = c01b = c10a = c10b = c11a = c11b = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < kRun; ++j) {
+          if (z0 + j >= a.Z) continue;
+          const float gz = s_linz[z0 + j];
+          const float xc = fmaf(s[2], gz, bx), yc = fmaf(s[5], gz, by), zc = fmaf(s[8], gz, bz);
+          const float inv = rcp_approx(zc);
+          const float y0 = xc * inv, y1 = yc * inv;
+          const float r2 = fminf(fmaf(y0, y0, y1 * y1), 1e10f);
+          const float radial = fmaf(r2, fmaf(r2, fmaf(r2, s[18], s[17]), s[16]), 1.0f);
+          const float tan = fmaf(s[19], y1, s[20] * y0);
+          const float corr = fmaf(2.0f, tan, radial);
+          const float u = fmaf(y0, corr, s[20] * r2);
+          const float vv = fmaf(y1, corr, s[19] * r2);
+          const float px = fmaf(s[12], u, s[14]);
+          const float py = fmaf(s[13], vv, s[15]);
+          if (!(px >= 0.0f && py >= 0.0f && px < s[27] && py < s[28])) continue;   // outside the image
+          den[j] += 1.0f;
+          float fx = fmaf(s[21], px, fmaf(s[22], py, s[23]));
+          float fy = fmaf(s[24], px, fmaf(s[25], py, s[26]));
+          fx = fminf(fmaxf(fx, -2.0f), wmax);
+          fy = fminf(fmaxf(fy, -2.0f), hmax);
+          const float x0f = floorf(fx), y0f = floorf(fy);
+          const int x0 = (int)x0f, y0i = (int)y0f;
+          float wx1 = fx - x0f, wy1 = fy - y0f;
+          float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
+          wx0 = ((unsigned)x0 < (unsigned)a.w) ? wx0 : 0.0f;
+          wx1 = ((unsigned)(x0 + 1) < (unsigned)a.w) ? wx1 : 0.0f;
+          wy0 = ((unsigned)y0i < (unsigned)a.h) ? wy0 : 0.0f;
+          wy1 = ((unsigned)(y0i + 1) < (unsigned)a.h) ? wy1 : 0.0f;
+          const int k = (y0i + 4) * 65536 + (x0 + 4);
+          if (k != key) {
+            key = k;
+            const int xa = min(max(x0, 0), a.w - 1), xb = min(max(x0 + 1, 0), a.w - 1);
+            const int ya = min(max(y0i, 0), a.h - 1), yb = min(max(y0i + 1, 0), a.h - 1);
+            const uint32_t ra = (uint32_t)(ya * a.w) * 32u, rb = (uint32_t)(yb * a.w) * 32u;   // byte offsets: 32 B per pixel
+            const uint32_t o00 = ra + xa * 32u, o01 = ra + xb * 32u, o10 = rb + xa * 32u, o11 = rb + xb * 32u;
+            c00a = ldg_u4(hm, o00); c00b = ldg_u4(hm, o00 + 16); c01a = ldg_u4(hm, o01); c01b = ldg_u4(hm, o01 + 16);
+            c10a = ldg_u4(hm, o10); c10b = ldg_u4(hm, o10 + 16); c11a = ldg_u4(hm, o11); c11b = ldg_u4(hm, o11 + 16);
+          }
+          const __half2 w00 = __float2half2_rn(wx0 * wy0), w01 = __float2half2_rn(wx1 * wy0);
+          const __half2 w10 = __float2half2_rn(wx0 * wy1), w11 = __float2half2_rn(wx1 * wy1);
+          const uint32_t t00[8] = {c00a.x, c00a.y, c00a.z, c00a.w, c00b.x, c00b.y, c00b.z, c00b.w};
+          const uint32_t t01[8] = {c01a.x, c01a.y, c01a.z, c01a.w, c01b.x, c01b.y, c01b.z, c01b.w};
+          const uint32_t t10[8] = {c10a.x, c10a.y, c10a.z, c10a.w, c10b.x, c10b.y, c10b.z, c10b.w};
+          const uint32_t t11[8] = {c11a.x, c11a.y, c11a.z, c11a.w, c11b.x, c11b.y, c11b.z, c11b.w};
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            __half2 r = __hfma2(u32_as_h2(t00[c]), w00, acc[j][c]);
+            r = __hfma2(u32_as_h2(t01[c]), w01, r);
+            r = __hfma2(u32_as_h2(t10[c]), w10, r);
+            acc[j][c] = __hfma2(u32_as_h2(t11[c]), w11, r);
+          }
+        }
+      }
+    }
+    // finished run -> this lane's padded row in shared memory
+#pragma unroll
+    for (int j = 0; j < kRun; ++j) {
+      const float inv_den = 1.0f / (den[j] + 1e-6f);
+      uint32_t o[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float2 f = __half22float2(acc[j][c]);
+        const float r0 = fminf(fmaxf(f.x * inv_den, 0.0f), 1.0f);
+        const float r1 = fminf(fmaxf(f.y * inv_den, 0.0f), 1.0f);
+        const __nv_bfloat162 b = __floats2bfloat162_rn(r0, (2 * c + 1 < a.C) ? r1 : 0.0f);
+        o[c] = *reinterpret_cast<const uint32_t*>(&b);
+      }
+      uint4* row = reinterpret_cast<uint4*>(my_out + lane * kRowBytes + j * 32);
+      row[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      row[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+    __syncwarp();
+    // transposed write-out: 8 lanes cover one column's 128-byte run, 4 columns per store instruction
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int idx = r * 32 + lane;
+      const int col = idx >> 3, piece = idx & 7;          // column of the 4 x 8 tile, 16-byte piece of its run
+      const int cx = tx0 + (col >> 3), cy = ty0 + (col & 7), cz = z0 + (piece >> 1);
+      if (cx < a.X && cy < a.Y && cz < a.Z) {
+        const uint4 val = *reinterpret_cast<const uint4*>(my_out + col * kRowBytes + piece * 16);
+        *reinterpret_cast<uint4*>(cube_out + (((int64_t)cx * a.Y + cy) * a.Z + z0) * 16 + piece * 8) = val;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // float32 heat-maps [B, C, h, w] (any strides) of V views -> fp16 channel-last [V][B][h][w][16], channels >= C zero
 __global__ void heatmaps_to_f16_kernel(const sp3d_heatmaps_f16_args a) {
   const int64_t per_view = (int64_t)a.B * a.h * a.w;
@@ -237,8 +399,14 @@ int unproject_fast(const sp3d_unproject_args* a, cudaStream_t st) {
   p.img_w = a->img_w; p.img_h = a->img_h; p.hm_cfg_w = a->hm_cfg_w; p.hm_cfg_h = a->hm_cfg_h;
   p.cubes = reinterpret_cast<__nv_bfloat16*>(a->cubes);
   p.out_stride_cube = a->out_stride_cube;
-  dim3 grid(ceil_div(a->X, kTileX) * ceil_div(a->Y, kTileY), a->n_cubes);
-  unproject_fast_kernel<<<grid, kFastThreads, 0, st>>>(p);
+  static const bool use_block_form = getenv("SP3D_UNPROJECT_BLOCK_FORM") != nullptr;   // the earlier 2x4x4-block form
+  if (use_block_form) {
+    dim3 grid(ceil_div(a->X, kTileX) * ceil_div(a->Y, kTileY), a->n_cubes);
+    unproject_fast_kernel<<<grid, kFastThreads, 0, st>>>(p);
+  } else {
+    dim3 grid(ceil_div(a->X, kColsX) * ceil_div(a->Y, kColsY), a->n_cubes);
+    unproject_zrun_kernel<<<grid, kFastThreads, 0, st>>>(p);
+  }
   return check_launch();
 }
 
