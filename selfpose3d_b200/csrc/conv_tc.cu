@@ -778,6 +778,9 @@ int conv_tc(const sp3d_conv_args* a, cudaStream_t st) {
   SP3D_TC_CASE(7, 7, 32, 16, 2, 49, 2, 2, 2, 128, 2)
   // 7^3 stem, z-folded by 2: rows of 2 positions x 16 channels, N = 2 x 16, 8 windows per (dx, dy); one halo buffer
   SP3D_TC_CASE_F(7, 7, 64, 32, 4, 8, 3, 1, 2, 128, 1, 2)
+  // 3^3 16->32 and 32->32, z-folded by 2 (N = 2 x 32, 4 windows per (dx, dy))
+  SP3D_TC_CASE_F(3, 3, 64, 64, 4, 4, 3, 2, 2, 128, 1, 2)
+  SP3D_TC_CASE_F(3, 3, 128, 64, 4, 4, 2, 1, 2, 128, 1, 2)
   SP3D_TC_CASE(3, 3, 32, 32, 4, 27, 2, 2, 3, 128, 2)
   SP3D_TC_CASE(3, 3, 64, 32, 4, 9, 2, 2, 2, 128, 2)
   SP3D_TC_CASE(3, 3, 64, 64, 4, 3, 3, 2, 2, 64, 2)

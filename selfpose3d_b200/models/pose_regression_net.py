@@ -54,12 +54,16 @@ class PoseRegressionNet(nn.Module):
         self.v2v_net = V2VNet(cfg.NETWORK.NUM_JOINTS, cfg.NETWORK.NUM_JOINTS)
         self.soft_argmax_layer = SoftArgmaxLayer(cfg)
 
-    def regress(self, all_heatmaps, cams, centers, cube_sample, chunk=16):
+    def regress(self, all_heatmaps, cams, centers, cube_sample, chunk=None):
         """Joints of ``n`` person cubes: ``centers [n,>=3]`` (all valid), ``cube_sample [n]`` int32
         sample index of each cube -> ``[n, J, 3]`` world mm.  Cubes are processed ``chunk`` at a
         time to bound activation memory (a 64^3 cube needs ~0.4 GB of float32 activations)."""
         n = int(centers.shape[0])
         J = self.num_joints
+        if chunk is None:
+            import os
+            # bf16 activations of one 64^3 cube through V2VNet peak at ~0.2 GB (float32: ~0.4 GB)
+            chunk = int(os.environ.get("SP3D_CUBE_CHUNK", "80" if ops.volume_dtype() == torch.bfloat16 else "16"))
         out = torch.empty(n, J, 3, device=centers.device, dtype=torch.float32)
         X, Y, Z = [int(s) for s in self.cube_size]
         bf16 = ops.volume_dtype() == torch.bfloat16

@@ -513,23 +513,31 @@ class PackedConv:
     ZFOLD = 2
 
     def _tc_zfold_ok(self, w_extent, out_pitch):
-        """The 7^3 stem (cin <= 16 -> 16 channels) runs z-folded: 2 output positions per GEMM row (N = 32)."""
-        return (self.nd == 3 and not self.transposed and self.k == [7, 7, 7] and self.stride == [1, 1, 1]
-                and self.padding == [3, 3, 3] and self.cin <= 16 and self.cout == 16 and out_pitch == 16
-                and w_extent % self.ZFOLD == 0)
+        """Layers whose channel tile is narrow (N = 16 / 32 leaves the tensor core waiting on its A operand) run
+        z-folded: 2 output positions per GEMM row.  Covered: the 7^3 stem (cin <= 16 -> 16, cout 16) and the 3^3
+        convolutions with cin in {16, 32} and cout 32."""
+        if not (self.nd == 3 and not self.transposed and self.stride == [1, 1, 1] and w_extent % self.ZFOLD == 0):
+            return False
+        if self.k == [7, 7, 7] and self.padding == [3, 3, 3]:
+            return self.cin <= 16 and self.cout == 16 and out_pitch == 16
+        if self.k == [3, 3, 3] and self.padding == [1, 1, 1]:
+            return self.cin in (16, 32) and self.cout == 32 and out_pitch == 32
+        return False
 
     def _tc_pack_zfold(self):
-        """bf16 ``[1, 1, kd*kh*(k+F-1), F*16, 16]``: per (kd, kh) the k+F-1 windows e, rows (ro, co), tap kw = e - ro."""
+        """bf16 ``[1, 1, kd*kh*(k+F-1), F*cout_p, cin_p]``: per (kd, kh) the k+F-1 windows e, rows (ro, co), tap
+        kw = e - ro (zero rows where that falls outside the kernel)."""
         if getattr(self, "_tc_zf", None) is None:
             F, k = self.ZFOLD, self.k[2]
+            cin_p, cout_p = round_up(self.cin, 16), round_up(self.cout, 16)
             w5 = self._subs[0]                                     # [Cout, Cin, kd, kh, kw]
-            full = torch.zeros(self.k[0], self.k[1], k + F - 1, F, 16, 16, device=w5.device, dtype=torch.float32)
+            full = torch.zeros(self.k[0], self.k[1], k + F - 1, F, cout_p, cin_p, device=w5.device, dtype=torch.float32)
             for e in range(k + F - 1):
                 for ro in range(F):
                     kw = e - ro
                     if 0 <= kw < k:
                         full[:, :, e, ro, :self.cout, :self.cin] = w5[:, :, :, :, kw].permute(2, 3, 0, 1)
-            self._tc_zf = full.reshape(1, 1, -1, F * 16, 16).to(torch.bfloat16).contiguous()
+            self._tc_zf = full.reshape(1, 1, -1, F * cout_p, cin_p).to(torch.bfloat16).contiguous()
         return self._tc_zf
 
     def _tc_fused_ok(self, out_pitch, out_dtype):
@@ -570,10 +578,10 @@ class PackedConv:
             outk = out.view(1, N, o[1], o[2], out_pitch)
             resk = residual.view(1, N, o[1], o[2], out_pitch) if residual is not None else None
             D, o = N, [N, o[1], o[2]]
-        if not self.transposed and pitch == 16 and self._tc_zfold_ok(W, out_pitch):
-            conv_launch(xk, self._tc_pack_zfold(), self.scale, self.shift, resk, outk, 16, self.cout, o, self.k,
+        if not self.transposed and pitch == round_up(self.cin, 16) and self._tc_zfold_ok(W, out_pitch):
+            conv_launch(xk, self._tc_pack_zfold(), self.scale, self.shift, resk, outk, pitch, self.cout, o, self.k,
                         self.stride, [-p for p in self.padding], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu,
-                        _lib.CONV_TC_BF16, cin_real=self.cin, cout_pitch_w=16 * self.ZFOLD, zfold=self.ZFOLD)
+                        _lib.CONV_TC_BF16, cin_real=self.cin, cout_pitch_w=out_pitch * self.ZFOLD, zfold=self.ZFOLD)
         elif not self.transposed:
             conv_launch(xk, packs[0], self.scale, self.shift, resk, outk, cin_tc, self.cout, o, self.k, self.stride,
                         [-p for p in self.padding], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu, _lib.CONV_TC_BF16,

@@ -94,6 +94,34 @@ def test_tc_transposed_conv_matches_float64_reference(cin, cout, with_skip, shap
     assert float((gotb - want).abs().max()) <= 6e-3 * scale
 
 
+@pytest.mark.parametrize("cin", [16, 32])
+@pytest.mark.parametrize("with_res", [True, False])
+@pytest.mark.parametrize("shape", [(6, 20, 12), (5, 17, 34)])
+def test_tc_conv3_zfold_matches_float64_reference(cin, with_res, shape):
+    """3^3 cin -> 32 layers run z-folded (N = 2 x 32) when W is even; with and without the fused residual."""
+    torch.manual_seed(cin + 3)
+    conv = nn.Conv3d(cin, 32, 3, 1, 1)
+    bn = rand_bn(nn.BatchNorm3d(32), cin)
+    with torch.no_grad():
+        conv.weight.copy_(bf16_round(conv.weight))
+    x = bf16_round(torch.randn(2, cin, *shape))
+    res = bf16_round(torch.randn(2, 32, *shape))
+    with torch.no_grad():
+        want = bn.double()(conv.double()(x.double()))
+        want = F.relu(want + res.double()) if with_res else F.relu(want)
+    conv, bn = conv.float().to(DEV), bn.float().to(DEV)
+    pc = ops.PackedConv(conv.weight, conv.bias, bn, 1, 1, relu=1)
+    assert pc._tc_zfold_ok(shape[2], 32)
+    res_cl = ops.to_channel_last(res.to(DEV), c_pitch=32, dtype=torch.float32) if with_res else None
+    y = pc(to_cl_bf16(x), residual=res_cl, out_pitch=32, out_dtype=torch.float32)
+    got = ops.to_channel_first(y, 32).cpu().double()
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) <= 2e-5 * scale, float((got - want).abs().max()) / scale
+    yb = pc(to_cl_bf16(x), residual=res_cl.to(torch.bfloat16) if with_res else None, out_pitch=32)
+    gotb = ops.to_channel_first(yb, 32, dtype=torch.float32).cpu().double()
+    assert float((gotb - want).abs().max()) <= 6e-3 * scale
+
+
 @pytest.mark.parametrize("cin", [15, 1])
 @pytest.mark.parametrize("shape", [(6, 20, 12), (5, 17, 34), (3, 9, 7)])    # even W: z-folded kernel; odd W: plain kernel
 def test_tc_stem_conv7_zfold_matches_float64_reference(cin, shape):
