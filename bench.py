@@ -37,8 +37,15 @@ HEATMAP_SIZE = [72, 96]
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-# (profiles/r01_ncu_*_summary.csv); filled in by hand when a capture is refreshed, None until then
-NCU_EVIDENCE = {}
+# (profiles/r01_ncu_*_summary.csv), keyed by the launch's layer string; refreshed by hand with the captures
+NCU_EVIDENCE = {
+    "conv algo1 k7 15->16 @80x64x64x64": {
+        "dram_bytes_per_launch": 672.02e6 + 634.73e6,   # algorithmic: 671 MB bf16 cubes in + 671 MB out
+        "source": "profiles/r01_ncu_conv_pose_v11_summary.csv (conv_tc_kernel<7,7,64,32,...,F=2>, ncu --set full)"},
+    "unproject": {
+        "dram_bytes_per_launch": 0.004e6 + 619.41e6,    # bf16 cubes written once; the 8 MB of fp16 maps stay in L2
+        "source": "profiles/r01_ncu_k1_k3_k4_v11_summary.csv (unproject_zrun_kernel, 80 cubes, ncu --set full)"},
+}
 
 
 def load_peaks():
@@ -264,26 +271,41 @@ def run_ours(args, rank, world, local_rank):
     h2d = sum(int(im.numel()) * 4 for im in host_images)
     d2h = BATCH * PROPOSALS * cfg.NETWORK.NUM_JOINTS * 5 * 4
 
-    # dominant kernel family: the convolutions (tensor roofline); the un-projection is reported beside it (HBM)
+    # roofline of the DOMINANT KERNEL: the single launch type with the largest share of the step (the 7^3 V2V stem
+    # over all person cubes), Sum algorithmic FLOPs / Sum CUDA-event time of its launches; the whole convolution
+    # family and the un-projection (HBM) are reported beside it
     conv = kernels.get("conv", {"ms": 0.0, "work": 0.0, "launches": 0})
     unp = kernels.get("unproject", {"ms": 0.0, "work": 0.0, "launches": 0})
+    layers = prof.detail_summary()
+    top_name, top = max(layers.items(), key=lambda kv: kv[1]["ms"]) if layers else ("", {"ms": 0.0, "work": 0.0, "launches": 0})
+    top_tflops = top["work"] / (top["ms"] * 1e-3) / 1e12 if top["ms"] > 0 else 0.0
     conv_tflops = conv["work"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
     unp_gbs = unp["work"] / (unp["ms"] * 1e-3) / 1e9 if unp["ms"] > 0 else 0.0
-    roofline = {"kernel": "sp3d_conv_fwd (implicit-GEMM convolution family, all launches of the step)",
-                "bound": "tensor", "achieved": conv_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": conv_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
+    ev = NCU_EVIDENCE.get(top_name, {})
+    roofline = {"kernel": "sp3d_conv_fwd / conv_tc_kernel: " + top_name, "bound": "tensor", "achieved": top_tflops,
+                "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": top_tflops / peaks["bf16_tflops_sustained"],
+                "traffic": ev.get("dram_bytes_per_launch"), "traffic_source": ev.get("source"),
                 "peak_source": peaks["source"] + " (sustained bf16: kernels timed inside a long step)",
-                "launches_per_step": conv["launches"] / prof_steps,
-                "share_of_step": conv["ms"] / ms_prof if ms_prof > 0 else None,
-                "ncu": NCU_EVIDENCE.get("conv")}
+                "launches_per_step": top["launches"] / prof_steps,
+                "avg_launch_ms": top["ms"] / max(top["launches"], 1),
+                "share_of_step": top["ms"] / ms_prof if ms_prof > 0 else None,
+                "flops_per_launch": top["work"] / max(top["launches"], 1)}
+    roofline_conv_family = {"kernel": "sp3d_conv_fwd (all convolution launches of the step)", "bound": "tensor",
+                            "achieved": conv_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                            "frac": conv_tflops / peaks["bf16_tflops_sustained"],
+                            "launches_per_step": conv["launches"] / prof_steps,
+                            "share_of_step": conv["ms"] / ms_prof if ms_prof > 0 else None}
+    ev = NCU_EVIDENCE.get("unproject", {})
     roofline_unproject = {"kernel": "sp3d_unproject_fwd (person cubes + root grid)", "bound": "hbm",
                           "achieved": unp_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                          "frac": unp_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                          "frac": unp_gbs / peaks["hbm_gbs"], "traffic": ev.get("dram_bytes_per_launch"),
+                          "traffic_source": ev.get("source"), "peak_source": peaks["source"],
                           "launches_per_step": unp["launches"] / prof_steps,
                           "share_of_step": unp["ms"] / ms_prof if ms_prof > 0 else None,
                           "note": "achieved = SURVEY 8(d) algorithmic bytes (float32 cubes written once + maps read "
-                                  "once) / time; the bf16 volume mode physically writes half of that",
-                          "ncu": NCU_EVIDENCE.get("unproject")}
+                                  "once) / time; the bf16 volume mode physically writes half of that; ncu shows the "
+                                  "kernel bound by L1 wavefronts / issue slots, not DRAM (DESIGN.md)"}
 
     cpu_frames = 5
     cpu_fps, cpu_spf = cpu_reference_frames_per_s(cpu_frames, 1, 1) if not args.no_cpu_baseline else (None, None)
@@ -299,6 +321,7 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,
+        "roofline_conv_family": roofline_conv_family,
         "roofline_unproject": roofline_unproject,
         "kernel_ms_per_step": {k: v["ms"] / prof_steps for k, v in kernels.items()},
         "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
