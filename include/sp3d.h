@@ -187,8 +187,17 @@ typedef struct {
                                the packed weight holds, per (kd, kh), k + F - 1 windows e of [F * cout_pitch][cin] rows
                                ordered (ro, co) with tap kw = e - ro (zero rows where that is outside the kernel);
                                cout_pitch_w = F * cout_pitch.  0 / 1: off */
+  const sp3d_softargmax_args* head_softargmax;
+                            /* tensor-core path only, 1x1x1 convolutions with cout <= 15 (the V2VNet head,
+                               lib/models/v2v_net.py:124 + lib/models/pose_regression_net.py:19-28 in one pass):
+                               when non-NULL the convolution output is NOT stored (out may be NULL); the soft-argmax
+                               of scale * acc + shift over each of the N volumes is accumulated on chip and written
+                               to head->out [N, cout, 3].  Uses head->centers / lin_* / beta / out and
+                               head->workspace of sp3d_conv_head_workspace() bytes; x / strides are ignored,
+                               n_cubes, C, X, Y, Z must equal N, cout, OD, OH, OW; check_flag must be 0. */
 } sp3d_conv_args;
 int sp3d_conv_fwd(const sp3d_conv_args* a, void* stream);
+int64_t sp3d_conv_head_workspace(const sp3d_conv_args* a);
 /* Debug aid (profiles/conv_stalls.py): when given a device buffer of 148 * 16 uint64, every tensor-core
  * convolution launch writes per-CTA pipeline wait cycles into it (process-global; NULL switches it off). */
 void sp3d_debug_conv_profile(void* dev_u64_buffer);

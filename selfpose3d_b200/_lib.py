@@ -89,6 +89,7 @@ class ConvArgs(C.Structure):
         ("ksize", _i3), ("stride", _i3), ("tap_off0", _i3), ("tap_step", _i3), ("ostride", _i3), ("ooffset", _i3),
         ("relu", C.c_int), ("algo", C.c_int), ("in_dtype", C.c_int), ("out_dtype", C.c_int),
         ("fused_phases", C.c_int), ("zfold", C.c_int),
+        ("head_softargmax", C.POINTER(SoftargmaxArgs)),
     ]
 
 
@@ -130,6 +131,7 @@ SYMBOLS = {
     "sp3d_softargmax3d_workspace": (C.c_int64, [C.POINTER(SoftargmaxArgs)]),
     "sp3d_softargmax3d_fwd": (C.c_int, [C.POINTER(SoftargmaxArgs), C.c_void_p]),
     "sp3d_conv_fwd": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
+    "sp3d_conv_head_workspace": (C.c_int64, [C.POINTER(ConvArgs)]),
     "sp3d_debug_conv_profile": (None, [C.c_void_p]),
     "sp3d_maxpool_fwd": (C.c_int, [C.POINTER(MaxpoolArgs), C.c_void_p]),
     "sp3d_layout_convert": (C.c_int, [C.POINTER(LayoutArgs), C.c_void_p]),

@@ -41,6 +41,13 @@ constexpr int largest_divisor_le(int n, int cap) {
   return best;
 }
 
+// 2^x on the special-function unit (2 ulp)
+__device__ __forceinline__ float ex2_sfu(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct alignas(64) TcStoreMaps {
   CUtensorMap m[4];              // [0] for a regular launch; one per (px, py) phase pair for the fused transposed form
 };
@@ -64,6 +71,16 @@ struct TcConvParams {
   void* out;
   int fused_cols;                // fused k2/s2 transposed convolution: columns per (px, py) output phase pair
                                  // (= 2 * cout: (pz, co) is contiguous in the output), else 0
+  int blocked;                   // 1: contiguous item blocks per CTA (fused soft-argmax head)
+  // fused soft-argmax head (N = 16 kernels): the output is not stored; per (CTA, epilogue group, cube) online-softmax
+  // partials [m, s, wx, wy, wz] per channel go to sa_ws (float64) and softargmax_merge_kernel finishes them
+  double* sa_ws;
+  const float* sa_lin_x;
+  const float* sa_lin_y;
+  const float* sa_lin_z;
+  const float* sa_centers;
+  int sa_center_stride, sa_C, sa_slots;
+  float sa_beta;
   int col_mod;                   // > 0: GEMM column -> channel is col % col_mod (fused phases, z-fold)
   int tma_store;                 // 1: epilogue stages rows in smem and stores (and pre-loads the residual) by TMA
   int has_res;
@@ -171,6 +188,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
   // work item -> (outer index, brick origin in output coordinates, channel tile); the channel tile is the fastest
   // index so that concurrently running CTAs share one input halo through L2
   const int n_items = p.n_bricks * p.n_tiles;
+  // round-robin over CTAs, or (fused soft-argmax head) one contiguous block of items per CTA so that a CTA meets at
+  // most a few cubes
+  const int items_per_cta = (n_items + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int wi_begin = p.blocked ? (int)blockIdx.x * items_per_cta : (int)blockIdx.x;
+  const int wi_end = p.blocked ? min(n_items, wi_begin + items_per_cta) : n_items;
+  const int wi_step = p.blocked ? 1 : (int)gridDim.x;
   auto item_coords = [&](int wi, int& n, int& x0, int& y0, int& z0, int& nt) {
     nt = wi % p.n_tiles;
     const int b = wi / p.n_tiles;
@@ -184,7 +207,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ halo producer
     uint32_t u = 0;
-    for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x) {
+    for (int wi = wi_begin; wi < wi_end; wi += wi_step) {
       int n, x0, y0, z0, nt;
       item_coords(wi, n, x0, y0, z0, nt);
       for (int c = 0; c < p.n_chunks; ++c, ++u) {
@@ -200,7 +223,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
     // ------------------------------------------------------------------ weight producer (G taps per stage)
     // packed weights: rows ordered [n_tile][chunk][tap][N]; a stage holds taps g*G .. g*G+G-1 of one chunk
     uint32_t w = 0;
-    for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x) {
+    for (int wi = wi_begin; wi < wi_end; wi += wi_step) {
       const int nt = wi % p.n_tiles;
       for (int c = 0; c < p.n_chunks; ++c) {
         for (int g = 0; g < C::kGroups; ++g, ++w) {
@@ -226,7 +249,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
     long long t_begin = 0, t_halo = 0, t_w = 0, t_acc = 0, t0 = 0;
     const bool prof = p.prof != nullptr;
     if (prof) t_begin = clock64();
-    for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x, ++it) {
+    for (int wi = wi_begin; wi < wi_end; wi += wi_step, ++it) {
       const uint32_t accbuf = it & 1;
       if (prof) t0 = clock64();
       mbar_wait(&acc_empty[accbuf], ((it >> 1) & 1) ^ 1);
@@ -309,7 +332,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
       constexpr uint32_t SWZ = C::kStageRow == 128 ? 7u : (C::kStageRow == 64 ? 3u : 1u);
       const bool has_res = p.has_res != 0;
       const bool leader = row == 0;
-      int pf_wi = blockIdx.x, pf_t = grp, pf_sc = 0;          // residual prefetch cursor (leader)
+      int pf_wi = wi_begin, pf_t = grp, pf_sc = 0;          // residual prefetch cursor (leader)
       uint32_t pf_u = 0;
       auto issue_res = [&]() {
         int n, x0, y0, z0, nt;
@@ -327,12 +350,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
           pf_sc = 0;
           if ((pf_t += EG) >= TX) {
             pf_t = grp;
-            pf_wi += gridDim.x;
+            pf_wi += wi_step;
           }
         }
       };
       if (has_res && leader)
-        for (int i = 0; i < SB - 1 && pf_wi < n_items; ++i) issue_res();
+        for (int i = 0; i < SB - 1 && pf_wi < wi_end; ++i) issue_res();
       // N <= 32: the folded-BatchNorm scale / shift stay in registers (shared-memory loads queue behind the tensor
       // core's operand reads while MMAs run); wider tiles read them as float4 from shared memory
       constexpr bool kRegSS = N <= 32;
@@ -346,7 +369,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
       }
       uint32_t u = 0;
       long long pe[5] = {0, 0, 0, 0, 0};   // tmem load, residual wait, math + smem, fence + barrier, store + ring wait
-      for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x, ++it) {
+      for (int wi = wi_begin; wi < wi_end; wi += wi_step, ++it) {
         int n, x0, y0, z0, nt;
         item_coords(wi, n, x0, y0, z0, nt);
         const uint32_t accbuf = it & 1;
@@ -468,7 +491,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
               tma_store_5d(&maps_out.m[mi], sbuf, gc, z0, y0, x0 + t, n);
               bulk_commit();
               if (has_res) {
-                if (pf_wi < n_items) {         // slot (u - 1) % SB: its store (unit u - 1) must have left smem
+                if (pf_wi < wi_end) {          // slot (u - 1) % SB: its store (unit u - 1) must have left smem
                   bulk_wait_read<1>();
                   issue_res();
                 }
@@ -489,14 +512,117 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
         for (int i = 0; i < 5; ++i) o[8 + i] = pe[i];
       }
     };
-    if (p.tma_store) {
+    if constexpr (N == 16) {
+      if (p.sa_ws != nullptr) {
+        // ---- fused soft-argmax head: logits = scale * acc + shift never leave the SM
+        // scratch carved out of this group's (unused) staging ring: coordinate tables, per-warp maxima and sums
+        static_assert(SB * C::kStageBytes >= (3 * 256 + 4 * 16 + 4 * 16 * 4) * 4, "staging ring too small for the head");
+        float (*sa_g)[256] = reinterpret_cast<float (*)[256]>(gstage);                       // [3][256]
+        float (*sa_max)[16] = reinterpret_cast<float (*)[16]>(gstage + 3 * 256 * 4);         // [4][16]
+        float (*sa_sum)[16][4] = reinterpret_cast<float (*)[16][4]>(gstage + (3 * 256 + 4 * 16) * 4);   // [4][16][4]
+        constexpr float kLog2e = 1.4426950408889634f;
+        float m[15], s[15], wx[15], wy[15], wz[15];
+        int cur_n = -1;
+        const int lane = tid & 31, wq = warp & 3;
+        auto reset = [&]() {
+#pragma unroll
+          for (int c = 0; c < 15; ++c) { m[c] = -INFINITY; s[c] = 0.f; wx[c] = 0.f; wy[c] = 0.f; wz[c] = 0.f; }
+        };
+        auto flush = [&](int n) {       // merge the group's 128 thread states of cube n and write one partial
+#pragma unroll
+          for (int c = 0; c < 15; ++c) {
+            float mm = m[c];
+            for (int off = 16; off > 0; off >>= 1) mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, off));
+            if (lane == 0) sa_max[wq][c] = mm;
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+#pragma unroll
+          for (int c = 0; c < 15; ++c) {
+            const float M = fmaxf(fmaxf(sa_max[0][c], sa_max[1][c]), fmaxf(sa_max[2][c], sa_max[3][c]));
+            const float f = s[c] > 0.0f ? ex2_sfu((m[c] - M) * kLog2e) : 0.0f;
+            float v4[4] = {s[c] * f, wx[c] * f, wy[c] * f, wz[c] * f};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              for (int off = 16; off > 0; off >>= 1) v4[i] += __shfl_xor_sync(0xffffffffu, v4[i], off);
+              if (lane == 0) sa_sum[wq][c][i] = v4[i];
+            }
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          if (row < p.sa_C) {
+            const int c = row;
+            const float M = fmaxf(fmaxf(sa_max[0][c], sa_max[1][c]), fmaxf(sa_max[2][c], sa_max[3][c]));
+            double* o = p.sa_ws + (((int64_t)n * p.sa_slots + (int)blockIdx.x * EG + grp) * p.sa_C + c) * 5;
+            o[0] = (double)M;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              o[1 + i] = (double)sa_sum[0][c][i] + (double)sa_sum[1][c][i] + (double)sa_sum[2][c][i] +
+                         (double)sa_sum[3][c][i];
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        };
+        float hsc[16], hsh[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { hsc[c] = s_scale[0][c]; hsh[c] = s_shift[0][c]; }
+        reset();
+        for (int wi = wi_begin; wi < wi_end; wi += wi_step, ++it) {
+          int n, x0, y0, z0, nt;
+          item_coords(wi, n, x0, y0, z0, nt);
+          if (n != cur_n) {
+            if (cur_n >= 0) flush(cur_n);
+            reset();
+            cur_n = n;
+            const float* cen = p.sa_centers + (int64_t)n * p.sa_center_stride;
+            const float cx = cen[0], cy = cen[1], cz = cen[2];
+            // g - centre with g = fl(lin + centre): the `grids` values of ProjectLayer.compute_grid
+            for (int i = row; i < p.X; i += 128) sa_g[0][i] = __fsub_rn(__fadd_rn(p.sa_lin_x[i], cx), cx);
+            for (int i = row; i < p.Y; i += 128) sa_g[1][i] = __fsub_rn(__fadd_rn(p.sa_lin_y[i], cy), cy);
+            for (int i = row; i < p.Z; i += 128) sa_g[2][i] = __fsub_rn(__fadd_rn(p.sa_lin_z[i], cz), cz);
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          }
+          const uint32_t accbuf = it & 1;
+          mbar_wait(&acc_full[accbuf], (it >> 1) & 1);
+          tc_fence_after();
+          const int y = y0 + ly, z = z0 + lz;
+#pragma unroll 1
+          for (int t = grp; t < TX; t += EG) {
+            const int x = x0 + t;
+            uint32_t v[16];
+            tmem_ld_x16(tmem_base + lane_base + (accbuf * TX + t) * N, v);
+            tmem_ld_wait();
+            if (x < p.X && y < p.Y && z < p.Z) {
+              const float gx = sa_g[0][x], gy = sa_g[1][y], gz = sa_g[2][z];
+#pragma unroll
+              for (int c = 0; c < 15; ++c) {
+                if (c < p.sa_C) {
+                  const float logit = __uint_as_float(v[c]) * hsc[c] + hsh[c];
+                  const float zz = __fmul_rn(p.sa_beta, logit);
+                  // branch-free online softmax: 15 independent chains keep the few epilogue warps busy
+                  const float mn = fmaxf(m[c], zz);
+                  const float sc = ex2_sfu((m[c] - mn) * kLog2e);     // 2^-inf = 0 on the first voxel
+                  const float e = ex2_sfu((zz - mn) * kLog2e);
+                  s[c] = fmaf(s[c], sc, e);
+                  wx[c] = fmaf(wx[c], sc, e * gx);
+                  wy[c] = fmaf(wy[c], sc, e * gy);
+                  wz[c] = fmaf(wz[c], sc, e * gz);
+                  m[c] = mn;
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&acc_empty[accbuf]);
+        }
+        if (cur_n >= 0) flush(cur_n);
+      }
+    }
+    if (p.tma_store && !p.sa_ws) {
       if (p.out_f32) staged(float{});
       else staged(__nv_bfloat16{});
     }
     // ---- direct form (rows whose byte pitch is not a multiple of 16, e.g. the 1-channel float32 score volume)
     // (compiled for the N = 16 kernels only: that is where a 1- or 15-channel float32 head lands)
     if constexpr (N == 16)
-    for (int wi = blockIdx.x; !p.tma_store && wi < n_items; wi += gridDim.x, ++it) {
+    for (int wi = wi_begin; !p.tma_store && !p.sa_ws && wi < wi_end; wi += wi_step, ++it) {
       int n, x0, y0, z0, nt;
       item_coords(wi, n, x0, y0, z0, nt);
       const uint32_t accbuf = it & 1;
@@ -600,6 +726,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+__global__ void softargmax_merge_kernel(const sp3d_softargmax_args a, int splits);   // csrc/softargmax.cu
+
 // Debug only (profiles/conv_stalls.py): a device buffer of 148 * kProfSlots u64 receiving per-CTA wait cycles.
 static unsigned long long* g_conv_prof = nullptr;
 void set_conv_profile(void* dev) { g_conv_prof = static_cast<unsigned long long*>(dev); }
@@ -724,6 +852,14 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
   p.out_f32 = a->out_dtype == SP3D_F32;
   p.scale = a->scale; p.shift = a->shift; p.residual = a->residual; p.out = a->out;
   p.prof = g_conv_prof;
+  const sp3d_softargmax_args* head = a->head_softargmax;
+  if (head != nullptr) {
+    if (N != 16 || F != 1 || n_tiles != 1 || a->fused_phases || head->C < 1 || head->C > 15 || head->n_cubes != a->N ||
+        head->X != a->OD || head->Y != a->OH || head->Z != a->OW || a->OD > 256 || a->OH > 256 || a->OW > 256 ||
+        head->centers == nullptr || head->out == nullptr || head->lin_x == nullptr || head->lin_y == nullptr ||
+        head->lin_z == nullptr || head->check_flag)
+      return SP3D_ERR_UNSUPPORTED;
+  }
   p.tma_store = tma_store ? 1 : 0;
   p.fused_cols = fused ? 2 * a->cout : 0;
   p.col_mod = fused ? a->cout : (F > 1 ? a->cout_pitch : 0);
@@ -740,7 +876,24 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
   if (e != cudaSuccess) { set_last_error(e); return SP3D_ERR_LAUNCH; }
   const int items = p.n_bricks * p.n_tiles;
   const int grid = items < n_sm ? items : n_sm;
+  if (head != nullptr) {
+    const int slots = grid * EG;
+    const int64_t need = (int64_t)a->N * slots * head->C * 5 * (int64_t)sizeof(double);
+    if (head->workspace == nullptr || head->workspace_bytes < need || (reinterpret_cast<uintptr_t>(head->workspace) % 8))
+      return SP3D_ERR_WORKSPACE;
+    cudaError_t me = cudaMemsetAsync(head->workspace, 0, (size_t)need, st);   // s = 0 marks "no partial from this slot"
+    if (me != cudaSuccess) { set_last_error(me); return SP3D_ERR_LAUNCH; }
+    p.blocked = 1;
+    p.sa_ws = reinterpret_cast<double*>(head->workspace);
+    p.sa_lin_x = head->lin_x; p.sa_lin_y = head->lin_y; p.sa_lin_z = head->lin_z;
+    p.sa_centers = head->centers; p.sa_center_stride = head->center_stride;
+    p.sa_C = head->C; p.sa_slots = slots; p.sa_beta = head->beta;
+  }
   kern<<<grid, C::kThreads, C::kSmemBytes, st>>>(map_in, map_w, maps_out, maps_res, p);
+  int rc = check_launch();
+  if (rc != SP3D_OK || head == nullptr) return rc;
+  const int total = head->n_cubes * head->C;
+  softargmax_merge_kernel<<<(total + 3) / 4, 128, 0, st>>>(*head, grid * EG);
   return check_launch();
 }
 

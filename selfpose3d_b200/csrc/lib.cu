@@ -35,9 +35,18 @@ extern "C" const char* sp3d_last_cuda_error(void) { return sp3d::g_last_error; }
 
 extern "C" void sp3d_debug_conv_profile(void* dev_u64_buffer) { sp3d::set_conv_profile(dev_u64_buffer); }
 
+extern "C" int64_t sp3d_conv_head_workspace(const sp3d_conv_args* a) {
+  if (a == nullptr || a->head_softargmax == nullptr || a->N < 0) return 0;
+  int dev = 0, n_sm = 0;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+  return (int64_t)a->N * (2 * n_sm) * a->head_softargmax->C * 5 * (int64_t)sizeof(double);
+}
+
 extern "C" int sp3d_conv_fwd(const sp3d_conv_args* a, void* stream) {
   using namespace sp3d;
-  if (a == nullptr || a->in == nullptr || a->weight == nullptr || a->out == nullptr || a->N < 0 || a->cin < 1 ||
+  if (a == nullptr || a->in == nullptr || a->weight == nullptr || (a->out == nullptr && a->head_softargmax == nullptr) ||
+      a->N < 0 || a->cin < 1 ||
       a->cout < 1 || a->cout_pitch < a->cout || a->cout_pitch_w < 1 || a->OD < 0 || a->OH < 0 || a->OW < 0)
     return SP3D_ERR_INVALID_ARG;
   for (int d = 0; d < 3; ++d)
@@ -47,6 +56,7 @@ extern "C" int sp3d_conv_fwd(const sp3d_conv_args* a, void* stream) {
   switch (a->algo) {
     case SP3D_CONV_SIMT_F32:
       if (a->cout_pitch_w < a->cout) return SP3D_ERR_INVALID_ARG;
+      if (a->head_softargmax != nullptr) return SP3D_ERR_UNSUPPORTED;
       return conv_simt_f32(a, st);
     case SP3D_CONV_TC_BF16:
     case SP3D_CONV_TC_TF32X3: return conv_tc(a, st);

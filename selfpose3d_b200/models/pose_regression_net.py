@@ -78,6 +78,11 @@ class PoseRegressionNet(nn.Module):
                                                      self.cube_size, cube_sample=cube_sample[s:e],
                                                      dtype=ops.volume_dtype(), c_pitch=ops.round_up(J, 16) if bf16 else None,
                                                      hms_f16=hms_f16)
+            if bf16 and J <= 15 and max(X, Y, Z) <= 256:
+                # output layer + soft-argmax in one kernel (csrc/conv_tc.cu, fused head)
+                head = ops.SoftargmaxHead(e - s, J, (X, Y, Z), centers[s:e], self.grid_size, self.soft_argmax_layer.beta)
+                out[s:e] = self.v2v_net.forward_softargmax_cl(cubes, head)
+                continue
             y = self.v2v_net.forward_cl(cubes)
             pitch = int(y.shape[-1])
             out[s:e] = ops.softargmax(y, (X * Y * Z * pitch, 1, pitch), e - s, J, (X, Y, Z), centers[s:e],

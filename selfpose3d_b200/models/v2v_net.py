@@ -220,6 +220,17 @@ class V2VNet(nn.Module):
         # the score / heat-map volume leaves the net in float32 in either mode (NMS and soft-argmax read it)
         return self._out_packed()(x, out_pitch=out_pitch, out_dtype=torch.float32)
 
+    def forward_softargmax_cl(self, x, head):
+        """bf16 volume mode: like ``forward_cl`` but the 1x1x1 output layer feeds ``head`` (``ops.SoftargmaxHead``)
+        on chip -- the heat-map volume is never written; returns ``[N, output_channels, 3]``."""
+        _no_train(self)
+        if any(int(s) % 4 for s in x.shape[1:4]):
+            raise ValueError("V2VNet needs spatial extents divisible by 4, got %s" % (tuple(x.shape[1:4]),))
+        x = self.front_layers[0].forward_cl(x)
+        x = self.front_layers[1].forward_cl(x)
+        x = self.encoder_decoder.forward_cl(x)
+        return self._out_packed()(x, head=head)
+
     def forward(self, x):
         y = self.forward_cl(_to_volume_cl(x))
         return ops.to_channel_first(y, self.output_channels)

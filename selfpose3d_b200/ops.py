@@ -344,8 +344,13 @@ def _set3(field, vals):
 
 def conv_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksize, stride, tap_off0, tap_step,
                 ostride, ooffset, relu, algo=_lib.CONV_SIMT_F32, cin_real=None, cout_pitch_w=None, fused_phases=False,
-                zfold=0):
-    """One implicit-GEMM convolution launch.  ``x`` / ``out`` are channel-last 5-D ``[N,D,H,W,pitch]``."""
+                zfold=0, head=None):
+    """One implicit-GEMM convolution launch.  ``x`` / ``out`` are channel-last 5-D ``[N,D,H,W,pitch]``.
+    ``head``: a ``SoftargmaxHead`` -- the output is consumed on chip by the fused soft-argmax (``out`` is then a
+    shape-only placeholder: a ``torch.Size``-like tuple ``(N, D, H, W, pitch)``)."""
+    if head is not None:
+        return _conv_launch_head(x, weight, scale, shift, out, cin, cout, out_grid, ksize, relu, algo, cin_real,
+                                 cout_pitch_w, head)
     a = _lib.ConvArgs()
     a.in_ = x.data_ptr()
     a.weight = weight.data_ptr()
@@ -378,6 +383,67 @@ def conv_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksi
     detail = "conv%s algo%d k%d %d->%d @%dx%dx%dx%d" % ("T8" if fused_phases else "", a.algo, a.ksize[2], cin_real or a.cin,
                                                        a.cout, a.N, a.OD, a.OH, a.OW)
     _lib.call("sp3d_conv_fwd", a, _stream(), kind="conv", work=flops, detail=detail)
+
+
+class SoftargmaxHead:
+    """Arguments of the soft-argmax fused behind a 1x1x1 tensor-core convolution (``sp3d_conv_args.head_softargmax``):
+    ``centers [n, >=3]`` float32 CUDA, cube geometry, beta.  ``out`` receives ``[n, channels, 3]``."""
+
+    def __init__(self, n_cubes, channels, cube_size, centers, grid_size, beta):
+        _require_cuda(centers)
+        dev = centers.device
+        self.out = torch.empty(n_cubes, channels, 3, device=dev, dtype=torch.float32)
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        self.ws = torch.empty(max(n_cubes * 2 * sms * channels * 5, 1), device=dev, dtype=torch.float64)
+        self.centers = centers
+        self.lin = linspace_axes(grid_size, cube_size, dev)
+        a = _lib.SoftargmaxArgs()
+        a.x = None
+        a.n_cubes, a.C = int(n_cubes), int(channels)
+        a.X, a.Y, a.Z = [int(v) for v in cube_size]
+        a.centers = centers.data_ptr()
+        a.center_stride = int(centers.stride(0))
+        a.check_flag = 0
+        a.lin_x, a.lin_y, a.lin_z = self.lin[0].data_ptr(), self.lin[1].data_ptr(), self.lin[2].data_ptr()
+        a.beta = float(beta)
+        a.out = self.out.data_ptr()
+        a.workspace = self.ws.data_ptr()
+        a.workspace_bytes = self.ws.numel() * 8
+        self.args = a
+
+
+def _conv_launch_head(x, weight, scale, shift, out_shape, cin, cout, out_grid, ksize, relu, algo, cin_real,
+                      cout_pitch_w, head):
+    import ctypes
+    a = _lib.ConvArgs()
+    a.in_ = x.data_ptr()
+    a.weight = weight.data_ptr()
+    a.scale = scale.data_ptr() if scale is not None else None
+    a.shift = shift.data_ptr() if shift is not None else None
+    a.residual = None
+    a.out = None
+    a.N, a.D, a.H, a.W = [int(s) for s in x.shape[:4]]
+    a.cin = int(cin)
+    a.cin_pitch = int(x.shape[4])
+    a.OD, a.OH, a.OW = [int(s) for s in out_grid]
+    a.TD, a.TH, a.TW = [int(s) for s in out_shape[1:4]]
+    a.cout = int(cout)
+    a.cout_pitch = int(out_shape[4])
+    a.cout_pitch_w = int(cout_pitch_w)
+    _set3(a.ksize, ksize)
+    _set3(a.stride, [1, 1, 1])
+    _set3(a.tap_off0, [0, 0, 0])
+    _set3(a.tap_step, [1, 1, 1])
+    _set3(a.ostride, [1, 1, 1])
+    _set3(a.ooffset, [0, 0, 0])
+    a.relu = int(relu)
+    a.algo = int(algo)
+    a.in_dtype, a.out_dtype = _DT[x.dtype], _lib.F32
+    a.head_softargmax = ctypes.pointer(head.args)
+    flops = 2.0 * a.N * a.OD * a.OH * a.OW * a.cout * (cin_real or a.cin)
+    detail = "conv+softargmax algo%d k1 %d->%d @%dx%dx%dx%d" % (a.algo, cin_real or a.cin, a.cout, a.N, a.OD, a.OH, a.OW)
+    _lib.call("sp3d_conv_fwd", a, _stream(), launches=2, kind="conv", work=flops, detail=detail)
+    return head.out
 
 
 def maxpool(x, channels, k, s, p):
@@ -559,7 +625,7 @@ class PackedConv:
             self._tc_fused = (full.to(torch.bfloat16).contiguous(), cin_tc)
         return self._tc_fused
 
-    def _call_tc(self, x, residual, out_pitch, out_dtype):
+    def _call_tc(self, x, residual, out_pitch, out_dtype, head=None):
         if not self.tc_supported():
             raise _lib.Sp3dError("convolution shape not covered by the tensor-core path")
         packs, n, cin_tc = self._tc_pack()
@@ -569,6 +635,12 @@ class PackedConv:
         o = self.out_shape((D, H, W))
         out_dtype = torch.bfloat16 if out_dtype is None else out_dtype
         out_pitch = round_up(self.cout, 16) if out_pitch is None else int(out_pitch)
+        if head is not None:      # fused soft-argmax head: the volume is never materialised
+            if self.k != [1, 1, 1] or self.transposed or self.nd != 3 or residual is not None or self.cout > 15:
+                raise _lib.Sp3dError("the fused soft-argmax head needs a 1x1x1 convolution with at most 15 output channels")
+            return conv_launch(x, packs[0], self.scale, self.shift, None, (N, o[0], o[1], o[2], 16), cin_tc, self.cout, o,
+                               self.k, self.stride, [0, 0, 0], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu,
+                               _lib.CONV_TC_BF16, cin_real=self.cin, cout_pitch_w=n, head=head)
         out = torch.empty((N, o[0], o[1], o[2], out_pitch), device=x.device, dtype=out_dtype)
         if residual is not None and (residual.dtype != out_dtype or residual.shape != out.shape):
             raise _lib.Sp3dError("residual must match the output dtype and shape")
@@ -599,14 +671,16 @@ class PackedConv:
                             cout_pitch_w=n)
         return out
 
-    def __call__(self, x, residual=None, out_pitch=None, algo=None, out_dtype=None):
+    def __call__(self, x, residual=None, out_pitch=None, algo=None, out_dtype=None, head=None):
         """``x``: channel-last ``[N,D,H,W,pitch]``.  float32 activations take the float32 SIMT kernel; bf16
         activations the tcgen05 kernel where the shape is covered (``out_dtype`` float32 there gives a float32
         result), else the SIMT kernel with bf16 storage and float32 math."""
         if algo is None:
             algo = _lib.CONV_TC_BF16 if (x.dtype == torch.bfloat16 and self.tc_supported()) else _lib.CONV_SIMT_F32
         if algo == _lib.CONV_TC_BF16:
-            return self._call_tc(x, residual, out_pitch, out_dtype)
+            return self._call_tc(x, residual, out_pitch, out_dtype, head=head)
+        if head is not None:
+            raise _lib.Sp3dError("the fused soft-argmax head exists on the tensor-core path only")
         N, D, H, W, pitch = [int(v) for v in x.shape]
         if pitch < self.cin_p:
             raise _lib.Sp3dError("activation pitch %d smaller than packed cin %d" % (pitch, self.cin_p))

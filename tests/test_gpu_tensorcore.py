@@ -171,6 +171,37 @@ def test_tc_stride2_conv_space_to_depth_matches_float64_reference(k, p, cin, cou
     assert float((got - want).abs().max()) <= 6e-3 * scale, float((got - want).abs().max()) / scale
 
 
+@pytest.mark.parametrize("n,shape,J", [(5, (32, 32, 32), 15), (3, (20, 24, 12), 15), (2, (16, 16, 16), 4)])
+def test_tc_output_layer_with_fused_softargmax_head(n, shape, J):
+    """V2VNet's 1x1x1 output layer + soft-argmax in one kernel (the heat-map volume never reaches HBM) against the
+    two-kernel path (float32 volume + sp3d_softargmax3d_fwd) on the same inputs, and against a float64 evaluation
+    of the soft-argmax on that float32 volume.  CTAs span cube boundaries in the first case (320 items / 148 CTAs)."""
+    torch.manual_seed(n * 10 + J)
+    conv = nn.Conv3d(32, J, 1).to(DEV)
+    with torch.no_grad():
+        conv.weight.mul_(0.05)
+    pc = ops.PackedConv(conv.weight, conv.bias, None, 1, 0, relu=0)
+    X, Y, Z = shape
+    x = torch.randn(n, X, Y, Z, 32, device=DEV).to(torch.bfloat16)
+    centers = torch.tensor([[100.0 * i, -500.0 + 37.0 * i, 800.0, 0.0, 1.0] for i in range(n)], device=DEV)
+    beta, grid = 100.0, [2000.0] * 3
+    vol = pc(x, out_pitch=16, out_dtype=torch.float32)
+    two = ops.softargmax(vol, (X * Y * Z * 16, 1, 16), n, J, shape, centers, grid, beta)
+    head = ops.SoftargmaxHead(n, J, shape, centers, grid, beta)
+    before = ops._lib.launch_count
+    fused = pc(x, head=head)
+    assert ops._lib.launch_count - before == 2 and fused.shape == (n, J, 3)
+    assert float((fused - two).abs().max()) <= 2e-3, float((fused - two).abs().max())
+    # float64 soft-argmax of the same float32 logits
+    lin = [torch.linspace(-grid[a] / 2, grid[a] / 2, shape[a]) for a in range(3)]
+    v = vol[..., :J].double().cpu().reshape(n, -1, J)
+    w = torch.softmax(beta * v, dim=1)
+    for i in range(n):
+        g = torch.stack(torch.meshgrid(*[(lin[a] + centers[i, a].cpu()).float() for a in range(3)], indexing="ij"), -1)
+        want = (w[i].T @ g.reshape(-1, 3).double())
+        assert float((fused[i].cpu().double() - want).abs().max()) <= 2e-3
+
+
 def test_v2v_net_bf16_mode_vs_float64_oracle():
     """Whole V2VNet(15,15) on a 32^3 cube and V2VNet(1,1) on a 40x40x12 grid in bf16 tensor-core mode.
     bf16 activations carry ~3 significant digits; the result is compared with the float64 oracle relative
