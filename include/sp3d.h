@@ -237,6 +237,18 @@ typedef struct {
 } sp3d_s2d_args;
 int sp3d_space_to_depth(const sp3d_s2d_args* a, void* stream);
 
+/* Stacks the x-neighbourhood of a 1-channel bf16 volume into channels:
+ * dst[n, x, y, z, j] = src[n, x + j - pad, y, z, 0] (0 outside), j < taps; dst is [N, X, Y, Z, 16] bf16.
+ * Lets the 1 -> 16 channel 7^3 stem of the root V2VNet (lib/models/v2v_net.py:117, input_channels = 1) run as a
+ * 1 x 7 x 7 tensor-core convolution over 7 "tap channels" instead of 7^3 taps over 15 padding zeros. */
+typedef struct {
+  const void* src; void* dst;
+  int N, X, Y, Z;
+  int src_pitch;            /* channels per voxel of src (elements); channel 0 is read */
+  int taps, pad;
+} sp3d_stack_args;
+int sp3d_stack_x_shifts(const sp3d_stack_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

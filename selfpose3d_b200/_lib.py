@@ -111,6 +111,14 @@ class S2DArgs(C.Structure):
     ]
 
 
+class StackArgs(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("dst", C.c_void_p),
+        ("N", C.c_int), ("X", C.c_int), ("Y", C.c_int), ("Z", C.c_int),
+        ("src_pitch", C.c_int), ("taps", C.c_int), ("pad", C.c_int),
+    ]
+
+
 class LayoutArgs(C.Structure):
     _fields_ = [
         ("src", C.c_void_p), ("dst", C.c_void_p),
@@ -136,6 +144,7 @@ SYMBOLS = {
     "sp3d_maxpool_fwd": (C.c_int, [C.POINTER(MaxpoolArgs), C.c_void_p]),
     "sp3d_layout_convert": (C.c_int, [C.POINTER(LayoutArgs), C.c_void_p]),
     "sp3d_space_to_depth": (C.c_int, [C.POINTER(S2DArgs), C.c_void_p]),
+    "sp3d_stack_x_shifts": (C.c_int, [C.POINTER(StackArgs), C.c_void_p]),
 }
 
 _lib = None

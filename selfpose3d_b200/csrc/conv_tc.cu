@@ -123,7 +123,7 @@ struct TcCfg {
   static constexpr int kIssuers = TX >= 2 ? 2 : 1;
   static constexpr uint32_t kLayout = RB == 128 ? kSwizzle128 : (RB == 64 ? kSwizzle64 : kSwizzle32);
   static constexpr uint32_t kLayoutW = kPosBytes == 128 ? kSwizzle128 : (kPosBytes == 64 ? kSwizzle64 : kSwizzle32);
-  static_assert(F == 1 || (KSX == KS && kPosBytes >= 32), "z-fold: 3-D same convolutions, one K chunk");
+  static_assert(F == 1 || ((KSX == KS || KSX == 1) && kPosBytes >= 32), "z-fold: same convolutions, one K chunk");
   static_assert(2 * TX * N <= 512, "accumulators exceed TMEM");
   static_assert(kSmemBytes + 3072 <= 227 * 1024, "shared memory budget (dynamic + ~3 KB static)");
 };
@@ -479,6 +479,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
             }
             if (prof) c3 = clock64();
             fence_proxy_async_smem();
+            // no residual: before publishing "unit u written", the leader makes sure the store that last used the NEXT
+            // slot (unit u + 1 - SB) has left shared memory, so this one barrier also frees that slot for unit u + 1
+            if (!has_res && leader) bulk_wait_read<SB - 2>();
             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
             if (prof) c4 = clock64();
             if (prof) { pe[0] += c1 - c0; pe[1] += c2 - c1; pe[2] += c3 - c2; pe[3] += c4 - c3; }
@@ -495,11 +498,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                   bulk_wait_read<1>();
                   issue_res();
                 }
-              } else {
-                bulk_wait_read<SB - 1>();      // slot (u + 1) % SB: the store of unit u + 1 - SB has left smem
               }
             }
-            if (!has_res) asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
             if (prof) pe[4] += clock64() - c4;
           }
         }
@@ -933,6 +933,8 @@ int conv_tc(const sp3d_conv_args* a, cudaStream_t st) {
   SP3D_TC_CASE_F(7, 7, 64, 32, 4, 8, 3, 1, 2, 128, 1, 2)
   // 3^3 16->32 and 32->32, z-folded by 2 (N = 2 x 32, 4 windows per (dx, dy))
   SP3D_TC_CASE_F(3, 3, 64, 64, 4, 4, 3, 2, 2, 128, 1, 2)
+  // 1-channel 7^3 stem with the x taps stacked into channels: 1 x 7 x 7, z-folded by 2
+  SP3D_TC_CASE_F(1, 7, 64, 32, 4, 8, 3, 2, 2, 128, 2, 2)
   SP3D_TC_CASE_F(3, 3, 128, 64, 4, 4, 2, 1, 2, 128, 1, 2)
   SP3D_TC_CASE(3, 3, 32, 32, 4, 27, 2, 2, 3, 128, 2)
   SP3D_TC_CASE(3, 3, 64, 32, 4, 9, 2, 2, 2, 128, 2)

@@ -49,7 +49,42 @@ __global__ void space_to_depth_kernel(const sp3d_s2d_args a) {
   }
 }
 
+// dst[n, x, y, z, j] = src[n, x + j - pad, y, z, 0] for j < taps (zero outside the volume), channels >= taps zero:
+// a 1-channel volume with its x-neighbourhood stacked into the channel dimension, so that a k^3 convolution on one
+// input channel becomes a 1 x k x k convolution on `taps` channels (K = 16 of the tensor-core MMA is then used for
+// taps instead of 15 padding zeros).  One thread per voxel, one 32-byte store.
+__global__ void stack_x_shifts_kernel(const sp3d_stack_args a) {
+  const int64_t yz = (int64_t)a.Y * a.Z;
+  const int64_t total = (int64_t)a.N * a.X * yz;
+  const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(a.src);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)((i / yz) % a.X);
+    __align__(16) __nv_bfloat16 o[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int xs = x + j - a.pad;
+      const bool ok = j < a.taps && xs >= 0 && xs < a.X;
+      o[j] = ok ? src[(i + (int64_t)(j - a.pad) * yz) * a.src_pitch] : __float2bfloat16_rn(0.0f);
+    }
+    uint4* d = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.dst) + i * 16);
+    d[0] = *reinterpret_cast<const uint4*>(o);
+    d[1] = *reinterpret_cast<const uint4*>(o + 8);
+  }
+}
+
 }  // namespace sp3d
+
+extern "C" int sp3d_stack_x_shifts(const sp3d_stack_args* a, void* stream) {
+  using namespace sp3d;
+  if (a == nullptr || a->src == nullptr || a->dst == nullptr || a->N < 0 || a->X < 1 || a->Y < 1 || a->Z < 1 ||
+      a->taps < 1 || a->taps > 16 || a->pad < 0 || a->src_pitch < 1 || (reinterpret_cast<uintptr_t>(a->dst) % 16))
+    return SP3D_ERR_INVALID_ARG;
+  const int64_t total = (int64_t)a->N * a->X * a->Y * a->Z;
+  if (total == 0) return SP3D_OK;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  stack_x_shifts_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
+  return check_launch();
+}
 
 extern "C" int sp3d_space_to_depth(const sp3d_s2d_args* a, void* stream) {
   using namespace sp3d;

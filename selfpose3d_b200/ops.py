@@ -286,6 +286,19 @@ def space_to_depth(x, channels, strides, n, h, w, dst_pitch):
     return out
 
 
+def stack_x_shifts(x, taps, pad):
+    """Channel-last bf16 ``[N,X,Y,Z,pitch]`` (channel 0 used) -> ``[N,X,Y,Z,16]`` with channel ``j`` =
+    ``x[:, x+j-pad, y, z, 0]`` (zero outside), ``j < taps``."""
+    _require_cuda(x)
+    N, X, Y, Z, pitch = [int(v) for v in x.shape]
+    out = torch.empty(N, X, Y, Z, 16, device=x.device, dtype=torch.bfloat16)
+    a = _lib.StackArgs()
+    a.src, a.dst = x.data_ptr(), out.data_ptr()
+    a.N, a.X, a.Y, a.Z, a.src_pitch, a.taps, a.pad = N, X, Y, Z, pitch, int(taps), int(pad)
+    _lib.call("sp3d_stack_x_shifts", a, _stream(), kind="layout", work=N * X * Y * Z * (2 * taps + 32))
+    return out
+
+
 class S2DConv:
     """A stride-2 2-D convolution (3x3/p1 or 7x7/p3, + folded BatchNorm + ReLU) evaluated on the tcgen05 path as a
     stride-1 convolution over the 2x2 space-to-depth tensor: tap ``d`` with offset ``t = d - pad`` lands on
@@ -606,6 +619,26 @@ class PackedConv:
             self._tc_zf = full.reshape(1, 1, -1, F * cout_p, cin_p).to(torch.bfloat16).contiguous()
         return self._tc_zf
 
+    def _tc_stack_ok(self, w_extent, out_pitch):
+        """The root net's 1 -> 16 channel 7^3 stem: x taps stacked into channels (1 x 7 x 7 over 7 tap channels)."""
+        return (self.nd == 3 and not self.transposed and self.k == [7, 7, 7] and self.stride == [1, 1, 1]
+                and self.padding == [3, 3, 3] and self.cin == 1 and self.cout == 16 and out_pitch == 16
+                and w_extent % self.ZFOLD == 0)
+
+    def _tc_pack_stack(self):
+        """bf16 ``[1, 1, kh*(k+F-1), F*16, 16]``: K index j = x tap, per kh the k+F-1 z-windows, rows (ro, co)."""
+        if getattr(self, "_tc_st", None) is None:
+            F, k = self.ZFOLD, 7
+            w5 = self._subs[0]                                     # [Cout, 1, kd, kh, kw]
+            full = torch.zeros(k, k + F - 1, F, 16, 16, device=w5.device, dtype=torch.float32)
+            for e in range(k + F - 1):
+                for ro in range(F):
+                    kw = e - ro
+                    if 0 <= kw < k:
+                        full[:, e, ro, :self.cout, :k] = w5[:, 0, :, :, kw].permute(2, 0, 1)   # [kh, co, kd]
+            self._tc_st = full.reshape(1, 1, -1, F * 16, 16).to(torch.bfloat16).contiguous()
+        return self._tc_st
+
     def _tc_fused_ok(self, out_pitch, out_dtype):
         """k2/s2 transposed 3-D convolution as ONE launch (all 8 output phases are extra GEMM columns)."""
         esz = 4 if out_dtype == torch.float32 else 2
@@ -650,7 +683,12 @@ class PackedConv:
             outk = out.view(1, N, o[1], o[2], out_pitch)
             resk = residual.view(1, N, o[1], o[2], out_pitch) if residual is not None else None
             D, o = N, [N, o[1], o[2]]
-        if not self.transposed and pitch == round_up(self.cin, 16) and self._tc_zfold_ok(W, out_pitch):
+        if pitch == 16 and residual is None and self._tc_stack_ok(W, out_pitch):
+            xs = stack_x_shifts(xk, 7, 3)
+            conv_launch(xs, self._tc_pack_stack(), self.scale, self.shift, None, outk, 16, self.cout, o, [1, 7, 7],
+                        self.stride, [0, -3, -3], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu, _lib.CONV_TC_BF16,
+                        cin_real=7, cout_pitch_w=16 * self.ZFOLD, zfold=self.ZFOLD)
+        elif not self.transposed and pitch == round_up(self.cin, 16) and self._tc_zfold_ok(W, out_pitch):
             conv_launch(xk, self._tc_pack_zfold(), self.scale, self.shift, resk, outk, pitch, self.cout, o, self.k,
                         self.stride, [-p for p in self.padding], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu,
                         _lib.CONV_TC_BF16, cin_real=self.cin, cout_pitch_w=out_pitch * self.ZFOLD, zfold=self.ZFOLD)

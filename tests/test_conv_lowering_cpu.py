@@ -210,6 +210,32 @@ def test_space_to_depth_stride2_lowering(monkeypatch, k, p, cin, cout, hw):
     assert float((got - want).abs().max()) <= 1e-2 * float(want.abs().max())    # bf16 output
 
 
+def emulate_stack_x_shifts(x, taps, pad):
+    """include/sp3d.h, sp3d_stack_args: dst[n, x, y, z, j] = src[n, x + j - pad, y, z, 0], zero outside."""
+    N, X, Y, Z, _ = x.shape
+    out = torch.zeros(N, X, Y, Z, 16)
+    v = x[..., 0].float()
+    for j in range(taps):
+        lo, hi = max(0, pad - j), min(X, X + pad - j)
+        out[:, lo:hi, :, :, j] = v[:, lo + j - pad:hi + j - pad]
+    return out.to(torch.bfloat16)
+
+
+def test_one_channel_stem_tap_stacking(monkeypatch):
+    """Root-net stem (1 -> 16 channels, 7^3): x taps stacked into channels + 1 x 7 x 7 z-folded packing."""
+    monkeypatch.setattr(ops, "conv_launch", emulate_any_launch)
+    monkeypatch.setattr(ops, "stack_x_shifts", emulate_stack_x_shifts)
+    torch.manual_seed(3)
+    conv, bn = nn.Conv3d(1, 16, 7, 1, 3), rand_bn(nn.BatchNorm3d(16))
+    conv.weight.data = bf(conv.weight.data)
+    x = bf(torch.randn(2, 1, 5, 4, 6))
+    want = F.relu(bn(conv(x)))
+    pc = ops.PackedConv(conv.weight, conv.bias, bn, 1, 3, relu=1)
+    assert pc._tc_stack_ok(6, 16)
+    got = cf(pc(cl16(x), out_pitch=16, out_dtype=torch.float32), 16, 3)
+    assert float((got - want).abs().max()) <= 1e-4 * float(want.abs().max())
+
+
 @pytest.mark.parametrize("case", ["1x1", "1x1s2", "3x3", "deconv", "3d_k3", "3d_convT", "3d_stem_zfold"])
 def test_tensorcore_lowering(monkeypatch, case):
     monkeypatch.setattr(ops, "conv_launch", emulate_any_launch)
