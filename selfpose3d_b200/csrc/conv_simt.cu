@@ -322,6 +322,38 @@ __global__ void maxpool_bf16_kernel(const sp3d_maxpool_args a) {
   }
 }
 
+// bf16, window 2 stride 2 no padding (V2VNet's pools): the 8 taps are independent 16-byte loads issued together and
+// reduced with packed bf16x2 max
+__global__ void maxpool_bf16_k2s2_kernel(const sp3d_maxpool_args a) {
+  const int cvec = a.c_pitch / 8;
+  const int64_t total = (int64_t)a.N * a.OD * a.OH * a.OW * cvec;
+  const uint4* in = reinterpret_cast<const uint4*>(a.in);
+  uint4* out = reinterpret_cast<uint4*>(a.out);
+  const int64_t sw = cvec, sh = (int64_t)a.W * cvec, sd = (int64_t)a.H * a.W * cvec;   // input strides in 16-byte units
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    int64_t pos = i / cvec;
+    const int ow = (int)(pos % a.OW); pos /= a.OW;
+    const int oh = (int)(pos % a.OH); pos /= a.OH;
+    const int od = (int)(pos % a.OD);
+    const int64_t n = pos / a.OD;
+    const uint4* p = in + n * a.D * sd + (int64_t)(2 * od) * sd + (int64_t)(2 * oh) * sh + (int64_t)(2 * ow) * sw + cv;
+    uint4 q[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) q[t] = __ldg(p + (t >> 2) * sd + ((t >> 1) & 1) * sh + (t & 1) * sw);
+    uint32_t r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 m = *reinterpret_cast<const __nv_bfloat162*>(&(reinterpret_cast<const uint32_t*>(&q[0])[j]));
+#pragma unroll
+      for (int t = 1; t < 8; ++t)
+        m = __hmax2(m, *reinterpret_cast<const __nv_bfloat162*>(&(reinterpret_cast<const uint32_t*>(&q[t])[j])));
+      r[j] = *reinterpret_cast<const uint32_t*>(&m);
+    }
+    out[i] = make_uint4(r[0], r[1], r[2], r[3]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ layout
 // [N, C, S] <-> [N, S, c_pitch] through a 32x32 shared-memory transpose tile.
 template <typename SrcT, typename DstT>
@@ -385,7 +417,12 @@ extern "C" int sp3d_maxpool_fwd(const sp3d_maxpool_args* a, void* stream) {
   if (total == 0) return SP3D_OK;
   const int64_t want = (total + 255) / 256;
   const int blocks = (int)(want < 148 * 32 ? want : 148 * 32);
+  const bool k2s2 = a->dtype == SP3D_BF16 && a->k[0] == 2 && a->k[1] == 2 && a->k[2] == 2 && a->s[0] == 2 &&
+                    a->s[1] == 2 && a->s[2] == 2 && a->p[0] == 0 && a->p[1] == 0 && a->p[2] == 0 &&
+                    2 * a->OD <= a->D && 2 * a->OH <= a->H && 2 * a->OW <= a->W &&
+                    (reinterpret_cast<uintptr_t>(a->in) % 16) == 0 && (reinterpret_cast<uintptr_t>(a->out) % 16) == 0;
   if (a->dtype == SP3D_F32) maxpool_f32_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
+  else if (k2s2) maxpool_bf16_k2s2_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
   else maxpool_bf16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
   return check_launch();
 }

@@ -202,6 +202,17 @@ def test_tc_output_layer_with_fused_softargmax_head(n, shape, J):
         assert float((fused[i].cpu().double() - want).abs().max()) <= 2e-3
 
 
+@pytest.mark.parametrize("shape", [(8, 12, 16), (6, 10, 4)])
+def test_maxpool_bf16_k2s2_exact(shape):
+    """V2VNet's 2x2x2 pools on bf16 channel-last activations: exact (max of bf16 values is a bf16 value)."""
+    torch.manual_seed(1)
+    x = bf16_round(torch.randn(3, 32, *shape))
+    want = F.max_pool3d(x, 2, 2)
+    y = ops.maxpool(to_cl_bf16(x), 32, [2, 2, 2], [2, 2, 2], [0, 0, 0])
+    got = ops.to_channel_first(y, 32, dtype=torch.float32).cpu()
+    assert torch.equal(got, want)
+
+
 def test_v2v_net_bf16_mode_vs_float64_oracle():
     """Whole V2VNet(15,15) on a 32^3 cube and V2VNet(1,1) on a 40x40x12 grid in bf16 tensor-core mode.
     bf16 activations carry ~3 significant digits; the result is compared with the float64 oracle relative
