@@ -600,7 +600,8 @@ class PackedConv:
         if self.k == [7, 7, 7] and self.padding == [3, 3, 3]:
             return self.cin <= 16 and self.cout == 16 and out_pitch == 16
         if self.k == [3, 3, 3] and self.padding == [1, 1, 1]:
-            return self.cin in (16, 32) and self.cout == 32 and out_pitch == 32
+            # only where the folded extent still fills the 8-row bricks (W = 20 would run 10 of 16 rows)
+            return self.cin in (16, 32) and self.cout == 32 and out_pitch == 32 and w_extent % 16 == 0
         return False
 
     def _tc_pack_zfold(self):
