@@ -64,8 +64,17 @@ def pack_cameras(meta, image_size, flip_xcoords=None):
         table[:, c, 16:19] = cam["k"].reshape(B, 3)
         table[:, c, 19:21] = cam["p"].reshape(B, 2)
         for i in range(B):
-            trans = get_affine_transform(center[i], scale[i], rot[i], image_size)
-            table[i, c, 21:27] = trans.reshape(6)
+            # the affine depends on (center, scale, rotation, input size) only; views and samples of one rig share
+            # it, so the float64 elimination runs once per distinct tuple (content-keyed: no stale entries)
+            key = (center[i].tobytes(), scale[i].tobytes(), np.asarray(rot[i]).tobytes(), center.dtype.str,
+                   scale.dtype.str, np.asarray(rot[i]).dtype.str, tuple(float(v) for v in image_size))
+            trans = _AFFINE_CACHE.get(key)
+            if trans is None:
+                if len(_AFFINE_CACHE) > 4096:
+                    _AFFINE_CACHE.clear()
+                trans = get_affine_transform(center[i], scale[i], rot[i], image_size).reshape(6).astype(np.float32)
+                _AFFINE_CACHE[key] = trans
+            table[i, c, 21:27] = trans
             # width, height = center * 2, compared against float32 pixels (project_layer.py:68,78-80)
             table[i, c, 27] = center[i][0] * 2
             table[i, c, 28] = center[i][1] * 2
@@ -74,6 +83,7 @@ def pack_cameras(meta, image_size, flip_xcoords=None):
 
 
 _LIN_CACHE = {}
+_AFFINE_CACHE = {}   # (center, scale, rotation, input size) bytes -> float32 [6] affine
 
 # dtype of the voxel cubes and V2V activations: float32 -> float32 SIMT convolutions (bit-faithful parity
 # path), bfloat16 -> tcgen05 tensor-core convolutions with float32 accumulation.
