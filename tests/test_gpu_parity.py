@@ -373,6 +373,27 @@ def test_inference_from_heatmaps_matches_reference_golden(golden):
     assert not pred.cpu().numpy()[~valid][..., :3].any()
 
 
+def test_inference_bf16_throughput_mode_vs_reference_golden(golden):
+    """The bench's mode (fp16 maps + half2 un-projection, tcgen05 convolutions, fused soft-argmax head) on the
+    reference's own golden inference case.  bf16 activations carry 8 significant bits: proposals that land on the
+    reference's voxel are compared at centimetre level; this documents the accuracy envelope of the throughput mode,
+    the float32 mode above is the parity mode."""
+    g = golden("inference_small")
+    model, _ = _small_model(g, float(g["threshold"]))
+    hms = [torch.from_numpy(h).to(DEV) for h in g["heatmaps"]]
+    ops.set_volume_dtype(torch.bfloat16)
+    try:
+        pred, _, gc = model(views1=None, meta1=meta_from_golden(g), input_heatmaps1=hms, inference=True)
+    finally:
+        ops.set_volume_dtype(torch.float32)
+    pred, gc = pred.cpu().numpy(), gc.cpu().numpy()
+    valid = g["pred"][:, :, 0, 3] >= 0
+    same = valid & (pred[:, :, 0, 3] >= 0) & (np.abs(gc[:, :, :3] - g["grid_centers"][:, :, :3]).max(-1) < 1.0)
+    assert same.sum() >= max(1, valid.sum() // 2), (int(same.sum()), int(valid.sum()))
+    err = np.abs(pred[same][..., :3] - g["pred"][same][..., :3])
+    assert float(np.median(err)) < 10.0 and float(err.max()) < 60.0, (float(np.median(err)), float(err.max()))
+
+
 def test_inference_from_images_matches_reference_golden(golden):
     g0, g = golden("inference_small"), golden("inference_images")
     model, _ = _small_model(g0, float(g["threshold"]))
