@@ -124,7 +124,11 @@ typedef struct {
                                (config values were float64 numpy arrays), 0: all float32 (YAML lists) */
   float* grid_centers;      /* [B, K, 5]: x, y, z, flag = (score > threshold) - 1, score */
   int32_t* topk_index;      /* optional [B, K] flat voxel index, or NULL */
+  void* workspace;          /* optional sp3d_nms_topk3d_workspace() bytes: 16 CTAs per sample (x slabs) + a merge
+                               instead of one CTA per sample; same result */
+  int64_t workspace_bytes;
 } sp3d_nms_topk_args;
+int64_t sp3d_nms_topk3d_workspace(const sp3d_nms_topk_args* a);
 int sp3d_nms_topk3d(const sp3d_nms_topk_args* a, void* stream);
 
 /* Soft-argmax over a voxel cube: sum_v softmax(beta * x)_v * grid_v, one (x,y,z) per channel.

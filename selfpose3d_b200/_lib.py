@@ -63,6 +63,7 @@ class NmsTopkArgs(C.Structure):
         ("space_size", C.c_double * 3), ("space_center", C.c_double * 3),
         ("loc_f64", C.c_int),
         ("grid_centers", C.c_void_p), ("topk_index", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 
 
@@ -136,6 +137,7 @@ SYMBOLS = {
     "sp3d_heatmaps_to_f16": (C.c_int, [C.POINTER(HeatmapsF16Args), C.c_void_p]),
     "sp3d_unproject_finalize": (C.c_int, [C.POINTER(UnprojectFinalizeArgs), C.c_void_p]),
     "sp3d_nms_topk3d": (C.c_int, [C.POINTER(NmsTopkArgs), C.c_void_p]),
+    "sp3d_nms_topk3d_workspace": (C.c_int64, [C.POINTER(NmsTopkArgs)]),
     "sp3d_softargmax3d_workspace": (C.c_int64, [C.POINTER(SoftargmaxArgs)]),
     "sp3d_softargmax3d_fwd": (C.c_int, [C.POINTER(SoftargmaxArgs), C.c_void_p]),
     "sp3d_conv_fwd": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),

@@ -13,9 +13,34 @@ namespace sp3d {
 
 constexpr int kNmsMaxThreads = 1024;   // one CTA per sample: as many threads as the candidate lists leave room for
 constexpr int kNmsMaxK = 32;
+constexpr int kNmsSlabs = 16;          // CTAs per sample when the caller provides a workspace
 
 __device__ __forceinline__ bool better(float va, int ia, float vb, int ib) {
   return va > vb || (va == vb && ia < ib);
+}
+
+// proposal k of sample b: flat index -> world location (float32 or float64 as torch's type promotion does), flag, score
+__device__ __forceinline__ void write_proposal(const sp3d_nms_topk_args& a, int b, int k, float bv, int bi) {
+  const int X = a.X, Y = a.Y, Z = a.Z, K = a.K;
+  const int iz = bi % Z, iy = (bi / Z) % Y, ix = bi / (Z * Y);
+  const int idx[3] = {ix, iy, iz};
+  const int dims[3] = {X, Y, Z};
+  float* gc = a.grid_centers + ((int64_t)b * K + k) * 5;
+  for (int d = 0; d < 3; ++d) {
+    const float q = __fdiv_rn((float)idx[d], __fsub_rn((float)dims[d], 1.0f));
+    float loc;
+    if (a.loc_f64) {
+      const double s = a.space_size[d];
+      loc = (float)(__dsub_rn(__dadd_rn(__dmul_rn((double)q, s), a.space_center[d]), s / 2.0));
+    } else {
+      const float s = (float)a.space_size[d];
+      loc = __fsub_rn(__fadd_rn(__fmul_rn(q, s), (float)a.space_center[d]), __fdiv_rn(s, 2.0f));
+    }
+    gc[d] = loc;
+  }
+  gc[3] = (bv > a.threshold) ? 0.0f : -1.0f;
+  gc[4] = bv;
+  if (a.topk_index != nullptr) a.topk_index[(int64_t)b * K + k] = bi;
 }
 
 __global__ void __launch_bounds__(kNmsMaxThreads) nms_topk_kernel(const sp3d_nms_topk_args a) {
@@ -29,7 +54,7 @@ __global__ void __launch_bounds__(kNmsMaxThreads) nms_topk_kernel(const sp3d_nms
   __shared__ int red_t[kNmsMaxThreads / 32];
   __shared__ int win_t;
 
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;                       // sample; blockIdx.x = slab of x-slices (1 slab without a workspace)
   const int tid = threadIdx.x;
   const int K = a.K;
   const int X = a.X, Y = a.Y, Z = a.Z;
@@ -41,7 +66,9 @@ __global__ void __launch_bounds__(kNmsMaxThreads) nms_topk_kernel(const sp3d_nms
     cand_v[s * kNmsThreads + tid] = ninf;
     cand_i[s * kNmsThreads + tid] = 0x7fffffff;
   }
-  for (int n = tid; n < N; n += kNmsThreads) {
+  const int xs = (X + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_begin = (int)blockIdx.x * xs * Y * Z, n_end = min(N, ((int)blockIdx.x + 1) * xs * Y * Z);
+  for (int n = n_begin + tid; n < n_end; n += kNmsThreads) {
     const int iz = n % Z, iy = (n / Z) % Y, ix = n / (Z * Y);
     const float c = x[n];
     float mx = ninf;
@@ -91,32 +118,57 @@ __global__ void __launch_bounds__(kNmsMaxThreads) nms_topk_kernel(const sp3d_nms
       for (int w = 1; w < kNmsThreads / 32; ++w)
         if (better(red_v[w], red_i[w], bv, bi)) { bv = red_v[w]; bi = red_i[w]; bt = red_t[w]; }
       win_t = bt;
-      const int iz = bi % Z, iy = (bi / Z) % Y, ix = bi / (Z * Y);
-      const int idx[3] = {ix, iy, iz};
-      const int dims[3] = {X, Y, Z};
-      float* gc = a.grid_centers + ((int64_t)b * K + k) * 5;
-      for (int d = 0; d < 3; ++d) {
-        const float q = __fdiv_rn((float)idx[d], __fsub_rn((float)dims[d], 1.0f));
-        float loc;
-        if (a.loc_f64) {
-          const double s = a.space_size[d];
-          loc = (float)(__dsub_rn(__dadd_rn(__dmul_rn((double)q, s), a.space_center[d]), s / 2.0));
-        } else {
-          const float s = (float)a.space_size[d];
-          loc = __fsub_rn(__fadd_rn(__fmul_rn(q, s), (float)a.space_center[d]), __fdiv_rn(s, 2.0f));
-        }
-        gc[d] = loc;
+      if (a.workspace != nullptr && gridDim.x > 1) {   // slab mode: this CTA's k-th candidate, merged by nms_merge_kernel
+        float* cv = reinterpret_cast<float*>(a.workspace) + (((int64_t)b * gridDim.x + blockIdx.x) * K + k) * 2;
+        cv[0] = bv;
+        reinterpret_cast<int*>(cv)[1] = bi;
+      } else {
+        write_proposal(a, b, k, bv, bi);
       }
-      gc[3] = (bv > a.threshold) ? 0.0f : -1.0f;
-      gc[4] = bv;
-      if (a.topk_index != nullptr) a.topk_index[(int64_t)b * K + k] = bi;
     }
     __syncthreads();
     if (tid == win_t) ++head;
   }
 }
 
+// slab mode, stage 2: one warp per sample picks the K best of the S * K slab candidates (same order relation)
+__global__ void nms_merge_kernel(const sp3d_nms_topk_args a, int slabs) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const int K = a.K, total = slabs * K;
+  const float* cand = reinterpret_cast<const float*>(a.workspace) + (int64_t)b * total * 2;
+  unsigned long long taken_lo = 0, taken_hi = 0;        // candidates of this lane already emitted (<= 128 per lane)
+  for (int k = 0; k < K; ++k) {
+    float v = -INFINITY;
+    int i = 0x7fffffff, src = -1;
+    for (int c = lane, j = 0; c < total; c += 32, ++j) {
+      const bool used = j < 64 ? ((taken_lo >> j) & 1ull) : ((taken_hi >> (j - 64)) & 1ull);
+      if (used) continue;
+      const float cv = cand[2 * c];
+      const int ci = reinterpret_cast<const int*>(cand)[2 * c + 1];
+      if (better(cv, ci, v, i)) { v = cv; i = ci; src = j; }
+    }
+    float bv = v;
+    int bi = i, bl = lane;
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      const int ol = __shfl_xor_sync(0xffffffffu, bl, off);
+      if (better(ov, oi, bv, bi) || (ov == bv && oi == bi && ol < bl)) { bv = ov; bi = oi; bl = ol; }
+    }
+    if (lane == bl && src >= 0) {
+      if (src < 64) taken_lo |= 1ull << src;
+      else taken_hi |= 1ull << (src - 64);
+    }
+    if (lane == 0) write_proposal(a, b, k, bv, bi);
+  }
+}
+
 }  // namespace sp3d
+
+extern "C" int64_t sp3d_nms_topk3d_workspace(const sp3d_nms_topk_args* a) {
+  if (a == nullptr || a->B < 1 || a->K < 1) return 0;
+  return (int64_t)a->B * sp3d::kNmsSlabs * a->K * 2 * (int64_t)sizeof(float);
+}
 
 extern "C" int sp3d_nms_topk3d(const sp3d_nms_topk_args* a, void* stream) {
   using namespace sp3d;
@@ -125,14 +177,24 @@ extern "C" int sp3d_nms_topk3d(const sp3d_nms_topk_args* a, void* stream) {
     return SP3D_ERR_INVALID_ARG;
   if ((int64_t)a->X * a->Y * a->Z < a->K) return SP3D_ERR_INVALID_ARG;  // torch.topk would raise
   if (a->B == 0) return SP3D_OK;
+  // with a workspace: kNmsSlabs CTAs of 256 threads per sample (x slabs) + a one-warp merge; else one big CTA.
+  const bool slabs = a->workspace != nullptr && a->workspace_bytes >= sp3d_nms_topk3d_workspace(a) &&
+                     a->X >= kNmsSlabs && (int64_t)((a->X + kNmsSlabs - 1) / kNmsSlabs) * a->Y * a->Z >= a->K &&
+                     kNmsSlabs * a->K <= 32 * 128 && (reinterpret_cast<uintptr_t>(a->workspace) % 8) == 0;
   // per-thread candidate lists of K (value, index) pairs live in shared memory: 1024 threads up to K = 25
-  int threads = kNmsMaxThreads;
+  int threads = slabs ? 256 : kNmsMaxThreads;
   while ((size_t)a->K * threads * 8 > 200 * 1024) threads /= 2;
   const size_t smem = (size_t)a->K * threads * (sizeof(float) + sizeof(int));
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(nms_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_last_error(e); return SP3D_ERR_LAUNCH; }
   }
-  nms_topk_kernel<<<a->B, threads, smem, static_cast<cudaStream_t>(stream)>>>(*a);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  sp3d_nms_topk_args k = *a;
+  if (!slabs) k.workspace = nullptr;
+  nms_topk_kernel<<<dim3(slabs ? kNmsSlabs : 1, a->B), threads, smem, st>>>(k);
+  int rc = check_launch();
+  if (rc != SP3D_OK || !slabs) return rc;
+  nms_merge_kernel<<<a->B, 32, 0, st>>>(k, kNmsSlabs);
   return check_launch();
 }

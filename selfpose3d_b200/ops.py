@@ -206,7 +206,10 @@ def nms_topk(root_cubes, max_people, threshold, space_size, space_center, loc_f6
     a.loc_f64 = int(bool(loc_f64))
     a.grid_centers = gc.data_ptr()
     a.topk_index = idx.data_ptr() if idx is not None else None
-    _lib.call("sp3d_nms_topk3d", a, _stream(), kind="nms_topk", work=4 * B * X * Y * Z)
+    nbytes = int(_lib.load().sp3d_nms_topk3d_workspace(a))
+    ws = torch.empty(max(nbytes // 4, 1), device=root_cubes.device, dtype=torch.float32)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
+    _lib.call("sp3d_nms_topk3d", a, _stream(), launches=2, kind="nms_topk", work=4 * B * X * Y * Z)
     return (gc, idx) if return_index else gc
 
 
