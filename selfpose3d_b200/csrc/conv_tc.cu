@@ -872,8 +872,16 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   }
   auto kern = conv_tc_kernel<KSX, KS, RB, N, TX, G, S, HB, SB, SR, EG, F>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-  if (e != cudaSuccess) { set_last_error(e); return SP3D_ERR_LAUNCH; }
+  {  // opt in to the large dynamic shared memory once per (kernel instance, device)
+    static unsigned long long done_mask = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 64 || !((done_mask >> dev) & 1ull)) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+      if (e != cudaSuccess) { set_last_error(e); return SP3D_ERR_LAUNCH; }
+      if (dev < 64) done_mask |= 1ull << dev;
+    }
+  }
   const int items = p.n_bricks * p.n_tiles;
   const int grid = items < n_sm ? items : n_sm;
   if (head != nullptr) {

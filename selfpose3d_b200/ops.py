@@ -377,38 +377,54 @@ def conv_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksi
     if head is not None:
         return _conv_launch_head(x, weight, scale, shift, out, cin, cout, out_grid, ksize, relu, algo, cin_real,
                                  cout_pitch_w, head)
-    a = _lib.ConvArgs()
+    # the argument struct of a (layer, shapes, launch geometry) is built once and re-used: only the three activation
+    # pointers change between calls (filling ~40 ctypes fields costs more host time than a small kernel runs)
+    key = (weight.data_ptr(), tuple(x.shape), x.dtype, tuple(out.shape), out.dtype, residual is not None,
+           tuple(out_grid), tuple(tap_off0), tuple(ostride), tuple(ooffset), int(algo), bool(fused_phases), int(zfold))
+    hit = _CONV_ARGS_CACHE.get(key)
+    if hit is None:
+        a = _lib.ConvArgs()
+        a.weight = weight.data_ptr()
+        a.scale = scale.data_ptr() if scale is not None else None
+        a.shift = shift.data_ptr() if shift is not None else None
+        a.N, a.D, a.H, a.W = [int(s) for s in x.shape[:4]]
+        a.cin = int(cin)
+        a.cin_pitch = int(x.shape[4])
+        a.OD, a.OH, a.OW = [int(s) for s in out_grid]
+        a.TD, a.TH, a.TW = [int(s) for s in out.shape[1:4]]
+        a.cout = int(cout)
+        a.cout_pitch = int(out.shape[4])
+        a.cout_pitch_w = int(weight.shape[-1]) if cout_pitch_w is None else int(cout_pitch_w)
+        _set3(a.ksize, ksize)
+        _set3(a.stride, stride)
+        _set3(a.tap_off0, tap_off0)
+        _set3(a.tap_step, tap_step)
+        _set3(a.ostride, ostride)
+        _set3(a.ooffset, ooffset)
+        a.relu = int(relu)
+        a.algo = int(algo)
+        a.in_dtype, a.out_dtype = _DT[x.dtype], _DT[out.dtype]
+        a.fused_phases = int(bool(fused_phases))
+        a.zfold = int(zfold)
+        flops = 2.0 * a.N * a.OD * a.OH * a.OW * a.cout * (cin_real or a.cin) * (a.ksize[0] * a.ksize[1] * a.ksize[2])
+        if fused_phases:
+            flops *= 8
+        detail = "conv%s algo%d k%d %d->%d @%dx%dx%dx%d" % ("T8" if fused_phases else "", a.algo, a.ksize[2],
+                                                           cin_real or a.cin, a.cout, a.N, a.OD, a.OH, a.OW)
+        if len(_CONV_ARGS_CACHE) > 4096:
+            _CONV_ARGS_CACHE.clear()
+        # (weight, scale, shift) are kept alive by the cache entry so that their addresses cannot be recycled
+        hit = _CONV_ARGS_CACHE[key] = (a, flops, detail, (weight, scale, shift), (int(relu), int(cout), int(cin)))
+    a, flops, detail, _, sig = hit
+    if sig != (int(relu), int(cout), int(cin)):
+        raise _lib.Sp3dError("conv_launch cache collision")
     a.in_ = x.data_ptr()
-    a.weight = weight.data_ptr()
-    a.scale = scale.data_ptr() if scale is not None else None
-    a.shift = shift.data_ptr() if shift is not None else None
     a.residual = residual.data_ptr() if residual is not None else None
     a.out = out.data_ptr()
-    a.N, a.D, a.H, a.W = [int(s) for s in x.shape[:4]]
-    a.cin = int(cin)
-    a.cin_pitch = int(x.shape[4])
-    a.OD, a.OH, a.OW = [int(s) for s in out_grid]
-    a.TD, a.TH, a.TW = [int(s) for s in out.shape[1:4]]
-    a.cout = int(cout)
-    a.cout_pitch = int(out.shape[4])
-    a.cout_pitch_w = int(weight.shape[-1]) if cout_pitch_w is None else int(cout_pitch_w)
-    _set3(a.ksize, ksize)
-    _set3(a.stride, stride)
-    _set3(a.tap_off0, tap_off0)
-    _set3(a.tap_step, tap_step)
-    _set3(a.ostride, ostride)
-    _set3(a.ooffset, ooffset)
-    a.relu = int(relu)
-    a.algo = int(algo)
-    a.in_dtype, a.out_dtype = _DT[x.dtype], _DT[out.dtype]
-    a.fused_phases = int(bool(fused_phases))
-    a.zfold = int(zfold)
-    flops = 2.0 * a.N * a.OD * a.OH * a.OW * a.cout * (cin_real or a.cin) * (a.ksize[0] * a.ksize[1] * a.ksize[2])
-    if fused_phases:
-        flops *= 8
-    detail = "conv%s algo%d k%d %d->%d @%dx%dx%dx%d" % ("T8" if fused_phases else "", a.algo, a.ksize[2], cin_real or a.cin,
-                                                       a.cout, a.N, a.OD, a.OH, a.OW)
     _lib.call("sp3d_conv_fwd", a, _stream(), kind="conv", work=flops, detail=detail)
+
+
+_CONV_ARGS_CACHE = {}
 
 
 class SoftargmaxHead:
