@@ -113,3 +113,24 @@ def test_synthetic_is_deterministic():
     s1 = synthetic.trained_like_state_dict(m, seed=3)
     s2 = synthetic.trained_like_state_dict(m, seed=3)
     assert all(torch.equal(s1[k], s2[k]) for k in s1)
+
+
+def test_pack_cameras_affine_cache_is_content_keyed():
+    """The input affine is cached by the bytes of (center, scale, rotation, input size): a different rig or
+    augmentation must never see a stale entry, and a repeated call returns identical tables."""
+    from selfpose3d_b200 import ops, synthetic
+    from selfpose3d_b200.utils.transforms import get_affine_transform
+    cams = synthetic.ring_cameras(3, seed=4)
+    m1 = synthetic.make_meta(cams, 2, (96, 128))
+    m2 = synthetic.make_meta(cams, 2, (96, 128), rotation=[[7.0, -3.0]] * 3, scale_mul=[[1.2, 0.8]] * 3)
+    t1a, t2, t1b = ops.pack_cameras(m1, (96, 128)), ops.pack_cameras(m2, (96, 128)), ops.pack_cameras(m1, (96, 128))
+    assert torch.equal(t1a, t1b) and not torch.equal(t1a[..., 21:27], t2[..., 21:27])
+    for meta, table in ((m1, t1a), (m2, t2)):
+        for c, m in enumerate(meta):
+            for i in range(2):
+                want = get_affine_transform(np.asarray(m["center"][i]), np.asarray(m["scale"][i]),
+                                            np.asarray(m["rotation"][i]), (96, 128)).reshape(6).astype(np.float32)
+                assert np.array_equal(table[i, c, 21:27].numpy(), want)
+    # same rig at another network input size: other affine
+    t3 = ops.pack_cameras(m1, (192, 256))
+    assert not torch.equal(t1a[..., 21:27], t3[..., 21:27])
