@@ -71,7 +71,7 @@ class ProjectLayer(nn.Module):
         pitch = ops.round_up(C, 4) if c_pitch is None else int(c_pitch)
         dev = hms[0].device
         cubes = torch.empty(n_cubes, X, Y, Z, pitch, device=dev, dtype=dtype)
-        if dtype == torch.bfloat16 and pitch == 16 and 1 < C <= 16 and not want_grids and Z <= 256:
+        if dtype == torch.bfloat16 and pitch == 16 and 1 <= C <= 16 and not want_grids and Z <= 256:
             # throughput form (bf16 volume mode): fp16 channel-last maps, half2 tap blending
             h, w = int(hms[0].shape[2]), int(hms[0].shape[3])
             if hms_f16 is None:
