@@ -299,13 +299,16 @@ def run_ours(args, rank, world, local_rank):
     ev = NCU_EVIDENCE.get("unproject", {})
     roofline_unproject = {"kernel": "sp3d_unproject_fwd (person cubes + root grid)", "bound": "hbm",
                           "achieved": unp_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                          "frac": unp_gbs / peaks["hbm_gbs"], "traffic": ev.get("dram_bytes_per_launch"),
+                          "frac": unp_gbs / peaks["hbm_gbs"],
+                          "achieved_physical_bytes": unp_gbs * (0.5 if args.volume_dtype == "bf16" else 1.0),
+                          "traffic": ev.get("dram_bytes_per_launch"),
                           "traffic_source": ev.get("source"), "peak_source": peaks["source"],
                           "launches_per_step": unp["launches"] / prof_steps,
                           "share_of_step": unp["ms"] / ms_prof if ms_prof > 0 else None,
-                          "note": "achieved = SURVEY 8(d) algorithmic bytes (float32 cubes written once + maps read "
-                                  "once) / time; the bf16 volume mode physically writes half of that; ncu shows the "
-                                  "kernel bound by L1 wavefronts / issue slots, not DRAM (DESIGN.md)"}
+                          "note": "achieved = SURVEY 8(d) algorithmic bytes (float32 cubes written once + float32 maps "
+                                  "read once) / time; the bf16 volume mode physically writes bf16 cubes, i.e. about "
+                                  "half of that (achieved_physical_bytes); ncu shows the kernel bound by instruction "
+                                  "issue / L1 wavefronts, not DRAM (DESIGN.md)"}
 
     cpu_frames = 5
     cpu_fps, cpu_spf = cpu_reference_frames_per_s(cpu_frames, 1, 1) if not args.no_cpu_baseline else (None, None)

@@ -156,7 +156,9 @@ def unproject(heatmaps, hm_strides, cams, centers, grid_size, cube_size, image_s
     a.hm_dtype = _DT[heatmaps[0].dtype]
     a.math_mode = int(bool(fast))
     n_vox = a.X * a.Y * a.Z
-    work = (a.view_end - a.view_begin) * a.B * a.C * a.h * a.w * 4 + a.n_cubes * a.C * n_vox * out.element_size()
+    # SURVEY 8(d) algorithmic bytes: every float32 heat-map read once + every float32 cube written once (the bf16
+    # volume mode physically moves half of the cube bytes; bench.py reports both)
+    work = (a.view_end - a.view_begin) * a.B * a.C * a.h * a.w * 4 + a.n_cubes * a.C * n_vox * 4
     _lib.call("sp3d_unproject_fwd", a, _stream(), kind="unproject", work=work)
 
 
