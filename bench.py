@@ -180,6 +180,8 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     _lib.load()
     ops.set_volume_dtype(torch.bfloat16 if args.volume_dtype == "bf16" else torch.float32)
+    if args.volume_dtype in ("f32x3", "f32x6"):
+        ops.set_float32_conv("bf16x3" if args.volume_dtype == "f32x3" else "bf16x6")
     cfg = make_cfg(BATCH)
     model = multi_person_posenet_ssv.get_multi_person_pose_net(cfg, is_train=False)
     model.load_state_dict(synthetic.trained_like_state_dict(model, seed=0), strict=True)
@@ -310,14 +312,42 @@ def run_ours(args, rank, world, local_rank):
                                   "half of that (achieved_physical_bytes); ncu shows the kernel bound by instruction "
                                   "issue / L1 wavefronts, not DRAM (DESIGN.md)"}
 
+    # the float32-faithful tensor-core mode (float32 activations, operands split into bf16 terms, SP3D_CONV_TC_BF16X3)
+    # timed beside the bf16 throughput mode on the same resident batch: N = 1 only, a few steps, never fatal
+    f32_faithful = None
+    if world == 1 and args.volume_dtype == "bf16" and not args.no_f32_faithful:
+        f32_faithful = {}
+        for mode in ("bf16x3", "bf16x6"):
+            try:
+                ops.set_volume_dtype(torch.float32)
+                ops.set_float32_conv(mode)
+                for _ in range(2):
+                    step_resident()
+                n = min(args.steps, 5)
+                ms_f, launches_f, _, _ = timed(step_resident, n)
+                f32_faithful[mode] = {"value": BATCH * n / (ms_f * 1e-3), "unit": "frames/s", "ms_per_step": ms_f / n,
+                                      "steps": n, "gpu_launches": launches_f}
+            except Exception as exc:   # noqa: BLE001 -- a side measurement must not take the bench line down
+                f32_faithful[mode] = {"error": repr(exc)[:300]}
+            finally:
+                ops.set_float32_conv("simt")
+                ops.set_volume_dtype(torch.bfloat16)
+        f32_faithful["note"] = ("float32 activations / weights as sums of 2 (bf16x3) or 3 (bf16x6) bf16 terms on the same "
+                                "tcgen05 kernel, float32 accumulation; accuracy: tests/test_gpu_split.py")
+
     cpu_frames = 5
     cpu_fps, cpu_spf = cpu_reference_frames_per_s(cpu_frames, 1, 1) if not args.no_cpu_baseline else (None, None)
     line = {
         "metric": "frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if args.volume_dtype == "bf16" else "f32",
-        "dtype_detail": ("V2V 3-D convolutions: bf16 operands, float32 accumulation (tcgen05); backbone, un-projection "
-                         "geometry, NMS, soft-argmax: float32") if args.volume_dtype == "bf16" else "float32 everywhere",
+        "dtype_detail": {"bf16": "convolutions: bf16 operands, float32 accumulation (tcgen05); un-projection geometry, "
+                                 "NMS, soft-argmax: float32",
+                         "f32": "float32 everywhere (SIMT convolutions)",
+                         "f32x3": "float32 activations; convolutions on tcgen05 with operands split into 2 bf16 terms "
+                                  "(3 term pairs), float32 accumulation",
+                         "f32x6": "float32 activations; convolutions on tcgen05 with operands split into 3 bf16 terms "
+                                  "(6 term pairs), float32 accumulation"}[args.volume_dtype],
         "data": "synthetic", "config": workload_config(BATCH),
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
@@ -327,6 +357,7 @@ def run_ours(args, rank, world, local_rank):
         "roofline_conv_family": roofline_conv_family,
         "roofline_unproject": roofline_unproject,
         "kernel_ms_per_step": {k: v["ms"] / prof_steps for k, v in kernels.items()},
+        "f32_faithful": f32_faithful,
         "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                          "sample": "%d x 1 frame (5 views 3x384x288, 10 proposals) through oracle/pipeline.py on torch "
                                    "CPU (all host threads), 1 warm-up, %s s per frame"
@@ -342,9 +373,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--volume-dtype", default="bf16", choices=["f32", "bf16"],
+    ap.add_argument("--volume-dtype", default="bf16", choices=["f32", "bf16", "f32x3", "f32x6"],
                     help="voxel-cube / V2V activation dtype: bf16 = tcgen05 tensor-core convolutions with float32 "
-                         "accumulation, f32 = float32 SIMT convolutions (bit-faithful parity path)")
+                         "accumulation, f32 = float32 SIMT convolutions (bit-faithful parity path), f32x3 / f32x6 = "
+                         "float32 activations on the tcgen05 kernel through bf16 operand splitting")
+    ap.add_argument("--no-f32-faithful", action="store_true", help="skip the float32-faithful side measurement")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -161,7 +161,11 @@ int sp3d_softargmax3d_fwd(const sp3d_softargmax_args* a, void* stream);
  * lib/models/v2v_net.py:10-69,124 and conv2d/conv_transpose2d + batch_norm + relu of
  * lib/models/pose_resnet.py:58-93,102-124,161-207 (evaluation-mode BatchNorm folded into
  * scale/shift by the caller). */
-typedef enum { SP3D_CONV_SIMT_F32 = 0, SP3D_CONV_TC_BF16 = 1, SP3D_CONV_TC_TF32X3 = 2 } sp3d_conv_algo;
+typedef enum {
+  SP3D_CONV_SIMT_F32 = 0,   /* float32 FMA, any shape */
+  SP3D_CONV_TC_BF16 = 1,    /* tcgen05, bf16 operands, float32 accumulation */
+  SP3D_CONV_TC_BF16X3 = 2   /* tcgen05 on float32 data split into bf16 terms (split_terms below): float32-faithful */
+} sp3d_conv_algo;
 typedef struct {
   const void* in;           /* [N, D, H, W, cin_pitch] */
   const void* weight;       /* [ntaps, cin, cout_pitch_w] packed, taps ordered (kd, kh, kw) */
@@ -199,6 +203,17 @@ typedef struct {
                                to head->out [N, cout, 3].  Uses head->centers / lin_* / beta / out and
                                head->workspace of sp3d_conv_head_workspace() bytes; x / strides are ignored,
                                n_cubes, C, X, Y, Z must equal N, cout, OD, OH, OW; check_flag must be 0. */
+  int split_terms;          /* SP3D_CONV_TC_BF16X3 only: 3 or 6.  The float32 operands are used as sums of bf16 terms
+                               (x = x0 + x1 (+ x2), each term the bf16 rounding of what the previous ones left) and the
+                               product is accumulated in float32 over the term pairs
+                                 3: x1 w0 + x0 w1 + x0 w0                          (drops ~3 * 2^-18 per product)
+                                 6: x2 w0 + x1 w1 + x0 w2 + x1 w0 + x0 w1 + x0 w0   (drops ~2^-24 per product)
+                               as extra K blocks of ONE implicit GEMM, small products first (the tensor core's float32
+                               accumulator loses ~2^-24 of its magnitude per MMA, which bounds both variants: measured
+                               ~1e-5 of the output range per layer, tests/test_gpu_split.py).  `in` is the bf16 tensor
+                               sp3d_split_bf16 writes: S = 2 (3 pairs) or 3 (6 pairs) term planes [S][N, D, H, W, cin],
+                               cin_pitch = cin; `weight` is packed [n_tile][term pair][chunk][tap][N][chunk channels]
+                               with the matching weight term per pair.  The fused soft-argmax head is not available. */
 } sp3d_conv_args;
 int sp3d_conv_fwd(const sp3d_conv_args* a, void* stream);
 int64_t sp3d_conv_head_workspace(const sp3d_conv_args* a);
@@ -240,6 +255,18 @@ typedef struct {
   int dst_pitch;            /* >= 4 C, multiple of 8 */
 } sp3d_s2d_args;
 int sp3d_space_to_depth(const sp3d_s2d_args* a, void* stream);
+
+/* float32 channel-last activations [P, src_pitch] (C channels used) -> bf16 [S][P, c_block]: plane s holds term s
+ * of the bf16 expansion x = x0 + x1 (+ x2) (x0 = bf16(x), x1 = bf16(x - x0), x2 = bf16(x - x0 - x1)); channels
+ * [C, c_block) of every plane are zeros.  Input layout of SP3D_CONV_TC_BF16X3. */
+typedef struct {
+  const float* src; void* dst;
+  int64_t P;                /* positions */
+  int C, src_pitch;
+  int c_block;              /* channels per position in dst (multiple of 8, >= C) */
+  int S;                    /* 2 or 3 planes */
+} sp3d_split_args;
+int sp3d_split_bf16(const sp3d_split_args* a, void* stream);
 
 /* Stacks the x-neighbourhood of a 1-channel bf16 volume into channels:
  * dst[n, x, y, z, j] = src[n, x + j - pad, y, z, 0] (0 outside), j < taps; dst is [N, X, Y, Z, 16] bf16.

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libsp3d.so")
 MAX_VIEWS = 8
 CAM_FLOATS = 32
 F32, BF16, F16 = 0, 1, 2
-CONV_SIMT_F32, CONV_TC_BF16, CONV_TC_TF32X3 = 0, 1, 2
+CONV_SIMT_F32, CONV_TC_BF16, CONV_TC_BF16X3 = 0, 1, 2
 
 _i3 = C.c_int * 3
 
@@ -91,6 +91,7 @@ class ConvArgs(C.Structure):
         ("relu", C.c_int), ("algo", C.c_int), ("in_dtype", C.c_int), ("out_dtype", C.c_int),
         ("fused_phases", C.c_int), ("zfold", C.c_int),
         ("head_softargmax", C.POINTER(SoftargmaxArgs)),
+        ("split_terms", C.c_int),
     ]
 
 
@@ -109,6 +110,13 @@ class S2DArgs(C.Structure):
         ("src", C.c_void_p), ("dst", C.c_void_p), ("src_dtype", C.c_int),
         ("stride_n", C.c_int64), ("stride_c", C.c_int64), ("stride_y", C.c_int64), ("stride_x", C.c_int64),
         ("N", C.c_int), ("C", C.c_int), ("H", C.c_int), ("W", C.c_int), ("dst_pitch", C.c_int),
+    ]
+
+
+class SplitArgs(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("dst", C.c_void_p), ("P", C.c_int64),
+        ("C", C.c_int), ("src_pitch", C.c_int), ("c_block", C.c_int), ("S", C.c_int),
     ]
 
 
@@ -147,6 +155,7 @@ SYMBOLS = {
     "sp3d_layout_convert": (C.c_int, [C.POINTER(LayoutArgs), C.c_void_p]),
     "sp3d_space_to_depth": (C.c_int, [C.POINTER(S2DArgs), C.c_void_p]),
     "sp3d_stack_x_shifts": (C.c_int, [C.POINTER(StackArgs), C.c_void_p]),
+    "sp3d_split_bf16": (C.c_int, [C.POINTER(SplitArgs), C.c_void_p]),
 }
 
 _lib = None

@@ -57,7 +57,10 @@ struct TcConvParams {
   int n_outer;                   // leading (cube) dimension
   int bricks_x, bricks_y, bricks_z, n_bricks;
   int n_tiles;                   // tiles of N output channels
-  int n_chunks;                  // K chunks of (RB / 2) input channels
+  int n_chunks;                  // K chunks of (RB / 2) input channels (all K blocks of the split-operand mode)
+  int nc_block;                  // chunks per K block (= n_chunks unless the operands are split into bf16 terms)
+  uint32_t block_act;            // split-operand mode: nibble b = activation term plane read by K block b (plane t of
+                                 // cube n is outer index t * n_outer + n of the activation tensor map), else 0
   int istride[3];                // input step per output step (x, y, z)
   int origin[3];                 // input offset of tap 0 (x, y, z)
   int cout, cout_pitch;          // channels computed / distance between output positions (elements)
@@ -214,9 +217,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
         const uint32_t buf = u % HB;
         mbar_wait(&halo_empty[buf], ((u / HB) & 1) ^ 1);
         mbar_arrive_expect_tx(&halo_full[buf], C::kHaloBytes);
-        tma_load_5d(halo + buf * C::kHaloStride, &map_in, &halo_full[buf], c * (RB / 2),
+        // split-operand mode: K block kb = c / nc_block reads activation term plane (block_act >> 4 kb) & 15
+        const int kb = c / p.nc_block;
+        const int plane = (int)((p.block_act >> (4 * kb)) & 15u);
+        tma_load_5d(halo + buf * C::kHaloStride, &map_in, &halo_full[buf], (c - kb * p.nc_block) * (RB / 2),
                     z0 * p.istride[2] + p.origin[2], y0 * p.istride[1] + p.origin[1],
-                    x0 * p.istride[0] + p.origin[0], n);
+                    x0 * p.istride[0] + p.origin[0], plane * p.n_outer + n);
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -763,7 +769,16 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
   if (F > 1 && (a->zfold != F || a->W % F || a->OW % F || a->cin_pitch != chunk_ch || a->cout_pitch * F != N ||
                 a->fused_phases || a->stride[2] != 1 || a->ostride[2] != 1 || a->tap_off0[2] != -C::kPad))
     return SP3D_ERR_UNSUPPORTED;
-  const int n_chunks = (a->cin + chunk_ch - 1) / chunk_ch;
+  const int nc_block = (a->cin + chunk_ch - 1) / chunk_ch;
+  const bool split = a->algo == SP3D_CONV_TC_BF16X3;
+  // term pairs (activation term, weight term) per K block, small products first:
+  //   3 -> (1,0) (0,1) (0,0);   6 -> (2,0) (1,1) (0,2) (1,0) (0,1) (0,0)
+  const uint32_t block_act = !split ? 0u : (a->split_terms == 3 ? 0x001u : 0x001012u);
+  const int act_planes = !split ? 1 : (a->split_terms == 3 ? 2 : 3);
+  if (split && (a->head_softargmax != nullptr || (a->split_terms != 3 && a->split_terms != 6) || a->cin % chunk_ch ||
+                a->cin_pitch != a->cin))
+    return SP3D_ERR_UNSUPPORTED;
+  const int n_chunks = nc_block * (split ? a->split_terms : 1);
   const int n_tiles = a->fused_phases ? (8 * a->cout) / N : (F > 1 ? 1 : (a->cout + N - 1) / N);
 
   CUtensorMap map_in, map_w;
@@ -809,7 +824,9 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
     }
   }
   {  // activations: [N][D][H][W][cin_pitch] bf16; box = {chunk, HZ, HY, HX, 1} positions, stepped by the conv stride
-    cuuint64_t gdim[5] = {(cuuint64_t)a->cin_pitch * F, (cuuint64_t)a->W / F, (cuuint64_t)a->H, (cuuint64_t)a->D, (cuuint64_t)a->N};
+    // (split-operand mode: the term planes follow each other, plane t of cube n = outer index t * N + n)
+    cuuint64_t gdim[5] = {(cuuint64_t)a->cin_pitch * F, (cuuint64_t)a->W / F, (cuuint64_t)a->H, (cuuint64_t)a->D,
+                          (cuuint64_t)a->N * act_planes};
     cuuint64_t gstr[4] = {(cuuint64_t)a->cin_pitch * 2 * F, (cuuint64_t)a->cin_pitch * 2 * a->W,
                           (cuuint64_t)a->cin_pitch * 2 * a->W * a->H, (cuuint64_t)a->cin_pitch * 2 * a->W * a->H * a->D};
     cuuint32_t es[5] = {1, (cuuint32_t)a->stride[2], (cuuint32_t)a->stride[1], (cuuint32_t)a->stride[0], 1};
@@ -839,6 +856,8 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
   p.n_bricks = a->N * p.bricks_x * p.bricks_y * p.bricks_z;
   p.n_tiles = n_tiles;
   p.n_chunks = n_chunks;
+  p.nc_block = nc_block;
+  p.block_act = block_act;
   for (int d = 0; d < 3; ++d) {
     p.istride[d] = a->stride[d];
     p.origin[d] = a->tap_off0[d];
@@ -908,7 +927,7 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
 // Shapes taken by the tensor-core path.  `cin` is the padded channel count (a multiple of 16, or of 64 above 64),
 // `cout_pitch_w` the output-channel tile N the weights were packed for.
 int conv_tc(const sp3d_conv_args* a, cudaStream_t st) {
-  if (a->algo != SP3D_CONV_TC_BF16) return SP3D_ERR_UNSUPPORTED;   // TF32x3 variant: not built yet
+  if (a->algo != SP3D_CONV_TC_BF16 && a->algo != SP3D_CONV_TC_BF16X3) return SP3D_ERR_UNSUPPORTED;
   if (a->in_dtype != SP3D_BF16) return SP3D_ERR_UNSUPPORTED;
   if (a->out_dtype != SP3D_BF16 && a->out_dtype != SP3D_F32) return SP3D_ERR_UNSUPPORTED;
   if (a->fused_phases && (a->ksize[0] != 1 || a->ksize[1] != 1 || a->ksize[2] != 1 || a->ostride[0] != 2 ||

@@ -59,7 +59,7 @@ extern "C" int sp3d_conv_fwd(const sp3d_conv_args* a, void* stream) {
       if (a->head_softargmax != nullptr) return SP3D_ERR_UNSUPPORTED;
       return conv_simt_f32(a, st);
     case SP3D_CONV_TC_BF16:
-    case SP3D_CONV_TC_TF32X3: return conv_tc(a, st);
+    case SP3D_CONV_TC_BF16X3: return conv_tc(a, st);
     default: return SP3D_ERR_UNSUPPORTED;
   }
 }

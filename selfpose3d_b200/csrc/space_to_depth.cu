@@ -72,7 +72,56 @@ __global__ void stack_x_shifts_kernel(const sp3d_stack_args a) {
   }
 }
 
+// float32 -> sum of S bf16 terms, term s into plane s (the operand layout of the split-operand tensor-core
+// convolution).  One thread per (position, group of 8 channels): two 16-byte loads, S 16-byte stores.
+template <int S>
+__global__ void split_bf16_kernel(const sp3d_split_args a) {
+  const int groups = a.c_block / 8;
+  const int64_t total = a.P * groups;
+  const bool vec = (a.src_pitch % 4) == 0 && (reinterpret_cast<uintptr_t>(a.src) % 16) == 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const int64_t pos = i / groups;
+    const float* sp = a.src + pos * a.src_pitch + 8 * g;
+    float v[8];
+    if (vec && 8 * g + 8 <= a.C) {
+      const float4 lo = ldg4(sp), hi = ldg4(sp + 4);
+      v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+      v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (8 * g + j < a.C) ? __ldg(sp + j) : 0.0f;
+    }
+    __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(a.dst) + pos * a.c_block + 8 * g;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j] = __float2bfloat16_rn(v[j]);
+        v[j] = __fsub_rn(v[j], __bfloat162float(o[j]));   // exact: the remainder of a bf16 rounding fits float32
+      }
+      *reinterpret_cast<uint4*>(dp + (int64_t)s * a.P * a.c_block) = *reinterpret_cast<const uint4*>(o);
+    }
+  }
+}
+
 }  // namespace sp3d
+
+extern "C" int sp3d_split_bf16(const sp3d_split_args* a, void* stream) {
+  using namespace sp3d;
+  if (a == nullptr || a->src == nullptr || a->dst == nullptr || a->P < 0 || a->C < 1 || a->src_pitch < a->C ||
+      a->c_block < a->C || (a->c_block % 8) || (reinterpret_cast<uintptr_t>(a->dst) % 16))
+    return SP3D_ERR_INVALID_ARG;
+  if (a->S != 2 && a->S != 3) return SP3D_ERR_UNSUPPORTED;
+  const int64_t total = a->P * (a->c_block / 8);
+  if (total == 0) return SP3D_OK;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a->S == 2) split_bf16_kernel<2><<<blocks, 256, 0, st>>>(*a);
+  else split_bf16_kernel<3><<<blocks, 256, 0, st>>>(*a);
+  return check_launch();
+}
 
 extern "C" int sp3d_stack_x_shifts(const sp3d_stack_args* a, void* stream) {
   using namespace sp3d;

@@ -63,7 +63,9 @@ class PoseRegressionNet(nn.Module):
         if chunk is None:
             import os
             # bf16 activations of one 64^3 cube through V2VNet peak at ~0.2 GB (float32: ~0.4 GB)
-            chunk = int(os.environ.get("SP3D_CUBE_CHUNK", "80" if ops.volume_dtype() == torch.bfloat16 else "16"))
+            # (float32 activations on the split-operand tensor-core path: 40 cubes = ~20 GB incl. the bf16 term copies)
+            default = "80" if ops.volume_dtype() == torch.bfloat16 else ("16" if ops.float32_conv() == "simt" else "40")
+            chunk = int(os.environ.get("SP3D_CUBE_CHUNK", default))
         out = torch.empty(n, J, 3, device=centers.device, dtype=torch.float32)
         X, Y, Z = [int(s) for s in self.cube_size]
         bf16 = ops.volume_dtype() == torch.bfloat16

@@ -101,6 +101,23 @@ def volume_dtype():
     return _VOLUME_DTYPE
 
 
+# How float32 activations are convolved: "simt" (float32 FMA kernel, the bit-for-bit parity path), or "bf16x3" /
+# "bf16x6": the tcgen05 kernel on float32 data expanded into 2 / 3 bf16 terms (3 / 6 term pairs accumulated in
+# float32 as extra K blocks) -- float32-faithful results at tensor-core speed (SP3D_CONV_TC_BF16X3).
+_F32_CONV = "simt"
+
+
+def set_float32_conv(mode):
+    global _F32_CONV
+    if mode not in ("simt", "bf16x3", "bf16x6"):
+        raise ValueError('float32 convolution mode must be "simt", "bf16x3" or "bf16x6"')
+    _F32_CONV = mode
+
+
+def float32_conv():
+    return _F32_CONV
+
+
 def linspace_axes(grid_size, cube_size, device):
     """The three ``torch.linspace(-s/2, s/2, n)`` vectors of ``compute_grid``
     (``lib/models/project_layer.py:28-30``), evaluated once on the host and cached on ``device``."""
@@ -314,6 +331,47 @@ def stack_x_shifts(x, taps, pad):
     return out
 
 
+def split_bf16(x, channels, c_block, blocks):
+    """float32 channel-last ``[..., pitch]`` -> bf16 ``[blocks, ..., c_block]``: plane ``s`` holds term ``s`` of
+    the expansion ``x = x0 + x1 (+ x2)`` into bf16 values (``sp3d_split_bf16``)."""
+    _require_cuda(x)
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise _lib.Sp3dError("split_bf16 expects a contiguous float32 channel-last tensor")
+    out = torch.empty((blocks,) + tuple(x.shape[:-1]) + (c_block,), device=x.device, dtype=torch.bfloat16)
+    a = _lib.SplitArgs()
+    a.src, a.dst = x.data_ptr(), out.data_ptr()
+    a.P = x.numel() // int(x.shape[-1])
+    a.C, a.src_pitch, a.c_block, a.S = int(channels), int(x.shape[-1]), int(c_block), int(blocks)
+    _lib.call("sp3d_split_bf16", a, _stream(), kind="layout", work=a.P * (int(channels) * 4 + blocks * c_block * 2))
+    return out
+
+
+def bf16_terms(w, n):
+    """float32 tensor -> ``n`` float32 tensors of bf16-representable values with ``w ~= sum`` (each term is the
+    bf16 rounding of what the previous ones left; the host-side twin of ``sp3d_split_bf16``)."""
+    terms, rest = [], w.float()
+    for _ in range(n):
+        t = rest.to(torch.bfloat16).float()
+        terms.append(t)
+        rest = rest - t
+    return terms
+
+
+# (activation term, weight term) per K block of the split-operand convolution (include/sp3d.h, split_terms): the
+# small correction products are accumulated FIRST -- the tensor core's float32 accumulator loses ~2^-24 of its
+# current magnitude per MMA, so only the final x0 w0 chain should run on a full-size accumulator
+SPLIT_PAIRS = {3: ((1, 0), (0, 1), (0, 0)), 6: ((2, 0), (1, 1), (0, 2), (1, 0), (0, 1), (0, 0))}
+
+
+def _tc_finish(full, terms):
+    """float32 ``[n_tiles, n_chunks, taps, N, chunk]`` -> the bf16 tensor the kernel streams: as is (``terms`` 0), or
+    ``[n_tiles, K blocks, n_chunks, taps, N, chunk]`` with K block ``b`` = weight term of ``SPLIT_PAIRS[terms][b]``."""
+    if not terms:
+        return full.to(torch.bfloat16).contiguous()
+    wts = bf16_terms(full, max(wt for _, wt in SPLIT_PAIRS[terms]) + 1)
+    return torch.stack([wts[wt] for _, wt in SPLIT_PAIRS[terms]], 1).to(torch.bfloat16).contiguous()
+
+
 class S2DConv:
     """A stride-2 2-D convolution (3x3/p1 or 7x7/p3, + folded BatchNorm + ReLU) evaluated on the tcgen05 path as a
     stride-1 convolution over the 2x2 space-to-depth tensor: tap ``d`` with offset ``t = d - pad`` lands on
@@ -372,7 +430,7 @@ def _set3(field, vals):
 
 def conv_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksize, stride, tap_off0, tap_step,
                 ostride, ooffset, relu, algo=_lib.CONV_SIMT_F32, cin_real=None, cout_pitch_w=None, fused_phases=False,
-                zfold=0, head=None):
+                zfold=0, head=None, split_terms=0):
     """One implicit-GEMM convolution launch.  ``x`` / ``out`` are channel-last 5-D ``[N,D,H,W,pitch]``.
     ``head``: a ``SoftargmaxHead`` -- the output is consumed on chip by the fused soft-argmax (``out`` is then a
     shape-only placeholder: a ``torch.Size``-like tuple ``(N, D, H, W, pitch)``)."""
@@ -382,7 +440,8 @@ def conv_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksi
     # the argument struct of a (layer, shapes, launch geometry) is built once and re-used: only the three activation
     # pointers change between calls (filling ~40 ctypes fields costs more host time than a small kernel runs)
     key = (weight.data_ptr(), tuple(x.shape), x.dtype, tuple(out.shape), out.dtype, residual is not None,
-           tuple(out_grid), tuple(tap_off0), tuple(ostride), tuple(ooffset), int(algo), bool(fused_phases), int(zfold))
+           tuple(out_grid), tuple(tap_off0), tuple(ostride), tuple(ooffset), int(algo), bool(fused_phases), int(zfold),
+           int(split_terms))
     hit = _CONV_ARGS_CACHE.get(key)
     if hit is None:
         a = _lib.ConvArgs()
@@ -408,6 +467,7 @@ def conv_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksi
         a.in_dtype, a.out_dtype = _DT[x.dtype], _DT[out.dtype]
         a.fused_phases = int(bool(fused_phases))
         a.zfold = int(zfold)
+        a.split_terms = int(split_terms)
         flops = 2.0 * a.N * a.OD * a.OH * a.OW * a.cout * (cin_real or a.cin) * (a.ksize[0] * a.ksize[1] * a.ksize[2])
         if fused_phases:
             flops *= 8
@@ -598,27 +658,38 @@ class PackedConv:
             return k == [1, 3, 3] and s == [1, 1, 1] and p == [0, 1, 1]
         return False
 
-    def _tc_pack(self):
-        """bf16 weights ``[n_tiles, n_chunks, taps, N, chunk]`` (rows = output channel, K-major): N = output-channel
-        tile (cout padded to 16/32/64/128, or tiles of 128), chunk = min(cin padded to 16, 64) channels (= one
-        swizzled smem row).  Taps are ordered by ascending input offset (transposed sub-kernels are flipped)."""
-        if self._tc is None:
-            n = next((v for v in (16, 32, 64, 128) if v >= self.cout), 128)
+    # Weight packings of the tcgen05 path.  Each returns the bf16 tensor the kernel streams,
+    # [n_tiles, (K blocks,) n_chunks, taps, N, chunk] (rows = output channel, K-major); ``terms`` = 0 for bf16
+    # operands, 3 / 6 for float32 operands split into bf16 terms (one K block per term pair, ``_tc_finish``).
+    def _tc_cached(self, kind, terms, build):
+        cache = self.__dict__.setdefault("_tc_cache", {})
+        if (kind, terms) not in cache:
+            cache[(kind, terms)] = build()
+        return cache[(kind, terms)]
+
+    def _tc_dims(self):
+        """(N = output-channel tile, cin padded for the kernel, K chunk = channels of one swizzled smem row)."""
+        n = next((v for v in (16, 32, 64, 128) if v >= self.cout), 128)
+        cin_tc = round_up(self.cin, 16) if self.cin < 64 else round_up(self.cin, 64)
+        return n, cin_tc, min(cin_tc, 64)
+
+    def _tc_pack(self, terms=0):
+        """One tensor per sub-kernel (transposed-convolution phase): N = cout padded to 16/32/64/128, or tiles of
+        128.  Taps are ordered by ascending input offset (transposed sub-kernels are flipped)."""
+        def build():
+            n, cin_tc, chunk = self._tc_dims()
             n_tiles = -(-self.cout // n)
-            cin_tc = round_up(self.cin, 16) if self.cin < 64 else round_up(self.cin, 64)
-            chunk = min(cin_tc, 64)
             packs = []
             for sub in self._subs:
                 if self.transposed:
                     sub = sub.flip(2, 3, 4)
                 taps = int(sub.shape[2] * sub.shape[3] * sub.shape[4])
-                t = sub.permute(2, 3, 4, 0, 1).reshape(taps, self.cout, self.cin)
                 full = torch.zeros(taps, n_tiles * n, cin_tc, device=sub.device, dtype=torch.float32)
-                full[:, :self.cout, :self.cin] = t
+                full[:, :self.cout, :self.cin] = sub.permute(2, 3, 4, 0, 1).reshape(taps, self.cout, self.cin)
                 full = full.reshape(taps, n_tiles, n, cin_tc // chunk, chunk).permute(1, 3, 0, 2, 4)
-                packs.append(full.to(torch.bfloat16).contiguous())
-            self._tc = (packs, n, cin_tc)
-        return self._tc
+                packs.append(_tc_finish(full, terms))
+            return packs, n, cin_tc
+        return self._tc_cached("plain", terms, build)
 
     ZFOLD = 2
 
@@ -635,10 +706,10 @@ class PackedConv:
             return self.cin in (16, 32) and self.cout == 32 and out_pitch == 32 and w_extent % 16 == 0
         return False
 
-    def _tc_pack_zfold(self):
-        """bf16 ``[1, 1, kd*kh*(k+F-1), F*cout_p, cin_p]``: per (kd, kh) the k+F-1 windows e, rows (ro, co), tap
-        kw = e - ro (zero rows where that falls outside the kernel)."""
-        if getattr(self, "_tc_zf", None) is None:
+    def _tc_pack_zfold(self, terms=0):
+        """``[1, (K blocks,) 1, kd*kh*(k+F-1), F*cout_p, cin_p]``: per (kd, kh) the k+F-1 windows e, rows (ro, co),
+        tap kw = e - ro (zero rows where that falls outside the kernel)."""
+        def build():
             F, k = self.ZFOLD, self.k[2]
             cin_p, cout_p = round_up(self.cin, 16), round_up(self.cout, 16)
             w5 = self._subs[0]                                     # [Cout, Cin, kd, kh, kw]
@@ -648,8 +719,8 @@ class PackedConv:
                     kw = e - ro
                     if 0 <= kw < k:
                         full[:, :, e, ro, :self.cout, :self.cin] = w5[:, :, :, :, kw].permute(2, 3, 0, 1)
-            self._tc_zf = full.reshape(1, 1, -1, F * cout_p, cin_p).to(torch.bfloat16).contiguous()
-        return self._tc_zf
+            return _tc_finish(full.reshape(1, 1, -1, F * cout_p, cin_p), terms)
+        return self._tc_cached("zfold", terms, build)
 
     def _tc_stack_ok(self, w_extent, out_pitch):
         """The root net's 1 -> 16 channel 7^3 stem: x taps stacked into channels (1 x 7 x 7 over 7 tap channels)."""
@@ -657,9 +728,9 @@ class PackedConv:
                 and self.padding == [3, 3, 3] and self.cin == 1 and self.cout == 16 and out_pitch == 16
                 and w_extent % self.ZFOLD == 0)
 
-    def _tc_pack_stack(self):
-        """bf16 ``[1, 1, kh*(k+F-1), F*16, 16]``: K index j = x tap, per kh the k+F-1 z-windows, rows (ro, co)."""
-        if getattr(self, "_tc_st", None) is None:
+    def _tc_pack_stack(self, terms=0):
+        """``[1, (K blocks,) 1, kh*(k+F-1), F*16, 16]``: K index j = x tap, per kh the k+F-1 z-windows, rows (ro, co)."""
+        def build():
             F, k = self.ZFOLD, 7
             w5 = self._subs[0]                                     # [Cout, 1, kd, kh, kw]
             full = torch.zeros(k, k + F - 1, F, 16, 16, device=w5.device, dtype=torch.float32)
@@ -668,8 +739,8 @@ class PackedConv:
                     kw = e - ro
                     if 0 <= kw < k:
                         full[:, e, ro, :self.cout, :k] = w5[:, 0, :, :, kw].permute(2, 0, 1)   # [kh, co, kd]
-            self._tc_st = full.reshape(1, 1, -1, F * 16, 16).to(torch.bfloat16).contiguous()
-        return self._tc_st
+            return _tc_finish(full.reshape(1, 1, -1, F * 16, 16), terms)
+        return self._tc_cached("stack", terms, build)
 
     def _tc_fused_ok(self, out_pitch, out_dtype):
         """k2/s2 transposed 3-D convolution as ONE launch (all 8 output phases are extra GEMM columns)."""
@@ -677,29 +748,45 @@ class PackedConv:
         return (self.transposed and self.nd == 3 and self.k == [2, 2, 2] and (8 * self.cout) % 128 == 0
                 and out_pitch == self.cout and (2 * self.cout * esz) % 128 == 0)
 
-    def _tc_pack_fused(self):
-        """bf16 ``[n_tiles, n_chunks, 1, 128, chunk]``: GEMM rows ordered (px, py, pz, co)."""
-        if getattr(self, "_tc_fused", None) is None:
+    def _tc_pack_fused(self, terms=0):
+        """``[n_tiles, (K blocks,) n_chunks, 1, 128, chunk]``: GEMM rows ordered (px, py, pz, co)."""
+        def build():
             w = torch.stack([sub.reshape(self.cout, self.cin) for sub in self._subs], 0)   # [8 phases (pd,ph,pw), Cout, Cin]
-            cin_tc = round_up(self.cin, 16) if self.cin < 64 else round_up(self.cin, 64)
-            chunk = min(cin_tc, 64)
+            _, cin_tc, chunk = self._tc_dims()
             full = torch.zeros(8 * self.cout, cin_tc, device=w.device, dtype=torch.float32)
             full[:, :self.cin] = w.reshape(8 * self.cout, self.cin)
             n_tiles = 8 * self.cout // 128
             full = full.reshape(n_tiles, 128, cin_tc // chunk, chunk).permute(0, 2, 1, 3).unsqueeze(2)
-            self._tc_fused = (full.to(torch.bfloat16).contiguous(), cin_tc)
-        return self._tc_fused
+            return _tc_finish(full, terms)
+        return self._tc_cached("fused", terms, build)
 
-    def _call_tc(self, x, residual, out_pitch, out_dtype, head=None):
+    def _call_tc(self, x, residual, out_pitch, out_dtype, head=None, terms=0):
+        """tcgen05 path.  ``terms`` = 0: ``x`` is bf16 channel-last.  ``terms`` = 3 / 6 (SP3D_CONV_TC_BF16X3): ``x`` is
+        float32 channel-last; it is expanded into bf16 term planes (``split_bf16``) that the kernel multiplies with the
+        matching weight terms as extra K blocks of the same implicit GEMM; output and residual are float32."""
         if not self.tc_supported():
             raise _lib.Sp3dError("convolution shape not covered by the tensor-core path")
-        packs, n, cin_tc = self._tc_pack()
+        packs, n, cin_tc = self._tc_pack(terms)
         N, D, H, W, pitch = [int(v) for v in x.shape]
-        if pitch < cin_tc or pitch % 8:
-            raise _lib.Sp3dError("bf16 activation pitch %d incompatible with packed cin %d" % (pitch, cin_tc))
         o = self.out_shape((D, H, W))
-        out_dtype = torch.bfloat16 if out_dtype is None else out_dtype
-        out_pitch = round_up(self.cout, 16) if out_pitch is None else int(out_pitch)
+        if terms:
+            if head is not None or out_dtype not in (None, torch.float32) or x.dtype != torch.float32:
+                raise _lib.Sp3dError("the split-operand mode takes float32 activations, writes float32 and has no fused head")
+            if pitch < self.cin:
+                raise _lib.Sp3dError("activation pitch %d smaller than the input channel count %d" % (pitch, self.cin))
+            out_dtype = torch.float32
+            out_pitch = round_up(self.cout, 4) if out_pitch is None else int(out_pitch)
+            planes = 2 if terms == 3 else 3
+            x = split_bf16(x, self.cin, cin_tc, planes)          # [planes, N, D, H, W, cin_tc]
+            pitch = cin_tc
+            algo = _lib.CONV_TC_BF16X3
+        else:
+            if pitch < cin_tc or pitch % 8:
+                raise _lib.Sp3dError("bf16 activation pitch %d incompatible with packed cin %d" % (pitch, cin_tc))
+            out_dtype = torch.bfloat16 if out_dtype is None else out_dtype
+            out_pitch = round_up(self.cout, 16) if out_pitch is None else int(out_pitch)
+            planes = 0
+            algo = _lib.CONV_TC_BF16
         if head is not None:      # fused soft-argmax head: the volume is never materialised
             if self.k != [1, 1, 1] or self.transposed or self.nd != 3 or residual is not None or self.cout > 15:
                 raise _lib.Sp3dError("the fused soft-argmax head needs a 1x1x1 convolution with at most 15 output channels")
@@ -709,36 +796,39 @@ class PackedConv:
         out = torch.empty((N, o[0], o[1], o[2], out_pitch), device=x.device, dtype=out_dtype)
         if residual is not None and (residual.dtype != out_dtype or residual.shape != out.shape):
             raise _lib.Sp3dError("residual must match the output dtype and shape")
-        xk, outk, resk = x, out, residual
-        if self.nd == 2:   # image batch -> the brick's x axis: [N,1,H,W,C] viewed as [1,N,H,W,C]
-            xk = x.view(1, N, H, W, pitch)
+        # kernel view of the activations: [N, D, H, W, pitch] (split mode: plane 0; the kernel steps over the planes
+        # through the outer index).  2-D: image batch -> the brick's x axis, [N,1,H,W,C] viewed as [1,N,H,W,C]
+        outk, resk = out, residual
+        if self.nd == 2:
+            xk = x.view(planes, 1, N, H, W, pitch)[0] if planes else x.view(1, N, H, W, pitch)
             outk = out.view(1, N, o[1], o[2], out_pitch)
             resk = residual.view(1, N, o[1], o[2], out_pitch) if residual is not None else None
             D, o = N, [N, o[1], o[2]]
+        else:
+            xk = x[0] if planes else x
+        kw = dict(algo=algo, split_terms=terms)
         if pitch == 16 and residual is None and self._tc_stack_ok(W, out_pitch):
-            xs = stack_x_shifts(xk, 7, 3)
-            conv_launch(xs, self._tc_pack_stack(), self.scale, self.shift, None, outk, 16, self.cout, o, [1, 7, 7],
-                        self.stride, [0, -3, -3], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu, _lib.CONV_TC_BF16,
-                        cin_real=7, cout_pitch_w=16 * self.ZFOLD, zfold=self.ZFOLD)
+            xs = stack_x_shifts(x.view(-1, D, H, W, pitch), 7, 3)       # every plane: [planes * N, ...]
+            conv_launch(xs[:N], self._tc_pack_stack(terms), self.scale, self.shift, None, outk, 16, self.cout, o, [1, 7, 7],
+                        self.stride, [0, -3, -3], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu,
+                        cin_real=7, cout_pitch_w=16 * self.ZFOLD, zfold=self.ZFOLD, **kw)
         elif not self.transposed and pitch == round_up(self.cin, 16) and self._tc_zfold_ok(W, out_pitch):
-            conv_launch(xk, self._tc_pack_zfold(), self.scale, self.shift, resk, outk, pitch, self.cout, o, self.k,
+            conv_launch(xk, self._tc_pack_zfold(terms), self.scale, self.shift, resk, outk, pitch, self.cout, o, self.k,
                         self.stride, [-p for p in self.padding], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu,
-                        _lib.CONV_TC_BF16, cin_real=self.cin, cout_pitch_w=out_pitch * self.ZFOLD, zfold=self.ZFOLD)
+                        cin_real=self.cin, cout_pitch_w=out_pitch * self.ZFOLD, zfold=self.ZFOLD, **kw)
         elif not self.transposed:
             conv_launch(xk, packs[0], self.scale, self.shift, resk, outk, cin_tc, self.cout, o, self.k, self.stride,
-                        [-p for p in self.padding], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu, _lib.CONV_TC_BF16,
-                        cin_real=self.cin, cout_pitch_w=n)
+                        [-p for p in self.padding], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu,
+                        cin_real=self.cin, cout_pitch_w=n, **kw)
         elif self._tc_fused_ok(out_pitch, out_dtype):
-            wgt, _ = self._tc_pack_fused()
-            conv_launch(xk, wgt, self.scale, self.shift, resk, outk, cin_tc, self.cout, (D, H, W), [1, 1, 1], [1, 1, 1],
-                        [0, 0, 0], [1, 1, 1], self.stride, [0, 0, 0], self.relu, _lib.CONV_TC_BF16, cin_real=self.cin,
-                        cout_pitch_w=128, fused_phases=True)
+            conv_launch(xk, self._tc_pack_fused(terms), self.scale, self.shift, resk, outk, cin_tc, self.cout, (D, H, W),
+                        [1, 1, 1], [1, 1, 1], [0, 0, 0], [1, 1, 1], self.stride, [0, 0, 0], self.relu, cin_real=self.cin,
+                        cout_pitch_w=128, fused_phases=True, **kw)
         else:
             for wgt, (phase, off0, ks) in zip(packs, self.phases):
                 origin = [off0[i] - (ks[i] - 1) for i in range(3)]     # taps ascend from the lowest input offset
                 conv_launch(xk, wgt, self.scale, self.shift, resk, outk, cin_tc, self.cout, (D, H, W), ks, [1, 1, 1],
-                            origin, [1, 1, 1], self.stride, phase, self.relu, _lib.CONV_TC_BF16, cin_real=self.cin,
-                            cout_pitch_w=n)
+                            origin, [1, 1, 1], self.stride, phase, self.relu, cin_real=self.cin, cout_pitch_w=n, **kw)
         return out
 
     def __call__(self, x, residual=None, out_pitch=None, algo=None, out_dtype=None, head=None):
@@ -746,9 +836,17 @@ class PackedConv:
         activations the tcgen05 kernel where the shape is covered (``out_dtype`` float32 there gives a float32
         result), else the SIMT kernel with bf16 storage and float32 math."""
         if algo is None:
-            algo = _lib.CONV_TC_BF16 if (x.dtype == torch.bfloat16 and self.tc_supported()) else _lib.CONV_SIMT_F32
+            if x.dtype == torch.bfloat16 and self.tc_supported():
+                algo = _lib.CONV_TC_BF16
+            elif (x.dtype == torch.float32 and _F32_CONV != "simt" and head is None and self.tc_supported()
+                  and out_dtype in (None, torch.float32)):
+                algo = _lib.CONV_TC_BF16X3
+            else:
+                algo = _lib.CONV_SIMT_F32
         if algo == _lib.CONV_TC_BF16:
             return self._call_tc(x, residual, out_pitch, out_dtype, head=head)
+        if algo == _lib.CONV_TC_BF16X3:
+            return self._call_tc(x, residual, out_pitch, out_dtype, terms=6 if _F32_CONV == "bf16x6" else 3)
         if head is not None:
             raise _lib.Sp3dError("the fused soft-argmax head exists on the tensor-core path only")
         N, D, H, W, pitch = [int(v) for v in x.shape]

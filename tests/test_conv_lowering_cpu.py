@@ -130,7 +130,7 @@ def test_output_pitch_one_and_padding_lanes_zero():
 # ---------------------------------------------------------------------------------------------- tcgen05 packing
 def emulate_any_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksize, stride, tap_off0,
                        tap_step, ostride, ooffset, relu, algo=0, cin_real=None, cout_pitch_w=None, fused_phases=False,
-                       zfold=0):
+                       zfold=0, split_terms=0):
     """Dispatch on the packing: the tensor-core launch carries [n_tiles, n_chunks, taps, N, chunk] bf16 weights;
     `fused_phases` and `zfold` follow the sp3d_conv_args field descriptions in include/sp3d.h."""
     res = None if residual is None else residual.float()
@@ -272,3 +272,93 @@ def test_tensorcore_lowering(monkeypatch, case):
         pc = ops.PackedConv(ct.weight, ct.bias, bn, 2, 0, transposed=True, relu=2)
         got = cf(pc(cl16(x), out_dtype=torch.float32), 64, 3)
     torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------- split-operand mode
+def emulate_split_bf16(x, channels, c_block, blocks):
+    """include/sp3d.h, sp3d_split_args: plane s = term s of the bf16 expansion, channels >= C zero."""
+    out = torch.zeros((blocks,) + tuple(x.shape[:-1]) + (c_block,))
+    for s, t in enumerate(ops.bf16_terms(x[..., :channels], blocks)):
+        out[s, ..., :channels] = t
+    return out.to(torch.bfloat16)
+
+
+def emulate_split_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksize, stride, tap_off0,
+                         tap_step, ostride, ooffset, relu, algo=0, cin_real=None, cout_pitch_w=None,
+                         fused_phases=False, zfold=0, split_terms=0):
+    """SP3D_CONV_TC_BF16X3 (include/sp3d.h, split_terms): `x` is plane 0 of the term planes [S][N,D,H,W,cin]; K block
+    b multiplies activation plane SPLIT_PAIRS[b][0] with weight block b, all blocks accumulate into one GEMM -- i.e.
+    the plain tensor-core launch on the K-concatenated operands."""
+    assert algo == 2 and split_terms in (3, 6)
+    pairs = ops.SPLIT_PAIRS[split_terms]
+    nt, kb, nc, taps, n, chunk = weight.shape
+    assert kb == len(pairs) and cin == nc * chunk and x.shape[-1] == cin
+    planes = torch.as_strided(x, (max(a for a, _ in pairs) + 1,) + tuple(x.shape), (x.numel(),) + tuple(x.stride()),
+                              x.storage_offset())
+    xcat = torch.cat([planes[a] for a, _ in pairs], -1)
+    emulate_any_launch(xcat, weight.reshape(nt, kb * nc, taps, n, chunk), scale, shift, residual, out, kb * cin, cout,
+                       out_grid, ksize, stride, tap_off0, tap_step, ostride, ooffset, relu, algo=1,
+                       cout_pitch_w=cout_pitch_w, fused_phases=fused_phases, zfold=zfold)
+
+
+def emulate_stack_planes(x, taps, pad):
+    return emulate_stack_x_shifts(x, taps, pad)
+
+
+@pytest.mark.parametrize("terms,tol", [(3, 4e-5), (6, 2e-6)])
+@pytest.mark.parametrize("case", ["3d_k3_res", "3d_k3_zfold", "3d_k7_zfold", "3d_k7_stack", "3d_convT_fused", "2d_1x1s2",
+                                  "2d_deconv"])
+def test_split_operand_lowering(monkeypatch, case, terms, tol):
+    """float32 activations / weights through the tensor-core packings (plain, z-folded, tap-stacked, fused transposed,
+    per-phase transposed) as sums of bf16 terms: the result must be float32-faithful (3 term pairs: ~2^-16; 6:
+    float32 rounding level) for un-rounded operands."""
+    monkeypatch.setattr(ops, "conv_launch", emulate_split_launch)
+    monkeypatch.setattr(ops, "split_bf16", emulate_split_bf16)
+    monkeypatch.setattr(ops, "stack_x_shifts", emulate_stack_planes)
+    monkeypatch.setattr(ops, "_F32_CONV", "bf16x3" if terms == 3 else "bf16x6")
+    torch.manual_seed(5)
+    res = None
+    if case == "3d_k3_res":
+        conv, bn = nn.Conv3d(32, 64, 3, 1, 1), rand_bn(nn.BatchNorm3d(64))
+        x, res = torch.randn(1, 32, 4, 5, 6), torch.randn(1, 64, 4, 5, 6)
+        want = F.relu(bn.double()(conv.double()(x.double())) + res.double())
+        pc = ops.PackedConv(conv.float().weight, conv.bias, bn.float(), 1, 1, relu=1)
+        nd, cout = 3, 64
+    elif case == "3d_k3_zfold":
+        conv, bn = nn.Conv3d(16, 32, 3, 1, 1), rand_bn(nn.BatchNorm3d(32))
+        x, res = torch.randn(1, 16, 3, 4, 16), torch.randn(1, 32, 3, 4, 16)
+        want = F.relu(bn.double()(conv.double()(x.double())) + res.double())
+        pc = ops.PackedConv(conv.float().weight, conv.bias, bn.float(), 1, 1, relu=1)
+        assert pc._tc_zfold_ok(16, 32)
+        nd, cout = 3, 32
+    elif case in ("3d_k7_zfold", "3d_k7_stack"):
+        cin = 15 if case == "3d_k7_zfold" else 1
+        conv, bn = nn.Conv3d(cin, 16, 7, 1, 3), rand_bn(nn.BatchNorm3d(16))
+        x = torch.rand(1, cin, 4, 8, 6)
+        want = F.relu(bn.double()(conv.double()(x.double())))
+        pc = ops.PackedConv(conv.float().weight, conv.bias, bn.float(), 1, 3, relu=1)
+        assert pc._tc_zfold_ok(6, 16) if cin == 15 else pc._tc_stack_ok(6, 16)
+        nd, cout = 3, 16
+    elif case == "3d_convT_fused":
+        ct, bn = nn.ConvTranspose3d(128, 64, 2, 2), rand_bn(nn.BatchNorm3d(64))
+        x, res = torch.randn(1, 128, 3, 2, 4), torch.randn(1, 64, 6, 4, 8)
+        want = F.relu(bn.double()(ct.double()(x.double()))) + res.double()
+        pc = ops.PackedConv(ct.float().weight, ct.bias, bn.float(), 2, 0, transposed=True, relu=2)
+        assert pc._tc_fused_ok(64, torch.float32)
+        nd, cout = 3, 64
+    elif case == "2d_1x1s2":
+        conv, bn = nn.Conv2d(64, 256, 1, 2, 0, bias=False), rand_bn(nn.BatchNorm2d(256))
+        x = torch.randn(3, 64, 9, 7)
+        want = bn.double()(conv.double()(x.double()))
+        pc = ops.PackedConv(conv.float().weight, None, bn.float(), 2, 0, relu=0)
+        nd, cout = 2, 256
+    else:
+        ct, bn = nn.ConvTranspose2d(64, 256, 4, 2, 1, bias=False), rand_bn(nn.BatchNorm2d(256))
+        x = torch.randn(2, 64, 5, 3)
+        want = F.relu(bn.double()(ct.double()(x.double())))
+        pc = ops.PackedConv(ct.float().weight, None, bn.float(), 2, 1, transposed=True, relu=1)
+        nd, cout = 2, 256
+    assert pc.tc_supported()
+    got = cf(pc(cl(x), residual=None if res is None else cl(res)), cout, nd).double()
+    err = float((got - want).abs().max()) / float(want.abs().max())
+    assert err <= tol, err
