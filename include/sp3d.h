@@ -280,6 +280,98 @@ typedef struct {
 } sp3d_stack_args;
 int sp3d_stack_x_shifts(const sp3d_stack_args* a, void* stream);
 
+/* ==========================================================================================
+ * Backward operators (unproject_bwd, softargmax3d_bwd, maxpool bwd, conv wgrad, bn stats /
+ * apply / bwd).  float32, channel-last unless strides say otherwise.  They replace what torch.autograd runs for the
+ * reference's training forward/backward through the same path (lib/models/multi_person_posenet_ssv.py:222-501 calls
+ * the modules below under autograd).  The input gradient of a convolution (dgrad) is sp3d_conv_fwd itself on the
+ * flipped / transposed weight (host-side packing, selfpose3d_b200/ops.py conv_dgrad).
+ * ========================================================================================== */
+
+/* Gradient of sp3d_unproject_fwd (math_mode 0, partial 0) with respect to the heat-maps: the adjoint of
+ * F.grid_sample(bilinear, zeros, align_corners=True) + masked mean + NaN->0 + clamp(0,1) of
+ * lib/models/project_layer.py:93-99 (voxel coordinates carry no gradient: grid centres are detached,
+ * lib/models/cuboid_proposal_net_soft.py:57).  The clamp gate (0 <= r <= 1, not NaN) is re-evaluated from the
+ * forward inputs. */
+typedef struct {
+  sp3d_unproject_args fwd;  /* the forward call's arguments; fwd.cubes / fwd.out_dtype / fwd.grids are not used */
+  const float* grad_cubes;  /* dL/dcubes, float32, addressed through fwd.out_stride_{cube,c,vox} */
+  float* grad_heatmaps[SP3D_MAX_VIEWS]; /* dL/dheatmaps per view, addressed through fwd.hm_stride_*;
+                                           ACCUMULATED into (atomic adds): the caller zeroes them */
+} sp3d_unproject_bwd_args;
+int sp3d_unproject_bwd(const sp3d_unproject_bwd_args* a, void* stream);
+
+/* Gradient of sp3d_softargmax3d_fwd with respect to x: dx_v = beta * p_v * sum_d (g_vd - out_d) * grad_out_d,
+ * p = softmax(beta * x) (autograd of lib/models/pose_regression_net.py:22-27). */
+typedef struct {
+  sp3d_softargmax_args fwd; /* forward arguments (x float32; fwd.out = the forward RESULT [n_cubes, C, 3];
+                               workspace unused) */
+  const float* grad_out;    /* [n_cubes, C, 3] */
+  float* grad_x;            /* float32, addressed like fwd.x; written (cubes skipped by check_flag get zeros) */
+} sp3d_softargmax_bwd_args;
+int sp3d_softargmax3d_bwd(const sp3d_softargmax_bwd_args* a, void* stream);
+
+/* Gradient of sp3d_maxpool_fwd (float32): each window's gradient goes to its first maximum in (d, h, w) scan
+ * order, as ATen's max_pool backward does (F.max_pool3d of lib/models/v2v_net.py:54, nn.MaxPool2d of
+ * lib/models/pose_resnet.py:105). */
+typedef struct {
+  sp3d_maxpool_args fwd;    /* forward arguments, dtype SP3D_F32; fwd.in = the forward input, fwd.out unused */
+  const float* grad_out;    /* [N, OD, OH, OW, c_pitch] */
+  float* grad_in;           /* [N, D, H, W, c_pitch]; overwritten (zero-filled, then scattered into) */
+} sp3d_maxpool_bwd_args;
+int sp3d_maxpool_bwd(const sp3d_maxpool_bwd_args* a, void* stream);
+
+/* Weight (and bias) gradient of one sp3d_conv_fwd launch (float32 SIMT geometry, no scale/shift/activation:
+ * grad_out is the gradient of the raw convolution result):
+ *   grad_weight[t, ci, co] += sum_{n, o} in[n, o*stride + tap_off0 + t*tap_step, ci] * grad_out[n, o*ostride+ooffset, co]
+ *   grad_bias[co]          += sum_{n, o} grad_out[n, o*ostride+ooffset, co]
+ * Replaces cudnn's convolution backward-filter for nn.Conv{2,3}d / nn.ConvTranspose{2,3}d (one call per output
+ * phase for the transposed ones, exactly as the forward). */
+typedef struct {
+  sp3d_conv_args fwd;       /* geometry of the forward launch; fwd.in = the forward input (float32);
+                               weight / scale / shift / residual / out / relu / algo are not used */
+  const float* grad_out;    /* [N, TD, TH, TW, cout_pitch] */
+  float* grad_weight;       /* [ntaps, cin, cout_pitch_w], packed like the SIMT forward weight; ACCUMULATED into */
+  float* grad_bias;         /* optional [cout]; ACCUMULATED into */
+} sp3d_conv_wgrad_args;
+int sp3d_conv_wgrad(const sp3d_conv_wgrad_args* a, void* stream);
+
+/* Training-mode BatchNorm on channel-last activations x [P, pitch] (P = all positions of the batch):
+ *   sp3d_bn_stats: mean[c], var[c] (biased, the normalisation's variance) over P -- F.batch_norm(training=True) of
+ *                  nn.BatchNorm{2,3}d (lib/models/v2v_net.py:14,27,30, lib/models/pose_resnet.py:49-...);
+ *   sp3d_bn_apply: y = act(x * scale[c] + shift[c] (+ residual)), relu as in sp3d_conv_args (0 / 1 / 2);
+ *   sp3d_bn_bwd:   with xhat = (x - mean) * rsqrt(var + eps) and dz = grad_y masked by (y > 0) when `y` is given
+ *                  (ReLU directly after the normalisation):
+ *                    dgamma = sum dz * xhat,  dbeta = sum dz,
+ *                    dx = gamma * rsqrt(var + eps) * (dz - dbeta / P - xhat * dgamma / P). */
+typedef struct {
+  const float* x; int64_t P; int C, pitch;
+  float* mean; float* var;  /* [C] outputs */
+  double* workspace;        /* 2 * C doubles */
+  int64_t workspace_bytes;
+} sp3d_bn_stats_args;
+int sp3d_bn_stats(const sp3d_bn_stats_args* a, void* stream);
+
+typedef struct {
+  const float* x; const float* residual; float* y;   /* [P, pitch]; residual optional */
+  int64_t P; int C, pitch;
+  const float* scale; const float* shift;            /* [C] */
+  int relu;
+} sp3d_bn_apply_args;
+int sp3d_bn_apply(const sp3d_bn_apply_args* a, void* stream);
+
+typedef struct {
+  const float* x; const float* grad_y; const float* y;   /* [P, pitch]; y optional (ReLU mask) */
+  int64_t P; int C, pitch;
+  const float* mean; const float* var; const float* gamma;   /* [C]; gamma NULL = 1 */
+  float eps;
+  float* grad_x;            /* [P, pitch], written; padding channels get zeros */
+  float* grad_gamma; float* grad_beta;   /* [C], written */
+  double* workspace;        /* 2 * C doubles */
+  int64_t workspace_bytes;
+} sp3d_bn_bwd_args;
+int sp3d_bn_bwd(const sp3d_bn_bwd_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

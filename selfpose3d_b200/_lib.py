@@ -136,6 +136,41 @@ class LayoutArgs(C.Structure):
     ]
 
 
+class UnprojectBwdArgs(C.Structure):
+    _fields_ = [("fwd", UnprojectArgs), ("grad_cubes", C.c_void_p), ("grad_heatmaps", C.c_void_p * MAX_VIEWS)]
+
+
+class SoftargmaxBwdArgs(C.Structure):
+    _fields_ = [("fwd", SoftargmaxArgs), ("grad_out", C.c_void_p), ("grad_x", C.c_void_p)]
+
+
+class MaxpoolBwdArgs(C.Structure):
+    _fields_ = [("fwd", MaxpoolArgs), ("grad_out", C.c_void_p), ("grad_in", C.c_void_p)]
+
+
+class ConvWgradArgs(C.Structure):
+    _fields_ = [("fwd", ConvArgs), ("grad_out", C.c_void_p), ("grad_weight", C.c_void_p), ("grad_bias", C.c_void_p)]
+
+
+class BnStatsArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("P", C.c_int64), ("C", C.c_int), ("pitch", C.c_int),
+                ("mean", C.c_void_p), ("var", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
+
+
+class BnApplyArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("residual", C.c_void_p), ("y", C.c_void_p),
+                ("P", C.c_int64), ("C", C.c_int), ("pitch", C.c_int),
+                ("scale", C.c_void_p), ("shift", C.c_void_p), ("relu", C.c_int)]
+
+
+class BnBwdArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("grad_y", C.c_void_p), ("y", C.c_void_p),
+                ("P", C.c_int64), ("C", C.c_int), ("pitch", C.c_int),
+                ("mean", C.c_void_p), ("var", C.c_void_p), ("gamma", C.c_void_p), ("eps", C.c_float),
+                ("grad_x", C.c_void_p), ("grad_gamma", C.c_void_p), ("grad_beta", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
+
+
 # every symbol include/sp3d.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "sp3d_abi_version": (C.c_int, []),
@@ -156,6 +191,13 @@ SYMBOLS = {
     "sp3d_space_to_depth": (C.c_int, [C.POINTER(S2DArgs), C.c_void_p]),
     "sp3d_stack_x_shifts": (C.c_int, [C.POINTER(StackArgs), C.c_void_p]),
     "sp3d_split_bf16": (C.c_int, [C.POINTER(SplitArgs), C.c_void_p]),
+    "sp3d_unproject_bwd": (C.c_int, [C.POINTER(UnprojectBwdArgs), C.c_void_p]),
+    "sp3d_softargmax3d_bwd": (C.c_int, [C.POINTER(SoftargmaxBwdArgs), C.c_void_p]),
+    "sp3d_maxpool_bwd": (C.c_int, [C.POINTER(MaxpoolBwdArgs), C.c_void_p]),
+    "sp3d_conv_wgrad": (C.c_int, [C.POINTER(ConvWgradArgs), C.c_void_p]),
+    "sp3d_bn_stats": (C.c_int, [C.POINTER(BnStatsArgs), C.c_void_p]),
+    "sp3d_bn_apply": (C.c_int, [C.POINTER(BnApplyArgs), C.c_void_p]),
+    "sp3d_bn_bwd": (C.c_int, [C.POINTER(BnBwdArgs), C.c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,244 @@
+"""Torch-tensor front end of the backward operators of the C ABI (``include/sp3d.h``, "Backward operators").
+
+Same rules as ``ops.py``: CUDA tensors in, POD argument structs, launches on torch's current stream, no CPU path.
+All tensors are float32; activations are channel-last ``[N, D, H, W, pitch]``.
+
+What is here is the operator level of the training path: gradients of the un-projection,
+the soft-argmax, max pooling, the convolution family (weight gradient kernel; the input gradient is the forward
+kernel on the adjoint weight) and training-mode BatchNorm.  The module-level ``autograd`` wiring of whole nets is the
+next step and is not part of this file.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib, ops
+from .ops import _require_cuda, _set3, _stream
+
+
+def _f32(*tensors):
+    for t in tensors:
+        if t is not None and (t.dtype != torch.float32 or not t.is_cuda):
+            raise _lib.Sp3dError("backward operators take float32 CUDA tensors")
+
+
+# --------------------------------------------------------------------------------------------- un-projection
+def unproject_bwd(heatmaps, hm_strides, cams, centers, grid_size, cube_size, image_size, heatmap_hw, channels,
+                  grad_cubes, grad_strides, grad_heatmaps, check_flag=False, cubes_per_sample=1, cube_sample=None,
+                  heatmap_cfg_wh=None):
+    """Accumulate ``dL/dheatmaps`` into ``grad_heatmaps`` (list[V], addressed like ``heatmaps`` through
+    ``hm_strides``; zero them first) given ``grad_cubes`` addressed through ``grad_strides = (cube, channel, voxel)``.
+    The remaining arguments are those of the forward ``ops.unproject`` call."""
+    _f32(grad_cubes, *heatmaps, *grad_heatmaps)
+    b = _lib.UnprojectBwdArgs()
+    ops.unproject_args(heatmaps, hm_strides, cams, centers, grid_size, cube_size, image_size, heatmap_hw, channels,
+                       None, grad_strides, 0, check_flag, cubes_per_sample, cube_sample, None, None, False,
+                       heatmap_cfg_wh, False, a=b.fwd)
+    b.grad_cubes = grad_cubes.data_ptr()
+    for v, g in enumerate(grad_heatmaps):
+        b.grad_heatmaps[v] = g.data_ptr()
+    n_vox = b.fwd.X * b.fwd.Y * b.fwd.Z
+    _lib.call("sp3d_unproject_bwd", b, _stream(), kind="unproject_bwd",
+              work=b.fwd.n_cubes * b.fwd.C * n_vox * 4 + 2 * b.fwd.V * b.fwd.B * b.fwd.C * b.fwd.h * b.fwd.w * 4)
+
+
+# --------------------------------------------------------------------------------------------- soft-argmax
+def softargmax_bwd(x, strides, n_cubes, channels, cube_size, centers, grid_size, beta, out, grad_out, check_flag=False,
+                   lin=None):
+    """``dL/dx`` of ``ops.softargmax`` (same arguments; ``out`` = its result, ``grad_out [n_cubes, C, 3]``).
+    Returns a tensor shaped and strided like ``x`` (padding channels zero)."""
+    _f32(x, out, grad_out)
+    _require_cuda(centers)
+    gx = torch.zeros_like(x)
+    b = _lib.SoftargmaxBwdArgs()
+    a = b.fwd
+    a.x, a.x_dtype = x.data_ptr(), _lib.F32
+    a.stride_cube, a.stride_c, a.stride_vox = [int(s) for s in strides]
+    a.n_cubes, a.C = int(n_cubes), int(channels)
+    a.X, a.Y, a.Z = [int(s) for s in cube_size]
+    a.centers, a.center_stride = centers.data_ptr(), int(centers.stride(0))
+    a.check_flag = int(bool(check_flag))
+    if lin is None:
+        lin = ops.linspace_axes(grid_size, cube_size, x.device)
+    a.lin_x, a.lin_y, a.lin_z = lin[0].data_ptr(), lin[1].data_ptr(), lin[2].data_ptr()
+    a.beta = float(beta)
+    out, grad_out = out.contiguous(), grad_out.contiguous()
+    a.out = out.data_ptr()
+    b.grad_out = grad_out.data_ptr()
+    b.grad_x = gx.data_ptr()
+    _lib.call("sp3d_softargmax3d_bwd", b, _stream(), kind="softargmax_bwd",
+              work=4 * a.n_cubes * a.C * a.X * a.Y * a.Z * 4)
+    return gx
+
+
+# --------------------------------------------------------------------------------------------- max pool
+def maxpool_bwd(x, channels, k, s, p, grad_out):
+    """``dL/dx`` of ``ops.maxpool(x, channels, k, s, p)`` for float32 channel-last ``x``."""
+    _f32(x, grad_out)
+    N, D, H, W, pitch = [int(v) for v in x.shape]
+    dims = (D, H, W)
+    o = [(dims[i] + 2 * p[i] - k[i]) // s[i] + 1 for i in range(3)]
+    if tuple(grad_out.shape) != (N, o[0], o[1], o[2], pitch) or not grad_out.is_contiguous() or not x.is_contiguous():
+        raise _lib.Sp3dError("maxpool_bwd: grad_out must be the contiguous pooled shape")
+    gi = torch.empty_like(x)
+    b = _lib.MaxpoolBwdArgs()
+    a = b.fwd
+    a.in_ = x.data_ptr()
+    a.N, a.D, a.H, a.W, a.C, a.c_pitch = N, D, H, W, int(channels), pitch
+    a.OD, a.OH, a.OW = o
+    _set3(a.k, k)
+    _set3(a.s, s)
+    _set3(a.p, p)
+    a.dtype = _lib.F32
+    b.grad_out, b.grad_in = grad_out.data_ptr(), gi.data_ptr()
+    _lib.call("sp3d_maxpool_bwd", b, _stream(), launches=2, kind="maxpool_bwd", work=3 * x.numel() * 4)
+    return gi
+
+
+# --------------------------------------------------------------------------------------------- convolutions
+def _conv_geometry(a, x, out_shape, cin, cout, cout_pitch_w, out_grid, ksize, stride, tap_off0, tap_step, ostride, ooffset):
+    a.N, a.D, a.H, a.W = [int(s) for s in x.shape[:4]]
+    a.cin, a.cin_pitch = int(cin), int(x.shape[4])
+    a.OD, a.OH, a.OW = [int(s) for s in out_grid]
+    a.TD, a.TH, a.TW = [int(s) for s in out_shape[1:4]]
+    a.cout, a.cout_pitch, a.cout_pitch_w = int(cout), int(out_shape[4]), int(cout_pitch_w)
+    _set3(a.ksize, ksize)
+    _set3(a.stride, stride)
+    _set3(a.tap_off0, tap_off0)
+    _set3(a.tap_step, tap_step)
+    _set3(a.ostride, ostride)
+    _set3(a.ooffset, ooffset)
+    a.in_dtype = a.out_dtype = _lib.F32
+
+
+def conv_wgrad(pc, x, grad_out, with_bias=True):
+    """Weight / bias gradient of the convolution ``pc`` (an ``ops.PackedConv``; its folded scale / shift / ReLU are
+    NOT part of this: ``grad_out`` is the gradient of the raw convolution result) for the forward input ``x``.
+    Returns ``(grad_weight, grad_bias)`` in the layout of the reference parameter (``nn.Conv*``: ``[Cout,Cin,k..]``,
+    ``nn.ConvTranspose*``: ``[Cin,Cout,k..]``)."""
+    _f32(x, grad_out)
+    if not x.is_contiguous() or not grad_out.is_contiguous():
+        raise _lib.Sp3dError("conv_wgrad expects contiguous channel-last tensors")
+    N, D, H, W, pitch = [int(v) for v in x.shape]
+    if pitch < pc.cin_p:
+        raise _lib.Sp3dError("activation pitch %d smaller than packed cin %d" % (pitch, pc.cin_p))
+    o = pc.out_shape((D, H, W))
+    if tuple(grad_out.shape[:4]) != (N, o[0], o[1], o[2]) or int(grad_out.shape[4]) < pc.cout:
+        raise _lib.Sp3dError("conv_wgrad: grad_out does not match the convolution's output shape")
+    gb = torch.zeros(pc.cout, device=x.device, dtype=torch.float32) if with_bias else None
+    subs = []
+    launches = [(None, [-p for p in pc.padding], pc.k, o, [1, 1, 1], [1, 1, 1], [0, 0, 0])] if not pc.transposed else [
+        (i, off0, ks, [(o[d] - phase[d] + pc.stride[d] - 1) // pc.stride[d] for d in range(3)], [-1, -1, -1], pc.stride, phase)
+        for i, (phase, off0, ks) in enumerate(pc.phases)]
+    for (_, off0, ks, grid, step, ostride, ooff) in launches:
+        taps = int(ks[0] * ks[1] * ks[2])
+        gw = torch.zeros(taps, pc.cin_p, pc.cout_pw, device=x.device, dtype=torch.float32)
+        b = _lib.ConvWgradArgs()
+        _conv_geometry(b.fwd, x, grad_out.shape, pc.cin_p, pc.cout, pc.cout_pw, grid, ks,
+                       pc.stride if not pc.transposed else [1, 1, 1], off0, step, ostride, ooff)
+        b.fwd.in_ = x.data_ptr()
+        b.grad_out, b.grad_weight = grad_out.data_ptr(), gw.data_ptr()
+        b.grad_bias = gb.data_ptr() if gb is not None else None
+        flops = 2.0 * N * grid[0] * grid[1] * grid[2] * pc.cout * pc.cin * taps
+        _lib.call("sp3d_conv_wgrad", b, _stream(), kind="conv_wgrad", work=flops)
+        subs.append(gw[:, :pc.cin, :pc.cout].reshape(int(ks[0]), int(ks[1]), int(ks[2]), pc.cin, pc.cout)
+                    .permute(4, 3, 0, 1, 2))                       # [Cout, Cin, a, b, c]
+    if not pc.transposed:
+        w5 = subs[0]
+    else:
+        w5 = torch.zeros(pc.cout, pc.cin, *pc.k, device=x.device, dtype=torch.float32)
+        s_, p_ = pc.stride, pc.padding
+        for sub, (phase, _, _) in zip(subs, pc.phases):
+            t0 = [(phase[i] + p_[i]) % s_[i] for i in range(3)]
+            w5[:, :, t0[0]::s_[0], t0[1]::s_[1], t0[2]::s_[2]] = sub
+        w5 = w5.permute(1, 0, 2, 3, 4)                             # nn.ConvTranspose layout [Cin, Cout, k..]
+    shape = list(w5.shape[:2]) + list(w5.shape[2 + (3 - pc.nd):])
+    return w5.reshape(shape).contiguous(), gb
+
+
+def conv_dgrad(pc, grad_out, in_dims=None):
+    """Input gradient of the convolution ``pc`` (raw convolution, no scale / shift / ReLU) -- the forward kernel
+    on the adjoint weight.  Covered: stride-1 "same" convolutions (adjoint = the flipped, channel-transposed kernel)
+    and kernel == stride transposed convolutions without padding (adjoint = the strided convolution with the same
+    kernel): every layer of V2VNet and the stride-1 layers of PoseResNet."""
+    _f32(grad_out)
+    adj = pc.__dict__.get("_adjoint")
+    if adj is None:
+        w = pc._subs[0] if not pc.transposed else None
+        if not pc.transposed:
+            if pc.stride != [1, 1, 1] or any(2 * pc.padding[i] != pc.k[i] - 1 for i in range(3)):
+                raise _lib.Sp3dError("conv_dgrad covers stride-1 'same' convolutions")
+            wa = w.permute(1, 0, 2, 3, 4).flip(2, 3, 4)            # [Cin, Cout, k..] = an nn.Conv weight with Cout' = Cin
+            wa = wa.reshape(list(wa.shape[:2]) + list(wa.shape[2 + (3 - pc.nd):]))
+            adj = ops.PackedConv(wa.contiguous(), None, None, 1, pc.padding[-1], relu=0)
+        else:
+            if pc.k != pc.stride or any(pc.padding):
+                raise _lib.Sp3dError("conv_dgrad covers kernel == stride transposed convolutions without padding")
+            full = torch.zeros(pc.cout, pc.cin, *pc.k, device=grad_out.device, dtype=torch.float32)
+            for sub, (phase, _, _) in zip(pc._subs, pc.phases):
+                full[:, :, phase[0]::pc.stride[0], phase[1]::pc.stride[1], phase[2]::pc.stride[2]] = sub
+            wa = full.permute(1, 0, 2, 3, 4)                       # [Cin_t, Cout_t, k..]: a strided nn.Conv weight
+            wa = wa.reshape(list(wa.shape[:2]) + list(wa.shape[2 + (3 - pc.nd):]))
+            adj = ops.PackedConv(wa.contiguous(), None, None, pc.stride[-1], 0, relu=0)
+        pc.__dict__["_adjoint"] = adj
+    return adj(grad_out, algo=_lib.CONV_SIMT_F32)
+
+
+# --------------------------------------------------------------------------------------------- BatchNorm (training)
+def _flat(x):
+    if not x.is_contiguous():
+        raise _lib.Sp3dError("BatchNorm operators expect contiguous channel-last tensors")
+    pitch = int(x.shape[-1])
+    return x.numel() // pitch, pitch
+
+
+def bn_stats(x, channels):
+    """Per-channel batch mean and biased variance of channel-last ``x`` -> ``(mean [C], var [C])``."""
+    _f32(x)
+    P, pitch = _flat(x)
+    mean = torch.empty(channels, device=x.device, dtype=torch.float32)
+    var = torch.empty_like(mean)
+    ws = torch.empty(2 * channels, device=x.device, dtype=torch.float64)
+    a = _lib.BnStatsArgs()
+    a.x, a.P, a.C, a.pitch = x.data_ptr(), P, int(channels), pitch
+    a.mean, a.var = mean.data_ptr(), var.data_ptr()
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 8
+    _lib.call("sp3d_bn_stats", a, _stream(), launches=2, kind="bn", work=x.numel() * 4)
+    return mean, var
+
+
+def bn_apply(x, channels, scale, shift, relu=0, residual=None):
+    """``act(x * scale[c] + shift[c] (+ residual))`` on channel-last ``x`` (``relu`` as in ``sp3d_conv_args``)."""
+    _f32(x, scale, shift, residual)
+    P, pitch = _flat(x)
+    y = torch.empty_like(x)
+    a = _lib.BnApplyArgs()
+    a.x, a.y = x.data_ptr(), y.data_ptr()
+    a.residual = residual.data_ptr() if residual is not None else None
+    a.P, a.C, a.pitch = P, int(channels), pitch
+    a.scale, a.shift, a.relu = scale.data_ptr(), shift.data_ptr(), int(relu)
+    _lib.call("sp3d_bn_apply", a, _stream(), kind="bn", work=2 * x.numel() * 4)
+    return y
+
+
+def bn_bwd(x, channels, grad_y, mean, var, gamma, eps, y=None):
+    """Backward of training-mode BatchNorm (+ the ReLU right after it when its output ``y`` is given) ->
+    ``(grad_x, grad_gamma, grad_beta)``."""
+    _f32(x, grad_y, mean, var, gamma, y)
+    P, pitch = _flat(x)
+    gx = torch.empty_like(x)
+    gg = torch.empty(channels, device=x.device, dtype=torch.float32)
+    gb = torch.empty_like(gg)
+    ws = torch.empty(2 * channels, device=x.device, dtype=torch.float64)
+    a = _lib.BnBwdArgs()
+    grad_y = grad_y.contiguous()
+    a.x, a.grad_y = x.data_ptr(), grad_y.data_ptr()
+    a.y = y.data_ptr() if y is not None else None
+    a.P, a.C, a.pitch = P, int(channels), pitch
+    a.mean, a.var = mean.data_ptr(), var.data_ptr()
+    a.gamma = gamma.data_ptr() if gamma is not None else None
+    a.eps = float(eps)
+    a.grad_x, a.grad_gamma, a.grad_beta = gx.data_ptr(), gg.data_ptr(), gb.data_ptr()
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 8
+    _lib.call("sp3d_bn_bwd", a, _stream(), launches=3, kind="bn", work=4 * x.numel() * 4)
+    return gx, gg, gb

@@ -139,8 +139,22 @@ def unproject(heatmaps, hm_strides, cams, centers, grid_size, cube_size, image_s
     cams ``[B,V,32]``, centers ``[n_cubes, >=3]`` float32 CUDA.  ``out`` receives the cubes through
     ``out_strides = (cube, channel, voxel)``.
     """
+    a = unproject_args(heatmaps, hm_strides, cams, centers, grid_size, cube_size, image_size, heatmap_hw, channels,
+                       out, out_strides, out_c_pad, check_flag, cubes_per_sample, cube_sample, grids, view_range,
+                       partial, heatmap_cfg_wh, fast)
+    n_vox = a.X * a.Y * a.Z
+    # SURVEY 8(d) algorithmic bytes: every float32 heat-map read once + every float32 cube written once (the bf16
+    # volume mode physically moves half of the cube bytes; bench.py reports both)
+    work = (a.view_end - a.view_begin) * a.B * a.C * a.h * a.w * 4 + a.n_cubes * a.C * n_vox * 4
+    _lib.call("sp3d_unproject_fwd", a, _stream(), kind="unproject", work=work)
+
+
+def unproject_args(heatmaps, hm_strides, cams, centers, grid_size, cube_size, image_size, heatmap_hw, channels,
+                   out, out_strides, out_c_pad=0, check_flag=False, cubes_per_sample=1, cube_sample=None,
+                   grids=None, view_range=None, partial=False, heatmap_cfg_wh=None, fast=False, a=None):
+    """Fill ``sp3d_unproject_args`` (see ``unproject``); ``out`` may be None (backward: only the strides matter)."""
     _require_cuda(cams, centers, out, *heatmaps)
-    a = _lib.UnprojectArgs()
+    a = _lib.UnprojectArgs() if a is None else a
     V = len(heatmaps)
     for v in range(V):
         a.heatmaps[v] = heatmaps[v].data_ptr()
@@ -151,7 +165,7 @@ def unproject(heatmaps, hm_strides, cams, centers, grid_size, cube_size, image_s
     a.check_flag = int(bool(check_flag))
     a.cubes_per_sample = int(cubes_per_sample)
     a.cube_sample = cube_sample.data_ptr() if cube_sample is not None else None
-    lin = linspace_axes(grid_size, cube_size, out.device)
+    lin = linspace_axes(grid_size, cube_size, cams.device)
     a.lin_x, a.lin_y, a.lin_z = lin[0].data_ptr(), lin[1].data_ptr(), lin[2].data_ptr()
     a.B = int(cams.shape[0])
     a.V = V
@@ -165,18 +179,14 @@ def unproject(heatmaps, hm_strides, cams, centers, grid_size, cube_size, image_s
     a.hm_cfg_w, a.hm_cfg_h = float(heatmap_cfg_wh[0]), float(heatmap_cfg_wh[1])
     a.view_begin, a.view_end = (0, V) if view_range is None else (int(view_range[0]), int(view_range[1]))
     a.partial = int(bool(partial))
-    a.cubes = out.data_ptr()
-    a.out_dtype = _DT[out.dtype]
+    a.cubes = out.data_ptr() if out is not None else None
+    a.out_dtype = _DT[out.dtype] if out is not None else _lib.F32
     a.out_stride_cube, a.out_stride_c, a.out_stride_vox = [int(s) for s in out_strides]
     a.out_c_pad = int(out_c_pad)
     a.grids = grids.data_ptr() if grids is not None else None
     a.hm_dtype = _DT[heatmaps[0].dtype]
     a.math_mode = int(bool(fast))
-    n_vox = a.X * a.Y * a.Z
-    # SURVEY 8(d) algorithmic bytes: every float32 heat-map read once + every float32 cube written once (the bf16
-    # volume mode physically moves half of the cube bytes; bench.py reports both)
-    work = (a.view_end - a.view_begin) * a.B * a.C * a.h * a.w * 4 + a.n_cubes * a.C * n_vox * 4
-    _lib.call("sp3d_unproject_fwd", a, _stream(), kind="unproject", work=work)
+    return a
 
 
 def heatmaps_to_f16(heatmaps, hm_strides, channels):

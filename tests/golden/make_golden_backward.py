@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""Golden GRADIENTS from the unmodified reference (``/root/reference/lib``), CPU autograd, seeded synthetic inputs:
+``ProjectLayer`` (the per-person case of ``project_layer_pose.npz``: rotation / scale augmentation, h-flip, one
+invalid row), ``SoftArgmaxLayer`` and a training-mode ``Basic3DBlock``.  Build container only:
+``python tests/golden/make_golden_backward.py`` -> ``tests/golden/backward.npz``."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import ref_import  # noqa: E402
+
+ref_import.install()
+
+from core.config import config as ref_cfg  # noqa: E402
+import models  # noqa: E402,F401
+from models.project_layer import ProjectLayer  # noqa: E402
+from models.v2v_net import Basic3DBlock  # noqa: E402
+from models.pose_regression_net import SoftArgmaxLayer  # noqa: E402
+
+torch.set_num_threads(8)
+
+
+def main():
+    out = {}
+    # ---- ProjectLayer: inputs of the committed forward golden
+    g = dict(np.load(os.path.join(HERE, "project_layer_pose.npz")))
+    ref_cfg.NETWORK.IMAGE_SIZE = np.array(g["image_size"])
+    ref_cfg.NETWORK.HEATMAP_SIZE = np.array(g["heatmap_size"])
+    ref_cfg.NETWORK.NUM_JOINTS = int(g["heatmaps"].shape[2])
+    V = g["heatmaps"].shape[0]
+    meta = [{"center": torch.from_numpy(g["center"][c]), "scale": torch.from_numpy(g["scale"][c]),
+             "rotation": torch.from_numpy(g["rotation"][c]),
+             "camera": {k[4:]: torch.from_numpy(g[k][c]) for k in g if k.startswith("cam_")}} for c in range(V)]
+    hms = [torch.from_numpy(g["heatmaps"][c]).clone().requires_grad_(True) for c in range(V)]
+    cubes, _ = ProjectLayer(ref_cfg)(hms, meta, [float(v) for v in g["grid_size"]], torch.from_numpy(g["grid_center"]),
+                                     [int(v) for v in g["cube_size"]], flip_xcoords=torch.from_numpy(g["flip"]))
+    assert np.allclose(cubes.detach().numpy(), g["cubes"], atol=1e-6)
+    rs = np.random.RandomState(31)
+    gc = torch.from_numpy(rs.randn(*cubes.shape).astype(np.float32))
+    (cubes * gc).sum().backward()
+    out["pl_grad_cubes"] = gc.numpy()
+    out["pl_grad_heatmaps"] = np.stack([h.grad.numpy() for h in hms])
+
+    # ---- SoftArgmaxLayer: inputs of softargmax.npz
+    s = dict(np.load(os.path.join(HERE, "softargmax.npz")))
+    ref_cfg.NETWORK.BETA = float(s["beta"])
+    x = torch.from_numpy(s["x"]).clone().requires_grad_(True)
+    o = SoftArgmaxLayer(ref_cfg)(x, torch.from_numpy(s["grids"]))
+    go = torch.from_numpy(rs.randn(*o.shape).astype(np.float32))
+    (o * go).sum().backward()
+    out["sa_grad_out"] = go.numpy()
+    out["sa_grad_x"] = x.grad.numpy()
+
+    # ---- Basic3DBlock(4, 8, 3) in training mode (batch statistics)
+    torch.manual_seed(7)
+    blk = Basic3DBlock(4, 8, 3).train()
+    with torch.no_grad():
+        blk.block[1].weight.uniform_(0.5, 1.5)
+        blk.block[1].bias.normal_(0, 0.2)
+    xb = torch.from_numpy(rs.rand(2, 4, 6, 5, 4).astype(np.float32)).requires_grad_(True)
+    y = blk(xb)
+    gy = torch.from_numpy(rs.randn(*y.shape).astype(np.float32))
+    (y * gy).sum().backward()
+    out.update(b3_x=xb.detach().numpy(), b3_w=blk.block[0].weight.detach().numpy(), b3_b=blk.block[0].bias.detach().numpy(),
+               b3_gamma=blk.block[1].weight.detach().numpy(), b3_beta=blk.block[1].bias.detach().numpy(),
+               b3_grad_y=gy.numpy(), b3_y=y.detach().numpy(), b3_grad_x=xb.grad.numpy(),
+               b3_grad_w=blk.block[0].weight.grad.numpy(), b3_grad_b=blk.block[0].bias.grad.numpy(),
+               b3_grad_gamma=blk.block[1].weight.grad.numpy(), b3_grad_beta=blk.block[1].bias.grad.numpy())
+    path = os.path.join(HERE, "backward.npz")
+    np.savez_compressed(path, **out)
+    print("backward.npz %.1f KB" % (os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__":
+    main()

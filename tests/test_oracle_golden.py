@@ -179,3 +179,33 @@ def test_inference_from_images_matches_reference(golden):
     np.testing.assert_allclose(torch.stack(hms).numpy(), g["heatmaps"], rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(gc.numpy(), g["grid_centers"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(pred.numpy(), g["pred"], rtol=0, atol=1e-2)
+
+
+# ---------------------------------------------------------------------------------------------- gradients
+def test_backward_oracle_matches_reference_gradients(golden):
+    """oracle/backward.py (autograd over the oracle's torch restatements) against gradients recorded from the
+    unmodified reference modules (tests/golden/make_golden_backward.py)."""
+    from oracle import backward
+    gb = golden("backward")
+    g = golden("project_layer_pose")
+    hms = [torch.from_numpy(h) for h in g["heatmaps"]]
+    grads, cubes = backward.unproject_grad(
+        hms, cam_arrays(g), g["center"], g["scale"], g["rotation"], g["image_size"], g["heatmap_size"],
+        g["grid_size"], g["grid_center"], g["cube_size"], torch.from_numpy(gb["pl_grad_cubes"]), flip=g.get("flip"))
+    want = gb["pl_grad_heatmaps"]
+    got = np.stack([t.numpy() for t in grads])
+    assert np.abs(want).max() > 0 and not got[:, 1].any()        # the invalid proposal row receives no gradient
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-4 * np.abs(want).max())
+
+    s = golden("softargmax")
+    gx, _ = backward.softargmax_grad(torch.from_numpy(s["x"]), torch.from_numpy(s["grids"]), float(s["beta"]),
+                                     torch.from_numpy(gb["sa_grad_out"]))
+    np.testing.assert_allclose(gx.numpy(), gb["sa_grad_x"], rtol=0, atol=1e-5 * np.abs(gb["sa_grad_x"]).max())
+
+    t = {k: torch.from_numpy(gb["b3_" + k]) for k in ("x", "w", "b", "gamma", "beta", "grad_y")}
+    y, dx, dw, db, dg, dbeta, _, _ = backward.basic3d_train(t["x"], t["w"], t["b"], t["gamma"], t["beta"], t["grad_y"], 3)
+    for got_, name in ((y, "y"), (dx, "grad_x"), (dw, "grad_w"), (dg, "grad_gamma"), (dbeta, "grad_beta")):
+        want_ = gb["b3_" + name]
+        np.testing.assert_allclose(got_.numpy(), want_, rtol=0, atol=2e-5 * max(np.abs(want_).max(), 1e-3), err_msg=name)
+    # (the conv bias gradient is annihilated by the batch normalisation: both sides are rounding noise)
+    assert np.abs(db.numpy()).max() < 1e-3 and np.abs(gb["b3_grad_b"]).max() < 1e-3
