@@ -372,6 +372,14 @@ typedef struct {
 } sp3d_bn_bwd_args;
 int sp3d_bn_bwd(const sp3d_bn_bwd_args* a, void* stream);
 
+/* Backward of a ReLU whose output y is at hand: grad_x[i] = y[i] > 0 ? grad_y[i] : 0 over n contiguous floats
+ * (the residual branches relu(a + b) of lib/models/v2v_net.py:44 and lib/models/pose_resnet.py:90). */
+typedef struct {
+  const float* grad_y; const float* y; float* grad_x;
+  int64_t n;
+} sp3d_relu_bwd_args;
+int sp3d_relu_bwd(const sp3d_relu_bwd_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,7 +15,12 @@ import torch
 import torch.nn.functional as F
 
 
+_BATCH_STATS = False   # True inside v2v_forward(training=True): nn.BatchNorm3d in .train() mode (batch statistics)
+
+
 def _bn(x, sd, pfx, eps=1e-5):
+    if _BATCH_STATS:
+        return F.batch_norm(x, None, None, sd[pfx + ".weight"], sd[pfx + ".bias"], True, 0.0, eps)
     return F.batch_norm(x, sd[pfx + ".running_mean"], sd[pfx + ".running_var"],
                         sd[pfx + ".weight"], sd[pfx + ".bias"], False, 0.0, eps)
 
@@ -52,8 +57,18 @@ def upsample3d(x, sd, pfx):
     return F.relu(_bn(x, sd, pfx + ".block.1"))
 
 
-def v2v_forward(x, sd, pfx="", dtype=torch.float32):
-    """V2VNet.forward (v2v_net.py:126-131) with EncoderDecorder.forward (:91-110)."""
+def v2v_forward(x, sd, pfx="", dtype=torch.float32, training=False):
+    """V2VNet.forward (v2v_net.py:126-131) with EncoderDecorder.forward (:91-110).  ``training``: the module in
+    ``.train()`` mode (batch-statistics BatchNorm); differentiable with respect to ``x`` and the entries of ``sd``."""
+    global _BATCH_STATS
+    _BATCH_STATS = bool(training)
+    try:
+        return _v2v_forward(x, sd, pfx, dtype)
+    finally:
+        _BATCH_STATS = False
+
+
+def _v2v_forward(x, sd, pfx, dtype):
     sd = _cast(sd, dtype)
     x = x.to(dtype)
     x = basic3d(x, sd, pfx + "front_layers.0")

@@ -171,6 +171,10 @@ class BnBwdArgs(C.Structure):
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
 
 
+class ReluBwdArgs(C.Structure):
+    _fields_ = [("grad_y", C.c_void_p), ("y", C.c_void_p), ("grad_x", C.c_void_p), ("n", C.c_int64)]
+
+
 # every symbol include/sp3d.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "sp3d_abi_version": (C.c_int, []),
@@ -198,6 +202,7 @@ SYMBOLS = {
     "sp3d_bn_stats": (C.c_int, [C.POINTER(BnStatsArgs), C.c_void_p]),
     "sp3d_bn_apply": (C.c_int, [C.POINTER(BnApplyArgs), C.c_void_p]),
     "sp3d_bn_bwd": (C.c_int, [C.POINTER(BnBwdArgs), C.c_void_p]),
+    "sp3d_relu_bwd": (C.c_int, [C.POINTER(ReluBwdArgs), C.c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,195 @@
+"""``torch.autograd.Function`` wrappers over the forward / backward operators of the C ABI: the training path
+(batch-statistics BatchNorm, gradients) of the voxel networks, on channel-last float32 activations.
+
+``torch.autograd`` only records the graph; every forward and backward step below is one of the hand-written kernels
+(``ops`` / ``grad_ops``).  The reference trains by running autograd through its ATen / cuDNN modules
+(``lib/models/multi_person_posenet_ssv.py:222-501``); these functions are what replaces that for
+``lib/models/v2v_net.py`` (all blocks), ``ProjectLayer`` and ``SoftArgmaxLayer``.
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+
+from . import _lib, grad_ops, ops
+
+
+class ToChannelLast(Function):
+    """``[N, C, *spatial]`` -> channel-last ``[N, *spatial, pitch]`` (a permutation: the backward is its inverse)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.channels = int(x.shape[1])
+        return ops.to_channel_last(x.float())
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.to_channel_first(g.contiguous(), ctx.channels)
+
+
+class ToChannelFirst(Function):
+    @staticmethod
+    def forward(ctx, x, channels):
+        ctx.pitch = int(x.shape[-1])
+        return ops.to_channel_first(x, channels)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.to_channel_last(g.contiguous(), c_pitch=ctx.pitch), None
+
+
+class Conv(Function):
+    """Raw convolution / transposed convolution (+ bias) of an ``nn.Conv*`` / ``nn.ConvTranspose*`` parameter pair."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, transposed):
+        pc = ops.PackedConv(weight, bias, None, stride, padding, transposed=transposed, relu=0)
+        ctx.pc, ctx.has_bias = pc, bias is not None
+        ctx.save_for_backward(x)
+        return pc(x, algo=_lib.CONV_SIMT_F32)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = grad_ops.conv_dgrad(ctx.pc, gy, out_pitch=int(x.shape[-1])) if ctx.needs_input_grad[0] else None
+        gw, gb = grad_ops.conv_wgrad(ctx.pc, x, gy, with_bias=ctx.has_bias)
+        return gx, gw, gb, None, None, None
+
+
+class BatchNormAct(Function):
+    """Training-mode BatchNorm (batch statistics) with an optional ReLU right after it.  Returns ``(y, mean, var)``;
+    the statistics are for the caller's running-average update and carry no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, channels, eps, relu):
+        mean, var = grad_ops.bn_stats(x, channels)
+        scale = gamma * torch.rsqrt(var + eps)                 # [C] vectors: a handful of scalars, not a hot path
+        y = grad_ops.bn_apply(x, channels, scale.contiguous(), (beta - mean * scale).contiguous(), relu=1 if relu else 0)
+        ctx.channels, ctx.eps, ctx.relu = channels, eps, bool(relu)
+        ctx.save_for_backward(x, mean, var, gamma, y if relu else None)
+        ctx.mark_non_differentiable(mean, var)
+        return y, mean, var
+
+    @staticmethod
+    def backward(ctx, gy, _gm, _gv):
+        x, mean, var, gamma, y = ctx.saved_tensors
+        gx, gg, gb = grad_ops.bn_bwd(x, ctx.channels, gy.contiguous(), mean, var, gamma, ctx.eps, y=y)
+        return gx, gg, gb, None, None, None
+
+
+class AddAct(Function):
+    """``a + b`` or ``relu(a + b)`` on channel-last tensors (the residual joins of the V2V blocks)."""
+
+    @staticmethod
+    def forward(ctx, a, b, channels, relu):
+        one = torch.ones(channels, device=a.device, dtype=torch.float32)
+        y = grad_ops.bn_apply(a, channels, one, torch.zeros_like(one), relu=1 if relu else 0, residual=b)
+        ctx.relu = bool(relu)
+        ctx.save_for_backward(y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        g = grad_ops.relu_bwd(gy, y) if ctx.relu else gy
+        return g, g, None, None
+
+
+class MaxPool(Function):
+    @staticmethod
+    def forward(ctx, x, channels, k, s, p):
+        ctx.args = (channels, list(k), list(s), list(p))
+        ctx.save_for_backward(x)
+        return ops.maxpool(x, channels, k, s, p)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        channels, k, s, p = ctx.args
+        return grad_ops.maxpool_bwd(x, channels, k, s, p, gy.contiguous()), None, None, None, None
+
+
+def conv(x, module, transposed=False):
+    """``module``: ``nn.Conv{2,3}d`` / ``nn.ConvTranspose{2,3}d`` -> raw convolution of channel-last ``x``."""
+    return Conv.apply(x, module.weight, module.bias, int(module.stride[0]), int(module.padding[0]), transposed)
+
+
+def batch_norm(x, bn, relu=False):
+    """``nn.BatchNorm{2,3}d`` in training mode on channel-last ``x`` (+ ReLU), with the module's running-statistics
+    update (momentum, unbiased running variance, ``num_batches_tracked``) done as ``F.batch_norm`` does it."""
+    channels = int(bn.num_features)
+    y, mean, var = BatchNormAct.apply(x, bn.weight, bn.bias, channels, float(bn.eps), relu)
+    if bn.track_running_stats and bn.running_mean is not None:
+        with torch.no_grad():
+            n = x.numel() // int(x.shape[-1])
+            bn.num_batches_tracked += 1
+            m = 1.0 / float(bn.num_batches_tracked) if bn.momentum is None else float(bn.momentum)
+            bn.running_mean.mul_(1.0 - m).add_(mean, alpha=m)
+            bn.running_var.mul_(1.0 - m).add_(var * (n / max(n - 1, 1)), alpha=m)
+    return y
+
+
+def add(a, b, channels, relu=False):
+    return AddAct.apply(a, b, channels, relu)
+
+
+def max_pool(x, channels, k, s, p):
+    return MaxPool.apply(x, channels, k, s, p)
+
+
+class Unproject(Function):
+    """Per-cube un-projection of heat-maps into channel-last cubes, differentiable with respect to the heat-maps
+    (``sp3d_unproject_fwd`` / ``sp3d_unproject_bwd``).  ``hms``: one contiguous float32 ``[B,C,h,w]`` per view."""
+
+    @staticmethod
+    def forward(ctx, cams, centers, cube_sample, spec, *hms):
+        grid_size, cube_size, img_size, hm_cfg_wh, channels, pitch = spec
+        if any(h.dtype != torch.float32 or not h.is_contiguous() for h in hms):
+            raise _lib.Sp3dError("autograd.Unproject expects contiguous float32 heat-maps")
+        X, Y, Z = [int(s) for s in cube_size]
+        n = int(centers.shape[0])
+        cubes = torch.empty(n, X, Y, Z, pitch, device=hms[0].device, dtype=torch.float32)
+        ops.unproject(list(hms), hms[0].stride(), cams, centers, grid_size, (X, Y, Z), img_size, tuple(hms[0].shape[2:]),
+                      channels, cubes, (X * Y * Z * pitch, 1, pitch), out_c_pad=pitch, check_flag=False,
+                      cube_sample=cube_sample, heatmap_cfg_wh=hm_cfg_wh)
+        ctx.spec = spec
+        ctx.save_for_backward(cams, centers, cube_sample, *hms)
+        return cubes
+
+    @staticmethod
+    def backward(ctx, g):
+        cams, centers, cube_sample, *hms = ctx.saved_tensors
+        grid_size, cube_size, img_size, hm_cfg_wh, channels, pitch = ctx.spec
+        X, Y, Z = [int(s) for s in cube_size]
+        grads = [torch.zeros_like(h) for h in hms]
+        grad_ops.unproject_bwd(hms, hms[0].stride(), cams, centers, grid_size, (X, Y, Z), img_size,
+                               tuple(hms[0].shape[2:]), channels, g.contiguous(), (X * Y * Z * pitch, 1, pitch), grads,
+                               check_flag=False, cube_sample=cube_sample, heatmap_cfg_wh=hm_cfg_wh)
+        return (None, None, None, None) + tuple(grads)
+
+
+class SoftArgmax(Function):
+    """Soft-argmax of channel-last float32 volumes ``[n,X,Y,Z,pitch]`` -> ``[n,C,3]`` (``sp3d_softargmax3d_fwd`` /
+    ``sp3d_softargmax3d_bwd``)."""
+
+    @staticmethod
+    def forward(ctx, y, centers, spec):
+        channels, cube_size, grid_size, beta = spec
+        n, pitch = int(y.shape[0]), int(y.shape[-1])
+        X, Y, Z = [int(s) for s in cube_size]
+        y = y.contiguous()
+        out = ops.softargmax(y, (X * Y * Z * pitch, 1, pitch), n, channels, (X, Y, Z), centers, grid_size, beta)
+        ctx.spec = spec
+        ctx.save_for_backward(y, centers, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        y, centers, out = ctx.saved_tensors
+        channels, cube_size, grid_size, beta = ctx.spec
+        n, pitch = int(y.shape[0]), int(y.shape[-1])
+        X, Y, Z = [int(s) for s in cube_size]
+        gx = grad_ops.softargmax_bwd(y, (X * Y * Z * pitch, 1, pitch), n, channels, (X, Y, Z), centers, grid_size, beta,
+                                     out, g.contiguous())
+        return gx, None, None

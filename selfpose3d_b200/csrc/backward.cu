@@ -396,6 +396,11 @@ __global__ void bn_bwd_finish_kernel(const double* ws, int C, float* grad_gamma,
   if (grad_gamma != nullptr) grad_gamma[c] = (float)ws[C + c];
 }
 
+__global__ void relu_bwd_kernel(const sp3d_relu_bwd_args a) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x)
+    a.grad_x[i] = __ldg(a.y + i) > 0.0f ? __ldg(a.grad_y + i) : 0.0f;
+}
+
 static int grid_for(int64_t total, int threads, int cap) {
   const int64_t want = (total + threads - 1) / threads;
   return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
@@ -533,5 +538,13 @@ extern "C" int sp3d_bn_bwd(const sp3d_bn_bwd_args* a, void* stream) {
   rc = check_launch();
   if (rc != SP3D_OK) return rc;
   bn_bwd_finish_kernel<<<(a->C + 127) / 128, 128, 0, st>>>(a->workspace, a->C, a->grad_gamma, a->grad_beta);
+  return check_launch();
+}
+
+extern "C" int sp3d_relu_bwd(const sp3d_relu_bwd_args* a, void* stream) {
+  if (a == nullptr || a->n < 0 || (a->n > 0 && (a->grad_y == nullptr || a->y == nullptr || a->grad_x == nullptr)))
+    return SP3D_ERR_INVALID_ARG;
+  if (a->n == 0) return SP3D_OK;
+  relu_bwd_kernel<<<grid_for(a->n, 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
   return check_launch();
 }

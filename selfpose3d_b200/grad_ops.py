@@ -156,7 +156,7 @@ def conv_wgrad(pc, x, grad_out, with_bias=True):
     return w5.reshape(shape).contiguous(), gb
 
 
-def conv_dgrad(pc, grad_out, in_dims=None):
+def conv_dgrad(pc, grad_out, out_pitch=None):
     """Input gradient of the convolution ``pc`` (raw convolution, no scale / shift / ReLU) -- the forward kernel
     on the adjoint weight.  Covered: stride-1 "same" convolutions (adjoint = the flipped, channel-transposed kernel)
     and kernel == stride transposed convolutions without padding (adjoint = the strided convolution with the same
@@ -181,7 +181,7 @@ def conv_dgrad(pc, grad_out, in_dims=None):
             wa = wa.reshape(list(wa.shape[:2]) + list(wa.shape[2 + (3 - pc.nd):]))
             adj = ops.PackedConv(wa.contiguous(), None, None, pc.stride[-1], 0, relu=0)
         pc.__dict__["_adjoint"] = adj
-    return adj(grad_out, algo=_lib.CONV_SIMT_F32)
+    return adj(grad_out, algo=_lib.CONV_SIMT_F32, out_pitch=out_pitch)
 
 
 # --------------------------------------------------------------------------------------------- BatchNorm (training)
@@ -242,3 +242,14 @@ def bn_bwd(x, channels, grad_y, mean, var, gamma, eps, y=None):
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 8
     _lib.call("sp3d_bn_bwd", a, _stream(), launches=3, kind="bn", work=4 * x.numel() * 4)
     return gx, gg, gb
+
+
+def relu_bwd(grad_y, y):
+    """``grad_y`` where ``y > 0`` else 0 (backward of the ReLU that produced ``y``)."""
+    _f32(grad_y, y)
+    grad_y, y = grad_y.contiguous(), y.contiguous()
+    gx = torch.empty_like(y)
+    a = _lib.ReluBwdArgs()
+    a.grad_y, a.y, a.grad_x, a.n = grad_y.data_ptr(), y.data_ptr(), gx.data_ptr(), y.numel()
+    _lib.call("sp3d_relu_bwd", a, _stream(), kind="elementwise", work=3 * y.numel() * 4)
+    return gx

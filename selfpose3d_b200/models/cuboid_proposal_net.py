@@ -91,6 +91,8 @@ class CuboidProposalNet(nn.Module):
         cubes, _ = self.project_layer.project_cl(hms, cams, centers, False, self.grid_size, self.cube_size,
                                                  dtype=ops.volume_dtype(),
                                                  c_pitch=ops.round_up(hms[0].shape[1], 16) if bf16 else None)
+        if self.v2v_net.training:   # batch-statistics BatchNorm + gradients of the net's own parameters (float32 path)
+            return self.v2v_net.forward_cl(cubes)[..., 0].contiguous()
         root = self.v2v_net.forward_cl(cubes, out_pitch=1)
         return root.view(root.shape[0], root.shape[1], root.shape[2], root.shape[3])
 

@@ -60,6 +60,8 @@ class PoseRegressionNet(nn.Module):
         time to bound activation memory (a 64^3 cube needs ~0.4 GB of float32 activations)."""
         n = int(centers.shape[0])
         J = self.num_joints
+        if self.training:
+            return self._regress_train(all_heatmaps, cams, centers, cube_sample)
         if chunk is None:
             import os
             # bf16 activations of one 64^3 cube through V2VNet peak at ~0.2 GB (float32: ~0.4 GB)
@@ -90,6 +92,21 @@ class PoseRegressionNet(nn.Module):
             out[s:e] = ops.softargmax(y, (X * Y * Z * pitch, 1, pitch), e - s, J, (X, Y, Z), centers[s:e],
                                       self.grid_size, self.soft_argmax_layer.beta)
         return out
+
+    def _regress_train(self, all_heatmaps, cams, centers, cube_sample):
+        """``.train()`` mode: the same three steps under autograd (``selfpose3d_b200.autograd``) -- gradients reach the
+        heat-maps (and through them the backbone) and the V2VNet parameters, as in the reference's training forward
+        (``lib/models/multi_person_posenet_ssv.py:330-407`` calls this module under autograd).  float32 only."""
+        from .. import autograd as ag
+        if ops.volume_dtype() != torch.float32:
+            raise ValueError("the training path runs on float32 volumes (ops.set_volume_dtype(torch.float32))")
+        J = self.num_joints
+        hms = [h.float().contiguous() for h in all_heatmaps]
+        spec = ([float(v) for v in self.grid_size], [int(v) for v in self.cube_size], self.project_layer.img_size,
+                self.project_layer.heatmap_size, J, ops.round_up(J, 4))
+        cubes = ag.Unproject.apply(cams, centers, cube_sample, spec, *hms)
+        y = self.v2v_net.forward_cl(cubes)
+        return ag.SoftArgmax.apply(y, centers, (J, spec[1], spec[0], float(self.soft_argmax_layer.beta)))
 
     def forward(self, all_heatmaps, meta, grid_centers, flip_xcoords=None):
         device = all_heatmaps[0].device

@@ -8,14 +8,19 @@ ReLU and the residual add fused into the convolution epilogue, and ``sp3d_maxpoo
 
 ``forward(x)`` keeps the reference contract (``[N,C,X,Y,Z]`` in and out); ``forward_cl`` is the
 layout-native entry used by the proposal / regression nets (channel-last ``[N,X,Y,Z,pitch]``).
-Training-mode BatchNorm (batch statistics) and autograd are not implemented in this backend yet
-and raise.
+
+Modules in ``.train()`` mode take the training path: float32 activations, batch-statistics BatchNorm with the
+running-average update, and gradients through ``selfpose3d_b200.autograd`` (raw convolution -> ``sp3d_bn_stats`` /
+``sp3d_bn_apply`` -> joins; backward through ``sp3d_bn_bwd``, the forward kernel on the adjoint weight,
+``sp3d_conv_wgrad``, ``sp3d_maxpool_bwd``).  Modules in ``.eval()`` mode take the fused inference path, which
+records no gradient.
 """
 from __future__ import annotations
 
 import torch
 import torch.nn as nn
 
+from .. import autograd as ag
 from .. import ops
 
 
@@ -26,11 +31,18 @@ def _to_volume_cl(x):
     return ops.to_channel_last(x.float())
 
 
+def _forward_cf(module, x, out_channels):
+    """The reference contract ``[N,C,X,Y,Z] -> [N,C',X,Y,Z]`` around a module's channel-last ``forward_cl``."""
+    if module.training:
+        return ag.ToChannelFirst.apply(module.forward_cl(ag.ToChannelLast.apply(x)), out_channels)
+    return ops.to_channel_first(module.forward_cl(_to_volume_cl(x)), out_channels)
+
+
 def _no_train(module):
     if module.training:
         raise NotImplementedError(
-            "selfpose3d_b200: training-mode forward (batch-statistics BatchNorm + backward kernels) is not "
-            "implemented yet; call .eval() -- the inference path is the supported one")
+            "selfpose3d_b200: the training-mode forward (batch-statistics BatchNorm + backward kernels) of %s is not "
+            "implemented yet (V2VNet and its blocks are); call .eval() for the inference path" % type(module).__name__)
 
 
 class _PackedCache:
@@ -65,11 +77,12 @@ class Basic3DBlock(nn.Module):
         return self._cache.get(self, lambda: ops.PackedConv(c.weight, c.bias, b, 1, c.padding[0], relu=1))
 
     def forward_cl(self, x):
+        if self.training:
+            return ag.batch_norm(ag.conv(x, self.block[0]), self.block[1], relu=True)
         return self._packed()(x)
 
     def forward(self, x):
-        _no_train(self)
-        return ops.to_channel_first(self.forward_cl(_to_volume_cl(x)), self.block[0].out_channels)
+        return _forward_cf(self, x, self.block[0].out_channels)
 
 
 class Res3DBlock(nn.Module):
@@ -104,13 +117,18 @@ class Res3DBlock(nn.Module):
         return self._cache.get(self, build)
 
     def forward_cl(self, x):
+        if self.training:
+            rb = self.res_branch
+            r = ag.batch_norm(ag.conv(x, rb[0]), rb[1], relu=True)
+            r = ag.batch_norm(ag.conv(r, rb[3]), rb[4])
+            skip = x if len(self.skip_con) == 0 else ag.batch_norm(ag.conv(x, self.skip_con[0]), self.skip_con[1])
+            return ag.add(r, skip, self.out_planes, relu=True)
         a, b, s = self._packed()
         skip = x if s is None else s(x)
         return b(a(x), residual=skip)
 
     def forward(self, x):
-        _no_train(self)
-        return ops.to_channel_first(self.forward_cl(_to_volume_cl(x)), self.out_planes)
+        return _forward_cf(self, x, self.out_planes)
 
 
 class Pool3DBlock(nn.Module):
@@ -122,10 +140,14 @@ class Pool3DBlock(nn.Module):
 
     def forward_cl(self, x, channels):
         k = [self.pool_size] * 3
+        if self.training:
+            return ag.max_pool(x, channels, k, k, [0, 0, 0])
         return ops.maxpool(x, channels, k, k, [0, 0, 0])
 
     def forward(self, x):
-        c = x.shape[1]
+        c = int(x.shape[1])
+        if self.training:
+            return ag.ToChannelFirst.apply(self.forward_cl(ag.ToChannelLast.apply(x), c), c)
         return ops.to_channel_first(self.forward_cl(_to_volume_cl(x), c), c)
 
 
@@ -150,11 +172,13 @@ class Upsample3DBlock(nn.Module):
         return self._cache.get(self, lambda: ops.PackedConv(c.weight, c.bias, b, 2, 0, transposed=True, relu=2))
 
     def forward_cl(self, x, skip=None):
+        if self.training:
+            y = ag.batch_norm(ag.conv(x, self.block[0], transposed=True), self.block[1], relu=True)
+            return y if skip is None else ag.add(y, skip, self.out_planes)
         return self._packed()(x, residual=skip)
 
     def forward(self, x):
-        _no_train(self)
-        return ops.to_channel_first(self.forward_cl(_to_volume_cl(x)), self.out_planes)
+        return _forward_cf(self, x, self.out_planes)
 
 
 class EncoderDecorder(nn.Module):
@@ -185,8 +209,7 @@ class EncoderDecorder(nn.Module):
         return self.decoder_upsample1.forward_cl(x, skip=skip_x1)
 
     def forward(self, x):
-        _no_train(self)
-        return ops.to_channel_first(self.forward_cl(_to_volume_cl(x)), 32)
+        return _forward_cf(self, x, 32)
 
 
 class V2VNet(nn.Module):
@@ -211,12 +234,18 @@ class V2VNet(nn.Module):
     def forward_cl(self, x, out_pitch=None):
         """``x``: channel-last ``[N,X,Y,Z,pitch]`` float32, spatial extents divisible by 4.
         Returns channel-last ``[N,X,Y,Z,out_pitch]`` (default pitch: channels rounded up to 4)."""
-        _no_train(self)
         if any(int(s) % 4 for s in x.shape[1:4]):
             raise ValueError("V2VNet needs spatial extents divisible by 4, got %s" % (tuple(x.shape[1:4]),))
+        if self.training:
+            if x.dtype != torch.float32:
+                raise ValueError("the training path runs on float32 activations (ops.set_volume_dtype(torch.float32))")
+            if out_pitch not in (None, ops.round_up(self.output_channels, 4)):
+                raise ValueError("the training path writes the default channel pitch")
         x = self.front_layers[0].forward_cl(x)
         x = self.front_layers[1].forward_cl(x)
         x = self.encoder_decoder.forward_cl(x)
+        if self.training:
+            return ag.conv(x, self.output_layer)
         # the score / heat-map volume leaves the net in float32 in either mode (NMS and soft-argmax read it)
         return self._out_packed()(x, out_pitch=out_pitch, out_dtype=torch.float32)
 
@@ -232,8 +261,7 @@ class V2VNet(nn.Module):
         return self._out_packed()(x, head=head)
 
     def forward(self, x):
-        y = self.forward_cl(_to_volume_cl(x))
-        return ops.to_channel_first(y, self.output_channels)
+        return _forward_cf(self, x, self.output_channels)
 
     def _initialize_weights(self):
         # reference v2v_net.py:135-144: N(0, 0.001) weights, zero bias for conv and transposed conv

@@ -20,7 +20,7 @@ ref_import.install()
 from core.config import config as ref_cfg  # noqa: E402
 import models  # noqa: E402,F401
 from models.project_layer import ProjectLayer  # noqa: E402
-from models.v2v_net import Basic3DBlock  # noqa: E402
+from models.v2v_net import Basic3DBlock, V2VNet  # noqa: E402
 from models.pose_regression_net import SoftArgmaxLayer  # noqa: E402
 
 torch.set_num_threads(8)
@@ -72,6 +72,23 @@ def main():
                b3_grad_y=gy.numpy(), b3_y=y.detach().numpy(), b3_grad_x=xb.grad.numpy(),
                b3_grad_w=blk.block[0].weight.grad.numpy(), b3_grad_b=blk.block[0].bias.grad.numpy(),
                b3_grad_gamma=blk.block[1].weight.grad.numpy(), b3_grad_beta=blk.block[1].bias.grad.numpy())
+    # ---- whole V2VNet(3, 3) in training mode: output, input gradient, per-parameter gradient norms / sums and the
+    # updated running statistics of the first BatchNorm (weights regenerated from the seed by the tests)
+    from selfpose3d_b200 import synthetic
+    net = V2VNet(3, 3)
+    net.load_state_dict(synthetic.trained_like_state_dict(net, seed=53), strict=True)
+    net.train()
+    xv = torch.from_numpy(rs.rand(2, 3, 8, 8, 4).astype(np.float32)).requires_grad_(True)
+    yv = net(xv)
+    gv = torch.from_numpy(rs.randn(*yv.shape).astype(np.float32))
+    (yv * gv).sum().backward()
+    names = [n for n, _ in net.named_parameters()]
+    out.update(v2v_seed=53, v2v_x=xv.detach().numpy(), v2v_grad_y=gv.numpy(), v2v_y=yv.detach().numpy(),
+               v2v_grad_x=xv.grad.numpy(), v2v_param_names=np.array(names),
+               v2v_param_grad_norm=np.array([float(p.grad.double().norm()) for _, p in net.named_parameters()]),
+               v2v_param_grad_sum=np.array([float(p.grad.double().sum()) for _, p in net.named_parameters()]),
+               v2v_bn0_running_mean=net.front_layers[0].block[1].running_mean.numpy(),
+               v2v_bn0_running_var=net.front_layers[0].block[1].running_var.numpy())
     path = os.path.join(HERE, "backward.npz")
     np.savez_compressed(path, **out)
     print("backward.npz %.1f KB" % (os.path.getsize(path) / 1024))

@@ -134,3 +134,36 @@ def test_pack_cameras_affine_cache_is_content_keyed():
     # same rig at another network input size: other affine
     t3 = ops.pack_cameras(m1, (192, 256))
     assert not torch.equal(t1a[..., 21:27], t3[..., 21:27])
+
+
+def test_ctypes_struct_layouts_match_the_c_header(tmp_path):
+    """Every argument struct of include/sp3d.h has the same size under gcc as its ctypes mirror in _lib.py (field
+    order / padding drift would silently corrupt launches)."""
+    import ctypes
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        import pytest
+        pytest.skip("no C compiler")
+    pairs = {
+        "sp3d_unproject_args": _lib.UnprojectArgs, "sp3d_heatmaps_f16_args": _lib.HeatmapsF16Args,
+        "sp3d_unproject_finalize_args": _lib.UnprojectFinalizeArgs, "sp3d_nms_topk_args": _lib.NmsTopkArgs,
+        "sp3d_softargmax_args": _lib.SoftargmaxArgs, "sp3d_conv_args": _lib.ConvArgs, "sp3d_maxpool_args": _lib.MaxpoolArgs,
+        "sp3d_layout_args": _lib.LayoutArgs, "sp3d_s2d_args": _lib.S2DArgs, "sp3d_stack_args": _lib.StackArgs,
+        "sp3d_split_args": _lib.SplitArgs, "sp3d_unproject_bwd_args": _lib.UnprojectBwdArgs,
+        "sp3d_softargmax_bwd_args": _lib.SoftargmaxBwdArgs, "sp3d_maxpool_bwd_args": _lib.MaxpoolBwdArgs,
+        "sp3d_conv_wgrad_args": _lib.ConvWgradArgs, "sp3d_bn_stats_args": _lib.BnStatsArgs,
+        "sp3d_bn_apply_args": _lib.BnApplyArgs, "sp3d_bn_bwd_args": _lib.BnBwdArgs, "sp3d_relu_bwd_args": _lib.ReluBwdArgs,
+    }
+    header = open(os.path.join(ROOT, "include", "sp3d.h")).read()
+    declared = set(re.findall(r"}\s*(sp3d_[a-z0-9_]+_args)\s*;", header))
+    assert declared == set(pairs), declared ^ set(pairs)
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "sp3d.h"\nint main(void){'
+                   + "".join('printf("%s %%zu\\n", sizeof(%s));' % (n, n) for n in pairs) + "return 0;}\n")
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    out = subprocess.check_output([str(exe)]).decode().strip().splitlines()
+    for line in out:
+        name, size = line.split()
+        assert ctypes.sizeof(pairs[name]) == int(size), (name, ctypes.sizeof(pairs[name]), int(size))

@@ -209,3 +209,27 @@ def test_backward_oracle_matches_reference_gradients(golden):
         np.testing.assert_allclose(got_.numpy(), want_, rtol=0, atol=2e-5 * max(np.abs(want_).max(), 1e-3), err_msg=name)
     # (the conv bias gradient is annihilated by the batch normalisation: both sides are rounding noise)
     assert np.abs(db.numpy()).max() < 1e-3 and np.abs(gb["b3_grad_b"]).max() < 1e-3
+
+
+def _v2v_train_oracle(gb):
+    """Autograd through oracle.nets.v2v_forward(training=True) on the inputs of the recorded reference step."""
+    from selfpose3d_b200.models import v2v_net
+    net = v2v_net.V2VNet(3, 3)
+    sd0 = synthetic.trained_like_state_dict(net, seed=int(gb["v2v_seed"]))
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+          for k, v in sd0.items()}
+    x = torch.from_numpy(gb["v2v_x"]).clone().requires_grad_(True)
+    y = nets.v2v_forward(x, sd, training=True)
+    (y * torch.from_numpy(gb["v2v_grad_y"])).sum().backward()
+    return y.detach(), x.grad, sd
+
+
+def test_v2v_training_oracle_matches_reference_step(golden):
+    gb = golden("backward")
+    y, gx, sd = _v2v_train_oracle(gb)
+    np.testing.assert_allclose(y.numpy(), gb["v2v_y"], rtol=0, atol=1e-5 * np.abs(gb["v2v_y"]).max())
+    np.testing.assert_allclose(gx.numpy(), gb["v2v_grad_x"], rtol=0, atol=1e-4 * np.abs(gb["v2v_grad_x"]).max())
+    for name, norm, tot in zip(gb["v2v_param_names"], gb["v2v_param_grad_norm"], gb["v2v_param_grad_sum"]):
+        g = sd[str(name)].grad.double()
+        assert abs(float(g.norm()) - norm) <= 1e-3 * max(norm, 1e-3), name
+        assert abs(float(g.sum()) - tot) <= 1e-3 * max(norm, 1e-3) * max(1.0, np.sqrt(g.numel())), name
