@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-layer device time of one bench step (CUDA events around every C-ABI launch):
-  python profiles/layer_times.py [--volume-dtype bf16|f32] [--batch B] [--proposals P]"""
+  python profiles/layer_times.py [--volume-dtype bf16|f32|f32x3|f32x6] [--batch B] [--proposals P]"""
 import argparse
 import os
 import sys
@@ -18,6 +18,8 @@ ap.add_argument("--proposals", type=int, default=bench.PROPOSALS)
 ap.add_argument("--volume-dtype", default="bf16")
 a = ap.parse_args()
 ops.set_volume_dtype(torch.bfloat16 if a.volume_dtype == "bf16" else torch.float32)
+if a.volume_dtype in ("f32x3", "f32x6"):    # float32 activations on the tcgen05 kernel through bf16 operand splitting
+    ops.set_float32_conv("bf16x3" if a.volume_dtype == "f32x3" else "bf16x6")
 bench.PROPOSALS = a.proposals
 cfg = bench.make_cfg(a.batch)
 model = multi_person_posenet_ssv.get_multi_person_pose_net(cfg, is_train=False)

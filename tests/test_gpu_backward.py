@@ -275,8 +275,10 @@ def test_v2v_net_training_step_matches_reference(golden):
 
 
 def test_v2v_net_training_step_pose_size_vs_oracle():
-    """One training step of V2VNet(15, 15) on a 32^3 cube (the per-person net at half extent): gradients against
-    float64 autograd through the oracle's restatement."""
+    """One training step of V2VNet(15, 15) on a 32^3 cube (the per-person net at half extent, batch of one).  At this
+    size float32 itself is the limit: ReLU gates and max-pool winners that are decided in the last bits differ between
+    float32 and float64 (the float32 CPU oracle is 1.5e-2 / 4.7e-2 of the range away from the float64 one on dL/dx /
+    dL/dparams), so the kernels are held to the float32 oracle's own distance to float64, not to an absolute bound."""
     from oracle import nets
     from selfpose3d_b200.models import v2v_net
     net = v2v_net.V2VNet(15, 15)
@@ -285,24 +287,33 @@ def test_v2v_net_training_step_pose_size_vs_oracle():
     rs = np.random.RandomState(5)
     x = torch.from_numpy(rs.rand(1, 15, 32, 32, 32).astype(np.float32))
     gy = torch.from_numpy(rs.randn(1, 15, 32, 32, 32).astype(np.float32))
-    sd = {k: (v.double().clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
-          for k, v in sd0.items()}
-    xo = x.double().clone().requires_grad_(True)
-    yo = nets.v2v_forward(xo, sd, dtype=torch.float64, training=True)
-    (yo * gy.double()).sum().backward()
+
+    def oracle(dtype):
+        sd = {k: (v.to(dtype).clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+              for k, v in sd0.items()}
+        xo = x.to(dtype).clone().requires_grad_(True)
+        yo = nets.v2v_forward(xo, sd, dtype=dtype, training=True)
+        (yo * gy.to(dtype)).sum().backward()
+        return yo.detach(), xo.grad, sd
+
+    y64, gx64, sd64 = oracle(torch.float64)
+    y32, gx32, sd32 = oracle(torch.float32)
     net = net.to(DEV).train()
     xin = x.to(DEV).requires_grad_(True)
     y = net(xin)
     (y * gy.to(DEV)).sum().backward()
-    assert rel_err(y.detach().cpu().numpy(), yo.detach().numpy()) <= 1e-4
-    assert rel_err(xin.grad.cpu().numpy(), xo.grad.numpy()) <= 1e-3
-    worst = 0.0
+    assert rel_err(y.detach().cpu().numpy(), y64.numpy()) <= 1e-4
+    e_x, r_x = rel_err(xin.grad.cpu().numpy(), gx64.numpy()), rel_err(gx32.numpy(), gx64.numpy())
+    assert e_x <= max(1e-3, 3 * r_x), (e_x, r_x)
+    worst, worst_ref = 0.0, 0.0
     for name, p in net.named_parameters():
-        ref = sd[name].grad
+        ref = sd64[name].grad
         if float(ref.abs().max()) < 1e-9 * float(gy.abs().max()):
             continue                                   # conv biases in front of a batch normalisation cancel exactly
         worst = max(worst, rel_err(p.grad.cpu().numpy(), ref.numpy()))
-    assert worst <= 2e-3, worst
+        worst_ref = max(worst_ref, rel_err(sd32[name].grad.numpy(), ref.numpy()))
+    print("V2VNet(15) 32^3 training step: dL/dx %.3g (float32 oracle %.3g), dL/dparams %.3g (%.3g)" % (e_x, r_x, worst, worst_ref))
+    assert worst <= max(2e-3, 3 * worst_ref), (worst, worst_ref)
 
 
 def test_pose_regression_net_training_step_vs_oracle(golden):
