@@ -42,8 +42,9 @@ class Conv(Function):
     """Raw convolution / transposed convolution (+ bias) of an ``nn.Conv*`` / ``nn.ConvTranspose*`` parameter pair."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, padding, transposed):
-        pc = ops.PackedConv(weight, bias, None, stride, padding, transposed=transposed, relu=0)
+    def forward(ctx, x, weight, bias, stride, padding, transposed, pc=None):
+        if pc is None:
+            pc = ops.PackedConv(weight, bias, None, stride, padding, transposed=transposed, relu=0)
         ctx.pc, ctx.has_bias = pc, bias is not None
         ctx.save_for_backward(x)
         return pc(x, algo=_lib.CONV_SIMT_F32)
@@ -54,7 +55,7 @@ class Conv(Function):
         gy = gy.contiguous()
         gx = grad_ops.conv_dgrad(ctx.pc, gy, out_pitch=int(x.shape[-1])) if ctx.needs_input_grad[0] else None
         gw, gb = grad_ops.conv_wgrad(ctx.pc, x, gy, with_bias=ctx.has_bias)
-        return gx, gw, gb, None, None, None
+        return gx, gw, gb, None, None, None, None
 
 
 class BatchNormAct(Function):
@@ -111,8 +112,16 @@ class MaxPool(Function):
 
 
 def conv(x, module, transposed=False):
-    """``module``: ``nn.Conv{2,3}d`` / ``nn.ConvTranspose{2,3}d`` -> raw convolution of channel-last ``x``."""
-    return Conv.apply(x, module.weight, module.bias, int(module.stride[0]), int(module.padding[0]), transposed)
+    """``module``: ``nn.Conv{2,3}d`` / ``nn.ConvTranspose{2,3}d`` -> raw convolution of channel-last ``x``.
+    The packed weight (and its adjoint for the input gradient) is kept on the module until the parameter changes
+    (optimizer step, ``load_state_dict``, ``.to()``)."""
+    w, b = module.weight, module.bias
+    key = (w.data_ptr(), w._version, None if b is None else (b.data_ptr(), b._version), transposed)
+    hit = module.__dict__.get("_sp3d_train_pack")
+    if hit is None or hit[0] != key:
+        pc = ops.PackedConv(w, b, None, int(module.stride[0]), int(module.padding[0]), transposed=transposed, relu=0)
+        hit = module.__dict__["_sp3d_train_pack"] = (key, pc)
+    return Conv.apply(x, w, b, int(module.stride[0]), int(module.padding[0]), transposed, hit[1])
 
 
 def batch_norm(x, bn, relu=False):

@@ -483,7 +483,7 @@ def conv_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksi
             flops *= 8
         detail = "conv%s algo%d k%d %d->%d @%dx%dx%dx%d" % ("T8" if fused_phases else "", a.algo, a.ksize[2],
                                                            cin_real or a.cin, a.cout, a.N, a.OD, a.OH, a.OW)
-        if len(_CONV_ARGS_CACHE) > 4096:
+        if len(_CONV_ARGS_CACHE) > 1024:   # (entries pin their packed weights; training re-packs after every step)
             _CONV_ARGS_CACHE.clear()
         # (weight, scale, shift) are kept alive by the cache entry so that their addresses cannot be recycled
         hit = _CONV_ARGS_CACHE[key] = (a, flops, detail, (weight, scale, shift), (int(relu), int(cout), int(cin)))
