@@ -87,12 +87,21 @@ class CuboidProposalNet(nn.Module):
         if cams is None:
             cams = ops.pack_cameras(meta, self.project_layer.img_size, flip_xcoords).to(device, non_blocking=True)
         centers, _ = self.project_layer.centers_tensor([list(self.grid_center)], B, device)
+        if self.v2v_net.training:
+            # training path (float32): differentiable un-projection -> V2VNet with batch statistics; gradients reach the
+            # heat-maps and the net's parameters
+            from .. import autograd as ag
+            if ops.volume_dtype() != torch.float32:
+                raise ValueError("the training path runs on float32 volumes (ops.set_volume_dtype(torch.float32))")
+            C = int(hms[0].shape[1])
+            spec = ([float(v) for v in self.grid_size], [int(v) for v in self.cube_size], self.project_layer.img_size,
+                    self.project_layer.heatmap_size, C, ops.round_up(C, 4))
+            cubes = ag.Unproject.apply(cams, centers, None, spec, *[h.float().contiguous() for h in hms])
+            return self.v2v_net.forward_cl(cubes)[..., 0].contiguous()
         bf16 = ops.volume_dtype() == torch.bfloat16
         cubes, _ = self.project_layer.project_cl(hms, cams, centers, False, self.grid_size, self.cube_size,
                                                  dtype=ops.volume_dtype(),
                                                  c_pitch=ops.round_up(hms[0].shape[1], 16) if bf16 else None)
-        if self.v2v_net.training:   # batch-statistics BatchNorm + gradients of the net's own parameters (float32 path)
-            return self.v2v_net.forward_cl(cubes)[..., 0].contiguous()
         root = self.v2v_net.forward_cl(cubes, out_pitch=1)
         return root.view(root.shape[0], root.shape[1], root.shape[2], root.shape[3])
 

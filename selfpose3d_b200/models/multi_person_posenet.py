@@ -43,9 +43,7 @@ class MultiPersonPoseNet(nn.Module):
     def forward(self, views=None, meta=None, targets_2d=None, weights_2d=None, targets_3d=None,
                 input_heatmaps=None):
         if self.training:
-            raise NotImplementedError(
-                "selfpose3d_b200: supervised training forward/backward is not implemented in this backend yet; "
-                "call .eval()")
+            return self._forward_train(views, meta, targets_2d, weights_2d, targets_3d, input_heatmaps)
         with torch.no_grad():
             if self.train_only_2d:
                 all_heatmaps = (_inference.backbone_heatmaps(self.backbone, views) if views is not None
@@ -67,6 +65,69 @@ class MultiPersonPoseNet(nn.Module):
                 loss_3d = _per_joint_mse(root_cubes, targets_3d.to(device))
             loss_cord = torch.zeros((), device=device)   # only accumulated when training (reference :90-99)
             return pred, all_heatmaps, grid_centers, loss_2d, loss_3d, loss_cord
+
+
+def _per_joint_l1(output, target, weight):
+    """PerJointL1Loss with target weights (reference lib/core/loss.py:61-78)."""
+    B, J = output.shape[:2]
+    return torch.mean(torch.abs(output.reshape(B, J, -1) * weight - target.reshape(B, J, -1) * weight))
+
+
+def _forward_train(self, views, meta, targets_2d, weights_2d, targets_3d, input_heatmaps):
+    """The supervised training forward (reference multi_person_posenet.py:36-102 with ``self.training``): root net and
+    pose net run their training paths (batch-statistics BatchNorm, gradients through the backward kernels), the pose
+    net once per proposal slot on the rows matched to a ground-truth person -- as the reference does, so that the
+    batch statistics see the same batches.  The three losses are plain reductions over small tensors.  The 2-D
+    backbone's own training mode is not built: with ``views`` it must be in ``.eval()`` (frozen), its heat-maps then
+    enter as constants."""
+    if views is not None:
+        if self.backbone.training:
+            raise NotImplementedError("selfpose3d_b200: the 2-D backbone has no training path yet; freeze it "
+                                      "(model.backbone.eval()) or pass input_heatmaps")
+        with torch.no_grad():
+            all_heatmaps = _inference.backbone_heatmaps(self.backbone, views)
+    else:
+        all_heatmaps = [h if h.is_cuda else h.cuda() for h in input_heatmaps]
+    device = all_heatmaps[0].device
+    B = int(all_heatmaps[0].shape[0])
+    loss_2d = torch.zeros((), device=device)
+    if targets_2d is not None:
+        for t, w, o in zip(targets_2d, weights_2d, all_heatmaps):
+            loss_2d = loss_2d + _per_joint_mse(o, t.to(device), w.to(device))
+        loss_2d = loss_2d / len(all_heatmaps)
+    if self.train_only_2d:
+        return loss_2d, all_heatmaps
+    loss_3d = torch.zeros((), device=device)
+    if self.USE_GT:
+        grid_centers = _inference.gt_grid_centers(meta, B, self.num_cand, device)
+    else:
+        root_cubes, grid_centers = self.root_net(all_heatmaps, meta)
+        if targets_3d is not None:
+            loss_3d = _per_joint_mse(root_cubes, targets_3d.to(device))
+    pred = torch.zeros(B, self.num_cand, self.num_joints, 5, device=device)
+    pred[:, :, :, 3:] = grid_centers[:, :, 3:].reshape(B, -1, 1, 2)
+    loss_cord = torch.zeros((), device=device)
+    count = 0
+    has_gt = "joints_3d" in meta[0] and "joints_3d_vis" in meta[0]
+    flags = grid_centers[:, :, 3].detach().cpu()                       # one host sync (the reference: one per slot)
+    for n in range(self.num_cand):
+        if not bool((flags[:, n] >= 0).any()):
+            continue
+        single_pose = self.pose_net(all_heatmaps, meta, grid_centers[:, n])
+        pred[:, n, :, 0:3] = single_pose.detach()
+        if has_gt:
+            gt_3d = meta[0]["joints_3d"].float().to(device)
+            vis = meta[0]["joints_3d_vis"].float().to(device)
+            for i in range(B):
+                if flags[i, n] >= 0:
+                    g = int(flags[i, n])
+                    count += 1
+                    term = _per_joint_l1(single_pose[i:i + 1], gt_3d[i:i + 1, g], vis[i:i + 1, g, :, 0:1])
+                    loss_cord = (loss_cord * (count - 1) + term) / count
+    return pred, all_heatmaps, grid_centers, loss_2d, loss_3d, loss_cord
+
+
+MultiPersonPoseNet._forward_train = _forward_train
 
 
 def get_multi_person_pose_net(cfg, is_train=True):

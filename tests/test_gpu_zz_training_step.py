@@ -1,0 +1,70 @@
+"""GPU: one supervised training step of ``MultiPersonPoseNet`` (root net + pose net in ``.train()``, heat-maps given)
+through the kernels, against the step recorded from the unmodified reference (``backward.npz``, keys ``sup_*``).
+
+The host-side logic of this step is pinned on CPU (tests/test_training_cpu.py, kernels emulated) and every kernel it
+launches is checked on the GPU on its own (tests/test_gpu_backward.py).  This end-to-end composition was written
+after the round's GPU budget was spent, so its first B200 run is the round-end run: it is a NON-STRICT xfail until
+it has been seen green once (an XPASS in the log is that observation)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+from selfpose3d_b200 import synthetic  # noqa: E402
+from selfpose3d_b200.config import default_config  # noqa: E402
+from selfpose3d_b200.models import multi_person_posenet  # noqa: E402
+
+DEV = "cuda:0"
+
+
+@pytest.mark.xfail(strict=False, reason="first B200 run of this composition (GPU budget of the round was spent); "
+                                        "host logic verified on CPU in tests/test_training_cpu.py")
+def test_supervised_training_step_matches_reference_on_gpu(golden):
+    g, gb = golden("inference_small"), golden("backward")
+    cfg = default_config()
+    J = int(g["num_joints"])
+    cfg.NETWORK.IMAGE_SIZE, cfg.NETWORK.HEATMAP_SIZE = [int(v) for v in g["image_size"]], [int(v) for v in g["heatmap_size"]]
+    cfg.NETWORK.NUM_JOINTS = J
+    cfg.DATASET.ROOTIDX = cfg.DATASET.ROOTIDX_PSEUDO = 2
+    cfg.NETWORK.ROOTNET_ROOTHM, cfg.NETWORK.USE_GT, cfg.NETWORK.TRAIN_ONLY_2D, cfg.NETWORK.BETA = True, False, False, 100.0
+    cfg.MULTI_PERSON.SPACE_SIZE = [float(v) for v in g["space_size"]]
+    cfg.MULTI_PERSON.SPACE_CENTER = [float(v) for v in g["space_center"]]
+    cfg.MULTI_PERSON.INITIAL_CUBE_SIZE = [int(v) for v in g["initial_cube_size"]]
+    cfg.MULTI_PERSON.MAX_PEOPLE_NUM = int(g["max_people"])
+    cfg.MULTI_PERSON.THRESHOLD = float(g["threshold"])
+    cfg.PICT_STRUCT.GRID_SIZE = [float(v) for v in g["grid_size"]]
+    cfg.PICT_STRUCT.CUBE_SIZE = [int(v) for v in g["cube_size"]]
+    cfg.BACKBONE_MODEL = ""
+    model = multi_person_posenet.get_multi_person_pose_net(cfg, is_train=True)
+    model.load_state_dict(synthetic.trained_like_state_dict(model, seed=int(gb["sup_seed"])), strict=True)
+    model = model.to(DEV).train()
+    V = g["heatmaps"].shape[0]
+    meta = [{"center": torch.from_numpy(g["center"][v]), "scale": torch.from_numpy(g["scale"][v]),
+             "rotation": torch.from_numpy(g["rotation"][v]),
+             "camera": {k[4:]: torch.from_numpy(g[k][v]) for k in g if k.startswith("cam_")}} for v in range(V)]
+    meta[0].update(roots_3d=torch.from_numpy(gb["sup_roots_3d"]), num_person=torch.from_numpy(gb["sup_num_person"]),
+                   joints_3d=torch.from_numpy(gb["sup_joints_3d"]), joints_3d_vis=torch.from_numpy(gb["sup_joints_3d_vis"]))
+    hms = [torch.from_numpy(g["heatmaps"][v]).to(DEV).requires_grad_(True) for v in range(V)]
+    pred, _, gc, loss_2d, loss_3d, loss_cord = model(views=None, meta=meta, targets_3d=torch.from_numpy(gb["sup_targets_3d"]),
+                                                     input_heatmaps=hms)
+    (loss_3d + loss_cord).backward()
+    gc = gc.detach().cpu().numpy()
+    np.testing.assert_allclose(gc[..., :3], gb["sup_grid_centers"][..., :3], rtol=1e-5, atol=1e-3)
+    assert np.array_equal(gc[..., 3], gb["sup_grid_centers"][..., 3])
+    np.testing.assert_allclose(gc[..., 4], gb["sup_grid_centers"][..., 4], rtol=0, atol=1e-5)
+    assert abs(float(loss_3d) - float(gb["sup_loss_3d"])) <= 1e-5 * float(gb["sup_loss_3d"])
+    assert abs(float(loss_cord) - float(gb["sup_loss_cord"])) <= 1e-4 * float(gb["sup_loss_cord"])
+    np.testing.assert_allclose(pred.detach().cpu().numpy(), gb["sup_pred"], rtol=0, atol=0.3)
+    gh = np.stack([h.grad.cpu().numpy() for h in hms])
+    want = gb["sup_grad_heatmaps"]
+    assert np.abs(gh - want).max() <= 2e-3 * np.abs(want).max()
+    params = dict(model.named_parameters())
+    top = float(gb["sup_param_grad_norm"].max())
+    for name, norm in zip(gb["sup_param_names"], gb["sup_param_grad_norm"]):
+        p = params[str(name)]
+        gn = 0.0 if p.grad is None else float(p.grad.double().norm())
+        if norm < 1e-5 * top or str(name) == "pose_net.v2v_net.output_layer.bias":   # cancelled: rounding noise only
+            assert gn < 1e-3 * top, (name, gn, norm)
+            continue
+        assert abs(gn - norm) <= 5e-3 * norm, (name, gn, norm)

@@ -1,0 +1,151 @@
+"""CPU check of the supervised training forward (``models/multi_person_posenet.py`` ``_forward_train``, the training
+branches of ``CuboidProposalNet`` / ``PoseRegressionNet``) against ONE TRAINING STEP RECORDED FROM THE UNMODIFIED
+REFERENCE (``tests/golden/make_golden_backward.py`` -> ``backward.npz``, keys ``sup_*``): proposals, matched
+ground-truth ids, joints, both 3-D losses, the gradient of every heat-map and the gradient norm / sum of all 180
+parameters.  Every kernel entry point is replaced by a torch / numpy emulation of its documented semantics
+(include/sp3d.h), so this pins the host-side logic; the kernels are checked on the GPU
+(tests/test_gpu_backward.py)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import volume_ops
+from selfpose3d_b200 import autograd as ag
+from selfpose3d_b200 import ops, synthetic
+from selfpose3d_b200.config import default_config
+from selfpose3d_b200.models import multi_person_posenet
+from test_autograd_cpu import emulated  # noqa: F401  (fixture: convolution / BatchNorm / pooling kernels emulated)
+
+
+def emul_unproject(cams, centers, cube_sample, spec, *hms):
+    """sp3d_unproject_fwd (include/sp3d.h; lib/models/project_layer.py:42-102) from the packed camera table, with
+    torch ops so that autograd provides sp3d_unproject_bwd's result."""
+    grid_size, cube_size, img_size, hm_cfg_wh, C, pitch = spec
+    X, Y, Z = [int(v) for v in cube_size]
+    N = X * Y * Z
+    W, H = float(img_size[0]), float(img_size[1])
+    wc, hc = float(hm_cfg_wh[0]), float(hm_cfg_wh[1])
+    lin = [torch.linspace(-grid_size[a] / 2, grid_size[a] / 2, cube_size[a]) for a in range(3)]
+    cubes = []
+    for q in range(int(centers.shape[0])):
+        b = int(cube_sample[q]) if cube_sample is not None else q
+        gx, gy, gz = torch.meshgrid(*[lin[a] + centers[q, a] for a in range(3)], indexing="ij")
+        grid = torch.stack([gx.reshape(-1), gy.reshape(-1), gz.reshape(-1)], dim=1)
+        num, den = torch.zeros(C, N), torch.zeros(N)
+        for v in range(len(hms)):
+            cam = cams[b, v]
+            R, T, k, p, A = cam[0:9].view(3, 3), cam[9:12], cam[16:19], cam[19:21], cam[21:27].view(2, 3)
+            xcam = torch.mm(R, grid.t() - T[:, None])
+            y = xcam[:2] / (xcam[2] + 1e-5)
+            r2 = torch.clamp((y ** 2).sum(0), max=1e10)
+            corr = 1 + k[0] * r2 + k[1] * r2 ** 2 + k[2] * r2 ** 3 + 2 * (p[0] * y[1] + p[1] * y[0])
+            px = cam[12] * (y[0] * corr + p[1] * r2) + cam[14]
+            py = cam[13] * (y[1] * corr + p[0] * r2) + cam[15]
+            width, height = float(cam[27]), float(cam[28])
+            m = ((px >= 0) & (py >= 0) & (px < width) & (py < height)).float()
+            px, py = px.clamp(-1.0, max(width, height)), py.clamp(-1.0, max(width, height))
+            qx = A[0, 0] * px + A[0, 1] * py + A[0, 2]
+            qy = A[1, 0] * px + A[1, 1] * py + A[1, 2]
+            if float(cam[29]) != 0:
+                qx = W - qx
+            sx = (qx * wc / W / (wc - 1) * 2.0 - 1.0).clamp(-1.1, 1.1)
+            sy = (qy * hc / H / (hc - 1) * 2.0 - 1.0).clamp(-1.1, 1.1)
+            s = F.grid_sample(hms[v][b:b + 1], torch.stack([sx, sy], dim=1).view(1, 1, N, 2), align_corners=True)[0, :, 0]
+            num, den = num + s * m[None], den + m
+        o = num / (den + 1e-6)[None]
+        o = torch.where(o != o, torch.zeros_like(o), o).clamp(0.0, 1.0)
+        cubes.append(F.pad(o.t().reshape(X, Y, Z, C), (0, pitch - C)))
+    return torch.stack(cubes)
+
+
+def emul_softargmax(y, centers, spec):
+    """sp3d_softargmax3d_fwd: sum_v softmax(beta x)_v * fl(lin + centre) (lib/models/pose_regression_net.py:19-28)."""
+    C, cube_size, grid_size, beta = spec
+    n = int(y.shape[0])
+    lin = [torch.linspace(-grid_size[a] / 2, grid_size[a] / 2, cube_size[a]) for a in range(3)]
+    out = []
+    for q in range(n):
+        gx, gy, gz = torch.meshgrid(*[lin[a] + centers[q, a] for a in range(3)], indexing="ij")
+        grid = torch.stack([gx.reshape(-1), gy.reshape(-1), gz.reshape(-1)], dim=1)            # [N, 3]
+        p = F.softmax(beta * y[q, ..., :C].reshape(-1, C).t(), dim=1)                           # [C, N]
+        out.append(p @ grid)
+    return torch.stack(out)
+
+
+def emul_nms_topk(root_cubes, max_people, threshold, space_size, space_center, loc_f64=False, return_index=False):
+    gc = volume_ops.proposal_layer(root_cubes.detach().numpy(), space_size, space_center, list(root_cubes.shape[1:]),
+                                   int(max_people), float(threshold), f64=loc_f64)
+    return torch.from_numpy(np.asarray(gc, dtype=np.float32))
+
+
+class _Apply:
+    def __init__(self, fn):
+        self.apply = staticmethod(fn).__func__
+
+
+def test_supervised_training_step_matches_reference(emulated, monkeypatch, golden):  # noqa: F811
+    monkeypatch.setattr(ag, "Unproject", _Apply(emul_unproject))
+    monkeypatch.setattr(ag, "SoftArgmax", _Apply(emul_softargmax))
+    monkeypatch.setattr(ops, "nms_topk", emul_nms_topk)
+    g, gb = golden("inference_small"), golden("backward")
+    cfg = default_config()
+    J = int(g["num_joints"])
+    cfg.NETWORK.IMAGE_SIZE, cfg.NETWORK.HEATMAP_SIZE = [int(v) for v in g["image_size"]], [int(v) for v in g["heatmap_size"]]
+    cfg.NETWORK.NUM_JOINTS = J
+    cfg.DATASET.ROOTIDX = cfg.DATASET.ROOTIDX_PSEUDO = 2
+    cfg.NETWORK.ROOTNET_ROOTHM, cfg.NETWORK.USE_GT, cfg.NETWORK.TRAIN_ONLY_2D, cfg.NETWORK.BETA = True, False, False, 100.0
+    cfg.MULTI_PERSON.SPACE_SIZE = [float(v) for v in g["space_size"]]
+    cfg.MULTI_PERSON.SPACE_CENTER = [float(v) for v in g["space_center"]]
+    cfg.MULTI_PERSON.INITIAL_CUBE_SIZE = [int(v) for v in g["initial_cube_size"]]
+    cfg.MULTI_PERSON.MAX_PEOPLE_NUM = int(g["max_people"])
+    cfg.MULTI_PERSON.THRESHOLD = float(g["threshold"])
+    cfg.PICT_STRUCT.GRID_SIZE = [float(v) for v in g["grid_size"]]
+    cfg.PICT_STRUCT.CUBE_SIZE = [int(v) for v in g["cube_size"]]
+    cfg.BACKBONE_MODEL = ""
+    model = multi_person_posenet.get_multi_person_pose_net(cfg, is_train=True)
+    model.load_state_dict(synthetic.trained_like_state_dict(model, seed=int(gb["sup_seed"])), strict=True)
+    model.train()
+    V = g["heatmaps"].shape[0]
+    meta = [{"center": torch.from_numpy(g["center"][v]), "scale": torch.from_numpy(g["scale"][v]),
+             "rotation": torch.from_numpy(g["rotation"][v]),
+             "camera": {k[4:]: torch.from_numpy(g[k][v]) for k in g if k.startswith("cam_")}} for v in range(V)]
+    meta[0].update(roots_3d=torch.from_numpy(gb["sup_roots_3d"]), num_person=torch.from_numpy(gb["sup_num_person"]),
+                   joints_3d=torch.from_numpy(gb["sup_joints_3d"]), joints_3d_vis=torch.from_numpy(gb["sup_joints_3d_vis"]))
+    hms = [torch.from_numpy(g["heatmaps"][v]).clone().requires_grad_(True) for v in range(V)]
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)     # the module API moves inputs to the GPU
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
+    pred, _, gc, loss_2d, loss_3d, loss_cord = model(views=None, meta=meta, targets_3d=torch.from_numpy(gb["sup_targets_3d"]),
+                                                     input_heatmaps=hms)
+    (loss_3d + loss_cord).backward()
+
+    np.testing.assert_allclose(gc.detach().numpy()[..., :3], gb["sup_grid_centers"][..., :3], rtol=1e-5, atol=1e-3)
+    assert np.array_equal(gc.detach().numpy()[..., 3], gb["sup_grid_centers"][..., 3])          # matched ground-truth ids
+    np.testing.assert_allclose(gc.detach().numpy()[..., 4], gb["sup_grid_centers"][..., 4], rtol=0, atol=1e-5)
+    assert float(loss_2d) == 0.0
+    assert abs(float(loss_3d) - float(gb["sup_loss_3d"])) <= 1e-5 * float(gb["sup_loss_3d"])
+    assert abs(float(loss_cord) - float(gb["sup_loss_cord"])) <= 1e-4 * float(gb["sup_loss_cord"])
+    # (the emulated convolutions accumulate in float64, the reference in float32: beta = 100 turns that into ~0.1 mm)
+    np.testing.assert_allclose(pred.detach().numpy(), gb["sup_pred"], rtol=0, atol=0.3)          # mm
+    gh = np.stack([h.grad.numpy() for h in hms])
+    want = gb["sup_grad_heatmaps"]
+    assert np.abs(gh - want).max() <= 2e-3 * np.abs(want).max(), np.abs(gh - want).max() / np.abs(want).max()
+    params = dict(model.named_parameters())
+    top = float(gb["sup_param_grad_norm"].max())
+    checked = 0
+    for name, norm, tot in zip(gb["sup_param_names"], gb["sup_param_grad_norm"], gb["sup_param_grad_sum"]):
+        p = params[str(name)]
+        gn = 0.0 if p.grad is None else float(p.grad.double().norm())
+        if norm < 1e-5 * top:      # convolution biases in front of a batch normalisation: cancelled, rounding noise only
+            assert gn < 1e-4 * top, (name, gn, norm)
+            continue
+        if str(name) == "pose_net.v2v_net.output_layer.bias":
+            # the soft-argmax is invariant to a per-channel shift of its input: this gradient is exactly zero and what
+            # either side reports is float32 noise of sum_v dx_v (beta = 100)
+            assert gn < 1e-3 * top, (name, gn, norm)
+            continue
+        assert abs(gn - norm) <= 5e-3 * norm, (name, gn, norm)
+        gs = float(p.grad.double().sum())
+        assert abs(gs - tot) <= 5e-3 * norm * max(1.0, np.sqrt(p.numel())), (name, gs, tot)
+        checked += 1
+    assert checked >= 60, checked
