@@ -99,8 +99,18 @@ def _bottleneck(x, sd, pfx, stride):
     return F.relu(out + x)
 
 
-def pose_resnet_forward(x, sd, pfx="", layers=(3, 4, 6, 3), dtype=torch.float32):
-    """PoseResNet.forward (pose_resnet.py:191-207) for Bottleneck nets, deconv k4 s2 p1 without bias."""
+def pose_resnet_forward(x, sd, pfx="", layers=(3, 4, 6, 3), dtype=torch.float32, training=False):
+    """PoseResNet.forward (pose_resnet.py:191-207) for Bottleneck nets, deconv k4 s2 p1 without bias.  ``training``:
+    the module in ``.train()`` mode (batch-statistics BatchNorm); differentiable."""
+    global _BATCH_STATS
+    _BATCH_STATS = bool(training)
+    try:
+        return _pose_resnet_forward(x, sd, pfx, layers, dtype)
+    finally:
+        _BATCH_STATS = False
+
+
+def _pose_resnet_forward(x, sd, pfx, layers, dtype):
     sd = _cast(sd, dtype)
     x = x.to(dtype)
     x = F.relu(_bn(F.conv2d(x, sd[pfx + "conv1.weight"], stride=2, padding=3), sd, pfx + "bn1"))

@@ -53,7 +53,8 @@ class Conv(Function):
     def backward(ctx, gy):
         (x,) = ctx.saved_tensors
         gy = gy.contiguous()
-        gx = grad_ops.conv_dgrad(ctx.pc, gy, out_pitch=int(x.shape[-1])) if ctx.needs_input_grad[0] else None
+        gx = (grad_ops.conv_dgrad(ctx.pc, gy, out_pitch=int(x.shape[-1]), in_dims=tuple(x.shape[1:4]))
+              if ctx.needs_input_grad[0] else None)
         gw, gb = grad_ops.conv_wgrad(ctx.pc, x, gy, with_bias=ctx.has_bias)
         return gx, gw, gb, None, None, None, None
 

@@ -133,6 +133,10 @@ def conv_wgrad(pc, x, grad_out, with_bias=True):
     for (_, off0, ks, grid, step, ostride, ooff) in launches:
         taps = int(ks[0] * ks[1] * ks[2])
         gw = torch.zeros(taps, pc.cin_p, pc.cout_pw, device=x.device, dtype=torch.float32)
+        if taps == 0 or min(grid) <= 0:        # a phase without taps / without output positions
+            subs.append(gw[:, :pc.cin, :pc.cout].reshape(int(ks[0]), int(ks[1]), int(ks[2]), pc.cin, pc.cout)
+                        .permute(4, 3, 0, 1, 2))
+            continue
         b = _lib.ConvWgradArgs()
         _conv_geometry(b.fwd, x, grad_out.shape, pc.cin_p, pc.cout, pc.cout_pw, grid, ks,
                        pc.stride if not pc.transposed else [1, 1, 1], off0, step, ostride, ooff)
@@ -156,31 +160,41 @@ def conv_wgrad(pc, x, grad_out, with_bias=True):
     return w5.reshape(shape).contiguous(), gb
 
 
-def conv_dgrad(pc, grad_out, out_pitch=None):
+def conv_dgrad(pc, grad_out, out_pitch=None, in_dims=None):
     """Input gradient of the convolution ``pc`` (raw convolution, no scale / shift / ReLU) -- the forward kernel
-    on the adjoint weight.  Covered: stride-1 "same" convolutions (adjoint = the flipped, channel-transposed kernel)
-    and kernel == stride transposed convolutions without padding (adjoint = the strided convolution with the same
-    kernel): every layer of V2VNet and the stride-1 layers of PoseResNet."""
+    on the adjoint operator:
+      * stride-1 convolution           -> convolution with the flipped, channel-transposed kernel, padding k-1-p;
+      * strided convolution            -> transposed convolution with the same kernel (``in_dims``: the forward input's
+                                          spatial extent ``(D, H, W)``, which the output extent alone does not determine);
+      * transposed convolution         -> strided convolution with the same kernel."""
     _f32(grad_out)
     adj = pc.__dict__.get("_adjoint")
     if adj is None:
-        w = pc._subs[0] if not pc.transposed else None
-        if not pc.transposed:
-            if pc.stride != [1, 1, 1] or any(2 * pc.padding[i] != pc.k[i] - 1 for i in range(3)):
-                raise _lib.Sp3dError("conv_dgrad covers stride-1 'same' convolutions")
-            wa = w.permute(1, 0, 2, 3, 4).flip(2, 3, 4)            # [Cin, Cout, k..] = an nn.Conv weight with Cout' = Cin
-            wa = wa.reshape(list(wa.shape[:2]) + list(wa.shape[2 + (3 - pc.nd):]))
-            adj = ops.PackedConv(wa.contiguous(), None, None, 1, pc.padding[-1], relu=0)
+        def as_param(w5):        # [A, B, kd, kh, kw] -> drop the leading unit dims of a 2-D kernel
+            return w5.reshape(list(w5.shape[:2]) + list(w5.shape[2 + (3 - pc.nd):])).contiguous()
+        if not pc.transposed and pc.stride == [1, 1, 1]:
+            wa = pc._subs[0].permute(1, 0, 2, 3, 4).flip(2, 3, 4)      # an nn.Conv weight with Cout' = Cin
+            pads = [pc.k[i] - 1 - pc.padding[i] for i in range(3)][3 - pc.nd:]
+            if len(set(pads)) != 1:
+                raise _lib.Sp3dError("conv_dgrad: anisotropic padding is not covered")
+            adj = ops.PackedConv(as_param(wa), None, None, 1, pads[0], relu=0)
+        elif not pc.transposed:
+            # adjoint of a strided convolution: nn.ConvTranspose weight layout [in = Cout, out = Cin, k..] = the kernel as is
+            adj = ops.PackedConv(as_param(pc._subs[0]), None, None, pc.stride[-1], pc.padding[-1], transposed=True, relu=0)
         else:
-            if pc.k != pc.stride or any(pc.padding):
-                raise _lib.Sp3dError("conv_dgrad covers kernel == stride transposed convolutions without padding")
             full = torch.zeros(pc.cout, pc.cin, *pc.k, device=grad_out.device, dtype=torch.float32)
+            s_, p_ = pc.stride, pc.padding
             for sub, (phase, _, _) in zip(pc._subs, pc.phases):
-                full[:, :, phase[0]::pc.stride[0], phase[1]::pc.stride[1], phase[2]::pc.stride[2]] = sub
-            wa = full.permute(1, 0, 2, 3, 4)                       # [Cin_t, Cout_t, k..]: a strided nn.Conv weight
-            wa = wa.reshape(list(wa.shape[:2]) + list(wa.shape[2 + (3 - pc.nd):]))
-            adj = ops.PackedConv(wa.contiguous(), None, None, pc.stride[-1], 0, relu=0)
+                if sub.numel():
+                    t0 = [(phase[i] + p_[i]) % s_[i] for i in range(3)]
+                    full[:, :, t0[0]::s_[0], t0[1]::s_[1], t0[2]::s_[2]] = sub
+            # [Cin_t, Cout_t, k..]: an nn.Conv weight (Cout' = Cin_t) applied with the transposed convolution's stride / padding
+            adj = ops.PackedConv(as_param(full.permute(1, 0, 2, 3, 4)), None, None, pc.stride[-1], pc.padding[-1], relu=0)
         pc.__dict__["_adjoint"] = adj
+    if adj.transposed:
+        if in_dims is None:
+            raise _lib.Sp3dError("conv_dgrad of a strided convolution needs in_dims (the forward input's extent)")
+        return adj(grad_out, algo=_lib.CONV_SIMT_F32, out_pitch=out_pitch, out_dims=[int(v) for v in in_dims])
     return adj(grad_out, algo=_lib.CONV_SIMT_F32, out_pitch=out_pitch)
 
 

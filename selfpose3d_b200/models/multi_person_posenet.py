@@ -77,15 +77,15 @@ def _forward_train(self, views, meta, targets_2d, weights_2d, targets_3d, input_
     """The supervised training forward (reference multi_person_posenet.py:36-102 with ``self.training``): root net and
     pose net run their training paths (batch-statistics BatchNorm, gradients through the backward kernels), the pose
     net once per proposal slot on the rows matched to a ground-truth person -- as the reference does, so that the
-    batch statistics see the same batches.  The three losses are plain reductions over small tensors.  The 2-D
-    backbone's own training mode is not built: with ``views`` it must be in ``.eval()`` (frozen), its heat-maps then
-    enter as constants."""
+    batch statistics see the same batches.  The three losses are plain reductions over small tensors.  A backbone
+    in ``.train()`` mode runs once per view (the reference's batches, :38-41) on its own training path; a frozen one
+    (``.eval()``) runs the fused inference kernels on all views at once and its heat-maps enter as constants."""
     if views is not None:
         if self.backbone.training:
-            raise NotImplementedError("selfpose3d_b200: the 2-D backbone has no training path yet; freeze it "
-                                      "(model.backbone.eval()) or pass input_heatmaps")
-        with torch.no_grad():
-            all_heatmaps = _inference.backbone_heatmaps(self.backbone, views)
+            all_heatmaps = [self.backbone(view) for view in views]
+        else:
+            with torch.no_grad():
+                all_heatmaps = _inference.backbone_heatmaps(self.backbone, views)
     else:
         all_heatmaps = [h if h.is_cuda else h.cuda() for h in input_heatmaps]
     device = all_heatmaps[0].device

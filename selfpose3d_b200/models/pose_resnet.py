@@ -7,6 +7,10 @@ tree and state-dict keys (338 tensors for ResNet-50).  The forward pass lowers t
 ``sp3d_conv_fwd`` / ``sp3d_maxpool_fwd`` launches on channel-last activations with
 evaluation-mode BatchNorm, ReLU and the residual add fused into the convolution epilogue;
 a transposed 4x4 stride-2 convolution is four stride-1 2x2 sub-convolutions, one per output phase.
+
+In ``.train()`` mode the net takes the training path of ``selfpose3d_b200.autograd`` (float32, raw convolution ->
+batch-statistics BatchNorm with the running-average update -> ReLU / residual joins; backward through
+``sp3d_conv_wgrad``, the forward kernel on the adjoint operator, ``sp3d_bn_bwd``, ``sp3d_maxpool_bwd``).
 """
 from __future__ import annotations
 
@@ -16,8 +20,9 @@ import os
 import torch
 import torch.nn as nn
 
+from .. import autograd as ag
 from .. import ops
-from .v2v_net import _PackedCache, _no_train
+from .v2v_net import _PackedCache
 
 BN_MOMENTUM = 0.1
 logger = logging.getLogger(__name__)
@@ -70,6 +75,11 @@ class BasicBlock(nn.Module):
         return self._cache.get(self, build)
 
     def forward_cl(self, x):
+        if self.training:
+            r = ag.batch_norm(ag.conv(x, self.conv1), self.bn1, relu=True)
+            r = ag.batch_norm(ag.conv(r, self.conv2), self.bn2)
+            skip = x if self.downsample is None else ag.batch_norm(ag.conv(x, self.downsample[0]), self.downsample[1])
+            return ag.add(r, skip, self.conv2.out_channels, relu=True)
         a, b, d = self._packed()
         return b(a(x), residual=x if d is None else d(x))
 
@@ -98,6 +108,12 @@ class Bottleneck(nn.Module):
         return self._cache.get(self, build)
 
     def forward_cl(self, x):
+        if self.training:
+            r = ag.batch_norm(ag.conv(x, self.conv1), self.bn1, relu=True)
+            r = ag.batch_norm(ag.conv(r, self.conv2), self.bn2, relu=True)
+            r = ag.batch_norm(ag.conv(r, self.conv3), self.bn3)
+            skip = x if self.downsample is None else ag.batch_norm(ag.conv(x, self.downsample[0]), self.downsample[1])
+            return ag.add(r, skip, self.conv3.out_channels, relu=True)
         a, b, c, d, b2 = self._packed()
         return c(_strided_conv_cl(b, b2, a(x)), residual=x if d is None else d(x))
 
@@ -171,7 +187,8 @@ class PoseResNet(nn.Module):
     def forward_cl(self, x, out_pitch=None, image=None):
         """``x``: channel-last ``[N,1,H,W,4]`` float32 image batch, or ``image``: the ``[N,3,H,W]`` float32 tensor
         itself -> ``(heat-maps [N,1,h,w,pitch], features)``."""
-        _no_train(self)
+        if self.training:
+            return self._forward_train_cl(x, out_pitch, image)
         stem, deconvs, head, stem_s2d = self._packed()
         # bf16 mode: the 7x7 stem reads the float32 image and writes bf16; from there on activations are bf16
         # (tcgen05 convolutions where the shape is covered) and the heat-maps leave the net in float32
@@ -191,6 +208,24 @@ class PoseResNet(nn.Module):
         for d in deconvs:
             x = d(x)
         return head(x, out_pitch=out_pitch, out_dtype=torch.float32), x
+
+    def _forward_train_cl(self, x, out_pitch, image):
+        """Training path (float32): every convolution raw, BatchNorm on batch statistics, gradients recorded."""
+        if out_pitch not in (None, ops.round_up(self.num_joints, 4)):
+            raise ValueError("the training path writes the default channel pitch")
+        if x is None:
+            x = ag.ToChannelLast.apply(image.unsqueeze(2))
+        x = ag.batch_norm(ag.conv(x, self.conv1), self.bn1, relu=True)
+        x = ag.max_pool(x, 64, [1, 3, 3], [1, 2, 2], [0, 1, 1])
+        for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+            for blk in layer:
+                x = blk.forward_cl(x)
+        for i in range(0, len(self.deconv_layers), 3):
+            ct, bn = self.deconv_layers[i], self.deconv_layers[i + 1]
+            if ct.output_padding[0] != 0:
+                raise NotImplementedError("transposed convolution with output_padding in the training path")
+            x = ag.batch_norm(ag.conv(x, ct, transposed=True), bn, relu=True)
+        return ag.conv(x, self.final_layer), x
 
     def forward(self, x, attn=False):
         """``[N,3,H,W]`` -> ``[N,J,H/4,W/4]`` (reference :191-207).  The result is a zero-copy

@@ -641,7 +641,8 @@ class PackedConv:
                         t0 = [(phase[i] + p[i]) % s[i] for i in range(3)]
                         sub = w5[:, :, t0[0]::s[0], t0[1]::s[1], t0[2]::s[2]]
                         off0 = [(phase[i] + p[i] - t0[i]) // s[i] for i in range(3)]
-                        self.weights.append(pack(sub))
+                        # (a phase without taps, e.g. kernel 1 / stride 2, only ever produces the shift)
+                        self.weights.append(pack(sub) if sub.numel() else None)
                         self.phases.append((phase, off0, [int(v) for v in sub.shape[2:]]))
                         self._subs.append(sub)
 
@@ -841,10 +842,12 @@ class PackedConv:
                             origin, [1, 1, 1], self.stride, phase, self.relu, cin_real=self.cin, cout_pitch_w=n, **kw)
         return out
 
-    def __call__(self, x, residual=None, out_pitch=None, algo=None, out_dtype=None, head=None):
+    def __call__(self, x, residual=None, out_pitch=None, algo=None, out_dtype=None, head=None, out_dims=None):
         """``x``: channel-last ``[N,D,H,W,pitch]``.  float32 activations take the float32 SIMT kernel; bf16
         activations the tcgen05 kernel where the shape is covered (``out_dtype`` float32 there gives a float32
-        result), else the SIMT kernel with bf16 storage and float32 math."""
+        result), else the SIMT kernel with bf16 storage and float32 math.  ``out_dims``: explicit output extent of a
+        transposed convolution (``output_padding``; SIMT path) -- how the input gradient of a strided convolution
+        recovers the forward input's extent."""
         if algo is None:
             if x.dtype == torch.bfloat16 and self.tc_supported():
                 algo = _lib.CONV_TC_BF16
@@ -863,11 +866,19 @@ class PackedConv:
         if pitch < self.cin_p:
             raise _lib.Sp3dError("activation pitch %d smaller than packed cin %d" % (pitch, self.cin_p))
         o = self.out_shape((D, H, W))
+        if out_dims is not None:
+            if not self.transposed or any(not (0 <= int(out_dims[i]) - o[i] < self.stride[i]) for i in range(3)):
+                raise _lib.Sp3dError("out_dims must extend a transposed convolution's output by less than the stride")
+            o = [int(v) for v in out_dims]
         if out_dtype is None:
             out_dtype = x.dtype
         if out_pitch is None:
             out_pitch = round_up(self.cout, 4 if out_dtype == torch.float32 else 16)
-        out = torch.empty((N, o[0], o[1], o[2], int(out_pitch)), device=x.device, dtype=out_dtype)
+        empty_phase = self.transposed and any(w is None for w in self.weights)
+        if empty_phase and (self.shift is not None or residual is not None):
+            raise _lib.Sp3dError("transposed convolutions with tap-less phases are supported without shift / residual")
+        alloc = torch.zeros if empty_phase else torch.empty
+        out = alloc((N, o[0], o[1], o[2], int(out_pitch)), device=x.device, dtype=out_dtype)
         if not self.transposed:
             conv_launch(x, self.weights[0], self.scale, self.shift, residual, out, self.cin_p, self.cout, o, self.k,
                         self.stride, [-p for p in self.padding], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu, algo,
@@ -875,6 +886,8 @@ class PackedConv:
         else:
             for wgt, (phase, off0, ks) in zip(self.weights, self.phases):
                 grid = [(o[i] - phase[i] + self.stride[i] - 1) // self.stride[i] for i in range(3)]
+                if wgt is None or min(grid) <= 0:
+                    continue
                 conv_launch(x, wgt, self.scale, self.shift, residual, out, self.cin_p, self.cout, grid, ks,
                             [1, 1, 1], off0, [-1, -1, -1], self.stride, phase, self.relu, algo, cin_real=self.cin)
         return out

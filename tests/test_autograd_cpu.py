@@ -157,3 +157,91 @@ def test_v2v_net_training_step_wiring(emulated, cin, shape):
     net.eval()
     with torch.no_grad():
         assert net(x).shape == y.shape
+
+
+def _maxpool_any(x, channels, k, s, p):
+    y = F.max_pool3d(x.permute(0, 4, 1, 2, 3), tuple(k), tuple(s), tuple(p))
+    return y.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def _maxpool_bwd_any(x, channels, k, s, p, gy):
+    with torch.enable_grad():
+        xc = x.permute(0, 4, 1, 2, 3).detach().clone().requires_grad_(True)
+        F.max_pool3d(xc, tuple(k), tuple(s), tuple(p)).backward(gy.permute(0, 4, 1, 2, 3))
+    return xc.grad.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def _conv_wgrad_any(pc, x, grad_out, with_bias=True):
+    """Independent route for 2-D / strided / transposed layers: autograd of torch's convolution on the reference-shaped
+    parameter (3-D functional calls with a unit leading extent)."""
+    xc = x[..., :pc.cin].permute(0, 4, 1, 2, 3)
+    go = grad_out[..., :pc.cout].permute(0, 4, 1, 2, 3)
+    with torch.enable_grad():
+        if not pc.transposed:
+            w = pc._subs[0].detach().clone().requires_grad_(True)
+            y = F.conv3d(xc, w, None, stride=pc.stride, padding=pc.padding)
+        else:
+            full = torch.zeros(pc.cout, pc.cin, *pc.k)
+            for sub, (phase, _, _) in zip(pc._subs, pc.phases):
+                t0 = [(phase[i] + pc.padding[i]) % pc.stride[i] for i in range(3)]
+                full[:, :, t0[0]::pc.stride[0], t0[1]::pc.stride[1], t0[2]::pc.stride[2]] = sub
+            w = full.permute(1, 0, 2, 3, 4).detach().clone().requires_grad_(True)
+            y = F.conv_transpose3d(xc, w, None, stride=pc.stride, padding=pc.padding)
+        y.backward(go)
+    g = w.grad
+    g = g.reshape(list(g.shape[:2]) + list(g.shape[2 + (3 - pc.nd):]))
+    return g, (go.sum((0, 2, 3, 4)) if with_bias else None)
+
+
+def test_pose_resnet_training_step_wiring(emulated, monkeypatch):
+    """PoseResNet-50 in .train() on a 64 x 96 image batch: output, running statistics and the gradients of all 161
+    parameters (stride-2 3x3 / 1x1 convolutions and the k4/s2 transposed convolutions included) against autograd
+    through the oracle's functional restatement."""
+    from selfpose3d_b200.config import default_config
+    from selfpose3d_b200.models import pose_resnet
+    monkeypatch.setattr(ops, "maxpool", _maxpool_any)
+    monkeypatch.setattr(grad_ops, "maxpool_bwd", _maxpool_bwd_any)
+    monkeypatch.setattr(grad_ops, "conv_wgrad", _conv_wgrad_any)
+    cfg = default_config()
+    cfg.NETWORK.NUM_JOINTS = 5
+    net = pose_resnet.get_pose_net(cfg, is_train=False)
+    sd0 = synthetic.trained_like_state_dict(net, seed=90)
+    net.load_state_dict(sd0, strict=True)
+    net.train()
+    torch.manual_seed(2)
+    x = torch.randn(2, 3, 64, 96)
+    gy = torch.randn(2, 5, 16, 24)
+    def oracle(dtype):
+        sd_ = {k: (v.to(dtype).clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+               for k, v in sd0.items()}
+        yo_ = nets.pose_resnet_forward(x.to(dtype), sd_, dtype=dtype, training=True)
+        (yo_ * gy.to(dtype)).sum().backward()
+        return yo_.detach(), sd_
+
+    yo, sd = oracle(torch.float64)
+    _, sd32 = oracle(torch.float32)     # yardstick: ReLU gates decided in the last bits differ between float32 / float64
+    y = net(x)
+    assert y.shape == yo.shape
+    (y * gy).sum().backward()
+
+    def rel(a, b):
+        return float((a.double() - b.double()).abs().max()) / max(float(b.double().abs().max()), 1e-30)
+
+    assert rel(y, yo) < 1e-3, rel(y, yo)
+    top = max(float(v.grad.abs().max()) for v in sd.values() if v.is_floating_point() and v.grad is not None)
+    n_checked = 0
+    for name, p in net.named_parameters():
+        ref = sd[name].grad
+        assert p.grad is not None and p.grad.shape == ref.shape, name
+        if float(ref.abs().max()) < 1e-7 * top:
+            continue
+        # tiny feature maps (2 x 3) and a batch of 2 make single ReLU gates flip between float32 and float64 on either
+        # side (the float32 oracle is itself up to 0.14 of the range away from the float64 one on single entries), so
+        # the gradients are compared in the L2 norm, which a wiring error would move by O(1) and a flipped gate by ~1e-2
+        l2 = float((p.grad.double() - ref).norm() / ref.norm())
+        assert l2 < max(3e-2, 3 * float((sd32[name].grad.double() - ref).norm() / ref.norm())), (name, l2)
+        n_checked += 1
+    assert n_checked >= 100, n_checked
+    bn = net.layer2[0].downsample[1]                   # BatchNorm behind the 1x1 / stride-2 convolution
+    assert int(bn.num_batches_tracked) == int(sd0["layer2.0.downsample.1.num_batches_tracked"]) + 1
+    assert not torch.equal(bn.running_mean, sd0["layer2.0.downsample.1.running_mean"])

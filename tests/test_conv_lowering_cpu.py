@@ -362,3 +362,40 @@ def test_split_operand_lowering(monkeypatch, case, terms, tol):
     got = cf(pc(cl(x), residual=None if res is None else cl(res)), cout, nd).double()
     err = float((got - want).abs().max()) / float(want.abs().max())
     assert err <= tol, err
+
+
+# ---------------------------------------------------------------------------------------------- input gradients
+@pytest.mark.parametrize("case", ["3x3s2_even", "3x3s2_odd", "1x1s2", "7x7s2", "3x3s1", "deconv4s2", "3d_k3", "3d_convT2"])
+def test_conv_dgrad_lowering(monkeypatch, case):
+    """grad_ops.conv_dgrad: the input gradient as the forward kernel on the adjoint operator (flipped kernel for
+    stride 1, transposed convolution with an explicit output extent for strided convolutions -- incl. tap-less
+    phases of a 1x1 / stride-2 kernel --, strided convolution for transposed ones), against torch autograd."""
+    from selfpose3d_b200 import grad_ops
+    monkeypatch.setattr(ops, "conv_launch", emulate_conv_launch)
+    monkeypatch.setattr(grad_ops, "_f32", lambda *a: None)
+    torch.manual_seed(21)
+    nd, transposed = 2, False
+    if case.startswith("3x3s2"):
+        conv, x = nn.Conv2d(8, 12, 3, 2, 1), torch.randn(2, 8, *((10, 8) if case.endswith("even") else (9, 7)))
+    elif case == "1x1s2":
+        conv, x = nn.Conv2d(8, 12, 1, 2, 0), torch.randn(2, 8, 9, 8)
+    elif case == "7x7s2":
+        conv, x = nn.Conv2d(3, 8, 7, 2, 3), torch.randn(1, 3, 14, 12)
+    elif case == "3x3s1":
+        conv, x = nn.Conv2d(8, 8, 3, 1, 1), torch.randn(2, 8, 6, 5)
+    elif case == "deconv4s2":
+        conv, x, transposed = nn.ConvTranspose2d(8, 6, 4, 2, 1), torch.randn(2, 8, 5, 4), True
+    elif case == "3d_k3":
+        conv, x, nd = nn.Conv3d(4, 6, 3, 1, 1), torch.randn(1, 4, 4, 5, 3), 3
+    else:
+        conv, x, nd, transposed = nn.ConvTranspose3d(8, 4, 2, 2), torch.randn(1, 8, 3, 2, 4), 3, True
+    x.requires_grad_(True)
+    y = conv(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    pc = ops.PackedConv(conv.weight, conv.bias, None, conv.stride[0], conv.padding[0], transposed=transposed, relu=0)
+    xcl = cl(x.detach())
+    torch.testing.assert_close(cf(pc(xcl), y.shape[1], nd), y.detach(), rtol=1e-4, atol=1e-5)
+    gx = grad_ops.conv_dgrad(pc, cl(gy), out_pitch=xcl.shape[-1], in_dims=xcl.shape[1:4])
+    assert gx.shape == xcl.shape
+    torch.testing.assert_close(cf(gx, x.shape[1], nd), x.grad, rtol=1e-4, atol=1e-5)

@@ -333,12 +333,15 @@ def test_v2v_pose_size_vs_oracle_fp64():
     assert ours <= max(1e-4, 4 * ref), (ours, ref)   # heat-map tolerance 1e-4 relative
 
 
-def test_training_mode_of_unported_modules_raises():
-    """V2VNet trains through the backward kernels (tests/test_gpu_backward.py); the 2-D backbone's training path is
+def test_unported_training_forward_raises(golden):
+    """V2VNet, PoseResNet, the pose / root nets and the supervised MultiPersonPoseNet train through the backward kernels
+    (tests/test_gpu_backward.py, tests/test_gpu_zz_training_step.py); the SSL loss assembly of MultiPersonPoseNetSSV is
     not built yet and must say so instead of silently running the inference kernels."""
-    net = pose_resnet.get_pose_net(default_config(), is_train=False).to(DEV).train()
+    g = golden("inference_small")
+    model, _ = _small_model(g, float(g["threshold"]))
+    hms = [torch.from_numpy(h).to(DEV) for h in g["heatmaps"]]
     with pytest.raises(NotImplementedError):
-        net(torch.zeros(1, 3, 64, 64, device=DEV))
+        model.train()(views1=None, meta1=meta_from_golden(g), input_heatmaps1=hms, inference=False)
 
 
 def test_cpu_tensor_raises_no_fallback():

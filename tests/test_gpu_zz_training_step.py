@@ -68,3 +68,79 @@ def test_supervised_training_step_matches_reference_on_gpu(golden):
             assert gn < 1e-3 * top, (name, gn, norm)
             continue
         assert abs(gn - norm) <= 5e-3 * norm, (name, gn, norm)
+
+
+_FIRST_RUN = pytest.mark.xfail(strict=False, reason="first B200 run of this composition (GPU budget of the round was "
+                                                    "spent); lowering / wiring verified on CPU with emulated kernels")
+
+
+@_FIRST_RUN
+@pytest.mark.parametrize("case", ["3x3s2_even", "3x3s2_odd", "1x1s2", "7x7s2", "deconv4s2"])
+def test_strided_conv_dgrad_vs_autograd(case):
+    """Input gradients of strided / transposed 2-D convolutions (transposed convolution with an explicit output
+    extent and tap-less phases; strided convolution) -- CPU twin: tests/test_conv_lowering_cpu.py."""
+    import torch.nn as nn
+    from selfpose3d_b200 import grad_ops, ops
+    torch.manual_seed(21)
+    transposed = False
+    if case.startswith("3x3s2"):
+        conv, x = nn.Conv2d(64, 128, 3, 2, 1), torch.randn(2, 64, *((10, 8) if case.endswith("even") else (9, 7)))
+    elif case == "1x1s2":
+        conv, x = nn.Conv2d(64, 128, 1, 2, 0), torch.randn(2, 64, 9, 8)
+    elif case == "7x7s2":
+        conv, x = nn.Conv2d(3, 64, 7, 2, 3), torch.randn(1, 3, 14, 12)
+    else:
+        conv, x, transposed = nn.ConvTranspose2d(256, 64, 4, 2, 1), torch.randn(2, 256, 5, 4), True
+    conv = conv.double()
+    x = x.double().requires_grad_(True)
+    y = conv(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    pc = ops.PackedConv(conv.weight.detach().float().to(DEV), conv.bias.detach().float().to(DEV), None, conv.stride[0],
+                        conv.padding[0], transposed=transposed, relu=0)
+    xcl = ops.to_channel_last(x.detach().float().unsqueeze(2).to(DEV))
+    gycl = ops.to_channel_last(gy.float().unsqueeze(2).to(DEV))
+    gx = grad_ops.conv_dgrad(pc, gycl, out_pitch=int(xcl.shape[-1]), in_dims=tuple(xcl.shape[1:4]))
+    got = ops.to_channel_first(gx, x.shape[1])[:, :, 0].cpu().double()
+    assert float((got - x.grad).abs().max()) <= 2e-5 * float(x.grad.abs().max())
+
+
+@_FIRST_RUN
+def test_pose_resnet_training_step_vs_oracle():
+    """PoseResNet-50 in .train() on a 64 x 96 image batch through the kernels: output and the gradients of all
+    parameters against float64 autograd through the oracle's restatement (L2 norm: single ReLU gates flip between
+    float32 and float64 on feature maps this small) -- CPU twin: tests/test_autograd_cpu.py."""
+    from oracle import nets
+    from selfpose3d_b200.models import pose_resnet
+    cfg = default_config()
+    cfg.NETWORK.NUM_JOINTS = 5
+    net = pose_resnet.get_pose_net(cfg, is_train=False)
+    sd0 = synthetic.trained_like_state_dict(net, seed=90)
+    net.load_state_dict(sd0, strict=True)
+    torch.manual_seed(2)
+    x = torch.randn(2, 3, 64, 96)
+    gy = torch.randn(2, 5, 16, 24)
+
+    def oracle(dtype):
+        sd_ = {k: (v.to(dtype).clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+               for k, v in sd0.items()}
+        yo_ = nets.pose_resnet_forward(x.to(dtype), sd_, dtype=dtype, training=True)
+        (yo_ * gy.to(dtype)).sum().backward()
+        return yo_.detach(), sd_
+
+    yo, sd = oracle(torch.float64)
+    _, sd32 = oracle(torch.float32)
+    net = net.to(DEV).train()
+    y = net(x.to(DEV))
+    (y * gy.to(DEV)).sum().backward()
+    assert float((y.detach().cpu().double() - yo).abs().max()) <= 1e-3 * float(yo.abs().max())
+    top = max(float(v.grad.abs().max()) for v in sd.values() if v.is_floating_point() and v.grad is not None)
+    checked = 0
+    for name, p in net.named_parameters():
+        ref = sd[name].grad
+        if float(ref.abs().max()) < 1e-7 * top:
+            continue
+        l2 = float((p.grad.cpu().double() - ref).norm() / ref.norm())
+        assert l2 < max(3e-2, 3 * float((sd32[name].grad.double() - ref).norm() / ref.norm())), (name, l2)
+        checked += 1
+    assert checked >= 100
