@@ -6,8 +6,8 @@ Interface mirror of the reference's ``lib/models/multi_person_posenet_ssv.py``: 
 ``root_net``, ``pose_net``, ``attn`` and every state-dict key as in the reference.
 ``forward(..., inference=True)`` runs on the sm_100a kernels.  The SSL training branch of
 ``forward`` (:226-501: three augmented view sets, re-projection, Gaussian rendering, attention
-and Hungarian losses, with autograd through all of it) is the "next" part of the scope table and
-raises.
+and Hungarian losses) is in ``_ssl_train.py``: the networks take their training paths through the
+backward kernels, the loss assembly around them is plain tensor expressions on small tensors.
 """
 from __future__ import annotations
 
@@ -16,6 +16,7 @@ import torch.nn as nn
 
 from . import pose_resnet
 from . import _inference
+from . import _ssl_train
 from .cuboid_proposal_net_soft import CuboidProposalNetSoft
 from .pose_regression_net import PoseRegressionNet
 
@@ -30,12 +31,24 @@ class MultiPersonPoseNetSSV(nn.Module):
         if self.WITH_ATTN:
             self.attn = attn
             self.attn_weight = cfg.ATTN_WEIGHT
+        self.USE_L1, self.L1_WEIGHT, self.L1_ATTN = cfg.USE_L1, cfg.L1_WEIGHT, cfg.L1_ATTN
+        self.L1_EPOCH = cfg.TRAIN.L1_EPOCH
+        self.width, self.height = list(cfg.NETWORK.IMAGE_SIZE)[0], list(cfg.NETWORK.IMAGE_SIZE)[1]
         self.use_root_gt = cfg.NETWORK.USE_GT
         self.train_only_2d = cfg.NETWORK.TRAIN_ONLY_2D
         self.root_id = cfg.DATASET.ROOTIDX
         self.dataset_name = cfg.DATASET.TEST_DATASET
         self.train_only_rootnet = cfg.NETWORK.TRAIN_ONLY_ROOTNET
+        self.rootnet_train_synth = cfg.NETWORK.ROOTNET_TRAIN_SYNTH
+        self.freeze_rootnet = cfg.NETWORK.FREEZE_ROOTNET
+        self.single_aug_training_posenet = cfg.NETWORK.SINGLE_AUG_TRAINING_POSENET
+        self.init_train_epochs_rootnet = cfg.NETWORK.INIT_TRAIN_EPOCHS_ROOTNET
         self.eval_rootnet_only = cfg.EVAL_ROOTNET_ONLY
+        # heat-map pixel-index grids of the Gaussian rendering (reference :88-101; not part of the state dict)
+        hw, hh = int(cfg.NETWORK.HEATMAP_SIZE[0]), int(cfg.NETWORK.HEATMAP_SIZE[1])
+        yy, xx = torch.meshgrid(torch.arange(hh, dtype=torch.float32), torch.arange(hw, dtype=torch.float32), indexing="ij")
+        self.register_buffer("hm_xx", xx.view(1, 1, hh, hw), persistent=False)
+        self.register_buffer("hm_yy", yy.view(1, 1, hh, hw), persistent=False)
         if self.train_only_2d:
             self.use_root_gt = True
         elif not self.train_only_rootnet:
@@ -60,9 +73,10 @@ class MultiPersonPoseNetSSV(nn.Module):
         if inference:
             with torch.no_grad():
                 return self.do_inference(views1, meta1, input_heatmaps1, visualize_attn)
-        raise NotImplementedError(
-            "selfpose3d_b200: the SSL training forward (reference multi_person_posenet_ssv.py:226-501) is not "
-            "implemented in this backend yet; use forward(..., inference=True)")
+        return _ssl_train.forward_train(
+            self, views1, meta1, targets_2d1, weights_2d1, targets_3d1, input_heatmaps1,
+            views2, meta2, targets_2d2, weights_2d2, targets_3d2, input_heatmaps2,
+            views3, meta3, targets_2d3, weights_2d3, targets_3d3, input_heatmaps3, epoch)
 
 
 def get_multi_person_pose_net(cfg, is_train=True):

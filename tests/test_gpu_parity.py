@@ -333,17 +333,6 @@ def test_v2v_pose_size_vs_oracle_fp64():
     assert ours <= max(1e-4, 4 * ref), (ours, ref)   # heat-map tolerance 1e-4 relative
 
 
-def test_unported_training_forward_raises(golden):
-    """V2VNet, PoseResNet, the pose / root nets and the supervised MultiPersonPoseNet train through the backward kernels
-    (tests/test_gpu_backward.py, tests/test_gpu_zz_training_step.py); the SSL loss assembly of MultiPersonPoseNetSSV is
-    not built yet and must say so instead of silently running the inference kernels."""
-    g = golden("inference_small")
-    model, _ = _small_model(g, float(g["threshold"]))
-    hms = [torch.from_numpy(h).to(DEV) for h in g["heatmaps"]]
-    with pytest.raises(NotImplementedError):
-        model.train()(views1=None, meta1=meta_from_golden(g), input_heatmaps1=hms, inference=False)
-
-
 def test_cpu_tensor_raises_no_fallback():
     net = v2v_net.V2VNet(1, 1).eval()
     with pytest.raises(_lib.Sp3dError):

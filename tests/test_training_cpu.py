@@ -149,3 +149,75 @@ def test_supervised_training_step_matches_reference(emulated, monkeypatch, golde
         assert abs(gs - tot) <= 5e-3 * norm * max(1.0, np.sqrt(p.numel())), (name, gs, tot)
         checked += 1
     assert checked >= 60, checked
+
+
+# ---------------------------------------------------------------------------------------------- SSL step
+def emul_unproject_op(heatmaps, hm_strides, cams, centers, grid_size, cube_size, image_size, heatmap_hw, channels, out,
+                      out_strides, out_c_pad=0, check_flag=False, cubes_per_sample=1, cube_sample=None, grids=None,
+                      view_range=None, partial=False, heatmap_cfg_wh=None, fast=False):
+    """ops.unproject as the inference path calls it (channel-last float32 output, all views)."""
+    assert not partial and not fast and grids is None and view_range is None and cubes_per_sample == 1 and not check_flag
+    pitch = int(out.shape[-1])
+    spec = ([float(v) for v in grid_size], [int(v) for v in cube_size], image_size,
+            heatmap_cfg_wh if heatmap_cfg_wh is not None else (heatmap_hw[1], heatmap_hw[0]), int(channels), pitch)
+    with torch.no_grad():
+        out.copy_(emul_unproject(cams, centers, cube_sample, spec, *[h.float() for h in heatmaps]))
+
+
+def test_ssl_training_step_matches_reference(emulated, monkeypatch, golden):  # noqa: F811
+    """``MultiPersonPoseNetSSV.forward(inference=False)``: one self-supervised step (ResNet-50 backbone and ResNet-18
+    attention net in .train(), frozen root net, pose net in .train(); re-projection, Gaussian rendering, attention and
+    Hungarian-L1 losses) against the step recorded from the unmodified reference
+    (tests/golden/make_golden_ssl.py -> ssl_step.npz): the four losses, the joints, the proposals and the gradient
+    norms of all 331 trained parameters."""
+    import sys
+    import os
+    from conftest import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    import make_golden_ssl as gen
+    from test_autograd_cpu import _conv_wgrad_any, _maxpool_any, _maxpool_bwd_any
+    from selfpose3d_b200 import grad_ops
+    from selfpose3d_b200.models import multi_person_posenet_ssv
+    monkeypatch.setattr(ag, "Unproject", _Apply(emul_unproject))
+    monkeypatch.setattr(ag, "SoftArgmax", _Apply(emul_softargmax))
+    monkeypatch.setattr(ops, "nms_topk", emul_nms_topk)
+    monkeypatch.setattr(ops, "unproject", emul_unproject_op)
+    monkeypatch.setattr(ops, "maxpool", _maxpool_any)
+    monkeypatch.setattr(grad_ops, "maxpool_bwd", _maxpool_bwd_any)
+    monkeypatch.setattr(grad_ops, "conv_wgrad", _conv_wgrad_any)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
+    gs = golden("ssl_step")
+    cfg = gen.configure(default_config())
+    cfg.NETWORK.IMAGE_SIZE, cfg.NETWORK.HEATMAP_SIZE = list(gen.IMAGE), list(gen.HEATMAP)
+    model = multi_person_posenet_ssv.get_multi_person_pose_net(cfg, is_train=False)
+    model.load_state_dict(synthetic.trained_like_state_dict(model, seed=int(gs["seed"])), strict=True)
+    model.train()
+    model.root_net.eval()
+    (v1, m1, t1), (v2, m2, t2), (v3, m3, t3) = gen.ssl_case()
+    pred, hm3, gc, losses = model(views1=v1, meta1=m1, targets_2d1=t1, views2=v2, meta2=m2, targets_2d2=t2,
+                                  views3=v3, meta3=m3, targets_2d3=t3, inference=False, epoch=1)
+    sum(losses.values()).backward()
+
+    assert sorted(losses) == [str(n) for n in gs["loss_names"]]
+    for name, want in zip(gs["loss_names"], gs["loss_values"]):
+        assert abs(float(losses[str(name)]) - want) <= 2e-3 * abs(want), (name, float(losses[str(name)]), want)
+    np.testing.assert_allclose(torch.stack(hm3).detach().numpy(), gs["heatmaps3"], rtol=0,
+                               atol=1e-3 * np.abs(gs["heatmaps3"]).max())
+    np.testing.assert_allclose(gc.detach().numpy(), gs["grid_centers"], rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(pred.numpy(), gs["pred"], rtol=0, atol=1.0)          # mm (float64-accumulating emulation)
+    params = dict(model.named_parameters())
+    top = float(gs["param_grad_norm"].max())
+    checked = 0
+    for name, norm in zip(gs["param_names"], gs["param_grad_norm"]):
+        p = params[str(name)]
+        if norm < 0:                                   # frozen root net: no gradient on either side
+            assert p.grad is None or not p.grad.any(), name
+            continue
+        gn = float(p.grad.double().norm())
+        if norm < 1e-5 * top or str(name) == "pose_net.v2v_net.output_layer.bias":   # cancelled: rounding noise only
+            assert gn < 1e-3 * top, (name, gn, norm)
+            continue
+        assert abs(gn - norm) <= 5e-2 * norm, (name, gn, norm)
+        checked += 1
+    assert checked >= 150, checked
