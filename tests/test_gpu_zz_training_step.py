@@ -144,3 +144,43 @@ def test_pose_resnet_training_step_vs_oracle():
         assert l2 < max(3e-2, 3 * float((sd32[name].grad.double() - ref).norm() / ref.norm())), (name, l2)
         checked += 1
     assert checked >= 100
+
+
+@_FIRST_RUN
+def test_ssl_training_step_matches_reference_on_gpu(golden):
+    """``MultiPersonPoseNetSSV.forward(inference=False)`` through the kernels against the self-supervised step recorded
+    from the unmodified reference (ssl_step.npz) -- CPU twin: tests/test_training_cpu.py."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_ssl as gen
+    from selfpose3d_b200.models import multi_person_posenet_ssv
+    gs = golden("ssl_step")
+    cfg = gen.configure(default_config())
+    cfg.NETWORK.IMAGE_SIZE, cfg.NETWORK.HEATMAP_SIZE = list(gen.IMAGE), list(gen.HEATMAP)
+    model = multi_person_posenet_ssv.get_multi_person_pose_net(cfg, is_train=False)
+    model.load_state_dict(synthetic.trained_like_state_dict(model, seed=int(gs["seed"])), strict=True)
+    model = model.to(DEV).train()
+    model.root_net.eval()
+    sets = [([v.to(DEV) for v in views], meta, [t.to(DEV) for t in targets]) for views, meta, targets in gen.ssl_case()]
+    (v1, m1, t1), (v2, m2, t2), (v3, m3, t3) = sets
+    pred, hm3, gc, losses = model(views1=v1, meta1=m1, targets_2d1=t1, views2=v2, meta2=m2, targets_2d2=t2,
+                                  views3=v3, meta3=m3, targets_2d3=t3, inference=False, epoch=1)
+    sum(losses.values()).backward()
+    assert sorted(losses) == [str(n) for n in gs["loss_names"]]
+    for name, want in zip(gs["loss_names"], gs["loss_values"]):
+        assert abs(float(losses[str(name)]) - want) <= 2e-3 * abs(want), (name, float(losses[str(name)]), want)
+    np.testing.assert_allclose(gc.detach().cpu().numpy(), gs["grid_centers"], rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(pred.cpu().numpy(), gs["pred"], rtol=0, atol=1.0)
+    params = dict(model.named_parameters())
+    top = float(gs["param_grad_norm"].max())
+    for name, norm in zip(gs["param_names"], gs["param_grad_norm"]):
+        p = params[str(name)]
+        if norm < 0:
+            assert p.grad is None or not p.grad.any(), name
+            continue
+        gn = float(p.grad.double().norm())
+        if norm < 1e-5 * top or str(name) == "pose_net.v2v_net.output_layer.bias":
+            assert gn < 1e-3 * top, (name, gn, norm)
+            continue
+        assert abs(gn - norm) <= 5e-2 * norm, (name, gn, norm)
