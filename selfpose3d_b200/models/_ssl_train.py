@@ -9,7 +9,7 @@ forward / backward step is one of the kernels); what is restated here is the los
 tensors (a few people x 15 joints, ``V x B x J x h x w`` heat-maps): plain tensor expressions for now, the fused
 re-projection + rendering kernel is the next row of SURVEY.md section 8(f).
 
-Not covered (raises): the synthetic-root RootNet branch (``NETWORK.ROOTNET_TRAIN_SYNTH``).
+The synthetic-root RootNet branch (``NETWORK.ROOTNET_TRAIN_SYNTH``) lives in ``cuboid_proposal_net_soft.py``.
 """
 from __future__ import annotations
 
@@ -134,8 +134,15 @@ def forward_train(self, views1, meta1, targets_2d1, weights_2d1, targets_3d1, in
     elif self.freeze_rootnet:
         grid_centers = self.root_net(heatmaps3, meta3, flip_xcoords=meta3[0]["hflip"])[3]
     elif self.rootnet_train_synth:
-        raise NotImplementedError("selfpose3d_b200: the synthetic-root RootNet training branch (reference "
-                                  "cuboid_proposal_net_soft.py:151-241) is not part of this backend yet")
+        # synthetic-root supervision on all three sets + consistency of the real volumes with set 3's (:312-330)
+        main1, syn1, tgt1, _ = self.root_net(heatmaps1, meta1, flip_xcoords=meta1[0]["hflip"])
+        main2, syn2, tgt2, _ = self.root_net(heatmaps2, meta2, flip_xcoords=meta2[0]["hflip"])
+        main3, syn3, tgt3, grid_centers = self.root_net(heatmaps3, meta3, flip_xcoords=meta3[0]["hflip"])
+        losses["loss_root_syn"] = self.weight_root_syn * (F.mse_loss(syn1, tgt1) + F.mse_loss(syn2, tgt2)
+                                                          + F.mse_loss(syn3, tgt3))
+        if self.root_reg_loss:
+            main3 = main3.detach()
+            losses["loss_root_reg"] = self.weight_root_reg * (F.mse_loss(main1, main3) + F.mse_loss(main2, main3))
     else:
         cubes1 = self.root_net(heatmaps1, meta1, flip_xcoords=meta1[0]["hflip"])[0]
         cubes2 = self.root_net(heatmaps2, meta2, flip_xcoords=meta2[0]["hflip"])[0]

@@ -76,9 +76,10 @@ class CuboidProposalNet(nn.Module):
         self.v2v_net = V2VNet(1 if self.rootnet_roothm else cfg.NETWORK.NUM_JOINTS, 1)
         self.proposal_layer = ProposalLayer(cfg)
 
-    def root_volume(self, all_heatmaps, meta, flip_xcoords=None, cams=None):
-        """heat-maps -> ``root_cubes [B,X,Y,Z]`` (un-projection + V2VNet), layout-native."""
-        if self.rootnet_roothm:   # only the root joint's heat-map feeds the root net (reference :103-108)
+    def root_volume(self, all_heatmaps, meta, flip_xcoords=None, cams=None, select_root=True):
+        """heat-maps -> ``root_cubes [B,X,Y,Z]`` (un-projection + V2VNet), layout-native.  ``select_root=False``: the
+        maps already hold exactly the channels the root net reads (synthetic root heat-maps)."""
+        if self.rootnet_roothm and select_root:   # only the root joint's heat-map feeds the root net (reference :103-108)
             hms = [a[:, self.root_id:self.root_id + 1] for a in all_heatmaps]
         else:
             hms = all_heatmaps

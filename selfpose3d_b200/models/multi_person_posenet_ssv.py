@@ -43,6 +43,8 @@ class MultiPersonPoseNetSSV(nn.Module):
         self.freeze_rootnet = cfg.NETWORK.FREEZE_ROOTNET
         self.single_aug_training_posenet = cfg.NETWORK.SINGLE_AUG_TRAINING_POSENET
         self.init_train_epochs_rootnet = cfg.NETWORK.INIT_TRAIN_EPOCHS_ROOTNET
+        self.root_reg_loss = cfg.NETWORK.ROOT_CONSISTENCY_LOSS
+        self.weight_root_syn, self.weight_root_reg = cfg.NETWORK.WEIGHT_ROOT_SYN, cfg.NETWORK.WEIGHT_ROOT_REG
         self.eval_rootnet_only = cfg.EVAL_ROOTNET_ONLY
         # heat-map pixel-index grids of the Gaussian rendering (reference :88-101; not part of the state dict)
         hw, hh = int(cfg.NETWORK.HEATMAP_SIZE[0]), int(cfg.NETWORK.HEATMAP_SIZE[1])

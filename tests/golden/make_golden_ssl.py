@@ -64,6 +64,32 @@ def ssl_case():
     return sets
 
 
+SYNTH_TORCH_SEED = 1234
+
+
+def synth_root_step(cfg):
+    """The synthetic-root RootNet branch of the reference ``CuboidProposalNetSoft`` (.train(), ROOTNET_TRAIN_SYNTH) on
+    set 1 of ``ssl_case`` with seeded torch draws: real volume, synthetic volume, target volume, proposals and the
+    gradients of ``100 * mse(synthetic, target)``."""
+    from models.cuboid_proposal_net_soft import CuboidProposalNetSoft
+    from selfpose3d_b200 import synthetic
+    cfg.NETWORK.ROOTNET_TRAIN_SYNTH = True
+    try:
+        net = CuboidProposalNetSoft(cfg)
+    finally:
+        cfg.NETWORK.ROOTNET_TRAIN_SYNTH = False
+    net.load_state_dict(synthetic.trained_like_state_dict(net, seed=96), strict=True)
+    net.train()
+    (_, meta, targets), _, _ = ssl_case()
+    torch.manual_seed(SYNTH_TORCH_SEED)
+    main, syn, target, gc = net(targets, meta, flip_xcoords=meta[0]["hflip"])
+    (100.0 * torch.nn.functional.mse_loss(syn, target)).backward()
+    named = list(net.named_parameters())
+    return dict(syn_seed=96, syn_main=main.detach().numpy(), syn_cubes=syn.detach().numpy(), syn_target=target.numpy(),
+                syn_grid_centers=gc.detach().numpy(), syn_param_names=np.array([n for n, _ in named]),
+                syn_param_grad_norm=np.array([float(p.grad.double().norm()) for _, p in named]))
+
+
 def main():
     sys.path.insert(0, HERE)
     import ref_import
@@ -89,6 +115,7 @@ def main():
                param_names=np.array([n for n, _ in named]),
                param_grad_norm=np.array([-1.0 if p.grad is None else float(p.grad.double().norm()) for _, p in named]),
                param_grad_sum=np.array([0.0 if p.grad is None else float(p.grad.double().sum()) for _, p in named]))
+    out.update(synth_root_step(cfg))
     path = os.path.join(HERE, "ssl_step.npz")
     np.savez_compressed(path, **out)
     print("ssl_step.npz %.1f KB" % (os.path.getsize(path) / 1024), dict(zip(out["loss_names"], out["loss_values"])))

@@ -167,14 +167,3 @@ def test_ctypes_struct_layouts_match_the_c_header(tmp_path):
     for line in out:
         name, size = line.split()
         assert ctypes.sizeof(pairs[name]) == int(size), (name, ctypes.sizeof(pairs[name]), int(size))
-
-
-def test_unported_training_branch_raises():
-    """The one training branch that is not built (the synthetic-root RootNet branch, reference
-    cuboid_proposal_net_soft.py:151-241) says so instead of silently doing something else."""
-    from selfpose3d_b200.models import cuboid_proposal_net_soft
-    cfg = default_config()
-    cfg.NETWORK.ROOTNET_TRAIN_SYNTH = True
-    net = cuboid_proposal_net_soft.CuboidProposalNetSoft(cfg)
-    with pytest.raises(NotImplementedError):
-        net.train_rootnet(1, None, None, None)

@@ -221,3 +221,44 @@ def test_ssl_training_step_matches_reference(emulated, monkeypatch, golden):  # 
         assert abs(gn - norm) <= 5e-2 * norm, (name, gn, norm)
         checked += 1
     assert checked >= 150, checked
+
+
+def test_synthetic_root_step_matches_reference(emulated, monkeypatch, golden):  # noqa: F811
+    """``CuboidProposalNetSoft`` with ``ROOTNET_TRAIN_SYNTH`` in .train(): the random roots are drawn in the
+    reference's order, so with the same torch seed the target volume, the synthetic volume, the real volume, the
+    proposals and the gradients equal the step recorded from the reference (ssl_step.npz, keys ``syn_*``)."""
+    import sys
+    from conftest import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    import make_golden_ssl as gen
+    from selfpose3d_b200.models import cuboid_proposal_net_soft
+    monkeypatch.setattr(ag, "Unproject", _Apply(emul_unproject))
+    monkeypatch.setattr(ops, "nms_topk", emul_nms_topk)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
+    gs = golden("ssl_step")
+    cfg = gen.configure(default_config())
+    cfg.NETWORK.IMAGE_SIZE, cfg.NETWORK.HEATMAP_SIZE = list(gen.IMAGE), list(gen.HEATMAP)
+    cfg.NETWORK.ROOTNET_TRAIN_SYNTH = True
+    net = cuboid_proposal_net_soft.CuboidProposalNetSoft(cfg)
+    net.load_state_dict(synthetic.trained_like_state_dict(net, seed=int(gs["syn_seed"])), strict=True)
+    net.train()
+    (_, meta, targets), _, _ = gen.ssl_case()
+    torch.manual_seed(gen.SYNTH_TORCH_SEED)
+    main, syn, target, gc = net(targets, meta, flip_xcoords=meta[0]["hflip"])
+    (100.0 * F.mse_loss(syn, target)).backward()
+    np.testing.assert_allclose(target.numpy(), gs["syn_target"], rtol=0, atol=1e-6)
+    for got, key in ((main, "syn_main"), (syn, "syn_cubes")):
+        np.testing.assert_allclose(got.detach().numpy(), gs[key], rtol=0, atol=1e-4 * np.abs(gs[key]).max(), err_msg=key)
+    np.testing.assert_allclose(gc.detach().numpy(), gs["syn_grid_centers"], rtol=1e-4, atol=1e-3)
+    params = dict(net.named_parameters())
+    top = float(gs["syn_param_grad_norm"].max())
+    checked = 0
+    for name, norm in zip(gs["syn_param_names"], gs["syn_param_grad_norm"]):
+        gn = float(params[str(name)].grad.double().norm())
+        if norm < 1e-5 * top:
+            assert gn < 1e-3 * top, (name, gn, norm)
+            continue
+        assert abs(gn - norm) <= 1e-2 * norm, (name, gn, norm)
+        checked += 1
+    assert checked >= 40, checked
