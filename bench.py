@@ -171,6 +171,49 @@ def workload_config(batch):
             "parallelism": "independent frames per rank, no data-path collective"}
 
 
+def time_training_step(dev, timed, steps=2):
+    """Supervised ``MultiPersonPoseNet`` step (reference lib/models/multi_person_posenet.py:36-102 in .train()): frozen
+    PoseResNet-50 on 5 views of one 3x384x288 frame, root net (80x80x20) and pose net (10 ground-truth-matched 64^3
+    cubes) forward + backward through the float32 training path, SGD-free (gradients only)."""
+    from selfpose3d_b200 import synthetic, _lib, ops
+    from selfpose3d_b200.models import multi_person_posenet
+    ops.set_volume_dtype(torch.float32)
+    ops.set_float32_conv("simt")
+    cfg = make_cfg(1)
+    cfg.MODEL = "multi_person_posenet"
+    model = multi_person_posenet.get_multi_person_pose_net(cfg, is_train=False)
+    model.load_state_dict(synthetic.trained_like_state_dict(model, seed=0), strict=True)
+    model = model.to(dev).train()
+    model.backbone.eval()
+    cams = synthetic.ring_cameras(VIEWS, seed=0)
+    meta = synthetic.make_meta(cams, 1, IMAGE_SIZE)
+    images = [im.to(dev) for im in synthetic.random_images(1, VIEWS, IMAGE_SIZE, seed=5)]
+    # ground truth next to the proposals the (randomly weighted) root net makes in training mode (batch statistics), so
+    # that all 10 slots are matched to a person
+    with torch.no_grad():
+        _, _, gc, _, _, _ = model(views=images, meta=meta)
+    J = cfg.NETWORK.NUM_JOINTS
+    roots = gc[:, :, :3].detach().cpu().double() + 50.0
+    meta[0].update(roots_3d=roots, num_person=torch.tensor([PROPOSALS]),
+                   joints_3d=roots[:, :, None, :].expand(-1, -1, J, -1).contiguous(),
+                   joints_3d_vis=torch.ones(1, PROPOSALS, J, 3, dtype=torch.float64))
+    targets_3d = torch.rand(1, *cfg.MULTI_PERSON.INITIAL_CUBE_SIZE, device=dev)
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        _, _, grid, _, loss_3d, loss_cord = model(views=images, meta=meta, targets_3d=targets_3d)
+        (loss_3d + loss_cord).backward()
+        return grid
+
+    grid = step()
+    matched = int((grid[:, :, 3] >= 0).sum())
+    ms, launches, _, _ = timed(step, steps)
+    return {"value": steps / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms / steps, "steps": steps,
+            "gpu_launches": launches, "matched_proposals": matched,
+            "what": "supervised step, 1 frame x 5 views, frozen backbone, root net + pose net forward and backward "
+                    "(float32 SIMT training path)"}
+
+
 def run_ours(args, rank, world, local_rank):
     from selfpose3d_b200 import synthetic, _lib, ops
     from selfpose3d_b200.models import multi_person_posenet_ssv
@@ -335,6 +378,19 @@ def run_ours(args, rank, world, local_rank):
         f32_faithful["note"] = ("float32 activations / weights as sums of 2 (bf16x3) or 3 (bf16x6) bf16 terms on the same "
                                 "tcgen05 kernel, float32 accumulation; accuracy: tests/test_gpu_split.py")
 
+    # one supervised training step (forward + backward of root net and pose net on the float32 training path, heat-maps
+    # from the frozen backbone) on ONE frame: a first throughput number of the correctness-first backward kernels
+    # (SIMT float32).  N = 1 only, never fatal.
+    train_step = None
+    if world == 1 and not args.no_train_step:
+        try:
+            train_step = time_training_step(dev, timed)
+        except Exception as exc:   # noqa: BLE001
+            train_step = {"error": repr(exc)[:300]}
+        finally:
+            ops.set_float32_conv("simt")
+            ops.set_volume_dtype(torch.bfloat16 if args.volume_dtype == "bf16" else torch.float32)
+
     cpu_frames = 5
     cpu_fps, cpu_spf = cpu_reference_frames_per_s(cpu_frames, 1, 1) if not args.no_cpu_baseline else (None, None)
     line = {
@@ -358,6 +414,7 @@ def run_ours(args, rank, world, local_rank):
         "roofline_unproject": roofline_unproject,
         "kernel_ms_per_step": {k: v["ms"] / prof_steps for k, v in kernels.items()},
         "f32_faithful": f32_faithful,
+        "train_step": train_step,
         "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                          "sample": "%d x 1 frame (5 views 3x384x288, 10 proposals) through oracle/pipeline.py on torch "
                                    "CPU (all host threads), 1 warm-up, %s s per frame"
@@ -378,6 +435,7 @@ def main():
                          "accumulation, f32 = float32 SIMT convolutions (bit-faithful parity path), f32x3 / f32x6 = "
                          "float32 activations on the tcgen05 kernel through bf16 operand splitting")
     ap.add_argument("--no-f32-faithful", action="store_true", help="skip the float32-faithful side measurement")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the training-step side measurement")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
