@@ -380,7 +380,7 @@ def run_ours(args, rank, world, local_rank):
 
     # one supervised training step (forward + backward of root net and pose net on the float32 training path, heat-maps
     # from the frozen backbone) on ONE frame: a first throughput number of the correctness-first backward kernels
-    # (SIMT float32; DESIGN.md section 10).  N = 1 only, never fatal.
+    # (SIMT float32; DESIGN.md section 9).  N = 1 only, never fatal.
     train_step = None
     if world == 1 and not args.no_train_step:
         try:
