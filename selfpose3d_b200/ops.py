@@ -6,8 +6,6 @@ hand-written kernel on torch's current stream.  There is no CPU path.
 """
 from __future__ import annotations
 
-import math
-
 import numpy as np
 import torch
 

@@ -3,7 +3,6 @@
 (include/sp3d.h), and a whole V2VNet training step (forward, running statistics, gradients of the input and of all
 156 parameters) is compared with autograd through the oracle's functional restatement of the reference net.  The
 kernels themselves are checked on the GPU (tests/test_gpu_backward.py)."""
-import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F

@@ -6,7 +6,6 @@ parameters.  Every kernel entry point is replaced by a torch / numpy emulation o
 (include/sp3d.h), so this pins the host-side logic; the kernels are checked on the GPU
 (tests/test_gpu_backward.py)."""
 import numpy as np
-import pytest
 import torch
 import torch.nn.functional as F
 
@@ -171,7 +170,6 @@ def test_ssl_training_step_matches_reference(emulated, monkeypatch, golden):  # 
     (tests/golden/make_golden_ssl.py -> ssl_step.npz): the four losses, the joints, the proposals and the gradient
     norms of all 331 trained parameters."""
     import sys
-    import os
     from conftest import GOLDEN
     sys.path.insert(0, GOLDEN)
     import make_golden_ssl as gen
