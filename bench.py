@@ -171,33 +171,30 @@ def workload_config(batch):
             "parallelism": "independent frames per rank, no data-path collective"}
 
 
-def time_training_step(dev, timed, steps=2):
-    """Supervised ``MultiPersonPoseNet`` step (reference lib/models/multi_person_posenet.py:36-102 in .train()): frozen
-    PoseResNet-50 on 5 views of one 3x384x288 frame, root net (80x80x20) and pose net (10 ground-truth-matched 64^3
-    cubes) forward + backward through the float32 training path, SGD-free (gradients only)."""
-    from selfpose3d_b200 import synthetic, _lib, ops
+def build_training_step(cfg, dev, image_size, views, seed=5):
+    """Model, inputs and the step closure of the training-step measurement: supervised ``MultiPersonPoseNet`` step
+    (reference lib/models/multi_person_posenet.py:36-102 in .train()) on ONE frame -- frozen backbone, root net and
+    pose net (every proposal slot matched to a ground-truth person) forward + backward, gradients only."""
+    from selfpose3d_b200 import synthetic
     from selfpose3d_b200.models import multi_person_posenet
-    ops.set_volume_dtype(torch.float32)
-    ops.set_float32_conv("simt")
-    cfg = make_cfg(1)
     cfg.MODEL = "multi_person_posenet"
     model = multi_person_posenet.get_multi_person_pose_net(cfg, is_train=False)
     model.load_state_dict(synthetic.trained_like_state_dict(model, seed=0), strict=True)
     model = model.to(dev).train()
     model.backbone.eval()
-    cams = synthetic.ring_cameras(VIEWS, seed=0)
-    meta = synthetic.make_meta(cams, 1, IMAGE_SIZE)
-    images = [im.to(dev) for im in synthetic.random_images(1, VIEWS, IMAGE_SIZE, seed=5)]
+    cams = synthetic.ring_cameras(views, seed=0)
+    meta = synthetic.make_meta(cams, 1, image_size)
+    images = [im.to(dev) for im in synthetic.random_images(1, views, image_size, seed=seed)]
     # ground truth next to the proposals the (randomly weighted) root net makes in training mode (batch statistics), so
-    # that all 10 slots are matched to a person
+    # that every slot is matched to a person
     with torch.no_grad():
         _, _, gc, _, _, _ = model(views=images, meta=meta)
-    J = cfg.NETWORK.NUM_JOINTS
+    K, J = cfg.MULTI_PERSON.MAX_PEOPLE_NUM, cfg.NETWORK.NUM_JOINTS
     roots = gc[:, :, :3].detach().cpu().double() + 50.0
-    meta[0].update(roots_3d=roots, num_person=torch.tensor([PROPOSALS]),
+    meta[0].update(roots_3d=roots, num_person=torch.tensor([K]),
                    joints_3d=roots[:, :, None, :].expand(-1, -1, J, -1).contiguous(),
-                   joints_3d_vis=torch.ones(1, PROPOSALS, J, 3, dtype=torch.float64))
-    targets_3d = torch.rand(1, *cfg.MULTI_PERSON.INITIAL_CUBE_SIZE, device=dev)
+                   joints_3d_vis=torch.ones(1, K, J, 3, dtype=torch.float64))
+    targets_3d = torch.rand(1, *cfg.MULTI_PERSON.INITIAL_CUBE_SIZE).to(dev)
 
     def step():
         model.zero_grad(set_to_none=True)
@@ -205,6 +202,14 @@ def time_training_step(dev, timed, steps=2):
         (loss_3d + loss_cord).backward()
         return grid
 
+    return model, step
+
+
+def time_training_step(dev, timed, steps=2):
+    from selfpose3d_b200 import ops
+    ops.set_volume_dtype(torch.float32)
+    ops.set_float32_conv("simt")
+    _, step = build_training_step(make_cfg(1), dev, IMAGE_SIZE, VIEWS)
     grid = step()
     matched = int((grid[:, :, 3] >= 0).sum())
     ms, launches, _, _ = timed(step, steps)

@@ -260,3 +260,27 @@ def test_synthetic_root_step_matches_reference(emulated, monkeypatch, golden):  
         assert abs(gn - norm) <= 1e-2 * norm, (name, gn, norm)
         checked += 1
     assert checked >= 40, checked
+
+
+def test_bench_training_step_case(emulated, monkeypatch):  # noqa: F811
+    """bench.py's training-step side measurement at toy size with emulated kernels: the ground truth derived from the
+    training-mode proposals matches every slot, and the step leaves gradients on root-net and pose-net parameters
+    (none on the frozen backbone's)."""
+    import bench
+    from test_autograd_cpu import _maxpool_any
+    monkeypatch.setattr(ag, "Unproject", _Apply(emul_unproject))
+    monkeypatch.setattr(ag, "SoftArgmax", _Apply(emul_softargmax))
+    monkeypatch.setattr(ops, "nms_topk", emul_nms_topk)
+    monkeypatch.setattr(ops, "maxpool", _maxpool_any)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
+    cfg = default_config()
+    cfg.NETWORK.NUM_JOINTS = 3
+    cfg.NETWORK.IMAGE_SIZE, cfg.NETWORK.HEATMAP_SIZE = [64, 96], [16, 24]
+    cfg.MULTI_PERSON.INITIAL_CUBE_SIZE, cfg.MULTI_PERSON.MAX_PEOPLE_NUM, cfg.MULTI_PERSON.THRESHOLD = [8, 8, 4], 2, -1e9
+    cfg.PICT_STRUCT.CUBE_SIZE = [8, 8, 8]
+    model, step = bench.build_training_step(cfg, "cpu", [64, 96], 3)
+    grid = step()
+    assert int((grid[:, :, 3] >= 0).sum()) == 2
+    got = {n.split(".")[0] for n, p in model.named_parameters() if p.grad is not None and bool(p.grad.any())}
+    assert got == {"root_net", "pose_net"}, got
