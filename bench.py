@@ -194,7 +194,7 @@ def build_training_step(cfg, dev, image_size, views, seed=5):
     meta[0].update(roots_3d=roots, num_person=torch.tensor([K]),
                    joints_3d=roots[:, :, None, :].expand(-1, -1, J, -1).contiguous(),
                    joints_3d_vis=torch.ones(1, K, J, 3, dtype=torch.float64))
-    targets_3d = torch.rand(1, *cfg.MULTI_PERSON.INITIAL_CUBE_SIZE).to(dev)
+    targets_3d = torch.rand(1, *cfg.MULTI_PERSON.INITIAL_CUBE_SIZE, generator=torch.Generator().manual_seed(seed)).to(dev)
 
     def step():
         model.zero_grad(set_to_none=True)

@@ -168,3 +168,38 @@ def infer_view_sharded(model, local_views, meta, group=None):
     pred[:, :, :, 3:] = grid_centers[:, :, 3:].reshape(B, -1, 1, 2)
     regress_sharded(model.pose_net, all_heatmaps, cams, grid_centers, pred, group=group)
     return pred, all_heatmaps, grid_centers
+
+
+def allreduce_gradients(parameters, group=None, bucket_bytes=64 << 20):
+    """Data-parallel gradient exchange of the training path: the gradients of all trainable
+    ``parameters`` are averaged over the ranks with one sum all-reduce per bucket of ``bucket_bytes`` (flattened
+    float32; 211 MB for the 52.7 M trainable parameters of the SSL model = 4 buckets), NCCL on GPUs.  Parameters
+    without a gradient on this rank take part as zeros so that the buckets line up on every rank (the reference trains
+    under ``nn.DataParallel``, which sums replica gradients the same way, ``tools/train_3d.py:75``)."""
+    world = dist.get_world_size(group)
+    params = [p for p in parameters if p.requires_grad]
+    if world == 1 or not params:
+        return
+    bucket, size = [], 0
+    buckets = []
+    for p in params:
+        n = p.numel() * 4
+        if bucket and size + n > bucket_bytes:
+            buckets.append(bucket)
+            bucket, size = [], 0
+        bucket.append(p)
+        size += n
+    if bucket:
+        buckets.append(bucket)
+    for bucket in buckets:
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in bucket])
+        dist.all_reduce(flat, group=group)
+        flat /= world
+        off = 0
+        for p in bucket:
+            g = flat[off:off + p.numel()].view_as(p).to(p.dtype)
+            off += p.numel()
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)

@@ -73,3 +73,62 @@ def test_collective_helpers_world2_gloo():
     results = mgr.dict()
     mp.spawn(_worker, args=(world, port, results), nprocs=world, join=True)
     assert dict(results) == {0: (True, True, True), 1: (True, True, True)}
+
+
+def _toy_cfg():
+    from selfpose3d_b200.config import default_config
+    cfg = default_config()
+    cfg.NETWORK.NUM_JOINTS = 3
+    cfg.NETWORK.IMAGE_SIZE, cfg.NETWORK.HEATMAP_SIZE = [64, 96], [16, 24]
+    cfg.MULTI_PERSON.INITIAL_CUBE_SIZE, cfg.MULTI_PERSON.MAX_PEOPLE_NUM, cfg.MULTI_PERSON.THRESHOLD = [8, 8, 4], 2, -1e9
+    cfg.PICT_STRUCT.CUBE_SIZE = [8, 8, 8]
+    return cfg
+
+
+def _train_worker(rank, world, port, results):
+    """Data-parallel training step: every rank runs the supervised step on its own frame (kernels emulated on CPU),
+    then the gradients are averaged with sd.allreduce_gradients."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import bench
+    import test_training_cpu
+    test_training_cpu.apply_emulation_in_this_process()
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model, step = bench.build_training_step(_toy_cfg(), "cpu", [64, 96], 3, seed=5 + rank)
+        step()
+        sd.allreduce_gradients(model.parameters(), bucket_bytes=1 << 20)      # several buckets
+        results[rank] = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_average_world2_gloo():
+    import bench
+    import test_training_cpu
+    world = 2
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_train_worker, args=(world, _free_port(), results), nprocs=world, join=True)
+    got0, got1 = results[0], results[1]
+    assert set(got0) == set(got1) and all(torch.equal(got0[n], got1[n]) for n in got0)     # replicas agree
+    # single-process truth: the mean of the two ranks' own gradients
+    import subprocess
+    import sys
+    import pickle
+    code = ("import sys, pickle, torch; sys.path.insert(0, %r); sys.path.insert(0, %r); import bench, test_training_cpu, "
+            "test_dist_gloo; test_training_cpu.apply_emulation_in_this_process(); out = []\n"
+            "for seed in (5, 6):\n"
+            "    m, step = bench.build_training_step(test_dist_gloo._toy_cfg(), 'cpu', [64, 96], 3, seed=seed); step()\n"
+            "    out.append({n: p.grad for n, p in m.named_parameters() if p.grad is not None})\n"
+            "pickle.dump(out, sys.stdout.buffer)" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                      os.path.dirname(os.path.abspath(__file__))))
+    single = pickle.loads(subprocess.run([sys.executable, "-c", code], check=True, capture_output=True).stdout)
+    trained = [n for n in got0 if n.split(".")[0] in ("root_net", "pose_net")]
+    assert len(trained) >= 100
+    top = max(float(((single[0][n] + single[1][n]) / 2).norm()) for n in trained)
+    for n in trained:
+        want = (single[0][n] + single[1][n]) / 2
+        # (thread counts differ between the workers and the single process: summation order, not semantics)
+        assert float((got0[n] - want).norm()) <= 1e-3 * max(float(want.norm()), 1e-6 * top), n

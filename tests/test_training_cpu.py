@@ -284,3 +284,19 @@ def test_bench_training_step_case(emulated, monkeypatch):  # noqa: F811
     assert int((grid[:, :, 3] >= 0).sum()) == 2
     got = {n.split(".")[0] for n, p in model.named_parameters() if p.grad is not None and bool(p.grad.any())}
     assert got == {"root_net", "pose_net"}, got
+
+
+def apply_emulation_in_this_process():
+    """The same kernel emulations as the fixtures above, applied for good (spawned `gloo` workers of
+    tests/test_dist_gloo.py, which have no pytest fixtures)."""
+    import test_autograd_cpu as T
+    from selfpose3d_b200 import grad_ops
+    ops.conv_launch, ops.to_channel_last, ops.to_channel_first = T.emulate_conv_launch, T._cl, T._cf
+    ops.maxpool, ops.nms_topk = T._maxpool_any, emul_nms_topk
+    grad_ops._f32 = lambda *a: None
+    for name, fn in (("maxpool_bwd", T._maxpool_bwd_any), ("bn_stats", T._bn_stats), ("bn_apply", T._bn_apply),
+                     ("bn_bwd", T._bn_bwd), ("relu_bwd", T._relu_bwd), ("conv_wgrad", T._conv_wgrad_any)):
+        setattr(grad_ops, name, fn)
+    ag.Unproject, ag.SoftArgmax = _Apply(emul_unproject), _Apply(emul_softargmax)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.Tensor.is_cuda = property(lambda self: True)
