@@ -173,3 +173,34 @@ def random_images(batch, num_views, image_size, seed=0):
     rs = np.random.RandomState(seed + 77)
     W, H = int(image_size[0]), int(image_size[1])
     return [torch.from_numpy(rs.randn(batch, 3, H, W).astype(np.float32)) for _ in range(num_views)]
+
+
+def ssl_training_case(image_size, heatmap_size, num_joints, batch, num_views, max_people, seed=77, image_seed=40,
+                      augment=((12.0, 1.1, False), (-8.0, 0.9, True), (0.0, 1.0, False))):
+    """Inputs of one self-supervised training step (``MultiPersonPoseNetSSV.forward(inference=False)``): three view
+    sets ``(views, meta, pseudo heat-maps)`` -- set 1 and 2 with rotation / scale jitter (and an h-flip), set 3 plain --
+    with the ``meta`` entries the SSL forward reads (``camera`` incl. ``f`` / ``c``, ``trans``, ``hflip``, pseudo 2-D
+    poses ``joints`` / ``joints_vis``), as ``lib/dataset/JointsDatasetSSV.py:540-640`` collates them."""
+    from .utils.transforms import get_affine_transform
+    cams = ring_cameras(num_views, seed=0)
+    rs = np.random.RandomState(seed)
+    w, h = int(heatmap_size[0]), int(heatmap_size[1])
+    sets = []
+    for s, (rot, mul, flip) in enumerate(augment):
+        meta = make_meta(cams, batch, image_size, rotation=[[rot] * batch] * num_views, scale_mul=[[mul] * batch] * num_views)
+        for m in meta:
+            cam = {k: v.float() for k, v in m["camera"].items()}
+            cam["f"] = torch.stack([cam["fx"], cam["fy"]], -1).reshape(batch, 2, 1)
+            cam["c"] = torch.stack([cam["cx"], cam["cy"]], -1).reshape(batch, 2, 1)
+            m["camera"] = cam
+            m["joints"] = torch.zeros(batch, max_people, num_joints, 2, dtype=torch.float64)
+            m["joints"][:, :2] = torch.from_numpy(rs.uniform(5, 60, (batch, 2, num_joints, 2)))
+            m["joints_vis"] = torch.ones(batch, max_people, num_joints, 2, dtype=torch.float64)
+        trans = np.stack([get_affine_transform(meta[0]["center"][b].numpy(), meta[0]["scale"][b].numpy(),
+                                               float(meta[0]["rotation"][b]), image_size) for b in range(batch)])
+        meta[0]["trans"] = torch.from_numpy(trans.astype(np.float32))
+        meta[0]["hflip"] = torch.tensor([flip] * batch)
+        views = random_images(batch, num_views, image_size, seed=image_seed + s)
+        targets = [torch.from_numpy(rs.rand(batch, num_joints, h, w).astype(np.float32)) for _ in range(num_views)]
+        sets.append((views, meta, targets))
+    return sets

@@ -40,28 +40,7 @@ def ssl_case():
     """Seeded inputs of the step: three view sets (set 1: rotation / scale jitter; set 2: other jitter + h-flip; set 3
     plain), pseudo heat-maps, pseudo 2-D poses."""
     from selfpose3d_b200 import synthetic
-    from selfpose3d_b200.utils.transforms import get_affine_transform
-    cams = synthetic.ring_cameras(V, seed=0)
-    rs = np.random.RandomState(77)
-    sets = []
-    for s, (rot, mul, flip) in enumerate([(12.0, 1.1, False), (-8.0, 0.9, True), (0.0, 1.0, False)]):
-        meta = synthetic.make_meta(cams, B, IMAGE, rotation=[[rot] * B] * V, scale_mul=[[mul] * B] * V)
-        for m in meta:
-            cam = {k: v.float() for k, v in m["camera"].items()}
-            cam["f"] = torch.stack([cam["fx"], cam["fy"]], -1).reshape(B, 2, 1)
-            cam["c"] = torch.stack([cam["cx"], cam["cy"]], -1).reshape(B, 2, 1)
-            m["camera"] = cam
-            m["joints"] = torch.zeros(B, K, J, 2, dtype=torch.float64)
-            m["joints"][:, :2] = torch.from_numpy(rs.uniform(5, 60, (B, 2, J, 2)))
-            m["joints_vis"] = torch.ones(B, K, J, 2, dtype=torch.float64)
-        trans = np.stack([get_affine_transform(meta[0]["center"][b].numpy(), meta[0]["scale"][b].numpy(),
-                                               float(meta[0]["rotation"][b]), IMAGE) for b in range(B)])
-        meta[0]["trans"] = torch.from_numpy(trans.astype(np.float32))
-        meta[0]["hflip"] = torch.tensor([flip] * B)
-        views = synthetic.random_images(B, V, IMAGE, seed=40 + s)
-        targets = [torch.from_numpy(rs.rand(B, J, HEATMAP[1], HEATMAP[0]).astype(np.float32)) for _ in range(V)]
-        sets.append((views, meta, targets))
-    return sets
+    return synthetic.ssl_training_case(IMAGE, HEATMAP, J, B, V, K)
 
 
 SYNTH_TORCH_SEED = 1234
