@@ -47,7 +47,9 @@ class Conv(Function):
             pc = ops.PackedConv(weight, bias, None, stride, padding, transposed=transposed, relu=0)
         ctx.pc, ctx.has_bias = pc, bias is not None
         ctx.save_for_backward(x)
-        return pc(x, algo=_lib.CONV_SIMT_F32)
+        # float32 FMA kernel, or -- ops.set_float32_conv("bf16x3" / "bf16x6") -- the tcgen05 kernel on split operands
+        # where an instantiation exists for the shape (PackedConv.tc_available)
+        return pc(x)
 
     @staticmethod
     def backward(ctx, gy):

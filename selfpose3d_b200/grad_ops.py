@@ -195,7 +195,7 @@ def conv_dgrad(pc, grad_out, out_pitch=None, in_dims=None):
         if in_dims is None:
             raise _lib.Sp3dError("conv_dgrad of a strided convolution needs in_dims (the forward input's extent)")
         return adj(grad_out, algo=_lib.CONV_SIMT_F32, out_pitch=out_pitch, out_dims=[int(v) for v in in_dims])
-    return adj(grad_out, algo=_lib.CONV_SIMT_F32, out_pitch=out_pitch)
+    return adj(grad_out, out_pitch=out_pitch)      # float32 FMA kernel, or split operands on tcgen05 where compiled
 
 
 # --------------------------------------------------------------------------------------------- BatchNorm (training)

@@ -380,6 +380,21 @@ def _tc_finish(full, terms):
     return torch.stack([wts[wt] for _, wt in SPLIT_PAIRS[terms]], 1).to(torch.bfloat16).contiguous()
 
 
+# (kernel extent along x, along y / z, shared-memory row bytes, N = MMA columns, z-fold) of every conv_tc_kernel
+# instantiation in csrc/conv_tc.cu (the SP3D_TC_CASE list; tests/test_host_cpu.py keeps the two in step)
+TC_CASES = frozenset({
+    (7, 7, 32, 16, 1), (7, 7, 64, 32, 2), (3, 3, 64, 64, 2), (1, 7, 64, 32, 2), (3, 3, 128, 64, 2), (3, 3, 32, 32, 1),
+    (3, 3, 64, 32, 1), (3, 3, 64, 64, 1), (3, 3, 128, 64, 1), (3, 3, 128, 128, 1), (1, 1, 32, 32, 1), (1, 1, 64, 64, 1),
+    (1, 1, 64, 16, 1), (1, 1, 128, 16, 1), (1, 1, 128, 32, 1), (1, 1, 128, 64, 1), (1, 1, 128, 128, 1),
+    (1, 3, 128, 64, 1), (1, 3, 128, 128, 1), (1, 2, 128, 128, 1), (1, 4, 32, 64, 1)})
+
+
+def tc_case(ksize, cin, n, zfold=1):
+    """The kernel instantiation ``conv_tc`` (csrc/conv_tc.cu) dispatches a launch to: ``cin`` = channels per K block
+    as passed to the launch, ``n`` = ``cout_pitch_w``."""
+    return (int(ksize[0]), int(ksize[1]), 128 if cin >= 64 else int(cin) * 2 * max(int(zfold), 1), int(n), max(int(zfold), 1))
+
+
 class S2DConv:
     """A stride-2 2-D convolution (3x3/p1 or 7x7/p3, + folded BatchNorm + ReLU) evaluated on the tcgen05 path as a
     stride-1 convolution over the 2x2 space-to-depth tensor: tap ``d`` with offset ``t = d - pad`` lands on
@@ -769,6 +784,24 @@ class PackedConv:
             return _tc_finish(full, terms)
         return self._tc_cached("fused", terms, build)
 
+    def tc_plan(self, w_extent, out_pitch, out_dtype, with_residual):
+        """The kernel instantiations ``_call_tc`` would launch for an input whose innermost spatial extent is
+        ``w_extent`` (same branch order as ``_call_tc``)."""
+        n, cin_tc, _ = self._tc_dims()
+        if with_residual is False and self._tc_stack_ok(w_extent, out_pitch):
+            return [tc_case([1, 7, 7], 16, 16 * self.ZFOLD, self.ZFOLD)]
+        if not self.transposed and cin_tc == round_up(self.cin, 16) and self._tc_zfold_ok(w_extent, out_pitch):
+            return [tc_case(self.k, cin_tc, out_pitch * self.ZFOLD, self.ZFOLD)]
+        if not self.transposed:
+            return [tc_case(self.k, cin_tc, n)]
+        if self._tc_fused_ok(out_pitch, out_dtype):
+            return [tc_case([1, 1, 1], cin_tc, 128)]
+        return [tc_case(ks, cin_tc, n) for _, _, ks in self.phases]
+
+    def tc_available(self, w_extent, out_pitch, out_dtype, with_residual):
+        """``tc_supported()`` and every launch of the plan has a compiled kernel instantiation."""
+        return self.tc_supported() and all(c in TC_CASES for c in self.tc_plan(w_extent, out_pitch, out_dtype, with_residual))
+
     def _call_tc(self, x, residual, out_pitch, out_dtype, head=None, terms=0):
         """tcgen05 path.  ``terms`` = 0: ``x`` is bf16 channel-last.  ``terms`` = 3 / 6 (SP3D_CONV_TC_BF16X3): ``x`` is
         float32 channel-last; it is expanded into bf16 term planes (``split_bf16``) that the kernel multiplies with the
@@ -849,8 +882,10 @@ class PackedConv:
         if algo is None:
             if x.dtype == torch.bfloat16 and self.tc_supported():
                 algo = _lib.CONV_TC_BF16
-            elif (x.dtype == torch.float32 and _F32_CONV != "simt" and head is None and self.tc_supported()
-                  and out_dtype in (None, torch.float32)):
+            elif (x.dtype == torch.float32 and _F32_CONV != "simt" and head is None and out_dims is None
+                  and out_dtype in (None, torch.float32)
+                  and self.tc_available(int(x.shape[3]), round_up(self.cout, 4) if out_pitch is None else int(out_pitch),
+                                        torch.float32, residual is not None)):
                 algo = _lib.CONV_TC_BF16X3
             else:
                 algo = _lib.CONV_SIMT_F32

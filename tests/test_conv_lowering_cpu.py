@@ -399,3 +399,46 @@ def test_conv_dgrad_lowering(monkeypatch, case):
     gx = grad_ops.conv_dgrad(pc, cl(gy), out_pitch=xcl.shape[-1], in_dims=xcl.shape[1:4])
     assert gx.shape == xcl.shape
     torch.testing.assert_close(cf(gx, x.shape[1], nd), x.grad, rtol=1e-4, atol=1e-5)
+
+
+def test_tc_plan_predicts_the_launches(monkeypatch):
+    """PackedConv.tc_plan (used to decide whether the split-operand tensor-core path has a compiled kernel for a
+    layer) against the launches PackedConv._call_tc really makes, over every layer shape of V2VNet and PoseResNet."""
+    seen = []
+
+    def record(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksize, stride, tap_off0, tap_step, ostride,
+               ooffset, relu, algo=0, cin_real=None, cout_pitch_w=None, fused_phases=False, zfold=0, split_terms=0):
+        seen.append(ops.tc_case(ksize, cin, cout_pitch_w, zfold))
+
+    monkeypatch.setattr(ops, "conv_launch", record)
+    monkeypatch.setattr(ops, "split_bf16", emulate_split_bf16)
+    monkeypatch.setattr(ops, "stack_x_shifts", lambda x, taps, pad: torch.zeros(tuple(x.shape[:-1]) + (16,), dtype=torch.bfloat16))
+    monkeypatch.setattr(ops, "_F32_CONV", "bf16x3")
+    layers = [(nn.Conv3d(15, 16, 7, 1, 3), (4, 8, 6), False), (nn.Conv3d(1, 16, 7, 1, 3), (4, 8, 6), False),
+              (nn.Conv3d(1, 16, 7, 1, 3), (4, 8, 7), False), (nn.Conv3d(16, 32, 3, 1, 1), (4, 4, 16), True),
+              (nn.Conv3d(32, 32, 3, 1, 1), (4, 4, 16), True), (nn.Conv3d(32, 32, 3, 1, 1), (4, 4, 20), False),
+              (nn.Conv3d(32, 64, 3, 1, 1), (4, 4, 8), False), (nn.Conv3d(64, 64, 3, 1, 1), (4, 4, 8), True),
+              (nn.Conv3d(64, 128, 3, 1, 1), (4, 4, 4), False), (nn.Conv3d(128, 128, 3, 1, 1), (4, 4, 4), True),
+              (nn.Conv3d(16, 32, 1), (4, 4, 8), False), (nn.Conv3d(32, 15, 1), (4, 4, 8), False),
+              (nn.Conv3d(32, 1, 1), (4, 4, 8), False), (nn.ConvTranspose3d(128, 64, 2, 2), (2, 2, 2), True),
+              (nn.ConvTranspose3d(64, 32, 2, 2), (2, 2, 4), True), (nn.Conv2d(64, 256, 1), (6, 5), True),
+              (nn.Conv2d(256, 64, 1), (6, 5), False), (nn.Conv2d(64, 64, 3, 1, 1), (6, 5), False),
+              (nn.Conv2d(512, 512, 3, 1, 1), (6, 5), False), (nn.Conv2d(256, 512, 1, 2), (6, 4), False),
+              (nn.ConvTranspose2d(2048, 256, 4, 2, 1, bias=False), (3, 2), False), (nn.Conv2d(256, 15, 1), (6, 5), False)]
+    for mod, sp, with_res in layers:
+        transposed = isinstance(mod, (nn.ConvTranspose3d, nn.ConvTranspose2d))
+        pc = ops.PackedConv(mod.weight, mod.bias, None, mod.stride[0], mod.padding[0], transposed=transposed, relu=0)
+        x = torch.randn(1, mod.in_channels, *sp)
+        xcl = cl(x)
+        o = pc.out_shape(tuple(xcl.shape[1:4]))
+        pitch = ops.round_up(pc.cout, 4)
+        res = torch.zeros(1, o[0], o[1], o[2], pitch) if with_res else None
+        assert pc.tc_supported()
+        seen.clear()
+        plan = pc.tc_plan(int(xcl.shape[3]), pitch, torch.float32, with_res)
+        pc._call_tc(xcl, res, None, None, terms=3)
+        assert seen == plan, (mod, sp, seen, plan)
+        assert pc.tc_available(int(xcl.shape[3]), pitch, torch.float32, with_res), (mod, plan)
+    # adjoint shapes of the training path that have no compiled kernel must be reported as such (-> SIMT)
+    adj = ops.PackedConv(nn.Conv3d(32, 16, 3, 1, 1).weight, None, None, 1, 1, relu=0)      # dgrad of the 3^3 16 -> 32 layer
+    assert adj.tc_supported() and not adj.tc_available(8, 16, torch.float32, False)

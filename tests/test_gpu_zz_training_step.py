@@ -184,3 +184,30 @@ def test_ssl_training_step_matches_reference_on_gpu(golden):
             assert gn < 1e-3 * top, (name, gn, norm)
             continue
         assert abs(gn - norm) <= 5e-2 * norm, (name, gn, norm)
+
+
+@_FIRST_RUN
+def test_v2v_training_step_on_tensor_cores_matches_reference(golden):
+    """The V2VNet training step with ``ops.set_float32_conv("bf16x3")``: forward convolutions and the input gradients
+    whose adjoint shape has a compiled instantiation run on tcgen05 through split operands (weight gradients stay on
+    the float32 FMA kernel), against the step recorded from the reference (same bounds as the float32 path, x2)."""
+    from selfpose3d_b200 import ops
+    from selfpose3d_b200.models import v2v_net
+    gb = golden("backward")
+    net = v2v_net.V2VNet(3, 3)
+    net.load_state_dict(synthetic.trained_like_state_dict(net, seed=int(gb["v2v_seed"])), strict=True)
+    net = net.to(DEV).train()
+    x = torch.from_numpy(gb["v2v_x"]).to(DEV).requires_grad_(True)
+    ops.set_float32_conv("bf16x3")
+    try:
+        y = net(x)
+        (y * torch.from_numpy(gb["v2v_grad_y"]).to(DEV)).sum().backward()
+    finally:
+        ops.set_float32_conv("simt")
+    scale = float(np.abs(gb["v2v_y"]).max())
+    assert float(np.abs(y.detach().cpu().numpy() - gb["v2v_y"]).max()) <= 2e-4 * scale
+    assert float(np.abs(x.grad.cpu().numpy() - gb["v2v_grad_x"]).max()) <= 2e-3 * float(np.abs(gb["v2v_grad_x"]).max())
+    params = dict(net.named_parameters())
+    for name, norm in zip(gb["v2v_param_names"], gb["v2v_param_grad_norm"]):
+        g = params[str(name)].grad.double()
+        assert abs(float(g.norm()) - norm) <= 4e-3 * max(norm, 1e-3), (name, float(g.norm()), norm)

@@ -167,3 +167,17 @@ def test_ctypes_struct_layouts_match_the_c_header(tmp_path):
     for line in out:
         name, size = line.split()
         assert ctypes.sizeof(pairs[name]) == int(size), (name, ctypes.sizeof(pairs[name]), int(size))
+
+
+def test_tc_case_table_matches_the_kernel_instantiations():
+    """ops.TC_CASES (what the host believes is compiled) against the SP3D_TC_CASE list of csrc/conv_tc.cu."""
+    src = open(os.path.join(ROOT, "selfpose3d_b200", "csrc", "conv_tc.cu")).read()
+    body = src[src.index("int conv_tc(const sp3d_conv_args* a, cudaStream_t st)"):]
+    cases = set()
+    for m in re.finditer(r"^\s*SP3D_TC_CASE(_F)?\(([^)]*)\)\s*$", body, flags=re.M):
+        if not re.fullmatch(r"[\d,\s]+", m.group(2)):
+            continue                                   # the macro definitions themselves
+        v = [int(t) for t in m.group(2).split(",")]
+        cases.add((v[0], v[1], v[2], v[3], v[11] if m.group(1) else 1))
+    assert len(cases) >= 20
+    assert cases == set(ops.TC_CASES), cases ^ set(ops.TC_CASES)
