@@ -968,6 +968,9 @@ int conv_tc(const sp3d_conv_args* a, cudaStream_t st) {
   SP3D_TC_CASE(3, 3, 64, 64, 4, 3, 3, 2, 2, 64, 2)
   SP3D_TC_CASE(3, 3, 128, 64, 2, 1, 3, 2, 2, 64, 1)
   SP3D_TC_CASE(3, 3, 128, 128, 2, 1, 2, 2, 2, 32, 1)
+  // adjoint shapes of the training path's input gradients (3^3 32 -> 16 and 64 -> 32: dgrad of 16 -> 32 / 32 -> 64)
+  SP3D_TC_CASE(3, 3, 64, 16, 4, 9, 2, 2, 2, 128, 2)
+  SP3D_TC_CASE(3, 3, 128, 32, 2, 1, 3, 2, 2, 64, 1)
   // 1x1(x1) on any rank: a work item is a handful of MMAs, so the halo ring is deeper
   SP3D_TC_CASE(1, 1, 32, 32, 4, 1, 2, 6, 3, 128, 2)
   SP3D_TC_CASE(1, 1, 64, 64, 4, 1, 2, 4, 2, 128, 2)

@@ -384,7 +384,8 @@ def _tc_finish(full, terms):
 # instantiation in csrc/conv_tc.cu (the SP3D_TC_CASE list; tests/test_host_cpu.py keeps the two in step)
 TC_CASES = frozenset({
     (7, 7, 32, 16, 1), (7, 7, 64, 32, 2), (3, 3, 64, 64, 2), (1, 7, 64, 32, 2), (3, 3, 128, 64, 2), (3, 3, 32, 32, 1),
-    (3, 3, 64, 32, 1), (3, 3, 64, 64, 1), (3, 3, 128, 64, 1), (3, 3, 128, 128, 1), (1, 1, 32, 32, 1), (1, 1, 64, 64, 1),
+    (3, 3, 64, 32, 1), (3, 3, 64, 64, 1), (3, 3, 128, 64, 1), (3, 3, 128, 128, 1), (3, 3, 64, 16, 1), (3, 3, 128, 32, 1),
+    (1, 1, 32, 32, 1), (1, 1, 64, 64, 1),
     (1, 1, 64, 16, 1), (1, 1, 128, 16, 1), (1, 1, 128, 32, 1), (1, 1, 128, 64, 1), (1, 1, 128, 128, 1),
     (1, 3, 128, 64, 1), (1, 3, 128, 128, 1), (1, 2, 128, 128, 1), (1, 4, 32, 64, 1)})
 

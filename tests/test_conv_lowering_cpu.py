@@ -440,5 +440,7 @@ def test_tc_plan_predicts_the_launches(monkeypatch):
         assert seen == plan, (mod, sp, seen, plan)
         assert pc.tc_available(int(xcl.shape[3]), pitch, torch.float32, with_res), (mod, plan)
     # adjoint shapes of the training path that have no compiled kernel must be reported as such (-> SIMT)
-    adj = ops.PackedConv(nn.Conv3d(32, 16, 3, 1, 1).weight, None, None, 1, 1, relu=0)      # dgrad of the 3^3 16 -> 32 layer
+    adj = ops.PackedConv(nn.Conv3d(64, 16, 3, 1, 1).weight, None, None, 1, 1, relu=0)      # no such layer: 3^3 64 -> 16
     assert adj.tc_supported() and not adj.tc_available(8, 16, torch.float32, False)
+    adj = ops.PackedConv(nn.Conv3d(32, 16, 3, 1, 1).weight, None, None, 1, 1, relu=0)      # dgrad of the 3^3 16 -> 32 layer
+    assert adj.tc_available(8, 16, torch.float32, False)
