@@ -205,16 +205,26 @@ def build_training_step(cfg, dev, image_size, views, seed=5):
     return model, step
 
 
-def time_training_step(dev, timed, steps=2):
-    from selfpose3d_b200 import ops
+def time_training_step(dev, steps=2):
+    """Runs in a child process of the bench (``--train-step-only``), so that nothing it does can touch the main
+    measurement."""
+    from selfpose3d_b200 import ops, _lib
     ops.set_volume_dtype(torch.float32)
     ops.set_float32_conv("simt")
     _, step = build_training_step(make_cfg(1), dev, IMAGE_SIZE, VIEWS)
     grid = step()
     matched = int((grid[:, :, 3] >= 0).sum())
-    ms, launches, _, _ = timed(step, steps)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = _lib.launch_count
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
     return {"value": steps / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms / steps, "steps": steps,
-            "gpu_launches": launches, "matched_proposals": matched,
+            "gpu_launches": _lib.launch_count - l0, "matched_proposals": matched,
             "what": "supervised step, 1 frame x 5 views, frozen backbone, root net + pose net forward and backward "
                     "(float32 SIMT training path)"}
 
@@ -388,13 +398,14 @@ def run_ours(args, rank, world, local_rank):
     # (SIMT float32).  N = 1 only, never fatal.
     train_step = None
     if world == 1 and not args.no_train_step:
-        try:
-            train_step = time_training_step(dev, timed)
+        try:   # in a child process with a time limit: a side measurement must not be able to disturb this one
+            env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local_rank)))
+            res = subprocess.run([sys.executable, os.path.abspath(__file__), "--train-step-only"], capture_output=True,
+                                 text=True, timeout=240, env=env)
+            lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+            train_step = json.loads(lines[-1]) if lines else {"error": (res.stderr or "no output")[-300:]}
         except Exception as exc:   # noqa: BLE001
             train_step = {"error": repr(exc)[:300]}
-        finally:
-            ops.set_float32_conv("simt")
-            ops.set_volume_dtype(torch.bfloat16 if args.volume_dtype == "bf16" else torch.float32)
 
     cpu_frames = 5
     cpu_fps, cpu_spf = cpu_reference_frames_per_s(cpu_frames, 1, 1) if not args.no_cpu_baseline else (None, None)
@@ -441,6 +452,7 @@ def main():
                          "float32 activations on the tcgen05 kernel through bf16 operand splitting")
     ap.add_argument("--no-f32-faithful", action="store_true", help="skip the float32-faithful side measurement")
     ap.add_argument("--no-train-step", action="store_true", help="skip the training-step side measurement")
+    ap.add_argument("--train-step-only", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -448,6 +460,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.train_step_only:
+        torch.cuda.set_device(0)
+        print(json.dumps(time_training_step(torch.device("cuda", 0))), flush=True)
         return
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
