@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SP3D_ABI_VERSION 1
+#define SP3D_ABI_VERSION 2   /* 2: sp3d_conv_args.split_terms, sp3d_split_bf16, the backward operators */
 #define SP3D_MAX_VIEWS 8
 #define SP3D_CAM_FLOATS 32
 

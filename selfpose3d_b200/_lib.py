@@ -11,6 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsp3d.so")
 
+ABI_VERSION = 2      # SP3D_ABI_VERSION of include/sp3d.h these bindings were written against
 MAX_VIEWS = 8
 CAM_FLOATS = 32
 F32, BF16, F16 = 0, 1, 2
@@ -227,7 +228,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.sp3d_abi_version() != 1:
+    if lib.sp3d_abi_version() != ABI_VERSION:
         raise Sp3dError("libsp3d.so ABI version mismatch")
     _lib = lib
     return lib
