@@ -380,6 +380,27 @@ typedef struct {
 } sp3d_relu_bwd_args;
 int sp3d_relu_bwd(const sp3d_relu_bwd_args* a, void* stream);
 
+/* Gaussian joint rendering of the SSL losses (lib/models/multi_person_posenet_ssv.py:410-448): per (view, sample) and
+ * joint the heat-map  clip( sum_{p < n_people[b]} exp(-((x - kx/4)/3)^2/2 - ((y - ky/4)/3)^2/2), 0, 1 )  of the
+ * re-projected people, and its gradient with respect to the joint pixels (the clip passes gradient where the sum is
+ * <= 1).  kps [V, B, P, J, 2] network-input pixels; heatmaps [V, B, J, h, w]. */
+typedef struct {
+  const float* kps;
+  const int32_t* n_people;  /* [B] people per sample (<= P); rows beyond it are ignored */
+  int V, B, P, J, h, w;
+  float inv_scale;          /* heat-map pixels per network-input pixel (reference: 1/4) */
+  float sigma;              /* in heat-map pixels (reference: 3) */
+  float* heatmaps;
+} sp3d_gauss_render_args;
+int sp3d_gauss_render_fwd(const sp3d_gauss_render_args* a, void* stream);
+
+typedef struct {
+  sp3d_gauss_render_args fwd;   /* forward arguments; fwd.heatmaps is not used */
+  const float* grad_heatmaps;   /* [V, B, J, h, w] */
+  float* grad_kps;              /* [V, B, P, J, 2]; written (rows beyond n_people get zeros) */
+} sp3d_gauss_render_bwd_args;
+int sp3d_gauss_render_bwd(const sp3d_gauss_render_bwd_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -176,6 +176,16 @@ class ReluBwdArgs(C.Structure):
     _fields_ = [("grad_y", C.c_void_p), ("y", C.c_void_p), ("grad_x", C.c_void_p), ("n", C.c_int64)]
 
 
+class GaussRenderArgs(C.Structure):
+    _fields_ = [("kps", C.c_void_p), ("n_people", C.c_void_p),
+                ("V", C.c_int), ("B", C.c_int), ("P", C.c_int), ("J", C.c_int), ("h", C.c_int), ("w", C.c_int),
+                ("inv_scale", C.c_float), ("sigma", C.c_float), ("heatmaps", C.c_void_p)]
+
+
+class GaussRenderBwdArgs(C.Structure):
+    _fields_ = [("fwd", GaussRenderArgs), ("grad_heatmaps", C.c_void_p), ("grad_kps", C.c_void_p)]
+
+
 # every symbol include/sp3d.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "sp3d_abi_version": (C.c_int, []),
@@ -204,6 +214,8 @@ SYMBOLS = {
     "sp3d_bn_apply": (C.c_int, [C.POINTER(BnApplyArgs), C.c_void_p]),
     "sp3d_bn_bwd": (C.c_int, [C.POINTER(BnBwdArgs), C.c_void_p]),
     "sp3d_relu_bwd": (C.c_int, [C.POINTER(ReluBwdArgs), C.c_void_p]),
+    "sp3d_gauss_render_fwd": (C.c_int, [C.POINTER(GaussRenderArgs), C.c_void_p]),
+    "sp3d_gauss_render_bwd": (C.c_int, [C.POINTER(GaussRenderBwdArgs), C.c_void_p]),
 }
 
 _lib = None

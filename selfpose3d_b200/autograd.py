@@ -205,3 +205,20 @@ class SoftArgmax(Function):
         gx = grad_ops.softargmax_bwd(y, (X * Y * Z * pitch, 1, pitch), n, channels, (X, Y, Z), centers, grid_size, beta,
                                      out, g.contiguous())
         return gx, None, None
+
+
+class RenderGaussians(Function):
+    """Joint pixels ``[V,B,P,J,2]`` (+ people per sample) -> clipped Gaussian heat-maps ``[V,B,J,h,w]``
+    (``sp3d_gauss_render_fwd`` / ``sp3d_gauss_render_bwd``)."""
+
+    @staticmethod
+    def forward(ctx, kps, n_people, hw, inv_scale, sigma):
+        ctx.args = (tuple(hw), float(inv_scale), float(sigma))
+        ctx.save_for_backward(kps, n_people)
+        return grad_ops.gauss_render(kps, n_people, hw, inv_scale, sigma)
+
+    @staticmethod
+    def backward(ctx, g):
+        kps, n_people = ctx.saved_tensors
+        hw, inv_scale, sigma = ctx.args
+        return grad_ops.gauss_render_bwd(kps, n_people, hw, g, inv_scale, sigma), None, None, None, None

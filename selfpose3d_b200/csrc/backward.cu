@@ -401,6 +401,74 @@ __global__ void relu_bwd_kernel(const sp3d_relu_bwd_args a) {
     a.grad_x[i] = __ldg(a.y + i) > 0.0f ? __ldg(a.grad_y + i) : 0.0f;
 }
 
+// ------------------------------------------------------------------------------------------ Gaussian joint rendering
+// grid = (J, V * B): one CTA per (view, sample, joint) heat-map; the people's joint pixels sit in shared memory.
+constexpr int kGrMaxPeople = 32;
+
+__device__ __forceinline__ float gauss_term(float xx, float yy, float kx, float ky, float inv_sigma) {
+  const float a = (xx - kx) * inv_sigma, b = (yy - ky) * inv_sigma;
+  return expf(-(a * a) * 0.5f - (b * b) * 0.5f);
+}
+
+__global__ void __launch_bounds__(256) gauss_render_fwd_kernel(const sp3d_gauss_render_args a) {
+  __shared__ float s_k[kGrMaxPeople][2];
+  const int j = blockIdx.x, item = blockIdx.y, b = item % a.B;
+  const int n = min(a.n_people[b], a.P);
+  for (int p = threadIdx.x; p < n; p += blockDim.x) {
+    const float* k = a.kps + (((int64_t)item * a.P + p) * a.J + j) * 2;
+    s_k[p][0] = k[0] * a.inv_scale;
+    s_k[p][1] = k[1] * a.inv_scale;
+  }
+  __syncthreads();
+  const float inv_sigma = 1.0f / a.sigma;
+  float* out = a.heatmaps + ((int64_t)item * a.J + j) * a.h * a.w;
+  for (int i = threadIdx.x; i < a.h * a.w; i += blockDim.x) {
+    const float xx = (float)(i % a.w), yy = (float)(i / a.w);
+    float s = 0.0f;
+    for (int p = 0; p < n; ++p) s += gauss_term(xx, yy, s_k[p][0], s_k[p][1], inv_sigma);
+    out[i] = fminf(fmaxf(s, 0.0f), 1.0f);
+  }
+}
+
+__global__ void __launch_bounds__(256) gauss_render_bwd_kernel(const sp3d_gauss_render_bwd_args bw) {
+  const sp3d_gauss_render_args& a = bw.fwd;
+  __shared__ float s_k[kGrMaxPeople][2];
+  __shared__ double s_red[8];
+  const int j = blockIdx.x, item = blockIdx.y, b = item % a.B;
+  const int n = min(a.n_people[b], a.P);
+  for (int p = threadIdx.x; p < n; p += blockDim.x) {
+    const float* k = a.kps + (((int64_t)item * a.P + p) * a.J + j) * 2;
+    s_k[p][0] = k[0] * a.inv_scale;
+    s_k[p][1] = k[1] * a.inv_scale;
+  }
+  __syncthreads();
+  const float inv_sigma = 1.0f / a.sigma;
+  const float* g = bw.grad_heatmaps + ((int64_t)item * a.J + j) * a.h * a.w;
+  for (int p = 0; p < a.P; ++p) {
+    double gx = 0.0, gy = 0.0;
+    if (p < n) {
+      for (int i = threadIdx.x; i < a.h * a.w; i += blockDim.x) {
+        const float xx = (float)(i % a.w), yy = (float)(i / a.w);
+        float s = 0.0f;
+        for (int q = 0; q < n; ++q) s += gauss_term(xx, yy, s_k[q][0], s_k[q][1], inv_sigma);
+        if (s > 1.0f) continue;                       // clip(., 0, 1): no gradient above 1 (the sum is never below 0)
+        const float e = gauss_term(xx, yy, s_k[p][0], s_k[p][1], inv_sigma) * __ldg(g + i);
+        // d/dk of exp(-((x - k s)/sigma)^2 / 2) = e * (x - k s)/sigma * s/sigma with s = inv_scale
+        gx += (double)(e * (xx - s_k[p][0]));
+        gy += (double)(e * (yy - s_k[p][1]));
+      }
+    }
+    gx = block_sum(gx, s_red);
+    gy = block_sum(gy, s_red);
+    if (threadIdx.x == 0) {
+      float* o = bw.grad_kps + (((int64_t)item * a.P + p) * a.J + j) * 2;
+      const float c = inv_sigma * inv_sigma * a.inv_scale;
+      o[0] = (float)gx * c;
+      o[1] = (float)gy * c;
+    }
+  }
+}
+
 static int grid_for(int64_t total, int threads, int cap) {
   const int64_t want = (total + threads - 1) / threads;
   return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
@@ -546,5 +614,31 @@ extern "C" int sp3d_relu_bwd(const sp3d_relu_bwd_args* a, void* stream) {
     return SP3D_ERR_INVALID_ARG;
   if (a->n == 0) return SP3D_OK;
   relu_bwd_kernel<<<grid_for(a->n, 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
+  return check_launch();
+}
+
+static int gauss_render_check(const sp3d_gauss_render_args* a) {
+  if (a == nullptr || a->kps == nullptr || a->n_people == nullptr || a->V < 1 || a->B < 1 || a->P < 0 || a->J < 1 ||
+      a->h < 1 || a->w < 1 || !(a->sigma > 0.0f) || !(a->inv_scale > 0.0f))
+    return SP3D_ERR_INVALID_ARG;
+  if (a->P > kGrMaxPeople || a->J > 65535 || (int64_t)a->V * a->B > 65535) return SP3D_ERR_UNSUPPORTED;
+  return SP3D_OK;
+}
+
+extern "C" int sp3d_gauss_render_fwd(const sp3d_gauss_render_args* a, void* stream) {
+  int rc = gauss_render_check(a);
+  if (rc != SP3D_OK) return rc;
+  if (a->heatmaps == nullptr) return SP3D_ERR_INVALID_ARG;
+  gauss_render_fwd_kernel<<<dim3(a->J, a->V * a->B), 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
+  return check_launch();
+}
+
+extern "C" int sp3d_gauss_render_bwd(const sp3d_gauss_render_bwd_args* b, void* stream) {
+  if (b == nullptr) return SP3D_ERR_INVALID_ARG;
+  int rc = gauss_render_check(&b->fwd);
+  if (rc != SP3D_OK) return rc;
+  if (b->grad_heatmaps == nullptr || b->grad_kps == nullptr) return SP3D_ERR_INVALID_ARG;
+  if (b->fwd.P == 0) return SP3D_OK;
+  gauss_render_bwd_kernel<<<dim3(b->fwd.J, b->fwd.V * b->fwd.B), 256, 0, static_cast<cudaStream_t>(stream)>>>(*b);
   return check_launch();
 }

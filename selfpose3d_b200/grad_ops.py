@@ -267,3 +267,38 @@ def relu_bwd(grad_y, y):
     a.grad_y, a.y, a.grad_x, a.n = grad_y.data_ptr(), y.data_ptr(), gx.data_ptr(), y.numel()
     _lib.call("sp3d_relu_bwd", a, _stream(), kind="elementwise", work=3 * y.numel() * 4)
     return gx
+
+
+# --------------------------------------------------------------------------------------------- Gaussian joint rendering
+def _gauss_args(a, kps, n_people, hw, inv_scale, sigma):
+    V, B, P, J, _ = [int(v) for v in kps.shape]
+    a.kps, a.n_people = kps.data_ptr(), n_people.data_ptr()
+    a.V, a.B, a.P, a.J, a.h, a.w = V, B, P, J, int(hw[0]), int(hw[1])
+    a.inv_scale, a.sigma = float(inv_scale), float(sigma)
+
+
+def gauss_render(kps, n_people, hw, inv_scale=0.25, sigma=3.0):
+    """``kps [V,B,P,J,2]`` joint pixels (network input), ``n_people [B]`` int32 -> heat-maps ``[V,B,J,h,w]``:
+    clipped sum of the people's Gaussians (``sp3d_gauss_render_fwd``)."""
+    _f32(kps)
+    _require_cuda(n_people)
+    kps = kps.contiguous()
+    V, B, P, J, _ = [int(v) for v in kps.shape]
+    out = torch.empty(V, B, J, int(hw[0]), int(hw[1]), device=kps.device, dtype=torch.float32)
+    a = _lib.GaussRenderArgs()
+    _gauss_args(a, kps, n_people, hw, inv_scale, sigma)
+    a.heatmaps = out.data_ptr()
+    _lib.call("sp3d_gauss_render_fwd", a, _stream(), kind="render", work=out.numel() * 4)
+    return out
+
+
+def gauss_render_bwd(kps, n_people, hw, grad_heatmaps, inv_scale=0.25, sigma=3.0):
+    """Gradient of ``gauss_render`` with respect to ``kps``."""
+    _f32(kps, grad_heatmaps)
+    kps, grad_heatmaps = kps.contiguous(), grad_heatmaps.contiguous()
+    gk = torch.zeros_like(kps)
+    b = _lib.GaussRenderBwdArgs()
+    _gauss_args(b.fwd, kps, n_people, hw, inv_scale, sigma)
+    b.grad_heatmaps, b.grad_kps = grad_heatmaps.data_ptr(), gk.data_ptr()
+    _lib.call("sp3d_gauss_render_bwd", b, _stream(), kind="render", work=grad_heatmaps.numel() * 4)
+    return gk

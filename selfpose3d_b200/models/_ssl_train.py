@@ -13,6 +13,8 @@ The synthetic-root RootNet branch (``NETWORK.ROOTNET_TRAIN_SYNTH``) lives in ``c
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -56,6 +58,8 @@ def render_gaussians(kps_views, xx, yy):
     """Joint pixels -> heat-maps (reference :410-448): per (view, sample) a Gaussian of sigma 3 heat-map pixels around
     every person's joint, summed over the people and clipped to [0, 1].  ``kps_views``: list over views of lists over
     samples of ``[P_b, J, 2]``; ``xx, yy``: ``[1,1,h,w]`` pixel-index grids.  Returns ``[V, B, J, h, w]``."""
+    if os.environ.get("SP3D_RENDER_KERNEL") == "1":       # opt-in until its first B200 run: the fused rendering kernel
+        return _render_gaussians_kernel(kps_views, xx)
     views = []
     for kps_samples in kps_views:
         maps = []
@@ -66,6 +70,20 @@ def render_gaussians(kps_views, xx, yy):
             maps.append(torch.clip(g.sum(0), min=0.0, max=1.0))
         views.append(torch.stack(maps, 0))
     return torch.stack(views, 0)
+
+
+def _render_gaussians_kernel(kps_views, xx):
+    """The same through ``sp3d_gauss_render_fwd/bwd``: the ragged people lists are padded to ``[V,B,P,J,2]``."""
+    from .. import autograd as ag
+    counts = [int(kp.shape[0]) for kp in kps_views[0]]
+    P = max(max(counts), 1)
+    J = int(kps_views[0][0].shape[1])
+    dev = kps_views[0][0].device
+    padded = torch.stack([torch.stack([torch.cat([kp, kp.new_zeros(P - kp.shape[0], J, 2)], 0) for kp in samples], 0)
+                          for samples in kps_views], 0)
+    n_people = torch.tensor(counts, device=dev, dtype=torch.int32)
+    return ag.RenderGaussians.apply(padded.float(), n_people, (int(xx.shape[-2]), int(xx.shape[-1])),
+                                    1.0 / IMAGE_TO_HEATMAP, GAUSS_SIGMA)
 
 
 def hungarian_l1(kps_views, meta, width, height, drop_worst):

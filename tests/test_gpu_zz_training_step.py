@@ -211,3 +211,30 @@ def test_v2v_training_step_on_tensor_cores_matches_reference(golden):
     for name, norm in zip(gb["v2v_param_names"], gb["v2v_param_grad_norm"]):
         g = params[str(name)].grad.double()
         assert abs(float(g.norm()) - norm) <= 4e-3 * max(norm, 1e-3), (name, float(g.norm()), norm)
+
+
+@_FIRST_RUN
+def test_gauss_render_kernels_vs_autograd():
+    """sp3d_gauss_render_fwd / bwd against the tensor expression of the reference (:410-448) and its autograd gradient:
+    ragged people counts, joints inside and outside the map, sums above 1 (the clip gate)."""
+    from selfpose3d_b200 import autograd as ag
+    torch.manual_seed(5)
+    V, B, P, J, h, w = 3, 2, 4, 15, 24, 18
+    counts = torch.tensor([4, 2], dtype=torch.int32)
+    kps = (torch.rand(V, B, P, J, 2, dtype=torch.float64) * torch.tensor([4.0 * w, 4.0 * h]) * 1.2 - 8.0)
+    kps[:, 0, 1] = kps[:, 0, 0] + 0.5                       # two people on top of each other: the sum exceeds 1
+    kps.requires_grad_(True)
+    yy, xx = torch.meshgrid(torch.arange(h, dtype=torch.float64), torch.arange(w, dtype=torch.float64), indexing="ij")
+    k = kps / 4.0
+    g = torch.exp(-(((xx - k[..., 0, None, None]) / 3.0) ** 2) / 2 - (((yy - k[..., 1, None, None]) / 3.0) ** 2) / 2)
+    mask = (torch.arange(P)[None, :] < counts[:, None]).double()
+    want = torch.clip((g * mask[None, :, :, None, None, None]).sum(2), 0.0, 1.0)
+    G = torch.randn(V, B, J, h, w, dtype=torch.float64)
+    (want * G).sum().backward()
+    kd = kps.detach().float().to(DEV).requires_grad_(True)
+    got = ag.RenderGaussians.apply(kd, counts.to(DEV), (h, w), 0.25, 3.0)
+    (got * G.float().to(DEV)).sum().backward()
+    assert float((want >= 1).double().mean()) > 0.001
+    assert float((got.cpu().double() - want).abs().max()) <= 1e-5
+    ref = kps.grad * mask[None, :, :, None, None]
+    assert float((kd.grad.cpu().double() - ref).abs().max()) <= 1e-4 * float(ref.abs().max())

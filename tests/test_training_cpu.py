@@ -300,3 +300,41 @@ def apply_emulation_in_this_process():
     ag.Unproject, ag.SoftArgmax = _Apply(emul_unproject), _Apply(emul_softargmax)
     torch.Tensor.cuda = lambda self, *a, **k: self
     torch.Tensor.is_cuda = property(lambda self: True)
+
+
+def emul_render(kps, n_people, hw, inv_scale, sigma):
+    """sp3d_gauss_render_fwd (include/sp3d.h): clip(sum_{p < n[b]} exp(-((x - kx s)/sigma)^2/2 - ((y - ky s)/sigma)^2/2), 0, 1)."""
+    V, B, P, J, _ = kps.shape
+    yy, xx = torch.meshgrid(torch.arange(hw[0], dtype=torch.float32), torch.arange(hw[1], dtype=torch.float32), indexing="ij")
+    k = kps * inv_scale
+    g = torch.exp(-(((xx - k[..., 0, None, None]) / sigma) ** 2) / 2 - (((yy - k[..., 1, None, None]) / sigma) ** 2) / 2)
+    mask = (torch.arange(P)[None, :] < n_people[:, None]).float()                       # [B, P]
+    return torch.clip((g * mask[None, :, :, None, None, None]).sum(2), 0.0, 1.0)
+
+
+def test_render_kernel_wrapper_equals_the_tensor_expression(monkeypatch):
+    """The padded ``[V,B,P,J,2]`` wrapper around the rendering kernel (opt-in, SP3D_RENDER_KERNEL=1) against the
+    list-based tensor expression of ``_ssl_train.render_gaussians``, values and gradients, ragged people counts."""
+    from selfpose3d_b200.models import _ssl_train
+    monkeypatch.setattr(ag, "RenderGaussians", _Apply(emul_render))
+    torch.manual_seed(3)
+    V, B, J, h, w = 3, 3, 4, 12, 9
+    counts = [2, 0, 3]
+    base = [[(torch.rand(n, J, 2) * torch.tensor([4.0 * w, 4.0 * h])).requires_grad_(True) for n in counts] for _ in range(V)]
+    yy, xx = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+    xx, yy = xx.view(1, 1, h, w), yy.view(1, 1, h, w)
+    G = torch.randn(V, B, J, h, w)
+    want = _ssl_train.render_gaussians(base, xx, yy)
+    (want * G).sum().backward()
+    grads = [[kp.grad.clone() for kp in v] for v in base]
+    for v in base:
+        for kp in v:
+            kp.grad = None
+    monkeypatch.setenv("SP3D_RENDER_KERNEL", "1")
+    got = _ssl_train.render_gaussians(base, xx, yy)
+    (got * G).sum().backward()
+    assert torch.allclose(got, want, atol=1e-6)
+    for v in range(V):
+        for b in range(B):
+            if counts[b]:
+                assert torch.allclose(base[v][b].grad, grads[v][b], rtol=1e-4, atol=1e-7)
