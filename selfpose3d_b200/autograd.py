@@ -57,7 +57,9 @@ class Conv(Function):
         gy = gy.contiguous()
         gx = (grad_ops.conv_dgrad(ctx.pc, gy, out_pitch=int(x.shape[-1]), in_dims=tuple(x.shape[1:4]))
               if ctx.needs_input_grad[0] else None)
-        gw, gb = grad_ops.conv_wgrad(ctx.pc, x, gy, with_bias=ctx.has_bias)
+        gw = gb = None
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):     # (frozen layers: dgrad only)
+            gw, gb = grad_ops.conv_wgrad(ctx.pc, x, gy, with_bias=ctx.has_bias)
         return gx, gw, gb, None, None, None, None
 
 
