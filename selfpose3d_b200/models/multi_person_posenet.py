@@ -5,7 +5,9 @@ constructor, ``forward(views, meta, targets_2d, weights_2d, targets_3d, input_he
 6-tuple return ``(pred, all_heatmaps, grid_centers, loss_2d, loss_3d, loss_cord)`` (or
 ``(loss_2d, all_heatmaps)`` with ``TRAIN_ONLY_2D``).  Evaluation mode runs on the sm_100a kernels;
 the loss values are the reference's trivial MSE reductions evaluated with torch under ``no_grad``
-(SURVEY.md section 2.1 row 11).  Training mode (autograd) raises.
+(SURVEY.md section 2.1 row 11).  In ``.train()`` mode ``forward`` is the reference's supervised training step
+(``_forward_train`` below): the nets run their training paths (batch-statistics BatchNorm, gradients through the
+backward kernels).
 """
 from __future__ import annotations
 
