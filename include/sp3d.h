@@ -23,7 +23,8 @@
 extern "C" {
 #endif
 
-#define SP3D_ABI_VERSION 2   /* 2: sp3d_conv_args.split_terms, sp3d_split_bf16, the backward operators */
+#define SP3D_ABI_VERSION 3   /* 2: sp3d_conv_args.split_terms, sp3d_split_bf16, the backward operators;
+                                3: SP3D_BF16X2 activations, sp3d_merge_bf16, sp3d_s2d_args.dst_dtype, sp3d_gauss_render_* */
 #define SP3D_MAX_VIEWS 8
 #define SP3D_CAM_FLOATS 32
 
@@ -35,7 +36,12 @@ typedef enum {
   SP3D_ERR_WORKSPACE = -4
 } sp3d_status;
 
-typedef enum { SP3D_F32 = 0, SP3D_BF16 = 1, SP3D_F16 = 2 } sp3d_dtype;
+/* SP3D_BF16X2: a float32 tensor held as TWO bf16 term planes [2][...same shape...] (plane 0 = bf16(x), plane 1 =
+ * bf16(x - plane 0); x ~= plane 0 + plane 1 to 2^-17 relative) -- the activation format of the float32-faithful
+ * tensor-core mode: what sp3d_split_bf16 (S = 2) produces, what SP3D_CONV_TC_BF16X3 (split_terms = 3) reads, and what
+ * its epilogue, sp3d_maxpool_fwd, sp3d_unproject_fwd and sp3d_space_to_depth can write directly, so that no separate
+ * split pass runs between layers.  The pointer addresses plane 0; plane 1 follows the whole of plane 0. */
+typedef enum { SP3D_F32 = 0, SP3D_BF16 = 1, SP3D_F16 = 2, SP3D_BF16X2 = 3 } sp3d_dtype;
 
 /* ABI version of the loaded library and a static description of an error code. */
 int sp3d_abi_version(void);
@@ -185,7 +191,8 @@ typedef struct {
   int ostride[3], ooffset[3];
   int relu;                 /* 0: none; 1: ReLU after the residual add; 2: ReLU before the residual add */
   int algo;                 /* sp3d_conv_algo */
-  int in_dtype, out_dtype;  /* sp3d_dtype (SIMT path: F32 only) */
+  int in_dtype, out_dtype;  /* sp3d_dtype (SIMT path: F32 only).  SP3D_CONV_TC_BF16X3 also takes out_dtype = SP3D_BF16X2:
+                               out / residual are [2][N, TD, TH, TW, cout_pitch] bf16 term planes (cout_pitch % 8 == 0) */
   int fused_phases;         /* tensor-core path only.  1: kernel-2 stride-2 transposed 3-D convolution in ONE launch:
                                ksize = (1,1,1), ostride = (2,2,2), the packed weight has 8 * cout rows ordered
                                (px, py, pz, co), and out[2x+px, 2y+py, 2z+pz, co] is written for all 8 phases
@@ -229,7 +236,8 @@ typedef struct {
   int N, D, H, W, C, c_pitch;
   int OD, OH, OW;
   int k[3], s[3], p[3];
-  int dtype;
+  int dtype;                /* SP3D_F32, SP3D_BF16, or SP3D_BF16X2 (in = [2][N,D,H,W,c_pitch], out = [2][N,OD,OH,OW,c_pitch]:
+                               the maximum of plane 0 + plane 1, re-split) */
 } sp3d_maxpool_args;
 int sp3d_maxpool_fwd(const sp3d_maxpool_args* a, void* stream);
 
@@ -253,6 +261,8 @@ typedef struct {
   int64_t stride_n, stride_c, stride_y, stride_x; /* source strides in elements */
   int N, C, H, W;
   int dst_pitch;            /* >= 4 C, multiple of 8 */
+  int dst_dtype;            /* SP3D_BF16 (0 is read as SP3D_BF16), or SP3D_BF16X2 with a float32 source: dst is
+                               [2][N, H/2, W/2, dst_pitch] term planes */
 } sp3d_s2d_args;
 int sp3d_space_to_depth(const sp3d_s2d_args* a, void* stream);
 
@@ -267,6 +277,9 @@ typedef struct {
   int S;                    /* 2 or 3 planes */
 } sp3d_split_args;
 int sp3d_split_bf16(const sp3d_split_args* a, void* stream);
+/* The reverse for S = 2: dst[p, c] = plane0[p, c] + plane1[p, c] (float32, src_pitch = pitch of dst, c_block = pitch of
+ * the planes; `src` is the float32 destination, `dst` the bf16 planes -- the struct is shared with sp3d_split_bf16). */
+int sp3d_merge_bf16(const sp3d_split_args* a, void* stream);
 
 /* Stacks the x-neighbourhood of a 1-channel bf16 volume into channels:
  * dst[n, x, y, z, j] = src[n, x + j - pad, y, z, 0] (0 outside), j < taps; dst is [N, X, Y, Z, 16] bf16.

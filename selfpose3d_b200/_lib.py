@@ -11,10 +11,10 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsp3d.so")
 
-ABI_VERSION = 2      # SP3D_ABI_VERSION of include/sp3d.h these bindings were written against
+ABI_VERSION = 3      # SP3D_ABI_VERSION of include/sp3d.h these bindings were written against
 MAX_VIEWS = 8
 CAM_FLOATS = 32
-F32, BF16, F16 = 0, 1, 2
+F32, BF16, F16, BF16X2 = 0, 1, 2, 3
 CONV_SIMT_F32, CONV_TC_BF16, CONV_TC_BF16X3 = 0, 1, 2
 
 _i3 = C.c_int * 3
@@ -110,7 +110,7 @@ class S2DArgs(C.Structure):
     _fields_ = [
         ("src", C.c_void_p), ("dst", C.c_void_p), ("src_dtype", C.c_int),
         ("stride_n", C.c_int64), ("stride_c", C.c_int64), ("stride_y", C.c_int64), ("stride_x", C.c_int64),
-        ("N", C.c_int), ("C", C.c_int), ("H", C.c_int), ("W", C.c_int), ("dst_pitch", C.c_int),
+        ("N", C.c_int), ("C", C.c_int), ("H", C.c_int), ("W", C.c_int), ("dst_pitch", C.c_int), ("dst_dtype", C.c_int),
     ]
 
 
@@ -206,6 +206,7 @@ SYMBOLS = {
     "sp3d_space_to_depth": (C.c_int, [C.POINTER(S2DArgs), C.c_void_p]),
     "sp3d_stack_x_shifts": (C.c_int, [C.POINTER(StackArgs), C.c_void_p]),
     "sp3d_split_bf16": (C.c_int, [C.POINTER(SplitArgs), C.c_void_p]),
+    "sp3d_merge_bf16": (C.c_int, [C.POINTER(SplitArgs), C.c_void_p]),
     "sp3d_unproject_bwd": (C.c_int, [C.POINTER(UnprojectBwdArgs), C.c_void_p]),
     "sp3d_softargmax3d_bwd": (C.c_int, [C.POINTER(SoftargmaxBwdArgs), C.c_void_p]),
     "sp3d_maxpool_bwd": (C.c_int, [C.POINTER(MaxpoolBwdArgs), C.c_void_p]),
@@ -236,12 +237,14 @@ def load():
             "libsp3d.so not found at %s -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "or `make -C selfpose3d_b200/csrc`; there is no CPU or PyTorch fallback" % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
+    lib.sp3d_abi_version.restype = C.c_int
+    if lib.sp3d_abi_version() != ABI_VERSION:   # checked first: a stale library would otherwise fail on a missing symbol
+        raise Sp3dError("libsp3d.so ABI version mismatch (library %d, bindings %d): rebuild with `make -C "
+                        "selfpose3d_b200/csrc`" % (lib.sp3d_abi_version(), ABI_VERSION))
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.sp3d_abi_version() != ABI_VERSION:
-        raise Sp3dError("libsp3d.so ABI version mismatch")
     _lib = lib
     return lib
 

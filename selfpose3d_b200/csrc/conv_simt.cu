@@ -322,6 +322,61 @@ __global__ void maxpool_bf16_kernel(const sp3d_maxpool_args a) {
   }
 }
 
+// SP3D_BF16X2: float32 values as two bf16 term planes.  The maximum is taken over plane 0 + plane 1 (exact in float32:
+// the pair came from splitting a float32 value) and re-split, 8 channels per thread.
+__global__ void maxpool_pair_kernel(const sp3d_maxpool_args a) {
+  const int cvec = a.c_pitch / 8;
+  const int64_t total = (int64_t)a.N * a.OD * a.OH * a.OW * cvec;
+  const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(a.in);
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out);
+  const int64_t in_plane = (int64_t)a.N * a.D * a.H * a.W * a.c_pitch;
+  const int64_t out_plane = (int64_t)a.N * a.OD * a.OH * a.OW * a.c_pitch;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    int64_t pos = i / cvec;
+    const int ow = (int)(pos % a.OW); pos /= a.OW;
+    const int oh = (int)(pos % a.OH); pos /= a.OH;
+    const int od = (int)(pos % a.OD);
+    const int n = (int)(pos / a.OD);
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    for (int kd = 0; kd < a.k[0]; ++kd) {
+      const int id = od * a.s[0] - a.p[0] + kd;
+      if (id < 0 || id >= a.D) continue;
+      for (int kh = 0; kh < a.k[1]; ++kh) {
+        const int ih = oh * a.s[1] - a.p[1] + kh;
+        if (ih < 0 || ih >= a.H) continue;
+#pragma unroll 2
+        for (int kw = 0; kw < a.k[2]; ++kw) {
+          const int iw = ow * a.s[2] - a.p[2] + kw;
+          if (iw < 0 || iw >= a.W) continue;
+          const __nv_bfloat16* p = in + ((((int64_t)n * a.D + id) * a.H + ih) * a.W + iw) * a.c_pitch + cv * 8;
+          const uint4 qh = __ldg(reinterpret_cast<const uint4*>(p));
+          const uint4 ql = __ldg(reinterpret_cast<const uint4*>(p + in_plane));
+          const uint32_t h4[4] = {qh.x, qh.y, qh.z, qh.w}, l4[4] = {ql.x, ql.y, ql.z, ql.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            m[2 * j] = fmaxf(m[2 * j], __uint_as_float(h4[j] << 16) + __uint_as_float(l4[j] << 16));
+            m[2 * j + 1] = fmaxf(m[2 * j + 1], __uint_as_float(h4[j] & 0xffff0000u) + __uint_as_float(l4[j] & 0xffff0000u));
+          }
+        }
+      }
+    }
+    uint32_t w[4], u[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(m[2 * j], m[2 * j + 1]);
+      const __nv_bfloat162 l = __floats2bfloat162_rn(m[2 * j] - __low2float(h), m[2 * j + 1] - __high2float(h));
+      w[j] = *reinterpret_cast<const uint32_t*>(&h);
+      u[j] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    __nv_bfloat16* o = out + ((((int64_t)n * a.OD + od) * a.OH + oh) * a.OW + ow) * a.c_pitch + cv * 8;
+    *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(o + out_plane) = make_uint4(u[0], u[1], u[2], u[3]);
+  }
+}
+
 // bf16, window 2 stride 2 no padding (V2VNet's pools): the 8 taps are independent 16-byte loads issued together and
 // reduced with packed bf16x2 max
 __global__ void maxpool_bf16_k2s2_kernel(const sp3d_maxpool_args a) {
@@ -410,8 +465,10 @@ extern "C" int sp3d_maxpool_fwd(const sp3d_maxpool_args* a, void* stream) {
   using namespace sp3d;
   if (a == nullptr || a->in == nullptr || a->out == nullptr || a->N < 0 || a->C < 1 || a->c_pitch < a->C)
     return SP3D_ERR_INVALID_ARG;
-  if (a->dtype != SP3D_F32 && a->dtype != SP3D_BF16) return SP3D_ERR_UNSUPPORTED;
+  if (a->dtype != SP3D_F32 && a->dtype != SP3D_BF16 && a->dtype != SP3D_BF16X2) return SP3D_ERR_UNSUPPORTED;
   const int vec = a->dtype == SP3D_F32 ? 4 : 8;
+  if (a->dtype == SP3D_BF16X2 && ((reinterpret_cast<uintptr_t>(a->in) % 16) || (reinterpret_cast<uintptr_t>(a->out) % 16)))
+    return SP3D_ERR_INVALID_ARG;
   if ((a->c_pitch % vec) != 0) return SP3D_ERR_INVALID_ARG;
   const int64_t total = (int64_t)a->N * a->OD * a->OH * a->OW * (a->c_pitch / vec);
   if (total == 0) return SP3D_OK;
@@ -422,6 +479,7 @@ extern "C" int sp3d_maxpool_fwd(const sp3d_maxpool_args* a, void* stream) {
                     2 * a->OD <= a->D && 2 * a->OH <= a->H && 2 * a->OW <= a->W &&
                     (reinterpret_cast<uintptr_t>(a->in) % 16) == 0 && (reinterpret_cast<uintptr_t>(a->out) % 16) == 0;
   if (a->dtype == SP3D_F32) maxpool_f32_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
+  else if (a->dtype == SP3D_BF16X2) maxpool_pair_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
   else if (k2s2) maxpool_bf16_k2s2_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
   else maxpool_bf16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
   return check_launch();

@@ -26,6 +26,7 @@
 #include "tc_common.cuh"
 #include <cuda.h>
 #include <string.h>
+#include <type_traits>
 
 namespace sp3d {
 
@@ -48,6 +49,8 @@ __device__ __forceinline__ float ex2_sfu(float x) {
   return y;
 }
 
+struct SplitPair {};   // epilogue tag: float32 result stored as the bf16 pair (hi, lo), hi = bf16(r), lo = bf16(r - hi)
+
 struct alignas(64) TcStoreMaps {
   CUtensorMap m[4];              // [0] for a regular launch; one per (px, py) phase pair for the fused transposed form
 };
@@ -67,7 +70,8 @@ struct TcConvParams {
   int TD, TH, TW;                // full output tensor extent
   int ostride[3], ooff[3];       // output position = o * ostride + ooff (transposed-conv phases)
   int relu;
-  int out_f32;                   // 1: store float32, 0: bf16
+  int out_mode;                  // 0: store bf16, 1: float32, 2: float32 values as two bf16 term planes (SP3D_BF16X2:
+                                 //    plane t of cube n = outer index t * n_outer + n of the output / residual maps)
   const float* scale;
   const float* shift;
   const void* residual;          // same dtype / addressing as out
@@ -331,11 +335,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
     // A unit = one x-slice (128 positions) x one chunk of kStageRow bytes of channels; units walk a ring of SB slots.
     auto staged = [&](auto tag) {
       using T = decltype(tag);
-      constexpr int COLS = C::kStageRow / (int)sizeof(T);   // accumulator columns per unit
-      constexpr int CPU = 16 / (int)sizeof(T);              // columns per 16-byte smem unit
-      constexpr int UNITS = C::kStageRow / 16;
+      // split-pair output: a slot holds two half-width boxes (hi terms, then lo terms) of kStageRow / 2 bytes per row
+      constexpr bool kSplit = std::is_same<T, SplitPair>::value;
+      constexpr int ELT = kSplit ? 4 : (int)sizeof(T);      // staged bytes per accumulator column
+      constexpr int COLS = C::kStageRow / ELT;              // accumulator columns per unit
+      constexpr int CPU = kSplit ? 8 : 16 / ELT;            // columns per 16-byte smem unit (per box)
+      constexpr int BOXROW = kSplit ? C::kStageRow / 2 : C::kStageRow;   // bytes per row of one TMA box
+      constexpr int UNITS = BOXROW / 16;
       constexpr int NSC = N / COLS;                         // units per x-slice
-      constexpr uint32_t SWZ = C::kStageRow == 128 ? 7u : (C::kStageRow == 64 ? 3u : 1u);
+      constexpr uint32_t SWZ = BOXROW == 128 ? 7u : (BOXROW == 64 ? 3u : (BOXROW == 32 ? 1u : 0u));
+      constexpr int LO_OFF = C::kStageBytes / 2;            // split: byte offset of the lo box inside a slot
       const bool has_res = p.has_res != 0;
       const bool leader = row == 0;
       int pf_wi = wi_begin, pf_t = grp, pf_sc = 0;          // residual prefetch cursor (leader)
@@ -351,6 +360,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
           gc -= mi * p.fused_cols;
         }
         tma_load_5d(gstage + b * C::kStageBytes, &maps_res.m[mi], &gres_full[b], gc, z0, y0, x0 + pf_t, n);
+        if constexpr (kSplit)
+          tma_load_5d(gstage + b * C::kStageBytes + LO_OFF, &maps_res.m[mi], &gres_full[b], gc, z0, y0, x0 + pf_t,
+                      p.n_outer + n);
         ++pf_u;
         if (++pf_sc == NSC) {
           pf_sc = 0;
@@ -424,7 +436,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
             const uint32_t sbuf_s = smem_u32(sbuf);
 #pragma unroll
             for (int j = 0; j < UNITS; ++j) {
-              const uint32_t off = (uint32_t)row * C::kStageRow + j * 16;
+              const uint32_t off = (uint32_t)row * BOXROW + j * 16;
               const uint32_t q = sbuf_s + (off ^ (((off >> 7) & SWZ) << 4));
               const int col0 = sc * COLS + j * CPU;
               float r[CPU];
@@ -448,7 +460,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                 for (int i = 0; i < CPU; ++i) r[i] = fmaxf(r[i], 0.0f);
               }
               uint4 o;
-              if constexpr (sizeof(T) == 4) {
+              if constexpr (kSplit) {
+                if (has_res) {
+                  const uint4 rh = lds128(q), rl = lds128(q + LO_OFF);
+                  const uint32_t h4[4] = {rh.x, rh.y, rh.z, rh.w}, l4[4] = {rl.x, rl.y, rl.z, rl.w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    r[2 * i] += __uint_as_float(h4[i] << 16) + __uint_as_float(l4[i] << 16);
+                    r[2 * i + 1] += __uint_as_float(h4[i] & 0xffff0000u) + __uint_as_float(l4[i] & 0xffff0000u);
+                  }
+                }
+                if (p.relu == 1) {
+#pragma unroll
+                  for (int i = 0; i < CPU; ++i) r[i] = fmaxf(r[i], 0.0f);
+                }
+                uint32_t w4[4], u4[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const __nv_bfloat162 h = __floats2bfloat162_rn(r[2 * i], r[2 * i + 1]);
+                  // the remainder of a bf16 rounding is exact in float32
+                  const __nv_bfloat162 l = __floats2bfloat162_rn(r[2 * i] - __low2float(h), r[2 * i + 1] - __high2float(h));
+                  w4[i] = *reinterpret_cast<const uint32_t*>(&h);
+                  u4[i] = *reinterpret_cast<const uint32_t*>(&l);
+                }
+                o = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                sts128(q + LO_OFF, make_uint4(u4[0], u4[1], u4[2], u4[3]));
+              } else if constexpr (sizeof(T) == 4) {
                 if (has_res) {
                   const uint4 rv = lds128(q);
                   r[0] += __uint_as_float(rv.x); r[1] += __uint_as_float(rv.y);
@@ -498,6 +535,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                 gc -= mi * p.fused_cols;
               }
               tma_store_5d(&maps_out.m[mi], sbuf, gc, z0, y0, x0 + t, n);
+              if constexpr (kSplit) tma_store_5d(&maps_out.m[mi], sbuf + LO_OFF, gc, z0, y0, x0 + t, p.n_outer + n);
               bulk_commit();
               if (has_res) {
                 if (pf_wi < wi_end) {          // slot (u - 1) % SB: its store (unit u - 1) must have left smem
@@ -622,7 +660,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
       }
     }
     if (p.tma_store && !p.sa_ws) {
-      if (p.out_f32) staged(float{});
+      if (p.out_mode == 1) staged(float{});
+      else if (p.out_mode == 2) staged(SplitPair{});
       else staged(__nv_bfloat16{});
     }
     // ---- direct form (rows whose byte pitch is not a multiple of 16, e.g. the 1-channel float32 score volume)
@@ -671,7 +710,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
             if (p.relu == 2) r = fmaxf(r, 0.0f);
             f[j] = r;
           }
-          if (p.out_f32) {
+          if (p.out_mode == 1) {
             float* o = reinterpret_cast<float*>(p.out) + pos * p.cout_pitch + cbase;
             const float* rs = p.residual ? reinterpret_cast<const float*>(p.residual) + pos * p.cout_pitch + cbase : nullptr;
 #pragma unroll
@@ -757,7 +796,8 @@ static EncodeTiledFn get_encode() {
 }
 
 static CUtensorMapSwizzle swizzle_for(int rb) {
-  return rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  return rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                   : (rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (rb == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
 }
 
 template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB, int SB, int SR, int EG, int F>
@@ -785,12 +825,15 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
   TcStoreMaps maps_out, maps_res;
   memset(&maps_out, 0, sizeof(maps_out));
   memset(&maps_res, 0, sizeof(maps_res));
-  const int esz = a->out_dtype == SP3D_F32 ? 4 : 2;
+  const bool pair_out = a->out_dtype == SP3D_BF16X2;   // float32 results as two bf16 term planes [2][N, TD, TH, TW, pitch]
+  const int esz = a->out_dtype == SP3D_F32 ? 4 : 2;     // bytes per stored element
+  const int elt = pair_out ? 4 : esz;                   // staged bytes per accumulator column
   const bool fused = a->fused_phases != 0;
   const bool tma_store = ((int64_t)a->cout_pitch * esz) % 16 == 0 &&
                          (a->residual == nullptr || reinterpret_cast<uintptr_t>(a->residual) % 16 == 0);
   if (!tma_store && N != 16) return SP3D_ERR_UNSUPPORTED;   // the direct-store epilogue exists in the N = 16 kernels only
-  if (fused && (!tma_store || a->cout_pitch != a->cout || (2 * a->cout * esz) % 128 || (8 * a->cout) % N)) return SP3D_ERR_UNSUPPORTED;
+  if (fused && (!tma_store || a->cout_pitch != a->cout || (2 * a->cout * elt) % 128 || (8 * a->cout) % N)) return SP3D_ERR_UNSUPPORTED;
+  if (pair_out && !tma_store) return SP3D_ERR_UNSUPPORTED;
   if (tma_store) {
     // output / residual viewed through the launch's output stride and offset (transposed-convolution phases):
     // [N][OD][OH][OW][cout_pitch] with scaled strides; box = one x-slice of the brick x one staged channel chunk.
@@ -803,22 +846,23 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
       if ((int64_t)(og - 1) * a->ostride[d] + off >= full) return SP3D_ERR_INVALID_ARG;
     }
     cuuint64_t gdim[5] = {(cuuint64_t)(fused ? 2 * a->cout : a->cout_pitch * F), (cuuint64_t)a->OW / F, (cuuint64_t)a->OH,
-                          (cuuint64_t)a->OD, (cuuint64_t)a->N};
+                          (cuuint64_t)a->OD, (cuuint64_t)a->N * (pair_out ? 2 : 1)};
     cuuint64_t gstr[4] = {(cuuint64_t)(pe * a->ostride[2] * F), (cuuint64_t)(pe * a->TW * a->ostride[1]),
                           (cuuint64_t)(pe * a->TW * a->TH * a->ostride[0]), (cuuint64_t)(pe * a->TW * a->TH * a->TD)};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    cuuint32_t box[5] = {(cuuint32_t)(C::kStageRow / esz), (cuuint32_t)kBZ, (cuuint32_t)kBY, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)(C::kStageRow / elt), (cuuint32_t)kBZ, (cuuint32_t)kBY, 1, 1};
     const CUtensorMapDataType dt = esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const CUtensorMapSwizzle osw = swizzle_for(pair_out ? C::kStageRow / 2 : C::kStageRow);
     for (int mi = 0; mi < (fused ? 4 : 1); ++mi) {
       const int ox = fused ? (mi >> 1) : a->ooffset[0], oy = fused ? (mi & 1) : a->ooffset[1], oz = fused ? 0 : a->ooffset[2];
       const int64_t base_off = (((int64_t)ox * a->TH + oy) * a->TW + oz) * pe;
       if (encode(&maps_out.m[mi], dt, 5, static_cast<uint8_t*>(a->out) + base_off, gdim, gstr, box, es,
-                 CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(C::kStageRow), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, osw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return SP3D_ERR_INVALID_ARG;
       if (a->residual != nullptr &&
           encode(&maps_res.m[mi], dt, 5, const_cast<uint8_t*>(static_cast<const uint8_t*>(a->residual)) + base_off, gdim,
-                 gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(C::kStageRow),
+                 gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, osw,
                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return SP3D_ERR_INVALID_ARG;
     }
@@ -868,7 +912,7 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
   p.cout = a->cout; p.cout_pitch = a->cout_pitch;
   p.TD = a->TD; p.TH = a->TH; p.TW = a->TW;
   p.relu = a->relu;
-  p.out_f32 = a->out_dtype == SP3D_F32;
+  p.out_mode = a->out_dtype == SP3D_F32 ? 1 : (pair_out ? 2 : 0);
   p.scale = a->scale; p.shift = a->shift; p.residual = a->residual; p.out = a->out;
   p.prof = g_conv_prof;
   const sp3d_softargmax_args* head = a->head_softargmax;
@@ -929,7 +973,8 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
 int conv_tc(const sp3d_conv_args* a, cudaStream_t st) {
   if (a->algo != SP3D_CONV_TC_BF16 && a->algo != SP3D_CONV_TC_BF16X3) return SP3D_ERR_UNSUPPORTED;
   if (a->in_dtype != SP3D_BF16) return SP3D_ERR_UNSUPPORTED;
-  if (a->out_dtype != SP3D_BF16 && a->out_dtype != SP3D_F32) return SP3D_ERR_UNSUPPORTED;
+  if (a->out_dtype != SP3D_BF16 && a->out_dtype != SP3D_F32 && a->out_dtype != SP3D_BF16X2) return SP3D_ERR_UNSUPPORTED;
+  if (a->out_dtype == SP3D_BF16X2 && (a->head_softargmax != nullptr || (a->cout_pitch % 8))) return SP3D_ERR_UNSUPPORTED;
   if (a->fused_phases && (a->ksize[0] != 1 || a->ksize[1] != 1 || a->ksize[2] != 1 || a->ostride[0] != 2 ||
                           a->ostride[1] != 2 || a->ostride[2] != 2 || a->cout_pitch_w != 128))
     return SP3D_ERR_UNSUPPORTED;

@@ -14,7 +14,7 @@ template <>
 __device__ __forceinline__ float s2d_load<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
 // one thread per (output position, group of 8 output channels) -> one 16-byte store
-template <typename T>
+template <typename T, bool PAIR>
 __global__ void space_to_depth_kernel(const sp3d_s2d_args a) {
   const int groups = a.dst_pitch / 8;
   const int OH = a.H / 2, OW = a.W / 2;
@@ -25,7 +25,7 @@ __global__ void space_to_depth_kernel(const sp3d_s2d_args a) {
     const int64_t pos = i / groups;
     const int x = (int)(pos % OW), y = (int)((pos / OW) % OH);
     const int64_t n = pos / ((int64_t)OW * OH);
-    __align__(16) __nv_bfloat16 o[8];
+    __align__(16) __nv_bfloat16 o[8], lo[8];
     if (sizeof(T) == 2 && a.stride_c == 1 && (a.C % 8) == 0 && 8 * g < 4 * a.C) {
       // channel-last bf16 source: 8 consecutive channels of one source pixel = one 16-byte copy
       const int q = (8 * g) / a.C, c0 = (8 * g) % a.C;
@@ -42,10 +42,14 @@ __global__ void space_to_depth_kernel(const sp3d_s2d_args a) {
                           (int64_t)(2 * x + (q & 1)) * a.stride_x);
         }
         o[j] = __float2bfloat16_rn(v);
+        lo[j] = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(o[j])));
       }
     }
     *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.dst) + pos * a.dst_pitch + 8 * g) =
         *reinterpret_cast<const uint4*>(o);
+    if (PAIR)   // SP3D_BF16X2: second term plane
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.dst) + ((int64_t)a.N * OH * OW + pos) * a.dst_pitch + 8 * g) =
+          *reinterpret_cast<const uint4*>(lo);
   }
 }
 
@@ -106,7 +110,40 @@ __global__ void split_bf16_kernel(const sp3d_split_args a) {
   }
 }
 
+// bf16 term planes -> float32 (plane 0 + plane 1), 8 channels per thread
+__global__ void merge_bf16_kernel(const sp3d_split_args a) {
+  const int groups = a.c_block / 8;
+  const int64_t total = a.P * groups;
+  float* dst = const_cast<float*>(a.src);
+  const __nv_bfloat16* planes = reinterpret_cast<const __nv_bfloat16*>(a.dst);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const int64_t pos = i / groups;
+    const uint4 qh = __ldg(reinterpret_cast<const uint4*>(planes + pos * a.c_block + 8 * g));
+    const uint4 ql = __ldg(reinterpret_cast<const uint4*>(planes + (a.P + pos) * a.c_block + 8 * g));
+    const uint32_t h4[4] = {qh.x, qh.y, qh.z, qh.w}, l4[4] = {ql.x, ql.y, ql.z, ql.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t h = (j & 1) ? (h4[j >> 1] & 0xffff0000u) : (h4[j >> 1] << 16);
+      const uint32_t l = (j & 1) ? (l4[j >> 1] & 0xffff0000u) : (l4[j >> 1] << 16);
+      if (8 * g + j < a.src_pitch) dst[pos * a.src_pitch + 8 * g + j] = (8 * g + j < a.C) ? __uint_as_float(h) + __uint_as_float(l) : 0.0f;
+    }
+  }
+}
+
 }  // namespace sp3d
+
+extern "C" int sp3d_merge_bf16(const sp3d_split_args* a, void* stream) {
+  using namespace sp3d;
+  if (a == nullptr || a->src == nullptr || a->dst == nullptr || a->P < 0 || a->C < 1 || a->src_pitch < a->C ||
+      a->c_block < a->C || (a->c_block % 8) || (reinterpret_cast<uintptr_t>(a->dst) % 16) || a->S != 2)
+    return SP3D_ERR_INVALID_ARG;
+  const int64_t total = a->P * (a->c_block / 8);
+  if (total == 0) return SP3D_OK;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  merge_bf16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
+  return check_launch();
+}
 
 extern "C" int sp3d_split_bf16(const sp3d_split_args* a, void* stream) {
   using namespace sp3d;
@@ -146,14 +183,18 @@ extern "C" int sp3d_space_to_depth(const sp3d_s2d_args* a, void* stream) {
   if (total == 0) return SP3D_OK;
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool pair = a->dst_dtype == SP3D_BF16X2;
+  if (a->dst_dtype != 0 && a->dst_dtype != SP3D_BF16 && !pair) return SP3D_ERR_UNSUPPORTED;
+  if (pair && a->src_dtype != SP3D_F32) return SP3D_ERR_UNSUPPORTED;   // (bf16 term planes are re-arranged plane by plane)
   if (a->src_dtype == SP3D_F32) {
-    space_to_depth_kernel<float><<<blocks, 256, 0, st>>>(*a);
+    if (pair) space_to_depth_kernel<float, true><<<blocks, 256, 0, st>>>(*a);
+    else space_to_depth_kernel<float, false><<<blocks, 256, 0, st>>>(*a);
   } else {
     // the 16-byte copy path needs aligned source pixels
     if (a->stride_c == 1 && (a->C % 8) == 0 &&
         ((reinterpret_cast<uintptr_t>(a->src) % 16) || (a->stride_x % 8) || (a->stride_y % 8) || (a->stride_n % 8)))
       return SP3D_ERR_INVALID_ARG;
-    space_to_depth_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(*a);
+    space_to_depth_kernel<__nv_bfloat16, false><<<blocks, 256, 0, st>>>(*a);
   }
   return check_launch();
 }

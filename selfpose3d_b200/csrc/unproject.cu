@@ -25,8 +25,44 @@ __device__ __forceinline__ float to_out<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// Output element `i` of a voxel.  PAIR: the float32 value goes out as two bf16 terms (SP3D_BF16X2), hi = bf16(v) into
+// plane 0 and lo = bf16(v - hi) into plane 1 (`plane` elements further).
+template <typename OutT, bool PAIR>
+__device__ __forceinline__ void put(OutT* out, int64_t i, int64_t plane, float v) {
+  if (PAIR) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    reinterpret_cast<__nv_bfloat16*>(out)[i] = hi;
+    reinterpret_cast<__nv_bfloat16*>(out)[plane + i] = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(hi)));
+  } else {
+    out[i] = to_out<OutT>(v);
+  }
+}
+
+// Channel-last fast path: the kChanGroup = 16 values of one voxel as full 16-byte stores.
+__device__ __forceinline__ void store16(float* out, const float* r) {
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+}
+__device__ __forceinline__ void store16(__nv_bfloat16* out, const float* r) {
+  uint32_t w[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(r[2 * j], r[2 * j + 1]);
+    w[j] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(out) = make_uint4(w[0], w[1], w[2], w[3]);
+  *reinterpret_cast<uint4*>(out + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+}
+__device__ __forceinline__ void store16_pair(__nv_bfloat16* out, int64_t plane, const float* r) {
+  float lo[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) lo[j] = __fsub_rn(r[j], __bfloat162float(__float2bfloat16_rn(r[j])));
+  store16(out, r);
+  store16(out + plane, lo);
+}
+
 // HM_CL: heat-maps are channel-last (stride_c == 1) with 16-byte aligned pixels -> float4 taps.
-template <bool HM_CL, typename OutT>
+template <bool HM_CL, typename OutT, bool PAIR>
 __global__ void __launch_bounds__(kUnprojThreads) unproject_kernel(const sp3d_unproject_args a) {
   __shared__ float s_cam[SP3D_MAX_VIEWS * SP3D_CAM_FLOATS];
   __shared__ float s_center[4];
@@ -57,8 +93,12 @@ __global__ void __launch_bounds__(kUnprojThreads) unproject_kernel(const sp3d_un
   OutT* out = reinterpret_cast<OutT*>(a.cubes) + (int64_t)cube * a.out_stride_cube + (int64_t)vox * a.out_stride_vox;
   const int c_store = a.partial ? a.C + 1 : a.C;
   const int c_total = a.out_c_pad > c_store ? a.out_c_pad : c_store;
+  const int64_t plane = (int64_t)a.n_cubes * a.out_stride_cube;      // PAIR: distance between the two term planes
+  // channel-last voxels of exactly one channel group: one vectorised store of all 16 channels (padding included)
+  const bool vec16 = !a.partial && a.out_stride_c == 1 && c_total == kChanGroup && (a.out_stride_vox % kChanGroup) == 0 &&
+                     (a.out_stride_cube % 8) == 0 && (reinterpret_cast<uintptr_t>(a.cubes) % 16) == 0;
   if (skip) {
-    for (int c = 0; c < c_total; ++c) out[(int64_t)c * a.out_stride_c] = to_out<OutT>(0.0f);
+    for (int c = 0; c < c_total; ++c) put<OutT, PAIR>(out, (int64_t)c * a.out_stride_c, plane, 0.0f);
     return;
   }
   const float hm_w = (float)a.w, hm_h = (float)a.h;
@@ -108,21 +148,30 @@ __global__ void __launch_bounds__(kUnprojThreads) unproject_kernel(const sp3d_un
     if (a.partial) {
 #pragma unroll
       for (int j = 0; j < kChanGroup; ++j)
-        if (j < cn) out[(int64_t)(c0 + j) * a.out_stride_c] = to_out<OutT>(num[j]);
-      if (c0 + kChanGroup >= a.C) out[(int64_t)a.C * a.out_stride_c] = to_out<OutT>(den);
+        if (j < cn) put<OutT, PAIR>(out, (int64_t)(c0 + j) * a.out_stride_c, plane, num[j]);
+      if (c0 + kChanGroup >= a.C) put<OutT, PAIR>(out, (int64_t)a.C * a.out_stride_c, plane, den);
     } else {
       const float d = __fadd_rn(den, 1e-6f);
+      float r[kChanGroup];
 #pragma unroll
       for (int j = 0; j < kChanGroup; ++j) {
+        r[j] = 0.0f;
         if (j < cn) {
-          float r = __fdiv_rn(num[j], d);
-          r = (r != r) ? 0.0f : fminf(fmaxf(r, 0.0f), 1.0f);
-          out[(int64_t)(c0 + j) * a.out_stride_c] = to_out<OutT>(r);
+          const float q = __fdiv_rn(num[j], d);
+          r[j] = (q != q) ? 0.0f : fminf(fmaxf(q, 0.0f), 1.0f);
         }
       }
+      if (vec16) {
+        if (PAIR) store16_pair(reinterpret_cast<__nv_bfloat16*>(out), plane, r);
+        else store16(out, r);
+        return;
+      }
+#pragma unroll
+      for (int j = 0; j < kChanGroup; ++j)
+        if (j < cn) put<OutT, PAIR>(out, (int64_t)(c0 + j) * a.out_stride_c, plane, r[j]);
     }
   }
-  for (int c = c_store; c < c_total; ++c) out[(int64_t)c * a.out_stride_c] = to_out<OutT>(0.0f);
+  for (int c = c_store; c < c_total; ++c) put<OutT, PAIR>(out, (int64_t)c * a.out_stride_c, plane, 0.0f);
 }
 
 __global__ void unproject_finalize_kernel(const sp3d_unproject_finalize_args a) {
@@ -155,7 +204,8 @@ extern "C" int sp3d_unproject_fwd(const sp3d_unproject_args* a, void* stream) {
     return SP3D_ERR_INVALID_ARG;
   for (int v = a->view_begin; v < a->view_end; ++v)
     if (a->heatmaps[v] == nullptr) return SP3D_ERR_INVALID_ARG;
-  if (a->out_dtype != SP3D_F32 && a->out_dtype != SP3D_BF16) return SP3D_ERR_UNSUPPORTED;
+  if (a->out_dtype != SP3D_F32 && a->out_dtype != SP3D_BF16 && a->out_dtype != SP3D_BF16X2) return SP3D_ERR_UNSUPPORTED;
+  if (a->out_dtype == SP3D_BF16X2 && (a->math_mode != 0 || a->partial)) return SP3D_ERR_UNSUPPORTED;
   const int N = a->X * a->Y * a->Z;
   if (N <= 0 || a->n_cubes > 65535) return SP3D_ERR_INVALID_ARG;
   if (a->math_mode == 1) return unproject_fast(a, static_cast<cudaStream_t>(stream));
@@ -167,11 +217,14 @@ extern "C" int sp3d_unproject_fwd(const sp3d_unproject_args* a, void* stream) {
   dim3 grid(ceil_div(N, kUnprojThreads), a->n_cubes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (a->out_dtype == SP3D_F32) {
-    if (cl) unproject_kernel<true, float><<<grid, kUnprojThreads, 0, st>>>(*a);
-    else unproject_kernel<false, float><<<grid, kUnprojThreads, 0, st>>>(*a);
+    if (cl) unproject_kernel<true, float, false><<<grid, kUnprojThreads, 0, st>>>(*a);
+    else unproject_kernel<false, float, false><<<grid, kUnprojThreads, 0, st>>>(*a);
+  } else if (a->out_dtype == SP3D_BF16) {
+    if (cl) unproject_kernel<true, __nv_bfloat16, false><<<grid, kUnprojThreads, 0, st>>>(*a);
+    else unproject_kernel<false, __nv_bfloat16, false><<<grid, kUnprojThreads, 0, st>>>(*a);
   } else {
-    if (cl) unproject_kernel<true, __nv_bfloat16><<<grid, kUnprojThreads, 0, st>>>(*a);
-    else unproject_kernel<false, __nv_bfloat16><<<grid, kUnprojThreads, 0, st>>>(*a);
+    if (cl) unproject_kernel<true, __nv_bfloat16, true><<<grid, kUnprojThreads, 0, st>>>(*a);
+    else unproject_kernel<false, __nv_bfloat16, true><<<grid, kUnprojThreads, 0, st>>>(*a);
   }
   return check_launch();
 }

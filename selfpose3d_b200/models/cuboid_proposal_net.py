@@ -101,7 +101,7 @@ class CuboidProposalNet(nn.Module):
             return self.v2v_net.forward_cl(cubes)[..., 0].contiguous()
         bf16 = ops.volume_dtype() == torch.bfloat16
         cubes, _ = self.project_layer.project_cl(hms, cams, centers, False, self.grid_size, self.cube_size,
-                                                 dtype=ops.volume_dtype(),
+                                                 dtype="split" if ops.use_split() else ops.volume_dtype(),
                                                  c_pitch=ops.round_up(hms[0].shape[1], 16) if bf16 else None)
         root = self.v2v_net.forward_cl(cubes, out_pitch=1)
         return root.view(root.shape[0], root.shape[1], root.shape[2], root.shape[3])

@@ -66,7 +66,9 @@ class PoseRegressionNet(nn.Module):
             import os
             # bf16 activations of one 64^3 cube through V2VNet peak at ~0.2 GB (float32: ~0.4 GB)
             # (float32 activations on the split-operand tensor-core path: 40 cubes = ~20 GB incl. the bf16 term copies)
-            default = "80" if ops.volume_dtype() == torch.bfloat16 else ("16" if ops.float32_conv() == "simt" else "40")
+            # (term-pair activations of the 3-pair tensor-core mode: 2 x bf16 = ~0.4 GB per cube, 80 cubes = ~32 GB)
+            default = ("80" if ops.volume_dtype() == torch.bfloat16 or ops.use_split()
+                       else ("16" if ops.float32_conv() == "simt" else "40"))
             chunk = int(os.environ.get("SP3D_CUBE_CHUNK", default))
         out = torch.empty(n, J, 3, device=centers.device, dtype=torch.float32)
         X, Y, Z = [int(s) for s in self.cube_size]
@@ -80,7 +82,8 @@ class PoseRegressionNet(nn.Module):
             e = min(n, s + chunk)
             cubes, _ = self.project_layer.project_cl(all_heatmaps, cams, centers[s:e], False, self.grid_size,
                                                      self.cube_size, cube_sample=cube_sample[s:e],
-                                                     dtype=ops.volume_dtype(), c_pitch=ops.round_up(J, 16) if bf16 else None,
+                                                     dtype="split" if ops.use_split() else ops.volume_dtype(),
+                                                     c_pitch=ops.round_up(J, 16) if bf16 else None,
                                                      hms_f16=hms_f16)
             if bf16 and J <= 15 and max(X, Y, Z) <= 256:
                 # output layer + soft-argmax in one kernel (csrc/conv_tc.cu, fused head)

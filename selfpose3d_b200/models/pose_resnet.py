@@ -49,8 +49,11 @@ def _strided_conv_cl(pc, s2d, x):
     """``x``: channel-last ``[N,1,H,W,C]``.  bf16 activations with even extents take the space-to-depth tensor-core
     form of a stride-2 convolution; everything else the generic kernel."""
     N, _, H, W, C = [int(v) for v in x.shape]
-    if s2d is not None and x.dtype == torch.bfloat16 and H % 2 == 0 and W % 2 == 0 and C == s2d.cin:
-        return s2d(x, (H * W * C, 1, W * C, C), N, H, W)
+    if s2d is not None and H % 2 == 0 and W % 2 == 0 and C == s2d.cin:
+        if isinstance(x, ops.SplitAct):      # float32-faithful tensor-core mode
+            return s2d.call_split(x)
+        if x.dtype == torch.bfloat16:
+            return s2d(x, (H * W * C, 1, W * C, C), N, H, W)
     return pc(x)
 
 
@@ -193,14 +196,17 @@ class PoseResNet(nn.Module):
         # bf16 mode: the 7x7 stem reads the float32 image and writes bf16; from there on activations are bf16
         # (tcgen05 convolutions where the shape is covered) and the heat-maps leave the net in float32
         bf16 = ops.volume_dtype() == torch.bfloat16
-        if image is not None and bf16 and stem_s2d is not None and image.shape[2] % 2 == 0 and image.shape[3] % 2 == 0:
-            # straight from the NCHW float32 image: 2x2 space-to-depth (bf16) + 4x4 tensor-core convolution
+        split = ops.use_split()   # float32 values as bf16 term pairs from layer to layer (3-pair tensor-core mode)
+        if image is not None and (bf16 or split) and stem_s2d is not None and image.shape[2] % 2 == 0 and image.shape[3] % 2 == 0:
+            # straight from the NCHW float32 image: 2x2 space-to-depth (bf16 / term pairs) + 4x4 tensor-core convolution
             n, _, h, w = [int(v) for v in image.shape]
-            x = stem_s2d(image, image.stride(), n, h, w)
+            x = stem_s2d.call_split(image, image.stride(), n, h, w) if split else stem_s2d(image, image.stride(), n, h, w)
         else:
             if x is None:
                 x = ops.to_channel_last(image.unsqueeze(2), c_pitch=4)
             x = stem(x, out_dtype=torch.bfloat16 if bf16 else None)
+            if split:
+                x = ops.split_act(x, 64)
         x = ops.maxpool(x, 64, [1, 3, 3], [1, 2, 2], [0, 1, 1])
         for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
             for blk in layer:
@@ -233,6 +239,8 @@ class PoseResNet(nn.Module):
         y, feat = self.forward_cl(None, out_pitch=ops.round_up(self.num_joints, 4), image=x.float().contiguous())
         out = y[:, 0].permute(0, 3, 1, 2)[:, :self.num_joints]
         if attn:
+            if isinstance(feat, ops.SplitAct):
+                feat = ops.merge_act(feat, int(feat.shape[-1]))
             return out, feat[:, 0].permute(0, 3, 1, 2)[:, :feat.shape[-1]]
         return out
 

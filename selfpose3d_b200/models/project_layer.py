@@ -70,6 +70,16 @@ class ProjectLayer(nn.Module):
         n_cubes = int(centers.shape[0])
         pitch = ops.round_up(C, 4) if c_pitch is None else int(c_pitch)
         dev = hms[0].device
+        if dtype == "split":
+            # float32-faithful tensor-core mode: the float32 form of the kernel (bit-faithful geometry, float32 view
+            # accumulation) writes its result as the two bf16 term planes the convolutions read
+            pitch = ops.split_pitch(C) if c_pitch is None else int(c_pitch)
+            planes = torch.empty(2, n_cubes, X, Y, Z, pitch, device=dev, dtype=torch.bfloat16)
+            ops.unproject(hms, st, cams, centers, grid_size, (X, Y, Z), self.img_size, tuple(hms[0].shape[2:]), C,
+                          planes, (X * Y * Z * pitch, 1, pitch), out_c_pad=pitch, check_flag=check_flag,
+                          cubes_per_sample=cubes_per_sample, cube_sample=cube_sample,
+                          heatmap_cfg_wh=self.heatmap_size, pair_out=True)
+            return ops.SplitAct(planes), None
         cubes = torch.empty(n_cubes, X, Y, Z, pitch, device=dev, dtype=dtype)
         if dtype == torch.bfloat16 and pitch == 16 and 1 <= C <= 16 and not want_grids and Z <= 256:
             # throughput form (bf16 volume mode): fp16 channel-last maps, half2 tap blending

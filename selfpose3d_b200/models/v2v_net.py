@@ -28,14 +28,23 @@ def _to_volume_cl(x):
     """Channel-first float tensor -> channel-last activations in the configured volume dtype."""
     if ops.volume_dtype() == torch.bfloat16:
         return ops.to_channel_last(x.float(), c_pitch=ops.round_up(x.shape[1], 16), dtype=torch.bfloat16)
+    if ops.use_split():      # float32-faithful tensor-core mode: two bf16 term planes
+        return ops.split_act(ops.to_channel_last(x.float()), int(x.shape[1]))
     return ops.to_channel_last(x.float())
+
+
+def _to_channel_first(y, channels):
+    """Channel-last activations (float32 / bf16 tensor or ``SplitAct``) -> float32-or-bf16 ``[N,C,*spatial]``."""
+    if isinstance(y, ops.SplitAct):
+        y = ops.merge_act(y, channels)
+    return ops.to_channel_first(y, channels)
 
 
 def _forward_cf(module, x, out_channels):
     """The reference contract ``[N,C,X,Y,Z] -> [N,C',X,Y,Z]`` around a module's channel-last ``forward_cl``."""
     if module.training:
         return ag.ToChannelFirst.apply(module.forward_cl(ag.ToChannelLast.apply(x)), out_channels)
-    return ops.to_channel_first(module.forward_cl(_to_volume_cl(x)), out_channels)
+    return _to_channel_first(module.forward_cl(_to_volume_cl(x)), out_channels)
 
 
 def _no_train(module):
@@ -148,7 +157,7 @@ class Pool3DBlock(nn.Module):
         c = int(x.shape[1])
         if self.training:
             return ag.ToChannelFirst.apply(self.forward_cl(ag.ToChannelLast.apply(x), c), c)
-        return ops.to_channel_first(self.forward_cl(_to_volume_cl(x), c), c)
+        return _to_channel_first(self.forward_cl(_to_volume_cl(x), c), c)
 
 
 class Upsample3DBlock(nn.Module):

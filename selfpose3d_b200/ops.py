@@ -116,6 +116,12 @@ def float32_conv():
     return _F32_CONV
 
 
+def use_split():
+    """True in the float32-faithful tensor-core mode with 3 term pairs: evaluation-mode nets keep their activations as
+    ``SplitAct`` term pairs from layer to layer."""
+    return _VOLUME_DTYPE == torch.float32 and _F32_CONV == "bf16x3"
+
+
 def linspace_axes(grid_size, cube_size, device):
     """The three ``torch.linspace(-s/2, s/2, n)`` vectors of ``compute_grid``
     (``lib/models/project_layer.py:28-30``), evaluated once on the host and cached on ``device``."""
@@ -129,8 +135,9 @@ def linspace_axes(grid_size, cube_size, device):
 # --------------------------------------------------------------------------------------------- K1
 def unproject(heatmaps, hm_strides, cams, centers, grid_size, cube_size, image_size, heatmap_hw, channels,
               out, out_strides, out_c_pad=0, check_flag=False, cubes_per_sample=1, cube_sample=None,
-              grids=None, view_range=None, partial=False, heatmap_cfg_wh=None, fast=False):
-    """Launch the fused un-projection.  ``fast``: the throughput form (fp16 channel-last maps from
+              grids=None, view_range=None, partial=False, heatmap_cfg_wh=None, fast=False, pair_out=False):
+    """Launch the fused un-projection.  ``pair_out``: ``out`` is the two-plane bf16 tensor of a ``SplitAct``
+    (``[2, n_cubes, ...]``, strides of one plane): float32 results written as term pairs.  ``fast``: the throughput form (fp16 channel-last maps from
     ``heatmaps_to_f16``, bf16 channel-last cubes with pitch 16; see ``csrc/unproject_fast.cu``).
 
     heatmaps: list[V] of CUDA float32 tensors sharing ``hm_strides = (b, c, h, w)`` element strides.
@@ -140,6 +147,8 @@ def unproject(heatmaps, hm_strides, cams, centers, grid_size, cube_size, image_s
     a = unproject_args(heatmaps, hm_strides, cams, centers, grid_size, cube_size, image_size, heatmap_hw, channels,
                        out, out_strides, out_c_pad, check_flag, cubes_per_sample, cube_sample, grids, view_range,
                        partial, heatmap_cfg_wh, fast)
+    if pair_out:
+        a.out_dtype = _lib.BF16X2
     n_vox = a.X * a.Y * a.Z
     # SURVEY 8(d) algorithmic bytes: every float32 heat-map read once + every float32 cube written once (the bf16
     # volume mode physically moves half of the cube bytes; bench.py reports both)
@@ -311,14 +320,17 @@ def to_channel_first(x, channels, dtype=None):
     return dst
 
 
-def space_to_depth(x, channels, strides, n, h, w, dst_pitch):
+def space_to_depth(x, channels, strides, n, h, w, dst_pitch, pair=False):
     """``x`` addressed as ``[n, channels, h, w]`` through element ``strides = (n, c, y, x)`` (float32 or bf16) ->
-    channel-last bf16 ``[n, 1, h/2, w/2, dst_pitch]`` with channel ``(py*2+px)*channels + c``."""
+    channel-last bf16 ``[n, 1, h/2, w/2, dst_pitch]`` with channel ``(py*2+px)*channels + c``.  ``pair`` (float32
+    source): the result is the two-plane tensor ``[2, n, 1, h/2, w/2, dst_pitch]`` of a ``SplitAct``."""
     _require_cuda(x)
-    out = torch.empty(n, 1, h // 2, w // 2, dst_pitch, device=x.device, dtype=torch.bfloat16)
+    shape = (n, 1, h // 2, w // 2, dst_pitch)
+    out = torch.empty(((2,) + shape) if pair else shape, device=x.device, dtype=torch.bfloat16)
     a = _lib.S2DArgs()
     a.src, a.dst = x.data_ptr(), out.data_ptr()
     a.src_dtype = _DT[x.dtype]
+    a.dst_dtype = _lib.BF16X2 if pair else _lib.BF16
     a.stride_n, a.stride_c, a.stride_y, a.stride_x = [int(s) for s in strides]
     a.N, a.C, a.H, a.W, a.dst_pitch = int(n), int(channels), int(h), int(w), int(dst_pitch)
     _lib.call("sp3d_space_to_depth", a, _stream(), kind="layout",
@@ -363,6 +375,50 @@ def bf16_terms(w, n):
         terms.append(t)
         rest = rest - t
     return terms
+
+
+class SplitAct:
+    """float32 channel-last activations held as TWO bf16 term planes (``SP3D_BF16X2`` of include/sp3d.h):
+    ``planes [2, N, D, H, W, pitch]`` with ``x ~= planes[0] + planes[1]``.  This is what the float32-faithful
+    tensor-core convolutions read; their epilogue, the max-pool, the un-projection and the space-to-depth kernel write
+    it directly, so no separate split pass runs between the layers of a net."""
+    __slots__ = ("planes",)
+
+    def __init__(self, planes):
+        if planes.dtype != torch.bfloat16 or planes.dim() != 6 or planes.shape[0] != 2 or not planes.is_contiguous():
+            raise _lib.Sp3dError("SplitAct expects a contiguous bf16 [2, N, D, H, W, pitch] tensor")
+        self.planes = planes
+
+    @property
+    def shape(self):
+        return self.planes.shape[1:]
+
+    @property
+    def device(self):
+        return self.planes.device
+
+
+def split_pitch(channels):
+    """Channel pitch of a ``SplitAct`` with ``channels`` channels = the K extent the consuming convolution is packed for."""
+    return round_up(channels, 16) if channels < 64 else round_up(channels, 64)
+
+
+def split_act(x, channels, pitch=None):
+    """float32 channel-last ``[N,D,H,W,p]`` -> ``SplitAct`` (one ``sp3d_split_bf16`` pass)."""
+    return SplitAct(split_bf16(x, channels, split_pitch(channels) if pitch is None else int(pitch), 2))
+
+
+def merge_act(x, channels, pitch=None):
+    """``SplitAct`` -> float32 channel-last ``[N,D,H,W,pitch]`` (``sp3d_merge_bf16``; padding channels zero)."""
+    planes = x.planes
+    pitch = round_up(channels, 4) if pitch is None else int(pitch)
+    out = torch.empty(tuple(planes.shape[1:-1]) + (pitch,), device=planes.device, dtype=torch.float32)
+    a = _lib.SplitArgs()
+    a.src, a.dst = out.data_ptr(), planes.data_ptr()
+    a.P = planes[0].numel() // int(planes.shape[-1])
+    a.C, a.src_pitch, a.c_block, a.S = int(channels), pitch, int(planes.shape[-1]), 2
+    _lib.call("sp3d_merge_bf16", a, _stream(), kind="layout", work=a.P * int(channels) * 8)
+    return out
 
 
 # (activation term, weight term) per K block of the split-operand convolution (include/sp3d.h, split_terms): the
@@ -422,6 +478,8 @@ class S2DConv:
         taps = self.kp * self.kp
         full = w2.reshape(taps, n_tiles, self.n, self.cin_tc // chunk, chunk).permute(1, 3, 0, 2, 4)
         self.weight = full.to(torch.bfloat16).contiguous()
+        self._full = full
+        self._weight3 = None
         inv = torch.rsqrt(bn.running_var.detach().float() + bn.eps)
         self.scale = (bn.weight.detach().float() * inv).contiguous()
         self.shift = (bn.bias.detach().float() - bn.running_mean.detach().float() * self.scale).contiguous()
@@ -445,6 +503,25 @@ class S2DConv:
                     cin_real=self.cin * 4, cout_pitch_w=self.n)
         return out
 
+    def call_split(self, x, strides=None, n=None, h=None, w=None):
+        """Float32-faithful form (``SP3D_CONV_TC_BF16X3``, 3 term pairs): ``x`` is a ``SplitAct`` ``[2,n,1,h,w,cin]``, or
+        a float32 tensor addressed as ``[n, cin, h, w]`` through ``strides`` (the NCHW image).  Returns a ``SplitAct``."""
+        if isinstance(x, SplitAct):
+            _, n, _, h, w, c = [int(v) for v in x.planes.shape]
+            xs = space_to_depth(x.planes, self.cin, (h * w * c, 1, w * c, c), 2 * n, h, w, self.cin_tc)   # plane by plane
+        else:
+            xs = space_to_depth(x, self.cin, strides, n, h, w, self.cin_tc, pair=True)
+        if self._weight3 is None:
+            self._weight3 = _tc_finish(self._full, 3)
+        oh, ow = h // 2, w // 2
+        pitch = split_pitch(self.cout)
+        out = torch.empty(2, n, 1, oh, ow, pitch, device=xs.device, dtype=torch.bfloat16)
+        conv_launch(xs.view(2, 1, n, oh, ow, self.cin_tc)[0], self._weight3, self.scale, self.shift, None,
+                    out.view(2, 1, n, oh, ow, pitch)[0], self.cin_tc, self.cout, (n, oh, ow), [1, self.kp, self.kp],
+                    [1, 1, 1], [0, self.dmin, self.dmin], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu, _lib.CONV_TC_BF16X3,
+                    cin_real=self.cin * 4, cout_pitch_w=self.n, split_terms=3, pair_out=True)
+        return SplitAct(out)
+
 
 # --------------------------------------------------------------------------------------------- conv family
 def _set3(field, vals):
@@ -454,8 +531,9 @@ def _set3(field, vals):
 
 def conv_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksize, stride, tap_off0, tap_step,
                 ostride, ooffset, relu, algo=_lib.CONV_SIMT_F32, cin_real=None, cout_pitch_w=None, fused_phases=False,
-                zfold=0, head=None, split_terms=0):
+                zfold=0, head=None, split_terms=0, pair_out=False):
     """One implicit-GEMM convolution launch.  ``x`` / ``out`` are channel-last 5-D ``[N,D,H,W,pitch]``.
+    ``pair_out``: ``out`` (and ``residual``) are plane 0 of two-plane bf16 tensors (``SplitAct.planes[0]`` views).
     ``head``: a ``SoftargmaxHead`` -- the output is consumed on chip by the fused soft-argmax (``out`` is then a
     shape-only placeholder: a ``torch.Size``-like tuple ``(N, D, H, W, pitch)``)."""
     if head is not None:
@@ -465,7 +543,7 @@ def conv_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksi
     # pointers change between calls (filling ~40 ctypes fields costs more host time than a small kernel runs)
     key = (weight.data_ptr(), tuple(x.shape), x.dtype, tuple(out.shape), out.dtype, residual is not None,
            tuple(out_grid), tuple(tap_off0), tuple(ostride), tuple(ooffset), int(algo), bool(fused_phases), int(zfold),
-           int(split_terms))
+           int(split_terms), bool(pair_out))
     hit = _CONV_ARGS_CACHE.get(key)
     if hit is None:
         a = _lib.ConvArgs()
@@ -488,7 +566,7 @@ def conv_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksi
         _set3(a.ooffset, ooffset)
         a.relu = int(relu)
         a.algo = int(algo)
-        a.in_dtype, a.out_dtype = _DT[x.dtype], _DT[out.dtype]
+        a.in_dtype, a.out_dtype = _DT[x.dtype], (_lib.BF16X2 if pair_out else _DT[out.dtype])
         a.fused_phases = int(bool(fused_phases))
         a.zfold = int(zfold)
         a.split_terms = int(split_terms)
@@ -575,12 +653,18 @@ def _conv_launch_head(x, weight, scale, shift, out_shape, cin, cout, out_grid, k
 
 
 def maxpool(x, channels, k, s, p):
-    """Channel-last ``[N,D,H,W,pitch]`` max pooling; returns the pooled channel-last tensor."""
+    """Channel-last ``[N,D,H,W,pitch]`` max pooling; returns the pooled channel-last tensor (a ``SplitAct`` for a
+    ``SplitAct``: the maximum of the float32 values the term pairs stand for, re-split)."""
+    pair = isinstance(x, SplitAct)
+    if pair:
+        x = x.planes
+        N, D, H, W, pitch = [int(v) for v in x.shape[1:]]
+    else:
+        N, D, H, W, pitch = [int(v) for v in x.shape]
     _require_cuda(x)
-    N, D, H, W, pitch = [int(v) for v in x.shape]
     dims = (D, H, W)
     o = [(dims[i] + 2 * p[i] - k[i]) // s[i] + 1 for i in range(3)]
-    out = torch.empty((N, o[0], o[1], o[2], pitch), device=x.device, dtype=x.dtype)
+    out = torch.empty(((2,) if pair else ()) + (N, o[0], o[1], o[2], pitch), device=x.device, dtype=x.dtype)
     a = _lib.MaxpoolArgs()
     a.in_, a.out = x.data_ptr(), out.data_ptr()
     a.N, a.D, a.H, a.W, a.C, a.c_pitch = N, D, H, W, int(channels), pitch
@@ -588,10 +672,10 @@ def maxpool(x, channels, k, s, p):
     _set3(a.k, k)
     _set3(a.s, s)
     _set3(a.p, p)
-    a.dtype = _DT[x.dtype]
+    a.dtype = _lib.BF16X2 if pair else _DT[x.dtype]
     _lib.call("sp3d_maxpool_fwd", a, _stream(), kind="maxpool",
-              work=(N * D * H * W + N * o[0] * o[1] * o[2]) * int(channels) * x.element_size())
-    return out
+              work=(N * D * H * W + N * o[0] * o[1] * o[2]) * int(channels) * x.element_size() * (2 if pair else 1))
+    return SplitAct(out) if pair else out
 
 
 class PackedConv:
@@ -769,7 +853,7 @@ class PackedConv:
 
     def _tc_fused_ok(self, out_pitch, out_dtype):
         """k2/s2 transposed 3-D convolution as ONE launch (all 8 output phases are extra GEMM columns)."""
-        esz = 4 if out_dtype == torch.float32 else 2
+        esz = 2 if out_dtype == torch.bfloat16 else 4      # staged bytes per value (float32, or a bf16 term pair)
         return (self.transposed and self.nd == 3 and self.k == [2, 2, 2] and (8 * self.cout) % 128 == 0
                 and out_pitch == self.cout and (2 * self.cout * esz) % 128 == 0)
 
@@ -803,27 +887,39 @@ class PackedConv:
         """``tc_supported()`` and every launch of the plan has a compiled kernel instantiation."""
         return self.tc_supported() and all(c in TC_CASES for c in self.tc_plan(w_extent, out_pitch, out_dtype, with_residual))
 
-    def _call_tc(self, x, residual, out_pitch, out_dtype, head=None, terms=0):
+    def _call_tc(self, x, residual, out_pitch, out_dtype, head=None, terms=0, pair_out=False):
         """tcgen05 path.  ``terms`` = 0: ``x`` is bf16 channel-last.  ``terms`` = 3 / 6 (SP3D_CONV_TC_BF16X3): ``x`` is
-        float32 channel-last; it is expanded into bf16 term planes (``split_bf16``) that the kernel multiplies with the
-        matching weight terms as extra K blocks of the same implicit GEMM; output and residual are float32."""
+        float32 channel-last (expanded into bf16 term planes by ``split_bf16`` first) or, ``terms`` = 3, a ``SplitAct``
+        (already two term planes); the kernel multiplies the planes with the matching weight terms as extra K blocks of
+        the same implicit GEMM.  Output and residual are float32, or ``SplitAct`` with ``pair_out`` (the epilogue writes
+        the two term planes of its float32 result: no split pass in front of the next layer)."""
         if not self.tc_supported():
             raise _lib.Sp3dError("convolution shape not covered by the tensor-core path")
         packs, n, cin_tc = self._tc_pack(terms)
+        pre_split = isinstance(x, SplitAct)
         N, D, H, W, pitch = [int(v) for v in x.shape]
         o = self.out_shape((D, H, W))
         if terms:
-            if head is not None or out_dtype not in (None, torch.float32) or x.dtype != torch.float32:
+            if head is not None or out_dtype not in (None, torch.float32) or (not pre_split and x.dtype != torch.float32):
                 raise _lib.Sp3dError("the split-operand mode takes float32 activations, writes float32 and has no fused head")
+            if pre_split and (terms != 3 or pitch != cin_tc):
+                raise _lib.Sp3dError("a SplitAct input needs the 3-pair mode and pitch %d (got %d)" % (cin_tc, pitch))
             if pitch < self.cin:
                 raise _lib.Sp3dError("activation pitch %d smaller than the input channel count %d" % (pitch, self.cin))
             out_dtype = torch.float32
-            out_pitch = round_up(self.cout, 4) if out_pitch is None else int(out_pitch)
             planes = 2 if terms == 3 else 3
-            x = split_bf16(x, self.cin, cin_tc, planes)          # [planes, N, D, H, W, cin_tc]
+            x = x.planes if pre_split else split_bf16(x, self.cin, cin_tc, planes)   # [planes, N, D, H, W, cin_tc]
             pitch = cin_tc
             algo = _lib.CONV_TC_BF16X3
+            if pair_out:
+                if terms != 3:
+                    raise _lib.Sp3dError("term-pair output exists in the 3-pair mode only")
+                out_pitch = split_pitch(self.cout) if out_pitch is None else int(out_pitch)
+            else:
+                out_pitch = round_up(self.cout, 4) if out_pitch is None else int(out_pitch)
         else:
+            if pair_out:
+                raise _lib.Sp3dError("term-pair output needs the split-operand mode")
             if pitch < cin_tc or pitch % 8:
                 raise _lib.Sp3dError("bf16 activation pitch %d incompatible with packed cin %d" % (pitch, cin_tc))
             out_dtype = torch.bfloat16 if out_dtype is None else out_dtype
@@ -836,20 +932,35 @@ class PackedConv:
             return conv_launch(x, packs[0], self.scale, self.shift, None, (N, o[0], o[1], o[2], 16), cin_tc, self.cout, o,
                                self.k, self.stride, [0, 0, 0], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu,
                                _lib.CONV_TC_BF16, cin_real=self.cin, cout_pitch_w=n, head=head)
-        out = torch.empty((N, o[0], o[1], o[2], out_pitch), device=x.device, dtype=out_dtype)
-        if residual is not None and (residual.dtype != out_dtype or residual.shape != out.shape):
-            raise _lib.Sp3dError("residual must match the output dtype and shape")
+        oshape = (N, o[0], o[1], o[2], out_pitch)
+        if pair_out:
+            out_full = torch.empty((2,) + oshape, device=x.device, dtype=torch.bfloat16)
+            out = out_full[0]
+            if residual is not None:
+                if not isinstance(residual, SplitAct) or tuple(residual.planes.shape) != tuple(out_full.shape):
+                    raise _lib.Sp3dError("residual must be a SplitAct of the output's shape")
+                residual = residual.planes[0]
+        else:
+            out = torch.empty(oshape, device=x.device, dtype=out_dtype)
+            if residual is not None and (isinstance(residual, SplitAct) or residual.dtype != out_dtype
+                                         or residual.shape != out.shape):
+                raise _lib.Sp3dError("residual must match the output dtype and shape")
         # kernel view of the activations: [N, D, H, W, pitch] (split mode: plane 0; the kernel steps over the planes
         # through the outer index).  2-D: image batch -> the brick's x axis, [N,1,H,W,C] viewed as [1,N,H,W,C]
+        # (a term-pair output / residual is passed as its plane 0: plane 1 follows at the outer index n_outer + n)
         outk, resk = out, residual
         if self.nd == 2:
             xk = x.view(planes, 1, N, H, W, pitch)[0] if planes else x.view(1, N, H, W, pitch)
-            outk = out.view(1, N, o[1], o[2], out_pitch)
-            resk = residual.view(1, N, o[1], o[2], out_pitch) if residual is not None else None
+            if pair_out:
+                outk = out_full.view(2, 1, N, o[1], o[2], out_pitch)[0]
+                resk = residual.view(1, N, o[1], o[2], out_pitch) if residual is not None else None
+            else:
+                outk = out.view(1, N, o[1], o[2], out_pitch)
+                resk = residual.view(1, N, o[1], o[2], out_pitch) if residual is not None else None
             D, o = N, [N, o[1], o[2]]
         else:
             xk = x[0] if planes else x
-        kw = dict(algo=algo, split_terms=terms)
+        kw = dict(algo=algo, split_terms=terms, pair_out=pair_out)
         if pitch == 16 and residual is None and self._tc_stack_ok(W, out_pitch):
             xs = stack_x_shifts(x.view(-1, D, H, W, pitch), 7, 3)       # every plane: [planes * N, ...]
             conv_launch(xs[:N], self._tc_pack_stack(terms), self.scale, self.shift, None, outk, 16, self.cout, o, [1, 7, 7],
@@ -863,7 +974,7 @@ class PackedConv:
             conv_launch(xk, packs[0], self.scale, self.shift, resk, outk, cin_tc, self.cout, o, self.k, self.stride,
                         [-p for p in self.padding], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu,
                         cin_real=self.cin, cout_pitch_w=n, **kw)
-        elif self._tc_fused_ok(out_pitch, out_dtype):
+        elif self._tc_fused_ok(out_pitch, "pair" if pair_out else out_dtype):
             conv_launch(xk, self._tc_pack_fused(terms), self.scale, self.shift, resk, outk, cin_tc, self.cout, (D, H, W),
                         [1, 1, 1], [1, 1, 1], [0, 0, 0], [1, 1, 1], self.stride, [0, 0, 0], self.relu, cin_real=self.cin,
                         cout_pitch_w=128, fused_phases=True, **kw)
@@ -872,7 +983,25 @@ class PackedConv:
                 origin = [off0[i] - (ks[i] - 1) for i in range(3)]     # taps ascend from the lowest input offset
                 conv_launch(xk, wgt, self.scale, self.shift, resk, outk, cin_tc, self.cout, (D, H, W), ks, [1, 1, 1],
                             origin, [1, 1, 1], self.stride, phase, self.relu, cin_real=self.cin, cout_pitch_w=n, **kw)
-        return out
+        return SplitAct(out_full) if pair_out else out
+
+    def _call_split(self, x, residual, out_pitch, out_dtype, head, out_dims):
+        """``x``: ``SplitAct``.  Covered shapes run the 3-pair tensor-core form and return a ``SplitAct`` (float32 with
+        ``out_dtype=torch.float32``); anything else goes through the float32 kernel and is re-split."""
+        if head is not None or out_dims is not None or out_dtype not in (None, torch.float32):
+            raise _lib.Sp3dError("a SplitAct input takes out_dtype None (SplitAct) or torch.float32 only")
+        pair_out = out_dtype is None
+        w_extent = int(x.shape[3])
+        pitch_eff = (split_pitch(self.cout) if pair_out else round_up(self.cout, 4)) if out_pitch is None else int(out_pitch)
+        if int(x.shape[4]) == self._tc_dims()[1] and self.tc_available(w_extent, pitch_eff, "pair" if pair_out else torch.float32,
+                                                                      residual is not None):
+            return self._call_tc(x, residual, out_pitch, None, terms=3, pair_out=pair_out)
+        xf = merge_act(x, self.cin)
+        rf = None
+        if residual is not None:
+            rf = merge_act(residual, self.cout) if isinstance(residual, SplitAct) else residual
+        y = self.__call__(xf, residual=rf, algo=_lib.CONV_SIMT_F32)
+        return split_act(y, self.cout, out_pitch) if pair_out else y
 
     def __call__(self, x, residual=None, out_pitch=None, algo=None, out_dtype=None, head=None, out_dims=None):
         """``x``: channel-last ``[N,D,H,W,pitch]``.  float32 activations take the float32 SIMT kernel; bf16
@@ -880,6 +1009,8 @@ class PackedConv:
         result), else the SIMT kernel with bf16 storage and float32 math.  ``out_dims``: explicit output extent of a
         transposed convolution (``output_padding``; SIMT path) -- how the input gradient of a strided convolution
         recovers the forward input's extent."""
+        if isinstance(x, SplitAct):
+            return self._call_split(x, residual, out_pitch, out_dtype, head, out_dims)
         if algo is None:
             if x.dtype == torch.bfloat16 and self.tc_supported():
                 algo = _lib.CONV_TC_BF16

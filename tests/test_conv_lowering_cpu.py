@@ -130,7 +130,7 @@ def test_output_pitch_one_and_padding_lanes_zero():
 # ---------------------------------------------------------------------------------------------- tcgen05 packing
 def emulate_any_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksize, stride, tap_off0,
                        tap_step, ostride, ooffset, relu, algo=0, cin_real=None, cout_pitch_w=None, fused_phases=False,
-                       zfold=0, split_terms=0):
+                       zfold=0, split_terms=0, pair_out=False):
     """Dispatch on the packing: the tensor-core launch carries [n_tiles, n_chunks, taps, N, chunk] bf16 weights;
     `fused_phases` and `zfold` follow the sp3d_conv_args field descriptions in include/sp3d.h."""
     res = None if residual is None else residual.float()
@@ -285,20 +285,36 @@ def emulate_split_bf16(x, channels, c_block, blocks):
 
 def emulate_split_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksize, stride, tap_off0,
                          tap_step, ostride, ooffset, relu, algo=0, cin_real=None, cout_pitch_w=None,
-                         fused_phases=False, zfold=0, split_terms=0):
+                         fused_phases=False, zfold=0, split_terms=0, pair_out=False):
     """SP3D_CONV_TC_BF16X3 (include/sp3d.h, split_terms): `x` is plane 0 of the term planes [S][N,D,H,W,cin]; K block
     b multiplies activation plane SPLIT_PAIRS[b][0] with weight block b, all blocks accumulate into one GEMM -- i.e.
-    the plain tensor-core launch on the K-concatenated operands."""
+    the plain tensor-core launch on the K-concatenated operands.  `pair_out` (out_dtype SP3D_BF16X2): `out` and
+    `residual` are plane 0 of two-plane bf16 tensors holding float32 values as term pairs."""
     assert algo == 2 and split_terms in (3, 6)
     pairs = ops.SPLIT_PAIRS[split_terms]
     nt, kb, nc, taps, n, chunk = weight.shape
     assert kb == len(pairs) and cin == nc * chunk and x.shape[-1] == cin
-    planes = torch.as_strided(x, (max(a for a, _ in pairs) + 1,) + tuple(x.shape), (x.numel(),) + tuple(x.stride()),
-                              x.storage_offset())
+
+    def planes_of(t, count):
+        return torch.as_strided(t, (count,) + tuple(t.shape), (t.numel(),) + tuple(t.stride()), t.storage_offset())
+
+    planes = planes_of(x, max(a for a, _ in pairs) + 1)
     xcat = torch.cat([planes[a] for a, _ in pairs], -1)
-    emulate_any_launch(xcat, weight.reshape(nt, kb * nc, taps, n, chunk), scale, shift, residual, out, kb * cin, cout,
+    target = out
+    if pair_out:
+        assert split_terms == 3 and out.dtype == torch.bfloat16 and out.is_contiguous()
+        out_planes = planes_of(out, 2)
+        target = out_planes[0].float() + out_planes[1].float()      # other phases' results stay what they are
+        if residual is not None:
+            rp = planes_of(residual, 2)
+            residual = rp[0].float() + rp[1].float()
+    emulate_any_launch(xcat, weight.reshape(nt, kb * nc, taps, n, chunk), scale, shift, residual, target, kb * cin, cout,
                        out_grid, ksize, stride, tap_off0, tap_step, ostride, ooffset, relu, algo=1,
                        cout_pitch_w=cout_pitch_w, fused_phases=fused_phases, zfold=zfold)
+    if pair_out:
+        hi, lo = ops.bf16_terms(target, 2)
+        out_planes[0].copy_(hi)
+        out_planes[1].copy_(lo)
 
 
 def emulate_stack_planes(x, taps, pad):
@@ -407,7 +423,8 @@ def test_tc_plan_predicts_the_launches(monkeypatch):
     seen = []
 
     def record(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksize, stride, tap_off0, tap_step, ostride,
-               ooffset, relu, algo=0, cin_real=None, cout_pitch_w=None, fused_phases=False, zfold=0, split_terms=0):
+               ooffset, relu, algo=0, cin_real=None, cout_pitch_w=None, fused_phases=False, zfold=0, split_terms=0,
+               pair_out=False):
         seen.append(ops.tc_case(ksize, cin, cout_pitch_w, zfold))
 
     monkeypatch.setattr(ops, "conv_launch", record)
