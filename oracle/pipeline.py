@@ -26,33 +26,36 @@ def _cam_at(cam_arrays, c, i):
 
 
 def unproject_torch(heatmaps, cam_arrays, centers, scales, rotations, image_size, heatmap_size,
-                    grid_size, grid_center, cube_size, flip=None):
-    """project_layer.py:42-102 with torch CPU ops.  ``heatmaps`` list[V] of ``[B,C,h,w]``."""
+                    grid_size, grid_center, cube_size, flip=None, dtype=torch.float32):
+    """project_layer.py:42-102 with torch CPU ops.  ``heatmaps`` list[V] of ``[B,C,h,w]``.  ``dtype`` float64: the same
+    operations in double precision (the "truth" used to budget tolerances; the reference itself is float32)."""
     V = len(heatmaps)
     B, C = heatmaps[0].shape[:2]
     X, Y, Z = [int(s) for s in cube_size]
     N = X * Y * Z
     w, h = float(heatmap_size[0]), float(heatmap_size[1])
     W, H = float(image_size[0]), float(image_size[1])
-    gc_all = torch.as_tensor(np.asarray(grid_center), dtype=torch.float32)
-    cubes = torch.zeros(B, C, N)
-    grids = torch.zeros(B, N, 3)
+    gc_all = torch.as_tensor(np.asarray(grid_center), dtype=torch.float32).to(dtype)
+    cubes = torch.zeros(B, C, N, dtype=dtype)
+    grids = torch.zeros(B, N, 3, dtype=dtype)
+    heatmaps = [hm.to(dtype) for hm in heatmaps]
     for i in range(B):
         if gc_all.shape[1] != 3 and not gc_all[i, 3] >= 0:
             continue
         gc = gc_all[0] if gc_all.shape[0] == 1 else gc_all[i]
-        g1 = [torch.linspace(-grid_size[a] / 2, grid_size[a] / 2, cube_size[a]) + gc[a] for a in range(3)]
+        g1 = [torch.linspace(-grid_size[a] / 2, grid_size[a] / 2, cube_size[a]).to(dtype) + gc[a] for a in range(3)]
         gx, gy, gz = torch.meshgrid(g1[0], g1[1], g1[2], indexing="ij")
         grid = torch.stack([gx.reshape(-1), gy.reshape(-1), gz.reshape(-1)], dim=1)
         grids[i] = grid
-        num = torch.zeros(C, N)
-        den = torch.zeros(N)
+        num = torch.zeros(C, N, dtype=dtype)
+        den = torch.zeros(N, dtype=dtype)
         for c in range(V):
             cam = _cam_at(cam_arrays, c, i)
-            R = torch.as_tensor(cam["R"], dtype=torch.float32)
-            T = torch.as_tensor(cam["T"], dtype=torch.float32).reshape(3, 1)
-            k = torch.as_tensor(cam["k"], dtype=torch.float32).reshape(3)
-            p = torch.as_tensor(cam["p"], dtype=torch.float32).reshape(2)
+            # (camera parameters are cast to float32 first, as the reference does: cameras.py:14-23)
+            R = torch.as_tensor(cam["R"], dtype=torch.float32).to(dtype)
+            T = torch.as_tensor(cam["T"], dtype=torch.float32).reshape(3, 1).to(dtype)
+            k = torch.as_tensor(cam["k"], dtype=torch.float32).reshape(3).to(dtype)
+            p = torch.as_tensor(cam["p"], dtype=torch.float32).reshape(2).to(dtype)
             xcam = torch.mm(R, grid.t() - T)
             y = xcam[:2] / (xcam[2] + 1e-5)
             r2 = torch.clamp((y ** 2).sum(0), max=1e10)
@@ -64,12 +67,12 @@ def unproject_torch(heatmaps, cam_arrays, centers, scales, rotations, image_size
             px = float(cam["fx"]) * u + float(cam["cx"])
             py = float(cam["fy"]) * v + float(cam["cy"])
             width, height = 2 * float(centers[c][i][0]), 2 * float(centers[c][i][1])
-            m = ((px >= 0) & (py >= 0) & (px < width) & (py < height)).float()
+            m = ((px >= 0) & (py >= 0) & (px < width) & (py < height)).to(dtype)
             hi = max(width, height)
             px = px.clamp(-1.0, hi)
             py = py.clamp(-1.0, hi)
             A = torch.as_tensor(geometry.get_affine_transform(
-                centers[c][i], scales[c][i], rotations[c][i], image_size), dtype=torch.float32)
+                centers[c][i], scales[c][i], rotations[c][i], image_size), dtype=torch.float32).to(dtype)
             qx = A[0, 0] * px + A[0, 1] * py + A[0, 2]
             qy = A[1, 0] * px + A[1, 1] * py + A[1, 2]
             if flip is not None and bool(flip[i]):
@@ -91,7 +94,7 @@ def _sub(sd, prefix):
 
 
 def inference(sd, cfg, cam_arrays, centers, scales, rotations, images=None, heatmaps=None,
-              root_channel_only=True):
+              root_channel_only=True, dtype=torch.float32, grid_centers=None):
     """do_inference (multi_person_posenet_ssv.py:105-153).
 
     ``sd``: full model state dict (``backbone.*``, ``root_net.v2v_net.*``,
@@ -100,22 +103,29 @@ def inference(sd, cfg, cam_arrays, centers, scales, rotations, images=None, heat
     ``cube_size``, ``max_people``, ``threshold``, ``beta``, ``root_idx``.
     Returns ``pred [B,K,J,5]``, heat-maps ``list[V]``, ``grid_centers [B,K,5]``,
     ``root_cubes [B,X,Y,Z]`` (torch tensors).
+
+    ``dtype`` float64 evaluates every step in double precision (tolerance budgeting: how far the float32 reference
+    itself is from exact arithmetic).  ``grid_centers``: take these proposals instead of the root net's own (so that
+    a float64 run regresses the SAME person cubes as a float32 run whose near-tied top-K order may differ).
     """
     if heatmaps is None:
         bsd = _sub(sd, "backbone.")
-        heatmaps = [nets.pose_resnet_forward(v, bsd) for v in images]          # :108-110
+        heatmaps = [nets.pose_resnet_forward(v.to(dtype), bsd, dtype=dtype) for v in images]          # :108-110
     B, J = heatmaps[0].shape[:2]
     K = int(cfg["max_people"])
     hm_root = [h[:, cfg["root_idx"]][:, None].contiguous() for h in heatmaps] if root_channel_only else heatmaps
     init_cubes, _ = unproject_torch(hm_root, cam_arrays, centers, scales, rotations, cfg["image_size"],
                                     cfg["heatmap_size"], cfg["space_size"], [cfg["space_center"]],
-                                    cfg["initial_cube_size"])                  # cuboid_proposal_net_soft.py:137-144
-    root_cubes = nets.v2v_forward(init_cubes, _sub(sd, "root_net.v2v_net."))[:, 0]
-    gc = torch.from_numpy(volume_ops.proposal_layer(
-        root_cubes.numpy(), cfg["space_size"], cfg["space_center"], cfg["initial_cube_size"], K,
-        cfg["threshold"]))
-    pred = torch.zeros(B, K, J, 5)
-    pred[:, :, :, 3:] = gc[:, :, 3:].reshape(B, -1, 1, 2)                      # :139-140
+                                    cfg["initial_cube_size"], dtype=dtype)     # cuboid_proposal_net_soft.py:137-144
+    root_cubes = nets.v2v_forward(init_cubes, _sub(sd, "root_net.v2v_net."), dtype=dtype)[:, 0]
+    if grid_centers is None:
+        gc = torch.from_numpy(volume_ops.proposal_layer(
+            root_cubes.float().numpy(), cfg["space_size"], cfg["space_center"], cfg["initial_cube_size"], K,
+            cfg["threshold"]))
+    else:
+        gc = torch.as_tensor(grid_centers).float().clone()
+    pred = torch.zeros(B, K, J, 5, dtype=dtype)
+    pred[:, :, :, 3:] = gc[:, :, 3:].reshape(B, -1, 1, 2).to(dtype)            # :139-140
     psd = _sub(sd, "pose_net.v2v_net.")
     for n in range(K):                                                         # :143-148
         index = gc[:, n, 3] >= 0
@@ -123,8 +133,8 @@ def inference(sd, cfg, cam_arrays, centers, scales, rotations, images=None, heat
             continue
         cubes, grids = unproject_torch(heatmaps, cam_arrays, centers, scales, rotations, cfg["image_size"],
                                        cfg["heatmap_size"], cfg["grid_size"], gc[:, n].numpy(),
-                                       cfg["cube_size"])
-        valid = nets.v2v_forward(cubes[index], psd)                            # pose_regression_net.py:49-51
+                                       cfg["cube_size"], dtype=dtype)
+        valid = nets.v2v_forward(cubes[index], psd, dtype=dtype)               # pose_regression_net.py:49-51
         p = torch.softmax(float(cfg["beta"]) * valid.reshape(valid.shape[0], J, -1, 1), dim=2)
         pred[index, n, :, 0:3] = (p * grids[index].unsqueeze(1)).sum(dim=2)
     return pred, heatmaps, gc, root_cubes

@@ -11,6 +11,10 @@ Two shardings, one exchange step each:
   (16.6 MB at B = 8) are broadcast view by view from their owners, each rank regresses its slice of the valid
   cubes, and the ``[n, J, 3]`` results are all-gathered.
 
+``infer_image_sharded`` is the balanced form of the same split that ``bench.py --gpus N`` measures: the flattened
+(view, sample) image list is sharded instead of whole views (5 views leave 3 of 8 GPUs idle), the root-grid sum is a
+reduce-scatter over samples, the heat-maps travel in ONE all-gather that overlaps the root path.
+
 The partition arithmetic is pure Python (tested under ``gloo`` on CPU); the collectives are NCCL on GPUs.
 """
 from __future__ import annotations
@@ -112,6 +116,8 @@ def root_volume_view_sharded(root_net, local_heatmaps, meta, batch_size, group=N
     cubes = partial[:, :C].reshape(batch_size, C, X, Y, Z)
     if ops.volume_dtype() == torch.bfloat16:
         cl = ops.to_channel_last(cubes, c_pitch=ops.round_up(C, 16), dtype=torch.bfloat16)
+    elif ops.use_split():
+        cl = ops.split_act(ops.to_channel_last(cubes), C)
     else:
         cl = ops.to_channel_last(cubes)
     root = root_net.v2v_net.forward_cl(cl, out_pitch=1)
@@ -167,6 +173,124 @@ def infer_view_sharded(model, local_views, meta, group=None):
     pred = torch.zeros(B, K, J, 5, device=device)
     pred[:, :, :, 3:] = grid_centers[:, :, 3:].reshape(B, -1, 1, 2)
     regress_sharded(model.pose_net, all_heatmaps, cams, grid_centers, pred, group=group)
+    return pred, all_heatmaps, grid_centers
+
+
+# ------------------------------------------------------------------------------------------------ image sharding
+def image_shard(rank, world, num_views, batch_size):
+    """Balanced sharding of the flattened (view, sample) image list (index ``v * B + i``): the contiguous slice
+    owned by ``rank`` and, per view, the ``[begin, end)`` sample range of it that falls into that slice.
+    40 images (5 views x 8 frames) give 20 / 10 / 5 images per rank on 2 / 4 / 8 GPUs (view sharding would leave 3 of
+    8 GPUs without backbone work)."""
+    b, e = shard_slice(num_views * batch_size, rank, world)
+    per_view = {}
+    for v in range(num_views):
+        lo, hi = max(b, v * batch_size), min(e, (v + 1) * batch_size)
+        if hi > lo:
+            per_view[v] = (lo - v * batch_size, hi - v * batch_size)
+    return (b, e), per_view
+
+
+def infer_image_sharded(model, local_images, meta, group=None, side_stream=None):
+    """BASELINE configs[3] on ``world`` GPUs: ONE batch strong-scaled.
+
+    * backbone: the flattened (view, sample) image list is sharded (``image_shard``); ``local_images`` is this rank's
+      ``[n_local, 3, H, W]`` slice;
+    * root grid: every rank un-projects ITS images into partial numerators + view counts (``sp3d_unproject_fwd`` with
+      ``partial = 1``, one launch per owned view over the owned samples); ONE ``reduce_scatter`` (sum) of the
+      ``[B, C+1, X*Y*Z]`` float32 grid over NVLink leaves each rank with the summed grid of its samples (the
+      all-reduce of the north star, of which every rank keeps only the slice it goes on to use);
+      ``sp3d_unproject_finalize`` -> V2V-root -> NMS on ``B / world`` samples per rank; the ``[B, K, 5]`` proposals are
+      all-gathered (1.6 KB);
+    * heat-maps: ONE ``all_gather`` of the channel-last maps (16.6 MB at B = 8), issued on ``side_stream`` so that it
+      overlaps the root path;
+    * person cubes: sharded by (sample, proposal); the ``[n, J, 3]`` joints are all-gathered.
+
+    Returns ``(pred, all_heatmaps, grid_centers)``, identical on every rank."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    V = len(meta)
+    B = int(meta[0]["center"].shape[0])
+    device = torch.device("cuda", torch.cuda.current_device())
+    (ib, ie), per_view = image_shard(rank, world, V, B)
+    K, J = model.num_cand, model.num_joints
+    root_net = model.root_net
+    pl = root_net.project_layer
+    if (V * B) % world or B % world:
+        raise ValueError("image sharding needs V*B and B divisible by the world size (got V=%d B=%d world=%d)" % (V, B, world))
+
+    # ---- backbone on the local images: channel-last float32 heat-maps [n_local, h, w, pitch]
+    hm_local = model.backbone(local_images)                        # [n_local, J, h, w] view of a channel-last buffer
+    n_local, _, h, w = [int(v) for v in hm_local.shape]
+    hm_cl = hm_local.permute(0, 2, 3, 1)                            # [n_local, h, w, J] (stride-1 channels)
+    pitch = int(hm_cl.stride(2))
+    base = torch.as_strided(hm_cl, (n_local, h, w, pitch), (h * w * pitch, w * pitch, pitch, 1))
+
+    # ---- heat-map all-gather on the side stream (overlaps the root path)
+    cur = torch.cuda.current_stream()
+    gathered = torch.empty(V * B, h, w, pitch, device=device, dtype=torch.float32)
+    produced = torch.cuda.Event()
+    produced.record(cur)
+    stream = side_stream if side_stream is not None else cur
+    with torch.cuda.stream(stream):
+        stream.wait_event(produced)
+        dist.all_gather_into_tensor(gathered, base.contiguous(), group=group)
+        gathered_done = torch.cuda.Event()
+        gathered_done.record(stream)
+
+    # ---- partial root grid of the local images
+    cams = ops.pack_cameras(meta, pl.img_size).to(device, non_blocking=True)
+    X, Y, Z = [int(v) for v in root_net.cube_size]
+    n_vox = X * Y * Z
+    if root_net.rootnet_roothm:
+        C, c0 = 1, int(root_net.root_id)
+    else:
+        C, c0 = J, 0
+    partial = torch.zeros(B, C + 1, n_vox, device=device, dtype=torch.float32)
+    centers_all, _ = pl.centers_tensor([list(root_net.grid_center)], B, device)
+    for v, (s0, s1) in per_view.items():
+        # maps of view v, samples [s0, s1) = rows [first, first + cnt) of the local buffer; the launch sees them as a
+        # batch of cnt samples (camera table and centres sliced the same way), summing view v only
+        cnt, first = s1 - s0, v * B + s0 - ib
+        hm_v = torch.as_strided(base, (cnt, C, h, w), (h * w * pitch, 1, w * pitch, pitch),
+                                base.storage_offset() + first * h * w * pitch + c0)
+        tmp = torch.empty(cnt, C + 1, n_vox, device=device, dtype=torch.float32)
+        ops.unproject([hm_v] * V, hm_v.stride(), cams[s0:s1].contiguous(), centers_all[s0:s1].contiguous(),
+                      root_net.grid_size, (X, Y, Z), pl.img_size, (h, w), C, tmp, ((C + 1) * n_vox, n_vox, 1),
+                      view_range=(v, v + 1), partial=True, heatmap_cfg_wh=pl.heatmap_size)
+        partial[s0:s1] += tmp
+    # ---- the voxel-grid exchange: sum over ranks, each rank keeps its B / world samples
+    per = B // world
+    mine = torch.empty(per, C + 1, n_vox, device=device, dtype=torch.float32)
+    if world > 1:
+        dist.reduce_scatter_tensor(mine, partial, op=dist.ReduceOp.SUM, group=group)
+    else:
+        mine.copy_(partial)
+    ops.unproject_finalize(mine, per, C, n_vox, ((C + 1) * n_vox, n_vox, 1))
+    cubes = mine[:, :C].reshape(per, C, X, Y, Z)
+    if ops.volume_dtype() == torch.bfloat16:
+        cl = ops.to_channel_last(cubes, c_pitch=ops.round_up(C, 16), dtype=torch.bfloat16)
+    elif ops.use_split():
+        cl = ops.split_act(ops.to_channel_last(cubes), C)
+    else:
+        cl = ops.to_channel_last(cubes)
+    root = root_net.v2v_net.forward_cl(cl, out_pitch=1).view(per, X, Y, Z)
+    gc_mine = root_net.proposal_layer(root, None)                   # [per, K, 5]
+    grid_centers = torch.empty(B, K, 5, device=device, dtype=torch.float32)
+    if world > 1:
+        dist.all_gather_into_tensor(grid_centers, gc_mine.contiguous(), group=group)
+    else:
+        grid_centers.copy_(gc_mine)
+
+    # ---- person cubes, sharded by (sample, proposal), from ALL heat-maps
+    cur.wait_event(gathered_done)
+    all_heatmaps = [gathered[v * B:(v + 1) * B].permute(0, 3, 1, 2)[:, :J] for v in range(V)]
+    pred = torch.zeros(B, K, J, 5, device=device)
+    pred[:, :, :, 3:] = grid_centers[:, :, 3:].reshape(B, -1, 1, 2)
+    if world > 1:
+        regress_sharded(model.pose_net, all_heatmaps, cams, grid_centers, pred, group=group)
+    else:
+        from .models._inference import regress_valid
+        regress_valid(model.pose_net, all_heatmaps, cams, grid_centers, pred)
     return pred, all_heatmaps, grid_centers
 
 

@@ -6,6 +6,8 @@ hand-written kernel on torch's current stream.  There is no CPU path.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -99,10 +101,13 @@ def volume_dtype():
     return _VOLUME_DTYPE
 
 
-# How float32 activations are convolved: "simt" (float32 FMA kernel, the bit-for-bit parity path), or "bf16x3" /
-# "bf16x6": the tcgen05 kernel on float32 data expanded into 2 / 3 bf16 terms (3 / 6 term pairs accumulated in
-# float32 as extra K blocks) -- float32-faithful results at tensor-core speed (SP3D_CONV_TC_BF16X3).
-_F32_CONV = "simt"
+# How float32 activations are convolved.  "bf16x3" (the default: the product mode) / "bf16x6": the tcgen05 kernel on
+# float32 data expanded into 2 / 3 bf16 terms (3 / 6 term pairs accumulated in float32 as extra K blocks) --
+# float32-faithful results at tensor-core speed (SP3D_CONV_TC_BF16X3); "simt": the float32 FMA kernel (any shape; the
+# cross-check path of the parity tests).  SP3D_F32_CONV in the environment overrides the default.
+_F32_CONV = os.environ.get("SP3D_F32_CONV", "bf16x3")
+if _F32_CONV not in ("simt", "bf16x3", "bf16x6"):
+    raise ValueError('SP3D_F32_CONV must be "simt", "bf16x3" or "bf16x6"')
 
 
 def set_float32_conv(mode):

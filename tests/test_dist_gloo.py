@@ -31,6 +31,23 @@ def test_partitions_cover_everything_once():
     assert sd.view_range(7, 8, 5) == (5, 5)      # more ranks than views: idle rank
 
 
+def test_image_shard_is_balanced_and_covers_every_view_sample_once():
+    V, B = 5, 8
+    for world in (1, 2, 4, 8):
+        seen = []
+        for r in range(world):
+            (b, e), per_view = sd.image_shard(r, world, V, B)
+            assert e - b == V * B // world
+            rows = []
+            for v, (s0, s1) in sorted(per_view.items()):
+                assert 0 <= s0 < s1 <= B
+                rows += [v * B + i for i in range(s0, s1)]
+            assert rows == list(range(b, e))
+            seen += rows
+        assert seen == list(range(V * B))
+    assert sd.image_shard(1, 8, 5, 8) == ((5, 10), {0: (5, 8), 1: (0, 2)})
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

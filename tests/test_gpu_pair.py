@@ -18,6 +18,7 @@ from selfpose3d_b200.models import project_layer  # noqa: E402
 from test_gpu_tensorcore import rand_bn  # noqa: E402
 
 DEV = "cuda:0"
+DEFAULT_F32_CONV = ops.float32_conv()   # conftest: "simt" for the modules written against the float32 FMA kernels
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOL = 5e-5     # of the output range, as tests/test_gpu_split.py
 
@@ -35,7 +36,7 @@ def split_mode():
     ops.set_volume_dtype(torch.float32)
     ops.set_float32_conv("bf16x3")
     yield
-    ops.set_float32_conv("simt")
+    ops.set_float32_conv(DEFAULT_F32_CONV)
 
 
 def to_pair(x, channels=None):

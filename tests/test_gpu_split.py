@@ -22,6 +22,7 @@ from test_gpu_parity import _small_model, meta_from_golden  # noqa: E402
 from test_gpu_tensorcore import rand_bn  # noqa: E402
 
 DEV = "cuda:0"
+DEFAULT_F32_CONV = ops.float32_conv()   # conftest: "simt" for the modules written against the float32 FMA kernels
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # per-convolution bound relative to the output range.  3 term pairs drop ~3 * 2^-18 per product; beyond that both
 # variants sit on the tensor core's float32 accumulator, which loses ~2^-24 of its magnitude per MMA (measured
@@ -41,7 +42,7 @@ def note(line):
 def mode(request):
     ops.set_float32_conv(request.param)
     yield request.param
-    ops.set_float32_conv("simt")
+    ops.set_float32_conv(DEFAULT_F32_CONV)
 
 
 @pytest.mark.parametrize("blocks", [2, 3])

@@ -2,9 +2,8 @@
 through the kernels, against the step recorded from the unmodified reference (``backward.npz``, keys ``sup_*``).
 
 The host-side logic of this step is pinned on CPU (tests/test_training_cpu.py, kernels emulated) and every kernel it
-launches is checked on the GPU on its own (tests/test_gpu_backward.py).  This end-to-end composition was written
-after the round's GPU budget was spent, so its first B200 run is the round-end run: it is a NON-STRICT xfail until
-it has been seen green once (an XPASS in the log is that observation)."""
+launches is checked on the GPU on its own (tests/test_gpu_backward.py).  These end-to-end compositions passed on the
+B200 in the round-1 driver run (recorded as XPASS there); they are strict tests now."""
 import numpy as np
 import pytest
 import torch
@@ -16,10 +15,9 @@ from selfpose3d_b200.config import default_config  # noqa: E402
 from selfpose3d_b200.models import multi_person_posenet  # noqa: E402
 
 DEV = "cuda:0"
+DEFAULT_F32_CONV = "simt"   # tests/conftest.py runs this module on the float32 FMA kernels
 
 
-@pytest.mark.xfail(strict=False, reason="first B200 run of this composition (GPU budget of the round was spent); "
-                                        "host logic verified on CPU in tests/test_training_cpu.py")
 def test_supervised_training_step_matches_reference_on_gpu(golden):
     g, gb = golden("inference_small"), golden("backward")
     cfg = default_config()
@@ -70,11 +68,6 @@ def test_supervised_training_step_matches_reference_on_gpu(golden):
         assert abs(gn - norm) <= 5e-3 * norm, (name, gn, norm)
 
 
-_FIRST_RUN = pytest.mark.xfail(strict=False, reason="first B200 run of this composition (GPU budget of the round was "
-                                                    "spent); lowering / wiring verified on CPU with emulated kernels")
-
-
-@_FIRST_RUN
 @pytest.mark.parametrize("case", ["3x3s2_even", "3x3s2_odd", "1x1s2", "7x7s2", "deconv4s2"])
 def test_strided_conv_dgrad_vs_autograd(case):
     """Input gradients of strided / transposed 2-D convolutions (transposed convolution with an explicit output
@@ -105,7 +98,6 @@ def test_strided_conv_dgrad_vs_autograd(case):
     assert float((got - x.grad).abs().max()) <= 2e-5 * float(x.grad.abs().max())
 
 
-@_FIRST_RUN
 def test_pose_resnet_training_step_vs_oracle():
     """PoseResNet-50 in .train() on a 64 x 96 image batch through the kernels: output and the gradients of all
     parameters against float64 autograd through the oracle's restatement (L2 norm: single ReLU gates flip between
@@ -146,7 +138,6 @@ def test_pose_resnet_training_step_vs_oracle():
     assert checked >= 100
 
 
-@_FIRST_RUN
 def test_ssl_training_step_matches_reference_on_gpu(golden):
     """``MultiPersonPoseNetSSV.forward(inference=False)`` through the kernels against the self-supervised step recorded
     from the unmodified reference (ssl_step.npz) -- CPU twin: tests/test_training_cpu.py."""
@@ -186,7 +177,6 @@ def test_ssl_training_step_matches_reference_on_gpu(golden):
         assert abs(gn - norm) <= 5e-2 * norm, (name, gn, norm)
 
 
-@_FIRST_RUN
 def test_v2v_training_step_on_tensor_cores_matches_reference(golden):
     """The V2VNet training step with ``ops.set_float32_conv("bf16x3")``: forward convolutions and the input gradients
     whose adjoint shape has a compiled instantiation run on tcgen05 through split operands (weight gradients stay on
@@ -203,7 +193,7 @@ def test_v2v_training_step_on_tensor_cores_matches_reference(golden):
         y = net(x)
         (y * torch.from_numpy(gb["v2v_grad_y"]).to(DEV)).sum().backward()
     finally:
-        ops.set_float32_conv("simt")
+        ops.set_float32_conv(DEFAULT_F32_CONV)
     scale = float(np.abs(gb["v2v_y"]).max())
     assert float(np.abs(y.detach().cpu().numpy() - gb["v2v_y"]).max()) <= 2e-4 * scale
     assert float(np.abs(x.grad.cpu().numpy() - gb["v2v_grad_x"]).max()) <= 2e-3 * float(np.abs(gb["v2v_grad_x"]).max())
@@ -213,7 +203,6 @@ def test_v2v_training_step_on_tensor_cores_matches_reference(golden):
         assert abs(float(g.norm()) - norm) <= 4e-3 * max(norm, 1e-3), (name, float(g.norm()), norm)
 
 
-@_FIRST_RUN
 def test_gauss_render_kernels_vs_autograd():
     """sp3d_gauss_render_fwd / bwd against the tensor expression of the reference (:410-448) and its autograd gradient:
     ragged people counts, joints inside and outside the map, sums above 1 (the clip gate)."""

@@ -291,6 +291,7 @@ def apply_emulation_in_this_process():
     tests/test_dist_gloo.py, which have no pytest fixtures)."""
     import test_autograd_cpu as T
     from selfpose3d_b200 import grad_ops
+    ops.set_float32_conv("simt")     # the emulated launcher takes the float32 FMA kernel's arguments
     ops.conv_launch, ops.to_channel_last, ops.to_channel_first = T.emulate_conv_launch, T._cl, T._cf
     ops.maxpool, ops.nms_topk = T._maxpool_any, emul_nms_topk
     grad_ops._f32 = lambda *a: None
