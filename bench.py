@@ -109,7 +109,7 @@ def port_args(cfg, sd, meta):
             [m["scale"].numpy() for m in meta], [m["rotation"].numpy() for m in meta])
 
 
-def cpu_reference_frames_per_s(steps, warmup, frames_per_step=1, kind=None):
+def cpu_reference_frames_per_s(steps, warmup, frames_per_step=1, kind=None, images=None):
     """Times the reference's CPU implementation of the path on `frames_per_step` frames per step: the UNMODIFIED
     reference staged under oracle/_ref (kind "reference": MultiPersonPoseNetSSV.forward(inference=True) through its own
     module API, lib/models/multi_person_posenet_ssv.py:105-153) or, when that is absent, the oracle port
@@ -118,7 +118,8 @@ def cpu_reference_frames_per_s(steps, warmup, frames_per_step=1, kind=None):
     torch.set_num_threads(os.cpu_count() or 1)
     if kind is None:
         kind = "reference" if ref_runner.available() else "port"
-    cfg, sd, meta, images = cpu_inputs(frames_per_step)
+    cfg, sd, meta, own_images = cpu_inputs(frames_per_step)
+    images = own_images if images is None else images
     if kind == "reference":
         ocfg = oracle_cfg(cfg)
         model, _ = ref_runner.build_model(state_dict=sd, num_joints=cfg.NETWORK.NUM_JOINTS, **ocfg)
@@ -548,7 +549,7 @@ def run_ours(args, rank, world, local_rank):
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cpu_frames = 2
-        cpu_fps, cpu_spf, kind, ref_pred = cpu_reference_frames_per_s(cpu_frames, 1, 1)
+        cpu_fps, cpu_spf, kind, ref_pred = cpu_reference_frames_per_s(cpu_frames, 1, 1, images=[im[:1] for im in images])
         cpu_baseline = {"value": cpu_fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": kind,
                         "sample": "%d x 1 frame (5 views 3x384x288, 10 proposals) through %s on torch CPU (all host "
                                   "threads), 1 warm-up, %.2f s per frame"
@@ -614,9 +615,10 @@ def main():
         return
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; stdout carries exactly one JSON line here
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION and above (WARN included); stdout carries
+        # exactly one JSON line here, so anything below INFO is switched off
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ.pop("NCCL_DEBUG", None)
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
         run_ours(args, rank, world, local_rank)

@@ -54,7 +54,11 @@ def infer(model, views, meta, input_heatmaps, use_root_gt, eval_rootnet_only=Fal
     B = int(all_heatmaps[0].shape[0])
     K, J = model.num_cand, model.num_joints
 
-    img_size = (model.pose_net if hasattr(model, "pose_net") else model.root_net).project_layer.img_size
+    # (TRAIN_ONLY_2D models have neither a root net nor a pose net: the heat-maps are the whole result)
+    sub = getattr(model, "pose_net", None) or getattr(model, "root_net", None)
+    if sub is None:
+        return torch.zeros(B, K, J, 5, device=device), all_heatmaps, torch.zeros(B, K, 5, device=device), None
+    img_size = sub.project_layer.img_size
     cams = ops.pack_cameras(meta, img_size).to(device, non_blocking=True)
     root_cubes = None
     if use_root_gt:

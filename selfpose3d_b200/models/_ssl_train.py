@@ -133,7 +133,11 @@ def forward_train(self, views1, meta1, targets_2d1, weights_2d1, targets_3d1, in
     device = heatmaps1[0].device
     B = int(heatmaps1[0].shape[0])
     K, J = self.num_cand, self.num_joints
-    zero = heatmaps3[0].sum() * 0.0          # a zero that stays attached to the graph (reference: a dummy forward * 0)
+    # a zero that stays attached to the graph.  The reference uses `pose_net.v2v_net(zero_tensor).mean() * 0`
+    # (multi_person_posenet_ssv.py:91-97,342-349): it always reaches the pose net's parameters, so that every loss it
+    # stands in for requires grad and those parameters receive zero (not None) gradients
+    anchor = getattr(self, "pose_net", None) or getattr(self, "root_net", None) or self.backbone
+    zero = sum(p.sum() for p in anchor.parameters()) * 0.0 + heatmaps3[0].sum() * 0.0
 
     losses = {}
     t1 = torch.stack([t.to(device) for t in targets_2d1]) if targets_2d1 is not None else None

@@ -71,7 +71,7 @@ class MultiPersonPoseNetSSV(nn.Module):
                 input_heatmaps1=None, views2=None, meta2=None, targets_2d2=None, weights_2d2=None,
                 targets_3d2=None, input_heatmaps2=None, views3=None, meta3=None, targets_2d3=None,
                 weights_2d3=None, targets_3d3=None, input_heatmaps3=None, inference=False,
-                visualize_attn=False, epoch=None):
+                visualize_attn=False, epoch=0):
         if inference:
             with torch.no_grad():
                 return self.do_inference(views1, meta1, input_heatmaps1, visualize_attn)

@@ -17,6 +17,8 @@ records no gradient.
 """
 from __future__ import annotations
 
+import threading
+
 import torch
 import torch.nn as nn
 
@@ -55,19 +57,28 @@ def _no_train(module):
 
 
 class _PackedCache:
-    """Re-packs a module's parameters for the kernels when they change (load_state_dict, .to())."""
+    """Re-packs a module's parameters for the kernels when they change (load_state_dict, .to()).
+
+    One slot per device: ``nn.DataParallel`` replicas are shallow copies that share this object while their parameters
+    live on different GPUs and their forwards run in concurrent threads (``tools/train_3d.py:139-140`` wraps the model
+    that way), so the packed weights are keyed by the device of the parameters and guarded by a lock."""
 
     def __init__(self):
-        self.key = None
-        self.value = None
+        self.slots = {}
+        self.lock = threading.Lock()
 
     def get(self, module, build):
         tensors = list(module.parameters()) + list(module.buffers())
         key = tuple((t.data_ptr(), t._version) for t in tensors)
-        if key != self.key:
-            self.value = build()
-            self.key = key
-        return self.value
+        dev = tensors[0].device if tensors else None
+        with self.lock:
+            hit = self.slots.get(dev)
+            if hit is not None and hit[0] == key:
+                return hit[1]
+        value = build()
+        with self.lock:
+            self.slots[dev] = (key, value)
+        return value
 
 
 class Basic3DBlock(nn.Module):

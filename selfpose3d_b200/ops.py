@@ -7,6 +7,7 @@ hand-written kernel on torch's current stream.  There is no CPU path.
 from __future__ import annotations
 
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -580,11 +581,24 @@ def conv_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksi
             flops *= 8
         detail = "conv%s algo%d k%d %d->%d @%dx%dx%dx%d" % ("T8" if fused_phases else "", a.algo, a.ksize[2],
                                                            cin_real or a.cin, a.cout, a.N, a.OD, a.OH, a.OW)
-        if len(_CONV_ARGS_CACHE) > 1024:   # (entries pin their packed weights; training re-packs after every step)
-            _CONV_ARGS_CACHE.clear()
-        # (weight, scale, shift) are kept alive by the cache entry so that their addresses cannot be recycled
-        hit = _CONV_ARGS_CACHE[key] = (a, flops, detail, (weight, scale, shift), (int(relu), int(cout), int(cin)))
-    a, flops, detail, _, sig = hit
+        if len(_CONV_ARGS_CACHE) > 256:
+            # entries whose packed weight is gone (the training path re-packs every layer after each optimizer step)
+            for k in [k for k, v in _CONV_ARGS_CACHE.items() if v[3]() is None]:
+                del _CONV_ARGS_CACHE[k]
+            if len(_CONV_ARGS_CACHE) > 2048:
+                _CONV_ARGS_CACHE.clear()
+        # the entry holds a WEAK reference to the packed weight: it dies with the PackedConv that owns the tensor (no
+        # stale packs pinned in device memory), and a recycled address is detected by the dead / different referent
+        hit = _CONV_ARGS_CACHE[key] = (a, flops, detail, weakref.ref(weight), (int(relu), int(cout), int(cin)),
+                                       (scale.data_ptr() if scale is not None else 0,
+                                        shift.data_ptr() if shift is not None else 0))
+    a, flops, detail, wref, sig, ss = hit
+    if wref() is not weight or ss != (scale.data_ptr() if scale is not None else 0,
+                                      shift.data_ptr() if shift is not None else 0):
+        del _CONV_ARGS_CACHE[key]        # the address was recycled by another tensor: rebuild
+        return conv_launch(x, weight, scale, shift, residual, out, cin, cout, out_grid, ksize, stride, tap_off0, tap_step,
+                           ostride, ooffset, relu, algo, cin_real, cout_pitch_w, fused_phases, zfold, head, split_terms,
+                           pair_out)
     if sig != (int(relu), int(cout), int(cin)):
         raise _lib.Sp3dError("conv_launch cache collision")
     a.in_ = x.data_ptr()

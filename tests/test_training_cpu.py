@@ -286,6 +286,12 @@ def test_bench_training_step_case(emulated, monkeypatch):  # noqa: F811
     assert got == {"root_net", "pose_net"}, got
 
 
+def emul_softargmax_op(x, strides, n_cubes, channels, cube_size, centers, grid_size, beta, check_flag=False, lin=None):
+    """ops.softargmax as the inference path calls it (channel-last float32 volume ``[n, X, Y, Z, pitch]``)."""
+    assert lin is None and not check_flag
+    return emul_softargmax(x, centers, (int(channels), [int(v) for v in cube_size], [float(v) for v in grid_size], float(beta)))
+
+
 def apply_emulation_in_this_process():
     """The same kernel emulations as the fixtures above, applied for good (spawned `gloo` workers of
     tests/test_dist_gloo.py, which have no pytest fixtures)."""
@@ -294,6 +300,7 @@ def apply_emulation_in_this_process():
     ops.set_float32_conv("simt")     # the emulated launcher takes the float32 FMA kernel's arguments
     ops.conv_launch, ops.to_channel_last, ops.to_channel_first = T.emulate_conv_launch, T._cl, T._cf
     ops.maxpool, ops.nms_topk = T._maxpool_any, emul_nms_topk
+    ops.unproject, ops.softargmax = emul_unproject_op, emul_softargmax_op
     grad_ops._f32 = lambda *a: None
     for name, fn in (("maxpool_bwd", T._maxpool_bwd_any), ("bn_stats", T._bn_stats), ("bn_apply", T._bn_apply),
                      ("bn_bwd", T._bn_bwd), ("relu_bwd", T._relu_bwd), ("conv_wgrad", T._conv_wgrad_any)):
