@@ -210,11 +210,17 @@ typedef struct {
                                to head->out [N, cout, 3].  Uses head->centers / lin_* / beta / out and
                                head->workspace of sp3d_conv_head_workspace() bytes; x / strides are ignored,
                                n_cubes, C, X, Y, Z must equal N, cout, OD, OH, OW; check_flag must be 0. */
-  int split_terms;          /* SP3D_CONV_TC_BF16X3 only: 3 or 6.  The float32 operands are used as sums of bf16 terms
+  int split_terms;          /* SP3D_CONV_TC_BF16X3 only: 3, 6 or 2.  The float32 operands are used as sums of bf16 terms
                                (x = x0 + x1 (+ x2), each term the bf16 rounding of what the previous ones left) and the
                                product is accumulated in float32 over the term pairs
                                  3: x1 w0 + x0 w1 + x0 w0                          (drops ~3 * 2^-18 per product)
                                  6: x2 w0 + x1 w1 + x0 w2 + x1 w0 + x0 w1 + x0 w0   (drops ~2^-24 per product)
+                                 2: the same 3 pairs in TWO K blocks -- x0 [w0 | w1] as MMAs of 2 N columns (the A
+                                    operand is read once for two products: narrow channel tiles are bound by that
+                                    read), x1 w0 onto the upper N columns; the epilogue adds the halves.  `weight` is
+                                    packed [n_tile][chunk][tap][2 N rows: w0 rows, w1 rows][chunk channels] followed by
+                                    [chunk][tap][N rows of w0][chunk channels].  Available for the layer shapes listed
+                                    in csrc/conv_tc.cu (SP3D_TC_CASE_W); outputs must be 16-byte pitched.
                                as extra K blocks of ONE implicit GEMM, small products first (the tensor core's float32
                                accumulator loses ~2^-24 of its magnitude per MMA, which bounds both variants: measured
                                ~1e-5 of the output range per layer, tests/test_gpu_split.py).  `in` is the bf16 tensor

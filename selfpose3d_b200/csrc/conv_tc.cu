@@ -62,6 +62,7 @@ struct TcConvParams {
   int n_tiles;                   // tiles of N output channels
   int n_chunks;                  // K chunks of (RB / 2) input channels (all K blocks of the split-operand mode)
   int nc_block;                  // chunks per K block (= n_chunks unless the operands are split into bf16 terms)
+  int w_rows_tile;               // packed-weight rows of one channel tile (the weight producer streams them linearly)
   uint32_t block_act;            // split-operand mode: nibble b = activation term plane read by K block b (plane t of
                                  // cube n is outer index t * n_outer + n of the activation tensor map), else 0
   int istride[3];                // input step per output step (x, y, z)
@@ -98,7 +99,12 @@ constexpr int kProfSlots = 16;    // per CTA: mma total, wait halo, wait weights
 // KSX / KS kernel extent along x / along y and z, RB bytes per smem row (= channels per K chunk * 2),
 // N = MMA N (output-channel tile), TX = x-slices (M tiles) per brick, G = taps per weight stage, S = weight stages.
 // HB = halo buffers (2 for the compute-heavy kernels, deeper for 1x1 where a work item is a few MMAs).
-template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB = 2, int SB = 2, int SR = 128, int EG = 2, int F = 1>
+// WD = 2 (split-operand mode, split_terms 2): the accumulator of an x-slice is 2 N columns wide -- the K block on the
+// activation term x0 multiplies the weight rows [w0 | w1] in ONE MMA of 2 N columns (the A operand, whose shared-memory
+// read bounds narrow tiles, is read once for two products), the K block on x1 multiplies w0 into the upper N columns;
+// the epilogue adds the two halves.
+template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB = 2, int SB = 2, int SR = 128, int EG = 2, int F = 1,
+          int WD = 1>
 struct TcCfg {
   static constexpr int kThreads = kTcBaseThreads + 128 * EG;
   // epilogue staging ring: SB slots of one x-slice (128 positions) x kStageRow bytes (one swizzled TMA-store box)
@@ -120,7 +126,8 @@ struct TcCfg {
   static constexpr int kTaps = KSX * KS * KZ;
   static constexpr int kGroups = kTaps / G;             // weight stages consumed per (brick, chunk)
   static constexpr int kTapBytes = N * kPosBytes;
-  static constexpr int kWBytes = G * kTapBytes;         // one stage = G consecutive taps
+  static constexpr int kWBytes = G * kTapBytes * WD;    // one stage = G consecutive taps (WD = 2: of up to 2 N rows each)
+  static constexpr int kAcc = N * WD;                   // accumulator columns of one x-slice
   static constexpr int kWStride = (kWBytes + 1023) / 1024 * 1024;
   static constexpr int kTapsPerLoad = largest_divisor_le(G, 256 / N);   // TMA box rows <= 256
   static constexpr int kLoads = G / kTapsPerLoad;
@@ -131,16 +138,17 @@ struct TcCfg {
   static constexpr uint32_t kLayout = RB == 128 ? kSwizzle128 : (RB == 64 ? kSwizzle64 : kSwizzle32);
   static constexpr uint32_t kLayoutW = kPosBytes == 128 ? kSwizzle128 : (kPosBytes == 64 ? kSwizzle64 : kSwizzle32);
   static_assert(F == 1 || ((KSX == KS || KSX == 1) && kPosBytes >= 32), "z-fold: same convolutions, one K chunk");
-  static_assert(2 * TX * N <= 512, "accumulators exceed TMEM");
+  static_assert(2 * TX * N * WD <= 512, "accumulators exceed TMEM");
+  static_assert(WD == 1 || WD == 2, "accumulator width factor");
   static_assert(kSmemBytes + 3072 <= 227 * 1024, "shared memory budget (dynamic + ~3 KB static)");
 };
 
-template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB, int SB, int SR, int EG, int F>
+template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB, int SB, int SR, int EG, int F, int WD>
 __global__ void __launch_bounds__(kTcBaseThreads + 128 * EG, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ TcStoreMaps maps_out, const __grid_constant__ TcStoreMaps maps_res,
                const TcConvParams p) {
-  using C = TcCfg<KSX, KS, RB, N, TX, G, S, HB, SB, SR, EG, F>;
+  using C = TcCfg<KSX, KS, RB, N, TX, G, S, HB, SB, SR, EG, F, WD>;
   constexpr int kWStages = S;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t halo_full[HB], halo_empty[HB], w_full[kWStages], w_empty[kWStages], acc_full[2], acc_empty[2];
@@ -235,15 +243,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
     uint32_t w = 0;
     for (int wi = wi_begin; wi < wi_end; wi += wi_step) {
       const int nt = wi % p.n_tiles;
+      int row = nt * p.w_rows_tile;            // rows are consumed in storage order: [chunk][tap][N (or 2 N) rows]
       for (int c = 0; c < p.n_chunks; ++c) {
+        const bool wide = WD == 2 && c < p.nc_block;       // K block 0 of the 2-block split mode: taps of 2 N rows
+        const int loads = wide ? 2 * C::kLoads : C::kLoads;
         for (int g = 0; g < C::kGroups; ++g, ++w) {
           const uint32_t st = w % kWStages;
           mbar_wait(&w_empty[st], ((w / kWStages) & 1) ^ 1);
-          mbar_arrive_expect_tx(&w_full[st], C::kWBytes);
+          mbar_arrive_expect_tx(&w_full[st], (uint32_t)loads * (C::kTapsPerLoad * C::kTapBytes));
 #pragma unroll 1
-          for (int l = 0; l < C::kLoads; ++l)
-            tma_load_2d(wbuf + st * C::kWStride + l * (C::kTapsPerLoad * C::kTapBytes), &map_w, &w_full[st], 0,
-                        (((nt * p.n_chunks + c) * C::kTaps + g * G) + l * C::kTapsPerLoad) * N);
+          for (int l = 0; l < loads; ++l, row += C::kTapsPerLoad * N)
+            tma_load_2d(wbuf + st * C::kWStride + l * (C::kTapsPerLoad * C::kTapBytes), &map_w, &w_full[st], 0, row);
         }
       }
     }
@@ -252,7 +262,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
     // The whole warp runs this loop (warp-uniform control flow and values); only the tcgen05.mma / commit
     // instructions are predicated on the elected lane.
     const int q = warp - 2;
-    const uint32_t idesc = make_idesc(kFmtBF16, 128, N);
+    const uint32_t idesc_n = make_idesc(kFmtBF16, 128, N), idesc_w = make_idesc(kFmtBF16, 128, N * WD);
     const uint64_t a_desc0 = make_smem_desc(smem_u32(halo), 0, C::HZ * RB, C::kLayout);
     const uint64_t b_desc0 = make_smem_desc(smem_u32(wbuf), 0, 8 * C::kPosBytes, C::kLayoutW);
     uint32_t u = 0, w = 0, it = 0;
@@ -278,38 +288,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
         uint32_t accum = c ? 1u : 0u;                              // first tap of the first chunk overwrites
         int dz = 0, dy = 0;
         uint32_t a_tap = a_lo0 + C::kE0 * kPos16;                  // start of the current tap's shifted window
-        for (int g = 0; g < C::kGroups; ++g, ++w) {
-          const uint32_t st = w % kWStages;
-          if (prof) t0 = clock64();
-          mbar_wait(&w_full[st], (w / kWStages) & 1);
-          if (prof) t_w += clock64() - t0;
-          tc_fence_after();
-          uint32_t b_lo = (uint32_t)b_desc0 + (uint32_t)((st * C::kWStride) >> 4);
+        // One K chunk.  WIDE (WD = 2 only, K block 0 = activation term x0): MMAs of 2 N columns over the weight rows
+        // [w0 | w1]; the other block (x1) adds its N columns onto the upper half, so that the small products
+        // x0 w1 + x1 w0 share one accumulator.  Compile-time so that descriptor steps stay immediates in the issue loop.
+        auto issue_chunk = [&](auto wide_tag) {
+          constexpr bool WIDE = decltype(wide_tag)::value;
+          const uint32_t idesc = WIDE ? idesc_w : idesc_n;
+          constexpr uint32_t d_off = (WD == 2 && !WIDE) ? (uint32_t)N : 0u;
+          constexpr uint32_t b_step = (uint32_t)((WIDE ? 2 * C::kTapBytes : C::kTapBytes) >> 4);
+          for (int g = 0; g < C::kGroups; ++g, ++w) {
+            const uint32_t st = w % kWStages;
+            if (prof) t0 = clock64();
+            mbar_wait(&w_full[st], (w / kWStages) & 1);
+            if (prof) t_w += clock64() - t0;
+            tc_fence_after();
+            uint32_t b_lo = (uint32_t)b_desc0 + (uint32_t)((st * C::kWStride) >> 4);
 #pragma unroll(G % C::KZ == 0 ? C::KZ : 1)
-          for (int j = 0; j < G; ++j) {
+            for (int j = 0; j < G; ++j) {
 #pragma unroll
-            for (int t = q; t < TX; t += C::kIssuers) {
-              const uint32_t a_lo = a_tap + (uint32_t)(t * C::HY * C::HZ) * kRow16;
-              const uint32_t d_tmem = tmem_base + (accbuf * TX + t) * N;
+              for (int t = q; t < TX; t += C::kIssuers) {
+                const uint32_t a_lo = a_tap + (uint32_t)(t * C::HY * C::HZ) * kRow16;
+                const uint32_t d_tmem = tmem_base + (accbuf * TX + t) * C::kAcc + d_off;
 #pragma unroll
-              for (int k = 0; k < C::kKSteps; ++k)
-                if (elect_one_sync()) mma_f16_ss_lohi(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k ? 1u : accum);
-            }
-            accum = 1u;
-            b_lo += (uint32_t)(C::kTapBytes >> 4);
-            // next tap: z fastest, then y, then x
-            a_tap += kPos16;
-            if (++dz == C::KZ) {
-              dz = 0;
-              a_tap += (uint32_t)C::HZ * kRow16 - (uint32_t)C::KZ * kPos16;
-              if (++dy == KS) {
-                dy = 0;
-                a_tap += (uint32_t)((C::HY - KS) * C::HZ) * kRow16;
+                for (int k = 0; k < C::kKSteps; ++k)
+                  if (elect_one_sync()) mma_f16_ss_lohi(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k ? 1u : accum);
+              }
+              accum = 1u;
+              b_lo += b_step;
+              // next tap: z fastest, then y, then x
+              a_tap += kPos16;
+              if (++dz == C::KZ) {
+                dz = 0;
+                a_tap += (uint32_t)C::HZ * kRow16 - (uint32_t)C::KZ * kPos16;
+                if (++dy == KS) {
+                  dy = 0;
+                  a_tap += (uint32_t)((C::HY - KS) * C::HZ) * kRow16;
+                }
               }
             }
+            if (elect_one_sync()) mma_commit(&w_empty[st]);
           }
-          if (elect_one_sync()) mma_commit(&w_empty[st]);
-        }
+        };
+        if (WD == 2 && c < p.nc_block) issue_chunk(std::integral_constant<bool, WD == 2>{});
+        else issue_chunk(std::false_type{});
         if (elect_one_sync()) mma_commit(&halo_empty[buf]);
       }
       if (elect_one_sync()) mma_commit(&acc_full[accbuf]);
@@ -419,7 +440,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
           for (int sc = 0; sc < NSC; ++sc, ++u) {
             const uint32_t b = u % SB;
             uint8_t* sbuf = gstage + b * C::kStageBytes;
-            const uint32_t taddr = tmem_base + lane_base + (accbuf * TX + t) * N + sc * COLS;
+            const uint32_t taddr = tmem_base + lane_base + (accbuf * TX + t) * C::kAcc + sc * COLS;
             uint32_t v[COLS];
             if constexpr (COLS >= 16) {
 #pragma unroll
@@ -430,6 +451,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
             long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
             if (prof) c0 = clock64();
             tmem_ld_wait();
+            if constexpr (WD == 2) {      // add the small-product accumulator (upper N columns)
+              uint32_t v2[COLS];
+              if constexpr (COLS >= 16) {
+#pragma unroll
+                for (int c = 0; c < COLS; c += 16) tmem_ld_x16(taddr + N + c, v2 + c);
+              } else {
+                tmem_ld_x8(taddr + N, v2);
+              }
+              tmem_ld_wait();
+#pragma unroll
+              for (int c = 0; c < COLS; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(v2[c]));
+            }
             if (prof) c1 = clock64();
             if (has_res) mbar_wait(&gres_full[b], (u / SB) & 1);
             if (prof) c2 = clock64();
@@ -556,7 +589,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
         for (int i = 0; i < 5; ++i) o[8 + i] = pe[i];
       }
     };
-    if constexpr (N == 16) {
+    if constexpr (N == 16 && WD == 1) {
       if (p.sa_ws != nullptr) {
         // ---- fused soft-argmax head: logits = scale * acc + shift never leave the SM
         // scratch carved out of this group's (unused) staging ring: coordinate tables, per-warp maxima and sums
@@ -666,7 +699,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
     }
     // ---- direct form (rows whose byte pitch is not a multiple of 16, e.g. the 1-channel float32 score volume)
     // (compiled for the N = 16 kernels only: that is where a 1- or 15-channel float32 head lands)
-    if constexpr (N == 16)
+    if constexpr (N == 16 && WD == 1)
     for (int wi = wi_begin; !p.tma_store && !p.sa_ws && wi < wi_end; wi += wi_step, ++it) {
       int n, x0, y0, z0, nt;
       item_coords(wi, n, x0, y0, z0, nt);
@@ -800,9 +833,9 @@ static CUtensorMapSwizzle swizzle_for(int rb) {
                    : (rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (rb == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
 }
 
-template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB, int SB, int SR, int EG, int F>
+template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB, int SB, int SR, int EG, int F, int WD>
 static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
-  using C = TcCfg<KSX, KS, RB, N, TX, G, S, HB, SB, SR, EG, F>;
+  using C = TcCfg<KSX, KS, RB, N, TX, G, S, HB, SB, SR, EG, F, WD>;
   EncodeTiledFn encode = get_encode();
   if (encode == nullptr) return SP3D_ERR_UNSUPPORTED;
   const int chunk_ch = C::kPosBytes / 2;
@@ -813,11 +846,13 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
   const bool split = a->algo == SP3D_CONV_TC_BF16X3;
   // term pairs (activation term, weight term) per K block, small products first:
   //   3 -> (1,0) (0,1) (0,0);   6 -> (2,0) (1,1) (0,2) (1,0) (0,1) (0,0)
-  const uint32_t block_act = !split ? 0u : (a->split_terms == 3 ? 0x001u : 0x001012u);
-  const int act_planes = !split ? 1 : (a->split_terms == 3 ? 2 : 3);
-  if (split && (a->head_softargmax != nullptr || (a->split_terms != 3 && a->split_terms != 6) || a->cin % chunk_ch ||
-                a->cin_pitch != a->cin))
+  //   2 -> x0 [w0 | w1] (2 N columns), x1 w0 (upper N columns): the 3 pairs in 2 K blocks (WD = 2 kernels)
+  const uint32_t block_act = !split ? 0u : (a->split_terms == 3 ? 0x001u : (a->split_terms == 2 ? 0x10u : 0x001012u));
+  const int act_planes = !split ? 1 : (a->split_terms == 6 ? 3 : 2);
+  if (split && (a->head_softargmax != nullptr || (a->split_terms != 2 && a->split_terms != 3 && a->split_terms != 6) ||
+                a->cin % chunk_ch || a->cin_pitch != a->cin))
     return SP3D_ERR_UNSUPPORTED;
+  if ((WD == 2) != (split && a->split_terms == 2)) return SP3D_ERR_UNSUPPORTED;
   const int n_chunks = nc_block * (split ? a->split_terms : 1);
   const int n_tiles = a->fused_phases ? (8 * a->cout) / N : (F > 1 ? 1 : (a->cout + N - 1) / N);
 
@@ -834,6 +869,7 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
   if (!tma_store && N != 16) return SP3D_ERR_UNSUPPORTED;   // the direct-store epilogue exists in the N = 16 kernels only
   if (fused && (!tma_store || a->cout_pitch != a->cout || (2 * a->cout * elt) % 128 || (8 * a->cout) % N)) return SP3D_ERR_UNSUPPORTED;
   if (pair_out && !tma_store) return SP3D_ERR_UNSUPPORTED;
+  if (WD == 2 && (!tma_store || a->head_softargmax != nullptr)) return SP3D_ERR_UNSUPPORTED;
   if (tma_store) {
     // output / residual viewed through the launch's output stride and offset (transposed-convolution phases):
     // [N][OD][OH][OW][cout_pitch] with scaled strides; box = one x-slice of the brick x one staged channel chunk.
@@ -883,7 +919,9 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
       return SP3D_ERR_INVALID_ARG;
   }
   {  // weights: [n_tiles * n_chunks * taps * N rows][chunk channels] bf16 (K-major rows), box = {chunk, taps_per_load * N}
-    cuuint64_t gdim[2] = {(cuuint64_t)chunk_ch, (cuuint64_t)C::kTaps * n_chunks * n_tiles * N};
+    // rows per channel tile: every chunk holds kTaps taps of N rows (2 N rows in the x0 block of the WD = 2 form)
+    const int64_t rows_tile = (int64_t)C::kTaps * N * (WD == 2 ? 3 * nc_block : n_chunks);
+    cuuint64_t gdim[2] = {(cuuint64_t)chunk_ch, (cuuint64_t)(rows_tile * n_tiles)};
     cuuint64_t gstr[1] = {(cuuint64_t)C::kPosBytes};
     cuuint32_t box[2] = {(cuuint32_t)chunk_ch, (cuuint32_t)(C::kTapsPerLoad * N)};
     cuuint32_t es[2] = {1, 1};
@@ -901,6 +939,7 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
   p.n_tiles = n_tiles;
   p.n_chunks = n_chunks;
   p.nc_block = nc_block;
+  p.w_rows_tile = C::kTaps * N * (WD == 2 ? 3 * nc_block : n_chunks);
   p.block_act = block_act;
   for (int d = 0; d < 3; ++d) {
     p.istride[d] = a->stride[d];
@@ -934,7 +973,7 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   }
-  auto kern = conv_tc_kernel<KSX, KS, RB, N, TX, G, S, HB, SB, SR, EG, F>;
+  auto kern = conv_tc_kernel<KSX, KS, RB, N, TX, G, S, HB, SB, SR, EG, F, WD>;
   {  // opt in to the large dynamic shared memory once per (kernel instance, device)
     static unsigned long long done_mask = 0;
     int dev = 0;
@@ -992,9 +1031,12 @@ int conv_tc(const sp3d_conv_args* a, cudaStream_t st) {
   if (cin >= 64 && (cin % 64)) return SP3D_ERR_UNSUPPORTED;
   if (a->cin_pitch < cin) return SP3D_ERR_INVALID_ARG;
   // (kernel x, kernel yz, row bytes, N, x-slices per brick, taps per weight stage, weight stages)
+  const int wd = (a->algo == SP3D_CONV_TC_BF16X3 && a->split_terms == 2) ? 2 : 1;
+#define SP3D_TC_CASE_W(KSX_, KS_, RB_, N_, TX_, G_, S_, HB_, SB_, SR_, EG_, F_, WD_) \
+  if (ksx == KSX_ && ks == KS_ && rb == RB_ && n == N_ && zf == F_ && wd == WD_) \
+    return launch_tc<KSX_, KS_, RB_, N_, TX_, G_, S_, HB_, SB_, SR_, EG_, F_, WD_>(a, st);
 #define SP3D_TC_CASE_F(KSX_, KS_, RB_, N_, TX_, G_, S_, HB_, SB_, SR_, EG_, F_) \
-  if (ksx == KSX_ && ks == KS_ && rb == RB_ && n == N_ && zf == F_) \
-    return launch_tc<KSX_, KS_, RB_, N_, TX_, G_, S_, HB_, SB_, SR_, EG_, F_>(a, st);
+  SP3D_TC_CASE_W(KSX_, KS_, RB_, N_, TX_, G_, S_, HB_, SB_, SR_, EG_, F_, 1)
 #define SP3D_TC_CASE(KSX_, KS_, RB_, N_, TX_, G_, S_, HB_, SB_, SR_, EG_) \
   SP3D_TC_CASE_F(KSX_, KS_, RB_, N_, TX_, G_, S_, HB_, SB_, SR_, EG_, 1)
   // (kernel x, kernel yz, row bytes, N, x-slices per brick, taps per weight stage, weight stages, halo buffers,
@@ -1030,8 +1072,14 @@ int conv_tc(const sp3d_conv_args* a, cudaStream_t st) {
   SP3D_TC_CASE(1, 2, 128, 128, 2, 2, 3, 2, 2, 128, 1)
   // 7x7/s2 stem on the 2x2 space-to-depth image (4x4 taps over 16 channels)
   SP3D_TC_CASE(1, 4, 32, 64, 4, 4, 3, 2, 2, 128, 2)
+  // split_terms 2 (3 term pairs in 2 K blocks, 2 N accumulator columns): the layers whose narrow channel tile leaves the
+  // tensor core waiting on the A operand -- 7^3 stems (z-folded, N = 32) and the 3^3 16 -> 32 layer at N = 32
+  SP3D_TC_CASE_W(7, 7, 64, 32, 4, 8, 2, 1, 2, 128, 1, 2, 2)
+  SP3D_TC_CASE_W(1, 7, 64, 32, 4, 8, 2, 2, 2, 128, 2, 2, 2)
+  SP3D_TC_CASE_W(3, 3, 64, 32, 4, 3, 3, 2, 2, 128, 2, 1, 2)
 #undef SP3D_TC_CASE
 #undef SP3D_TC_CASE_F
+#undef SP3D_TC_CASE_W
   return SP3D_ERR_UNSUPPORTED;
 }
 

@@ -225,6 +225,77 @@ static void rates(uint32_t layout, int row_bytes, int pitch_rows) {
       }
 }
 
+// ---------------------------------------------------------------------------------------------- mixed-layout SS rate
+// The z-folded stem reads A from 64-byte rows (SWIZZLE_64B, halo pitch 12) and B from 32-byte rows (SWIZZLE_32B).
+// Cycles per smem-sourced MMA for A fixed as in the stem and B in 32 / 64 / 128-byte rows, N = 32 .. 128, 2 issuers.
+template <int N>
+__global__ void __launch_bounds__(128) mixed_rate_kernel(uint32_t b_layout, uint32_t b_row_bytes, int issuers, int repeat,
+                                                         long long* __restrict__ cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar[4];
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t a_row = 64, a_pitch = 12;
+  const uint32_t a_bytes = (16 * a_pitch + 40) * a_row * 4, b_bytes = 8 * N * b_row_bytes;
+  for (uint32_t i = tid * 16; i < a_bytes + b_bytes + 2048; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmD = tmem_base + (uint32_t)warp * 128;
+  const uint32_t base = smem_u32(smem);
+  const uint32_t b_base = base + ((a_bytes + 1023) & ~1023u);
+  const uint32_t idesc = make_idesc(kFmtBF16, 128, N);
+  const uint64_t da = make_smem_desc(base + 3 * a_row, 0, a_pitch * a_row, kSwizzle64);
+  const uint64_t db = make_smem_desc(b_base, 0, 8 * b_row_bytes, b_layout);
+  if (warp < issuers) {
+    const long long t0 = clock64();
+    for (int r = 0; r < repeat; ++r) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)     // A: another x-slice / tap window per MMA (as the conv kernel), B: the next tap
+        if (elect_one_sync())
+          mma_f16_ss(tmD, da + (uint64_t)((j * 37 + warp * 264 * 4 + 1) * (32 >> 4)), db + (uint64_t)(j * (N * b_row_bytes >> 4)), idesc, 1u);
+    }
+    if (elect_one_sync()) mma_commit(&bar[warp]);
+    __syncwarp();
+    mbar_wait(&bar[warp], 0);
+    if (lane == 0) cycles[warp] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+template <int N>
+static void mixed_rates() {
+  CK(cudaFuncSetAttribute(mixed_rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  struct L { const char* name; uint32_t layout, row; } ls[] = {{"SW32/32B", kSwizzle32, 32}, {"SW64/64B", kSwizzle64, 64}, {"SW128/128B", kSwizzle128, 128}};
+  for (auto& l : ls) {
+    const int smem = (16 * 12 + 40) * 64 * 4 + 8 * N * (int)l.row + 4096;
+    if (smem > 220 * 1024) continue;
+    for (int issuers : {1, 2}) {
+      CK(cudaMemset(d_cyc, 0, 32));
+      mixed_rate_kernel<N><<<1, 128, smem, 0>>>(l.layout, l.row, issuers, 512, d_cyc);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("mixed rate kernel failed: %s\n", cudaGetErrorString(e)); exit(3); }
+      long long cyc[4];
+      CK(cudaMemcpy(cyc, d_cyc, 32, cudaMemcpyDeviceToHost));
+      long long mx = 0;
+      for (int i = 0; i < issuers; ++i) mx = cyc[i] > mx ? cyc[i] : mx;
+      printf("rate4 A=SW64/64B rows (halo pitch 12), B=%-10s N=%3d issuers=%d : %6.1f cycles per MMA per SM (model 32 + N/4 = %d)\n",
+             l.name, N, issuers, (double)mx / (512 * 8) / issuers, 32 + N / 4);
+    }
+  }
+}
+
 static uint16_t f2bf(float f) {
   uint32_t u;
   memcpy(&u, &f, 4);
@@ -336,6 +407,12 @@ int main() {
   CK(cudaMalloc(&d_out, 128 * 256 * 4));
   CK(cudaMalloc(&d_cyc, 32));
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  if (getenv("PROBE_MIXED")) {
+    mixed_rates<32>();
+    mixed_rates<64>();
+    mixed_rates<128>();
+    return 0;
+  }
   int fails = 0;
   fails += correctness("SW128 dense", kSwizzle128, 64, 32, 0, 8);
   fails += correctness("SW64 dense", kSwizzle64, 32, 32, 0, 8);

@@ -122,6 +122,11 @@ def float32_conv():
     return _F32_CONV
 
 
+# The 3-pair split mode evaluates x0 w0 + x0 w1 in one MMA of twice the columns where the kernel is instantiated for
+# the layer (include/sp3d.h, split_terms 2); SP3D_WIDE_SPLIT=0 switches that off (A/B measurements).
+_WIDE_SPLIT = os.environ.get("SP3D_WIDE_SPLIT", "1") != "0"
+
+
 def use_split():
     """True in the float32-faithful tensor-core mode with 3 term pairs: evaluation-mode nets keep their activations as
     ``SplitAct`` term pairs from layer to layer."""
@@ -435,15 +440,24 @@ SPLIT_PAIRS = {3: ((1, 0), (0, 1), (0, 0)), 6: ((2, 0), (1, 1), (0, 2), (1, 0), 
 
 def _tc_finish(full, terms):
     """float32 ``[n_tiles, n_chunks, taps, N, chunk]`` -> the bf16 tensor the kernel streams: as is (``terms`` 0), or
-    ``[n_tiles, K blocks, n_chunks, taps, N, chunk]`` with K block ``b`` = weight term of ``SPLIT_PAIRS[terms][b]``."""
+    ``[n_tiles, K blocks, n_chunks, taps, N, chunk]`` with K block ``b`` = weight term of ``SPLIT_PAIRS[terms][b]``;
+    ``terms`` 2 (the 3 pairs in two K blocks, include/sp3d.h): ``[n_tiles, rows, chunk]`` -- per tile the x0 block
+    ``[chunk][tap][w0 rows | w1 rows]`` followed by the x1 block ``[chunk][tap][w0 rows]``."""
     if not terms:
         return full.to(torch.bfloat16).contiguous()
+    if terms == 2:
+        w0, w1 = bf16_terms(full, 2)
+        nt, chunk = int(full.shape[0]), int(full.shape[-1])
+        wide = torch.cat([w0, w1], 3).reshape(nt, -1, chunk)
+        return torch.cat([wide, w0.reshape(nt, -1, chunk)], 1).to(torch.bfloat16).contiguous()
     wts = bf16_terms(full, max(wt for _, wt in SPLIT_PAIRS[terms]) + 1)
     return torch.stack([wts[wt] for _, wt in SPLIT_PAIRS[terms]], 1).to(torch.bfloat16).contiguous()
 
 
 # (kernel extent along x, along y / z, shared-memory row bytes, N = MMA columns, z-fold) of every conv_tc_kernel
 # instantiation in csrc/conv_tc.cu (the SP3D_TC_CASE list; tests/test_host_cpu.py keeps the two in step)
+# instantiations of the 2-K-block form of the 3-pair split mode (split_terms 2: accumulators of 2 N columns)
+TC_WIDE_CASES = frozenset({(7, 7, 64, 32, 2), (1, 7, 64, 32, 2), (3, 3, 64, 32, 1)})
 TC_CASES = frozenset({
     (7, 7, 32, 16, 1), (7, 7, 64, 32, 2), (3, 3, 64, 64, 2), (1, 7, 64, 32, 2), (3, 3, 128, 64, 2), (3, 3, 32, 32, 1),
     (3, 3, 64, 32, 1), (3, 3, 64, 64, 1), (3, 3, 128, 64, 1), (3, 3, 128, 128, 1), (3, 3, 64, 16, 1), (3, 3, 128, 32, 1),
@@ -980,19 +994,29 @@ class PackedConv:
         else:
             xk = x[0] if planes else x
         kw = dict(algo=algo, split_terms=terms, pair_out=pair_out)
+        tma_out = (out_pitch * (2 if pair_out or out_dtype == torch.bfloat16 else 4)) % 16 == 0
+
+        def wide(case):
+            """3 term pairs: take the 2-K-block form (``split_terms`` 2) where the kernel has it for this launch."""
+            return terms == 3 and _WIDE_SPLIT and tma_out and case in TC_WIDE_CASES
+
         if pitch == 16 and residual is None and self._tc_stack_ok(W, out_pitch):
             xs = stack_x_shifts(x.view(-1, D, H, W, pitch), 7, 3)       # every plane: [planes * N, ...]
-            conv_launch(xs[:N], self._tc_pack_stack(terms), self.scale, self.shift, None, outk, 16, self.cout, o, [1, 7, 7],
+            t = 2 if wide(tc_case([1, 7, 7], 16, 16 * self.ZFOLD, self.ZFOLD)) else terms
+            conv_launch(xs[:N], self._tc_pack_stack(t), self.scale, self.shift, None, outk, 16, self.cout, o, [1, 7, 7],
                         self.stride, [0, -3, -3], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu,
-                        cin_real=7, cout_pitch_w=16 * self.ZFOLD, zfold=self.ZFOLD, **kw)
+                        cin_real=7, cout_pitch_w=16 * self.ZFOLD, zfold=self.ZFOLD, **dict(kw, split_terms=t))
         elif not self.transposed and pitch == round_up(self.cin, 16) and self._tc_zfold_ok(W, out_pitch):
-            conv_launch(xk, self._tc_pack_zfold(terms), self.scale, self.shift, resk, outk, pitch, self.cout, o, self.k,
+            t = 2 if wide(tc_case(self.k, pitch, out_pitch * self.ZFOLD, self.ZFOLD)) else terms
+            conv_launch(xk, self._tc_pack_zfold(t), self.scale, self.shift, resk, outk, pitch, self.cout, o, self.k,
                         self.stride, [-p for p in self.padding], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu,
-                        cin_real=self.cin, cout_pitch_w=out_pitch * self.ZFOLD, zfold=self.ZFOLD, **kw)
+                        cin_real=self.cin, cout_pitch_w=out_pitch * self.ZFOLD, zfold=self.ZFOLD, **dict(kw, split_terms=t))
         elif not self.transposed:
-            conv_launch(xk, packs[0], self.scale, self.shift, resk, outk, cin_tc, self.cout, o, self.k, self.stride,
+            t = 2 if wide(tc_case(self.k, cin_tc, n)) else terms
+            wgt = packs[0] if t == terms else self._tc_pack(2)[0][0]
+            conv_launch(xk, wgt, self.scale, self.shift, resk, outk, cin_tc, self.cout, o, self.k, self.stride,
                         [-p for p in self.padding], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu,
-                        cin_real=self.cin, cout_pitch_w=n, **kw)
+                        cin_real=self.cin, cout_pitch_w=n, **dict(kw, split_terms=t))
         elif self._tc_fused_ok(out_pitch, "pair" if pair_out else out_dtype):
             conv_launch(xk, self._tc_pack_fused(terms), self.scale, self.shift, resk, outk, cin_tc, self.cout, (D, H, W),
                         [1, 1, 1], [1, 1, 1], [0, 0, 0], [1, 1, 1], self.stride, [0, 0, 0], self.relu, cin_real=self.cin,

@@ -290,8 +290,20 @@ def emulate_split_launch(x, weight, scale, shift, residual, out, cin, cout, out_
     b multiplies activation plane SPLIT_PAIRS[b][0] with weight block b, all blocks accumulate into one GEMM -- i.e.
     the plain tensor-core launch on the K-concatenated operands.  `pair_out` (out_dtype SP3D_BF16X2): `out` and
     `residual` are plane 0 of two-plane bf16 tensors holding float32 values as term pairs."""
-    assert algo == 2 and split_terms in (3, 6)
-    pairs = ops.SPLIT_PAIRS[split_terms]
+    assert algo == 2 and split_terms in (2, 3, 6)
+    if split_terms == 2:
+        # the 3 pairs in two K blocks: per tile [chunk][tap][w0 rows | w1 rows] then [chunk][tap][w0 rows]
+        nt, rows, chunk = weight.shape
+        n, nc = cout_pitch_w, cin // chunk
+        taps = rows // (3 * n * nc)
+        assert rows == 3 * n * nc * taps and cin == nc * chunk
+        wide = weight[:, :2 * n * nc * taps].reshape(nt, nc, taps, 2 * n, chunk)
+        narrow = weight[:, 2 * n * nc * taps:].reshape(nt, nc, taps, n, chunk)
+        assert torch.equal(wide[:, :, :, :n], narrow)
+        weight = torch.stack([wide[:, :, :, :n], wide[:, :, :, n:], narrow], 1)      # K blocks x0 w0, x0 w1, x1 w0
+        pairs = ((0, 0), (0, 1), (1, 0))
+    else:
+        pairs = ops.SPLIT_PAIRS[split_terms]
     nt, kb, nc, taps, n, chunk = weight.shape
     assert kb == len(pairs) and cin == nc * chunk and x.shape[-1] == cin
 
@@ -302,7 +314,7 @@ def emulate_split_launch(x, weight, scale, shift, residual, out, cin, cout, out_
     xcat = torch.cat([planes[a] for a, _ in pairs], -1)
     target = out
     if pair_out:
-        assert split_terms == 3 and out.dtype == torch.bfloat16 and out.is_contiguous()
+        assert split_terms in (2, 3) and out.dtype == torch.bfloat16 and out.is_contiguous()
         out_planes = planes_of(out, 2)
         target = out_planes[0].float() + out_planes[1].float()      # other phases' results stay what they are
         if residual is not None:
@@ -375,9 +387,16 @@ def test_split_operand_lowering(monkeypatch, case, terms, tol):
         pc = ops.PackedConv(ct.float().weight, None, bn.float(), 2, 1, transposed=True, relu=1)
         nd, cout = 2, 256
     assert pc.tc_supported()
+    seen = []
+    monkeypatch.setattr(ops, "conv_launch", lambda *a, **k: (seen.append(k.get("split_terms")), emulate_split_launch(*a, **k))[1])
     got = cf(pc(cl(x), residual=None if res is None else cl(res)), cout, nd).double()
     err = float((got - want).abs().max()) / float(want.abs().max())
     assert err <= tol, err
+    # the stems take the 2-K-block form of the 3-pair mode (split_terms 2) where the kernel is instantiated for it
+    if terms == 3 and case in ("3d_k7_zfold", "3d_k7_stack"):
+        assert seen == [2], seen
+    else:
+        assert all(t == terms for t in seen), seen
 
 
 # ---------------------------------------------------------------------------------------------- input gradients
