@@ -24,7 +24,8 @@ extern "C" {
 #endif
 
 #define SP3D_ABI_VERSION 3   /* 2: sp3d_conv_args.split_terms, sp3d_split_bf16, the backward operators;
-                                3: SP3D_BF16X2 activations, sp3d_merge_bf16, sp3d_s2d_args.dst_dtype, sp3d_gauss_render_* */
+                                3: SP3D_BF16X2 activations, sp3d_merge_bf16, sp3d_s2d_args.dst_dtype, sp3d_gauss_render_*,
+                                   split_terms 2, sp3d_target_heatmaps / sp3d_target_volume */
 #define SP3D_MAX_VIEWS 8
 #define SP3D_CAM_FLOATS 32
 
@@ -419,6 +420,47 @@ typedef struct {
   float* grad_kps;              /* [V, B, P, J, 2]; written (rows beyond n_people get zeros) */
 } sp3d_gauss_render_bwd_args;
 int sp3d_gauss_render_bwd(const sp3d_gauss_render_bwd_args* a, void* stream);
+
+/* ==========================================================================================
+ * Training targets on the device: what the reference's DataLoader workers render with
+ * numpy per item, lib/dataset/JointsDataset.py:237-341.
+ * ========================================================================================== */
+
+/* generate_target_heatmap (:237-302): per (item, joint) the pixel-wise MAXIMUM over the item's people of a sigma-wide
+ * Gaussian centred on the TRUNCATED heat-map pixel  mu = int(joint / feat_stride)  and cut to the (2 * 3 sigma + 1)^2
+ * window around it; joints with vis == 0 and people without any visible joint are skipped; target_weight[j] = 1 when
+ * any person shows joint j.  `window` is the reference's own Gaussian window  g[dy][dx] = exp(-((dx - r)^2 + (dy - r)^2)
+ * / (2 sigma^2)), r = 3 sigma, as float32 [2r+1][2r+1] (evaluated once on the host with numpy, so that the device
+ * result is bit-identical to the reference's). */
+typedef struct {
+  const double* joints;     /* [n_items, P, J, jstride] float64 as the dataset holds them: x, y (network-input pixels) */
+  const double* joints_vis; /* [n_items, P, J, vstride]: visibility in [..][0] */
+  const int32_t* n_people;  /* [n_items] people per item (<= P) */
+  int n_items, P, J, jstride, vstride;
+  int h, w;                 /* heat-map extent */
+  double stride_x, stride_y; /* feat_stride = image_size / heatmap_size (float64 division, as numpy's) */
+  const float* window;      /* [2r+1][2r+1] */
+  int radius;               /* r = int(3 sigma) */
+  float* target;            /* [n_items, J, h, w] */
+  float* target_weight;     /* [n_items, J] */
+} sp3d_target_heatmaps_args;
+int sp3d_target_heatmaps(const sp3d_target_heatmaps_args* a, void* stream);
+
+/* generate_3d_target (:304-341): per item the voxel-wise maximum over the people of  exp(-|g - mu|^2 / (2 sigma^2))
+ * (float64, as numpy evaluates it; stored as float32) on the voxels with |g_axis - mu_axis| <= 3 sigma on every axis,
+ * where g are the np.linspace voxel centres (given as three float64 vectors) and mu the person's root. */
+typedef struct {
+  const double* roots;      /* [n_items, P, 3] world mm */
+  const int32_t* n_people;  /* [n_items] */
+  int n_items, P;
+  const double* grid_x;     /* [X] np.linspace(-size/2, size/2, X) + centre */
+  const double* grid_y;     /* [Y] */
+  const double* grid_z;     /* [Z] */
+  int X, Y, Z;
+  double sigma;             /* reference: 200 mm */
+  float* target;            /* [n_items, X, Y, Z] */
+} sp3d_target_volume_args;
+int sp3d_target_volume(const sp3d_target_volume_args* a, void* stream);
 
 #ifdef __cplusplus
 }

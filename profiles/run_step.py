@@ -19,7 +19,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=bench.BATCH)
 ap.add_argument("--proposals", type=int, default=bench.PROPOSALS)
 ap.add_argument("--warmup", type=int, default=1)
-ap.add_argument("--volume-dtype", default="bf16", choices=["bf16", "f32"])
+ap.add_argument("--volume-dtype", default="f32", choices=["bf16", "f32"], help="f32 = the default float32-faithful tensor-core mode (bf16 term pairs)")
 a = ap.parse_args()
 
 from selfpose3d_b200 import ops  # noqa: E402

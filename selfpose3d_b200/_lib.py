@@ -186,6 +186,19 @@ class GaussRenderBwdArgs(C.Structure):
     _fields_ = [("fwd", GaussRenderArgs), ("grad_heatmaps", C.c_void_p), ("grad_kps", C.c_void_p)]
 
 
+class TargetHeatmapsArgs(C.Structure):
+    _fields_ = [("joints", C.c_void_p), ("joints_vis", C.c_void_p), ("n_people", C.c_void_p),
+                ("n_items", C.c_int), ("P", C.c_int), ("J", C.c_int), ("jstride", C.c_int), ("vstride", C.c_int),
+                ("h", C.c_int), ("w", C.c_int), ("stride_x", C.c_double), ("stride_y", C.c_double),
+                ("window", C.c_void_p), ("radius", C.c_int), ("target", C.c_void_p), ("target_weight", C.c_void_p)]
+
+
+class TargetVolumeArgs(C.Structure):
+    _fields_ = [("roots", C.c_void_p), ("n_people", C.c_void_p), ("n_items", C.c_int), ("P", C.c_int),
+                ("grid_x", C.c_void_p), ("grid_y", C.c_void_p), ("grid_z", C.c_void_p),
+                ("X", C.c_int), ("Y", C.c_int), ("Z", C.c_int), ("sigma", C.c_double), ("target", C.c_void_p)]
+
+
 # every symbol include/sp3d.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "sp3d_abi_version": (C.c_int, []),
@@ -217,6 +230,8 @@ SYMBOLS = {
     "sp3d_relu_bwd": (C.c_int, [C.POINTER(ReluBwdArgs), C.c_void_p]),
     "sp3d_gauss_render_fwd": (C.c_int, [C.POINTER(GaussRenderArgs), C.c_void_p]),
     "sp3d_gauss_render_bwd": (C.c_int, [C.POINTER(GaussRenderBwdArgs), C.c_void_p]),
+    "sp3d_target_heatmaps": (C.c_int, [C.POINTER(TargetHeatmapsArgs), C.c_void_p]),
+    "sp3d_target_volume": (C.c_int, [C.POINTER(TargetVolumeArgs), C.c_void_p]),
 }
 
 _lib = None

@@ -58,7 +58,9 @@ def render_gaussians(kps_views, xx, yy):
     """Joint pixels -> heat-maps (reference :410-448): per (view, sample) a Gaussian of sigma 3 heat-map pixels around
     every person's joint, summed over the people and clipped to [0, 1].  ``kps_views``: list over views of lists over
     samples of ``[P_b, J, 2]``; ``xx, yy``: ``[1,1,h,w]`` pixel-index grids.  Returns ``[V, B, J, h, w]``."""
-    if os.environ.get("SP3D_RENDER_KERNEL") == "1":       # opt-in until its first B200 run: the fused rendering kernel
+    # the fused rendering kernel (sp3d_gauss_render_fwd / _bwd) on the device; the tensor expression below is what the
+    # CPU wiring tests (kernels emulated) evaluate, and SP3D_RENDER_KERNEL=0 keeps it for A/B checks
+    if kps_views[0][0].is_cuda and os.environ.get("SP3D_RENDER_KERNEL", "1") != "0":
         return _render_gaussians_kernel(kps_views, xx)
     views = []
     for kps_samples in kps_views:
@@ -91,26 +93,42 @@ def hungarian_l1(kps_views, meta, width, height, drop_worst):
     :155-194): per (view, sample) the summed cost of the Hungarian matching between the re-projected people and the
     pseudo 2-D poses ``meta[v]['joints']`` (people whose joints are all zero are padding), coordinates normalised by
     the network-input size; mean over (view, sample), or -- ``drop_worst`` (``L1_ATTN``) -- the mean without the
-    largest entry."""
+    largest entry.
+
+    The reference synchronises with the host once per (view, sample) (``d_matrix.cpu()`` at :182).  Here all ``V * B``
+    cost matrices are built on the device in one padded ``[V*B, G, P]`` tensor, cross to the host in ONE copy, are
+    assigned there (``scipy.optimize.linear_sum_assignment``, a few people per matrix), and the matched entries are
+    gathered back with one index tensor."""
     from scipy.optimize import linear_sum_assignment
     V, B = len(meta), len(kps_views[0])
     dev = kps_views[0][0].device
     size = torch.tensor([float(width), float(height)], device=dev)
-    per = []
-    for v in range(V):
-        for b in range(B):
-            joints = meta[v]["joints"][b].to(dev)
-            n_gt = int((joints.sum(-1).sum(-1) != 0).sum())
-            pred = kps_views[v][b]
-            if n_gt == 0 or pred.shape[0] == 0:
-                per.append(torch.zeros((), device=dev))
-                continue
-            target = joints[:n_gt] / size.to(joints.dtype)
-            vis = meta[v]["joints_vis"][b][:n_gt].to(dev)
-            cost = (((pred / size)[None] - target[:, None]) * vis[:, None]).abs().mean((-1, -2)).to(torch.float32)  # [G,P]
-            rows, cols = linear_sum_assignment(cost.detach().cpu().numpy())
-            per.append(cost[torch.as_tensor(rows, device=dev), torch.as_tensor(cols, device=dev)].sum())
-    per = torch.stack(per)
+    joints = torch.stack([meta[v]["joints"].to(dev) for v in range(V)])                 # [V, B, G, J, 2]
+    vis = torch.stack([meta[v]["joints_vis"].to(dev) for v in range(V)])                # [V, B, G, J, 2]
+    G = int(joints.shape[2])
+    n_pred = [int(kp.shape[0]) for kp in kps_views[0]]                                  # people per sample (same in every view)
+    P = max(max(n_pred), 1)
+    J = int(joints.shape[3])
+    pred = torch.stack([torch.stack([torch.cat([kp, kp.new_zeros(P - kp.shape[0], J, 2)], 0) for kp in samples])
+                        for samples in kps_views])                                      # [V, B, P, J, 2]
+    target = joints / size.to(joints.dtype)
+    cost = (((pred / size)[:, :, None] - target[:, :, :, None]) * vis[:, :, :, None]).abs().mean((-1, -2)).to(torch.float32)
+    cost = cost.reshape(V * B, G, P)                                                    # [V*B, G, P]
+    n_gt = (joints.sum(-1).sum(-1) != 0).sum(-1).reshape(V * B)                         # pseudo people per (view, sample)
+    host_cost, host_gt = cost.detach().cpu().numpy(), n_gt.cpu().numpy()                # the one device -> host copy
+    idx_m, idx_r, idx_c = [], [], []
+    for m in range(V * B):
+        g, p_ = int(host_gt[m]), n_pred[m % B]
+        if g == 0 or p_ == 0:
+            continue
+        rows, cols = linear_sum_assignment(host_cost[m, :g, :p_])
+        idx_m += [m] * len(rows)
+        idx_r += rows.tolist()
+        idx_c += cols.tolist()
+    per = torch.zeros(V * B, device=dev)
+    if idx_m:
+        sel = torch.tensor([idx_m, idx_r, idx_c], device=dev)
+        per = per.index_add(0, sel[0], cost[sel[0], sel[1], sel[2]])
     if drop_worst:
         keep = torch.ones_like(per)
         keep[torch.argmax(per)] = 0.0

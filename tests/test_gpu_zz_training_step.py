@@ -227,3 +227,43 @@ def test_gauss_render_kernels_vs_autograd():
     assert float((got.cpu().double() - want).abs().max()) <= 1e-5
     ref = kps.grad * mask[None, :, :, None, None]
     assert float((kd.grad.cpu().double() - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
+
+
+def test_synthetic_root_step_matches_reference_on_gpu(golden):
+    """``CuboidProposalNetSoft`` with ``ROOTNET_TRAIN_SYNTH`` in ``.train()`` (reference
+    ``lib/models/cuboid_proposal_net_soft.py:151-241``) through the kernels: the random roots are drawn in the
+    reference's order on the host RNG, so with the same torch seed the target volume, the synthetic and the real score
+    volumes, the proposals and the parameter gradients equal the step recorded from the unmodified reference
+    (ssl_step.npz, keys ``syn_*``) -- CPU twin: tests/test_training_cpu.py::test_synthetic_root_step_matches_reference."""
+    import os
+    import sys
+    import torch.nn.functional as F
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_ssl as gen
+    from selfpose3d_b200.models import cuboid_proposal_net_soft
+    gs = golden("ssl_step")
+    cfg = gen.configure(default_config())
+    cfg.NETWORK.IMAGE_SIZE, cfg.NETWORK.HEATMAP_SIZE = list(gen.IMAGE), list(gen.HEATMAP)
+    cfg.NETWORK.ROOTNET_TRAIN_SYNTH = True
+    net = cuboid_proposal_net_soft.CuboidProposalNetSoft(cfg)
+    net.load_state_dict(synthetic.trained_like_state_dict(net, seed=int(gs["syn_seed"])), strict=True)
+    net = net.to(DEV).train()
+    (_, meta, targets), _, _ = gen.ssl_case()
+    torch.manual_seed(gen.SYNTH_TORCH_SEED)
+    main, syn, target, gc = net([t.to(DEV) for t in targets], meta, flip_xcoords=meta[0]["hflip"])
+    (100.0 * F.mse_loss(syn, target)).backward()
+    np.testing.assert_allclose(target.cpu().numpy(), gs["syn_target"], rtol=0, atol=1e-6)
+    for got, key in ((main, "syn_main"), (syn, "syn_cubes")):
+        np.testing.assert_allclose(got.detach().cpu().numpy(), gs[key], rtol=0, atol=1e-4 * np.abs(gs[key]).max(), err_msg=key)
+    np.testing.assert_allclose(gc.detach().cpu().numpy(), gs["syn_grid_centers"], rtol=1e-4, atol=1e-3)
+    params = dict(net.named_parameters())
+    top = float(gs["syn_param_grad_norm"].max())
+    checked = 0
+    for name, norm in zip(gs["syn_param_names"], gs["syn_param_grad_norm"]):
+        gn = float(params[str(name)].grad.double().norm())
+        if norm < 1e-5 * top:
+            assert gn < 1e-3 * top, (name, gn, norm)
+            continue
+        assert abs(gn - norm) <= 1e-2 * norm, (name, gn, norm)
+        checked += 1
+    assert checked >= 40, checked

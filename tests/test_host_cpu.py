@@ -155,6 +155,7 @@ def test_ctypes_struct_layouts_match_the_c_header(tmp_path):
         "sp3d_conv_wgrad_args": _lib.ConvWgradArgs, "sp3d_bn_stats_args": _lib.BnStatsArgs,
         "sp3d_bn_apply_args": _lib.BnApplyArgs, "sp3d_bn_bwd_args": _lib.BnBwdArgs, "sp3d_relu_bwd_args": _lib.ReluBwdArgs,
         "sp3d_gauss_render_args": _lib.GaussRenderArgs, "sp3d_gauss_render_bwd_args": _lib.GaussRenderBwdArgs,
+        "sp3d_target_heatmaps_args": _lib.TargetHeatmapsArgs, "sp3d_target_volume_args": _lib.TargetVolumeArgs,
     }
     header = open(os.path.join(ROOT, "include", "sp3d.h")).read()
     declared = set(re.findall(r"}\s*(sp3d_[a-z0-9_]+_args)\s*;", header))
@@ -182,3 +183,10 @@ def test_tc_case_table_matches_the_kernel_instantiations():
         cases.add((v[0], v[1], v[2], v[3], v[11] if m.group(1) else 1))
     assert len(cases) >= 20
     assert cases == set(ops.TC_CASES), cases ^ set(ops.TC_CASES)
+    # the 2-K-block form of the 3-pair split mode (WD = 2 instantiations) against ops.TC_WIDE_CASES
+    wide = set()
+    for m in re.finditer(r"^\s*SP3D_TC_CASE_W\(([\d,\s]+)\)\s*$", body, flags=re.M):
+        v = [int(t) for t in m.group(1).split(",")]
+        assert v[12] == 2
+        wide.add((v[0], v[1], v[2], v[3], v[11]))
+    assert wide == set(ops.TC_WIDE_CASES), wide ^ set(ops.TC_WIDE_CASES)

@@ -233,3 +233,21 @@ def test_v2v_training_oracle_matches_reference_step(golden):
         g = sd[str(name)].grad.double()
         assert abs(float(g.norm()) - norm) <= 1e-3 * max(norm, 1e-3), name
         assert abs(float(g.sum()) - tot) <= 1e-3 * max(norm, 1e-3) * max(1.0, np.sqrt(g.numel())), name
+
+
+def test_target_generation_oracle_matches_reference_golden(golden):
+    """oracle/targets.py (JointsDataset.generate_target_heatmap / generate_3d_target restated) against the vectors
+    recorded from the unmodified reference (tests/golden/make_golden_targets.py)."""
+    from oracle import targets
+    g = golden("targets")
+    for i, n in enumerate(g["counts"]):
+        n = int(n)
+        if n:
+            t, w = targets.target_heatmap([g["joints"][i, p] for p in range(n)], [g["joints_vis"][i, p] for p in range(n)],
+                                          g["image_size"], g["heatmap_size"], sigma=3)
+            assert np.array_equal(t, g["target"][i]) and np.array_equal(w, g["weight"][i])
+        else:
+            assert not g["target"][i].any() and not g["weight"][i].any()
+        v = targets.target_volume(g["roots"][i, :n], g["space_size"], g["space_center"], [int(c) for c in g["cube_size"]])
+        assert np.array_equal(v, g["volume"][i])
+    assert g["target"].max() == 1.0 and g["volume"].max() > 0.5

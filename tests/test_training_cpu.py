@@ -178,6 +178,7 @@ def test_ssl_training_step_matches_reference(emulated, monkeypatch, golden):  # 
     from selfpose3d_b200.models import multi_person_posenet_ssv
     monkeypatch.setattr(ag, "Unproject", _Apply(emul_unproject))
     monkeypatch.setattr(ag, "SoftArgmax", _Apply(emul_softargmax))
+    monkeypatch.setattr(ag, "RenderGaussians", _Apply(emul_render))       # sp3d_gauss_render_fwd (+ autograd for _bwd)
     monkeypatch.setattr(ops, "nms_topk", emul_nms_topk)
     monkeypatch.setattr(ops, "unproject", emul_unproject_op)
     monkeypatch.setattr(ops, "maxpool", _maxpool_any)
@@ -306,6 +307,7 @@ def apply_emulation_in_this_process():
                      ("bn_bwd", T._bn_bwd), ("relu_bwd", T._relu_bwd), ("conv_wgrad", T._conv_wgrad_any)):
         setattr(grad_ops, name, fn)
     ag.Unproject, ag.SoftArgmax = _Apply(emul_unproject), _Apply(emul_softargmax)
+    ag.RenderGaussians = _Apply(emul_render)
     torch.Tensor.cuda = lambda self, *a, **k: self
     torch.Tensor.is_cuda = property(lambda self: True)
 
