@@ -229,7 +229,7 @@ def test_gauss_render_kernels_vs_autograd():
     assert float((kd.grad.cpu().double() - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
 
 
-def test_synthetic_root_step_matches_reference_on_gpu(golden):
+def test_synthetic_root_step_matches_reference_on_gpu(golden, monkeypatch):
     """``CuboidProposalNetSoft`` with ``ROOTNET_TRAIN_SYNTH`` in ``.train()`` (reference
     ``lib/models/cuboid_proposal_net_soft.py:151-241``) through the kernels: the random roots are drawn in the
     reference's order on the host RNG, so with the same torch seed the target volume, the synthetic and the real score
@@ -249,6 +249,10 @@ def test_synthetic_root_step_matches_reference_on_gpu(golden):
     net.load_state_dict(synthetic.trained_like_state_dict(net, seed=int(gs["syn_seed"])), strict=True)
     net = net.to(DEV).train()
     (_, meta, targets), _, _ = gen.ssl_case()
+    # the heat-map noise is drawn with randn_like on the maps' device; the recorded step drew it from the host
+    # generator, so the test routes every randn_like through the host RNG (same seed -> same noise, same draw order)
+    host_randn_like = torch.randn_like
+    monkeypatch.setattr(torch, "randn_like", lambda t, **k: host_randn_like(t.cpu(), **k).to(t.device))
     torch.manual_seed(gen.SYNTH_TORCH_SEED)
     main, syn, target, gc = net([t.to(DEV) for t in targets], meta, flip_xcoords=meta[0]["hflip"])
     (100.0 * F.mse_loss(syn, target)).backward()
