@@ -186,6 +186,14 @@ class GaussRenderBwdArgs(C.Structure):
     _fields_ = [("fwd", GaussRenderArgs), ("grad_heatmaps", C.c_void_p), ("grad_kps", C.c_void_p)]
 
 
+class ConvWgradTcArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("grad_out", C.c_void_p),
+                ("N", C.c_int), ("X", C.c_int), ("Y", C.c_int), ("Z", C.c_int),
+                ("cin", C.c_int), ("x_pitch", C.c_int), ("cout", C.c_int), ("g_pitch", C.c_int), ("k", C.c_int),
+                ("grad_weight", C.c_void_p), ("gw_cin", C.c_int), ("gw_pitch", C.c_int), ("grad_bias", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
+
+
 class TargetHeatmapsArgs(C.Structure):
     _fields_ = [("joints", C.c_void_p), ("joints_vis", C.c_void_p), ("n_people", C.c_void_p),
                 ("n_items", C.c_int), ("P", C.c_int), ("J", C.c_int), ("jstride", C.c_int), ("vstride", C.c_int),
@@ -230,6 +238,8 @@ SYMBOLS = {
     "sp3d_relu_bwd": (C.c_int, [C.POINTER(ReluBwdArgs), C.c_void_p]),
     "sp3d_gauss_render_fwd": (C.c_int, [C.POINTER(GaussRenderArgs), C.c_void_p]),
     "sp3d_gauss_render_bwd": (C.c_int, [C.POINTER(GaussRenderBwdArgs), C.c_void_p]),
+    "sp3d_conv_wgrad_tc": (C.c_int, [C.POINTER(ConvWgradTcArgs), C.c_void_p]),
+    "sp3d_conv_wgrad_tc_workspace": (C.c_int64, [C.POINTER(ConvWgradTcArgs)]),
     "sp3d_target_heatmaps": (C.c_int, [C.POINTER(TargetHeatmapsArgs), C.c_void_p]),
     "sp3d_target_volume": (C.c_int, [C.POINTER(TargetVolumeArgs), C.c_void_p]),
 }

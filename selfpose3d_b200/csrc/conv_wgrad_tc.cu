@@ -1,0 +1,371 @@
+// Weight gradient of the 3-D "same" convolutions on tcgen05 (training path).
+//
+//   dW[tap, ci, co] = sum over positions p of  x[p + off(tap), ci] * dy[p, co]
+//
+// contracts over POSITIONS, so both operands have to be K-major in the position index.  Two steps:
+//
+//  1. wgrad_prep_kernel turns the channel-last float32 tensors into channel-FIRST bf16 term planes (x = hi + lo, as
+//     the split-operand forward convolution uses them): every (cube, channel, x, y) owns a contiguous z-line.  For x,
+//     one copy per z tap (the line shifted by dz, zero outside) so that a z tap never is a sub-16-byte shift; dx / dy
+//     taps are whole-line offsets.  The dy pass also sums the bias gradient.
+//  2. wgrad_tc_kernel is a plain tcgen05 GEMM over K blocks = pieces of z-lines.  Its A tile [128 rows][KB positions]
+//     is ASSEMBLED BY TMA: rows are (tap, ci) -- 128 / ci taps per tile, each tap one box [ci rows][KB] of the matching
+//     shifted copy at (x + dx, y + dy), out-of-range lines zero-filled by TMA (= the convolution's padding).  B =
+//     [dy_hi rows | dy_lo rows].  Per A tile and K step: one MMA of 2 co columns (x_hi * [dy_hi | dy_lo]) and one of
+//     co columns (x_lo * dy_hi, onto the upper half) -- the three term pairs of the float32-faithful mode.  Every
+//     (tap-tile) keeps its own TMEM accumulator for the whole launch; tap tiles that do not fit 512 columns go to other
+//     CTAs (grid.y); the K blocks are split over grid.x; results are added into dW with float atomics at the end.
+//
+// Replaces the autograd weight gradient of nn.Conv3d in lib/models/v2v_net.py:10-45,124 (cudnn wgrad in the reference).
+#include "sp3d_common.cuh"
+#include "tc_common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <string.h>
+
+namespace sp3d {
+
+using namespace tc;
+
+// ------------------------------------------------------------------------------------------------ operand prep
+// src: float32 channel-last [lines = N*X*Y][Z][pitch] (C channels used).  dst: bf16 [2 planes][copies][N][Cp][X*Y*Z]
+// with copy j holding the z-line shifted by (j - pad): dst[.., z] = src[.., z + j - pad] (zero outside [0, Z)).
+// CTAs walk the z-lines grid-stride; bias: per-channel sums of src, one atomic per channel and CTA (dy pass only).
+__global__ void __launch_bounds__(256) wgrad_prep_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                         int N, int XY, int Z, int C, int Cp, int pitch, int copies, int pad,
+                                                         float* __restrict__ bias) {
+  extern __shared__ float tile[];          // [Z][C + 1]
+  const int cs = C + 1;
+  const int zg = Z / 8;                    // 16-byte groups of 8 positions
+  const int64_t plane = (int64_t)copies * N * Cp * XY * Z;
+  float bsum = 0.0f;                       // thread c < C: running sum of channel c
+  for (int line = blockIdx.x; line < N * XY; line += gridDim.x) {
+    const int n = line / XY, xy = line % XY;
+    const float* s = src + (int64_t)line * Z * pitch;
+    __syncthreads();                       // the previous line's readers are done with the tile
+    for (int i = threadIdx.x; i < Z * pitch; i += blockDim.x) {
+      const int z = i / pitch, c = i % pitch;
+      if (c < C) tile[z * cs + c] = __ldg(s + i);
+    }
+    __syncthreads();
+    if (bias != nullptr && (int)threadIdx.x < C) {
+      for (int z = 0; z < Z; ++z) bsum += tile[z * cs + threadIdx.x];
+    }
+    for (int i = threadIdx.x; i < copies * Cp * zg; i += blockDim.x) {
+      const int g = i % zg, c = (i / zg) % Cp, j = i / (zg * Cp);
+      __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int z = g * 8 + q + j - pad;
+        const float v = (c < C && z >= 0 && z < Z) ? tile[z * cs + c] : 0.0f;
+        hi[q] = __float2bfloat16_rn(v);
+        lo[q] = __float2bfloat16_rn(v - __bfloat162float(hi[q]));
+      }
+      const int64_t o = ((((int64_t)j * N + n) * Cp + c) * XY + xy) * Z + g * 8;
+      *reinterpret_cast<uint4*>(dst + o) = *reinterpret_cast<const uint4*>(hi);
+      *reinterpret_cast<uint4*>(dst + plane + o) = *reinterpret_cast<const uint4*>(lo);
+    }
+  }
+  if (bias != nullptr && (int)threadIdx.x < C) atomicAdd(bias + threadIdx.x, bsum);
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM
+struct WgradParams {
+  int N, X, Y, Z, k, pad, taps;
+  int Cp, co16;                  // rows of one tap in an A tile / rows of one dy term in the B tile (multiples of 16)
+  int cin, cout;
+  int taps_per_tile, n_tiles, tiles_per_group;
+  int copies;                    // = k: z-shifted copies of x
+  int n_kblocks, kb_per_line;    // K blocks = (n, x, y, z piece)
+  float* gw;                     // [taps][gw_cin][gw_pitch] float32, added into
+  int gw_cin, gw_pitch;
+};
+
+constexpr int kWgStages = 4;      // A stages (hi tile + lo tile each)
+
+template <int KB>                 // positions per K block: 64 / 32 / 16 -> 128 / 64 / 32-byte swizzled rows
+__global__ void __launch_bounds__(128, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, const WgradParams p) {
+  constexpr int RB = KB * 2;
+  constexpr int kTile = 128 * RB;                       // one A tile (one term plane)
+  constexpr uint32_t kLayout = RB == 128 ? kSwizzle128 : (RB == 64 ? kSwizzle64 : kSwizzle32);
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t a_full[kWgStages], a_empty[kWgStages], b_full[2], b_empty[2], done;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_buf = smem;                                // [kWgStages][2 planes][kTile]
+  uint8_t* b_buf = smem + kWgStages * 2 * kTile;        // [2][256 rows * RB]
+  constexpr int kBStride = 256 * RB;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  if (tid == 0) {
+    for (int i = 0; i < kWgStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    mbar_init(&done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  if (warp == 1 && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_dy);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);
+
+  const int group = blockIdx.y;
+  const int tile0 = group * p.tiles_per_group;
+  const int my_tiles = min(p.tiles_per_group, p.n_tiles - tile0);
+  const int acc_cols = 2 * p.co16;
+  auto kblock_coords = [&](int kb, int& n, int& x, int& y, int& z0) {
+    z0 = (kb % p.kb_per_line) * KB;
+    const int line = kb / p.kb_per_line;
+    y = line % p.Y;
+    x = (line / p.Y) % p.X;
+    n = line / (p.Y * p.X);
+  };
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    uint32_t sa = 0, sb = 0;
+    for (int kb = blockIdx.x; kb < p.n_kblocks; kb += gridDim.x, ++sb) {
+      int n, x, y, z0;
+      kblock_coords(kb, n, x, y, z0);
+      const uint32_t bb = sb & 1;
+      mbar_wait(&b_empty[bb], ((sb >> 1) & 1) ^ 1);
+      mbar_arrive_expect_tx(&b_full[bb], (uint32_t)(2 * p.co16 * RB));
+      uint8_t* bdst = b_buf + bb * kBStride;
+      tma_load_5d(bdst, &map_dy, &b_full[bb], z0, y, x, 0, n);                               // dy_hi rows
+      tma_load_5d(bdst + p.co16 * RB, &map_dy, &b_full[bb], z0, y, x, 0, p.N + n);           // dy_lo rows
+      for (int t = 0; t < my_tiles; ++t, ++sa) {
+        const uint32_t st = sa % kWgStages;
+        mbar_wait(&a_empty[st], ((sa / kWgStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&a_full[st], 2u * kTile);
+        uint8_t* adst = a_buf + st * 2 * kTile;
+        for (int s = 0; s < p.taps_per_tile; ++s) {
+          const int tap = (tile0 + t) * p.taps_per_tile + s;
+          int dz = 0, xx = -100000, yy = 0;                    // taps beyond the kernel: a box far outside -> zero rows
+          if (tap < p.taps) {
+            dz = tap % p.k;
+            yy = y + (tap / p.k) % p.k - p.pad;
+            xx = x + tap / (p.k * p.k) - p.pad;
+          }
+          const int row_off = s * p.Cp * RB;
+          // outer index: (plane * copies + dz) * N + n
+          tma_load_5d(adst + row_off, &map_x, &a_full[st], z0, yy, xx, 0, dz * p.N + n);
+          tma_load_5d(adst + kTile + row_off, &map_x, &a_full[st], z0, yy, xx, 0, (p.copies + dz) * p.N + n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform, elect-predicated)
+    const uint32_t idesc_w = make_idesc(kFmtBF16, 128, (uint32_t)(2 * p.co16));
+    const uint32_t idesc_n = make_idesc(kFmtBF16, 128, (uint32_t)p.co16);
+    const uint64_t a_desc0 = make_smem_desc(smem_u32(a_buf), 0, 8 * RB, kLayout);
+    const uint64_t b_desc0 = make_smem_desc(smem_u32(b_buf), 0, 8 * RB, kLayout);
+    uint32_t sa = 0, sb = 0;
+    bool first = true;
+    for (int kb = blockIdx.x; kb < p.n_kblocks; kb += gridDim.x, ++sb) {
+      const uint32_t bb = sb & 1;
+      mbar_wait(&b_full[bb], (sb >> 1) & 1);
+      tc_fence_after();
+      const uint64_t bd = b_desc0 + (uint64_t)((bb * kBStride) >> 4);
+      for (int t = 0; t < my_tiles; ++t, ++sa) {
+        const uint32_t st = sa % kWgStages;
+        mbar_wait(&a_full[st], (sa / kWgStages) & 1);
+        tc_fence_after();
+        const uint64_t ad_hi = a_desc0 + (uint64_t)((st * 2 * kTile) >> 4);
+        const uint64_t ad_lo = ad_hi + (uint64_t)(kTile >> 4);
+        const uint32_t d = tmem_base + (uint32_t)(t * acc_cols);
+#pragma unroll
+        for (int ks = 0; ks < KB / 16; ++ks) {
+          if (elect_one_sync()) {
+            // x_hi * [dy_hi | dy_lo] -> 2 co columns; x_lo * dy_hi -> the upper co columns (small products together)
+            mma_f16_ss(d, ad_hi + 2 * ks, bd + 2 * ks, idesc_w, (first && ks == 0) ? 0u : 1u);
+            mma_f16_ss(d + (uint32_t)p.co16, ad_lo + 2 * ks, bd + 2 * ks, idesc_n, 1u);
+          }
+        }
+        if (elect_one_sync()) mma_commit(&a_empty[st]);
+      }
+      if (elect_one_sync()) mma_commit(&b_empty[bb]);
+      first = false;
+    }
+    if (elect_one_sync()) mma_commit(&done);
+  }
+  // ------------------------------------------------------------------ epilogue: all four warps, thread <-> A row
+  __syncthreads();
+  const bool any = (int)blockIdx.x < p.n_kblocks;
+  if (any) {
+    mbar_wait(&done, 0);
+    tc_fence_after();
+    const int row = tid;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int tap = (tile0 + t) * p.taps_per_tile + row / p.Cp;
+      const int ci = row % p.Cp;
+      const bool ok = tap < p.taps && ci < p.cin;
+      float* o = p.gw + ((int64_t)tap * p.gw_cin + ci) * p.gw_pitch;
+      for (int c0 = 0; c0 < p.co16; c0 += 16) {
+        uint32_t v0[16], v1[16];
+        tmem_ld_x16(tmem_base + lane_base + (uint32_t)(t * acc_cols + c0), v0);
+        tmem_ld_x16(tmem_base + lane_base + (uint32_t)(t * acc_cols + p.co16 + c0), v1);
+        tmem_ld_wait();
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float g = __uint_as_float(v0[j]) + __uint_as_float(v1[j]);
+            if (c0 + j < p.cout && g != 0.0f) atomicAdd(o + c0 + j, g);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn wg_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    cudaDriverEntryPointQueryResult q;
+    void* ptr = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+struct WgShape {
+  int Cp, co16, KB, taps, taps_per_tile, n_tiles, tiles_per_group, groups;
+  int64_t x_elems, dy_elems;    // bf16 elements of the two workspace regions
+};
+
+static int wg_shape(const sp3d_conv_wgrad_tc_args* a, WgShape* s) {
+  if (a == nullptr || a->N < 1 || a->X < 1 || a->Y < 1 || a->Z < 1 || a->cin < 1 || a->cout < 1 || a->x_pitch < a->cin ||
+      a->g_pitch < a->cout || a->cin > 128 || a->cout > 128)
+    return SP3D_ERR_INVALID_ARG;
+  if (a->k != 1 && a->k != 3 && a->k != 7) return SP3D_ERR_UNSUPPORTED;
+  s->Cp = (a->cin + 15) / 16 * 16;
+  s->co16 = (a->cout + 15) / 16 * 16;
+  if ((s->Cp != 16 && s->Cp != 32 && s->Cp != 64 && s->Cp != 128) || s->co16 > 128) return SP3D_ERR_UNSUPPORTED;
+  s->KB = a->Z >= 64 ? 64 : a->Z;
+  if ((s->KB != 64 && s->KB != 32 && s->KB != 16) || a->Z % s->KB) return SP3D_ERR_UNSUPPORTED;
+  s->taps = a->k * a->k * a->k;
+  s->taps_per_tile = 128 / s->Cp;
+  s->n_tiles = (s->taps + s->taps_per_tile - 1) / s->taps_per_tile;
+  s->tiles_per_group = 512 / (2 * s->co16);
+  if (s->tiles_per_group > s->n_tiles) s->tiles_per_group = s->n_tiles;
+  s->groups = (s->n_tiles + s->tiles_per_group - 1) / s->tiles_per_group;
+  const int64_t vox = (int64_t)a->N * a->X * a->Y * a->Z;
+  s->x_elems = 2 * (int64_t)a->k * s->Cp * vox;
+  s->dy_elems = 2 * (int64_t)s->co16 * vox;
+  if ((int64_t)a->N * a->X * a->Y > 2147483647LL || 2 * (int64_t)a->k * a->N > 2147483647LL) return SP3D_ERR_UNSUPPORTED;
+  return SP3D_OK;
+}
+
+template <int KB>
+static int wg_launch(const sp3d_conv_wgrad_tc_args* a, const WgShape& s, const CUtensorMap& mx, const CUtensorMap& mdy,
+                     cudaStream_t st) {
+  WgradParams p{};
+  p.N = a->N; p.X = a->X; p.Y = a->Y; p.Z = a->Z; p.k = a->k; p.pad = (a->k - 1) / 2; p.taps = s.taps;
+  p.Cp = s.Cp; p.co16 = s.co16; p.cin = a->cin; p.cout = a->cout;
+  p.taps_per_tile = s.taps_per_tile; p.n_tiles = s.n_tiles; p.tiles_per_group = s.tiles_per_group;
+  p.copies = a->k;
+  p.kb_per_line = a->Z / KB;
+  p.n_kblocks = a->N * a->X * a->Y * p.kb_per_line;
+  p.gw = a->grad_weight; p.gw_cin = a->gw_cin; p.gw_pitch = a->gw_pitch;
+  constexpr int kSmem = kWgStages * 2 * 128 * KB * 2 + 2 * 256 * KB * 2 + 1024;
+  auto kern = wgrad_tc_kernel<KB>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) { set_last_error(e); return SP3D_ERR_LAUNCH; }
+    attr_done = true;
+  }
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int gx = n_sm / s.groups;
+  if (gx < 1) gx = 1;
+  if (gx > p.n_kblocks) gx = p.n_kblocks;
+  kern<<<dim3(gx, s.groups), 128, kSmem, st>>>(mx, mdy, p);
+  return check_launch();
+}
+
+}  // namespace sp3d
+
+extern "C" int64_t sp3d_conv_wgrad_tc_workspace(const sp3d_conv_wgrad_tc_args* a) {
+  sp3d::WgShape s;
+  if (sp3d::wg_shape(a, &s) != SP3D_OK) return -1;
+  return (s.x_elems + s.dy_elems) * 2 + 1024;
+}
+
+extern "C" int sp3d_conv_wgrad_tc(const sp3d_conv_wgrad_tc_args* a, void* stream) {
+  using namespace sp3d;
+  WgShape s;
+  int rc = wg_shape(a, &s);
+  if (rc != SP3D_OK) return rc;
+  if (a->x == nullptr || a->grad_out == nullptr || a->grad_weight == nullptr || a->workspace == nullptr ||
+      a->gw_cin < a->cin || a->gw_pitch < a->cout)
+    return SP3D_ERR_INVALID_ARG;
+  if (a->workspace_bytes < (s.x_elems + s.dy_elems) * 2 + 1024 || (reinterpret_cast<uintptr_t>(a->workspace) % 16))
+    return SP3D_ERR_WORKSPACE;
+  EncodeTiledFn encode = wg_encode();
+  if (encode == nullptr) return SP3D_ERR_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(a->workspace) + 1023) & ~uintptr_t(1023));
+  __nv_bfloat16* xT = reinterpret_cast<__nv_bfloat16*>(ws);
+  __nv_bfloat16* dyT = xT + s.x_elems;
+  const int XY = a->X * a->Y, lines = a->N * XY;
+  const int pad = (a->k - 1) / 2;
+  const int prep_ctas = lines < 148 * 8 ? lines : 148 * 8;
+  wgrad_prep_kernel<<<prep_ctas, 256, (size_t)a->Z * (a->cin + 1) * sizeof(float), st>>>(a->x, xT, a->N, XY, a->Z, a->cin, s.Cp,
+                                                                                        a->x_pitch, a->k, pad, nullptr);
+  rc = check_launch();
+  if (rc != SP3D_OK) return rc;
+  wgrad_prep_kernel<<<prep_ctas, 256, (size_t)a->Z * (a->cout + 1) * sizeof(float), st>>>(a->grad_out, dyT, a->N, XY, a->Z, a->cout,
+                                                                                         s.co16, a->g_pitch, 1, 0, a->grad_bias);
+  rc = check_launch();
+  if (rc != SP3D_OK) return rc;
+
+  CUtensorMap mx, mdy;
+  const CUtensorMapSwizzle sw = s.KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (s.KB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  {  // x^T: [2 planes * k copies * N][Cp][X][Y][Z] bf16; box = {KB, 1, 1, Cp, 1}
+    cuuint64_t gdim[5] = {(cuuint64_t)a->Z, (cuuint64_t)a->Y, (cuuint64_t)a->X, (cuuint64_t)s.Cp, (cuuint64_t)(2 * a->k * a->N)};
+    cuuint64_t gstr[4] = {(cuuint64_t)a->Z * 2, (cuuint64_t)a->Z * a->Y * 2, (cuuint64_t)a->Z * a->Y * a->X * 2,
+                          (cuuint64_t)a->Z * a->Y * a->X * s.Cp * 2};
+    cuuint32_t box[5] = {(cuuint32_t)s.KB, 1, 1, (cuuint32_t)s.Cp, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    if (encode(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, xT, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return SP3D_ERR_INVALID_ARG;
+  }
+  {  // dy^T: [2 planes * N][co16][X][Y][Z] bf16; box = {KB, 1, 1, co16, 1}
+    cuuint64_t gdim[5] = {(cuuint64_t)a->Z, (cuuint64_t)a->Y, (cuuint64_t)a->X, (cuuint64_t)s.co16, (cuuint64_t)(2 * a->N)};
+    cuuint64_t gstr[4] = {(cuuint64_t)a->Z * 2, (cuuint64_t)a->Z * a->Y * 2, (cuuint64_t)a->Z * a->Y * a->X * 2,
+                          (cuuint64_t)a->Z * a->Y * a->X * s.co16 * 2};
+    cuuint32_t box[5] = {(cuuint32_t)s.KB, 1, 1, (cuuint32_t)s.co16, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    if (encode(&mdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, dyT, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return SP3D_ERR_INVALID_ARG;
+  }
+  if (s.KB == 64) return wg_launch<64>(a, s, mx, mdy, st);
+  if (s.KB == 32) return wg_launch<32>(a, s, mx, mdy, st);
+  return wg_launch<16>(a, s, mx, mdy, st);
+}

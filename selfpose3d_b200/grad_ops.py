@@ -126,6 +126,8 @@ def conv_wgrad(pc, x, grad_out, with_bias=True):
     if tuple(grad_out.shape[:4]) != (N, o[0], o[1], o[2]) or int(grad_out.shape[4]) < pc.cout:
         raise _lib.Sp3dError("conv_wgrad: grad_out does not match the convolution's output shape")
     gb = torch.zeros(pc.cout, device=x.device, dtype=torch.float32) if with_bias else None
+    if _wgrad_tc_ok(pc, x, grad_out):
+        return _conv_wgrad_tc(pc, x, grad_out, gb), gb
     subs = []
     launches = [(None, [-p for p in pc.padding], pc.k, o, [1, 1, 1], [1, 1, 1], [0, 0, 0])] if not pc.transposed else [
         (i, off0, ks, [(o[d] - phase[d] + pc.stride[d] - 1) // pc.stride[d] for d in range(3)], [-1, -1, -1], pc.stride, phase)
@@ -158,6 +160,45 @@ def conv_wgrad(pc, x, grad_out, with_bias=True):
         w5 = w5.permute(1, 0, 2, 3, 4)                             # nn.ConvTranspose layout [Cin, Cout, k..]
     shape = list(w5.shape[:2]) + list(w5.shape[2 + (3 - pc.nd):])
     return w5.reshape(shape).contiguous(), gb
+
+
+_WGRAD_TC = __import__("os").environ.get("SP3D_WGRAD_TC", "1") != "0"
+
+
+def _wgrad_tc_ok(pc, x, grad_out):
+    """The tcgen05 weight gradient (``sp3d_conv_wgrad_tc``) takes stride-1 "same" 3-D convolutions with a cubic kernel
+    of 1, 3 or 7 taps, at most 128 channels with ``round_up(cin, 16)`` in {16, 32, 64, 128}, and a z extent of 16, 32
+    or a multiple of 64 -- every ``nn.Conv3d`` of the pose net's V2VNet.  Not in the float32 FMA mode."""
+    if not _WGRAD_TC or ops.float32_conv() == "simt" or pc.nd != 3 or pc.transposed:
+        return False
+    k = pc.k[0]
+    if pc.k != [k] * 3 or k not in (1, 3, 7) or pc.stride != [1, 1, 1] or pc.padding != [k // 2] * 3:
+        return False
+    Z = int(x.shape[3])
+    if pc.cout > 128 or ops.round_up(pc.cin, 16) not in (16, 32, 64, 128):
+        return False
+    return Z in (16, 32) or Z % 64 == 0
+
+
+def _conv_wgrad_tc(pc, x, grad_out, gb):
+    """``[Cout, Cin, k, k, k]`` weight gradient through ``sp3d_conv_wgrad_tc`` (bias gradient added into ``gb``)."""
+    N, X, Y, Z, pitch = [int(v) for v in x.shape]
+    k = pc.k[0]
+    gw = torch.zeros(k ** 3, pc.cin_p, pc.cout_pw, device=x.device, dtype=torch.float32)
+    a = _lib.ConvWgradTcArgs()
+    a.x, a.grad_out = x.data_ptr(), grad_out.data_ptr()
+    a.N, a.X, a.Y, a.Z = N, X, Y, Z
+    a.cin, a.x_pitch, a.cout, a.g_pitch, a.k = pc.cin, pitch, pc.cout, int(grad_out.shape[4]), k
+    a.grad_weight, a.gw_cin, a.gw_pitch = gw.data_ptr(), pc.cin_p, pc.cout_pw
+    a.grad_bias = gb.data_ptr() if gb is not None else None
+    nbytes = int(_lib.load().sp3d_conv_wgrad_tc_workspace(a))
+    if nbytes < 0:
+        raise _lib.Sp3dError("sp3d_conv_wgrad_tc: shape not supported")
+    ws = torch.empty(nbytes + 16, device=x.device, dtype=torch.uint8)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
+    flops = 2.0 * N * X * Y * Z * pc.cout * pc.cin * k ** 3
+    _lib.call("sp3d_conv_wgrad_tc", a, _stream(), launches=3, kind="conv_wgrad_tc", work=flops)
+    return gw[:, :pc.cin, :pc.cout].reshape(k, k, k, pc.cin, pc.cout).permute(4, 3, 0, 1, 2).contiguous()
 
 
 def conv_dgrad(pc, grad_out, out_pitch=None, in_dims=None):

@@ -156,6 +156,7 @@ def test_ctypes_struct_layouts_match_the_c_header(tmp_path):
         "sp3d_bn_apply_args": _lib.BnApplyArgs, "sp3d_bn_bwd_args": _lib.BnBwdArgs, "sp3d_relu_bwd_args": _lib.ReluBwdArgs,
         "sp3d_gauss_render_args": _lib.GaussRenderArgs, "sp3d_gauss_render_bwd_args": _lib.GaussRenderBwdArgs,
         "sp3d_target_heatmaps_args": _lib.TargetHeatmapsArgs, "sp3d_target_volume_args": _lib.TargetVolumeArgs,
+        "sp3d_conv_wgrad_tc_args": _lib.ConvWgradTcArgs,
     }
     header = open(os.path.join(ROOT, "include", "sp3d.h")).read()
     declared = set(re.findall(r"}\s*(sp3d_[a-z0-9_]+_args)\s*;", header))
