@@ -8,8 +8,9 @@ losses on pseudo heat-maps) data-parallel over the GPUs of one box.
 Per rank: ``--batch-per-gpu`` frames of 5 views 3x384x288 in three augmented sets, ``MultiPersonPoseNetSSV`` in
 .train() (root net .eval(): FREEZE_ROOTNET), forward + backward on the float32 training path, gradient average with
 ``selfpose3d_b200.dist.allreduce_gradients``, no optimizer.  Prints one JSON line (frames/s over all ranks, max over
-ranks, CUDA events).  NOT YET RUN ON A GPU: written after round 1's GPU minutes were spent; the model-level path is
-covered on CPU (tests/test_training_cpu.py, tests/test_dist_gloo.py)."""
+ranks, CUDA events).  The model-level path is
+covered on CPU (tests/test_training_cpu.py, tests/test_dist_gloo.py).  Round 2: run on 1 / 2 / 8 B200s
+(profiles/r02_config5_train_*.json); the V2VNet weight gradients run on tcgen05 (sp3d_conv_wgrad_tc)."""
 import argparse
 import json
 import os
