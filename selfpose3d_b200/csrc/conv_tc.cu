@@ -138,7 +138,10 @@ struct TcCfg {
   static constexpr uint32_t kLayout = RB == 128 ? kSwizzle128 : (RB == 64 ? kSwizzle64 : kSwizzle32);
   static constexpr uint32_t kLayoutW = kPosBytes == 128 ? kSwizzle128 : (kPosBytes == 64 ? kSwizzle64 : kSwizzle32);
   static_assert(F == 1 || ((KSX == KS || KSX == 1) && kPosBytes >= 32), "z-fold: same convolutions, one K chunk");
-  static_assert(2 * TX * N * WD <= 512, "accumulators exceed TMEM");
+  // accumulator sets in TMEM: two (the epilogue drains one brick while the next one accumulates) where they fit the 512
+  // columns, else one (the MMA warps wait for the drain: a few percent, against the MMAs a wider tile saves)
+  static constexpr int kAB = 2 * TX * N * WD <= 512 ? 2 : 1;
+  static_assert(kAB * TX * N * WD <= 512, "accumulators exceed TMEM");
   static_assert(WD == 1 || WD == 2, "accumulator width factor");
   static_assert(kSmemBytes + 3072 <= 227 * 1024, "shared memory budget (dynamic + ~3 KB static)");
 };
@@ -270,9 +273,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
     const bool prof = p.prof != nullptr;
     if (prof) t_begin = clock64();
     for (int wi = wi_begin; wi < wi_end; wi += wi_step, ++it) {
-      const uint32_t accbuf = it & 1;
+      const uint32_t accbuf = it % C::kAB;
       if (prof) t0 = clock64();
-      mbar_wait(&acc_empty[accbuf], ((it >> 1) & 1) ^ 1);
+      mbar_wait(&acc_empty[accbuf], ((it / C::kAB) & 1) ^ 1);
       if (prof) t_acc += clock64() - t0;
       tc_fence_after();
       for (int c = 0; c < p.n_chunks; ++c, ++u) {
@@ -303,7 +306,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
             if (prof) t_w += clock64() - t0;
             tc_fence_after();
             uint32_t b_lo = (uint32_t)b_desc0 + (uint32_t)((st * C::kWStride) >> 4);
-#pragma unroll(G % C::KZ == 0 ? C::KZ : 1)
+#pragma unroll(G % C::KZ == 0 ? C::KZ : (G <= 4 ? G : 1))
             for (int j = 0; j < G; ++j) {
 #pragma unroll
               for (int t = q; t < TX; t += C::kIssuers) {
@@ -411,9 +414,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
       for (int wi = wi_begin; wi < wi_end; wi += wi_step, ++it) {
         int n, x0, y0, z0, nt;
         item_coords(wi, n, x0, y0, z0, nt);
-        const uint32_t accbuf = it & 1;
+        const uint32_t accbuf = it % C::kAB;
         if (prof) e0 = clock64();
-        mbar_wait(&acc_full[accbuf], (it >> 1) & 1);
+        mbar_wait(&acc_full[accbuf], (it / C::kAB) & 1);
         if (prof) e_wait += clock64() - e0;
         tc_fence_after();
         const int ch0 = nt * N;
@@ -656,8 +659,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
             for (int i = row; i < p.Z; i += 128) sa_g[2][i] = __fsub_rn(__fadd_rn(p.sa_lin_z[i], cz), cz);
             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
           }
-          const uint32_t accbuf = it & 1;
-          mbar_wait(&acc_full[accbuf], (it >> 1) & 1);
+          const uint32_t accbuf = it % C::kAB;
+          mbar_wait(&acc_full[accbuf], (it / C::kAB) & 1);
           tc_fence_after();
           const int y = y0 + ly, z = z0 + lz;
 #pragma unroll 1
@@ -703,9 +706,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
     for (int wi = wi_begin; !p.tma_store && !p.sa_ws && wi < wi_end; wi += wi_step, ++it) {
       int n, x0, y0, z0, nt;
       item_coords(wi, n, x0, y0, z0, nt);
-      const uint32_t accbuf = it & 1;
+      const uint32_t accbuf = it % C::kAB;
       if (prof) e0 = clock64();
-      mbar_wait(&acc_full[accbuf], (it >> 1) & 1);
+      mbar_wait(&acc_full[accbuf], (it / C::kAB) & 1);
       if (prof) e_wait += clock64() - e0;
       tc_fence_after();
       const int y = y0 + ly, z = z0 + lz;
@@ -1077,6 +1080,11 @@ int conv_tc(const sp3d_conv_args* a, cudaStream_t st) {
   SP3D_TC_CASE_W(7, 7, 64, 32, 4, 8, 2, 1, 2, 128, 1, 2, 2)
   SP3D_TC_CASE_W(1, 7, 64, 32, 4, 8, 2, 2, 2, 128, 2, 2, 2)
   SP3D_TC_CASE_W(3, 3, 64, 32, 4, 3, 3, 2, 2, 128, 2, 1, 2)
+  // 3^3 64 -> 64 (N = 64): 2 x 64 accumulator columns per x-slice at TX = 2, one halo buffer.  (The z-folded 16 / 32 -> 32
+  // layers would need TX = 4 with ONE accumulator set: measured slower, 14.0 against 12.5 ms per 80 cubes.)
+  SP3D_TC_CASE_W(3, 3, 128, 64, 2, 1, 4, 1, 2, 64, 1, 1, 2)
+  SP3D_TC_CASE_W(3, 3, 128, 64, 2, 4, 2, 1, 2, 128, 1, 2, 2)
+  SP3D_TC_CASE_W(3, 3, 64, 64, 2, 4, 3, 2, 2, 128, 1, 2, 2)
 #undef SP3D_TC_CASE
 #undef SP3D_TC_CASE_F
 #undef SP3D_TC_CASE_W

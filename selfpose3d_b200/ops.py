@@ -457,7 +457,8 @@ def _tc_finish(full, terms):
 # (kernel extent along x, along y / z, shared-memory row bytes, N = MMA columns, z-fold) of every conv_tc_kernel
 # instantiation in csrc/conv_tc.cu (the SP3D_TC_CASE list; tests/test_host_cpu.py keeps the two in step)
 # instantiations of the 2-K-block form of the 3-pair split mode (split_terms 2: accumulators of 2 N columns)
-TC_WIDE_CASES = frozenset({(7, 7, 64, 32, 2), (1, 7, 64, 32, 2), (3, 3, 64, 32, 1)})
+TC_WIDE_CASES = frozenset({(7, 7, 64, 32, 2), (1, 7, 64, 32, 2), (3, 3, 64, 32, 1), (3, 3, 128, 64, 1), (3, 3, 128, 64, 2),
+                           (3, 3, 64, 64, 2)})
 TC_CASES = frozenset({
     (7, 7, 32, 16, 1), (7, 7, 64, 32, 2), (3, 3, 64, 64, 2), (1, 7, 64, 32, 2), (3, 3, 128, 64, 2), (3, 3, 32, 32, 1),
     (3, 3, 64, 32, 1), (3, 3, 64, 64, 1), (3, 3, 128, 64, 1), (3, 3, 128, 128, 1), (3, 3, 64, 16, 1), (3, 3, 128, 32, 1),
