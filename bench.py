@@ -283,7 +283,8 @@ def time_training_step(dev, steps=2, mode="bf16x3"):
             "gpu_launches": _lib.launch_count - l0, "matched_proposals": matched,
             "what": "supervised step, 1 frame x 5 views, frozen backbone, root net + pose net forward and backward; "
                     "float32 training path, convolutions: %s" % ("float32 FMA kernels" if mode == "simt" else
-                    "forward and covered input gradients on tcgen05 (split operands), weight gradients float32 FMA")}
+                    "forward, covered input gradients and the V2VNet weight gradients on tcgen05 (split operands); "
+                    "root-net (z = 20) and transposed-convolution weight gradients on the float32 FMA kernel")}
 
 
 
