@@ -55,14 +55,33 @@ if a.stalls:
     from selfpose3d_b200 import _lib
     lib = _lib.load()
     buf = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
-    lib.sp3d_debug_conv_profile(C.c_void_p(buf.data_ptr()))
+
+    def counters(name, fn):
+        with torch.no_grad():
+            fn()
+            torch.cuda.synchronize()
+            lib.sp3d_debug_conv_profile(C.c_void_p(buf.data_ptr()))
+            buf.zero_()
+            fn()
+            torch.cuda.synchronize()
+            lib.sp3d_debug_conv_profile(C.c_void_p(0))
+        t = buf.view(148, 16).double().cpu()
+        t = t[t[:, 0] > 0]
+        m = (t.mean(0) / 1e3).tolist()
+        print("%-22s per-CTA mean kclk: mma total %.1f | wait halo %.1f (%.1f%%), wait weights %.1f (%.1f%%), wait acc_empty %.1f "
+              "(%.1f%%) | epilogue busy %.1f (%.1f%%) | items %.1f | epi: ld %.1f res %.1f math %.1f fence+bar %.1f store+ring %.1f"
+              % (name, m[0], m[1], 100 * m[1] / m[0], m[2], 100 * m[2] / m[0], m[3], 100 * m[3] / m[0], m[4] - m[5],
+                 100 * (m[4] - m[5]) / max(m[4], 1e-9), m[6] * 1e3, m[8], m[9], m[10], m[11], m[12]))
+
     with torch.no_grad():
-        net.front_layers[0].forward_cl(xs)
-    torch.cuda.synchronize()
-    lib.sp3d_debug_conv_profile(C.c_void_p(0))
-    t = buf.view(148, 16).double().cpu()
-    t = t[t[:, 0] > 0]
-    m = (t.mean(0) / 1e3).tolist()
-    print("stem per-CTA mean kclk: mma total %.1f | wait halo %.1f, wait weights %.1f, wait acc_empty %.1f | epilogue total %.1f, "
-          "epilogue waits acc_full %.1f | items %.1f | epi: ld %.1f res %.1f math %.1f fence+bar %.1f store+ring %.1f"
-          % (m[0], m[1], m[2], m[3], m[4], m[5], m[6] * 1e3, m[8], m[9], m[10], m[11], m[12]))
+        h1 = net.front_layers[0].forward_cl(xs)                      # [2, n, 64^3, 16]
+        c16, c32b, _ = net.front_layers[1]._packed()
+        h2 = c16(h1)                                                  # 16 -> 32
+        pool = net.encoder_decoder.encoder_pool1.forward_cl(h2, 32)
+        e_a, e_b, e_s = net.encoder_decoder.encoder_res1._packed()    # 32 -> 64, 64 -> 64 at 32^3
+        h3 = e_a(pool)
+    counters("7^3 15->16 stem", lambda: net.front_layers[0].forward_cl(xs))
+    counters("3^3 16->32", lambda: c16(h1))
+    counters("3^3 32->32 +res", lambda: c32b(h2, residual=h2))
+    counters("3^3 32->64 @32^3", lambda: e_a(pool))
+    counters("3^3 64->64 +res @32^3", lambda: e_b(h3, residual=h3))

@@ -1082,9 +1082,10 @@ int conv_tc(const sp3d_conv_args* a, cudaStream_t st) {
   SP3D_TC_CASE_W(3, 3, 64, 32, 4, 3, 3, 2, 2, 128, 2, 1, 2)
   // 3^3 64 -> 64 (N = 64): 2 x 64 accumulator columns per x-slice at TX = 2, one halo buffer.  (The z-folded 16 / 32 -> 32
   // layers would need TX = 4 with ONE accumulator set: measured slower, 14.0 against 12.5 ms per 80 cubes.)
-  SP3D_TC_CASE_W(3, 3, 128, 64, 2, 1, 4, 1, 2, 64, 1, 1, 2)
-  SP3D_TC_CASE_W(3, 3, 128, 64, 2, 4, 2, 1, 2, 128, 1, 2, 2)
-  SP3D_TC_CASE_W(3, 3, 64, 64, 2, 4, 3, 2, 2, 128, 1, 2, 2)
+  // (weight rings sized from the in-kernel wait counters, profiles/r02_conv_stalls.log)
+  SP3D_TC_CASE_W(3, 3, 128, 64, 2, 1, 6, 1, 2, 64, 1, 1, 2)
+  SP3D_TC_CASE_W(3, 3, 128, 64, 2, 4, 3, 1, 2, 128, 1, 2, 2)
+  SP3D_TC_CASE_W(3, 3, 64, 64, 2, 4, 4, 2, 2, 128, 2, 2, 2)
 #undef SP3D_TC_CASE
 #undef SP3D_TC_CASE_F
 #undef SP3D_TC_CASE_W

@@ -197,7 +197,8 @@ def _conv_wgrad_tc(pc, x, grad_out, gb):
     ws = torch.empty(nbytes + 16, device=x.device, dtype=torch.uint8)
     a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
     flops = 2.0 * N * X * Y * Z * pc.cout * pc.cin * k ** 3
-    _lib.call("sp3d_conv_wgrad_tc", a, _stream(), launches=3, kind="conv_wgrad_tc", work=flops)
+    _lib.call("sp3d_conv_wgrad_tc", a, _stream(), launches=3, kind="conv_wgrad_tc", work=flops,
+              detail="wgrad tc k%d %d->%d @%dx%dx%dx%d" % (k, pc.cin, pc.cout, N, X, Y, Z))
     return gw[:, :pc.cin, :pc.cout].reshape(k, k, k, pc.cin, pc.cout).permute(4, 3, 0, 1, 2).contiguous()
 
 
