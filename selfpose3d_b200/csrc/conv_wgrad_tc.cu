@@ -92,6 +92,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t a_full[kWgStages], a_empty[kWgStages], b_full[2], b_empty[2], done;
   __shared__ uint32_t tmem_base_s;
+  __shared__ int3 s_tap[32 * 8];                        // <= 32 tiles per CTA x 8 tap slots per tile
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_buf = smem;                                // [kWgStages][2 planes][kTile]
   uint8_t* b_buf = smem + kWgStages * 2 * kTile;        // [2][256 rows * RB]
@@ -122,6 +123,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const int tile0 = group * p.tiles_per_group;
   const int my_tiles = min(p.tiles_per_group, p.n_tiles - tile0);
   const int acc_cols = 2 * p.co16;
+  // tap table of this CTA's tiles: slot s of tile t -> (dz copy, dy - pad, dx - pad); taps beyond the kernel get an x
+  // offset far outside the tensor (TMA zero-fills the box)
+  for (int i = tid; i < my_tiles * 8; i += 128) {
+    const int tap = (tile0 + i / 8) * p.taps_per_tile + (i % 8);
+    int3 tp = make_int3(0, 0, -100000);
+    if ((i % 8) < p.taps_per_tile && tap < p.taps) tp = make_int3(tap % p.k, (tap / p.k) % p.k - p.pad, tap / (p.k * p.k) - p.pad);
+    s_tap[i] = tp;
+  }
+  __syncthreads();
   auto kblock_coords = [&](int kb, int& n, int& x, int& y, int& z0) {
     z0 = (kb % p.kb_per_line) * KB;
     const int line = kb / p.kb_per_line;
@@ -130,35 +140,34 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     n = line / (p.Y * p.X);
   };
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------------ TMA producer
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer: the whole warp.  Lane s issues the
+    // two boxes (hi / lo plane) of tap slot s of every A tile -- one thread issuing all of a tile's boxes (up to 16 for
+    // the 7^3 stem) was the bottleneck of the first version (about 300 cycles of address arithmetic per box).
     uint32_t sa = 0, sb = 0;
+    const int slot = lane;
     for (int kb = blockIdx.x; kb < p.n_kblocks; kb += gridDim.x, ++sb) {
       int n, x, y, z0;
       kblock_coords(kb, n, x, y, z0);
       const uint32_t bb = sb & 1;
       mbar_wait(&b_empty[bb], ((sb >> 1) & 1) ^ 1);
-      mbar_arrive_expect_tx(&b_full[bb], (uint32_t)(2 * p.co16 * RB));
-      uint8_t* bdst = b_buf + bb * kBStride;
-      tma_load_5d(bdst, &map_dy, &b_full[bb], z0, y, x, 0, n);                               // dy_hi rows
-      tma_load_5d(bdst + p.co16 * RB, &map_dy, &b_full[bb], z0, y, x, 0, p.N + n);           // dy_lo rows
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&b_full[bb], (uint32_t)(2 * p.co16 * RB));
+        uint8_t* bdst = b_buf + bb * kBStride;
+        tma_load_5d(bdst, &map_dy, &b_full[bb], z0, y, x, 0, n);                               // dy_hi rows
+        tma_load_5d(bdst + p.co16 * RB, &map_dy, &b_full[bb], z0, y, x, 0, p.N + n);           // dy_lo rows
+      }
       for (int t = 0; t < my_tiles; ++t, ++sa) {
         const uint32_t st = sa % kWgStages;
         mbar_wait(&a_empty[st], ((sa / kWgStages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&a_full[st], 2u * kTile);
-        uint8_t* adst = a_buf + st * 2 * kTile;
-        for (int s = 0; s < p.taps_per_tile; ++s) {
-          const int tap = (tile0 + t) * p.taps_per_tile + s;
-          int dz = 0, xx = -100000, yy = 0;                    // taps beyond the kernel: a box far outside -> zero rows
-          if (tap < p.taps) {
-            dz = tap % p.k;
-            yy = y + (tap / p.k) % p.k - p.pad;
-            xx = x + tap / (p.k * p.k) - p.pad;
-          }
-          const int row_off = s * p.Cp * RB;
+        if (lane == 0) mbar_arrive_expect_tx(&a_full[st], 2u * kTile);
+        __syncwarp();
+        if (slot < p.taps_per_tile) {
+          uint8_t* adst = a_buf + st * 2 * kTile + slot * p.Cp * RB;
+          const int3 tp = s_tap[t * 8 + slot];               // (dz copy, y offset, x offset); x far outside: no such tap
           // outer index: (plane * copies + dz) * N + n
-          tma_load_5d(adst + row_off, &map_x, &a_full[st], z0, yy, xx, 0, dz * p.N + n);
-          tma_load_5d(adst + kTile + row_off, &map_x, &a_full[st], z0, yy, xx, 0, (p.copies + dz) * p.N + n);
+          tma_load_5d(adst, &map_x, &a_full[st], z0, y + tp.y, x + tp.z, 0, tp.x * p.N + n);
+          tma_load_5d(adst + kTile, &map_x, &a_full[st], z0, y + tp.y, x + tp.z, 0, (p.copies + tp.x) * p.N + n);
         }
       }
     }
