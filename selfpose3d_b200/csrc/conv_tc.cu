@@ -122,7 +122,16 @@ struct TcCfg {
   static constexpr int HX = TX + KSX - 1, HY = kBY + KS - 1, HZ = kBZ + (kE0 + KZ - 1) / F;
   static constexpr int kHaloRows = HX * HY * HZ;
   static constexpr int kHaloBytes = kHaloRows * RB;
-  static constexpr int kHaloStride = (kHaloBytes + 1023) / 1024 * 1024;
+  // Single-halo-buffer kernels with taps along x load and release the halo PER X-SLICE: slice d is last read by the taps
+  // with dx = d, so the next brick's slice d streams in while the taps dx > d still run (the wait on a monolithic
+  // single buffer was 5 - 22 % of the MMA warps' time).  Slices are padded to 1024 bytes (swizzle atom alignment).
+  // (3^3 kernels only: for the 7^3 stem the ten extra boxes per fill cost more weight-stream stalls than the 4.7 % halo
+  // wait they remove -- 22.9 against 22.5 Mclk per CTA, profiles/r02_conv_stalls*.log)
+  static constexpr bool kSliced = HB == 1 && KSX > 1 && KSX <= 3;
+  static constexpr int kSliceBytes = HY * HZ * RB;
+  static constexpr int kSliceStride = kSliced ? (kSliceBytes + 1023) / 1024 * 1024 : kSliceBytes;
+  static constexpr int kHBar = kSliced ? HX : HB;      // halo barriers (full / empty each)
+  static constexpr int kHaloStride = kSliced ? HX * kSliceStride : (kHaloBytes + 1023) / 1024 * 1024;
   static constexpr int kTaps = KSX * KS * KZ;
   static constexpr int kGroups = kTaps / G;             // weight stages consumed per (brick, chunk)
   static constexpr int kTapBytes = N * kPosBytes;
@@ -133,6 +142,8 @@ struct TcCfg {
   static constexpr int kLoads = G / kTapsPerLoad;
   static constexpr int kSmemBytes = HB * kHaloStride + S * kWStride + EG * SB * kStageBytes + 1024;   // + alignment slack
   static_assert(kTaps % G == 0, "taps per stage must divide the tap count");
+  static constexpr int kGroupsPerDx = (KS * KZ) / G;    // weight stages per x tap (sliced halo: slice hand-over points)
+  static_assert(!kSliced || (KS * KZ) % G == 0, "sliced halo: weight stages must not straddle x taps");
   static constexpr int kKSteps = kPosBytes / 32;   // tcgen05.mma K = 16 bf16 = 32 bytes
   static constexpr int kIssuers = TX >= 2 ? 2 : 1;
   static constexpr uint32_t kLayout = RB == 128 ? kSwizzle128 : (RB == 64 ? kSwizzle64 : kSwizzle32);
@@ -154,7 +165,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
   using C = TcCfg<KSX, KS, RB, N, TX, G, S, HB, SB, SR, EG, F, WD>;
   constexpr int kWStages = S;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t halo_full[HB], halo_empty[HB], w_full[kWStages], w_empty[kWStages], acc_full[2], acc_empty[2];
+  __shared__ uint64_t halo_full[C::kHBar], halo_empty[C::kHBar], w_full[kWStages], w_empty[kWStages], acc_full[2], acc_empty[2];
   __shared__ uint64_t res_full[EG][SB];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_scale[2][N], s_shift[2][N];      // per accumulator buffer (the channel tile may change per item)
@@ -167,7 +178,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
   if (tid == 0) {
-    for (int i = 0; i < HB; ++i) {
+    for (int i = 0; i < C::kHBar; ++i) {
       mbar_init(&halo_full[i], 1);
       mbar_init(&halo_empty[i], C::kIssuers);
     }
@@ -229,15 +240,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
       int n, x0, y0, z0, nt;
       item_coords(wi, n, x0, y0, z0, nt);
       for (int c = 0; c < p.n_chunks; ++c, ++u) {
-        const uint32_t buf = u % HB;
-        mbar_wait(&halo_empty[buf], ((u / HB) & 1) ^ 1);
-        mbar_arrive_expect_tx(&halo_full[buf], C::kHaloBytes);
         // split-operand mode: K block kb = c / nc_block reads activation term plane (block_act >> 4 kb) & 15
         const int kb = c / p.nc_block;
         const int plane = (int)((p.block_act >> (4 * kb)) & 15u);
-        tma_load_5d(halo + buf * C::kHaloStride, &map_in, &halo_full[buf], (c - kb * p.nc_block) * (RB / 2),
-                    z0 * p.istride[2] + p.origin[2], y0 * p.istride[1] + p.origin[1],
-                    x0 * p.istride[0] + p.origin[0], plane * p.n_outer + n);
+        if constexpr (C::kSliced) {
+          for (int xs = 0; xs < C::HX; ++xs) {          // one box per x-slice (the tensor map's box is one slice thick)
+            mbar_wait(&halo_empty[xs], (u & 1) ^ 1);
+            mbar_arrive_expect_tx(&halo_full[xs], C::kSliceBytes);
+            tma_load_5d(halo + xs * C::kSliceStride, &map_in, &halo_full[xs], (c - kb * p.nc_block) * (RB / 2),
+                        z0 * p.istride[2] + p.origin[2], y0 * p.istride[1] + p.origin[1],
+                        x0 * p.istride[0] + p.origin[0] + xs, plane * p.n_outer + n);
+          }
+        } else {
+          const uint32_t buf = u % HB;
+          mbar_wait(&halo_empty[buf], ((u / HB) & 1) ^ 1);
+          mbar_arrive_expect_tx(&halo_full[buf], C::kHaloBytes);
+          tma_load_5d(halo + buf * C::kHaloStride, &map_in, &halo_full[buf], (c - kb * p.nc_block) * (RB / 2),
+                      z0 * p.istride[2] + p.origin[2], y0 * p.istride[1] + p.origin[1],
+                      x0 * p.istride[0] + p.origin[0], plane * p.n_outer + n);
+        }
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -279,9 +300,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
       if (prof) t_acc += clock64() - t0;
       tc_fence_after();
       for (int c = 0; c < p.n_chunks; ++c, ++u) {
-        const uint32_t buf = u % HB;
+        const uint32_t buf = C::kSliced ? 0u : u % HB;
         if (prof) t0 = clock64();
-        mbar_wait(&halo_full[buf], (u / HB) & 1);
+        if constexpr (C::kSliced) {
+#pragma unroll 1
+          for (int xs = 0; xs < TX; ++xs) mbar_wait(&halo_full[xs], u & 1);     // the slices the taps dx = 0 read
+        } else {
+          mbar_wait(&halo_full[buf], (u / HB) & 1);
+        }
         if (prof) t_halo += clock64() - t0;
         // descriptor low words advance in 16-byte units; the high words (SBO, version, layout) never change
         const uint32_t a_lo0 = (uint32_t)a_desc0 + (uint32_t)((buf * C::kHaloStride) >> 4);
@@ -300,6 +326,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
           constexpr uint32_t d_off = (WD == 2 && !WIDE) ? (uint32_t)N : 0u;
           constexpr uint32_t b_step = (uint32_t)((WIDE ? 2 * C::kTapBytes : C::kTapBytes) >> 4);
           for (int g = 0; g < C::kGroups; ++g, ++w) {
+            if constexpr (C::kSliced) {
+              if (g > 0 && g % C::kGroupsPerDx == 0) {      // taps move on to dx = g / kGroupsPerDx
+                const int dxn = g / C::kGroupsPerDx;
+                if (elect_one_sync()) mma_commit(&halo_empty[dxn - 1]);        // slice dx - 1 has been read for the last time
+                if (prof) t0 = clock64();
+                mbar_wait(&halo_full[dxn + TX - 1], u & 1);                   // the one new slice these taps touch
+                if (prof) t_halo += clock64() - t0;
+              }
+            }
             const uint32_t st = w % kWStages;
             if (prof) t0 = clock64();
             mbar_wait(&w_full[st], (w / kWStages) & 1);
@@ -310,7 +345,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
             for (int j = 0; j < G; ++j) {
 #pragma unroll
               for (int t = q; t < TX; t += C::kIssuers) {
-                const uint32_t a_lo = a_tap + (uint32_t)(t * C::HY * C::HZ) * kRow16;
+                const uint32_t a_lo = a_tap + (uint32_t)t * (uint32_t)(C::kSliceStride >> 4);
                 const uint32_t d_tmem = tmem_base + (accbuf * TX + t) * C::kAcc + d_off;
 #pragma unroll
                 for (int k = 0; k < C::kKSteps; ++k)
@@ -325,7 +360,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                 a_tap += (uint32_t)C::HZ * kRow16 - (uint32_t)C::KZ * kPos16;
                 if (++dy == KS) {
                   dy = 0;
-                  a_tap += (uint32_t)((C::HY - KS) * C::HZ) * kRow16;
+                  a_tap += (uint32_t)((C::HY - KS) * C::HZ) * kRow16 + (uint32_t)((C::kSliceStride - C::kSliceBytes) >> 4);
                 }
               }
             }
@@ -334,7 +369,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
         };
         if (WD == 2 && c < p.nc_block) issue_chunk(std::integral_constant<bool, WD == 2>{});
         else issue_chunk(std::false_type{});
-        if (elect_one_sync()) mma_commit(&halo_empty[buf]);
+        if constexpr (C::kSliced) {
+#pragma unroll 1
+          for (int xs = KSX - 1; xs < C::HX; ++xs)
+            if (elect_one_sync()) mma_commit(&halo_empty[xs]);
+        } else {
+          if (elect_one_sync()) mma_commit(&halo_empty[buf]);
+        }
       }
       if (elect_one_sync()) mma_commit(&acc_full[accbuf]);
     }
@@ -915,7 +956,7 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
     cuuint32_t es[5] = {1, (cuuint32_t)a->stride[2], (cuuint32_t)a->stride[1], (cuuint32_t)a->stride[0], 1};
     // with an element stride s the box extent is given in traversed elements: ceil(box / s) elements are loaded
     cuuint32_t box[5] = {(cuuint32_t)(chunk_ch * F), (cuuint32_t)(C::HZ * a->stride[2]), (cuuint32_t)(C::HY * a->stride[1]),
-                         (cuuint32_t)(C::HX * a->stride[0]), 1};
+                         (cuuint32_t)((C::kSliced ? 1 : C::HX) * a->stride[0]), 1};
     if (encode(&map_in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(a->in), gdim, gstr, box, es,
                CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(RB), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
