@@ -234,6 +234,10 @@ int64_t sp3d_conv_head_workspace(const sp3d_conv_args* a);
 /* Debug aid (profiles/conv_stalls.py): when given a device buffer of 148 * 16 uint64, every tensor-core
  * convolution launch writes per-CTA pipeline wait cycles into it (process-global; NULL switches it off). */
 void sp3d_debug_conv_profile(void* dev_u64_buffer);
+/* Debug aid (A/B measurements): 0 (the default) keeps every tensor-core convolution on single CTAs; 1 lets the large
+ * 3^3 / 7^3 launches run as CTA pairs (clusters of two) that share one multicast weight stream.  Same results bit for bit,
+ * and on B200 the same speed. */
+void sp3d_debug_conv_pair(int enable);
 
 /* Max pooling on channel-last activations (window k, stride s, padding p per axis; -inf padding).
  * Replaces F.max_pool3d(k2,s2) (lib/models/v2v_net.py:54) and nn.MaxPool2d(3,2,1)

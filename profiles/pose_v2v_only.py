@@ -21,7 +21,10 @@ ap.add_argument("--cubes", type=int, default=80)
 ap.add_argument("--layers", default="all", help="'stem' = the 7^3 stem only")
 ap.add_argument("--repeat", type=int, default=1)
 ap.add_argument("--stalls", action="store_true", help="print the kernel's own per-CTA wait counters (sp3d_debug_conv_profile)")
+ap.add_argument("--pair", type=int, default=0, help="0: single CTAs only (sp3d_debug_conv_pair), 1: CTA pairs share the weight stream")
 a = ap.parse_args()
+from selfpose3d_b200 import _lib as _l  # noqa: E402
+_l.load().sp3d_debug_conv_pair(a.pair)
 ops.set_volume_dtype(torch.float32)
 ops.set_float32_conv("bf16x3")
 net = v2v_net.V2VNet(15, 15)

@@ -222,6 +222,7 @@ SYMBOLS = {
     "sp3d_conv_fwd": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "sp3d_conv_head_workspace": (C.c_int64, [C.POINTER(ConvArgs)]),
     "sp3d_debug_conv_profile": (None, [C.c_void_p]),
+    "sp3d_debug_conv_pair": (None, [C.c_int]),
     "sp3d_maxpool_fwd": (C.c_int, [C.POINTER(MaxpoolArgs), C.c_void_p]),
     "sp3d_layout_convert": (C.c_int, [C.POINTER(LayoutArgs), C.c_void_p]),
     "sp3d_space_to_depth": (C.c_int, [C.POINTER(S2DArgs), C.c_void_p]),
@@ -271,6 +272,8 @@ def load():
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    if os.environ.get("SP3D_CONV_PAIR") in ("0", "1"):     # A/B switch of the CTA-pair weight multicast (ops.py)
+        lib.sp3d_debug_conv_pair(int(os.environ["SP3D_CONV_PAIR"]))
     return lib
 
 

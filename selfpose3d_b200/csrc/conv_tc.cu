@@ -157,7 +157,11 @@ struct TcCfg {
   static_assert(kSmemBytes + 3072 <= 227 * 1024, "shared memory budget (dynamic + ~3 KB static)");
 };
 
-template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB, int SB, int SR, int EG, int F, int WD>
+// CL = 2: CTA pairs (clusters of two) share the weight stream.  Both CTAs of a pair walk the same stage sequence; each
+// loads HALF of every stage and multicasts it into both shared memories, so the L2 serves every weight byte once per pair
+// (tried against the 13 - 33 % of the MMA warps' time spent waiting on weights in the 3^3 layers; see g_conv_pair below).
+// A stage is recycled when the MMA warps of BOTH CTAs have released it (multicast tcgen05.commit).
+template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB, int SB, int SR, int EG, int F, int WD, int CL>
 __global__ void __launch_bounds__(kTcBaseThreads + 128 * EG, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ TcStoreMaps maps_out, const __grid_constant__ TcStoreMaps maps_res,
@@ -188,7 +192,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
     }
     for (int i = 0; i < kWStages; ++i) {
       mbar_init(&w_full[i], 1);
-      mbar_init(&w_empty[i], C::kIssuers);
+      mbar_init(&w_empty[i], C::kIssuers * CL);
     }
     for (int i = 0; i < EG * SB; ++i) mbar_init(&res_full[0][0] + i, 1);
     fence_barrier_init();
@@ -210,9 +214,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
     if (p.has_res) tma_prefetch_desc(&maps_res.m[0]);
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast to them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);   // warp-uniform for the compiler
+  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
 
   // work item -> (outer index, brick origin in output coordinates, channel tile); the channel tile is the fastest
   // index so that concurrently running CTAs share one input halo through L2
@@ -223,6 +229,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
   const int wi_begin = p.blocked ? (int)blockIdx.x * items_per_cta : (int)blockIdx.x;
   const int wi_end = p.blocked ? min(n_items, wi_begin + items_per_cta) : n_items;
   const int wi_step = p.blocked ? 1 : (int)gridDim.x;
+  // CL = 2 (round-robin items, one channel tile): the odd CTA may own one item less than the even one; it still walks the
+  // weight stages of that item (producer and MMA warps, no MMAs) so that the pair's stage sequences stay identical
+  const int pair_items = CL > 1 ? (n_items - ((int)blockIdx.x & ~1) + wi_step - 1) / wi_step : 0;
+  const int my_items = CL > 1 ? (n_items - (int)blockIdx.x + wi_step - 1) / wi_step : 0;
   auto item_coords = [&](int wi, int& n, int& x0, int& y0, int& z0, int& nt) {
     nt = wi % p.n_tiles;
     const int b = wi / p.n_tiles;
@@ -265,7 +275,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
     // ------------------------------------------------------------------ weight producer (G taps per stage)
     // packed weights: rows ordered [n_tile][chunk][tap][N]; a stage holds taps g*G .. g*G+G-1 of one chunk
     uint32_t w = 0;
-    for (int wi = wi_begin; wi < wi_end; wi += wi_step) {
+    const int wi_end_w = CL > 1 ? wi_begin + pair_items * wi_step : wi_end;
+    for (int wi = wi_begin; wi < wi_end_w; wi += wi_step) {
       const int nt = wi % p.n_tiles;
       int row = nt * p.w_rows_tile;            // rows are consumed in storage order: [chunk][tap][N (or 2 N) rows]
       for (int c = 0; c < p.n_chunks; ++c) {
@@ -275,9 +286,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
           const uint32_t st = w % kWStages;
           mbar_wait(&w_empty[st], ((w / kWStages) & 1) ^ 1);
           mbar_arrive_expect_tx(&w_full[st], (uint32_t)loads * (C::kTapsPerLoad * C::kTapBytes));
+          if constexpr (CL > 1) {
+            // this CTA's half of every box, delivered to both CTAs (data and complete_tx at the same offsets)
+            constexpr int kHalfRows = C::kTapsPerLoad * N / 2, kHalfBytes = C::kTapsPerLoad * C::kTapBytes / 2;
 #pragma unroll 1
-          for (int l = 0; l < loads; ++l, row += C::kTapsPerLoad * N)
-            tma_load_2d(wbuf + st * C::kWStride + l * (C::kTapsPerLoad * C::kTapBytes), &map_w, &w_full[st], 0, row);
+            for (int l = 0; l < loads; ++l, row += C::kTapsPerLoad * N)
+              tma_load_2d_mc(wbuf + st * C::kWStride + l * (C::kTapsPerLoad * C::kTapBytes) + cta_rank * kHalfBytes, &map_w,
+                             &w_full[st], 0, row + (int)cta_rank * kHalfRows, (uint16_t)3);
+          } else {
+#pragma unroll 1
+            for (int l = 0; l < loads; ++l, row += C::kTapsPerLoad * N)
+              tma_load_2d(wbuf + st * C::kWStride + l * (C::kTapsPerLoad * C::kTapBytes), &map_w, &w_full[st], 0, row);
+          }
         }
       }
     }
@@ -364,7 +384,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
                 }
               }
             }
-            if (elect_one_sync()) mma_commit(&w_empty[st]);
+            if (elect_one_sync()) {
+              if constexpr (CL > 1) mma_commit_mc(&w_empty[st], (uint16_t)3);
+              else mma_commit(&w_empty[st]);
+            }
           }
         };
         if (WD == 2 && c < p.nc_block) issue_chunk(std::integral_constant<bool, WD == 2>{});
@@ -378,6 +401,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
         }
       }
       if (elect_one_sync()) mma_commit(&acc_full[accbuf]);
+    }
+    if constexpr (CL > 1) {
+      // the pair's last item has no twin here: release its weight stages unread
+      for (int i = my_items; i < pair_items; ++i)
+        for (int c = 0; c < p.n_chunks; ++c)
+          for (int g = 0; g < C::kGroups; ++g, ++w) {
+            const uint32_t st = w % kWStages;
+            mbar_wait(&w_full[st], (w / kWStages) & 1);
+            if (elect_one_sync()) mma_commit_mc(&w_empty[st], (uint16_t)3);
+          }
     }
     if (prof && q == 0 && lane == 0) {
       unsigned long long* o = p.prof + (size_t)blockIdx.x * kProfSlots;
@@ -843,7 +876,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it
+  else __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
@@ -853,6 +887,11 @@ __global__ void softargmax_merge_kernel(const sp3d_softargmax_args a, int splits
 // Debug only (profiles/conv_stalls.py): a device buffer of 148 * kProfSlots u64 receiving per-CTA wait cycles.
 static unsigned long long* g_conv_prof = nullptr;
 void set_conv_profile(void* dev) { g_conv_prof = static_cast<unsigned long long*>(dev); }
+// CTA-pair weight sharing for the large 3^3 / 7^3 launches.  Off by default: bit-identical results and, measured on B200
+// (profiles/r02_cta_pair_ab.log), the same step time -- the weight waits of the MMA warps are refill LATENCY of the ring,
+// not L2 bandwidth, so halving the L2 reads buys nothing.  Kept behind the switch as the measured experiment.
+static int g_conv_pair = 0;
+void set_conv_pair(int on) { g_conv_pair = on; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -877,9 +916,10 @@ static CUtensorMapSwizzle swizzle_for(int rb) {
                    : (rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (rb == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
 }
 
-template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB, int SB, int SR, int EG, int F, int WD>
+template <int KSX, int KS, int RB, int N, int TX, int G, int S, int HB, int SB, int SR, int EG, int F, int WD, int CL = 1>
 static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
   using C = TcCfg<KSX, KS, RB, N, TX, G, S, HB, SB, SR, EG, F, WD>;
+  static_assert(CL == 1 || (C::kTapsPerLoad * N) % 16 == 0, "pair form: half boxes of whole 8-row swizzle atoms");
   EncodeTiledFn encode = get_encode();
   if (encode == nullptr) return SP3D_ERR_UNSUPPORTED;
   const int chunk_ch = C::kPosBytes / 2;
@@ -967,7 +1007,7 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
     const int64_t rows_tile = (int64_t)C::kTaps * N * (WD == 2 ? 3 * nc_block : n_chunks);
     cuuint64_t gdim[2] = {(cuuint64_t)chunk_ch, (cuuint64_t)(rows_tile * n_tiles)};
     cuuint64_t gstr[1] = {(cuuint64_t)C::kPosBytes};
-    cuuint32_t box[2] = {(cuuint32_t)chunk_ch, (cuuint32_t)(C::kTapsPerLoad * N)};
+    cuuint32_t box[2] = {(cuuint32_t)chunk_ch, (cuuint32_t)(C::kTapsPerLoad * N / CL)};   // pair form: each CTA loads half
     cuuint32_t es[2] = {1, 1};
     if (encode(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a->weight), gdim, gstr, box, es,
                CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(C::kPosBytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1017,7 +1057,7 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   }
-  auto kern = conv_tc_kernel<KSX, KS, RB, N, TX, G, S, HB, SB, SR, EG, F, WD>;
+  auto kern = conv_tc_kernel<KSX, KS, RB, N, TX, G, S, HB, SB, SR, EG, F, WD, CL>;
   {  // opt in to the large dynamic shared memory once per (kernel instance, device)
     static unsigned long long done_mask = 0;
     int dev = 0;
@@ -1029,7 +1069,32 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
     }
   }
   const int items = p.n_bricks * p.n_tiles;
-  const int grid = items < n_sm ? items : n_sm;
+  int grid = items < n_sm ? items : n_sm;
+  if (CL > 1) {
+    // persistent CTA pairs: as many clusters as are co-resident (a second wave would double the run time); small launches
+    // keep the one-CTA form
+    if (head != nullptr || n_tiles != 1 || items < 4 * n_sm) return SP3D_ERR_UNSUPPORTED;
+    static int max_clusters[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int mc = dev < 64 ? max_clusters[dev] : 0;
+    if (mc == 0) {
+      cudaLaunchConfig_t qc = {};
+      qc.gridDim = dim3(n_sm / CL * CL); qc.blockDim = dim3(C::kThreads); qc.dynamicSmemBytes = C::kSmemBytes;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = CL; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      qc.attrs = qa; qc.numAttrs = 1;
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&mc, kern, &qc);
+      if (e != cudaSuccess || mc < 1) {          // no cluster support here (e.g. a partitioned GPU): single-CTA form
+        cudaGetLastError();
+        return SP3D_ERR_UNSUPPORTED;
+      }
+      if (dev < 64) max_clusters[dev] = mc;
+    }
+    grid = (items < CL * mc ? items : CL * mc) / CL * CL;
+    if (grid < CL) return SP3D_ERR_UNSUPPORTED;
+  }
   if (head != nullptr) {
     const int slots = grid * EG;
     const int64_t need = (int64_t)a->N * slots * head->C * 5 * (int64_t)sizeof(double);
@@ -1043,7 +1108,18 @@ static int launch_tc(const sp3d_conv_args* a, cudaStream_t st) {
     p.sa_centers = head->centers; p.sa_center_stride = head->center_stride;
     p.sa_C = head->C; p.sa_slots = slots; p.sa_beta = head->beta;
   }
-  kern<<<grid, C::kThreads, C::kSmemBytes, st>>>(map_in, map_w, maps_out, maps_res, p);
+  if (CL > 1) {
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(C::kThreads); lc.dynamicSmemBytes = C::kSmemBytes; lc.stream = st;
+    cudaLaunchAttribute la[1];
+    la[0].id = cudaLaunchAttributeClusterDimension;
+    la[0].val.clusterDim.x = CL; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+    lc.attrs = la; lc.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&lc, kern, map_in, map_w, maps_out, maps_res, p);
+    if (e != cudaSuccess) { set_last_error(e); return SP3D_ERR_LAUNCH; }
+  } else {
+    kern<<<grid, C::kThreads, C::kSmemBytes, st>>>(map_in, map_w, maps_out, maps_res, p);
+  }
   int rc = check_launch();
   if (rc != SP3D_OK || head == nullptr) return rc;
   const int total = head->n_cubes * head->C;
@@ -1079,6 +1155,15 @@ int conv_tc(const sp3d_conv_args* a, cudaStream_t st) {
 #define SP3D_TC_CASE_W(KSX_, KS_, RB_, N_, TX_, G_, S_, HB_, SB_, SR_, EG_, F_, WD_) \
   if (ksx == KSX_ && ks == KS_ && rb == RB_ && n == N_ && zf == F_ && wd == WD_) \
     return launch_tc<KSX_, KS_, RB_, N_, TX_, G_, S_, HB_, SB_, SR_, EG_, F_, WD_>(a, st);
+  // pair-able: large launches run as CTA pairs sharing the weight stream (CL = 2), the rest as single CTAs
+#define SP3D_TC_CASE_P(KSX_, KS_, RB_, N_, TX_, G_, S_, HB_, SB_, SR_, EG_, F_, WD_) \
+  if (ksx == KSX_ && ks == KS_ && rb == RB_ && n == N_ && zf == F_ && wd == WD_) { \
+    if (g_conv_pair) { \
+      const int rc2 = launch_tc<KSX_, KS_, RB_, N_, TX_, G_, S_, HB_, SB_, SR_, EG_, F_, WD_, 2>(a, st); \
+      if (rc2 != SP3D_ERR_UNSUPPORTED) return rc2; \
+    } \
+    return launch_tc<KSX_, KS_, RB_, N_, TX_, G_, S_, HB_, SB_, SR_, EG_, F_, WD_>(a, st); \
+  }
 #define SP3D_TC_CASE_F(KSX_, KS_, RB_, N_, TX_, G_, S_, HB_, SB_, SR_, EG_, F_) \
   SP3D_TC_CASE_W(KSX_, KS_, RB_, N_, TX_, G_, S_, HB_, SB_, SR_, EG_, F_, 1)
 #define SP3D_TC_CASE(KSX_, KS_, RB_, N_, TX_, G_, S_, HB_, SB_, SR_, EG_) \
@@ -1098,7 +1183,7 @@ int conv_tc(const sp3d_conv_args* a, cudaStream_t st) {
   SP3D_TC_CASE(3, 3, 64, 32, 4, 9, 2, 2, 2, 128, 2)
   SP3D_TC_CASE(3, 3, 64, 64, 4, 3, 3, 2, 2, 64, 2)
   SP3D_TC_CASE(3, 3, 128, 64, 2, 1, 3, 2, 2, 64, 1)
-  SP3D_TC_CASE(3, 3, 128, 128, 2, 1, 2, 2, 2, 32, 1)
+  SP3D_TC_CASE_P(3, 3, 128, 128, 2, 1, 2, 2, 2, 32, 1, 1, 1)
   // adjoint shapes of the training path's input gradients (3^3 32 -> 16 and 64 -> 32: dgrad of 16 -> 32 / 32 -> 64)
   SP3D_TC_CASE(3, 3, 64, 16, 4, 9, 2, 2, 2, 128, 2)
   SP3D_TC_CASE(3, 3, 128, 32, 2, 1, 3, 2, 2, 64, 1)
@@ -1118,18 +1203,19 @@ int conv_tc(const sp3d_conv_args* a, cudaStream_t st) {
   SP3D_TC_CASE(1, 4, 32, 64, 4, 4, 3, 2, 2, 128, 2)
   // split_terms 2 (3 term pairs in 2 K blocks, 2 N accumulator columns): the layers whose narrow channel tile leaves the
   // tensor core waiting on the A operand -- 7^3 stems (z-folded, N = 32) and the 3^3 16 -> 32 layer at N = 32
-  SP3D_TC_CASE_W(7, 7, 64, 32, 4, 8, 2, 1, 2, 128, 1, 2, 2)
+  SP3D_TC_CASE_P(7, 7, 64, 32, 4, 8, 2, 1, 2, 128, 1, 2, 2)
   SP3D_TC_CASE_W(1, 7, 64, 32, 4, 8, 2, 2, 2, 128, 2, 2, 2)
   SP3D_TC_CASE_W(3, 3, 64, 32, 4, 3, 3, 2, 2, 128, 2, 1, 2)
   // 3^3 64 -> 64 (N = 64): 2 x 64 accumulator columns per x-slice at TX = 2, one halo buffer.  (The z-folded 16 / 32 -> 32
   // layers would need TX = 4 with ONE accumulator set: measured slower, 14.0 against 12.5 ms per 80 cubes.)
   // (weight rings sized from the in-kernel wait counters, profiles/r02_conv_stalls.log)
-  SP3D_TC_CASE_W(3, 3, 128, 64, 2, 1, 6, 1, 2, 64, 1, 1, 2)
-  SP3D_TC_CASE_W(3, 3, 128, 64, 2, 4, 3, 1, 2, 128, 1, 2, 2)
-  SP3D_TC_CASE_W(3, 3, 64, 64, 2, 4, 4, 2, 2, 128, 2, 2, 2)
+  SP3D_TC_CASE_P(3, 3, 128, 64, 2, 1, 6, 1, 2, 64, 1, 1, 2)
+  SP3D_TC_CASE_P(3, 3, 128, 64, 2, 4, 3, 1, 2, 128, 1, 2, 2)
+  SP3D_TC_CASE_P(3, 3, 64, 64, 2, 4, 4, 2, 2, 128, 2, 2, 2)
 #undef SP3D_TC_CASE
 #undef SP3D_TC_CASE_F
 #undef SP3D_TC_CASE_W
+#undef SP3D_TC_CASE_P
   return SP3D_ERR_UNSUPPORTED;
 }
 

@@ -15,6 +15,7 @@ void set_last_error(cudaError_t e) {
 int conv_simt_f32(const sp3d_conv_args* a, cudaStream_t st);
 int conv_tc(const sp3d_conv_args* a, cudaStream_t st);
 void set_conv_profile(void* dev);
+void set_conv_pair(int on);
 
 }  // namespace sp3d
 
@@ -34,6 +35,7 @@ extern "C" const char* sp3d_strerror(int status) {
 extern "C" const char* sp3d_last_cuda_error(void) { return sp3d::g_last_error; }
 
 extern "C" void sp3d_debug_conv_profile(void* dev_u64_buffer) { sp3d::set_conv_profile(dev_u64_buffer); }
+extern "C" void sp3d_debug_conv_pair(int enable) { sp3d::set_conv_pair(enable); }
 
 extern "C" int64_t sp3d_conv_head_workspace(const sp3d_conv_args* a) {
   if (a == nullptr || a->head_softargmax == nullptr || a->N < 0) return 0;

@@ -73,6 +73,27 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* map, uin
       : "memory");
 }
 
+// the same box delivered to the same shared-memory offset of every CTA in `mask` of this cluster; each destination CTA's
+// mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const void* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------- clusters
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// every thread of every CTA of the cluster (release / acquire: also orders shared-memory and mbarrier initialisation)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // smem tile -> global through a tiled tensor map (bulk async-group completion); out-of-bounds parts are clipped
 __device__ __forceinline__ void tma_store_5d(const void* map, const void* smem_src, int c0, int c1, int c2, int c3,
                                              int c4) {
@@ -152,6 +173,13 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, ui
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// the same, arriving on the barrier at this shared-memory offset in every CTA of `mask` (cluster)
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }

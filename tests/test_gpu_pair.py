@@ -212,3 +212,31 @@ def test_unproject_pair_output_equals_float32_form(C, cube):
     assert torch.equal(pair.planes[1, ..., :C].cpu().float(), lo)
     assert not pair.planes[..., C:].any()
     assert float(f32.max()) > 0.1
+
+
+# ---- CTA pairs sharing the weight stream (clusters of two, multicast TMA): same bits as the single-CTA launches
+# (k, cin, cout, N cubes, spatial shape): each case is large enough for the pair form (>= 4 items per SM); the 422-long
+# one has an ODD item count, so one CTA of a pair owns an item less than its twin and walks that item's stages unread
+PAIR_CTA_CASES = [(3, 64, 64, 8, (32, 32, 32), True), (3, 32, 32, 4, (32, 32, 64), True), (3, 16, 32, 4, (32, 32, 64), False),
+                  (3, 128, 128, 24, (16, 16, 16), True), (7, 15, 16, 3, (32, 32, 64), False),
+                  (3, 64, 64, 3, (422, 16, 8), True), (3, 32, 32, 3, (422, 16, 16), True)]
+
+
+@pytest.mark.parametrize("k,cin,cout,n,shape,with_res", PAIR_CTA_CASES)
+def test_cta_pair_weight_multicast_is_bit_exact(k, cin, cout, n, shape, with_res):
+    torch.manual_seed(k + cin + cout + n)
+    conv = nn.Conv3d(cin, cout, k, 1, k // 2).to(DEV)
+    bn = rand_bn(nn.BatchNorm3d(cout), cin + cout).float().to(DEV)
+    pc = ops.PackedConv(conv.weight, conv.bias, bn, 1, k // 2, relu=1)
+    xin = ops.split_act(torch.randn(n, *shape, ops.split_pitch(cin), device=DEV), cin)
+    rin = ops.split_act(torch.randn(n, *shape, ops.split_pitch(cout), device=DEV), cout) if with_res else None
+    outs = []
+    try:
+        for pair in (0, 1, 1):
+            ops._lib.load().sp3d_debug_conv_pair(pair)
+            outs.append(pc(xin, residual=rin).planes.clone())
+            torch.cuda.synchronize()
+    finally:
+        ops._lib.load().sp3d_debug_conv_pair(0)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+    assert outs[0].float().abs().max() > 0
