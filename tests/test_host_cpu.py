@@ -182,6 +182,9 @@ def test_tc_case_table_matches_the_kernel_instantiations():
             continue                                   # the macro definitions themselves
         v = [int(t) for t in m.group(2).split(",")]
         cases.add((v[0], v[1], v[2], v[3], v[11] if m.group(1) else 1))
+    # SP3D_TC_CASE_P: the same 13 parameters as _W, also compiled as CTA pairs (CL = 2, behind sp3d_debug_conv_pair)
+    pairable = [[int(t) for t in m.group(1).split(",")] for m in re.finditer(r"^\s*SP3D_TC_CASE_P\(([\d,\s]+)\)\s*$", body, flags=re.M)]
+    cases |= {(v[0], v[1], v[2], v[3], v[11]) for v in pairable if v[12] == 1}
     assert len(cases) >= 20
     assert cases == set(ops.TC_CASES), cases ^ set(ops.TC_CASES)
     # the 2-K-block form of the 3-pair split mode (WD = 2 instantiations) against ops.TC_WIDE_CASES
@@ -190,4 +193,5 @@ def test_tc_case_table_matches_the_kernel_instantiations():
         v = [int(t) for t in m.group(1).split(",")]
         assert v[12] == 2
         wide.add((v[0], v[1], v[2], v[3], v[11]))
+    wide |= {(v[0], v[1], v[2], v[3], v[11]) for v in pairable if v[12] == 2}
     assert wide == set(ops.TC_WIDE_CASES), wide ^ set(ops.TC_WIDE_CASES)
