@@ -23,9 +23,10 @@
 extern "C" {
 #endif
 
-#define SP3D_ABI_VERSION 3   /* 2: sp3d_conv_args.split_terms, sp3d_split_bf16, the backward operators;
+#define SP3D_ABI_VERSION 4   /* 2: sp3d_conv_args.split_terms, sp3d_split_bf16, the backward operators;
                                 3: SP3D_BF16X2 activations, sp3d_merge_bf16, sp3d_s2d_args.dst_dtype, sp3d_gauss_render_*,
-                                   split_terms 2, sp3d_target_heatmaps / sp3d_target_volume, sp3d_conv_wgrad_tc */
+                                   split_terms 2, sp3d_target_heatmaps / sp3d_target_volume, sp3d_conv_wgrad_tc;
+                                4: grouped BatchNorm statistics (sp3d_bn_*_args), sp3d_debug_conv_pair */
 #define SP3D_MAX_VIEWS 8
 #define SP3D_CAM_FLOATS 32
 
@@ -360,39 +361,54 @@ typedef struct {
 } sp3d_conv_wgrad_args;
 int sp3d_conv_wgrad(const sp3d_conv_wgrad_args* a, void* stream);
 
-/* Training-mode BatchNorm on channel-last activations x [P, pitch] (P = all positions of the batch):
+/* Training-mode BatchNorm on channel-last activations x [P, pitch] (P = all positions of the batch; pitch a multiple of
+ * 4, 16-byte aligned tensors):
  *   sp3d_bn_stats: mean[c], var[c] (biased, the normalisation's variance) over P -- F.batch_norm(training=True) of
  *                  nn.BatchNorm{2,3}d (lib/models/v2v_net.py:14,27,30, lib/models/pose_resnet.py:49-...);
  *   sp3d_bn_apply: y = act(x * scale[c] + shift[c] (+ residual)), relu as in sp3d_conv_args (0 / 1 / 2);
  *   sp3d_bn_bwd:   with xhat = (x - mean) * rsqrt(var + eps) and dz = grad_y masked by (y > 0) when `y` is given
  *                  (ReLU directly after the normalisation):
  *                    dgamma = sum dz * xhat,  dbeta = sum dz,
- *                    dx = gamma * rsqrt(var + eps) * (dz - dbeta / P - xhat * dgamma / P). */
+ *                    dx = gamma * rsqrt(var + eps) * (dz - dbeta / P - xhat * dgamma / P).
+ * GROUPED statistics (item_group != NULL): x is n_items equal items of P / n_items positions (the cubes of a launch);
+ * item i belongs to statistic group item_group[i] in [0, n_groups), group g holds group_items[g] items.  Every group is
+ * normalised with ITS OWN batch statistics -- what the reference gets by calling the pose net once per proposal slot
+ * (lib/models/multi_person_posenet.py:88-99) -- in one launch set: mean / var / scale / shift are [n_groups][C],
+ * workspaces n_groups * 2 * C doubles, grad_gamma / grad_beta [C] summed over the groups (shared parameters).
+ * item_group == NULL (n_groups <= 1): one group of P positions. */
 typedef struct {
   const float* x; int64_t P; int C, pitch;
-  float* mean; float* var;  /* [C] outputs */
-  double* workspace;        /* 2 * C doubles */
+  float* mean; float* var;  /* [n_groups][C] outputs */
+  double* workspace;        /* n_groups * 2 * C doubles */
   int64_t workspace_bytes;
+  int n_items, n_groups;
+  const int32_t* item_group;    /* [n_items] or NULL */
+  const int32_t* group_items;   /* [n_groups] items per group (with item_group) */
 } sp3d_bn_stats_args;
 int sp3d_bn_stats(const sp3d_bn_stats_args* a, void* stream);
 
 typedef struct {
   const float* x; const float* residual; float* y;   /* [P, pitch]; residual optional */
   int64_t P; int C, pitch;
-  const float* scale; const float* shift;            /* [C] */
+  const float* scale; const float* shift;            /* [n_groups][C] */
   int relu;
+  int n_items, n_groups;
+  const int32_t* item_group;    /* [n_items] or NULL */
 } sp3d_bn_apply_args;
 int sp3d_bn_apply(const sp3d_bn_apply_args* a, void* stream);
 
 typedef struct {
   const float* x; const float* grad_y; const float* y;   /* [P, pitch]; y optional (ReLU mask) */
   int64_t P; int C, pitch;
-  const float* mean; const float* var; const float* gamma;   /* [C]; gamma NULL = 1 */
+  const float* mean; const float* var; const float* gamma;   /* mean, var [n_groups][C]; gamma [C], NULL = 1 */
   float eps;
   float* grad_x;            /* [P, pitch], written; padding channels get zeros */
   float* grad_gamma; float* grad_beta;   /* [C], written */
-  double* workspace;        /* 2 * C doubles */
+  double* workspace;        /* n_groups * 2 * C doubles */
   int64_t workspace_bytes;
+  int n_items, n_groups;
+  const int32_t* item_group;    /* [n_items] or NULL */
+  const int32_t* group_items;   /* [n_groups] */
 } sp3d_bn_bwd_args;
 int sp3d_bn_bwd(const sp3d_bn_bwd_args* a, void* stream);
 

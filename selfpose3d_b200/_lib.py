@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsp3d.so")
 
-ABI_VERSION = 3      # SP3D_ABI_VERSION of include/sp3d.h these bindings were written against
+ABI_VERSION = 4      # SP3D_ABI_VERSION of include/sp3d.h these bindings were written against
 MAX_VIEWS = 8
 CAM_FLOATS = 32
 F32, BF16, F16, BF16X2 = 0, 1, 2, 3
@@ -155,13 +155,15 @@ class ConvWgradArgs(C.Structure):
 
 class BnStatsArgs(C.Structure):
     _fields_ = [("x", C.c_void_p), ("P", C.c_int64), ("C", C.c_int), ("pitch", C.c_int),
-                ("mean", C.c_void_p), ("var", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
+                ("mean", C.c_void_p), ("var", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+                ("n_items", C.c_int), ("n_groups", C.c_int), ("item_group", C.c_void_p), ("group_items", C.c_void_p)]
 
 
 class BnApplyArgs(C.Structure):
     _fields_ = [("x", C.c_void_p), ("residual", C.c_void_p), ("y", C.c_void_p),
                 ("P", C.c_int64), ("C", C.c_int), ("pitch", C.c_int),
-                ("scale", C.c_void_p), ("shift", C.c_void_p), ("relu", C.c_int)]
+                ("scale", C.c_void_p), ("shift", C.c_void_p), ("relu", C.c_int),
+                ("n_items", C.c_int), ("n_groups", C.c_int), ("item_group", C.c_void_p)]
 
 
 class BnBwdArgs(C.Structure):
@@ -169,7 +171,8 @@ class BnBwdArgs(C.Structure):
                 ("P", C.c_int64), ("C", C.c_int), ("pitch", C.c_int),
                 ("mean", C.c_void_p), ("var", C.c_void_p), ("gamma", C.c_void_p), ("eps", C.c_float),
                 ("grad_x", C.c_void_p), ("grad_gamma", C.c_void_p), ("grad_beta", C.c_void_p),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+                ("n_items", C.c_int), ("n_groups", C.c_int), ("item_group", C.c_void_p), ("group_items", C.c_void_p)]
 
 
 class ReluBwdArgs(C.Structure):

@@ -8,10 +8,40 @@
 """
 from __future__ import annotations
 
+import threading
+
 import torch
 from torch.autograd import Function
 
 from . import _lib, grad_ops, ops
+
+_TLS = threading.local()      # per thread: nn.DataParallel replicas run their forwards on threads
+
+
+class grouped_batches:
+    """``with grouped_batches(counts, device):`` -- every training-mode BatchNorm inside normalises the leading
+    (cube) dimension in GROUPS of ``counts[g]`` consecutive items, each with its own batch statistics, and updates the
+    running statistics as ``len(counts)`` successive calls would.  This is how ONE batched pose-net pass reproduces
+    the reference's one-call-per-proposal-slot training forward (``lib/models/multi_person_posenet.py:88-99``)."""
+
+    def __init__(self, counts, device):
+        self.groups = grad_ops.BnGroups(counts, device) if len(counts) > 1 else None
+
+    def __enter__(self):
+        self.prev = getattr(_TLS, "groups", None)
+        _TLS.groups = self.groups
+        return self.groups
+
+    def __exit__(self, *exc):
+        _TLS.groups = self.prev
+        return False
+
+
+def _active_groups(x):
+    g = getattr(_TLS, "groups", None)
+    if g is not None and int(x.shape[0]) != g.n_items:
+        raise _lib.Sp3dError("grouped BatchNorm: the batch has %d items, the groups cover %d" % (int(x.shape[0]), g.n_items))
+    return g
 
 
 class ToChannelLast(Function):
@@ -68,11 +98,12 @@ class BatchNormAct(Function):
     the statistics are for the caller's running-average update and carry no gradient."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, channels, eps, relu):
-        mean, var = grad_ops.bn_stats(x, channels)
+    def forward(ctx, x, gamma, beta, channels, eps, relu, groups=None):
+        mean, var = grad_ops.bn_stats(x, channels, groups=groups)     # [C], or [n_groups, C]
         scale = gamma * torch.rsqrt(var + eps)                 # [C] vectors: a handful of scalars, not a hot path
-        y = grad_ops.bn_apply(x, channels, scale.contiguous(), (beta - mean * scale).contiguous(), relu=1 if relu else 0)
-        ctx.channels, ctx.eps, ctx.relu = channels, eps, bool(relu)
+        y = grad_ops.bn_apply(x, channels, scale.contiguous(), (beta - mean * scale).contiguous(), relu=1 if relu else 0,
+                              groups=groups)
+        ctx.channels, ctx.eps, ctx.relu, ctx.groups = channels, eps, bool(relu), groups
         ctx.save_for_backward(x, mean, var, gamma, y if relu else None)
         ctx.mark_non_differentiable(mean, var)
         return y, mean, var
@@ -80,8 +111,8 @@ class BatchNormAct(Function):
     @staticmethod
     def backward(ctx, gy, _gm, _gv):
         x, mean, var, gamma, y = ctx.saved_tensors
-        gx, gg, gb = grad_ops.bn_bwd(x, ctx.channels, gy.contiguous(), mean, var, gamma, ctx.eps, y=y)
-        return gx, gg, gb, None, None, None
+        gx, gg, gb = grad_ops.bn_bwd(x, ctx.channels, gy.contiguous(), mean, var, gamma, ctx.eps, y=y, groups=ctx.groups)
+        return gx, gg, gb, None, None, None, None
 
 
 class AddAct(Function):
@@ -133,14 +164,30 @@ def batch_norm(x, bn, relu=False):
     """``nn.BatchNorm{2,3}d`` in training mode on channel-last ``x`` (+ ReLU), with the module's running-statistics
     update (momentum, unbiased running variance, ``num_batches_tracked``) done as ``F.batch_norm`` does it."""
     channels = int(bn.num_features)
-    y, mean, var = BatchNormAct.apply(x, bn.weight, bn.bias, channels, float(bn.eps), relu)
+    groups = _active_groups(x)
+    y, mean, var = BatchNormAct.apply(x, bn.weight, bn.bias, channels, float(bn.eps), relu, groups)
     if bn.track_running_stats and bn.running_mean is not None:
         with torch.no_grad():
             n = x.numel() // int(x.shape[-1])
-            bn.num_batches_tracked += 1
-            m = 1.0 / float(bn.num_batches_tracked) if bn.momentum is None else float(bn.momentum)
-            bn.running_mean.mul_(1.0 - m).add_(mean, alpha=m)
-            bn.running_var.mul_(1.0 - m).add_(var * (n / max(n - 1, 1)), alpha=m)
+            if groups is None:
+                bn.num_batches_tracked += 1
+                m = 1.0 / float(bn.num_batches_tracked) if bn.momentum is None else float(bn.momentum)
+                bn.running_mean.mul_(1.0 - m).add_(mean, alpha=m)
+                bn.running_var.mul_(1.0 - m).add_(var * (n / max(n - 1, 1)), alpha=m)
+            elif bn.momentum is None:
+                per_item = n // groups.n_items
+                for g, c in enumerate(groups.counts):          # cumulative average: the weight changes per call
+                    bn.num_batches_tracked += 1
+                    m = 1.0 / float(bn.num_batches_tracked)
+                    ng = c * per_item
+                    bn.running_mean.mul_(1.0 - m).add_(mean[g], alpha=m)
+                    bn.running_var.mul_(1.0 - m).add_(var[g] * (ng / max(ng - 1, 1)), alpha=m)
+            else:
+                # len(counts) successive momentum updates in closed form: r <- (1-m)^G r + sum_g m (1-m)^(G-1-g) stat_g
+                w, unbias, keep = groups.momentum_weights(float(bn.momentum), n // groups.n_items)
+                bn.num_batches_tracked += groups.n_groups
+                bn.running_mean.mul_(keep).add_(w @ mean)
+                bn.running_var.mul_(keep).add_(w @ (var * unbias[:, None]))
     return y
 
 

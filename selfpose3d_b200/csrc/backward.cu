@@ -305,97 +305,6 @@ __global__ void __launch_bounds__(kWgThreads) conv_wgrad_kernel(const sp3d_conv_
   }
 }
 
-// ------------------------------------------------------------------------------------------ BatchNorm (training)
-// block = (32 channels, 8 positions); per-channel partial sums leave the CTA as double atomics.
-// MODE 0: sum x, sum x^2.   MODE 1: sum dz, sum dz * xhat  (dz = grad_y masked by y > 0 when y is given).
-template <int MODE>
-__global__ void bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ y,
-                                 const float* __restrict__ mean, const float* __restrict__ var, float eps, int64_t P, int C,
-                                 int pitch, double* ws) {
-  __shared__ double s0[8][33], s1[8][33];
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  for (int c0 = 0; c0 < C; c0 += 32) {
-    const int c = c0 + tx;
-    double a0 = 0.0, a1 = 0.0;
-    if (c < C) {
-      const float m = MODE ? mean[c] : 0.0f;
-      const float is = MODE ? 1.0f / sqrtf(var[c] + eps) : 0.0f;
-      for (int64_t p = (int64_t)blockIdx.x * 8 + ty; p < P; p += (int64_t)gridDim.x * 8) {
-        const float xv = __ldg(x + p * pitch + c);
-        if (MODE == 0) {
-          a0 += (double)xv;
-          a1 += (double)xv * (double)xv;
-        } else {
-          float dz = __ldg(dy + p * pitch + c);
-          if (y != nullptr && !(__ldg(y + p * pitch + c) > 0.0f)) dz = 0.0f;
-          a0 += (double)dz;
-          a1 += (double)dz * (double)((xv - m) * is);
-        }
-      }
-    }
-    s0[ty][tx] = a0;
-    s1[ty][tx] = a1;
-    __syncthreads();
-    if (ty == 0 && c < C) {
-      for (int k = 1; k < 8; ++k) { a0 += s0[k][tx]; a1 += s1[k][tx]; }
-      atomicAdd(ws + c, a0);
-      atomicAdd(ws + C + c, a1);
-    }
-    __syncthreads();
-  }
-}
-
-__global__ void bn_stats_finish_kernel(const double* ws, int64_t P, int C, float* mean, float* var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double m = ws[c] / (double)P;
-  double v = ws[C + c] / (double)P - m * m;
-  if (v < 0.0) v = 0.0;
-  mean[c] = (float)m;
-  var[c] = (float)v;
-}
-
-__global__ void bn_apply_kernel(const sp3d_bn_apply_args a) {
-  const int64_t total = a.P * a.pitch;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % a.pitch);
-    float r = 0.0f;
-    if (c < a.C) {
-      r = __ldg(a.x + i) * a.scale[c] + a.shift[c];
-      if (a.relu == 2) r = fmaxf(r, 0.0f);
-      if (a.residual != nullptr) r += __ldg(a.residual + i);
-      if (a.relu == 1) r = fmaxf(r, 0.0f);
-    }
-    a.y[i] = r;
-  }
-}
-
-__global__ void bn_bwd_apply_kernel(const sp3d_bn_bwd_args a) {
-  const int64_t total = a.P * a.pitch;
-  const double invP = 1.0 / (double)a.P;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % a.pitch);
-    float r = 0.0f;
-    if (c < a.C) {
-      const float is = 1.0f / sqrtf(a.var[c] + a.eps);
-      const float xh = (__ldg(a.x + i) - a.mean[c]) * is;
-      float dz = __ldg(a.grad_y + i);
-      if (a.y != nullptr && !(__ldg(a.y + i) > 0.0f)) dz = 0.0f;
-      const float db = (float)(a.workspace[c] * invP), dg = (float)(a.workspace[a.C + c] * invP);
-      const float g = a.gamma != nullptr ? a.gamma[c] : 1.0f;
-      r = g * is * (dz - db - xh * dg);
-    }
-    a.grad_x[i] = r;
-  }
-}
-
-__global__ void bn_bwd_finish_kernel(const double* ws, int C, float* grad_gamma, float* grad_beta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  if (grad_beta != nullptr) grad_beta[c] = (float)ws[c];
-  if (grad_gamma != nullptr) grad_gamma[c] = (float)ws[C + c];
-}
-
 __global__ void relu_bwd_kernel(const sp3d_relu_bwd_args a) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x)
     a.grad_x[i] = __ldg(a.y + i) > 0.0f ? __ldg(a.grad_y + i) : 0.0f;
@@ -559,53 +468,6 @@ extern "C" int sp3d_conv_wgrad(const sp3d_conv_wgrad_args* b, void* stream) {
   if (gx > 2147483647LL || gy > 65535 || gz > 65535) return SP3D_ERR_UNSUPPORTED;
   dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz);
   conv_wgrad_kernel<<<grid, kWgThreads, 0, static_cast<cudaStream_t>(stream)>>>(*b, CT, TL, ppc);
-  return check_launch();
-}
-
-extern "C" int sp3d_bn_stats(const sp3d_bn_stats_args* a, void* stream) {
-  if (a == nullptr || a->x == nullptr || a->mean == nullptr || a->var == nullptr || a->P < 1 || a->C < 1 || a->pitch < a->C)
-    return SP3D_ERR_INVALID_ARG;
-  if (a->workspace == nullptr || a->workspace_bytes < (int64_t)(2 * a->C * sizeof(double)) ||
-      (reinterpret_cast<uintptr_t>(a->workspace) % 8))
-    return SP3D_ERR_WORKSPACE;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(a->workspace, 0, 2 * a->C * sizeof(double), st);
-  if (e != cudaSuccess) { set_last_error(e); return SP3D_ERR_LAUNCH; }
-  bn_reduce_kernel<0><<<grid_for(a->P, 8 * 16, 148 * 4), dim3(32, 8), 0, st>>>(a->x, nullptr, nullptr, nullptr, nullptr, 0.0f,
-                                                                            a->P, a->C, a->pitch, a->workspace);
-  int rc = check_launch();
-  if (rc != SP3D_OK) return rc;
-  bn_stats_finish_kernel<<<(a->C + 127) / 128, 128, 0, st>>>(a->workspace, a->P, a->C, a->mean, a->var);
-  return check_launch();
-}
-
-extern "C" int sp3d_bn_apply(const sp3d_bn_apply_args* a, void* stream) {
-  if (a == nullptr || a->x == nullptr || a->y == nullptr || a->scale == nullptr || a->shift == nullptr || a->P < 0 ||
-      a->C < 1 || a->pitch < a->C || a->relu < 0 || a->relu > 2)
-    return SP3D_ERR_INVALID_ARG;
-  if (a->P == 0) return SP3D_OK;
-  bn_apply_kernel<<<grid_for(a->P * a->pitch, 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
-  return check_launch();
-}
-
-extern "C" int sp3d_bn_bwd(const sp3d_bn_bwd_args* a, void* stream) {
-  if (a == nullptr || a->x == nullptr || a->grad_y == nullptr || a->mean == nullptr || a->var == nullptr ||
-      a->grad_x == nullptr || a->P < 1 || a->C < 1 || a->pitch < a->C)
-    return SP3D_ERR_INVALID_ARG;
-  if (a->workspace == nullptr || a->workspace_bytes < (int64_t)(2 * a->C * sizeof(double)) ||
-      (reinterpret_cast<uintptr_t>(a->workspace) % 8))
-    return SP3D_ERR_WORKSPACE;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(a->workspace, 0, 2 * a->C * sizeof(double), st);
-  if (e != cudaSuccess) { set_last_error(e); return SP3D_ERR_LAUNCH; }
-  bn_reduce_kernel<1><<<grid_for(a->P, 8 * 16, 148 * 4), dim3(32, 8), 0, st>>>(a->x, a->grad_y, a->y, a->mean, a->var, a->eps,
-                                                                            a->P, a->C, a->pitch, a->workspace);
-  int rc = check_launch();
-  if (rc != SP3D_OK) return rc;
-  bn_bwd_apply_kernel<<<grid_for(a->P * a->pitch, 256, 148 * 16), 256, 0, st>>>(*a);
-  rc = check_launch();
-  if (rc != SP3D_OK) return rc;
-  bn_bwd_finish_kernel<<<(a->C + 127) / 128, 128, 0, st>>>(a->workspace, a->C, a->grad_gamma, a->grad_beta);
   return check_launch();
 }
 

@@ -248,23 +248,66 @@ def _flat(x):
     return x.numel() // pitch, pitch
 
 
-def bn_stats(x, channels):
-    """Per-channel batch mean and biased variance of channel-last ``x`` -> ``(mean [C], var [C])``."""
+class BnGroups:
+    """Statistic groups of a batched launch: item ``i`` (a cube of the leading dimension) belongs to group
+    ``item_group[i]``; every group is normalised with its own batch statistics (``include/sp3d.h``, grouped
+    BatchNorm).  ``counts``: items per group (host list, in group order)."""
+
+    def __init__(self, counts, device):
+        self.counts = [int(c) for c in counts]
+        if not self.counts or min(self.counts) < 1:
+            raise ValueError("every BatchNorm group needs at least one item")
+        self.n_groups, self.n_items = len(self.counts), sum(self.counts)
+        ids = [g for g, c in enumerate(self.counts) for _ in range(c)]
+        self.item_group = torch.tensor(ids, dtype=torch.int32).to(device)
+        self.group_items = torch.tensor(self.counts, dtype=torch.int32).to(device)
+        self._weights = {}
+
+    def momentum_weights(self, momentum, positions_per_item):
+        """``(w [G], unbias [G], keep)``: G successive running-average updates with ``momentum`` equal
+        ``r <- keep * r + w @ stats``; ``unbias[g] = n_g / (n_g - 1)`` turns the biased batch variance of group ``g``
+        (``n_g`` positions) into the unbiased one the running variance accumulates."""
+        key = (float(momentum), int(positions_per_item))
+        hit = self._weights.get(key)
+        if hit is None:
+            G, m = self.n_groups, float(momentum)
+            w = torch.tensor([m * (1.0 - m) ** (G - 1 - g) for g in range(G)], dtype=torch.float32)
+            n = [c * int(positions_per_item) for c in self.counts]
+            unbias = torch.tensor([ng / max(ng - 1, 1) for ng in n], dtype=torch.float32)
+            dev = self.item_group.device
+            hit = self._weights[key] = (w.to(dev), unbias.to(dev), (1.0 - m) ** G)
+        return hit
+
+    def fill(self, a, x, with_counts=True):
+        if int(x.shape[0]) != self.n_items:
+            raise ValueError("grouped BatchNorm: %d items expected, tensor has %d" % (self.n_items, int(x.shape[0])))
+        a.n_items, a.n_groups, a.item_group = self.n_items, self.n_groups, self.item_group.data_ptr()
+        if with_counts:
+            a.group_items = self.group_items.data_ptr()
+
+
+def bn_stats(x, channels, groups=None):
+    """Per-channel batch mean and biased variance of channel-last ``x`` -> ``(mean, var)``, each ``[C]`` or, with
+    ``groups`` (``BnGroups``), ``[n_groups, C]``."""
     _f32(x)
     P, pitch = _flat(x)
-    mean = torch.empty(channels, device=x.device, dtype=torch.float32)
+    G = groups.n_groups if groups is not None else 1
+    mean = torch.empty((G, channels) if groups is not None else (channels,), device=x.device, dtype=torch.float32)
     var = torch.empty_like(mean)
-    ws = torch.empty(2 * channels, device=x.device, dtype=torch.float64)
+    ws = torch.empty(G * 2 * channels, device=x.device, dtype=torch.float64)
     a = _lib.BnStatsArgs()
     a.x, a.P, a.C, a.pitch = x.data_ptr(), P, int(channels), pitch
     a.mean, a.var = mean.data_ptr(), var.data_ptr()
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 8
+    if groups is not None:
+        groups.fill(a, x)
     _lib.call("sp3d_bn_stats", a, _stream(), launches=2, kind="bn", work=x.numel() * 4)
     return mean, var
 
 
-def bn_apply(x, channels, scale, shift, relu=0, residual=None):
-    """``act(x * scale[c] + shift[c] (+ residual))`` on channel-last ``x`` (``relu`` as in ``sp3d_conv_args``)."""
+def bn_apply(x, channels, scale, shift, relu=0, residual=None, groups=None):
+    """``act(x * scale[c] + shift[c] (+ residual))`` on channel-last ``x`` (``relu`` as in ``sp3d_conv_args``);
+    ``scale`` / ``shift`` are ``[n_groups, C]`` with ``groups``."""
     _f32(x, scale, shift, residual)
     P, pitch = _flat(x)
     y = torch.empty_like(x)
@@ -273,19 +316,23 @@ def bn_apply(x, channels, scale, shift, relu=0, residual=None):
     a.residual = residual.data_ptr() if residual is not None else None
     a.P, a.C, a.pitch = P, int(channels), pitch
     a.scale, a.shift, a.relu = scale.data_ptr(), shift.data_ptr(), int(relu)
+    if groups is not None:
+        groups.fill(a, x, with_counts=False)
     _lib.call("sp3d_bn_apply", a, _stream(), kind="bn", work=2 * x.numel() * 4)
     return y
 
 
-def bn_bwd(x, channels, grad_y, mean, var, gamma, eps, y=None):
+def bn_bwd(x, channels, grad_y, mean, var, gamma, eps, y=None, groups=None):
     """Backward of training-mode BatchNorm (+ the ReLU right after it when its output ``y`` is given) ->
-    ``(grad_x, grad_gamma, grad_beta)``."""
+    ``(grad_x, grad_gamma, grad_beta)``; with ``groups`` the statistics are ``[n_groups, C]`` and the parameter
+    gradients are summed over the groups."""
     _f32(x, grad_y, mean, var, gamma, y)
     P, pitch = _flat(x)
+    G = groups.n_groups if groups is not None else 1
     gx = torch.empty_like(x)
     gg = torch.empty(channels, device=x.device, dtype=torch.float32)
     gb = torch.empty_like(gg)
-    ws = torch.empty(2 * channels, device=x.device, dtype=torch.float64)
+    ws = torch.empty(G * 2 * channels, device=x.device, dtype=torch.float64)
     a = _lib.BnBwdArgs()
     grad_y = grad_y.contiguous()
     a.x, a.grad_y = x.data_ptr(), grad_y.data_ptr()
@@ -296,6 +343,8 @@ def bn_bwd(x, channels, grad_y, mean, var, gamma, eps, y=None):
     a.eps = float(eps)
     a.grad_x, a.grad_gamma, a.grad_beta = gx.data_ptr(), gg.data_ptr(), gb.data_ptr()
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 8
+    if groups is not None:
+        groups.fill(a, x)
     _lib.call("sp3d_bn_bwd", a, _stream(), launches=3, kind="bn", work=4 * x.numel() * 4)
     return gx, gg, gb
 

@@ -18,7 +18,7 @@ import os
 import torch
 import torch.nn.functional as F
 
-from . import _inference
+from . import _inference, pose_regression_net
 
 GAUSS_SIGMA = 3.0        # reference :419 -- rendering sigma in heat-map pixels
 IMAGE_TO_HEATMAP = 4.0   # reference :416 -- network-input pixels per heat-map pixel (hard-coded there too)
@@ -201,9 +201,18 @@ def forward_train(self, views1, meta1, targets_2d1, weights_2d1, targets_3d1, in
     for hms, meta in sets:
         pred = torch.zeros(B, K, J, 5, device=device)
         pred[:, :, :, 3:] = grid_centers[:, :, 3:].reshape(B, -1, 1, 2)
-        for n in range(K):
-            if bool((flags[:, n] >= 0).any()):
-                pred[:, n, :, 0:3] = self.pose_net(hms, meta, grid_centers[:, n], flip_xcoords=meta[0]["hflip"])
+        if pose_regression_net.SLOT_BATCH:
+            # all slots in one pass, every slot's rows one BatchNorm statistic group (= the reference's per-slot calls)
+            got = self.pose_net.regress_slots(hms, meta, grid_centers, flags, flip_xcoords=meta[0]["hflip"])
+            if got is not None:
+                joints, slots, samples = got
+                idx = (torch.tensor(samples, device=device), torch.tensor(slots, device=device))
+                xyz = torch.zeros(B, K, J, 3, device=device).index_put(idx, joints)
+                pred = torch.cat([xyz, pred[..., 3:]], dim=-1)
+        else:
+            for n in range(K):
+                if bool((flags[:, n] >= 0).any()):
+                    pred[:, n, :, 0:3] = self.pose_net(hms, meta, grid_centers[:, n], flip_xcoords=meta[0]["hflip"])
         preds.append(pred)
     pred_out = preds[-1].detach().clone()
     n_valid = [int((flags[b] >= 0).sum()) for b in range(B)]

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import pose_resnet
-from . import _inference
+from . import _inference, pose_regression_net
 from .cuboid_proposal_net import CuboidProposalNet
 from .pose_regression_net import PoseRegressionNet
 
@@ -112,10 +112,18 @@ def _forward_train(self, views, meta, targets_2d, weights_2d, targets_3d, input_
     count = 0
     has_gt = "joints_3d" in meta[0] and "joints_3d_vis" in meta[0]
     flags = grid_centers[:, :, 3].detach().cpu()                       # one host sync (the reference: one per slot)
+    batched = None
+    if pose_regression_net.SLOT_BATCH:
+        # all slots in one pass, every slot's rows one BatchNorm statistic group (= the reference's per-slot calls)
+        got = self.pose_net.regress_slots(all_heatmaps, meta, grid_centers, flags)
+        if got is not None:
+            joints, slots, samples = got
+            idx = (torch.tensor(samples, device=device), torch.tensor(slots, device=device))
+            batched = torch.zeros(B, self.num_cand, self.num_joints, 3, device=device).index_put(idx, joints)
     for n in range(self.num_cand):
         if not bool((flags[:, n] >= 0).any()):
             continue
-        single_pose = self.pose_net(all_heatmaps, meta, grid_centers[:, n])
+        single_pose = batched[:, n] if batched is not None else self.pose_net(all_heatmaps, meta, grid_centers[:, n])
         pred[:, n, :, 0:3] = single_pose.detach()
         if has_gt:
             gt_3d = meta[0]["joints_3d"].float().to(device)

@@ -9,12 +9,19 @@ calls it.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
 from .. import ops
 from .project_layer import ProjectLayer
 from .v2v_net import V2VNet
+
+
+# Training forwards run all proposal slots of a step through the pose net in ONE pass (grouped BatchNorm statistics keep
+# the reference's per-slot batches); SP3D_SLOT_BATCH=0 keeps one pass per slot (A/B checks).
+SLOT_BATCH = os.environ.get("SP3D_SLOT_BATCH", "1") != "0"
 
 
 class SoftArgmaxLayer(nn.Module):
@@ -54,14 +61,16 @@ class PoseRegressionNet(nn.Module):
         self.v2v_net = V2VNet(cfg.NETWORK.NUM_JOINTS, cfg.NETWORK.NUM_JOINTS)
         self.soft_argmax_layer = SoftArgmaxLayer(cfg)
 
-    def regress(self, all_heatmaps, cams, centers, cube_sample, chunk=None):
+    def regress(self, all_heatmaps, cams, centers, cube_sample, chunk=None, group_counts=None):
         """Joints of ``n`` person cubes: ``centers [n,>=3]`` (all valid), ``cube_sample [n]`` int32
         sample index of each cube -> ``[n, J, 3]`` world mm.  Cubes are processed ``chunk`` at a
-        time to bound activation memory (a 64^3 cube needs ~0.4 GB of float32 activations)."""
+        time to bound activation memory (a 64^3 cube needs ~0.4 GB of float32 activations).
+        ``group_counts`` (training mode): the cubes are consecutive groups of that many items, each normalised with
+        its own batch statistics (``autograd.grouped_batches``) -- one pass for all proposal slots of a step."""
         n = int(centers.shape[0])
         J = self.num_joints
         if self.training:
-            return self._regress_train(all_heatmaps, cams, centers, cube_sample)
+            return self._regress_train(all_heatmaps, cams, centers, cube_sample, group_counts)
         if chunk is None:
             import os
             # bf16 activations of one 64^3 cube through V2VNet peak at ~0.2 GB (float32: ~0.4 GB)
@@ -96,7 +105,7 @@ class PoseRegressionNet(nn.Module):
                                       self.grid_size, self.soft_argmax_layer.beta)
         return out
 
-    def _regress_train(self, all_heatmaps, cams, centers, cube_sample):
+    def _regress_train(self, all_heatmaps, cams, centers, cube_sample, group_counts=None):
         """``.train()`` mode: the same three steps under autograd (``selfpose3d_b200.autograd``) -- gradients reach the
         heat-maps (and through them the backbone) and the V2VNet parameters, as in the reference's training forward
         (``lib/models/multi_person_posenet_ssv.py:330-407`` calls this module under autograd).  float32 only."""
@@ -108,8 +117,36 @@ class PoseRegressionNet(nn.Module):
         spec = ([float(v) for v in self.grid_size], [int(v) for v in self.cube_size], self.project_layer.img_size,
                 self.project_layer.heatmap_size, J, ops.round_up(J, 4))
         cubes = ag.Unproject.apply(cams, centers, cube_sample, spec, *hms)
-        y = self.v2v_net.forward_cl(cubes)
+        if group_counts is not None and sum(group_counts) != int(centers.shape[0]):
+            raise ValueError("group_counts must cover the %d cubes" % int(centers.shape[0]))
+        with ag.grouped_batches(group_counts if group_counts is not None else [int(centers.shape[0])], cubes.device):
+            y = self.v2v_net.forward_cl(cubes)
         return ag.SoftArgmax.apply(y, centers, (J, spec[1], spec[0], float(self.soft_argmax_layer.beta)))
+
+    def regress_slots(self, all_heatmaps, meta, grid_centers, flags, flip_xcoords=None):
+        """Training forward of ALL proposal slots in one pass: what the reference gets from
+        ``for n in range(num_cand): pose_net(all_heatmaps, meta, grid_centers[:, n])`` (one call per slot with at least one
+        valid row, V2VNet on that slot's valid rows: ``lib/models/multi_person_posenet.py:88-99``), with every slot's
+        rows as one BatchNorm statistic group.  ``grid_centers [B,K,>=4]``, ``flags``: its ``[..., 3]`` on the host.
+        Returns ``(joints [n,J,3], slot [n], sample [n])`` in slot-major order (host lists), or ``None`` when no slot
+        is valid."""
+        device = all_heatmaps[0].device
+        B, K = int(grid_centers.shape[0]), int(grid_centers.shape[1])
+        slots, samples, counts = [], [], []
+        for n in range(K):
+            rows = [i for i in range(B) if float(flags[i, n]) >= 0]
+            if rows:
+                counts.append(len(rows))
+                slots += [n] * len(rows)
+                samples += rows
+        if not counts:
+            return None
+        cams = ops.pack_cameras(meta, self.project_layer.img_size, flip_xcoords).to(device, non_blocking=True)
+        si = torch.tensor(samples, device=device, dtype=torch.long)
+        ni = torch.tensor(slots, device=device, dtype=torch.long)
+        centers = grid_centers.to(device=device, dtype=torch.float32)[si, ni].contiguous()
+        joints = self.regress(all_heatmaps, cams, centers, si.to(torch.int32), group_counts=counts)
+        return joints, slots, samples
 
     def forward(self, all_heatmaps, meta, grid_centers, flip_xcoords=None):
         device = all_heatmaps[0].device

@@ -67,6 +67,14 @@ class _PackedCache:
         self.slots = {}
         self.lock = threading.Lock()
 
+    # copy.deepcopy(model) / pickling: a copy starts with an empty cache (the packed tensors are derived data keyed by
+    # the ORIGINAL parameters' storage; the lock is not copyable)
+    def __deepcopy__(self, memo):
+        return _PackedCache()
+
+    def __reduce__(self):
+        return (_PackedCache, ())
+
     def get(self, module, build):
         tensors = list(module.parameters()) + list(module.buffers())
         key = tuple((t.data_ptr(), t._version) for t in tensors)

@@ -38,12 +38,26 @@ def _maxpool_bwd(x, channels, k, s, p, gy):
     return xc.grad.permute(0, 2, 3, 4, 1).contiguous()
 
 
-def _bn_stats(x, channels):
+def _group_slices(groups):
+    out, o = [], 0
+    for c in groups.counts:
+        out.append(slice(o, o + c))
+        o += c
+    return out
+
+
+def _bn_stats(x, channels, groups=None):
+    if groups is not None:      # grouped statistics: every group of items on its own
+        st = [_bn_stats(x[sl], channels) for sl in _group_slices(groups)]
+        return torch.stack([m for m, _ in st]), torch.stack([v for _, v in st])
     v = x.reshape(-1, x.shape[-1])[:, :channels].double()
     return v.mean(0).float(), v.var(0, unbiased=False).float()
 
 
-def _bn_apply(x, channels, scale, shift, relu=0, residual=None):
+def _bn_apply(x, channels, scale, shift, relu=0, residual=None, groups=None):
+    if groups is not None:
+        return torch.cat([_bn_apply(x[sl], channels, scale[g], shift[g], relu, None if residual is None else residual[sl])
+                          for g, sl in enumerate(_group_slices(groups))])
     y = torch.zeros_like(x)
     r = x[..., :channels] * scale + shift
     if relu == 2:
@@ -56,7 +70,11 @@ def _bn_apply(x, channels, scale, shift, relu=0, residual=None):
     return y
 
 
-def _bn_bwd(x, channels, grad_y, mean, var, gamma, eps, y=None):
+def _bn_bwd(x, channels, grad_y, mean, var, gamma, eps, y=None, groups=None):
+    if groups is not None:
+        parts = [_bn_bwd(x[sl], channels, grad_y[sl], mean[g], var[g], gamma, eps, None if y is None else y[sl])
+                 for g, sl in enumerate(_group_slices(groups))]
+        return (torch.cat([p[0] for p in parts]), sum(p[1] for p in parts), sum(p[2] for p in parts))
     P = x.numel() // x.shape[-1]
     xs, dz = x[..., :channels].double(), grad_y[..., :channels].double()
     if y is not None:

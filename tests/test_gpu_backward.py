@@ -218,6 +218,41 @@ def test_batchnorm_training_ops_vs_autograd(C, shape, with_relu):
     assert rel_err(gb.cpu().numpy(), beta.grad.numpy()) <= 2e-5
 
 
+@pytest.mark.parametrize("C,shape,counts", [(16, (6, 6, 4), [1, 3, 2]), (32, (4, 4, 8), [2, 2]), (15, (3, 5, 8), [1, 1, 1, 1]),
+                                            (128, (2, 2, 2), [3, 1]), (1, (4, 4, 4), [2, 1])])
+def test_grouped_batchnorm_equals_one_call_per_group(C, shape, counts):
+    """Grouped statistics (include/sp3d.h: item_group / group_items): ONE launch set over all items must give what one
+    call per group gives -- statistics, outputs, input gradients -- and the parameter gradients summed over groups."""
+    torch.manual_seed(C + len(counts))
+    n = sum(counts)
+    pitch = ops.round_up(C, 4)
+    x = (torch.randn(n, *shape, pitch, device=DEV) * 2 + 0.5) * torch.linspace(0.5, 2.0, n, device=DEV).view(n, 1, 1, 1, 1)
+    gy = torch.randn_like(x)
+    res = torch.randn_like(x)
+    gamma, beta = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.2
+    groups = grad_ops.BnGroups(counts, DEV)
+    mean, var = grad_ops.bn_stats(x, C, groups=groups)
+    assert mean.shape == (len(counts), C)
+    scale = gamma * torch.rsqrt(var + 1e-5)
+    y = grad_ops.bn_apply(x, C, scale.contiguous(), (beta - mean * scale).contiguous(), relu=1, residual=res, groups=groups)
+    gx, gg, gb = grad_ops.bn_bwd(x, C, gy, mean, var, gamma, 1e-5, y=y, groups=groups)
+    o, gg_ref, gb_ref = 0, 0, 0
+    for g, c in enumerate(counts):
+        sl = slice(o, o + c)
+        o += c
+        m1, v1 = grad_ops.bn_stats(x[sl], C)
+        assert torch.allclose(m1, mean[g], rtol=1e-6, atol=1e-7) and torch.allclose(v1, var[g], rtol=1e-5, atol=1e-7)
+        s1 = gamma * torch.rsqrt(v1 + 1e-5)
+        y1 = grad_ops.bn_apply(x[sl], C, s1, beta - m1 * s1, relu=1, residual=res[sl])
+        assert torch.allclose(y1, y[sl], rtol=1e-5, atol=1e-5)
+        gx1, gg1, gb1 = grad_ops.bn_bwd(x[sl], C, gy[sl], m1, v1, gamma, 1e-5, y=y1)
+        assert rel_err(gx[sl].cpu().numpy(), gx1.cpu().numpy()) <= 2e-5
+        gg_ref, gb_ref = gg_ref + gg1, gb_ref + gb1
+    assert rel_err(gg.cpu().numpy(), gg_ref.cpu().numpy()) <= 2e-5 and rel_err(gb.cpu().numpy(), gb_ref.cpu().numpy()) <= 2e-5
+    if pitch > C:
+        assert not y[..., C:].any() and not gx[..., C:].any()
+
+
 def test_basic3d_block_training_step_matches_reference_gradient(golden):
     """conv 3^3 -> batch-statistics BatchNorm -> ReLU (lib/models/v2v_net.py:10-20 in .train()) forward and backward
     composed from the operators, against the gradients recorded from the reference module."""

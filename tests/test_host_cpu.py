@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.sp3d_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.sp3d_abi_version() == _lib.ABI_VERSION == 4
     assert lib.sp3d_strerror(-1) == b"invalid argument"
 
 

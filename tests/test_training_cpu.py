@@ -348,3 +348,55 @@ def test_render_kernel_wrapper_equals_the_tensor_expression(monkeypatch):
         for b in range(B):
             if counts[b]:
                 assert torch.allclose(base[v][b].grad, grads[v][b], rtol=1e-4, atol=1e-7)
+
+
+def test_slot_batched_pose_net_equals_one_pass_per_slot(emulated, monkeypatch):  # noqa: F811
+    """``PoseRegressionNet.regress_slots`` (all proposal slots in one pass, grouped BatchNorm statistics) against the
+    reference's structure -- one training forward per slot on that slot's valid rows: joints, heat-map gradients,
+    parameter gradients and the running statistics after the step."""
+    import copy
+    from selfpose3d_b200 import autograd as ag
+    from selfpose3d_b200.models import pose_regression_net
+    monkeypatch.setattr(ag.Unproject, "apply", staticmethod(emul_unproject))
+    monkeypatch.setattr(ag.SoftArgmax, "apply", staticmethod(emul_softargmax))
+    ops.set_volume_dtype(torch.float32)
+    cfg = default_config()
+    cfg.NETWORK.NUM_JOINTS = 3
+    cfg.NETWORK.IMAGE_SIZE, cfg.NETWORK.HEATMAP_SIZE = [64, 48], [16, 12]
+    cfg.PICT_STRUCT.CUBE_SIZE = [8, 8, 8]
+    torch.manual_seed(3)
+    net_a = pose_regression_net.PoseRegressionNet(cfg).train()
+    net_b = copy.deepcopy(net_a)
+    B, V, K = 3, 2, 3
+    meta = synthetic.make_meta(synthetic.ring_cameras(V, seed=1), B, (64, 48))
+    hms_a = [torch.rand(B, 3, 12, 16, requires_grad=True) for _ in range(V)]
+    hms_b = [h.detach().clone().requires_grad_(True) for h in hms_a]
+    gc = torch.zeros(B, K, 5)
+    gc[..., :3] = torch.randn(B, K, 3) * 300
+    gc[..., 3] = torch.tensor([[0, 1, -1], [0, -1, -1], [1, 0, -1]], dtype=torch.float32)     # slot 2: no valid row
+    flags = gc[:, :, 3]
+    # (a) one pass for all slots
+    joints, slots, samples = net_a.regress_slots(hms_a, meta, gc, flags)
+    assert slots == [0, 0, 0, 1, 1] and samples == [0, 1, 2, 0, 2]
+    w = torch.randn_like(joints)
+    (joints * w).sum().backward()
+    # (b) the reference's loop
+    out, o = [], 0
+    for n in range(K):
+        if bool((flags[:, n] >= 0).any()):
+            single = net_b(hms_b, meta, gc[:, n])
+            rows = [i for i in range(B) if flags[i, n] >= 0]
+            out.append(single[rows])
+    ref = torch.cat(out)
+    (ref * w).sum().backward()
+    assert float((joints - ref).detach().abs().max()) <= 1e-3 * max(1.0, float(ref.detach().abs().max()))
+    for ha, hb in zip(hms_a, hms_b):
+        assert float((ha.grad - hb.grad).abs().max()) <= 1e-4 * float(hb.grad.abs().max())
+    # (a convolution bias in front of a batch-statistics BatchNorm has an exactly zero gradient: what both routes
+    #  compute there is rounding noise, so the bar is relative to the largest gradient of the net)
+    top = max(float(p.grad.abs().max()) for p in net_b.parameters())
+    for (name, pa), (_, pb) in zip(net_a.named_parameters(), net_b.named_parameters()):
+        scale = max(float(pb.grad.abs().max()), 1e-12)
+        assert float((pa.grad - pb.grad).abs().max()) <= max(2e-4 * scale, 2e-5 * top), name
+    for (name, ba), (_, bb) in zip(net_a.named_buffers(), net_b.named_buffers()):
+        assert torch.allclose(ba.float(), bb.float(), rtol=1e-5, atol=1e-6), name
