@@ -16,6 +16,7 @@ from selfpose3d_b200.models import multi_person_posenet_ssv  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch-per-gpu", type=int, default=2)
 ap.add_argument("--proposals", type=int, default=4)
+ap.add_argument("--cprofile", action="store_true", help="host-side profile of one step (top functions by own time)")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 cfg = bench.make_cfg(a.batch_per_gpu)
@@ -44,6 +45,15 @@ t0 = time.perf_counter()
 step()
 torch.cuda.synchronize()
 wall = (time.perf_counter() - t0) * 1e3
+if a.cprofile:
+    import cProfile
+    import pstats
+    pr = cProfile.Profile()
+    pr.enable()
+    step()
+    torch.cuda.synchronize()
+    pr.disable()
+    pstats.Stats(pr).sort_stats("tottime").print_stats(28)
 profiler.enable()
 step()
 profiler.disable()

@@ -28,7 +28,7 @@ def _heatmaps(backbone, views, given):
     """One backbone call per view, as the reference (:227-277): the BatchNorm batches are the per-view batches."""
     if views is None:
         return [h if h.is_cuda else h.cuda() for h in given]
-    return [backbone(view) for view in views]
+    return backbone.forward_views(views)      # (one pass, one BatchNorm statistic group per view)
 
 
 def project_to_views(poses, camera, trans):
@@ -143,9 +143,9 @@ def forward_train(self, views1, meta1, targets_2d1, weights_2d1, targets_3d1, in
     attn1 = attn2 = None
     if self.WITH_ATTN:
         if views1 is not None:
-            attn1 = torch.stack([self.attn(view) for view in views1], 0)
+            attn1 = torch.stack(self.attn.forward_views(views1), 0)
         if views2 is not None:
-            attn2 = torch.stack([self.attn(view) for view in views2], 0)
+            attn2 = torch.stack(self.attn.forward_views(views2), 0)
     heatmaps1 = _heatmaps(self.backbone, views1, input_heatmaps1)
     heatmaps2 = _heatmaps(self.backbone, views2, input_heatmaps2)
     device = heatmaps1[0].device

@@ -84,7 +84,7 @@ def _forward_train(self, views, meta, targets_2d, weights_2d, targets_3d, input_
     (``.eval()``) runs the fused inference kernels on all views at once and its heat-maps enter as constants."""
     if views is not None:
         if self.backbone.training:
-            all_heatmaps = [self.backbone(view) for view in views]
+            all_heatmaps = self.backbone.forward_views(views)      # one pass, one BatchNorm statistic group per view
         else:
             with torch.no_grad():
                 all_heatmaps = _inference.backbone_heatmaps(self.backbone, views)

@@ -87,6 +87,11 @@ class BasicBlock(nn.Module):
         return b(a(x), residual=x if d is None else d(x))
 
 
+# Training forwards over several views run as ONE pass with one BatchNorm statistic group per view
+# (PoseResNet.forward_views); SP3D_SLOT_BATCH=0 keeps one pass per view (A/B checks).
+_VIEW_BATCH = os.environ.get("SP3D_SLOT_BATCH", "1") != "0"
+
+
 class Bottleneck(nn.Module):
     expansion = 4
 
@@ -244,6 +249,21 @@ class PoseResNet(nn.Module):
             return out, feat[:, 0].permute(0, 3, 1, 2)[:, :feat.shape[-1]]
         return out
 
+    def forward_views(self, views):
+        """``[backbone(view) for view in views]`` -- the reference's one call per view
+        (``lib/models/multi_person_posenet_ssv.py:227-277``, ``multi_person_posenet.py:38-41``) -- in ONE pass in
+        training mode: the views are concatenated and every view is a BatchNorm statistic group of its own
+        (``autograd.grouped_batches``), so batch statistics, gradients and the running-average updates are those of the
+        per-view calls, at a fifth of the launches."""
+        views = list(views)
+        if not self.training or len(views) < 2 or not _VIEW_BATCH:
+            return [self(view) for view in views]
+        counts = [int(v.shape[0]) for v in views]
+        x = torch.cat([v.float() for v in views], dim=0)
+        with ag.grouped_batches(counts, x.device):
+            y = self(x)
+        return list(torch.split(y, counts, dim=0))
+
     def init_weights(self, pretrained="", mapping=None):
         """Reference :209-262: load an ImageNet/COCO checkpoint if the file exists (remapping the
         final layer to the Panoptic joint order), else N(0, 0.001) weights and unit BatchNorm."""
@@ -312,6 +332,9 @@ class PoseResAttnNet(nn.Module):
 
     def forward(self, x):
         return self.sigmoid(self.backbone(x))
+
+    def forward_views(self, views):
+        return [self.sigmoid(y) for y in self.backbone.forward_views(views)]
 
     def init_weights(self, pretrained="", mapping=None):
         self.backbone.init_weights(pretrained, mapping)
