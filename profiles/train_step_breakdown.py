@@ -15,6 +15,7 @@ from selfpose3d_b200 import ops, profiler  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--mode", default="bf16x3")
+ap.add_argument("--cprofile", action="store_true", help="host-side profile of one step (top functions by own time)")
 a = ap.parse_args()
 ops.set_volume_dtype(torch.float32)
 ops.set_float32_conv(a.mode)
@@ -26,6 +27,15 @@ t0 = time.perf_counter()
 step()
 torch.cuda.synchronize()
 wall = (time.perf_counter() - t0) * 1e3
+if a.cprofile:
+    import cProfile
+    import pstats
+    pr = cProfile.Profile()
+    pr.enable()
+    step()
+    torch.cuda.synchronize()
+    pr.disable()
+    pstats.Stats(pr).sort_stats("tottime").print_stats(25)
 profiler.enable()
 step()
 profiler.disable()

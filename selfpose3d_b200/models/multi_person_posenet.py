@@ -120,14 +120,15 @@ def _forward_train(self, views, meta, targets_2d, weights_2d, targets_3d, input_
             joints, slots, samples = got
             idx = (torch.tensor(samples, device=device), torch.tensor(slots, device=device))
             batched = torch.zeros(B, self.num_cand, self.num_joints, 3, device=device).index_put(idx, joints)
+    if has_gt:
+        gt_3d = meta[0]["joints_3d"].float().to(device)
+        vis = meta[0]["joints_3d_vis"].float().to(device)
     for n in range(self.num_cand):
         if not bool((flags[:, n] >= 0).any()):
             continue
         single_pose = batched[:, n] if batched is not None else self.pose_net(all_heatmaps, meta, grid_centers[:, n])
         pred[:, n, :, 0:3] = single_pose.detach()
         if has_gt:
-            gt_3d = meta[0]["joints_3d"].float().to(device)
-            vis = meta[0]["joints_3d_vis"].float().to(device)
             for i in range(B):
                 if flags[i, n] >= 0:
                     g = int(flags[i, n])
