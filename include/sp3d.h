@@ -26,7 +26,7 @@ extern "C" {
 #define SP3D_ABI_VERSION 4   /* 2: sp3d_conv_args.split_terms, sp3d_split_bf16, the backward operators;
                                 3: SP3D_BF16X2 activations, sp3d_merge_bf16, sp3d_s2d_args.dst_dtype, sp3d_gauss_render_*,
                                    split_terms 2, sp3d_target_heatmaps / sp3d_target_volume, sp3d_conv_wgrad_tc;
-                                4: grouped BatchNorm statistics (sp3d_bn_*_args), sp3d_debug_conv_pair */
+                                4: grouped BatchNorm statistics (sp3d_bn_*_args), sp3d_debug_conv_pair, general sp3d_conv_wgrad_tc_args */
 #define SP3D_MAX_VIEWS 8
 #define SP3D_CAM_FLOATS 32
 
@@ -441,21 +441,28 @@ typedef struct {
 } sp3d_gauss_render_bwd_args;
 int sp3d_gauss_render_bwd(const sp3d_gauss_render_bwd_args* a, void* stream);
 
-/* Weight (and bias) gradient of a stride-1 "same" 3-D convolution with a cubic kernel (k = 1, 3, 7) on the tensor cores:
- *   grad_weight[tap, ci, co] += sum_p x[p + off(tap), ci] * grad_out[p, co],   grad_bias[co] += sum_p grad_out[p, co]
- * taps ordered (kd, kh, kw), off = tap - (k-1)/2 per axis, zero padding.  float32 channel-last operands are used as sums
- * of two bf16 terms with three term pairs accumulated in float32 (the arithmetic of SP3D_CONV_TC_BF16X3); the contraction
- * over positions runs as a tcgen05 GEMM on channel-first z-lines staged in `workspace` (csrc/conv_wgrad_tc.cu).
- * Needs cin, cout <= 128 with round_up(cin, 16) in {16, 32, 64, 128}, and Z = 16, 32 or a multiple of 64; anything else
- * returns SP3D_ERR_UNSUPPORTED (callers fall back to sp3d_conv_wgrad).  Replaces cudnn's wgrad for the nn.Conv3d layers
- * of lib/models/v2v_net.py:10-45,124 in the training step (lib/core/function.py:27-217). */
+/* Weight (and bias) gradient on the tensor cores, for convolutions whose taps step by one input position per output
+ * position -- stride-1 convolutions (3-D, or 2-D with X = 1) and each output phase of a stride-s transposed convolution:
+ *   grad_weight[tap, ci, co] += sum_p x[p + tap_off + tap, ci] * grad_out[p * g_stride + g_off, co]
+ *   grad_bias[co]            += sum_p grad_out[p * g_stride + g_off, co]
+ * p runs over the position grid [N, X, Y, Z] (= x's extent), taps are ordered (kx, ky, kz), reads outside x are zero (the
+ * padding).  float32 channel-last operands are used as sums of two bf16 terms with three term pairs accumulated in
+ * float32 (the arithmetic of SP3D_CONV_TC_BF16X3); the contraction over positions runs as a tcgen05 GEMM on channel-first
+ * z-lines staged in `workspace` (csrc/conv_wgrad_tc.cu).  Needs Z <= 128, round_up(cin, 16) in {16, 32, 64} or cin > 64
+ * (padded to multiples of 128), cout <= 128 or a multiple of 128, taps <= 7 per axis; anything else returns
+ * SP3D_ERR_UNSUPPORTED (callers fall back to sp3d_conv_wgrad).  Replaces cudnn's wgrad for nn.Conv3d / nn.ConvTranspose3d
+ * of lib/models/v2v_net.py:10-69,124 and the stride-1 nn.Conv2d / nn.ConvTranspose2d of lib/models/pose_resnet.py in the
+ * training step (lib/core/function.py:27-217). */
 typedef struct {
   const float* x;           /* [N, X, Y, Z, x_pitch] forward input */
-  const float* grad_out;    /* [N, X, Y, Z, g_pitch] gradient of the raw convolution result */
+  const float* grad_out;    /* [N, GX, GY, GZ, g_pitch] gradient of the raw convolution result */
   int N, X, Y, Z;
   int cin, x_pitch, cout, g_pitch;
-  int k;
-  float* grad_weight;       /* [k^3, gw_cin, gw_pitch] float32, ADDED into (zero it first) */
+  int ksize[3];             /* taps per axis */
+  int tap_off[3];           /* input offset of tap 0 per axis (-padding for a "same" convolution) */
+  int GX, GY, GZ;           /* extent of grad_out */
+  int g_stride[3], g_off[3];/* gradient position of grid position p: p * g_stride + g_off (1 / 0 for a convolution) */
+  float* grad_weight;       /* [taps, gw_cin, gw_pitch] float32, ADDED into (zero it first) */
   int gw_cin, gw_pitch;
   float* grad_bias;         /* [cout], added into; or NULL */
   void* workspace;          /* sp3d_conv_wgrad_tc_workspace(args) bytes, 16-byte aligned */

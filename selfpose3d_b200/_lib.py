@@ -192,7 +192,9 @@ class GaussRenderBwdArgs(C.Structure):
 class ConvWgradTcArgs(C.Structure):
     _fields_ = [("x", C.c_void_p), ("grad_out", C.c_void_p),
                 ("N", C.c_int), ("X", C.c_int), ("Y", C.c_int), ("Z", C.c_int),
-                ("cin", C.c_int), ("x_pitch", C.c_int), ("cout", C.c_int), ("g_pitch", C.c_int), ("k", C.c_int),
+                ("cin", C.c_int), ("x_pitch", C.c_int), ("cout", C.c_int), ("g_pitch", C.c_int),
+                ("ksize", C.c_int * 3), ("tap_off", C.c_int * 3), ("GX", C.c_int), ("GY", C.c_int), ("GZ", C.c_int),
+                ("g_stride", C.c_int * 3), ("g_off", C.c_int * 3),
                 ("grad_weight", C.c_void_p), ("gw_cin", C.c_int), ("gw_pitch", C.c_int), ("grad_bias", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
 

@@ -1,6 +1,7 @@
-// Weight gradient of the 3-D "same" convolutions on tcgen05 (training path).
+// Weight gradient of stride-1 convolutions (3-D and 2-D, any tap window) and of the phases of stride-s transposed
+// convolutions on tcgen05 (training path).
 //
-//   dW[tap, ci, co] = sum over positions p of  x[p + off(tap), ci] * dy[p, co]
+//   dW[tap, ci, co] = sum over positions p of  x[p + tap_off + tap, ci] * dy[p * g_stride + g_off, co]
 //
 // contracts over POSITIONS, so both operands have to be K-major in the position index.  Two steps:
 //
@@ -10,72 +11,92 @@
 //     taps are whole-line offsets.  The dy pass also sums the bias gradient.
 //  2. wgrad_tc_kernel is a plain tcgen05 GEMM over K blocks = pieces of z-lines.  Its A tile [128 rows][KB positions]
 //     is ASSEMBLED BY TMA: rows are (tap, ci) -- 128 / ci taps per tile, each tap one box [ci rows][KB] of the matching
-//     shifted copy at (x + dx, y + dy), out-of-range lines zero-filled by TMA (= the convolution's padding).  B =
-//     [dy_hi rows | dy_lo rows].  Per A tile and K step: one MMA of 2 co columns (x_hi * [dy_hi | dy_lo]) and one of
+//     shifted copy at (x + dx, y + dy), out-of-range lines zero-filled by TMA (= the convolution's padding); layers
+//     with more than 128 input channels use one tap x 128 channels per tile, more than 128 output channels go to
+//     grid.z in blocks of 128.  Lines are padded to a multiple of 16 positions (zeros).  B = [dy_hi rows | dy_lo rows].  Per A tile and K step: one MMA of 2 co columns (x_hi * [dy_hi | dy_lo]) and one of
 //     co columns (x_lo * dy_hi, onto the upper half) -- the three term pairs of the float32-faithful mode.  Every
 //     (tap-tile) keeps its own TMEM accumulator for the whole launch; tap tiles that do not fit 512 columns go to other
 //     CTAs (grid.y); the K blocks are split over grid.x; results are added into dW with float atomics at the end.
 //
-// Replaces the autograd weight gradient of nn.Conv3d in lib/models/v2v_net.py:10-45,124 (cudnn wgrad in the reference).
+// Replaces the autograd weight gradient (cudnn wgrad in the reference) of nn.Conv3d / nn.ConvTranspose3d in
+// lib/models/v2v_net.py:10-69,124 and of the stride-1 nn.Conv2d / the nn.ConvTranspose2d layers of
+// lib/models/pose_resnet.py:58-93,161-207.
 #include "sp3d_common.cuh"
 #include "tc_common.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <string.h>
+#include <algorithm>
 
 namespace sp3d {
 
 using namespace tc;
 
 // ------------------------------------------------------------------------------------------------ operand prep
-// src: float32 channel-last [lines = N*X*Y][Z][pitch] (C channels used).  dst: bf16 [2 planes][copies][N][Cp][X*Y*Z]
-// with copy j holding the z-line shifted by (j - pad): dst[.., z] = src[.., z + j - pad] (zero outside [0, Z)).
-// CTAs walk the z-lines grid-stride; bias: per-channel sums of src, one atomic per channel and CTA (dy pass only).
+// src: float32 channel-last [N][SX][SY][SZ][pitch]; a LINE is the z-run of one (n, x, y) of the position grid
+// [N][X][Y][Z], read at src[n, x * st.x + of.x, y * st.y + of.y, z * st.z + of.z] (st = 1, of = 0 for the forward input;
+// the output phase of a transposed convolution for its gradient).  dst: bf16 [2 planes][copies][N][Cp][X*Y][Zp] with
+// copy j holding the line shifted by (j + shift0): dst[.., z] = line[z + j + shift0] (zero outside [0, Z) and in the
+// padding Z .. Zp).  grid = (line walkers, channel chunks of kPrepChunk); bias: per-channel sums of the lines, one
+// atomic per channel and CTA (dy pass only).
+constexpr int kPrepChunk = 64;
+struct PrepGeom {
+  int N, X, Y, Z, Zp;
+  int SX, SY, SZ;          // source tensor extents
+  int st[3], of[3];        // source position = grid position * st + of
+  int C, Cp, pitch, copies, shift0;
+};
 __global__ void __launch_bounds__(256) wgrad_prep_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                                         int N, int XY, int Z, int C, int Cp, int pitch, int copies, int pad,
-                                                         float* __restrict__ bias) {
-  extern __shared__ float tile[];          // [Z][C + 1]
-  const int cs = C + 1;
-  const int zg = Z / 8;                    // 16-byte groups of 8 positions
-  const int64_t plane = (int64_t)copies * N * Cp * XY * Z;
-  float bsum = 0.0f;                       // thread c < C: running sum of channel c
-  for (int line = blockIdx.x; line < N * XY; line += gridDim.x) {
+                                                         const PrepGeom g, float* __restrict__ bias) {
+  __shared__ float tile[128 * (kPrepChunk + 1)];      // [Z <= 128][chunk + 1]
+  constexpr int cs = kPrepChunk + 1;
+  const int c0 = blockIdx.y * kPrepChunk;
+  const int cn = min(kPrepChunk, g.Cp - c0);          // channels of this chunk (Cp is a multiple of 16)
+  const int zg = g.Zp / 8;                            // 16-byte groups of 8 positions
+  const int XY = g.X * g.Y;
+  const int64_t plane = (int64_t)g.copies * g.N * g.Cp * XY * g.Zp;
+  float bsum = 0.0f;                                  // thread c < cn: running sum of channel c0 + c
+  for (int line = blockIdx.x; line < g.N * XY; line += gridDim.x) {
     const int n = line / XY, xy = line % XY;
-    const float* s = src + (int64_t)line * Z * pitch;
-    __syncthreads();                       // the previous line's readers are done with the tile
-    for (int i = threadIdx.x; i < Z * pitch; i += blockDim.x) {
-      const int z = i / pitch, c = i % pitch;
-      if (c < C) tile[z * cs + c] = __ldg(s + i);
+    const int x = xy / g.Y, y = xy % g.Y;
+    const float* s = src + ((((int64_t)n * g.SX + (x * g.st[0] + g.of[0])) * g.SY + (y * g.st[1] + g.of[1])) * g.SZ + g.of[2]) *
+                               g.pitch + c0;
+    const int64_t zstep = (int64_t)g.st[2] * g.pitch;
+    __syncthreads();                                  // the previous line's readers are done with the tile
+    for (int i = threadIdx.x; i < g.Z * cn; i += blockDim.x) {
+      const int z = i / cn, c = i % cn;
+      tile[z * cs + c] = (c0 + c < g.C) ? __ldg(s + z * zstep + c) : 0.0f;
     }
     __syncthreads();
-    if (bias != nullptr && (int)threadIdx.x < C) {
-      for (int z = 0; z < Z; ++z) bsum += tile[z * cs + threadIdx.x];
+    if (bias != nullptr && (int)threadIdx.x < cn && c0 + (int)threadIdx.x < g.C) {
+      for (int z = 0; z < g.Z; ++z) bsum += tile[z * cs + threadIdx.x];
     }
-    for (int i = threadIdx.x; i < copies * Cp * zg; i += blockDim.x) {
-      const int g = i % zg, c = (i / zg) % Cp, j = i / (zg * Cp);
+    for (int i = threadIdx.x; i < g.copies * cn * zg; i += blockDim.x) {
+      const int q8 = i % zg, c = (i / zg) % cn, j = i / (zg * cn);
       __align__(16) __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const int z = g * 8 + q + j - pad;
-        const float v = (c < C && z >= 0 && z < Z) ? tile[z * cs + c] : 0.0f;
+        const int zo = q8 * 8 + q, z = zo + j + g.shift0;
+        const float v = (zo < g.Z && z >= 0 && z < g.Z) ? tile[z * cs + c] : 0.0f;
         hi[q] = __float2bfloat16_rn(v);
         lo[q] = __float2bfloat16_rn(v - __bfloat162float(hi[q]));
       }
-      const int64_t o = ((((int64_t)j * N + n) * Cp + c) * XY + xy) * Z + g * 8;
+      const int64_t o = ((((int64_t)j * g.N + n) * g.Cp + c0 + c) * XY + xy) * g.Zp + q8 * 8;
       *reinterpret_cast<uint4*>(dst + o) = *reinterpret_cast<const uint4*>(hi);
       *reinterpret_cast<uint4*>(dst + plane + o) = *reinterpret_cast<const uint4*>(lo);
     }
   }
-  if (bias != nullptr && (int)threadIdx.x < C) atomicAdd(bias + threadIdx.x, bsum);
+  if (bias != nullptr && (int)threadIdx.x < cn && c0 + (int)threadIdx.x < g.C) atomicAdd(bias + c0 + threadIdx.x, bsum);
 }
 
 // ------------------------------------------------------------------------------------------------ GEMM
 struct WgradParams {
-  int N, X, Y, Z, k, pad, taps;
-  int Cp, co16;                  // rows of one tap in an A tile / rows of one dy term in the B tile (multiples of 16)
+  int N, X, Y, Z, taps;          // Z: padded line length
+  int kx, ky, kz, ox, oy;        // tap window; x / y offset of tap 0 (the z offset lives in the shifted copies)
+  int Cr, cb;                    // rows of one tap in an A tile (min(Cp, 128)) / rows of one dy term in the B tile
   int cin, cout;
-  int taps_per_tile, n_tiles, tiles_per_group;
-  int copies;                    // = k: z-shifted copies of x
+  int taps_per_tile, ci_tiles, n_tiles, tiles_per_group;   // ci_tiles = Cp / 128 tiles per tap where Cp > 128
+  int copies;                    // = kz: z-shifted copies of x
   int n_kblocks, kb_per_line;    // K blocks = (n, x, y, z piece)
   float* gw;                     // [taps][gw_cin][gw_pitch] float32, added into
   int gw_cin, gw_pitch;
@@ -93,6 +114,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   __shared__ uint64_t a_full[kWgStages], a_empty[kWgStages], b_full[2], b_empty[2], done;
   __shared__ uint32_t tmem_base_s;
   __shared__ int3 s_tap[32 * 8];                        // <= 32 tiles per CTA x 8 tap slots per tile
+  __shared__ int s_ci0[32];                             // first input channel of each tile
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_buf = smem;                                // [kWgStages][2 planes][kTile]
   uint8_t* b_buf = smem + kWgStages * 2 * kTile;        // [2][256 rows * RB]
@@ -122,14 +144,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const int group = blockIdx.y;
   const int tile0 = group * p.tiles_per_group;
   const int my_tiles = min(p.tiles_per_group, p.n_tiles - tile0);
-  const int acc_cols = 2 * p.co16;
-  // tap table of this CTA's tiles: slot s of tile t -> (dz copy, dy - pad, dx - pad); taps beyond the kernel get an x
-  // offset far outside the tensor (TMA zero-fills the box)
+  const int acc_cols = 2 * p.cb;
+  const int co0 = blockIdx.z * p.cb;                    // first output channel of this CTA
+  // tap table of this CTA's tiles: slot s of tile t -> (dz copy, y offset, x offset); taps beyond the kernel get an x
+  // offset far outside the tensor (TMA zero-fills the box).  Cp > 128: one tap per tile, ci_tiles tiles per tap.
   for (int i = tid; i < my_tiles * 8; i += 128) {
-    const int tap = (tile0 + i / 8) * p.taps_per_tile + (i % 8);
+    const int tile = tile0 + i / 8;
+    const int tap = (tile / p.ci_tiles) * p.taps_per_tile + (i % 8);
     int3 tp = make_int3(0, 0, -100000);
-    if ((i % 8) < p.taps_per_tile && tap < p.taps) tp = make_int3(tap % p.k, (tap / p.k) % p.k - p.pad, tap / (p.k * p.k) - p.pad);
+    if ((i % 8) < p.taps_per_tile && tap < p.taps)
+      tp = make_int3(tap % p.kz, (tap / p.kz) % p.ky + p.oy, tap / (p.kz * p.ky) + p.ox);
     s_tap[i] = tp;
+    if ((i % 8) == 0) s_ci0[i / 8] = (tile % p.ci_tiles) * 128;
   }
   __syncthreads();
   auto kblock_coords = [&](int kb, int& n, int& x, int& y, int& z0) {
@@ -152,10 +178,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       const uint32_t bb = sb & 1;
       mbar_wait(&b_empty[bb], ((sb >> 1) & 1) ^ 1);
       if (lane == 0) {
-        mbar_arrive_expect_tx(&b_full[bb], (uint32_t)(2 * p.co16 * RB));
+        mbar_arrive_expect_tx(&b_full[bb], (uint32_t)(2 * p.cb * RB));
         uint8_t* bdst = b_buf + bb * kBStride;
-        tma_load_5d(bdst, &map_dy, &b_full[bb], z0, y, x, 0, n);                               // dy_hi rows
-        tma_load_5d(bdst + p.co16 * RB, &map_dy, &b_full[bb], z0, y, x, 0, p.N + n);           // dy_lo rows
+        tma_load_5d(bdst, &map_dy, &b_full[bb], z0, y, x, co0, n);                             // dy_hi rows
+        tma_load_5d(bdst + p.cb * RB, &map_dy, &b_full[bb], z0, y, x, co0, p.N + n);           // dy_lo rows
       }
       for (int t = 0; t < my_tiles; ++t, ++sa) {
         const uint32_t st = sa % kWgStages;
@@ -163,18 +189,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (lane == 0) mbar_arrive_expect_tx(&a_full[st], 2u * kTile);
         __syncwarp();
         if (slot < p.taps_per_tile) {
-          uint8_t* adst = a_buf + st * 2 * kTile + slot * p.Cp * RB;
+          uint8_t* adst = a_buf + st * 2 * kTile + slot * p.Cr * RB;
           const int3 tp = s_tap[t * 8 + slot];               // (dz copy, y offset, x offset); x far outside: no such tap
+          const int ci0 = s_ci0[t];
           // outer index: (plane * copies + dz) * N + n
-          tma_load_5d(adst, &map_x, &a_full[st], z0, y + tp.y, x + tp.z, 0, tp.x * p.N + n);
-          tma_load_5d(adst + kTile, &map_x, &a_full[st], z0, y + tp.y, x + tp.z, 0, (p.copies + tp.x) * p.N + n);
+          tma_load_5d(adst, &map_x, &a_full[st], z0, y + tp.y, x + tp.z, ci0, tp.x * p.N + n);
+          tma_load_5d(adst + kTile, &map_x, &a_full[st], z0, y + tp.y, x + tp.z, ci0, (p.copies + tp.x) * p.N + n);
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-uniform, elect-predicated)
-    const uint32_t idesc_w = make_idesc(kFmtBF16, 128, (uint32_t)(2 * p.co16));
-    const uint32_t idesc_n = make_idesc(kFmtBF16, 128, (uint32_t)p.co16);
+    const uint32_t idesc_w = make_idesc(kFmtBF16, 128, (uint32_t)(2 * p.cb));
+    const uint32_t idesc_n = make_idesc(kFmtBF16, 128, (uint32_t)p.cb);
     const uint64_t a_desc0 = make_smem_desc(smem_u32(a_buf), 0, 8 * RB, kLayout);
     const uint64_t b_desc0 = make_smem_desc(smem_u32(b_buf), 0, 8 * RB, kLayout);
     uint32_t sa = 0, sb = 0;
@@ -196,7 +223,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           if (elect_one_sync()) {
             // x_hi * [dy_hi | dy_lo] -> 2 co columns; x_lo * dy_hi -> the upper co columns (small products together)
             mma_f16_ss(d, ad_hi + 2 * ks, bd + 2 * ks, idesc_w, (first && ks == 0) ? 0u : 1u);
-            mma_f16_ss(d + (uint32_t)p.co16, ad_lo + 2 * ks, bd + 2 * ks, idesc_n, 1u);
+            mma_f16_ss(d + (uint32_t)p.cb, ad_lo + 2 * ks, bd + 2 * ks, idesc_n, 1u);
           }
         }
         if (elect_one_sync()) mma_commit(&a_empty[st]);
@@ -215,20 +242,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const int row = tid;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     for (int t = 0; t < my_tiles; ++t) {
-      const int tap = (tile0 + t) * p.taps_per_tile + row / p.Cp;
-      const int ci = row % p.Cp;
-      const bool ok = tap < p.taps && ci < p.cin;
-      float* o = p.gw + ((int64_t)tap * p.gw_cin + ci) * p.gw_pitch;
-      for (int c0 = 0; c0 < p.co16; c0 += 16) {
+      const int tile = tile0 + t;
+      const int tap = (tile / p.ci_tiles) * p.taps_per_tile + row / p.Cr;
+      const int ci = (tile % p.ci_tiles) * 128 + row % p.Cr;
+      const bool ok = row / p.Cr < p.taps_per_tile && tap < p.taps && ci < p.cin;
+      float* o = p.gw + ((int64_t)tap * p.gw_cin + ci) * p.gw_pitch + co0;
+      for (int c0 = 0; c0 < p.cb; c0 += 16) {
         uint32_t v0[16], v1[16];
         tmem_ld_x16(tmem_base + lane_base + (uint32_t)(t * acc_cols + c0), v0);
-        tmem_ld_x16(tmem_base + lane_base + (uint32_t)(t * acc_cols + p.co16 + c0), v1);
+        tmem_ld_x16(tmem_base + lane_base + (uint32_t)(t * acc_cols + p.cb + c0), v1);
         tmem_ld_wait();
         if (ok) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float g = __uint_as_float(v0[j]) + __uint_as_float(v1[j]);
-            if (c0 + j < p.cout && g != 0.0f) atomicAdd(o + c0 + j, g);
+            if (co0 + c0 + j < p.cout && g != 0.0f) atomicAdd(o + c0 + j, g);
           }
         }
       }
@@ -257,30 +285,43 @@ static EncodeTiledFn wg_encode() {
 }
 
 struct WgShape {
-  int Cp, co16, KB, taps, taps_per_tile, n_tiles, tiles_per_group, groups;
+  int Cp, Cr, co16, cb, co_blocks, Zp, KB, taps, taps_per_tile, ci_tiles, n_tiles, tiles_per_group, groups;
   int64_t x_elems, dy_elems;    // bf16 elements of the two workspace regions
 };
 
 static int wg_shape(const sp3d_conv_wgrad_tc_args* a, WgShape* s) {
   if (a == nullptr || a->N < 1 || a->X < 1 || a->Y < 1 || a->Z < 1 || a->cin < 1 || a->cout < 1 || a->x_pitch < a->cin ||
-      a->g_pitch < a->cout || a->cin > 128 || a->cout > 128)
+      a->g_pitch < a->cout)
     return SP3D_ERR_INVALID_ARG;
-  if (a->k != 1 && a->k != 3 && a->k != 7) return SP3D_ERR_UNSUPPORTED;
+  for (int d = 0; d < 3; ++d)
+    if (a->ksize[d] < 1 || a->ksize[d] > 7 || a->g_stride[d] < 1 || a->g_off[d] < 0) return SP3D_ERR_INVALID_ARG;
+  if (a->Z > 128) return SP3D_ERR_UNSUPPORTED;                       // one line has to fit the prep tile
   s->Cp = (a->cin + 15) / 16 * 16;
   s->co16 = (a->cout + 15) / 16 * 16;
-  if ((s->Cp != 16 && s->Cp != 32 && s->Cp != 64 && s->Cp != 128) || s->co16 > 128) return SP3D_ERR_UNSUPPORTED;
-  s->KB = a->Z >= 64 ? 64 : a->Z;
-  if ((s->KB != 64 && s->KB != 32 && s->KB != 16) || a->Z % s->KB) return SP3D_ERR_UNSUPPORTED;
-  s->taps = a->k * a->k * a->k;
-  s->taps_per_tile = 128 / s->Cp;
-  s->n_tiles = (s->taps + s->taps_per_tile - 1) / s->taps_per_tile;
-  s->tiles_per_group = 512 / (2 * s->co16);
+  if (s->Cp > 128) s->Cp = (s->Cp + 127) / 128 * 128;
+  if (s->Cp != 16 && s->Cp != 32 && s->Cp != 64 && (s->Cp % 128)) return SP3D_ERR_UNSUPPORTED;
+  if (s->co16 > 128 && (s->co16 % 128)) return SP3D_ERR_UNSUPPORTED;
+  s->Cr = s->Cp < 128 ? s->Cp : 128;
+  s->cb = s->co16 < 128 ? s->co16 : 128;
+  s->co_blocks = s->co16 / s->cb;
+  s->Zp = (a->Z + 15) / 16 * 16;
+  s->KB = s->Zp % 64 == 0 ? 64 : (s->Zp % 32 == 0 ? 32 : 16);
+  s->taps = a->ksize[0] * a->ksize[1] * a->ksize[2];
+  s->taps_per_tile = 128 / s->Cr;
+  s->ci_tiles = s->Cp <= 128 ? 1 : s->Cp / 128;
+  s->n_tiles = (s->taps + s->taps_per_tile - 1) / s->taps_per_tile * s->ci_tiles;
+  s->tiles_per_group = 512 / (2 * s->cb);
   if (s->tiles_per_group > s->n_tiles) s->tiles_per_group = s->n_tiles;
   s->groups = (s->n_tiles + s->tiles_per_group - 1) / s->tiles_per_group;
-  const int64_t vox = (int64_t)a->N * a->X * a->Y * a->Z;
-  s->x_elems = 2 * (int64_t)a->k * s->Cp * vox;
+  if (s->groups > 65535 || s->co_blocks > 65535) return SP3D_ERR_UNSUPPORTED;
+  const int64_t vox = (int64_t)a->N * a->X * a->Y * s->Zp;
+  s->x_elems = 2 * (int64_t)a->ksize[2] * s->Cp * vox;
   s->dy_elems = 2 * (int64_t)s->co16 * vox;
-  if ((int64_t)a->N * a->X * a->Y > 2147483647LL || 2 * (int64_t)a->k * a->N > 2147483647LL) return SP3D_ERR_UNSUPPORTED;
+  if ((int64_t)a->N * a->X * a->Y > 2147483647LL || 2 * (int64_t)a->ksize[2] * a->N > 2147483647LL) return SP3D_ERR_UNSUPPORTED;
+  // the gradient positions p * g_stride + g_off must lie inside grad_out
+  const int ge[3] = {a->GX, a->GY, a->GZ}, pe[3] = {a->X, a->Y, a->Z};
+  for (int d = 0; d < 3; ++d)
+    if ((int64_t)(pe[d] - 1) * a->g_stride[d] + a->g_off[d] >= ge[d]) return SP3D_ERR_INVALID_ARG;
   return SP3D_OK;
 }
 
@@ -288,20 +329,25 @@ template <int KB>
 static int wg_launch(const sp3d_conv_wgrad_tc_args* a, const WgShape& s, const CUtensorMap& mx, const CUtensorMap& mdy,
                      cudaStream_t st) {
   WgradParams p{};
-  p.N = a->N; p.X = a->X; p.Y = a->Y; p.Z = a->Z; p.k = a->k; p.pad = (a->k - 1) / 2; p.taps = s.taps;
-  p.Cp = s.Cp; p.co16 = s.co16; p.cin = a->cin; p.cout = a->cout;
-  p.taps_per_tile = s.taps_per_tile; p.n_tiles = s.n_tiles; p.tiles_per_group = s.tiles_per_group;
-  p.copies = a->k;
-  p.kb_per_line = a->Z / KB;
+  p.N = a->N; p.X = a->X; p.Y = a->Y; p.Z = s.Zp; p.taps = s.taps;
+  p.kx = a->ksize[0]; p.ky = a->ksize[1]; p.kz = a->ksize[2]; p.ox = a->tap_off[0]; p.oy = a->tap_off[1];
+  p.Cr = s.Cr; p.cb = s.cb; p.cin = a->cin; p.cout = a->cout;
+  p.taps_per_tile = s.taps_per_tile; p.ci_tiles = s.ci_tiles; p.n_tiles = s.n_tiles; p.tiles_per_group = s.tiles_per_group;
+  p.copies = a->ksize[2];
+  p.kb_per_line = s.Zp / KB;
   p.n_kblocks = a->N * a->X * a->Y * p.kb_per_line;
   p.gw = a->grad_weight; p.gw_cin = a->gw_cin; p.gw_pitch = a->gw_pitch;
   constexpr int kSmem = kWgStages * 2 * 128 * KB * 2 + 2 * 256 * KB * 2 + 1024;
   auto kern = wgrad_tc_kernel<KB>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    if (e != cudaSuccess) { set_last_error(e); return SP3D_ERR_LAUNCH; }
-    attr_done = true;
+  {  // opt in to the large dynamic shared memory once per device
+    static unsigned long long done_mask = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 64 || !((done_mask >> dev) & 1ull)) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+      if (e != cudaSuccess) { set_last_error(e); return SP3D_ERR_LAUNCH; }
+      if (dev < 64) done_mask |= 1ull << dev;
+    }
   }
   static int n_sm = 0;
   if (n_sm == 0) {
@@ -309,10 +355,10 @@ static int wg_launch(const sp3d_conv_wgrad_tc_args* a, const WgShape& s, const C
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   }
-  int gx = n_sm / s.groups;
+  int gx = n_sm / (s.groups * s.co_blocks);
   if (gx < 1) gx = 1;
   if (gx > p.n_kblocks) gx = p.n_kblocks;
-  kern<<<dim3(gx, s.groups), 128, kSmem, st>>>(mx, mdy, p);
+  kern<<<dim3(gx, s.groups, s.co_blocks), 128, kSmem, st>>>(mx, mdy, p);
   return check_launch();
 }
 
@@ -340,35 +386,41 @@ extern "C" int sp3d_conv_wgrad_tc(const sp3d_conv_wgrad_tc_args* a, void* stream
   uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(a->workspace) + 1023) & ~uintptr_t(1023));
   __nv_bfloat16* xT = reinterpret_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16* dyT = xT + s.x_elems;
-  const int XY = a->X * a->Y, lines = a->N * XY;
-  const int pad = (a->k - 1) / 2;
-  const int prep_ctas = lines < 148 * 8 ? lines : 148 * 8;
-  wgrad_prep_kernel<<<prep_ctas, 256, (size_t)a->Z * (a->cin + 1) * sizeof(float), st>>>(a->x, xT, a->N, XY, a->Z, a->cin, s.Cp,
-                                                                                        a->x_pitch, a->k, pad, nullptr);
+  const int lines = a->N * a->X * a->Y;
+  PrepGeom gx{};
+  gx.N = a->N; gx.X = a->X; gx.Y = a->Y; gx.Z = a->Z; gx.Zp = s.Zp;
+  gx.SX = a->X; gx.SY = a->Y; gx.SZ = a->Z;
+  for (int d = 0; d < 3; ++d) { gx.st[d] = 1; gx.of[d] = 0; }
+  gx.C = a->cin; gx.Cp = s.Cp; gx.pitch = a->x_pitch; gx.copies = a->ksize[2]; gx.shift0 = a->tap_off[2];
+  PrepGeom gd = gx;
+  gd.SX = a->GX; gd.SY = a->GY; gd.SZ = a->GZ;
+  for (int d = 0; d < 3; ++d) { gd.st[d] = a->g_stride[d]; gd.of[d] = a->g_off[d]; }
+  gd.C = a->cout; gd.Cp = s.co16; gd.pitch = a->g_pitch; gd.copies = 1; gd.shift0 = 0;
+  const int chunks_x = (s.Cp + kPrepChunk - 1) / kPrepChunk, chunks_d = (s.co16 + kPrepChunk - 1) / kPrepChunk;
+  const int walkers_x = std::max(1, std::min(lines, 148 * 8 / chunks_x)), walkers_d = std::max(1, std::min(lines, 148 * 8 / chunks_d));
+  wgrad_prep_kernel<<<dim3(walkers_x, chunks_x), 256, 0, st>>>(a->x, xT, gx, nullptr);
   rc = check_launch();
   if (rc != SP3D_OK) return rc;
-  wgrad_prep_kernel<<<prep_ctas, 256, (size_t)a->Z * (a->cout + 1) * sizeof(float), st>>>(a->grad_out, dyT, a->N, XY, a->Z, a->cout,
-                                                                                         s.co16, a->g_pitch, 1, 0, a->grad_bias);
+  wgrad_prep_kernel<<<dim3(walkers_d, chunks_d), 256, 0, st>>>(a->grad_out, dyT, gd, a->grad_bias);
   rc = check_launch();
   if (rc != SP3D_OK) return rc;
 
   CUtensorMap mx, mdy;
   const CUtensorMapSwizzle sw = s.KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (s.KB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  {  // x^T: [2 planes * k copies * N][Cp][X][Y][Z] bf16; box = {KB, 1, 1, Cp, 1}
-    cuuint64_t gdim[5] = {(cuuint64_t)a->Z, (cuuint64_t)a->Y, (cuuint64_t)a->X, (cuuint64_t)s.Cp, (cuuint64_t)(2 * a->k * a->N)};
-    cuuint64_t gstr[4] = {(cuuint64_t)a->Z * 2, (cuuint64_t)a->Z * a->Y * 2, (cuuint64_t)a->Z * a->Y * a->X * 2,
-                          (cuuint64_t)a->Z * a->Y * a->X * s.Cp * 2};
-    cuuint32_t box[5] = {(cuuint32_t)s.KB, 1, 1, (cuuint32_t)s.Cp, 1};
+  const cuuint64_t Zp = (cuuint64_t)s.Zp;
+  {  // x^T: [2 planes * kz copies * N][Cp][X][Y][Zp] bf16; box = {KB, 1, 1, Cr, 1}
+    cuuint64_t gdim[5] = {Zp, (cuuint64_t)a->Y, (cuuint64_t)a->X, (cuuint64_t)s.Cp, (cuuint64_t)(2 * a->ksize[2] * a->N)};
+    cuuint64_t gstr[4] = {Zp * 2, Zp * a->Y * 2, Zp * a->Y * a->X * 2, Zp * a->Y * a->X * s.Cp * 2};
+    cuuint32_t box[5] = {(cuuint32_t)s.KB, 1, 1, (cuuint32_t)s.Cr, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     if (encode(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, xT, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return SP3D_ERR_INVALID_ARG;
   }
-  {  // dy^T: [2 planes * N][co16][X][Y][Z] bf16; box = {KB, 1, 1, co16, 1}
-    cuuint64_t gdim[5] = {(cuuint64_t)a->Z, (cuuint64_t)a->Y, (cuuint64_t)a->X, (cuuint64_t)s.co16, (cuuint64_t)(2 * a->N)};
-    cuuint64_t gstr[4] = {(cuuint64_t)a->Z * 2, (cuuint64_t)a->Z * a->Y * 2, (cuuint64_t)a->Z * a->Y * a->X * 2,
-                          (cuuint64_t)a->Z * a->Y * a->X * s.co16 * 2};
-    cuuint32_t box[5] = {(cuuint32_t)s.KB, 1, 1, (cuuint32_t)s.co16, 1};
+  {  // dy^T: [2 planes * N][co16][X][Y][Zp] bf16; box = {KB, 1, 1, cb, 1}
+    cuuint64_t gdim[5] = {Zp, (cuuint64_t)a->Y, (cuuint64_t)a->X, (cuuint64_t)s.co16, (cuuint64_t)(2 * a->N)};
+    cuuint64_t gstr[4] = {Zp * 2, Zp * a->Y * 2, Zp * a->Y * a->X * 2, Zp * a->Y * a->X * s.co16 * 2};
+    cuuint32_t box[5] = {(cuuint32_t)s.KB, 1, 1, (cuuint32_t)s.cb, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     if (encode(&mdy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, dyT, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)

@@ -126,8 +126,7 @@ def conv_wgrad(pc, x, grad_out, with_bias=True):
     if tuple(grad_out.shape[:4]) != (N, o[0], o[1], o[2]) or int(grad_out.shape[4]) < pc.cout:
         raise _lib.Sp3dError("conv_wgrad: grad_out does not match the convolution's output shape")
     gb = torch.zeros(pc.cout, device=x.device, dtype=torch.float32) if with_bias else None
-    if _wgrad_tc_ok(pc, x, grad_out):
-        return _conv_wgrad_tc(pc, x, grad_out, gb), gb
+    use_tc = _wgrad_tc_ok(pc, x, grad_out)
     subs = []
     launches = [(None, [-p for p in pc.padding], pc.k, o, [1, 1, 1], [1, 1, 1], [0, 0, 0])] if not pc.transposed else [
         (i, off0, ks, [(o[d] - phase[d] + pc.stride[d] - 1) // pc.stride[d] for d in range(3)], [-1, -1, -1], pc.stride, phase)
@@ -139,14 +138,23 @@ def conv_wgrad(pc, x, grad_out, with_bias=True):
             subs.append(gw[:, :pc.cin, :pc.cout].reshape(int(ks[0]), int(ks[1]), int(ks[2]), pc.cin, pc.cout)
                         .permute(4, 3, 0, 1, 2))
             continue
-        b = _lib.ConvWgradArgs()
-        _conv_geometry(b.fwd, x, grad_out.shape, pc.cin_p, pc.cout, pc.cout_pw, grid, ks,
-                       pc.stride if not pc.transposed else [1, 1, 1], off0, step, ostride, ooff)
-        b.fwd.in_ = x.data_ptr()
-        b.grad_out, b.grad_weight = grad_out.data_ptr(), gw.data_ptr()
-        b.grad_bias = gb.data_ptr() if gb is not None else None
-        flops = 2.0 * N * grid[0] * grid[1] * grid[2] * pc.cout * pc.cin * taps
-        _lib.call("sp3d_conv_wgrad", b, _stream(), kind="conv_wgrad", work=flops)
+        if use_tc:
+            # transposed phases walk their taps backwards (tap_step -1 from off0): the same window read forwards starts
+            # at off0 - (k - 1), with the tap order reversed in the result
+            fwd_off = [int(off0[d]) if step[d] == 1 else int(off0[d]) - (int(ks[d]) - 1) for d in range(3)]
+            _conv_wgrad_tc(pc, x, grad_out, gb, gw, ks, fwd_off, ostride, ooff)
+            if step[0] == -1:
+                gw = gw.reshape(int(ks[0]), int(ks[1]), int(ks[2]), pc.cin_p, pc.cout_pw).flip(0, 1, 2).reshape(
+                    taps, pc.cin_p, pc.cout_pw)
+        else:
+            b = _lib.ConvWgradArgs()
+            _conv_geometry(b.fwd, x, grad_out.shape, pc.cin_p, pc.cout, pc.cout_pw, grid, ks,
+                           pc.stride if not pc.transposed else [1, 1, 1], off0, step, ostride, ooff)
+            b.fwd.in_ = x.data_ptr()
+            b.grad_out, b.grad_weight = grad_out.data_ptr(), gw.data_ptr()
+            b.grad_bias = gb.data_ptr() if gb is not None else None
+            flops = 2.0 * N * grid[0] * grid[1] * grid[2] * pc.cout * pc.cin * taps
+            _lib.call("sp3d_conv_wgrad", b, _stream(), kind="conv_wgrad", work=flops)
         subs.append(gw[:, :pc.cin, :pc.cout].reshape(int(ks[0]), int(ks[1]), int(ks[2]), pc.cin, pc.cout)
                     .permute(4, 3, 0, 1, 2))                       # [Cout, Cin, a, b, c]
     if not pc.transposed:
@@ -166,29 +174,46 @@ _WGRAD_TC = __import__("os").environ.get("SP3D_WGRAD_TC", "1") != "0"
 
 
 def _wgrad_tc_ok(pc, x, grad_out):
-    """The tcgen05 weight gradient (``sp3d_conv_wgrad_tc``) takes stride-1 "same" 3-D convolutions with a cubic kernel
-    of 1, 3 or 7 taps, at most 128 channels with ``round_up(cin, 16)`` in {16, 32, 64, 128}, and a z extent of 16, 32
-    or a multiple of 64 -- every ``nn.Conv3d`` of the pose net's V2VNet.  Not in the float32 FMA mode."""
-    if not _WGRAD_TC or ops.float32_conv() == "simt" or pc.nd != 3 or pc.transposed:
+    """The tcgen05 weight gradient (``sp3d_conv_wgrad_tc``) takes the convolutions whose taps step by one input position
+    per output position: stride-1 convolutions (3-D and 2-D) and stride-s transposed convolutions (phase by phase), with a
+    z extent (row length) of at most 128, ``round_up(cin, 16)`` in {16, 32, 64} or more than 64 input channels, at most 128
+    output channels or a multiple of 128.  Not in the float32 FMA mode."""
+    if not _WGRAD_TC or ops.float32_conv() == "simt":
         return False
-    k = pc.k[0]
-    if pc.k != [k] * 3 or k not in (1, 3, 7) or pc.stride != [1, 1, 1] or pc.padding != [k // 2] * 3:
+    if not pc.transposed and pc.stride != [1, 1, 1]:
         return False
-    Z = int(x.shape[3])
-    if pc.cout > 128 or ops.round_up(pc.cin, 16) not in (16, 32, 64, 128):
+    if max(pc.k) > 7 or int(x.shape[3]) > 128:
         return False
-    return Z in (16, 32) or Z % 64 == 0
+    cp, co16 = ops.round_up(pc.cin, 16), ops.round_up(pc.cout, 16)
+    if cp not in (16, 32, 64) and cp < 65:
+        return False
+    if co16 > 128 and co16 % 128:
+        return False
+    if pc.transposed:
+        # every phase must cover the whole input grid (output extent = stride * input extent)
+        D, H, W = [int(v) for v in x.shape[1:4]]
+        o = pc.out_shape((D, H, W))
+        for phase, _, ks in pc.phases:
+            grid = [(o[d] - phase[d] + pc.stride[d] - 1) // pc.stride[d] for d in range(3)]
+            if int(ks[0] * ks[1] * ks[2]) and grid != [D, H, W]:
+                return False
+    return True
 
 
-def _conv_wgrad_tc(pc, x, grad_out, gb):
-    """``[Cout, Cin, k, k, k]`` weight gradient through ``sp3d_conv_wgrad_tc`` (bias gradient added into ``gb``)."""
+def _conv_wgrad_tc(pc, x, grad_out, gb, gw, ks, tap_off, g_stride, g_off):
+    """One ``sp3d_conv_wgrad_tc`` launch: ``gw [taps, cin_p, cout_pw] +=`` the weight gradient of the tap window ``ks``
+    starting at input offset ``tap_off``, with the gradient read at ``p * g_stride + g_off`` (bias gradient added into
+    ``gb``)."""
     N, X, Y, Z, pitch = [int(v) for v in x.shape]
-    k = pc.k[0]
-    gw = torch.zeros(k ** 3, pc.cin_p, pc.cout_pw, device=x.device, dtype=torch.float32)
     a = _lib.ConvWgradTcArgs()
     a.x, a.grad_out = x.data_ptr(), grad_out.data_ptr()
     a.N, a.X, a.Y, a.Z = N, X, Y, Z
-    a.cin, a.x_pitch, a.cout, a.g_pitch, a.k = pc.cin, pitch, pc.cout, int(grad_out.shape[4]), k
+    a.cin, a.x_pitch, a.cout, a.g_pitch = pc.cin, pitch, pc.cout, int(grad_out.shape[4])
+    _set3(a.ksize, ks)
+    _set3(a.tap_off, tap_off)
+    a.GX, a.GY, a.GZ = [int(v) for v in grad_out.shape[1:4]]
+    _set3(a.g_stride, g_stride)
+    _set3(a.g_off, g_off)
     a.grad_weight, a.gw_cin, a.gw_pitch = gw.data_ptr(), pc.cin_p, pc.cout_pw
     a.grad_bias = gb.data_ptr() if gb is not None else None
     nbytes = int(_lib.load().sp3d_conv_wgrad_tc_workspace(a))
@@ -196,10 +221,10 @@ def _conv_wgrad_tc(pc, x, grad_out, gb):
         raise _lib.Sp3dError("sp3d_conv_wgrad_tc: shape not supported")
     ws = torch.empty(nbytes + 16, device=x.device, dtype=torch.uint8)
     a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
-    flops = 2.0 * N * X * Y * Z * pc.cout * pc.cin * k ** 3
+    taps = int(ks[0] * ks[1] * ks[2])
+    flops = 2.0 * N * X * Y * Z * pc.cout * pc.cin * taps
     _lib.call("sp3d_conv_wgrad_tc", a, _stream(), launches=3, kind="conv_wgrad_tc", work=flops,
-              detail="wgrad tc k%d %d->%d @%dx%dx%dx%d" % (k, pc.cin, pc.cout, N, X, Y, Z))
-    return gw[:, :pc.cin, :pc.cout].reshape(k, k, k, pc.cin, pc.cout).permute(4, 3, 0, 1, 2).contiguous()
+              detail="wgrad tc k%dx%dx%d %d->%d @%dx%dx%dx%d" % (int(ks[0]), int(ks[1]), int(ks[2]), pc.cin, pc.cout, N, X, Y, Z))
 
 
 def conv_dgrad(pc, grad_out, out_pitch=None, in_dims=None):

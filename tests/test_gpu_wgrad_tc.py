@@ -48,11 +48,65 @@ def test_wgrad_tc_vs_float64_autograd(k, cin, cout, sp, n):
     assert float((gw - gw_s).abs().max() / gw_s.abs().max()) <= 5e-5
 
 
+# (what, module, input shape [N, C, *spatial]): the generalised form -- rows that are not multiples of 16 (padded lines),
+# 2-D layers of PoseResNet (1x1 / 3x3, up to 2048 channels: ci tiles and co blocks), transposed convolutions by phase
+GENERAL = [("3d k3 z=20 (root grid)", lambda: nn.Conv3d(32, 32, 3, 1, 1), (2, 32, 6, 5, 20)),
+           ("3d k7 1->16 z=20", lambda: nn.Conv3d(1, 16, 7, 1, 3), (1, 1, 8, 8, 20)),
+           ("3d k3 z=10", lambda: nn.Conv3d(64, 64, 3, 1, 1), (1, 64, 5, 4, 10)),
+           ("3d k3 z=5", lambda: nn.Conv3d(128, 128, 3, 1, 1), (2, 128, 4, 4, 5)),
+           ("3d convT k2 s2", lambda: nn.ConvTranspose3d(64, 32, 2, 2), (2, 64, 4, 3, 8)),
+           ("3d convT k2 s2 128->64 z=5", lambda: nn.ConvTranspose3d(128, 64, 2, 2), (1, 128, 3, 3, 5)),
+           ("2d 1x1 64->256", lambda: nn.Conv2d(64, 256, 1, bias=False), (2, 64, 9, 24)),
+           ("2d 1x1 1024->256 w=12", lambda: nn.Conv2d(1024, 256, 1, bias=False), (2, 1024, 5, 12)),
+           ("2d 1x1 512->2048 w=12", lambda: nn.Conv2d(512, 2048, 1, bias=False), (1, 512, 4, 12)),
+           ("2d 3x3 64->64 w=96", lambda: nn.Conv2d(64, 64, 3, 1, 1, bias=False), (2, 64, 7, 96)),
+           ("2d 3x3 256->256 w=24", lambda: nn.Conv2d(256, 256, 3, 1, 1, bias=False), (2, 256, 6, 24)),
+           ("2d 3x3 512->512 w=12", lambda: nn.Conv2d(512, 512, 3, 1, 1, bias=False), (1, 512, 9, 12)),
+           ("2d convT k4 s2 p1 256->256", lambda: nn.ConvTranspose2d(256, 256, 4, 2, 1, bias=False), (2, 256, 5, 12)),
+           ("2d convT k4 s2 p1 2048->256", lambda: nn.ConvTranspose2d(2048, 256, 4, 2, 1, bias=False), (1, 2048, 3, 12)),
+           ("2d 1x1 256->15 head", lambda: nn.Conv2d(256, 15, 1), (2, 256, 8, 96))]
+
+
+@pytest.mark.parametrize("what,make,shape", GENERAL, ids=[g[0] for g in GENERAL])
+def test_general_wgrad_tc_vs_float64_autograd(what, make, shape):
+    torch.manual_seed(len(what) + shape[1])
+    mod = make().double()
+    x = torch.randn(*shape, dtype=torch.float64)
+    y = mod(x)
+    gy = torch.randn_like(y)
+    (y * gy).sum().backward()
+    transposed = isinstance(mod, (nn.ConvTranspose2d, nn.ConvTranspose3d))
+    bias = None if mod.bias is None else mod.bias.detach().float().to(DEV)
+    pc = ops.PackedConv(mod.weight.detach().float().to(DEV), bias, None, int(mod.stride[0]), int(mod.padding[0]),
+                        transposed=transposed, relu=0)
+    x5, g5 = (x, gy) if x.dim() == 5 else (x.unsqueeze(2), gy.unsqueeze(2))
+    xcl, gycl = cl(x5.float()), cl(g5.float())
+    ops.set_float32_conv("bf16x3")
+    assert grad_ops._wgrad_tc_ok(pc, xcl, gycl)
+    gw, gb = grad_ops.conv_wgrad(pc, xcl, gycl, with_bias=bias is not None)
+    want_w = mod.weight.grad.numpy()
+    err_w = float(np.abs(gw.cpu().numpy() - want_w).max() / np.abs(want_w).max())
+    print("wgrad tc %s: dW %.3g" % (what, err_w))
+    assert gw.shape == mod.weight.shape and err_w <= 5e-5, err_w
+    if bias is not None:
+        want_b = mod.bias.grad.numpy()
+        assert float(np.abs(gb.cpu().numpy() - want_b).max() / np.abs(want_b).max()) <= 2e-5
+    ops.set_float32_conv("simt")
+    gw_s, _ = grad_ops.conv_wgrad(pc, xcl, gycl, with_bias=bias is not None)
+    assert float((gw - gw_s).abs().max() / gw_s.abs().max()) <= 5e-5
+
+
 def test_shapes_outside_the_tensor_core_form_take_the_fma_kernel():
     ops.set_float32_conv("bf16x3")
-    conv = nn.Conv3d(32, 32, 3, 1, 1).to(DEV)
-    pc = ops.PackedConv(conv.weight, conv.bias, None, 1, 1, relu=0)
-    x = torch.randn(1, 8, 8, 20, 32, device=DEV)          # z extent 20: the root grid
+    conv = nn.Conv2d(64, 128, 3, 2, 1).to(DEV)            # strided convolutions: taps step by two input positions
+    pc = ops.PackedConv(conv.weight, conv.bias, None, 2, 1, relu=0)
+    x = torch.randn(1, 1, 8, 16, 64, device=DEV)
     assert not grad_ops._wgrad_tc_ok(pc, x, x)
-    ct = nn.ConvTranspose3d(32, 16, 2, 2).to(DEV)
-    assert not grad_ops._wgrad_tc_ok(ops.PackedConv(ct.weight, ct.bias, None, 2, 0, transposed=True, relu=0), x, x)
+    conv = nn.Conv2d(3, 64, 3, 1, 1).to(DEV)              # rows longer than 128 positions
+    assert not grad_ops._wgrad_tc_ok(ops.PackedConv(conv.weight, conv.bias, None, 1, 1, relu=0),
+                                     torch.randn(1, 1, 4, 192, 4, device=DEV), x)
+    ops.set_float32_conv("simt")
+    conv = nn.Conv3d(32, 32, 3, 1, 1).to(DEV)
+    assert not grad_ops._wgrad_tc_ok(ops.PackedConv(conv.weight, conv.bias, None, 1, 1, relu=0),
+                                     torch.randn(1, 8, 8, 16, 32, device=DEV), x)
+    ops.set_float32_conv("bf16x3")
