@@ -47,22 +47,22 @@ HEATMAP_SIZE = [72, 96]
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-# (profiles/r01_ncu_*_summary.csv), keyed by the launch's layer string; refreshed by hand with the captures
+# (profiles/r01_ncu_*_summary.csv, profiles/r02b_ncu_*_summary.csv), keyed by the launch's layer string; refreshed by hand with the captures
 NCU_EVIDENCE = {
     # float32-faithful mode, 7^3 stem over 80 cubes: 2 bf16 term planes in (2 x 671 MB) + 2 planes out (2 x 671 MB)
-    # algorithmic; measured 1.3456 GB read + 1.3059 GB written
+    # algorithmic; measured 1.3466 GB read + 1.3055 GB written
     "conv algo2 k7 15->16 @80x64x64x64": {
-        "dram_bytes_per_launch": 1.345561e9 + 1.305874e9,
-        "source": "profiles/r02_ncu_stem_80cubes_summary.csv (conv_tc_kernel<7,7,64,32,4,8,2,1,2,128,1,F=2,WD=2>, ncu --set "
-                  "full: sm__pipe_tensor_cycles_active 46.3 %)"},
+        "dram_bytes_per_launch": 1.346636e9 + 1.305537e9,
+        "source": "profiles/r02b_ncu_stem_80cubes_summary.csv (conv_tc_kernel<7,7,64,32,4,8,2,1,2,128,1,F=2,WD=2>, ncu --set "
+                  "full: sm__pipe_tensor_cycles_active 46.2 %)"},
     "conv algo1 k7 15->16 @80x64x64x64": {
         "dram_bytes_per_launch": 672.02e6 + 634.73e6,   # bf16 throughput mode: 671 MB bf16 cubes in + 671 MB out
         "source": "profiles/r01_ncu_conv_pose_v11_summary.csv (conv_tc_kernel<7,7,64,32,...,F=2>, ncu --set full)"},
-    # un-projection of the 80 person cubes, float32 arithmetic, term-pair output: 6.6 MB read (maps live in L2) + 1.2835 GB
+    # un-projection of the 80 person cubes, float32 arithmetic, term-pair output: 7.7 MB read (maps live in L2) + 1.2828 GB
     # written against 1.2749 GB algorithmic + the zero padding channel
     "unproject": {
-        "dram_bytes_per_launch": 0.006631e9 + 1.283479e9,
-        "source": "profiles/r02_ncu_k1_k3_k4_summary.csv (unproject_kernel<1, bf16, PAIR>, 80 cubes, ncu --set full)"},
+        "dram_bytes_per_launch": 0.007710e9 + 1.282782e9,
+        "source": "profiles/r02b_ncu_k1_k3_k4_summary.csv (unproject_kernel<1, bf16, PAIR>, 80 cubes, ncu --set full)"},
 }
 
 
@@ -283,8 +283,8 @@ def time_training_step(dev, steps=2, mode="bf16x3"):
             "gpu_launches": _lib.launch_count - l0, "matched_proposals": matched,
             "what": "supervised step, 1 frame x 5 views, frozen backbone, root net + pose net forward and backward; "
                     "float32 training path, convolutions: %s" % ("float32 FMA kernels" if mode == "simt" else
-                    "forward, covered input gradients and the V2VNet weight gradients on tcgen05 (split operands); "
-                    "root-net (z = 20) and transposed-convolution weight gradients on the float32 FMA kernel")}
+                    "forward, covered input gradients and all weight gradients on tcgen05 (split operands); all "
+                    "proposal slots in one pose-net pass (grouped BatchNorm statistics keep the per-slot batches)")}
 
 
 
