@@ -384,6 +384,10 @@ typedef struct {
   int n_items, n_groups;
   const int32_t* item_group;    /* [n_items] or NULL */
   const int32_t* group_items;   /* [n_groups] items per group (with item_group) */
+  float* running_mean; float* running_var;   /* optional [C] (both or neither): the module's running statistics, updated
+                                                in place as n_groups successive training-mode calls do it -- per group
+                                                r <- (1 - momentum) r + momentum stat, the variance unbiased n / (n - 1) */
+  float momentum;
 } sp3d_bn_stats_args;
 int sp3d_bn_stats(const sp3d_bn_stats_args* a, void* stream);
 

@@ -156,7 +156,8 @@ class ConvWgradArgs(C.Structure):
 class BnStatsArgs(C.Structure):
     _fields_ = [("x", C.c_void_p), ("P", C.c_int64), ("C", C.c_int), ("pitch", C.c_int),
                 ("mean", C.c_void_p), ("var", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
-                ("n_items", C.c_int), ("n_groups", C.c_int), ("item_group", C.c_void_p), ("group_items", C.c_void_p)]
+                ("n_items", C.c_int), ("n_groups", C.c_int), ("item_group", C.c_void_p), ("group_items", C.c_void_p),
+                ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("momentum", C.c_float)]
 
 
 class BnApplyArgs(C.Structure):

@@ -98,8 +98,8 @@ class BatchNormAct(Function):
     the statistics are for the caller's running-average update and carry no gradient."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, channels, eps, relu, groups=None):
-        mean, var = grad_ops.bn_stats(x, channels, groups=groups)     # [C], or [n_groups, C]
+    def forward(ctx, x, gamma, beta, channels, eps, relu, groups=None, running=None):
+        mean, var = grad_ops.bn_stats(x, channels, groups=groups, running=running)     # [C], or [n_groups, C]
         scale = gamma * torch.rsqrt(var + eps)                 # [C] vectors: a handful of scalars, not a hot path
         y = grad_ops.bn_apply(x, channels, scale.contiguous(), (beta - mean * scale).contiguous(), relu=1 if relu else 0,
                               groups=groups)
@@ -112,7 +112,7 @@ class BatchNormAct(Function):
     def backward(ctx, gy, _gm, _gv):
         x, mean, var, gamma, y = ctx.saved_tensors
         gx, gg, gb = grad_ops.bn_bwd(x, ctx.channels, gy.contiguous(), mean, var, gamma, ctx.eps, y=y, groups=ctx.groups)
-        return gx, gg, gb, None, None, None, None
+        return gx, gg, gb, None, None, None, None, None
 
 
 class AddAct(Function):
@@ -165,29 +165,28 @@ def batch_norm(x, bn, relu=False):
     update (momentum, unbiased running variance, ``num_batches_tracked``) done as ``F.batch_norm`` does it."""
     channels = int(bn.num_features)
     groups = _active_groups(x)
-    y, mean, var = BatchNormAct.apply(x, bn.weight, bn.bias, channels, float(bn.eps), relu, groups)
-    if bn.track_running_stats and bn.running_mean is not None:
+    track = bn.track_running_stats and bn.running_mean is not None
+    # momentum updates of the float32 running statistics ride on the statistics kernel (one launch instead of ~8 tiny
+    # tensor ops per layer); the cumulative-average form (momentum None) keeps the tensor expression
+    fused = (track and bn.momentum is not None and bn.running_mean.dtype == torch.float32
+             and bn.running_var.dtype == torch.float32 and bn.running_mean.is_contiguous() and bn.running_var.is_contiguous())
+    running = (bn.running_mean, bn.running_var, float(bn.momentum)) if fused else None
+    y, mean, var = BatchNormAct.apply(x, bn.weight, bn.bias, channels, float(bn.eps), relu, groups, running)
+    if track:
         with torch.no_grad():
-            n = x.numel() // int(x.shape[-1])
-            if groups is None:
-                bn.num_batches_tracked += 1
-                m = 1.0 / float(bn.num_batches_tracked) if bn.momentum is None else float(bn.momentum)
-                bn.running_mean.mul_(1.0 - m).add_(mean, alpha=m)
-                bn.running_var.mul_(1.0 - m).add_(var * (n / max(n - 1, 1)), alpha=m)
-            elif bn.momentum is None:
-                per_item = n // groups.n_items
-                for g, c in enumerate(groups.counts):          # cumulative average: the weight changes per call
-                    bn.num_batches_tracked += 1
-                    m = 1.0 / float(bn.num_batches_tracked)
+            bn.num_batches_tracked += groups.n_groups if groups is not None else 1
+            if not fused:
+                n = x.numel() // int(x.shape[-1])
+                counts = groups.counts if groups is not None else [1]
+                per_item = n // sum(counts)
+                nbt = int(bn.num_batches_tracked) - len(counts)
+                for g, c in enumerate(counts):
+                    nbt += 1
+                    m = 1.0 / float(nbt) if bn.momentum is None else float(bn.momentum)
                     ng = c * per_item
-                    bn.running_mean.mul_(1.0 - m).add_(mean[g], alpha=m)
-                    bn.running_var.mul_(1.0 - m).add_(var[g] * (ng / max(ng - 1, 1)), alpha=m)
-            else:
-                # len(counts) successive momentum updates in closed form: r <- (1-m)^G r + sum_g m (1-m)^(G-1-g) stat_g
-                w, unbias, keep = groups.momentum_weights(float(bn.momentum), n // groups.n_items)
-                bn.num_batches_tracked += groups.n_groups
-                bn.running_mean.mul_(keep).add_(w @ mean)
-                bn.running_var.mul_(keep).add_(w @ (var * unbias[:, None]))
+                    mg, vg = (mean[g], var[g]) if groups is not None else (mean, var)
+                    bn.running_mean.mul_(1.0 - m).add_(mg.to(bn.running_mean.dtype), alpha=m)
+                    bn.running_var.mul_(1.0 - m).add_((vg * (ng / max(ng - 1, 1))).to(bn.running_var.dtype), alpha=m)
     return y
 
 

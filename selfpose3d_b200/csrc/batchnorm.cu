@@ -137,17 +137,31 @@ __global__ void __launch_bounds__(kBnThreads) bn_reduce_kernel(const float* __re
   }
 }
 
-__global__ void bn_stats_finish_kernel(const double* ws, BnGeom g, float* mean, float* var) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= g.n_groups * g.C) return;
-  const int grp = i / g.C, c = i % g.C;
-  const double P = bn_group_positions(g, grp);
-  if (P <= 0.0) { mean[i] = 0.0f; var[i] = 0.0f; return; }
-  const double m = ws[(int64_t)grp * 2 * g.C + c] / P;
-  double v = ws[(int64_t)grp * 2 * g.C + g.C + c] / P - m * m;
-  if (v < 0.0) v = 0.0;
-  mean[i] = (float)m;
-  var[i] = (float)v;
+// one thread per channel: mean / biased variance of every group, then (optionally) the running-average update of the
+// module exactly as n_groups successive F.batch_norm calls make it: r <- (1 - m) r + m stat_g, the variance unbiased
+__global__ void bn_stats_finish_kernel(const double* ws, BnGeom g, float* mean, float* var, float* running_mean,
+                                       float* running_var, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= g.C) return;
+  float rm = running_mean ? running_mean[c] : 0.0f, rv = running_var ? running_var[c] : 0.0f;
+  for (int grp = 0; grp < g.n_groups; ++grp) {
+    const double P = bn_group_positions(g, grp);
+    float m = 0.0f, v = 0.0f;
+    if (P > 0.0) {
+      const double md = ws[(int64_t)grp * 2 * g.C + c] / P;
+      double vd = ws[(int64_t)grp * 2 * g.C + g.C + c] / P - md * md;
+      if (vd < 0.0) vd = 0.0;
+      m = (float)md;
+      v = (float)vd;
+      // (float32 arithmetic in torch's order: running.mul_(1 - m).add_(stat, alpha = m))
+      rm = rm * (1.0f - momentum) + momentum * m;
+      rv = rv * (1.0f - momentum) + momentum * (v * (float)(P / (P > 1.0 ? P - 1.0 : 1.0)));
+    }
+    mean[grp * g.C + c] = m;
+    var[grp * g.C + c] = v;
+  }
+  if (running_mean) running_mean[c] = rm;
+  if (running_var) running_var[c] = rv;
 }
 
 // grid = (chunks, items): y = act(x * scale[g][c] + shift[g][c] (+ residual)); padding channels are written as zeros
@@ -338,7 +352,9 @@ extern "C" int sp3d_bn_stats(const sp3d_bn_stats_args* a, void* stream) {
                                                                                a->workspace);
   int rc = check_launch();
   if (rc != SP3D_OK) return rc;
-  bn_stats_finish_kernel<<<(g.n_groups * a->C + 127) / 128, 128, 0, st>>>(a->workspace, g, a->mean, a->var);
+  if ((a->running_mean == nullptr) != (a->running_var == nullptr)) return SP3D_ERR_INVALID_ARG;
+  bn_stats_finish_kernel<<<(a->C + 127) / 128, 128, 0, st>>>(a->workspace, g, a->mean, a->var, a->running_mean, a->running_var,
+                                                             a->momentum);
   return check_launch();
 }
 

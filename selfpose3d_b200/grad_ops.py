@@ -311,9 +311,10 @@ class BnGroups:
             a.group_items = self.group_items.data_ptr()
 
 
-def bn_stats(x, channels, groups=None):
+def bn_stats(x, channels, groups=None, running=None):
     """Per-channel batch mean and biased variance of channel-last ``x`` -> ``(mean, var)``, each ``[C]`` or, with
-    ``groups`` (``BnGroups``), ``[n_groups, C]``."""
+    ``groups`` (``BnGroups``), ``[n_groups, C]``.  ``running = (running_mean, running_var, momentum)``: the module's
+    float32 running statistics are updated in place by the same launch (once per group, in group order)."""
     _f32(x)
     P, pitch = _flat(x)
     G = groups.n_groups if groups is not None else 1
@@ -326,7 +327,13 @@ def bn_stats(x, channels, groups=None):
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 8
     if groups is not None:
         groups.fill(a, x)
+    if running is not None:
+        _f32(running[0], running[1])
+        a.running_mean, a.running_var, a.momentum = running[0].data_ptr(), running[1].data_ptr(), float(running[2])
     _lib.call("sp3d_bn_stats", a, _stream(), launches=2, kind="bn", work=x.numel() * 4)
+    if running is not None:       # the kernel wrote them in place: caches keyed on the buffers' versions must notice
+        torch.autograd.graph.increment_version(running[0])
+        torch.autograd.graph.increment_version(running[1])
     return mean, var
 
 

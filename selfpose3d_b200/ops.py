@@ -19,7 +19,9 @@ _DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    """Raw handle of torch's current CUDA stream on the current device (the stream every launch goes to).
+    ``torch.cuda.current_stream().cuda_stream`` costs ~17 us of Python per call -- as much as a small launch."""
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def _require_cuda(*tensors):

@@ -46,12 +46,18 @@ def _group_slices(groups):
     return out
 
 
-def _bn_stats(x, channels, groups=None):
-    if groups is not None:      # grouped statistics: every group of items on its own
-        st = [_bn_stats(x[sl], channels) for sl in _group_slices(groups)]
+def _bn_stats(x, channels, groups=None, running=None):
+    if groups is not None:      # grouped statistics: every group of items on its own (running statistics: in group order)
+        st = [_bn_stats(x[sl], channels, running=running) for sl in _group_slices(groups)]
         return torch.stack([m for m, _ in st]), torch.stack([v for _, v in st])
     v = x.reshape(-1, x.shape[-1])[:, :channels].double()
-    return v.mean(0).float(), v.var(0, unbiased=False).float()
+    mean, var = v.mean(0).float(), v.var(0, unbiased=False).float()
+    if running is not None:     # (running_mean, running_var, momentum): updated in place, the variance unbiased
+        rm, rv, m = running
+        n = v.shape[0]
+        rm.mul_(1.0 - m).add_(mean, alpha=m)
+        rv.mul_(1.0 - m).add_(var * (n / max(n - 1, 1)), alpha=m)
+    return mean, var
 
 
 def _bn_apply(x, channels, scale, shift, relu=0, residual=None, groups=None):

@@ -251,6 +251,18 @@ def test_grouped_batchnorm_equals_one_call_per_group(C, shape, counts):
     assert rel_err(gg.cpu().numpy(), gg_ref.cpu().numpy()) <= 2e-5 and rel_err(gb.cpu().numpy(), gb_ref.cpu().numpy()) <= 2e-5
     if pitch > C:
         assert not y[..., C:].any() and not gx[..., C:].any()
+    # running statistics updated by the statistics launch = len(counts) successive momentum updates, unbiased variance
+    rm, rv = torch.randn(C, device=DEV), torch.rand(C, device=DEV) + 0.5
+    want_m, want_v = rm.clone(), rv.clone()
+    versions = (rm._version, rv._version)
+    grad_ops.bn_stats(x, C, groups=groups, running=(rm, rv, 0.1))
+    per_item = x[0].numel() // pitch
+    for g, c in enumerate(counts):
+        ng = c * per_item
+        want_m.mul_(0.9).add_(mean[g], alpha=0.1)
+        want_v.mul_(0.9).add_(var[g] * (ng / (ng - 1)), alpha=0.1)
+    assert torch.allclose(rm, want_m, rtol=1e-6, atol=1e-7) and torch.allclose(rv, want_v, rtol=1e-6, atol=1e-7)
+    assert rm._version > versions[0] and rv._version > versions[1]     # caches keyed on the buffers' versions notice
 
 
 def test_basic3d_block_training_step_matches_reference_gradient(golden):
