@@ -83,8 +83,14 @@ if a.stalls:
         pool = net.encoder_decoder.encoder_pool1.forward_cl(h2, 32)
         e_a, e_b, e_s = net.encoder_decoder.encoder_res1._packed()    # 32 -> 64, 64 -> 64 at 32^3
         h3 = e_a(pool)
+        h4 = e_b(h3, residual=h3)
+        pool2 = net.encoder_decoder.encoder_pool2.forward_cl(h4, 64)
+        f_a, f_b, f_s = net.encoder_decoder.encoder_res2._packed()    # 64 -> 128, 128 -> 128 at 16^3
+        h5 = f_a(pool2)
     counters("7^3 15->16 stem", lambda: net.front_layers[0].forward_cl(xs))
     counters("3^3 16->32", lambda: c16(h1))
     counters("3^3 32->32 +res", lambda: c32b(h2, residual=h2))
     counters("3^3 32->64 @32^3", lambda: e_a(pool))
     counters("3^3 64->64 +res @32^3", lambda: e_b(h3, residual=h3))
+    counters("3^3 64->128 @16^3", lambda: f_a(pool2))
+    counters("3^3 128->128 +res @16^3", lambda: f_b(h5, residual=h5))

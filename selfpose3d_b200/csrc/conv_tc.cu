@@ -1183,7 +1183,9 @@ int conv_tc(const sp3d_conv_args* a, cudaStream_t st) {
   SP3D_TC_CASE(3, 3, 64, 32, 4, 9, 2, 2, 2, 128, 2)
   SP3D_TC_CASE(3, 3, 64, 64, 4, 3, 3, 2, 2, 64, 2)
   SP3D_TC_CASE(3, 3, 128, 64, 2, 1, 3, 2, 2, 64, 1)
-  SP3D_TC_CASE_P(3, 3, 128, 128, 2, 1, 2, 2, 2, 32, 1, 1, 1)
+  // (one halo buffer handed over per x-slice leaves room for a 7-stage weight ring: with 2 stages beside two halo
+  //  buffers the MMA warps waited 42 % of their time on weights, profiles/r02_conv_stalls_v3.log)
+  SP3D_TC_CASE_P(3, 3, 128, 128, 2, 1, 7, 1, 2, 32, 1, 1, 1)
   // adjoint shapes of the training path's input gradients (3^3 32 -> 16 and 64 -> 32: dgrad of 16 -> 32 / 32 -> 64)
   SP3D_TC_CASE(3, 3, 64, 16, 4, 9, 2, 2, 2, 128, 2)
   SP3D_TC_CASE(3, 3, 128, 32, 2, 1, 3, 2, 2, 64, 1)
@@ -1211,6 +1213,7 @@ int conv_tc(const sp3d_conv_args* a, cudaStream_t st) {
   // (weight rings sized from the in-kernel wait counters, profiles/r02_conv_stalls.log)
   SP3D_TC_CASE_P(3, 3, 128, 64, 2, 1, 6, 1, 2, 64, 1, 1, 2)
   SP3D_TC_CASE_P(3, 3, 128, 64, 2, 4, 3, 1, 2, 128, 1, 2, 2)
+  // (16 -> 32 keeps two halo buffers: one sliced buffer + a 6-stage ring measured 4 % slower, halo wait 2 -> 13 %)
   SP3D_TC_CASE_P(3, 3, 64, 64, 2, 4, 4, 2, 2, 128, 2, 2, 2)
 #undef SP3D_TC_CASE
 #undef SP3D_TC_CASE_F
