@@ -888,8 +888,8 @@ __global__ void softargmax_merge_kernel(const sp3d_softargmax_args a, int splits
 static unsigned long long* g_conv_prof = nullptr;
 void set_conv_profile(void* dev) { g_conv_prof = static_cast<unsigned long long*>(dev); }
 // CTA-pair weight sharing for the large 3^3 / 7^3 launches.  Off by default: bit-identical results and, measured on B200
-// (profiles/r02_cta_pair_ab.log), the same step time -- the weight waits of the MMA warps are refill LATENCY of the ring,
-// not L2 bandwidth, so halving the L2 reads buys nothing.  Kept behind the switch as the measured experiment.
+// (profiles/r02_cta_pair_ab.log), the same step time -- every SM still takes in its full weight stream, so halving the L2
+// reads buys nothing (the limit is the SM-side ingest).  Kept behind the switch as the measured experiment.
 static int g_conv_pair = 0;
 void set_conv_pair(int on) { g_conv_pair = on; }
 
