@@ -125,13 +125,17 @@ struct TcCfg {
   // Single-halo-buffer kernels with taps along x load and release the halo PER X-SLICE: slice d is last read by the taps
   // with dx = d, so the next brick's slice d streams in while the taps dx > d still run (the wait on a monolithic
   // single buffer was 5 - 22 % of the MMA warps' time).  Slices are padded to 1024 bytes (swizzle atom alignment).
-  // (3^3 kernels only: for the 7^3 stem the ten extra boxes per fill cost more weight-stream stalls than the 4.7 % halo
+  // (3^3 kernels; for the F = 2 7^3 stem the ten extra boxes per fill cost more weight-stream stalls than the 4.7 % halo
   // wait they remove -- 22.9 against 22.5 Mclk per CTA, profiles/r02_conv_stalls*.log)
-  static constexpr bool kSliced = HB == 1 && KSX > 1 && KSX <= 3;
+  // The slices live in a RING of kSlots slots addressed by a running slice counter: where all HX slices of a brick fit,
+  // kSlots = HX (every slice has its own slot); the F = 4 stem (HX = 10 slices of 28 KB) keeps TX + 1 -- the TX slices the
+  // current x tap reads plus the one the next tap adds -- which is what makes a 4-fold z-fold fit in shared memory.
+  static constexpr bool kSliced = HB == 1 && KSX > 1 && (KSX <= 3 || F == 4);
   static constexpr int kSliceBytes = HY * HZ * RB;
   static constexpr int kSliceStride = kSliced ? (kSliceBytes + 1023) / 1024 * 1024 : kSliceBytes;
-  static constexpr int kHBar = kSliced ? HX : HB;      // halo barriers (full / empty each)
-  static constexpr int kHaloStride = kSliced ? HX * kSliceStride : (kHaloBytes + 1023) / 1024 * 1024;
+  static constexpr int kSlots = !kSliced ? HB : (HX * kSliceStride > 160 * 1024 ? TX + 1 : HX);
+  static constexpr int kHBar = kSlots;                 // halo barriers (full / empty each)
+  static constexpr int kHaloStride = kSliced ? kSlots * kSliceStride : (kHaloBytes + 1023) / 1024 * 1024;
   static constexpr int kTaps = KSX * KS * KZ;
   static constexpr int kGroups = kTaps / G;             // weight stages consumed per (brick, chunk)
   static constexpr int kTapBytes = N * kPosBytes;
@@ -140,7 +144,8 @@ struct TcCfg {
   static constexpr int kWStride = (kWBytes + 1023) / 1024 * 1024;
   static constexpr int kTapsPerLoad = largest_divisor_le(G, 256 / N);   // TMA box rows <= 256
   static constexpr int kLoads = G / kTapsPerLoad;
-  static constexpr int kSmemBytes = HB * kHaloStride + S * kWStride + EG * SB * kStageBytes + 1024;   // + alignment slack
+  static constexpr int kHaloRegion = kSliced ? kHaloStride : HB * kHaloStride;
+  static constexpr int kSmemBytes = kHaloRegion + S * kWStride + EG * SB * kStageBytes + 1024;   // + alignment slack
   static_assert(kTaps % G == 0, "taps per stage must divide the tap count");
   static constexpr int kGroupsPerDx = (KS * KZ) / G;    // weight stages per x tap (sliced halo: slice hand-over points)
   static_assert(!kSliced || (KS * KZ) % G == 0, "sliced halo: weight stages must not straddle x taps");
@@ -176,7 +181,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* halo = smem;                               // [HB][kHaloStride]
-  uint8_t* wbuf = smem + HB * C::kHaloStride;         // [kWStages][kWStride]
+  uint8_t* wbuf = smem + C::kHaloRegion;              // [kWStages][kWStride]
   uint8_t* stage = wbuf + kWStages * C::kWStride;     // [SB][kStageBytes]
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -255,9 +260,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
         const int plane = (int)((p.block_act >> (4 * kb)) & 15u);
         if constexpr (C::kSliced) {
           for (int xs = 0; xs < C::HX; ++xs) {          // one box per x-slice (the tensor map's box is one slice thick)
-            mbar_wait(&halo_empty[xs], (u & 1) ^ 1);
-            mbar_arrive_expect_tx(&halo_full[xs], C::kSliceBytes);
-            tma_load_5d(halo + xs * C::kSliceStride, &map_in, &halo_full[xs], (c - kb * p.nc_block) * (RB / 2),
+            const uint32_t q = u * C::HX + xs, sl = q % C::kSlots;      // running slice counter -> ring slot
+            mbar_wait(&halo_empty[sl], ((q / C::kSlots) & 1) ^ 1);
+            mbar_arrive_expect_tx(&halo_full[sl], C::kSliceBytes);
+            tma_load_5d(halo + sl * C::kSliceStride, &map_in, &halo_full[sl], (c - kb * p.nc_block) * (RB / 2),
                         z0 * p.istride[2] + p.origin[2], y0 * p.istride[1] + p.origin[1],
                         x0 * p.istride[0] + p.origin[0] + xs, plane * p.n_outer + n);
           }
@@ -322,9 +328,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
       for (int c = 0; c < p.n_chunks; ++c, ++u) {
         const uint32_t buf = C::kSliced ? 0u : u % HB;
         if (prof) t0 = clock64();
+        const uint32_t q0 = u * C::HX;                     // sliced halo: this chunk's first slice in the running count
         if constexpr (C::kSliced) {
 #pragma unroll 1
-          for (int xs = 0; xs < TX; ++xs) mbar_wait(&halo_full[xs], u & 1);     // the slices the taps dx = 0 read
+          for (int xs = 0; xs < TX; ++xs)                  // the slices the taps dx = 0 read
+            mbar_wait(&halo_full[(q0 + xs) % C::kSlots], ((q0 + xs) / C::kSlots) & 1);
         } else {
           mbar_wait(&halo_full[buf], (u / HB) & 1);
         }
@@ -337,6 +345,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
         uint32_t accum = c ? 1u : 0u;                              // first tap of the first chunk overwrites
         int dz = 0, dy = 0;
         uint32_t a_tap = a_lo0 + C::kE0 * kPos16;                  // start of the current tap's shifted window
+        // sliced halo: a_tap is the window's offset INSIDE a slice; soff[t] = ring slot of slice dx + t, in 16-byte units
+        uint32_t soff[TX];
+        if constexpr (C::kSliced) {
+#pragma unroll
+          for (int t = 0; t < TX; ++t) soff[t] = ((q0 + t) % C::kSlots) * (uint32_t)(C::kSliceStride >> 4);
+        }
         // One K chunk.  WIDE (WD = 2 only, K block 0 = activation term x0): MMAs of 2 N columns over the weight rows
         // [w0 | w1]; the other block (x1) adds its N columns onto the upper half, so that the small products
         // x0 w1 + x1 w0 share one accumulator.  Compile-time so that descriptor steps stay immediates in the issue loop.
@@ -348,11 +362,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
           for (int g = 0; g < C::kGroups; ++g, ++w) {
             if constexpr (C::kSliced) {
               if (g > 0 && g % C::kGroupsPerDx == 0) {      // taps move on to dx = g / kGroupsPerDx
-                const int dxn = g / C::kGroupsPerDx;
-                if (elect_one_sync()) mma_commit(&halo_empty[dxn - 1]);        // slice dx - 1 has been read for the last time
+                const uint32_t dxn = (uint32_t)(g / C::kGroupsPerDx);
+                if (elect_one_sync()) mma_commit(&halo_empty[(q0 + dxn - 1) % C::kSlots]);   // slice dx - 1: read for the last time
                 if (prof) t0 = clock64();
-                mbar_wait(&halo_full[dxn + TX - 1], u & 1);                   // the one new slice these taps touch
+                const uint32_t qn = q0 + dxn + TX - 1;                         // the one new slice these taps touch
+                mbar_wait(&halo_full[qn % C::kSlots], (qn / C::kSlots) & 1);
                 if (prof) t_halo += clock64() - t0;
+                a_tap = a_lo0 + C::kE0 * kPos16;
+#pragma unroll
+                for (int t = 0; t < TX; ++t) soff[t] = ((q0 + dxn + t) % C::kSlots) * (uint32_t)(C::kSliceStride >> 4);
               }
             }
             const uint32_t st = w % kWStages;
@@ -361,11 +379,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
             if (prof) t_w += clock64() - t0;
             tc_fence_after();
             uint32_t b_lo = (uint32_t)b_desc0 + (uint32_t)((st * C::kWStride) >> 4);
-#pragma unroll(G % C::KZ == 0 ? C::KZ : (G <= 4 ? G : 1))
+#pragma unroll(G % C::KZ == 0 ? C::KZ : (G <= 5 ? G : 1))
             for (int j = 0; j < G; ++j) {
 #pragma unroll
               for (int t = q; t < TX; t += C::kIssuers) {
-                const uint32_t a_lo = a_tap + (uint32_t)t * (uint32_t)(C::kSliceStride >> 4);
+                const uint32_t a_lo = C::kSliced ? a_tap + soff[t] : a_tap + (uint32_t)t * (uint32_t)(C::kSliceStride >> 4);
                 const uint32_t d_tmem = tmem_base + (accbuf * TX + t) * C::kAcc + d_off;
 #pragma unroll
                 for (int k = 0; k < C::kKSteps; ++k)
@@ -378,7 +396,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
               if (++dz == C::KZ) {
                 dz = 0;
                 a_tap += (uint32_t)C::HZ * kRow16 - (uint32_t)C::KZ * kPos16;
-                if (++dy == KS) {
+                if (++dy == KS) {       // next x tap (sliced halo: re-based at the slice hand-over above)
                   dy = 0;
                   a_tap += (uint32_t)((C::HY - KS) * C::HZ) * kRow16 + (uint32_t)((C::kSliceStride - C::kSliceBytes) >> 4);
                 }
@@ -395,7 +413,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
         if constexpr (C::kSliced) {
 #pragma unroll 1
           for (int xs = KSX - 1; xs < C::HX; ++xs)
-            if (elect_one_sync()) mma_commit(&halo_empty[xs]);
+            if (elect_one_sync()) mma_commit(&halo_empty[(q0 + xs) % C::kSlots]);
         } else {
           if (elect_one_sync()) mma_commit(&halo_empty[buf]);
         }
@@ -1206,6 +1224,9 @@ int conv_tc(const sp3d_conv_args* a, cudaStream_t st) {
   // split_terms 2 (3 term pairs in 2 K blocks, 2 N accumulator columns): the layers whose narrow channel tile leaves the
   // tensor core waiting on the A operand -- 7^3 stems (z-folded, N = 32) and the 3^3 16 -> 32 layer at N = 32
   SP3D_TC_CASE_P(7, 7, 64, 32, 4, 8, 2, 1, 2, 128, 1, 2, 2)
+  // 7^3 stem z-folded by FOUR (rows of 4 positions x 16 channels, N = 4 x 16, 10 windows per (dx, dy)): its 2 N = 128-column
+  // MMAs run at the math floor.  TX = 4 x-slices share a weight stage (one accumulator set), the halo is a 5-slot slice ring
+  SP3D_TC_CASE_W(7, 7, 128, 64, 4, 5, 3, 1, 2, 64, 1, 4, 2)
   SP3D_TC_CASE_W(1, 7, 64, 32, 4, 8, 2, 2, 2, 128, 2, 2, 2)
   SP3D_TC_CASE_W(3, 3, 64, 32, 4, 3, 3, 2, 2, 128, 2, 1, 2)
   // 3^3 64 -> 64 (N = 64): 2 x 64 accumulator columns per x-slice at TX = 2, one halo buffer.  (The z-folded 16 / 32 -> 32

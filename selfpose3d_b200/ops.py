@@ -127,6 +127,8 @@ def float32_conv():
 # The 3-pair split mode evaluates x0 w0 + x0 w1 in one MMA of twice the columns where the kernel is instantiated for
 # the layer (include/sp3d.h, split_terms 2); SP3D_WIDE_SPLIT=0 switches that off (A/B measurements).
 _WIDE_SPLIT = os.environ.get("SP3D_WIDE_SPLIT", "1") != "0"
+# SP3D_ZFOLD4=0 keeps the 7^3 stem on the 2-fold z-fold kernel (A/B measurements of the 4-fold one).
+_ZFOLD4 = os.environ.get("SP3D_ZFOLD4", "1") != "0"
 
 
 def use_split():
@@ -460,7 +462,7 @@ def _tc_finish(full, terms):
 # instantiation in csrc/conv_tc.cu (the SP3D_TC_CASE list; tests/test_host_cpu.py keeps the two in step)
 # instantiations of the 2-K-block form of the 3-pair split mode (split_terms 2: accumulators of 2 N columns)
 TC_WIDE_CASES = frozenset({(7, 7, 64, 32, 2), (1, 7, 64, 32, 2), (3, 3, 64, 32, 1), (3, 3, 128, 64, 1), (3, 3, 128, 64, 2),
-                           (3, 3, 64, 64, 2)})
+                           (3, 3, 64, 64, 2), (7, 7, 128, 64, 4)})
 TC_CASES = frozenset({
     (7, 7, 32, 16, 1), (7, 7, 64, 32, 2), (3, 3, 64, 64, 2), (1, 7, 64, 32, 2), (3, 3, 128, 64, 2), (3, 3, 32, 32, 1),
     (3, 3, 64, 32, 1), (3, 3, 64, 64, 1), (3, 3, 128, 64, 1), (3, 3, 128, 128, 1), (3, 3, 64, 16, 1), (3, 3, 128, 32, 1),
@@ -851,11 +853,21 @@ class PackedConv:
             return self.cin in (16, 32) and self.cout == 32 and out_pitch == 32 and w_extent % 16 == 0
         return False
 
-    def _tc_pack_zfold(self, terms=0):
+    def _zfold_factor(self, w_extent, wide_ok):
+        """Positions per GEMM row of a z-folded launch: 4 for the 7^3 stem in the 2-K-block split form where the row count
+        still fills the 8-row bricks (its N = 4 x 16 kernel exists in that form only, csrc/conv_tc.cu), else 2."""
+        if (wide_ok and self.k == [7, 7, 7] and w_extent % 32 == 0 and _ZFOLD4
+                and tc_case(self.k, 16, 64, 4) in TC_WIDE_CASES):
+            return 4
+        return self.ZFOLD
+
+    def _tc_pack_zfold(self, terms=0, F=None):
         """``[1, (K blocks,) 1, kd*kh*(k+F-1), F*cout_p, cin_p]``: per (kd, kh) the k+F-1 windows e, rows (ro, co),
         tap kw = e - ro (zero rows where that falls outside the kernel)."""
+        F = self.ZFOLD if F is None else int(F)
+
         def build():
-            F, k = self.ZFOLD, self.k[2]
+            k = self.k[2]
             cin_p, cout_p = round_up(self.cin, 16), round_up(self.cout, 16)
             w5 = self._subs[0]                                     # [Cout, Cin, kd, kh, kw]
             full = torch.zeros(self.k[0], self.k[1], k + F - 1, F, cout_p, cin_p, device=w5.device, dtype=torch.float32)
@@ -865,7 +877,7 @@ class PackedConv:
                     if 0 <= kw < k:
                         full[:, :, e, ro, :self.cout, :self.cin] = w5[:, :, :, :, kw].permute(2, 3, 0, 1)
             return _tc_finish(full.reshape(1, 1, -1, F * cout_p, cin_p), terms)
-        return self._tc_cached("zfold", terms, build)
+        return self._tc_cached("zfold%d" % F, terms, build)
 
     def _tc_stack_ok(self, w_extent, out_pitch):
         """The root net's 1 -> 16 channel 7^3 stem: x taps stacked into channels (1 x 7 x 7 over 7 tap channels)."""
@@ -912,7 +924,8 @@ class PackedConv:
         if with_residual is False and self._tc_stack_ok(w_extent, out_pitch):
             return [tc_case([1, 7, 7], 16, 16 * self.ZFOLD, self.ZFOLD)]
         if not self.transposed and cin_tc == round_up(self.cin, 16) and self._tc_zfold_ok(w_extent, out_pitch):
-            return [tc_case(self.k, cin_tc, out_pitch * self.ZFOLD, self.ZFOLD)]
+            F = self._zfold_factor(w_extent, _WIDE_SPLIT and _F32_CONV == "bf16x3" and volume_dtype() == torch.float32)
+            return [tc_case(self.k, cin_tc, out_pitch * F, F)]
         if not self.transposed:
             return [tc_case(self.k, cin_tc, n)]
         if self._tc_fused_ok(out_pitch, out_dtype):
@@ -921,7 +934,8 @@ class PackedConv:
 
     def tc_available(self, w_extent, out_pitch, out_dtype, with_residual):
         """``tc_supported()`` and every launch of the plan has a compiled kernel instantiation."""
-        return self.tc_supported() and all(c in TC_CASES for c in self.tc_plan(w_extent, out_pitch, out_dtype, with_residual))
+        return self.tc_supported() and all(c in TC_CASES or (_WIDE_SPLIT and c in TC_WIDE_CASES)     # (wide-only kernels)
+                                           for c in self.tc_plan(w_extent, out_pitch, out_dtype, with_residual))
 
     def _call_tc(self, x, residual, out_pitch, out_dtype, head=None, terms=0, pair_out=False):
         """tcgen05 path.  ``terms`` = 0: ``x`` is bf16 channel-last.  ``terms`` = 3 / 6 (SP3D_CONV_TC_BF16X3): ``x`` is
@@ -1010,10 +1024,11 @@ class PackedConv:
                         self.stride, [0, -3, -3], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu,
                         cin_real=7, cout_pitch_w=16 * self.ZFOLD, zfold=self.ZFOLD, **dict(kw, split_terms=t))
         elif not self.transposed and pitch == round_up(self.cin, 16) and self._tc_zfold_ok(W, out_pitch):
-            t = 2 if wide(tc_case(self.k, pitch, out_pitch * self.ZFOLD, self.ZFOLD)) else terms
-            conv_launch(xk, self._tc_pack_zfold(t), self.scale, self.shift, resk, outk, pitch, self.cout, o, self.k,
+            F = self._zfold_factor(W, terms == 3 and _WIDE_SPLIT and tma_out)
+            t = 2 if wide(tc_case(self.k, pitch, out_pitch * F, F)) else terms
+            conv_launch(xk, self._tc_pack_zfold(t, F), self.scale, self.shift, resk, outk, pitch, self.cout, o, self.k,
                         self.stride, [-p for p in self.padding], [1, 1, 1], [1, 1, 1], [0, 0, 0], self.relu,
-                        cin_real=self.cin, cout_pitch_w=out_pitch * self.ZFOLD, zfold=self.ZFOLD, **dict(kw, split_terms=t))
+                        cin_real=self.cin, cout_pitch_w=out_pitch * F, zfold=F, **dict(kw, split_terms=t))
         elif not self.transposed:
             t = 2 if wide(tc_case(self.k, cin_tc, n)) else terms
             wgt = packs[0] if t == terms else self._tc_pack(2)[0][0]

@@ -334,8 +334,8 @@ def emulate_stack_planes(x, taps, pad):
 
 
 @pytest.mark.parametrize("terms,tol", [(3, 4e-5), (6, 2e-6)])
-@pytest.mark.parametrize("case", ["3d_k3_res", "3d_k3_zfold", "3d_k7_zfold", "3d_k7_stack", "3d_convT_fused", "2d_1x1s2",
-                                  "2d_deconv"])
+@pytest.mark.parametrize("case", ["3d_k3_res", "3d_k3_zfold", "3d_k7_zfold", "3d_k7_zfold4", "3d_k7_stack", "3d_convT_fused",
+                                  "2d_1x1s2", "2d_deconv"])
 def test_split_operand_lowering(monkeypatch, case, terms, tol):
     """float32 activations / weights through the tensor-core packings (plain, z-folded, tap-stacked, fused transposed,
     per-phase transposed) as sums of bf16 terms: the result must be float32-faithful (3 term pairs: ~2^-16; 6:
@@ -359,13 +359,14 @@ def test_split_operand_lowering(monkeypatch, case, terms, tol):
         pc = ops.PackedConv(conv.float().weight, conv.bias, bn.float(), 1, 1, relu=1)
         assert pc._tc_zfold_ok(16, 32)
         nd, cout = 3, 32
-    elif case in ("3d_k7_zfold", "3d_k7_stack"):
-        cin = 15 if case == "3d_k7_zfold" else 1
+    elif case in ("3d_k7_zfold", "3d_k7_zfold4", "3d_k7_stack"):
+        cin = 1 if case == "3d_k7_stack" else 15
         conv, bn = nn.Conv3d(cin, 16, 7, 1, 3), rand_bn(nn.BatchNorm3d(16))
-        x = torch.rand(1, cin, 4, 8, 6)
+        # (a z extent that is a multiple of 32 takes the 4-fold z-fold in the 3-pair mode: rows of 4 positions)
+        x = torch.rand(1, cin, 4, 8, 32 if case == "3d_k7_zfold4" else 6)
         want = F.relu(bn.double()(conv.double()(x.double())))
         pc = ops.PackedConv(conv.float().weight, conv.bias, bn.float(), 1, 3, relu=1)
-        assert pc._tc_zfold_ok(6, 16) if cin == 15 else pc._tc_stack_ok(6, 16)
+        assert pc._tc_zfold_ok(int(x.shape[-1]), 16) if cin == 15 else pc._tc_stack_ok(6, 16)
         nd, cout = 3, 16
     elif case == "3d_convT_fused":
         ct, bn = nn.ConvTranspose3d(128, 64, 2, 2), rand_bn(nn.BatchNorm3d(64))
@@ -387,14 +388,17 @@ def test_split_operand_lowering(monkeypatch, case, terms, tol):
         pc = ops.PackedConv(ct.float().weight, None, bn.float(), 2, 1, transposed=True, relu=1)
         nd, cout = 2, 256
     assert pc.tc_supported()
-    seen = []
-    monkeypatch.setattr(ops, "conv_launch", lambda *a, **k: (seen.append(k.get("split_terms")), emulate_split_launch(*a, **k))[1])
+    seen, folds = [], []
+    monkeypatch.setattr(ops, "conv_launch", lambda *a, **k: (seen.append(k.get("split_terms")), folds.append(k.get("zfold", 0)),
+                                                             emulate_split_launch(*a, **k))[2])
     got = cf(pc(cl(x), residual=None if res is None else cl(res)), cout, nd).double()
     err = float((got - want).abs().max()) / float(want.abs().max())
     assert err <= tol, err
     # the stems and the z-folded 3^3 layers take the 2-K-block form of the 3-pair mode (split_terms 2: ops.TC_WIDE_CASES)
-    if terms == 3 and case in ("3d_k7_zfold", "3d_k7_stack", "3d_k3_zfold"):
+    if terms == 3 and case in ("3d_k7_zfold", "3d_k7_zfold4", "3d_k7_stack", "3d_k3_zfold"):
         assert seen == [2], seen
+        if case.startswith("3d_k7_zfold"):
+            assert folds == [4 if case == "3d_k7_zfold4" else 2], folds
     else:
         assert all(t == terms for t in seen), seen
 

@@ -64,7 +64,9 @@ def test_split_merge_roundtrip(C):
     assert not p.planes[..., C:].any()
 
 
+# (z extents that are multiples of 32 take the 4-fold z-folded stem kernel with its 5-slot halo slice ring)
 CONV_CASES = [(7, 15, 16, (6, 20, 12), False), (7, 1, 16, (6, 20, 12), False), (7, 15, 16, (5, 17, 34), False),
+              (7, 15, 16, (6, 20, 32), False), (7, 15, 16, (9, 18, 64), False), (7, 15, 16, (13, 35, 32), False),
               (3, 16, 32, (5, 17, 32), True), (3, 32, 32, (6, 20, 16), True), (3, 32, 32, (6, 20, 12), True),
               (3, 32, 64, (6, 20, 12), True), (3, 64, 64, (6, 20, 12), True), (3, 64, 128, (6, 20, 12), False),
               (3, 128, 128, (6, 20, 12), True), (1, 16, 32, (6, 20, 12), False), (1, 32, 64, (6, 20, 12), False),
