@@ -1226,7 +1226,7 @@ int conv_tc(const sp3d_conv_args* a, cudaStream_t st) {
   SP3D_TC_CASE_P(7, 7, 64, 32, 4, 8, 2, 1, 2, 128, 1, 2, 2)
   // 7^3 stem z-folded by FOUR (rows of 4 positions x 16 channels, N = 4 x 16, 10 windows per (dx, dy)): its 2 N = 128-column
   // MMAs run at the math floor.  TX = 4 x-slices share a weight stage (one accumulator set), the halo is a 5-slot slice ring
-  SP3D_TC_CASE_W(7, 7, 128, 64, 4, 5, 3, 1, 2, 64, 1, 4, 2)
+  SP3D_TC_CASE_W(7, 7, 128, 64, 4, 5, 3, 1, 2, 32, 2, 4, 2)
   SP3D_TC_CASE_W(1, 7, 64, 32, 4, 8, 2, 2, 2, 128, 2, 2, 2)
   SP3D_TC_CASE_W(3, 3, 64, 32, 4, 3, 3, 2, 2, 128, 2, 1, 2)
   // 3^3 64 -> 64 (N = 64): 2 x 64 accumulator columns per x-slice at TX = 2, one halo buffer.  (The z-folded 16 / 32 -> 32
