@@ -47,14 +47,14 @@ HEATMAP_SIZE = [72, 96]
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-# (profiles/r01_ncu_*_summary.csv, profiles/r02b_ncu_*_summary.csv), keyed by the launch's layer string; refreshed by hand with the captures
+# (profiles/r01_ncu_*_summary.csv, profiles/r02b_ncu_*_summary.csv, profiles/r02c_ncu_stem_*), keyed by the launch's layer string; refreshed by hand with the captures
 NCU_EVIDENCE = {
     # float32-faithful mode, 7^3 stem over 80 cubes: 2 bf16 term planes in (2 x 671 MB) + 2 planes out (2 x 671 MB)
-    # algorithmic; measured 1.3466 GB read + 1.3055 GB written
+    # algorithmic; measured 1.3497 GB read + 1.2976 GB written
     "conv algo2 k7 15->16 @80x64x64x64": {
-        "dram_bytes_per_launch": 1.346636e9 + 1.305537e9,
-        "source": "profiles/r02b_ncu_stem_80cubes_summary.csv (conv_tc_kernel<7,7,64,32,4,8,2,1,2,128,1,F=2,WD=2>, ncu --set "
-                  "full: sm__pipe_tensor_cycles_active 46.2 %)"},
+        "dram_bytes_per_launch": 1.349722e9 + 1.297612e9,
+        "source": "profiles/r02c_ncu_stem_80cubes_summary.csv (conv_tc_kernel<7,7,128,64,4,5,3,1,2,32,2,F=4,WD=2>, ncu --set "
+                  "full: sm__pipe_tensor_cycles_active 60.4 %)"},
     "conv algo1 k7 15->16 @80x64x64x64": {
         "dram_bytes_per_launch": 672.02e6 + 634.73e6,   # bf16 throughput mode: 671 MB bf16 cubes in + 671 MB out
         "source": "profiles/r01_ncu_conv_pose_v11_summary.csv (conv_tc_kernel<7,7,64,32,...,F=2>, ncu --set full)"},
