@@ -17,9 +17,10 @@ from selfpose3d_b200.models import cuboid_proposal_net  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=4)
 ap.add_argument("--root-channel", action="store_true", help="ROOTNET_ROOTHM: only the root joint's map (C = 1)")
+ap.add_argument("--mode", default="f32x3", choices=["f32x3", "bf16"], help="default (float32-faithful) or bf16 throughput mode")
 a = ap.parse_args()
 dev = "cuda:0"
-ops.set_volume_dtype(torch.bfloat16)
+ops.set_volume_dtype(torch.bfloat16 if a.mode == "bf16" else torch.float32)
 cfg = default_config()
 cfg.NETWORK.IMAGE_SIZE, cfg.NETWORK.HEATMAP_SIZE = [960, 512], [240, 128]
 cfg.NETWORK.ROOTNET_ROOTHM = bool(a.root_channel)
@@ -40,6 +41,18 @@ for _ in range(n):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
+# the same forward as ONE CUDA-graph launch (selfpose3d_b200/graphs.py): the host side of the ~40 launches disappears
+from selfpose3d_b200 import graphs  # noqa: E402
+graphed = graphs.graphed_proposal_net(net, hms, meta)
+for _ in range(3):
+    graphed(*hms)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(n):
+    graphed(*hms)
+e1.record()
+torch.cuda.synchronize()
+ms_graph = e0.elapsed_time(e1) / n
 profiler.enable()
 net(hms, meta)
 torch.cuda.synchronize()
@@ -47,8 +60,8 @@ profiler.disable()
 k = profiler.summary()
 C = 1 if a.root_channel else J
 alg = B * (V * C * 128 * 240 * 4 + C * 80 * 80 * 20 * 4)
-print("config 2 (B=%d, C=%d): %.3f ms per batch = %.0f frames/s; kernels: %s" %
-      (B, C, ms, B / ms * 1e3, {kk: round(v["ms"], 3) for kk, v in k.items()}))
+print("config 2 (B=%d, C=%d): %.3f ms per batch = %.0f frames/s eager, %.3f ms = %.0f frames/s as one CUDA graph; kernels: %s" %
+      (B, C, ms, B / ms * 1e3, ms_graph, B / ms_graph * 1e3, {kk: round(v["ms"], 3) for kk, v in k.items()}))
 unp = k.get("unproject")
 if unp:
     print("un-projection: %.1f us for %d algorithmic bytes = %.0f GB/s" % (unp["ms"] * 1e3, alg, alg / unp["ms"] * 1e-6))

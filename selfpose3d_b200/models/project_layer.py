@@ -25,6 +25,9 @@ def _common_strides(heatmaps):
     return hm, hm[0].stride()
 
 
+_CENTER_CACHE = {}
+
+
 class ProjectLayer(nn.Module):
     def __init__(self, cfg):
         super().__init__()
@@ -47,7 +50,14 @@ class ProjectLayer(nn.Module):
         if isinstance(grid_center, torch.Tensor):
             gc = grid_center.to(device=device, dtype=torch.float32)
         else:
-            gc = torch.as_tensor(np.asarray(grid_center, dtype=np.float32), device=device)
+            # configuration constants: uploaded once per device (also keeps the call capturable in a CUDA graph)
+            arr = np.asarray(grid_center, dtype=np.float32)
+            key = (arr.shape, arr.tobytes(), str(device))
+            gc = _CENTER_CACHE.get(key)
+            if gc is None:
+                if len(_CENTER_CACHE) > 64:
+                    _CENTER_CACHE.clear()
+                gc = _CENTER_CACHE[key] = torch.as_tensor(arr, device=device)
         if gc.dim() == 1:
             gc = gc[None]
         check = gc.shape[1] != 3                      # reference :54 -- rows with [3] < 0 are skipped

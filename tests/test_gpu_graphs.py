@@ -1,0 +1,50 @@
+"""GPU: CUDA-graph capture of the fixed-shape proposal stage (selfpose3d_b200/graphs.py): replays reproduce the eager
+launches bit for bit, for new heat-map contents in the captured buffers."""
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+from selfpose3d_b200 import graphs, ops, synthetic  # noqa: E402
+from selfpose3d_b200.config import default_config  # noqa: E402
+from selfpose3d_b200.models import cuboid_proposal_net  # noqa: E402
+
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+def test_graphed_proposal_net_equals_eager(mode):
+    prev_dtype, prev_conv = ops.volume_dtype(), ops.float32_conv()
+    try:
+        ops.set_volume_dtype(torch.bfloat16 if mode == "bf16" else torch.float32)
+        if mode != "bf16":
+            ops.set_float32_conv(mode)
+        cfg = default_config()
+        cfg.NETWORK.NUM_JOINTS = 4
+        cfg.NETWORK.IMAGE_SIZE, cfg.NETWORK.HEATMAP_SIZE = [96, 128], [24, 32]
+        cfg.MULTI_PERSON.INITIAL_CUBE_SIZE = [24, 24, 8]
+        cfg.MULTI_PERSON.MAX_PEOPLE_NUM = 3
+        cfg.MULTI_PERSON.THRESHOLD = -1.0
+        cfg.NETWORK.ROOTNET_ROOTHM = False
+        net = cuboid_proposal_net.CuboidProposalNet(cfg)
+        net.load_state_dict(synthetic.trained_like_state_dict(net, seed=2), strict=True)
+        net = net.to(DEV).eval()
+        B, V = 2, 5
+        meta = synthetic.make_meta(synthetic.ring_cameras(V, seed=0), B, (96, 128))
+        g = torch.Generator().manual_seed(3)
+        sets = [[torch.rand(B, 4, 32, 24, generator=g).to(DEV) for _ in range(V)] for _ in range(3)]
+        graphed = graphs.graphed_proposal_net(net, sets[0], meta)
+        before = ops._lib.launch_count
+        for hms in sets:
+            root_g, gc_g = [t.clone() for t in graphed(*hms)]
+            with torch.no_grad():
+                root_e, gc_e = net(hms, meta)
+            assert torch.equal(root_g, root_e) and torch.equal(gc_g, gc_e)
+        # (the replays launched nothing through the C ABI: only the three eager forwards did)
+        with torch.no_grad():
+            net(sets[0], meta)
+        per_eager = ops._lib.launch_count - before
+        assert per_eager % 4 == 0 and per_eager > 0
+    finally:
+        ops.set_volume_dtype(prev_dtype)
+        ops.set_float32_conv(prev_conv)
