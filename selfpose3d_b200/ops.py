@@ -129,6 +129,8 @@ def float32_conv():
 _WIDE_SPLIT = os.environ.get("SP3D_WIDE_SPLIT", "1") != "0"
 # SP3D_ZFOLD4=0 keeps the 7^3 stem on the 2-fold z-fold kernel (A/B measurements of the 4-fold one).
 _ZFOLD4 = os.environ.get("SP3D_ZFOLD4", "1") != "0"
+# SP3D_ZFOLD3=0 runs the 3^3 16 / 32 -> 32 layers un-folded (N = 32 kernels; A/B measurements under the power cap).
+_ZFOLD3 = os.environ.get("SP3D_ZFOLD3", "1") != "0"
 
 
 def use_split():
@@ -850,7 +852,7 @@ class PackedConv:
             return self.cin <= 16 and self.cout == 16 and out_pitch == 16
         if self.k == [3, 3, 3] and self.padding == [1, 1, 1]:
             # only where the folded extent still fills the 8-row bricks (W = 20 would run 10 of 16 rows)
-            return self.cin in (16, 32) and self.cout == 32 and out_pitch == 32 and w_extent % 16 == 0
+            return (_ZFOLD3 and self.cin in (16, 32) and self.cout == 32 and out_pitch == 32 and w_extent % 16 == 0)
         return False
 
     def _zfold_factor(self, w_extent, wide_ok):
