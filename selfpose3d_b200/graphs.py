@@ -25,6 +25,7 @@ class GraphedCall:
         if not example_inputs or not all(isinstance(t, torch.Tensor) and t.is_cuda for t in example_inputs):
             raise ValueError("GraphedCall captures functions of CUDA tensors")
         self._inputs = [t.clone() for t in example_inputs]
+        self._fn = fn       # the graph reads every tensor fn closes over (camera tables, ...) by ADDRESS: keep them alive
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():      # warm-up off the default stream: lazy one-time work (function
