@@ -18,10 +18,14 @@ from .utils.transforms import get_affine_transform
 _DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}
 
 
-def _stream():
-    """Raw handle of torch's current CUDA stream on the current device (the stream every launch goes to).
-    ``torch.cuda.current_stream().cuda_stream`` costs ~17 us of Python per call -- as much as a small launch."""
-    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+if hasattr(torch._C, "_cuda_getCurrentRawStream") and hasattr(torch._C, "_cuda_getDevice"):
+    def _stream():
+        """Raw handle of torch's current CUDA stream on the current device (the stream every launch goes to).
+        ``torch.cuda.current_stream().cuda_stream`` costs ~17 us of Python per call -- as much as a small launch."""
+        return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+else:       # (other torch builds: the public, slower route)
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
 
 
 def _require_cuda(*tensors):
