@@ -286,22 +286,6 @@ class BnGroups:
         ids = [g for g, c in enumerate(self.counts) for _ in range(c)]
         self.item_group = torch.tensor(ids, dtype=torch.int32).to(device)
         self.group_items = torch.tensor(self.counts, dtype=torch.int32).to(device)
-        self._weights = {}
-
-    def momentum_weights(self, momentum, positions_per_item):
-        """``(w [G], unbias [G], keep)``: G successive running-average updates with ``momentum`` equal
-        ``r <- keep * r + w @ stats``; ``unbias[g] = n_g / (n_g - 1)`` turns the biased batch variance of group ``g``
-        (``n_g`` positions) into the unbiased one the running variance accumulates."""
-        key = (float(momentum), int(positions_per_item))
-        hit = self._weights.get(key)
-        if hit is None:
-            G, m = self.n_groups, float(momentum)
-            w = torch.tensor([m * (1.0 - m) ** (G - 1 - g) for g in range(G)], dtype=torch.float32)
-            n = [c * int(positions_per_item) for c in self.counts]
-            unbias = torch.tensor([ng / max(ng - 1, 1) for ng in n], dtype=torch.float32)
-            dev = self.item_group.device
-            hit = self._weights[key] = (w.to(dev), unbias.to(dev), (1.0 - m) ** G)
-        return hit
 
     def fill(self, a, x, with_counts=True):
         if int(x.shape[0]) != self.n_items:
