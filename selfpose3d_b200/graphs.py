@@ -65,3 +65,11 @@ def graphed_proposal_net(root_net, heatmaps, meta, flip_xcoords=None):
         return root, root_net.proposal_layer(root, None)
 
     return GraphedCall(fn, *[h.contiguous() for h in heatmaps])
+
+
+def graphed_backbone(backbone, images):
+    """``PoseResNet`` (evaluation mode) on a fixed image-batch shape as one CUDA graph: ``g(images) -> heat-maps``
+    (the zero-copy channel-last view ``backbone(images)`` returns; valid until the next call)."""
+    if backbone.training:
+        raise ValueError("graph capture is for the inference path (call .eval())")
+    return GraphedCall(lambda x: backbone(x), images.float().contiguous())

@@ -51,3 +51,27 @@ def test_graphed_proposal_net_equals_eager(mode):
     finally:
         ops.set_volume_dtype(prev_dtype)
         ops.set_float32_conv(prev_conv)
+
+
+def test_graphed_backbone_equals_eager():
+    from selfpose3d_b200.models import pose_resnet
+    cfg = default_config()
+    cfg.NETWORK.NUM_JOINTS = 15
+    cfg.NETWORK.IMAGE_SIZE, cfg.NETWORK.HEATMAP_SIZE = [96, 128], [24, 32]
+    net = pose_resnet.get_pose_net(cfg, is_train=False)
+    net.load_state_dict(synthetic.trained_like_state_dict(net, seed=4), strict=True)
+    net = net.to(DEV).eval()
+    g = torch.Generator().manual_seed(5)
+    batches = [torch.rand(3, 3, 128, 96, generator=g).to(DEV) for _ in range(3)]
+    graphed = graphs.graphed_backbone(net, batches[0])
+    junk = [torch.randn(1 << 18, device=DEV) for _ in range(16)]
+    for x in batches:
+        before = ops._lib.launch_count
+        out = graphed(x)
+        assert ops._lib.launch_count == before
+        got = out.contiguous().clone()
+        with torch.no_grad():
+            want = net(x)
+        assert out.shape == want.shape and out.stride() == want.stride()      # the zero-copy channel-last view
+        assert torch.equal(got, want.contiguous()), float((got - want).abs().max())
+    del junk
