@@ -43,8 +43,11 @@ torch.cuda.synchronize()
 fam = profiler.summary()
 total = sum(v["ms"] for v in fam.values())
 print("mode %s: wall %.1f ms per step, kernel time %.1f ms in %d launches" % (a.mode, wall, total, sum(v["launches"] for v in fam.values())))
+HBM_KINDS = ("bn", "layout", "maxpool", "maxpool_bwd", "elementwise", "softargmax", "softargmax_bwd", "unproject", "unproject_bwd")
 for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
-    print("  %-22s %9.3f ms %6d launches" % (k, v["ms"], v["launches"]))
+    # (work = algorithmic bytes for the streaming kernels, FLOPs for the convolution families)
+    rate = ("%8.0f GB/s" % (v["work"] / max(v["ms"], 1e-9) * 1e-6)) if k in HBM_KINDS else ("%8.1f TFLOP/s" % (v["work"] / max(v["ms"], 1e-9) * 1e-9))
+    print("  %-22s %9.3f ms %6d launches %s" % (k, v["ms"], v["launches"], rate))
 rows = sorted(profiler.detail_summary().items(), key=lambda kv: -kv[1]["ms"])
 for k, v in rows[:25]:
     print("  %-52s %9.3f ms %5d launches %8.1f TFLOP/s" % (k, v["ms"], v["launches"], v["work"] / max(v["ms"], 1e-9) * 1e-9))
