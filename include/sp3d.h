@@ -329,8 +329,9 @@ int sp3d_unproject_bwd(const sp3d_unproject_bwd_args* a, void* stream);
 /* Gradient of sp3d_softargmax3d_fwd with respect to x: dx_v = beta * p_v * sum_d (g_vd - out_d) * grad_out_d,
  * p = softmax(beta * x) (autograd of lib/models/pose_regression_net.py:22-27). */
 typedef struct {
-  sp3d_softargmax_args fwd; /* forward arguments (x float32; fwd.out = the forward RESULT [n_cubes, C, 3];
-                               workspace unused) */
+  sp3d_softargmax_args fwd; /* forward arguments (x float32; fwd.out = the forward RESULT [n_cubes, C, 3]).
+                               fwd.workspace (optional, >= n_cubes * 64 * C * 8 bytes): channel-last volumes (stride_c = 1,
+                               stride_vox a multiple of 4, 16-byte aligned) then take the streaming two-launch form */
   const float* grad_out;    /* [n_cubes, C, 3] */
   float* grad_x;            /* float32, addressed like fwd.x; written (cubes skipped by check_flag get zeros) */
 } sp3d_softargmax_bwd_args;

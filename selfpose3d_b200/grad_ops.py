@@ -66,7 +66,9 @@ def softargmax_bwd(x, strides, n_cubes, channels, cube_size, centers, grid_size,
     a.out = out.data_ptr()
     b.grad_out = grad_out.data_ptr()
     b.grad_x = gx.data_ptr()
-    _lib.call("sp3d_softargmax3d_bwd", b, _stream(), kind="softargmax_bwd",
+    ws = torch.empty(max(a.n_cubes * 64 * a.C * 2, 1), device=x.device, dtype=torch.float32)   # streaming form's partials
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 4
+    _lib.call("sp3d_softargmax3d_bwd", b, _stream(), launches=2, kind="softargmax_bwd",
               work=4 * a.n_cubes * a.C * a.X * a.Y * a.Z * 4)
     return gx
 

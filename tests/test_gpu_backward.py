@@ -108,7 +108,7 @@ def test_unproject_bwd_seeded_many_channels_vs_oracle():
 
 
 # ------------------------------------------------------------------------------------------ soft-argmax
-@pytest.mark.parametrize("shape,C,pitch", [((6, 5, 4), 3, 4), ((16, 12, 20), 15, 16)])
+@pytest.mark.parametrize("shape,C,pitch", [((6, 5, 4), 3, 4), ((16, 12, 20), 15, 16), ((32, 32, 32), 15, 16), ((12, 10, 8), 5, 20)])
 def test_softargmax_bwd_vs_autograd(golden, shape, C, pitch):
     rs = np.random.RandomState(12)
     n = 2
