@@ -13,7 +13,11 @@
 //     is ASSEMBLED BY TMA: rows are (tap, ci) -- 128 / ci taps per tile, each tap one box [ci rows][KB] of the matching
 //     shifted copy at (x + dx, y + dy), out-of-range lines zero-filled by TMA (= the convolution's padding); layers
 //     with more than 128 input channels use one tap x 128 channels per tile, more than 128 output channels go to
-//     grid.z in blocks of 128.  Lines are padded to a multiple of 16 positions (zeros).  B = [dy_hi rows | dy_lo rows].  Per A tile and K step: one MMA of 2 co columns (x_hi * [dy_hi | dy_lo]) and one of
+//     grid.z in blocks of 128.  Lines are padded to a multiple of 16 positions (zeros).  B = [dy_hi rows | dy_lo rows].
+//     NARROW layers (kz * co <= 128: the 7^3 stem with 16 output channels, the 3^3 layers with 32) fold the z taps into N
+//     instead: x stays un-shifted, dy gets one copy per z tap shifted the OTHER way (x[p + tz] dy[p] = x[p'] dy[p' - tz]),
+//     the B tile holds kz * co rows per term and one MMA covers all z taps of a (dx, dy) pair -- 7 times fewer A tiles and
+//     MMAs of 2 * 112 instead of 2 * 16 columns for the stem.  Per A tile and K step: one MMA of 2 co columns (x_hi * [dy_hi | dy_lo]) and one of
 //     co columns (x_lo * dy_hi, onto the upper half) -- the three term pairs of the float32-faithful mode.  Every
 //     (tap-tile) keeps its own TMEM accumulator for the whole launch; tap tiles that do not fit 512 columns go to other
 //     CTAs (grid.y); the K blocks are split over grid.x; results are added into dW with float atomics at the end.
@@ -36,7 +40,7 @@ using namespace tc;
 // src: float32 channel-last [N][SX][SY][SZ][pitch]; a LINE is the z-run of one (n, x, y) of the position grid
 // [N][X][Y][Z], read at src[n, x * st.x + of.x, y * st.y + of.y, z * st.z + of.z] (st = 1, of = 0 for the forward input;
 // the output phase of a transposed convolution for its gradient).  dst: bf16 [2 planes][copies][N][Cp][X*Y][Zp] with
-// copy j holding the line shifted by (j + shift0): dst[.., z] = line[z + j + shift0] (zero outside [0, Z) and in the
+// copy j holding the line shifted by (j * shift_step + shift0): dst[.., z] = line[z + shift] (zero outside [0, Z) and in the
 // padding Z .. Zp).  grid = (line walkers, channel chunks of kPrepChunk); bias: per-channel sums of the lines, one
 // atomic per channel and CTA (dy pass only).
 constexpr int kPrepChunk = 64;
@@ -44,7 +48,7 @@ struct PrepGeom {
   int N, X, Y, Z, Zp;
   int SX, SY, SZ;          // source tensor extents
   int st[3], of[3];        // source position = grid position * st + of
-  int C, Cp, pitch, copies, shift0;
+  int C, Cp, pitch, copies, shift0, shift_step;      // copy j is shifted by j * shift_step + shift0
 };
 __global__ void __launch_bounds__(256) wgrad_prep_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                          const PrepGeom g, float* __restrict__ bias) {
@@ -76,7 +80,7 @@ __global__ void __launch_bounds__(256) wgrad_prep_kernel(const float* __restrict
       __align__(16) __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const int zo = q8 * 8 + q, z = zo + j + g.shift0;
+        const int zo = q8 * 8 + q, z = zo + j * g.shift_step + g.shift0;
         const float v = (zo < g.Z && z >= 0 && z < g.Z) ? tile[z * cs + c] : 0.0f;
         hi[q] = __float2bfloat16_rn(v);
         lo[q] = __float2bfloat16_rn(v - __bfloat162float(hi[q]));
@@ -96,7 +100,8 @@ struct WgradParams {
   int Cr, cb;                    // rows of one tap in an A tile (min(Cp, 128)) / rows of one dy term in the B tile
   int cin, cout;
   int taps_per_tile, ci_tiles, n_tiles, tiles_per_group;   // ci_tiles = Cp / 128 tiles per tap where Cp > 128
-  int copies;                    // = kz: z-shifted copies of x
+  int copies;                    // z-shifted copies of x (kz, or 1 when the z taps are folded into N)
+  int nfold;                     // z taps folded into N: the B tile holds nfold shifted copies of dy per term (else 1)
   int n_kblocks, kb_per_line;    // K blocks = (n, x, y, z piece)
   float* gw;                     // [taps][gw_cin][gw_pitch] float32, added into
   int gw_cin, gw_pitch;
@@ -144,7 +149,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const int group = blockIdx.y;
   const int tile0 = group * p.tiles_per_group;
   const int my_tiles = min(p.tiles_per_group, p.n_tiles - tile0);
-  const int acc_cols = 2 * p.cb;
+  const int cbn = p.nfold * p.cb;                       // columns of one dy term in the B tile / accumulator
+  const int acc_cols = 2 * cbn;
   const int co0 = blockIdx.z * p.cb;                    // first output channel of this CTA
   // tap table of this CTA's tiles: slot s of tile t -> (dz copy, y offset, x offset); taps beyond the kernel get an x
   // offset far outside the tensor (TMA zero-fills the box).  Cp > 128: one tap per tile, ci_tiles tiles per tap.
@@ -178,10 +184,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       const uint32_t bb = sb & 1;
       mbar_wait(&b_empty[bb], ((sb >> 1) & 1) ^ 1);
       if (lane == 0) {
-        mbar_arrive_expect_tx(&b_full[bb], (uint32_t)(2 * p.cb * RB));
+        mbar_arrive_expect_tx(&b_full[bb], (uint32_t)(2 * p.nfold * p.cb * RB));
         uint8_t* bdst = b_buf + bb * kBStride;
-        tma_load_5d(bdst, &map_dy, &b_full[bb], z0, y, x, co0, n);                             // dy_hi rows
-        tma_load_5d(bdst + p.cb * RB, &map_dy, &b_full[bb], z0, y, x, co0, p.N + n);           // dy_lo rows
+        // rows [dy_hi copy 0 .. nfold-1 | dy_lo copy 0 .. nfold-1]; outer index (plane * nfold + copy) * N + n
+        for (int j = 0; j < p.nfold; ++j) {
+          tma_load_5d(bdst + j * p.cb * RB, &map_dy, &b_full[bb], z0, y, x, co0, j * p.N + n);
+          tma_load_5d(bdst + (p.nfold + j) * p.cb * RB, &map_dy, &b_full[bb], z0, y, x, co0, (p.nfold + j) * p.N + n);
+        }
       }
       for (int t = 0; t < my_tiles; ++t, ++sa) {
         const uint32_t st = sa % kWgStages;
@@ -200,8 +209,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-uniform, elect-predicated)
-    const uint32_t idesc_w = make_idesc(kFmtBF16, 128, (uint32_t)(2 * p.cb));
-    const uint32_t idesc_n = make_idesc(kFmtBF16, 128, (uint32_t)p.cb);
+    const uint32_t idesc_w = make_idesc(kFmtBF16, 128, (uint32_t)(2 * cbn));
+    const uint32_t idesc_n = make_idesc(kFmtBF16, 128, (uint32_t)cbn);
     const uint64_t a_desc0 = make_smem_desc(smem_u32(a_buf), 0, 8 * RB, kLayout);
     const uint64_t b_desc0 = make_smem_desc(smem_u32(b_buf), 0, 8 * RB, kLayout);
     uint32_t sa = 0, sb = 0;
@@ -223,7 +232,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           if (elect_one_sync()) {
             // x_hi * [dy_hi | dy_lo] -> 2 co columns; x_lo * dy_hi -> the upper co columns (small products together)
             mma_f16_ss(d, ad_hi + 2 * ks, bd + 2 * ks, idesc_w, (first && ks == 0) ? 0u : 1u);
-            mma_f16_ss(d + (uint32_t)p.cb, ad_lo + 2 * ks, bd + 2 * ks, idesc_n, 1u);
+            mma_f16_ss(d + (uint32_t)cbn, ad_lo + 2 * ks, bd + 2 * ks, idesc_n, 1u);
           }
         }
         if (elect_one_sync()) mma_commit(&a_empty[st]);
@@ -246,17 +255,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       const int tap = (tile / p.ci_tiles) * p.taps_per_tile + row / p.Cr;
       const int ci = (tile % p.ci_tiles) * 128 + row % p.Cr;
       const bool ok = row / p.Cr < p.taps_per_tile && tap < p.taps && ci < p.cin;
-      float* o = p.gw + ((int64_t)tap * p.gw_cin + ci) * p.gw_pitch + co0;
-      for (int c0 = 0; c0 < p.cb; c0 += 16) {
-        uint32_t v0[16], v1[16];
-        tmem_ld_x16(tmem_base + lane_base + (uint32_t)(t * acc_cols + c0), v0);
-        tmem_ld_x16(tmem_base + lane_base + (uint32_t)(t * acc_cols + p.cb + c0), v1);
-        tmem_ld_wait();
-        if (ok) {
+      // folded z taps: the row's tap is the (dx, dy) pair, column block f is z tap f
+      for (int f = 0; f < p.nfold; ++f) {
+        float* o = p.gw + ((int64_t)(tap * p.nfold + f) * p.gw_cin + ci) * p.gw_pitch + co0;
+        for (int c0 = 0; c0 < p.cb; c0 += 16) {
+          uint32_t v0[16], v1[16];
+          tmem_ld_x16(tmem_base + lane_base + (uint32_t)(t * acc_cols + f * p.cb + c0), v0);
+          tmem_ld_x16(tmem_base + lane_base + (uint32_t)(t * acc_cols + cbn + f * p.cb + c0), v1);
+          tmem_ld_wait();
+          if (ok) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float g = __uint_as_float(v0[j]) + __uint_as_float(v1[j]);
-            if (co0 + c0 + j < p.cout && g != 0.0f) atomicAdd(o + c0 + j, g);
+            for (int j = 0; j < 16; ++j) {
+              const float g = __uint_as_float(v0[j]) + __uint_as_float(v1[j]);
+              if (co0 + c0 + j < p.cout && g != 0.0f) atomicAdd(o + c0 + j, g);
+            }
           }
         }
       }
@@ -286,6 +298,7 @@ static EncodeTiledFn wg_encode() {
 
 struct WgShape {
   int Cp, Cr, co16, cb, co_blocks, Zp, KB, taps, taps_per_tile, ci_tiles, n_tiles, tiles_per_group, groups;
+  int nfold;                    // z taps folded into N (narrow layers), else 1; `taps` then counts the (dx, dy) pairs
   int64_t x_elems, dy_elems;    // bf16 elements of the two workspace regions
 };
 
@@ -306,17 +319,19 @@ static int wg_shape(const sp3d_conv_wgrad_tc_args* a, WgShape* s) {
   s->co_blocks = s->co16 / s->cb;
   s->Zp = (a->Z + 15) / 16 * 16;
   s->KB = s->Zp % 64 == 0 ? 64 : (s->Zp % 32 == 0 ? 32 : 16);
-  s->taps = a->ksize[0] * a->ksize[1] * a->ksize[2];
+  // narrow layers: all z taps of a (dx, dy) pair in one MMA (kz * co columns per term; 2 * kz * co <= 256)
+  s->nfold = (a->ksize[2] > 1 && a->ksize[2] * s->co16 <= 128 && s->Cp <= 128) ? a->ksize[2] : 1;
+  s->taps = a->ksize[0] * a->ksize[1] * (s->nfold > 1 ? 1 : a->ksize[2]);
   s->taps_per_tile = 128 / s->Cr;
   s->ci_tiles = s->Cp <= 128 ? 1 : s->Cp / 128;
   s->n_tiles = (s->taps + s->taps_per_tile - 1) / s->taps_per_tile * s->ci_tiles;
-  s->tiles_per_group = 512 / (2 * s->cb);
+  s->tiles_per_group = 512 / (2 * s->nfold * s->cb);
   if (s->tiles_per_group > s->n_tiles) s->tiles_per_group = s->n_tiles;
   s->groups = (s->n_tiles + s->tiles_per_group - 1) / s->tiles_per_group;
   if (s->groups > 65535 || s->co_blocks > 65535) return SP3D_ERR_UNSUPPORTED;
   const int64_t vox = (int64_t)a->N * a->X * a->Y * s->Zp;
-  s->x_elems = 2 * (int64_t)a->ksize[2] * s->Cp * vox;
-  s->dy_elems = 2 * (int64_t)s->co16 * vox;
+  s->x_elems = 2 * (int64_t)(s->nfold > 1 ? 1 : a->ksize[2]) * s->Cp * vox;
+  s->dy_elems = 2 * (int64_t)s->nfold * s->co16 * vox;
   if ((int64_t)a->N * a->X * a->Y > 2147483647LL || 2 * (int64_t)a->ksize[2] * a->N > 2147483647LL) return SP3D_ERR_UNSUPPORTED;
   // the gradient positions p * g_stride + g_off must lie inside grad_out
   const int ge[3] = {a->GX, a->GY, a->GZ}, pe[3] = {a->X, a->Y, a->Z};
@@ -330,10 +345,11 @@ static int wg_launch(const sp3d_conv_wgrad_tc_args* a, const WgShape& s, const C
                      cudaStream_t st) {
   WgradParams p{};
   p.N = a->N; p.X = a->X; p.Y = a->Y; p.Z = s.Zp; p.taps = s.taps;
-  p.kx = a->ksize[0]; p.ky = a->ksize[1]; p.kz = a->ksize[2]; p.ox = a->tap_off[0]; p.oy = a->tap_off[1];
+  p.kx = a->ksize[0]; p.ky = a->ksize[1]; p.kz = s.nfold > 1 ? 1 : a->ksize[2]; p.ox = a->tap_off[0]; p.oy = a->tap_off[1];
+  p.nfold = s.nfold;
   p.Cr = s.Cr; p.cb = s.cb; p.cin = a->cin; p.cout = a->cout;
   p.taps_per_tile = s.taps_per_tile; p.ci_tiles = s.ci_tiles; p.n_tiles = s.n_tiles; p.tiles_per_group = s.tiles_per_group;
-  p.copies = a->ksize[2];
+  p.copies = s.nfold > 1 ? 1 : a->ksize[2];
   p.kb_per_line = s.Zp / KB;
   p.n_kblocks = a->N * a->X * a->Y * p.kb_per_line;
   p.gw = a->grad_weight; p.gw_cin = a->gw_cin; p.gw_pitch = a->gw_pitch;
@@ -391,11 +407,15 @@ extern "C" int sp3d_conv_wgrad_tc(const sp3d_conv_wgrad_tc_args* a, void* stream
   gx.N = a->N; gx.X = a->X; gx.Y = a->Y; gx.Z = a->Z; gx.Zp = s.Zp;
   gx.SX = a->X; gx.SY = a->Y; gx.SZ = a->Z;
   for (int d = 0; d < 3; ++d) { gx.st[d] = 1; gx.of[d] = 0; }
-  gx.C = a->cin; gx.Cp = s.Cp; gx.pitch = a->x_pitch; gx.copies = a->ksize[2]; gx.shift0 = a->tap_off[2];
+  gx.C = a->cin; gx.Cp = s.Cp; gx.pitch = a->x_pitch; gx.shift_step = 1;
+  gx.copies = s.nfold > 1 ? 1 : a->ksize[2];
+  gx.shift0 = s.nfold > 1 ? 0 : a->tap_off[2];
   PrepGeom gd = gx;
   gd.SX = a->GX; gd.SY = a->GY; gd.SZ = a->GZ;
   for (int d = 0; d < 3; ++d) { gd.st[d] = a->g_stride[d]; gd.of[d] = a->g_off[d]; }
-  gd.C = a->cout; gd.Cp = s.co16; gd.pitch = a->g_pitch; gd.copies = 1; gd.shift0 = 0;
+  gd.C = a->cout; gd.Cp = s.co16; gd.pitch = a->g_pitch;
+  // folded z taps: copy j of dy holds dy[z - (tap_off_z + j)], so that x[z] * dy_j[z] = x[p + tap_off_z + j] * dy[p]
+  gd.copies = s.nfold; gd.shift_step = -1; gd.shift0 = s.nfold > 1 ? -a->tap_off[2] : 0;
   const int chunks_x = (s.Cp + kPrepChunk - 1) / kPrepChunk, chunks_d = (s.co16 + kPrepChunk - 1) / kPrepChunk;
   const int walkers_x = std::max(1, std::min(lines, 148 * 8 / chunks_x)), walkers_d = std::max(1, std::min(lines, 148 * 8 / chunks_d));
   wgrad_prep_kernel<<<dim3(walkers_x, chunks_x), 256, 0, st>>>(a->x, xT, gx, nullptr);
@@ -409,7 +429,8 @@ extern "C" int sp3d_conv_wgrad_tc(const sp3d_conv_wgrad_tc_args* a, void* stream
   const CUtensorMapSwizzle sw = s.KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (s.KB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   const cuuint64_t Zp = (cuuint64_t)s.Zp;
   {  // x^T: [2 planes * kz copies * N][Cp][X][Y][Zp] bf16; box = {KB, 1, 1, Cr, 1}
-    cuuint64_t gdim[5] = {Zp, (cuuint64_t)a->Y, (cuuint64_t)a->X, (cuuint64_t)s.Cp, (cuuint64_t)(2 * a->ksize[2] * a->N)};
+    cuuint64_t gdim[5] = {Zp, (cuuint64_t)a->Y, (cuuint64_t)a->X, (cuuint64_t)s.Cp,
+                          (cuuint64_t)(2 * (s.nfold > 1 ? 1 : a->ksize[2]) * a->N)};
     cuuint64_t gstr[4] = {Zp * 2, Zp * a->Y * 2, Zp * a->Y * a->X * 2, Zp * a->Y * a->X * s.Cp * 2};
     cuuint32_t box[5] = {(cuuint32_t)s.KB, 1, 1, (cuuint32_t)s.Cr, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
@@ -418,7 +439,7 @@ extern "C" int sp3d_conv_wgrad_tc(const sp3d_conv_wgrad_tc_args* a, void* stream
       return SP3D_ERR_INVALID_ARG;
   }
   {  // dy^T: [2 planes * N][co16][X][Y][Zp] bf16; box = {KB, 1, 1, cb, 1}
-    cuuint64_t gdim[5] = {Zp, (cuuint64_t)a->Y, (cuuint64_t)a->X, (cuuint64_t)s.co16, (cuuint64_t)(2 * a->N)};
+    cuuint64_t gdim[5] = {Zp, (cuuint64_t)a->Y, (cuuint64_t)a->X, (cuuint64_t)s.co16, (cuuint64_t)(2 * s.nfold * a->N)};
     cuuint64_t gstr[4] = {Zp * 2, Zp * a->Y * 2, Zp * a->Y * a->X * 2, Zp * a->Y * a->X * s.co16 * 2};
     cuuint32_t box[5] = {(cuuint32_t)s.KB, 1, 1, (cuuint32_t)s.cb, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
