@@ -8,6 +8,7 @@ import torch
 import torch.nn.functional as F
 
 from oracle import nets
+from selfpose3d_b200 import autograd as ag
 from selfpose3d_b200 import grad_ops, ops, synthetic
 from selfpose3d_b200.models import v2v_net
 from test_conv_lowering_cpu import emulate_conv_launch
@@ -268,3 +269,23 @@ def test_pose_resnet_training_step_wiring(emulated, monkeypatch):
     bn = net.layer2[0].downsample[1]                   # BatchNorm behind the 1x1 / stride-2 convolution
     assert int(bn.num_batches_tracked) == int(sd0["layer2.0.downsample.1.num_batches_tracked"]) + 1
     assert not torch.equal(bn.running_mean, sd0["layer2.0.downsample.1.running_mean"])
+
+
+def test_grouped_batches_context_and_group_table():
+    """``autograd.grouped_batches`` / ``grad_ops.BnGroups``: the item -> group table, nesting, and the refusal of a batch
+    that does not match the groups (a silent fall-back to whole-batch statistics would change the training result)."""
+    from selfpose3d_b200 import _lib
+    g = grad_ops.BnGroups([2, 1, 3], "cpu")
+    assert g.n_groups == 3 and g.n_items == 6
+    assert g.item_group.tolist() == [0, 0, 1, 2, 2, 2] and g.group_items.tolist() == [2, 1, 3]
+    with pytest.raises(ValueError):
+        grad_ops.BnGroups([2, 0], "cpu")
+    assert ag._active_groups(torch.zeros(4, 1)) is None
+    with ag.grouped_batches([2, 2], "cpu") as outer:
+        assert ag._active_groups(torch.zeros(4, 1)) is outer
+        with ag.grouped_batches([3], "cpu") as inner:          # a single group = plain batch statistics
+            assert inner is None and ag._active_groups(torch.zeros(3, 1)) is None
+        assert ag._active_groups(torch.zeros(4, 1)) is outer
+        with pytest.raises(_lib.Sp3dError):
+            ag._active_groups(torch.zeros(5, 1))
+    assert ag._active_groups(torch.zeros(5, 1)) is None

@@ -454,7 +454,8 @@ def test_tc_plan_predicts_the_launches(monkeypatch):
     monkeypatch.setattr(ops, "split_bf16", emulate_split_bf16)
     monkeypatch.setattr(ops, "stack_x_shifts", lambda x, taps, pad: torch.zeros(tuple(x.shape[:-1]) + (16,), dtype=torch.bfloat16))
     monkeypatch.setattr(ops, "_F32_CONV", "bf16x3")
-    layers = [(nn.Conv3d(15, 16, 7, 1, 3), (4, 8, 6), False), (nn.Conv3d(1, 16, 7, 1, 3), (4, 8, 6), False),
+    layers = [(nn.Conv3d(15, 16, 7, 1, 3), (4, 8, 6), False), (nn.Conv3d(15, 16, 7, 1, 3), (4, 8, 32), False),
+              (nn.Conv3d(1, 16, 7, 1, 3), (4, 8, 6), False),
               (nn.Conv3d(1, 16, 7, 1, 3), (4, 8, 7), False), (nn.Conv3d(16, 32, 3, 1, 1), (4, 4, 16), True),
               (nn.Conv3d(32, 32, 3, 1, 1), (4, 4, 16), True), (nn.Conv3d(32, 32, 3, 1, 1), (4, 4, 20), False),
               (nn.Conv3d(32, 64, 3, 1, 1), (4, 4, 8), False), (nn.Conv3d(64, 64, 3, 1, 1), (4, 4, 8), True),
